@@ -1,0 +1,475 @@
+"""CPU oracle for the AdvMIL G+D hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a *restatement* of the reference algorithm (liupei101/AdvMIL) in plain
+PyTorch-on-CPU functional form.  It is not the product: only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may import it.
+The product path (advmil_b200.*) never imports anything from `oracle/`.
+
+Parity pin: the reference ships no tests and no golden vectors ("parity unpinned" by the
+reference's own tests).  The pin used here is the *live reference itself*:
+`oracle/make_golden.py` imports the reference modules from /root/reference in the build container,
+runs them on seeded inputs and writes `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks
+this restatement against those fixtures (max abs err ~1e-7 in fp32, exact in index work).
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+State dicts use the reference's parameter names so checkpoints interchange.
+
+All functions are differentiable torch code; gradients for parity come from autograd on fp32
+(or fp64 when `dtype=torch.float64` inputs are given).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _drop(v: Tensor, mask: Optional[Tensor], p: float) -> Tensor:
+    """nn.Dropout(p) in train mode with an explicit keep-mask (1 = keep). mask None = eval mode."""
+    if mask is None or p <= 0.0:
+        return v
+    return v * mask.to(v.dtype) / (1.0 - p)
+
+
+def _lin(v: Tensor, sd: SD, name: str) -> Tensor:
+    return F.linear(v, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+# ----------------------------------------------------------------------------------------------
+# G: ABMIL backbone + gated attention + pooling  (model/backbone.py:54-86, backbone_utils.py:11-29)
+# ----------------------------------------------------------------------------------------------
+def gated_attention_scores(h: Tensor, sd: SD, prefix: str, masks=None, p: float = 0.25) -> Tensor:
+    """Attn_Net_Gated.forward (model/backbone_utils.py:24-29): s = (tanh(hWa+ba) * sig(hWb+bb)) wc + bc."""
+    masks = masks or {}
+    a = _drop(torch.tanh(_lin(h, sd, prefix + ".attention_a.0")), masks.get("a"), p)
+    b = _drop(torch.sigmoid(_lin(h, sd, prefix + ".attention_b.0")), masks.get("b"), p)
+    return _lin(a * b, sd, prefix + ".attention_c")  # [N, 1]
+
+
+def abmil_forward(sd: SD, x: Tensor, masks=None, p: float = 0.25, prefix: str = "backbone") -> Dict[str, Tensor]:
+    """ABMIL.forward (model/backbone.py:79-86). x: [N, C] (the reference squeezes [1,N,C]).
+
+    masks: optional dict of keep-masks {'h':[N,h], 'a':[N,h], 'b':[N,h], 'rho':[1,h]} = train mode.
+    Returns h (post-dropout, the tensor that is pooled — quirk A.4#4), s, w, z, H.
+    """
+    masks = masks or {}
+    h = _drop(torch.relu(_lin(x, sd, f"{prefix}.attention_net.0")), masks.get("h"), p)  # backbone.py:67-70
+    s = gated_attention_scores(h, sd, f"{prefix}.attention_net.3", masks, p)              # backbone.py:71
+    w = torch.softmax(s.transpose(1, 0), dim=1)                                            # backbone.py:82-83
+    z = w @ h                                                                              # backbone.py:84
+    H = _drop(torch.relu(_lin(z, sd, f"{prefix}.rho.0")), masks.get("rho"), p)             # backbone.py:73-77,85
+    return {"h": h, "s": s.squeeze(-1), "w": w.squeeze(0), "z": z, "H": H}
+
+
+def deepattmisl_forward(sd: SD, x: Tensor, cluster_id: Tensor, num_clusters: int = 8, masks=None,
+                        p: float = 0.25, prefix: str = "backbone") -> Dict[str, Tensor]:
+    """DeepAttMISL.forward (model/backbone.py:105-123).
+
+    Per cluster c: mean over {n: cid[n]==c} of relu(x_n Wphi^T + bphi) (1x1 conv == linear,
+    backbone.py:98,112-116), zeros for an empty cluster (:114-115); then Linear+ReLU+Dropout,
+    gated attention over the clusters, softmax, weighted sum (:117-122). No rho layer.
+    """
+    masks = masks or {}
+    x = x.reshape(-1, x.shape[-1])
+    cid = cluster_id.reshape(-1)
+    Wphi = sd[f"{prefix}.phis.0.weight"].reshape(sd[f"{prefix}.phis.0.weight"].shape[0], -1)
+    hc = []
+    for c in range(num_clusters):
+        sel = cid == c
+        if int(sel.sum()) == 0:
+            hc.append(torch.zeros(Wphi.shape[0], dtype=x.dtype))
+        else:
+            hc.append(torch.relu(F.linear(x[sel], Wphi, sd[f"{prefix}.phis.0.bias"])).mean(dim=0))
+    hc = torch.stack(hc, dim=0)                                                            # [8, h]
+    g = _drop(torch.relu(_lin(hc, sd, f"{prefix}.attention_net.0")), masks.get("h"), p)
+    s = gated_attention_scores(g, sd, f"{prefix}.attention_net.3", masks, p)
+    w = torch.softmax(s.transpose(1, 0), dim=1)
+    H = w @ g
+    return {"hc": hc, "g": g, "s": s.squeeze(-1), "w": w.squeeze(0), "H": H}
+
+
+def generator_head(sd: SD, H: Tensor, noises: Sequence[Optional[Tensor]], noise_cfg: Sequence[int],
+                   masks=None, p: float = 0.6, out_scale: str = "sigmoid") -> Tensor:
+    """Noise-concat MLP head: Generator.forward (model/GANSurv.py:32-49) over the layers built by
+    make_noise_mlp_layer (model/model_utils.py:116-133): hidden layers Linear+ReLU+Dropout(p),
+    last layer plain Linear; noise of the same width concatenated in front of layers with noise[i]==1.
+    """
+    masks = masks or {}
+    n_layers = len(noise_cfg)
+    for i in range(n_layers):
+        data = torch.cat([H, noises[i]], dim=1) if noise_cfg[i] == 1 else H
+        H = _lin(data, sd, f"MLPs.{i}.0")
+        if i != n_layers - 1:
+            H = _drop(torch.relu(H), masks.get(f"mlp{i}"), p)
+    if out_scale == "sigmoid":
+        return torch.sigmoid(H)
+    if out_scale == "exp":
+        return torch.exp(H)
+    return H
+
+
+def generator_forward(sd: SD, x: Tensor, noises, noise_cfg=(0, 1), masks=None, backbone: str = "abmil",
+                      cluster_id: Optional[Tensor] = None, gen_dropout: float = 0.6,
+                      out_scale: str = "sigmoid") -> Dict[str, Tensor]:
+    """Generator.forward (model/GANSurv.py:30-49). `noises[i]` is the tensor generate_noise would have
+    produced for layer i (utils/func.py:154-164 == torch.rand / torch.randn on the CPU stream)."""
+    if backbone == "cluster":
+        bb = deepattmisl_forward(sd, x, cluster_id, masks=masks)
+    else:
+        bb = abmil_forward(sd, x, masks=masks)
+    pred = generator_head(sd, bb["H"], noises, noise_cfg, masks, gen_dropout, out_scale)
+    bb["pred"] = pred
+    return bb
+
+
+# ----------------------------------------------------------------------------------------------
+# D: region-level instance projection (RLIP)  (GANSurv.py:71-105, model_utils.py:157-210,
+#    backbone_utils.py:31-77,129-168)
+# ----------------------------------------------------------------------------------------------
+def region_of_row(n: np.ndarray, scale: int = 4) -> np.ndarray:
+    """Region id of level-1 row n: sequence2square (model/backbone_utils.py:62-69) views rows
+    16r..16r+15 as region r; this is the inverse of tools/big_to_small_patching.py:40-46,70-72."""
+    return np.asarray(n) // (scale * scale)
+
+
+def region_embed(sd: SD, x: Tensor, prefix: str = "net_pair_one.embedding", eps: float = 1e-5) -> Dict[str, Tensor]:
+    """AVGPoolPatchEmbedding.forward with ksize=1, stride=1, scale=4 (model/backbone_utils.py:158-168):
+    emb[r] = mean_{k<16} relu(LayerNorm_128(x[16r+k] Wc^T + bc)).  x: [N, C], N % 16 == 0 (:65)."""
+    N = x.shape[0]
+    assert N % 16 == 0
+    Wc = sd[f"{prefix}.conv.weight"]
+    Wc = Wc.reshape(Wc.shape[0], -1)
+    y = F.linear(x, Wc, sd[f"{prefix}.conv.bias"])
+    e = torch.relu(F.layer_norm(y, (y.shape[-1],), sd[f"{prefix}.norm.weight"], sd[f"{prefix}.norm.bias"], eps))
+    emb = e.reshape(N // 16, 16, -1).mean(dim=1)
+    return {"y": y, "e": e, "emb": emb}
+
+
+def _eff_mlp(v: Tensor, sd: SD, prefix: str, mask, p: float) -> Tensor:
+    """make_efficient_mlp_layer(dim, False, p) (model/model_utils.py:157-166): Lin(d,d/2) ReLU Drop Lin(d/2,d)."""
+    return _lin(_drop(torch.relu(_lin(v, sd, prefix + ".0")), mask, p), sd, prefix + ".3")
+
+
+def gapool(sd: SD, v: Tensor, prefix: str, masks=None, p: float = 0.25) -> Dict[str, Tensor]:
+    """GAPool.forward (model/backbone_utils.py:47-56) on [R, d] -> [1, d]; pools its *input* v."""
+    masks = masks or {}
+    ga = _drop(torch.tanh(_lin(v, sd, prefix + ".fc1.0")), masks.get("ga"), p)
+    gs = _drop(torch.sigmoid(_lin(v, sd, prefix + ".score.0")), masks.get("gs"), p)
+    rep = _lin(ga * gs, sd, prefix + ".fc2")              # [R,1]
+    attn = torch.softmax(rep.transpose(1, 0), dim=1)      # [1,R]
+    return {"rep": rep.squeeze(-1), "attn": attn.squeeze(0), "out": attn @ v}
+
+
+def embedx_forward(sd: SD, x: Tensor, masks=None, p: float = 0.25, prefix: str = "net_pair_one") -> Dict[str, Tensor]:
+    """EmbedXLayer.forward(x, return_instance=True) (model/model_utils.py:202-210).
+    Returns hx [1,d] and fi [R,d] — NB the *post-fc1* features are the 'instance embeddings' (quirk A.4#2)."""
+    masks = masks or {}
+    re = region_embed(sd, x, prefix + ".embedding")
+    fi = _eff_mlp(re["emb"], sd, prefix + ".fc1", masks.get("fc1"), p)
+    gp = gapool(sd, fi, prefix + ".pool", masks, p)
+    hx = _eff_mlp(gp["out"], sd, prefix + ".fc2", masks.get("fc2"), p)
+    return {"emb": re["emb"], "fi": fi, "attn": gp["attn"], "bag": gp["out"], "hx": hx}
+
+
+def time_embed(sd: SD, t: Tensor, n_layers: int = 2, prefix: str = "net_pair_two") -> Tensor:
+    """make_embedding_y_layer with norm=False, dropout=0 (model/model_utils.py:178-186): (Linear+ReLU) x n."""
+    v = t
+    for i in range(n_layers):
+        v = torch.relu(_lin(v, sd, f"{prefix}.{i}.0"))
+    return v
+
+
+def prjdisc_forward(sd: SD, x: Tensor, t: Tensor, masks=None, inner_product: str = "instance",
+                    prj_path: str = "x", p: float = 0.25) -> Dict[str, Tensor]:
+    """PrjDiscriminator.forward (model/GANSurv.py:89-105). x: [N,C]; t: [1,1]. Returns out [1,1]."""
+    ht = time_embed(sd, t)
+    ex = embedx_forward(sd, x, masks, p)
+    if inner_product == "bag":
+        out = (ht * ex["hx"]).sum(dim=-1, keepdim=True)                    # GANSurv.py:92-94
+    else:
+        out_ins = (ex["fi"].unsqueeze(0) * ht).sum(dim=-1)                 # GANSurv.py:97  [1,R]
+        out = out_ins.mean(dim=-1, keepdim=True)                           # GANSurv.py:98
+    if prj_path == "x":
+        out = out + _lin(ex["hx"], sd, "prj_layer")                        # GANSurv.py:102-104
+    elif prj_path == "y":
+        out = out + _lin(ht, sd, "prj_layer")
+    ex["ht"] = ht
+    ex["out"] = out
+    return ex
+
+
+# ----------------------------------------------------------------------------------------------
+# losses (loss/utils.py)
+# ----------------------------------------------------------------------------------------------
+def real_fake_loss(real: Optional[Tensor], fake: Tensor, which: str = "bce") -> Tensor:
+    """loss/utils.py:182-203, including the non-standard bce: -mean(1 - log(sig(fake)+1e-8)) - mean(log(sig(real)+1e-8))."""
+    fake = fake.reshape(-1)
+    if which == "bce":
+        loss = -torch.mean(1.0 - torch.log(torch.sigmoid(fake) + 1e-8))
+        if real is not None:
+            loss = loss - torch.mean(torch.log(torch.sigmoid(real.reshape(-1)) + 1e-8))
+    elif which == "hinge":
+        loss = torch.relu(1.0 + fake).mean()
+        if real is not None:
+            loss = loss + torch.relu(1.0 - real.reshape(-1)).mean()
+    elif which == "wasserstein":
+        loss = fake.mean()
+        if real is not None:
+            loss = loss - real.reshape(-1).mean()
+    else:
+        raise ValueError(which)
+    return loss
+
+
+def fake_generator_loss(fake: Tensor) -> Tensor:
+    """loss/utils.py:205-208."""
+    return -torch.mean(fake.reshape(-1))
+
+
+def recon_loss(pred_t: Tensor, t: Tensor, e: Tensor, alpha: float = 0.0, gamma: float = 0.0, norm: str = "l1") -> Tensor:
+    """loss/utils.py:21-41: e|p-t| + (1-e) relu(gamma - (p - t)); l2 squares both; alpha re-weights observed part."""
+    p_, t_, e_ = pred_t.reshape(-1), t.reshape(-1), e.reshape(-1)
+    lo = e_ * torch.abs(p_ - t_)
+    lc = (1 - e_) * torch.relu(gamma - (p_ - t_))
+    if norm == "l2":
+        lo, lc = lo * lo, lc * lc
+    return ((1.0 - alpha) * (lo + lc) + alpha * lo).mean()
+
+
+def loss_reg_l1(params: Sequence[Tensor], coef: float):
+    """loss/utils.py:6-14: coef * sum |W| over ALL parameters (biases included); 0.0 if coef <= 1e-8."""
+    if coef is None or coef <= 1e-8:
+        return 0.0
+    return coef * sum(torch.abs(w).sum() for w in params)
+
+
+# ----------------------------------------------------------------------------------------------
+# the adversarial step (model/model_handler.py:349-498) restated over a list of bags
+# ----------------------------------------------------------------------------------------------
+def disc_step_loss(sdG: SD, sdD: SD, bags: List[Tensor], ts: Tensor, es: Tensor, visible: Sequence[bool],
+                   noises: List[Sequence[Optional[Tensor]]], d_masks_real=None, d_masks_fake=None,
+                   which: str = "bce", noise_cfg=(0, 1), exts=None, backbone: str = "abmil") -> Dict[str, Tensor]:
+    """_update_disc (model_handler.py:349-424): D.train / G.eval. Real pair only if e==1 and label visible
+    (:373-377); fake pair uses pred.detach() (:396-401). Loss over all collected pairs (:412).
+    d_masks_*: per-bag dropout-mask dicts for D (None = no dropout, i.e. p treated as eval)."""
+    reals, fakes, preds = [], [], []
+    for i, x in enumerate(bags):
+        if float(es[i]) == 1.0 and visible[i]:
+            mk = None if d_masks_real is None else d_masks_real[i]
+            reals.append(prjdisc_forward(sdD, x, ts[i].reshape(1, 1), mk)["out"].reshape(-1))
+        with torch.no_grad():
+            g = generator_forward(sdG, x, noises[i], noise_cfg, None, backbone,
+                                  None if exts is None else exts[i])
+        pred = g["pred"].detach()
+        preds.append(pred)
+        mk = None if d_masks_fake is None else d_masks_fake[i]
+        fakes.append(prjdisc_forward(sdD, x, pred, mk)["out"].reshape(-1))
+    real = torch.cat(reals) if reals else None
+    fake = torch.cat(fakes)
+    return {"loss": real_fake_loss(real, fake, which), "real": real, "fake": fake, "pred": torch.cat(preds).reshape(-1)}
+
+
+def gen_step_loss(sdG: SD, sdD: SD, bags: List[Tensor], ts: Tensor, es: Tensor, visible: Sequence[bool],
+                  noises, g_masks=None, coef_gan: float = 0.004, coef_l1: float = 1e-5, noise_cfg=(0, 1),
+                  exts=None, backbone: str = "abmil", recon_kw=None) -> Dict[str, Tensor]:
+    """_update_gen (model_handler.py:426-498): D.eval / G.train. total = recon(visible bags) + coef_gan * (-mean f_fake)
+    + coef_l1 * sum|W_G| (:472-485)."""
+    recon_kw = recon_kw or {}
+    preds, fakes = [], []
+    for i, x in enumerate(bags):
+        mk = None if g_masks is None else g_masks[i]
+        g = generator_forward(sdG, x, noises[i], noise_cfg, mk, backbone, None if exts is None else exts[i])
+        preds.append(g["pred"])
+        fakes.append(prjdisc_forward(sdD, x, g["pred"], None)["out"].reshape(-1))
+    fake = torch.cat(fakes)
+    gen_loss = fake_generator_loss(fake)
+    vis = [i for i in range(len(bags)) if visible[i]]
+    if vis:
+        tp = torch.cat([preds[i] for i in vis], dim=0)
+        t_reg = recon_loss(tp, ts[vis], es[vis], **recon_kw)
+    else:
+        t_reg = torch.zeros((), dtype=fake.dtype)
+    total = t_reg if coef_gan == 0.0 else t_reg + coef_gan * gen_loss
+    total = total + loss_reg_l1(list(sdG.values()), coef_l1)
+    return {"loss": total, "gen_loss": gen_loss, "t_reg": t_reg, "fake": fake, "pred": torch.cat(preds).reshape(-1)}
+
+
+def adam_step(params: SD, grads: SD, state: Dict[str, Dict[str, Tensor]], lr: float, step: int,
+              weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+    """torch.optim.Adam as configured by the handler (model_handler.py:104-107; optim/optim_factory.py:25-37,76-77):
+    L2 weight decay (added to the gradient) on tensors with ndim > 1 whose name does not end in '.bias'; none otherwise."""
+    b1, b2 = betas
+    for k, p in params.items():
+        g = grads[k]
+        wd = weight_decay if (p.ndim > 1 and not k.endswith(".bias")) else 0.0
+        if wd:
+            g = g + wd * p
+        st = state.setdefault(k, {"m": torch.zeros_like(p), "v": torch.zeros_like(p)})
+        st["m"].mul_(b1).add_(g, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1 = 1 - b1 ** step
+        bc2 = 1 - b2 ** step
+        denom = (st["v"].sqrt() / math.sqrt(bc2)).add_(eps)
+        p.data.addcdiv_(st["m"], denom, value=-lr / bc1)
+
+
+# ----------------------------------------------------------------------------------------------
+# inference sampling + C-index (model_handler.py:598-643; eval/cindex.py)
+# ----------------------------------------------------------------------------------------------
+def lower_median(samples: Tensor, dim: int = 0) -> Tensor:
+    """torch.median semantics used at model_handler.py:639: for an even count returns the LOWER middle value."""
+    srt, _ = torch.sort(samples, dim=dim)
+    k = (samples.shape[dim] - 1) // 2
+    return srt.select(dim, k)
+
+
+def sample_times(sdG: SD, x: Tensor, noise_list: List[Tensor], noise_cfg=(0, 1)) -> Tensor:
+    """test_model inner loop (model_handler.py:624-636): G in eval mode, one prediction per noise draw. -> [S]"""
+    bb = abmil_forward(sdG, x)
+    out = []
+    for nz in noise_list:
+        noises = [nz if c == 1 else None for c in noise_cfg]
+        out.append(generator_head(sdG, bb["H"], noises, noise_cfg).reshape(-1))
+    return torch.cat(out)
+
+
+def concordance_index(t: np.ndarray, e: np.ndarray, y_pred: np.ndarray, tied_tol: float = 1e-8) -> float:
+    """Harrell's C as the reference computes it: concordance_index(y_true, y_pred) calls
+    concordance_index_censored(e, t, -y_pred) (eval/cindex.py:10-40,106-200).  A pair (i,j) is comparable
+    when t_i < t_j and e_i == 1; it is concordant when risk_i > risk_j (risk = -pred); |risk diff| <= tol is a
+    tie counted 0.5.  Pairs with equal times are never comparable when both had events; if only one of them
+    had the event, the event one is 'i' (eval/cindex.py:82-100)."""
+    t = np.asarray(t, dtype=np.float64).reshape(-1)
+    e = np.asarray(e).reshape(-1).astype(bool)
+    risk = -np.asarray(y_pred, dtype=np.float64).reshape(-1)
+    num = 0.0
+    den = 0.0
+    for i in np.nonzero(e)[0]:
+        comp = (t > t[i]) | ((t == t[i]) & (~e))
+        comp[i] = False
+        n = int(comp.sum())
+        if n == 0:
+            continue
+        d = risk[comp] - risk[i]
+        ties = np.abs(d) <= tied_tol
+        con = (d < 0) & (~ties)
+        num += con.sum() + 0.5 * ties.sum()
+        den += n
+    if den == 0:
+        raise ValueError("no comparable pairs")
+    return float(num / den)
+
+
+# ----------------------------------------------------------------------------------------------
+# level-2 -> level-1 patch index map (tools/big_to_small_patching.py:40-46,59-76)
+# ----------------------------------------------------------------------------------------------
+def region_index_map(coords_l2: np.ndarray, patch_size: int = 256, scale: int = 4) -> np.ndarray:
+    """coords_x5_to_x20: parent k (file order) -> 16 children at rows 16k + 4j + i with coords
+    c_k + (i*psize, j*psize), j outer / i inner (get_scaled_matrix :40-46); output float64 (:60,71-72)."""
+    coords_l2 = np.asarray(coords_l2)
+    M = coords_l2.shape[0]
+    out = np.zeros((M * scale * scale, 2), dtype=np.float64)
+    for k in range(M):
+        for j in range(scale):
+            for i in range(scale):
+                out[k * scale * scale + j * scale + i, 0] = coords_l2[k, 0] + i * patch_size
+                out[k * scale * scale + j * scale + i, 1] = coords_l2[k, 1] + j * patch_size
+    return out
+
+
+def mask_regions_zero(bag: Tensor, keep_regions: np.ndarray, scale: int = 4) -> Tensor:
+    """random_mask_square_instance(..., 'mask_zero') given the kept region ids (utils/func.py:14-40)."""
+    out = torch.zeros_like(bag)
+    s2 = scale * scale
+    for r in np.sort(np.asarray(keep_regions)):
+        out[r * s2:(r + 1) * s2] = bag[r * s2:(r + 1) * s2]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# deterministic synthetic inputs / parameters shared by oracle, goldens, tests and bench
+# ----------------------------------------------------------------------------------------------
+G_SHAPES = lambda C=1024, h=384, o=384: {  # noqa: E731  (ABMIL generator, noise 0-1, hops 1)
+    "MLPs.0.0.weight": (o // 2, o), "MLPs.0.0.bias": (o // 2,),
+    "MLPs.1.0.weight": (1, o), "MLPs.1.0.bias": (1,),
+    "backbone.attention_net.0.weight": (h, C), "backbone.attention_net.0.bias": (h,),
+    "backbone.attention_net.3.attention_a.0.weight": (h, h), "backbone.attention_net.3.attention_a.0.bias": (h,),
+    "backbone.attention_net.3.attention_b.0.weight": (h, h), "backbone.attention_net.3.attention_b.0.bias": (h,),
+    "backbone.attention_net.3.attention_c.weight": (1, h), "backbone.attention_net.3.attention_c.bias": (1,),
+    "backbone.rho.0.weight": (o, h), "backbone.rho.0.bias": (o,),
+}
+
+G_CLUSTER_SHAPES = lambda C=1024, h=384: {  # noqa: E731  DeepAttMISL generator
+    "MLPs.0.0.weight": (h // 2, h), "MLPs.0.0.bias": (h // 2,),
+    "MLPs.1.0.weight": (1, h), "MLPs.1.0.bias": (1,),
+    "backbone.phis.0.weight": (h, C, 1, 1), "backbone.phis.0.bias": (h,),
+    "backbone.attention_net.0.weight": (h, h), "backbone.attention_net.0.bias": (h,),
+    "backbone.attention_net.3.attention_a.0.weight": (h, h), "backbone.attention_net.3.attention_a.0.bias": (h,),
+    "backbone.attention_net.3.attention_b.0.weight": (h, h), "backbone.attention_net.3.attention_b.0.bias": (h,),
+    "backbone.attention_net.3.attention_c.weight": (1, h), "backbone.attention_net.3.attention_c.bias": (1,),
+}
+
+D_SHAPES = lambda C=1024, d=128, ty=(64, 128): {  # noqa: E731
+    "net_pair_one.embedding.conv.weight": (d, C, 1, 1), "net_pair_one.embedding.conv.bias": (d,),
+    "net_pair_one.embedding.norm.weight": (d,), "net_pair_one.embedding.norm.bias": (d,),
+    "net_pair_one.fc1.0.weight": (d // 2, d), "net_pair_one.fc1.0.bias": (d // 2,),
+    "net_pair_one.fc1.3.weight": (d, d // 2), "net_pair_one.fc1.3.bias": (d,),
+    "net_pair_one.pool.fc1.0.weight": (d, d), "net_pair_one.pool.fc1.0.bias": (d,),
+    "net_pair_one.pool.score.0.weight": (d, d), "net_pair_one.pool.score.0.bias": (d,),
+    "net_pair_one.pool.fc2.weight": (1, d), "net_pair_one.pool.fc2.bias": (1,),
+    "net_pair_one.fc2.0.weight": (d // 2, d), "net_pair_one.fc2.0.bias": (d // 2,),
+    "net_pair_one.fc2.3.weight": (d, d // 2), "net_pair_one.fc2.3.bias": (d,),
+    "net_pair_two.0.0.weight": (ty[0], 1), "net_pair_two.0.0.bias": (ty[0],),
+    "net_pair_two.1.0.weight": (ty[1], ty[0]), "net_pair_two.1.0.bias": (ty[1],),
+    "prj_layer.weight": (1, d), "prj_layer.bias": (1,),
+}
+
+
+def synth_state_dict(shapes: Dict[str, tuple], seed: int, dtype=torch.float32) -> SD:
+    """Deterministic parameters independent of torch's RNG/init order: for each tensor (sorted by name)
+    uniform(-b, b) with b = 1/sqrt(fan_in) (weights) or 0.1 (1-D); LayerNorm weight is shifted to ~1."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if len(shp) > 1:
+            fan_in = int(np.prod(shp[1:]))
+            b = 1.0 / math.sqrt(fan_in)
+        else:
+            b = 0.1
+        v = rng.uniform(-b, b, size=shp)
+        if name.endswith("norm.weight"):
+            v = v + 1.0
+        sd[name] = torch.tensor(v, dtype=dtype)
+    return sd
+
+
+def synth_bag(n_rows: int, seed: int, C: int = 1024, nonneg: bool = False, dtype=torch.float32) -> Tensor:
+    """Synthetic bag: randn features (precedent model_stats.py:93) or relu(randn)*0.5."""
+    rng = np.random.default_rng(1000 + seed)
+    v = rng.standard_normal((n_rows, C)).astype(np.float32)
+    if nonneg:
+        v = np.maximum(v, 0) * 0.5
+    return torch.tensor(v, dtype=dtype)
+
+
+def synth_labels(n_bags: int, seed: int, event_rate: float = 0.347):
+    """t ~ U(0,1), e ~ Bernoulli(0.347) (NLST event rate)."""
+    rng = np.random.default_rng(2000 + seed)
+    t = torch.tensor(rng.uniform(0.02, 0.98, size=n_bags), dtype=torch.float32)
+    e = torch.tensor((rng.uniform(size=n_bags) < event_rate).astype(np.float32))
+    return t, e
+
+
+def synth_masks(shape, keep_prob: float, seed: int) -> Tensor:
+    rng = np.random.default_rng(3000 + seed)
+    return torch.tensor((rng.uniform(size=shape) < keep_prob).astype(np.float32))
