@@ -1,0 +1,413 @@
+// C-ABI composites: generator fwd/bwd, discriminator embed/head fwd/bwd, stage-level entry points.
+// Host orchestration only — every kernel lives in gemm_*.cu / seg_kernels.cu / tail_kernels.cu.
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include <vector>
+#include "stages.cuh"
+
+namespace advmil {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+__global__ void scale_offsets_kernel(const int32_t* __restrict__ in, int n, int div, int32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] / div;
+}
+
+static int check_bags(const AdvmilBags* b, int C, bool need16) {
+  ADVMIL_REQUIRE(b && b->x && b->offsets && b->offsets_host, "bags: null pointer");
+  ADVMIL_REQUIRE(b->bags > 0 && b->rows > 0, "bags: empty batch (rows=%d bags=%d)", b->rows, b->bags);
+  ADVMIL_REQUIRE(b->C == C, "bags: feature width %d != model input width %d", b->C, C);
+  ADVMIL_REQUIRE(b->offsets_host[0] == 0 && b->offsets_host[b->bags] == b->rows, "bags: offsets must span [0, rows]");
+  for (int i = 0; i < b->bags; ++i) {
+    int len = b->offsets_host[i + 1] - b->offsets_host[i];
+    ADVMIL_REQUIRE(len > 0, "bags: bag %d is empty", i);
+    if (need16) ADVMIL_REQUIRE(len % 16 == 0, "bags: bag %d has %d rows, not a multiple of 16 (model/backbone_utils.py:65)", i, len);
+  }
+  return ADVMIL_OK;
+}
+
+#define WS_TAKE(var, type, count)                                                        \
+  type* var = ws.take<type>(count);                                                      \
+  if (!var) { set_error("%s: workspace too small (need > %zu bytes)", __func__, ws.cap); return ADVMIL_ERR_WORKSPACE; }
+
+}  // namespace advmil
+
+using namespace advmil;
+
+extern "C" int advmil_abi_version(void) { return ADVMIL_ABI_VERSION; }
+extern "C" const char* advmil_last_error(void) { return g_err; }
+extern "C" size_t advmil_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(AdvmilBags);
+    case 1: return sizeof(AdvmilGenParams);
+    case 2: return sizeof(AdvmilGenGrads);
+    case 3: return sizeof(AdvmilGenActs);
+    case 4: return sizeof(AdvmilDiscParams);
+    case 5: return sizeof(AdvmilDiscGrads);
+    case 6: return sizeof(AdvmilEmbedActs);
+    case 7: return sizeof(AdvmilHeadActs);
+    default: return 0;
+  }
+}
+extern "C" int64_t advmil_launch_count(int reset) {
+  long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+extern "C" int32_t advmil_gate_packed_width(int32_t D) { return gate_width(D); }
+
+// =============================================================================================
+// generator
+// =============================================================================================
+extern "C" size_t advmil_generator_workspace_bytes(const AdvmilGenParams* p, int32_t rows, int32_t bags, int32_t backward) {
+  const size_t h = p->h, C = p->C, o = p->o, hid = p->hid;
+  const size_t abw = gate_width(p->h);
+  size_t f = 0;  // floats
+  f += abw * h + abw + 512;                                   // packed gate weights
+  f += (abw / 128) * (size_t)rows + 256;                      // gate score partials
+  f += seg_pool_ws_floats(rows, bags, (int)h) + 256;
+  if (backward) {
+    f += (size_t)bags * (h + o + hid + 1) + 1024;             // per-bag gradient vectors
+    f += (size_t)rows * abw + (size_t)rows * h + 512;         // dAB, dh_pre
+    f += abw * h + abw + 512;                                 // packed gate weight grads
+    f += align_up((size_t)bags, 64) + (size_t)row_chunks(rows) * (h + 1) + 256;  // pool_gate partials
+    f += max(bwd_weight_ws_floats(rows, (int)abw, (int)h), bwd_weight_ws_floats(rows, (int)h, (int)C)) + 256;
+    f += (size_t)row_chunks(rows) * max(abw, h) + 256;        // colsum partials
+  }
+  return f * sizeof(float) + 64 * 256;
+}
+
+extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* bags, AdvmilGenActs* a, void* stream) {
+  ADVMIL_REQUIRE(p && a, "generator_fwd: null argument");
+  ADVMIL_TRY(check_bags(bags, p->C, false));
+  ADVMIL_REQUIRE(p->h % 4 == 0 && p->C % 4 == 0, "generator_fwd: C=%d and h=%d must be multiples of 4", p->C, p->h);
+  ADVMIL_REQUIRE(a->h && a->s && a->w && a->z && (a->pred || !p->W0), "generator_fwd: missing output buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = bags->rows, nb = bags->bags, h = p->h;
+  const int abw = gate_width(h);
+  Workspace ws(a->workspace, a->workspace_bytes);
+  WS_TAKE(Wp, float, (size_t)abw * h);
+  WS_TAKE(bp, float, abw);
+  WS_TAKE(part, float, (size_t)(abw / 128) * rows);
+  WS_TAKE(poolws, float, seg_pool_ws_floats(rows, nb, h));
+  Drop dh = Drop::make(a->mask_h, a->seed, SITE_H, p->p_backbone, a->train);
+  Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train);
+  Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train);
+  Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train);
+  Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train);
+  if (a->h_eval) ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, st));
+  else ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st));
+  ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
+  ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, a->s, part, a->precision, st));
+  ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st));
+  ADVMIL_TRY(gen_head_fwd(*p, a->z, a->noise0, a->noise1, nb, 1, drho, dmlp0, a->H, a->H1, a->pre, a->pred, st));
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* bags, const AdvmilGenActs* a,
+                                    const float* d_pred, AdvmilGenGrads* g, void* stream) {
+  ADVMIL_REQUIRE(p && a && g && d_pred, "generator_bwd: null argument");
+  ADVMIL_TRY(check_bags(bags, p->C, false));
+  ADVMIL_REQUIRE(a->ab && a->H && (a->H1 || !p->W0), "generator_bwd: forward was run without saving activations (ab/H/H1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = bags->rows, nb = bags->bags, h = p->h, o = p->o, hid = p->hid, C = p->C;
+  const int abw = gate_width(h);
+  const int prec = a->precision;
+  Workspace ws(a->workspace, a->workspace_bytes);
+  WS_TAKE(Wp, float, (size_t)abw * h);
+  WS_TAKE(bp, float, abw);
+  WS_TAKE(dz, float, (size_t)nb * h);
+  WS_TAKE(dHpre, float, (size_t)nb * o);
+  WS_TAKE(dH1pre, float, (size_t)nb * hid);
+  WS_TAKE(dpre, float, nb);
+  WS_TAKE(dAB, float, (size_t)rows * abw);
+  WS_TAKE(dhpre, float, (size_t)rows * h);
+  WS_TAKE(dWp, float, (size_t)abw * h);
+  WS_TAKE(dbp, float, abw);
+  WS_TAKE(pgws, float, align_up((size_t)nb, 64) + (size_t)row_chunks(rows) * (h + 1));
+  WS_TAKE(bwws, float, max(bwd_weight_ws_floats(rows, abw, h), bwd_weight_ws_floats(rows, h, C)));
+  WS_TAKE(csws, float, (size_t)row_chunks(rows) * max(abw, h));
+  const float ik_bb = (a->train && p->p_backbone > 0.f) ? 1.f / (1.f - p->p_backbone) : 1.f;
+  const float ik_hd = (a->train && p->p_head > 0.f) ? 1.f / (1.f - p->p_head) : 1.f;
+  Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train);
+  Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train);
+  // head
+  ADVMIL_TRY(gen_head_bwd(*p, d_pred, a->H, a->H1, a->pred, nb, ik_bb, ik_hd, dz, dHpre, dH1pre, dpre, st));
+  if (p->W0) {
+    ADVMIL_TRY(outer_sum(dpre, a->H1, hid, a->noise1, p->noise1 ? hid : 0, nb, 1, g->Wl, g->bl, 0, st));
+    ADVMIL_TRY(outer_sum(dH1pre, a->H, o, a->noise0, p->noise0 ? o : 0, nb, hid, g->W0, g->b0, 0, st));
+  }
+  if (p->Wrho) ADVMIL_TRY(outer_sum(dHpre, a->z, h, nullptr, 0, nb, o, g->Wrho, g->brho, 0, st));
+  // pooling + gate
+  ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
+  ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, 0, pgws, st));
+  BwdDataExtras ex;
+  ex.w = a->w; ex.dz = dz; ex.offsets = bags->offsets; ex.bags = nb; ex.relu_src = a->h; ex.ld_src = h; ex.inv_keep = ik_bb;
+  ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st));
+  ADVMIL_TRY(bwd_weight(dAB, a->h, rows, abw, h, dWp, 0, bwws, prec, st));
+  ADVMIL_TRY(colsum(dAB, rows, abw, abw, dbp, 0, csws, st));
+  ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st));
+  // first layer
+  ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st));
+  ADVMIL_TRY(colsum(dhpre, rows, h, h, g->b1, 0, csws, st));
+  if (g->dx) {
+    BwdDataExtras exx;
+    ADVMIL_TRY(bwd_data(dhpre, p->W1, rows, h, C, g->dx, exx, prec, st));
+  }
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_generator_sample(const AdvmilGenParams* p, const float* H, const float* noise0,
+                                       const float* noise1, int32_t bags, int32_t samples, float* out, void* stream) {
+  ADVMIL_REQUIRE(p && H && out && bags > 0 && samples > 0, "generator_sample: bad arguments");
+  // H is the backbone output (post rho); run only MLPs + out scale: present H as "z" with the rho layer disabled
+  AdvmilGenParams q = *p;
+  q.Wrho = nullptr; q.brho = nullptr; q.h = p->o;
+  Drop none = Drop::make(nullptr, 0, 0, 0.f, 0);
+  return gen_head_fwd(q, H, noise0, noise1, bags, samples, none, none, nullptr, nullptr, nullptr, out, (cudaStream_t)stream);
+}
+
+// =============================================================================================
+// discriminator
+// =============================================================================================
+extern "C" size_t advmil_disc_workspace_bytes(const AdvmilDiscParams* p, int32_t rows, int32_t bags, int32_t backward) {
+  const size_t d = p->d, dh = p->d / 2, C = p->C, R = rows / 16;
+  const size_t abw = gate_width(p->d);
+  size_t f = 0;
+  // head forward
+  f += abw * d + abw + 512 + (abw / 128) * R + 256 + seg_pool_ws_floats((int)R, bags, (int)d) + 256 + (bags + 1) + 64;
+  if (backward) {
+    // embed backward
+    size_t e = (size_t)rows * d + (size_t)row_chunks(rows) * 3 * d + bwd_weight_ws_floats(rows, (int)d, (int)C) + 1024;
+    // head backward
+    size_t hb = (size_t)bags * (3 * d + dh + p->t2 + p->t1 + 2) + 2048;
+    hb += R * abw + R * d + R * dh + abw * d + abw + 1024;
+    hb += align_up((size_t)bags, 64) + (size_t)row_chunks((int)R) * (d + 1) + 256;
+    hb += max(bwd_weight_ws_floats((int)R, (int)abw, (int)d), bwd_weight_ws_floats((int)R, (int)d, (int)dh)) + 256;
+    hb += (size_t)row_chunks((int)R) * abw + 256;
+    f += max(e, hb);
+  }
+  return f * sizeof(float) + 64 * 256;
+}
+
+extern "C" int advmil_disc_embed_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilEmbedActs* a, void* stream) {
+  ADVMIL_REQUIRE(p && a && a->emb, "disc_embed_fwd: null argument");
+  ADVMIL_TRY(check_bags(bags, p->C, true));
+  return region_embed_fwd(bags->x, p->Wc, p->bc, p->ln_g, p->ln_b, bags->rows, p->C, p->d, p->ln_eps, a->y_pre, a->emb,
+                          a->precision, (cudaStream_t)stream);
+}
+
+extern "C" int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilEmbedActs* a,
+                                     const float* d_emb, AdvmilDiscGrads* g, int32_t accumulate, void* stream) {
+  ADVMIL_REQUIRE(p && a && d_emb && g, "disc_embed_bwd: null argument");
+  ADVMIL_REQUIRE(a->y_pre, "disc_embed_bwd: forward was run without saving y_pre");
+  ADVMIL_TRY(check_bags(bags, p->C, true));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = bags->rows, d = p->d, C = p->C;
+  Workspace ws(a->workspace, a->workspace_bytes);
+  WS_TAKE(d_y, float, (size_t)rows * d);
+  WS_TAKE(lnws, float, (size_t)row_chunks(rows) * 3 * d);
+  WS_TAKE(bwws, float, bwd_weight_ws_floats(rows, d, C));
+  ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws, st));
+  ADVMIL_TRY(bwd_weight(d_y, bags->x, rows, d, C, g->Wc, accumulate, bwws, a->precision, st));
+  return ADVMIL_OK;
+}
+
+namespace {
+struct RegionOffsets {
+  std::vector<int32_t> host;
+  int32_t* dev;
+};
+}  // namespace
+
+static int make_region_offsets(const AdvmilBags* bags, Workspace& ws, cudaStream_t st, RegionOffsets& ro) {
+  ro.host.resize(bags->bags + 1);
+  for (int i = 0; i <= bags->bags; ++i) ro.host[i] = bags->offsets_host[i] / 16;
+  ro.dev = ws.take<int32_t>(bags->bags + 1);
+  if (!ro.dev) { set_error("disc_head: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  scale_offsets_kernel<<<cdiv(bags->bags + 1, 128), 128, 0, st>>>(bags->offsets, bags->bags + 1, 16, ro.dev);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilHeadActs* a, void* stream) {
+  ADVMIL_REQUIRE(p && a && a->emb && a->t && a->out, "disc_head_fwd: null argument");
+  ADVMIL_TRY(check_bags(bags, p->C, true));
+  ADVMIL_REQUIRE(a->f1 && a->fi && a->rep && a->attn && a->bagv && a->fbar && a->g1 && a->hx && a->u1 && a->ht,
+                 "disc_head_fwd: missing activation buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = bags->bags, d = p->d, dh = p->d / 2, R = bags->rows / 16;
+  const int abw = gate_width(d);
+  Workspace ws(a->workspace, a->workspace_bytes);
+  RegionOffsets ro;
+  ADVMIL_TRY(make_region_offsets(bags, ws, st, ro));
+  WS_TAKE(Wp, float, (size_t)abw * d);
+  WS_TAKE(bp, float, abw);
+  WS_TAKE(part, float, (size_t)(abw / 128) * R);
+  WS_TAKE(poolws, float, seg_pool_ws_floats(R, nb, d));
+  Drop dfc1 = Drop::make(a->mask_fc1, a->seed, SITE_FC1, p->p, a->train);
+  Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train);
+  Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train);
+  Drop dfc2 = Drop::make(a->mask_fc2, a->seed, SITE_FC2, p->p, a->train);
+  Drop none = Drop::make(nullptr, 0, 0, 0.f, 0);
+  // region-level work is tiny (R = rows/16): always the fp32 FFMA engine
+  ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, ADVMIL_FP32, st));
+  ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, ADVMIL_FP32, st));
+  ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
+  ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, a->rep, part, ADVMIL_FP32, st));
+  ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, a->fi, ro.dev, ro.host.data(), R, nb, d, a->attn, a->bagv, a->fbar, poolws, st));
+  ADVMIL_TRY(rlip_tail_fwd(*p, a->bagv, a->fbar, a->t, nb, dfc2, a->g1, a->hx, a->u1, a->ht, a->out, st));
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilHeadActs* a,
+                                    const float* d_out, float* d_emb, float* d_t, AdvmilDiscGrads* g,
+                                    int32_t accumulate, void* stream) {
+  ADVMIL_REQUIRE(p && a && d_out, "disc_head_bwd: null argument");
+  ADVMIL_TRY(check_bags(bags, p->C, true));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = bags->bags, d = p->d, dh = p->d / 2, R = bags->rows / 16, t1 = p->t1, t2 = p->t2;
+  const int abw = gate_width(d);
+  const float ik = (a->train && p->p > 0.f) ? 1.f / (1.f - p->p) : 1.f;
+  Workspace ws(a->workspace, a->workspace_bytes);
+  RegionOffsets ro;
+  ADVMIL_TRY(make_region_offsets(bags, ws, st, ro));
+  WS_TAKE(d_fbar, float, (size_t)nb * d);
+  WS_TAKE(d_bagv, float, (size_t)nb * d);
+  WS_TAKE(d_hx, float, (size_t)nb * d);
+  WS_TAKE(d_g1pre, float, (size_t)nb * dh);
+  WS_TAKE(d_htpre, float, (size_t)nb * t2);
+  WS_TAKE(d_u1pre, float, (size_t)nb * t1);
+  WS_TAKE(d_t_scratch, float, nb);
+  ADVMIL_TRY(rlip_tail_bwd(*p, d_out, a->bagv, a->fbar, a->g1, a->hx, a->u1, a->ht, nb, ik, d_fbar, d_bagv, d_hx, d_g1pre,
+                           d_htpre, d_u1pre, d_t ? d_t : d_t_scratch, st));
+  if (!d_emb && !g) return ADVMIL_OK;  // G step: only dL/dt is needed from D
+  if (g) {
+    ADVMIL_TRY(outer_sum(d_hx, a->g1, dh, nullptr, 0, nb, d, g->F2b_w, g->F2b_b, accumulate, st));
+    ADVMIL_TRY(outer_sum(d_g1pre, a->bagv, d, nullptr, 0, nb, dh, g->F2a_w, g->F2a_b, accumulate, st));
+    ADVMIL_TRY(outer_sum(d_htpre, a->u1, t1, nullptr, 0, nb, t2, g->T2_w, g->T2_b, accumulate, st));
+    ADVMIL_TRY(outer_sum(d_u1pre, a->t, 1, nullptr, 0, nb, t1, g->T1_w, g->T1_b, accumulate, st));
+    if (p->prj_path == 1) ADVMIL_TRY(outer_sum(d_out, a->hx, d, nullptr, 0, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
+    else if (p->prj_path == 2) ADVMIL_TRY(outer_sum(d_out, a->ht, t2, nullptr, 0, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
+  }
+  WS_TAKE(Wp, float, (size_t)abw * d);
+  WS_TAKE(bp, float, abw);
+  WS_TAKE(dAB, float, (size_t)R * abw);
+  WS_TAKE(d_fi, float, (size_t)R * d);
+  WS_TAKE(d_f1pre, float, (size_t)R * dh);
+  WS_TAKE(dWp, float, (size_t)abw * d);
+  WS_TAKE(dbp, float, abw);
+  WS_TAKE(dwc_scratch, float, d + 1);
+  WS_TAKE(pgws, float, align_up((size_t)nb, 64) + (size_t)row_chunks(R) * (d + 1));
+  WS_TAKE(bwws, float, max(bwd_weight_ws_floats(R, abw, d), bwd_weight_ws_floats(R, d, dh)));
+  WS_TAKE(csws, float, (size_t)row_chunks(R) * abw);
+  Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train);
+  Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train);
+  ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
+  ADVMIL_TRY(pool_gate_bwd(a->fi, a->attn, a->bagv, d_bagv, a->ab, p->Pc_w, ro.dev, R, nb, d, d, dga, dgs, dAB,
+                           g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? accumulate : 0, pgws, st));
+  BwdDataExtras ex;
+  ex.w = a->attn; ex.dz = d_bagv; ex.dmean = p->inner_instance ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
+  ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, ADVMIL_FP32, st));
+  if (g) {
+    ADVMIL_TRY(bwd_weight(dAB, a->fi, R, abw, d, dWp, 0, bwws, ADVMIL_FP32, st));
+    ADVMIL_TRY(colsum(dAB, R, abw, abw, dbp, 0, csws, st));
+    ADVMIL_TRY(gate_unpack_grads(dWp, dbp, d, d, g->Pg_w, g->Pg_b, g->Ps_w, g->Ps_b, accumulate, st));
+  }
+  BwdDataExtras ex1;
+  ex1.relu_src = a->f1; ex1.ld_src = dh; ex1.inv_keep = ik;
+  ADVMIL_TRY(bwd_data(d_fi, p->F1b_w, R, d, dh, d_f1pre, ex1, ADVMIL_FP32, st));
+  if (g) {
+    ADVMIL_TRY(bwd_weight(d_fi, a->f1, R, d, dh, g->F1b_w, accumulate, bwws, ADVMIL_FP32, st));
+    ADVMIL_TRY(colsum(d_fi, R, d, d, g->F1b_b, accumulate, csws, st));
+    ADVMIL_TRY(bwd_weight(d_f1pre, a->emb, R, dh, d, g->F1a_w, accumulate, bwws, ADVMIL_FP32, st));
+    ADVMIL_TRY(colsum(d_f1pre, R, dh, dh, g->F1a_b, accumulate, csws, st));
+  }
+  if (d_emb) {
+    BwdDataExtras ex2;
+    ex2.accumulate = accumulate;
+    ADVMIL_TRY(bwd_data(d_f1pre, p->F1a_w, R, dh, d, d_emb, ex2, ADVMIL_FP32, st));
+  }
+  return ADVMIL_OK;
+}
+
+// =============================================================================================
+// stage-level entry points
+// =============================================================================================
+extern "C" int advmil_linear_fwd(const float* x, const float* W, const float* b, int32_t rows, int32_t K, int32_t N,
+                                 int32_t act, float p_drop, const uint8_t* mask, uint64_t seed, int32_t site,
+                                 int32_t train, int32_t precision, float* y, void* stream) {
+  ADVMIL_REQUIRE(x && W && y && rows >= 0, "linear_fwd: null argument");
+  Drop dr = Drop::make(mask, seed, SITE_USER + site, p_drop, train);
+  return linear_fwd(x, W, b, rows, K, N, act, dr, y, precision, (cudaStream_t)stream);
+}
+
+extern "C" size_t advmil_linear_bwd_workspace_bytes(int32_t rows, int32_t K, int32_t N) {
+  return (bwd_weight_ws_floats(rows, N, K) + (size_t)row_chunks(rows) * N + 1024) * sizeof(float);
+}
+
+extern "C" int advmil_linear_bwd(const float* dY, const float* X, const float* W, int32_t rows, int32_t K, int32_t N,
+                                 float* dX, float* dW, float* db, int32_t accumulate, int32_t precision, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  ADVMIL_REQUIRE(dY, "linear_bwd: null dY");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  if (dX) {
+    ADVMIL_REQUIRE(W, "linear_bwd: dX needs W");
+    BwdDataExtras ex; ex.accumulate = accumulate;
+    ADVMIL_TRY(bwd_data(dY, W, rows, N, K, dX, ex, precision, st));
+  }
+  if (dW) {
+    ADVMIL_REQUIRE(X, "linear_bwd: dW needs X");
+    WS_TAKE(bwws, float, bwd_weight_ws_floats(rows, N, K));
+    ADVMIL_TRY(bwd_weight(dY, X, rows, N, K, dW, accumulate, bwws, precision, st));
+  }
+  if (db) {
+    WS_TAKE(csws, float, (size_t)row_chunks(rows) * N);
+    ADVMIL_TRY(colsum(dY, rows, N, N, db, accumulate, csws, st));
+  }
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_gated_score_fwd(const float* v, const float* Wa, const float* ba, const float* Wb, const float* bb,
+                                      const float* wc, const float* bc, int32_t rows, int32_t L, int32_t D, float p_drop,
+                                      const uint8_t* mask_a, const uint8_t* mask_b, uint64_t seed, int32_t site,
+                                      int32_t train, int32_t precision, float* ab, float* s, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  ADVMIL_REQUIRE(v && Wa && Wb && wc && bc && s, "gated_score_fwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int abw = gate_width(D);
+  Workspace ws(workspace, workspace_bytes);
+  WS_TAKE(Wp, float, (size_t)abw * L);
+  WS_TAKE(bp, float, abw);
+  WS_TAKE(part, float, (size_t)(abw / 128) * rows);
+  Drop da = Drop::make(mask_a, seed, SITE_USER + site, p_drop, train);
+  Drop db = Drop::make(mask_b, seed, SITE_USER + site + 1, p_drop, train);
+  ADVMIL_TRY(gate_pack_weights(Wa, ba, Wb, bb, L, D, Wp, bp, st));
+  return gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, part, precision, st);
+}
+
+extern "C" size_t advmil_seg_pool_workspace_bytes(int32_t rows, int32_t bags, int32_t width) {
+  return seg_pool_ws_floats(rows, bags, width) * sizeof(float) + 1024;
+}
+
+extern "C" int advmil_seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets,
+                                           const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width,
+                                           float* w, float* z, float* mean, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  ADVMIL_REQUIRE(s && v && offsets && offsets_host && w && z, "seg_softmax_pool_fwd: null argument");
+  Workspace ws(workspace, workspace_bytes);
+  WS_TAKE(poolws, float, seg_pool_ws_floats(rows, bags, width));
+  return seg_softmax_pool_fwd(s, v, offsets, offsets_host, rows, bags, width, w, z, mean, poolws, (cudaStream_t)stream);
+}

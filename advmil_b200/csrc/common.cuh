@@ -1,0 +1,171 @@
+// Shared device/host helpers for the advmil_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/advmil_b200.h"
+
+namespace advmil {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define ADVMIL_CHECK_CUDA(expr)                                                        \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::advmil::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return ADVMIL_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define ADVMIL_CHECK_LAUNCH()                                                          \
+  do {                                                                                 \
+    ::advmil::count_launch();                                                          \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      ::advmil::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return ADVMIL_ERR_CUDA;                                                          \
+    }                                                                                  \
+  } while (0)
+
+#define ADVMIL_REQUIRE(cond, ...)                                                      \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      ::advmil::set_error(__VA_ARGS__);                                                \
+      return ADVMIL_ERR_INVALID;                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define ADVMIL_TRY(expr)                                                               \
+  do {                                                                                 \
+    int _s = (expr);                                                                   \
+    if (_s != ADVMIL_OK) return _s;                                                    \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over the caller-provided workspace.
+struct Workspace {
+  char* base;
+  size_t cap, used;
+  Workspace(void* p, size_t n) : base((char*)p), cap(n), used(0) {}
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (used + bytes > cap || base == nullptr) return nullptr;
+    T* r = (T*)(base + used);
+    used += bytes;
+    return r;
+  }
+};
+
+// ---- dropout keep bits: counter-based, identical in forward and backward ----------------------
+// Sites (one id per dropout layer of the reference):
+enum DropSite : int {
+  SITE_H = 1, SITE_A = 2, SITE_B = 3, SITE_RHO = 4, SITE_MLP0 = 5,           // generator
+  SITE_FC1 = 11, SITE_GA = 12, SITE_GS = 13, SITE_FC2 = 14,                   // discriminator
+  SITE_USER = 100
+};
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+// uniform in [0,1) with 24 bits from (seed, site, element index)
+__host__ __device__ __forceinline__ float rng_uniform(uint64_t seed, int site, uint64_t idx) {
+  uint64_t r = mix64(seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1) + mix64(idx + 0xD1B54A32D192ED03ULL));
+  return (float)(r >> 40) * (1.0f / 16777216.0f);
+}
+
+struct Drop {          // one dropout site
+  const uint8_t* mask; // injected keep mask [rows, width] or nullptr
+  uint64_t seed;
+  float p;             // drop probability
+  float inv_keep;      // 1/(1-p)
+  int site;
+  int active;          // train && p > 0
+  __host__ static Drop make(const uint8_t* mask, uint64_t seed, int site, float p, int train) {
+    Drop d;
+    d.mask = mask; d.seed = seed; d.site = site; d.p = p;
+    d.active = (train && p > 0.f) ? 1 : 0;
+    d.inv_keep = d.active ? 1.0f / (1.0f - p) : 1.0f;
+    return d;
+  }
+  // multiplicative factor for element idx (= row*width + col): 0 or 1/(1-p); 1 when inactive
+  __device__ __forceinline__ float scale(uint64_t idx) const {
+    if (!active) return 1.0f;
+    bool keep = mask ? (mask[idx] != 0) : (rng_uniform(seed, site, idx) >= p);
+    return keep ? inv_keep : 0.0f;
+  }
+};
+
+// ---- warp helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float half_warp_sum(float v) {  // over 16 consecutive lanes
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum / max through shared memory (blockDim.x multiple of 32, <= 1024); all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* red /*[33]*/) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// bag of a packed row by binary search over offsets[0..bags]
+__device__ __forceinline__ int bag_of_row(const int32_t* __restrict__ offsets, int bags, int row) {
+  int lo = 0, hi = bags;  // invariant: offsets[lo] <= row < offsets[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (offsets[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// packed gate layout: tanh_j at 128*(j/64) + j%64, sigmoid_j at +64
+__host__ __device__ __forceinline__ int gate_width(int D) { return 128 * ((D + 63) / 64); }
+__host__ __device__ __forceinline__ int gate_col_a(int j) { return 128 * (j >> 6) + (j & 63); }
+
+}  // namespace advmil

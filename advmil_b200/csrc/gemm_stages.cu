@@ -1,0 +1,87 @@
+// Launchers for the N-row contractions.  precision == ADVMIL_FP32 runs the FFMA tile engine (gemm_simt.cuh);
+// ADVMIL_TF32 / ADVMIL_TF32X3 run the tcgen05 engine (gemm_tc.cu) for the shapes it supports and fall through to
+// the FFMA engine for the small region-level shapes, where the tensor pipe cannot be filled anyway.
+#include "gemm_simt.cuh"
+#include "stages.cuh"
+#include "gemm_tc.cuh"
+
+namespace advmil {
+
+static bool gemm_ok(int K, int N, const void* a, const void* b) {
+  return (K % 4 == 0) && (N % 4 == 0) && (((uintptr_t)a | (uintptr_t)b) % 16 == 0);
+}
+
+int linear_fwd(const float* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+               float* y, int precision, cudaStream_t st) {
+  ADVMIL_REQUIRE(gemm_ok(K, N, x, W), "linear_fwd: K=%d N=%d must be multiples of 4 and pointers 16B aligned", K, N);
+  if (rows == 0) return ADVMIL_OK;
+  if (precision != ADVMIL_FP32 && tc_linear_supported(rows, K, N))
+    return tc_linear_fwd(x, W, b, rows, K, N, relu, drop, y, precision, st);
+  GemmArgs g{x, W, rows, N, K, K, K, K};
+  EpiLinear epi{y, N, b, relu, drop, N};
+  return launch_gemm<true, true>(g, epi, 1, st);
+}
+
+int gated_score_fwd(const float* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
+                    int D, const Drop& da, const Drop& db, float* ab, float* s, float* part_ws, int precision,
+                    cudaStream_t st) {
+  ADVMIL_REQUIRE(L % 4 == 0, "gated_score_fwd: L=%d must be a multiple of 4", L);
+  if (rows == 0) return ADVMIL_OK;
+  int abw = gate_width(D);
+  if (precision != ADVMIL_FP32 && tc_gate_supported(rows, L, D))
+    return tc_gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, precision, st);
+  GemmArgs g{v, Wp, rows, abw, L, L, L, L};
+  EpiGate epi{ab, abw, bp, wc, part_ws, D, da, db};
+  ADVMIL_TRY((launch_gemm<true, true>(g, epi, 1, st)));
+  return gate_score_finish(part_ws, abw / 128, rows, bc, s, st);
+}
+
+int region_embed_fwd(const float* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows,
+                     int C, int d, float eps, float* y_pre, float* emb, int precision, cudaStream_t st) {
+  ADVMIL_REQUIRE(rows % 16 == 0, "region_embed: rows %d not a multiple of 16 (backbone_utils.py:65)", rows);
+  ADVMIL_REQUIRE(d <= 128 && d % 4 == 0 && C % 4 == 0, "region_embed: d=%d (<=128, %%4) C=%d (%%4) unsupported", d, C);
+  if (rows == 0) return ADVMIL_OK;
+  if (precision != ADVMIL_FP32 && tc_embed_supported(rows, C, d))
+    return tc_region_embed_fwd(x, Wc, bc, gamma, beta, rows, C, d, eps, y_pre, emb, precision, st);
+  GemmArgs g{x, Wc, rows, d, C, C, C, C};
+  EpiLNPool epi{y_pre, emb, bc, gamma, beta, d, eps};
+  return launch_gemm<true, true>(g, epi, 1, st);
+}
+
+int bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* dX, const BwdDataExtras& ex,
+             int precision, cudaStream_t st) {
+  ADVMIL_REQUIRE(gemm_ok(Ny, Nx, dY, W), "bwd_data: Ny=%d Nx=%d must be multiples of 4", Ny, Nx);
+  if (rows == 0) return ADVMIL_OK;
+  if (precision != ADVMIL_FP32 && tc_bwd_data_supported(rows, Ny, Nx))
+    return tc_bwd_data(dY, W, rows, Ny, Nx, dX, ex, precision, st);
+  GemmArgs g{dY, W, rows, Nx, Ny, Ny, Nx, Ny};
+  EpiBwdData epi{dX, Nx, ex.w, ex.dz, ex.dmean, ex.offsets, ex.bags, ex.relu_src, ex.ld_src, ex.inv_keep, ex.accumulate};
+  return launch_gemm<true, false>(g, epi, 1, st);
+}
+
+static int pick_splits(int rows, int N1, int N2) {
+  int tiles = cdiv(N1, BM) * cdiv(N2, BN);
+  int want = cdiv(148 * 4, tiles);                  // ~4 CTAs per SM
+  int max_by_k = max(1, rows / 256);                // at least 256 rows per split
+  int s = min(want, max_by_k);
+  return max(1, min(s, 256));
+}
+size_t bwd_weight_ws_floats(int rows, int N1, int N2) {
+  return (size_t)pick_splits(rows, N1, N2) * N1 * N2;
+}
+int bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+               int precision, cudaStream_t st) {
+  ADVMIL_REQUIRE(gemm_ok(N1, N2, dY, X), "bwd_weight: N1=%d N2=%d must be multiples of 4", N1, N2);
+  if (rows == 0) { if (!accumulate) return fill_zero(dW, (size_t)N1 * N2, st); return ADVMIL_OK; }
+  if (precision != ADVMIL_FP32 && tc_bwd_weight_supported(rows, N1, N2))
+    return tc_bwd_weight(dY, X, rows, N1, N2, dW, accumulate, ws, precision, st);
+  int splits = pick_splits(rows, N1, N2);
+  int kchunk = cdiv(cdiv(rows, splits), BK) * BK;
+  splits = cdiv(rows, kchunk);
+  GemmArgs g{dY, X, N1, N2, rows, N1, N2, kchunk};
+  EpiPartial epi{ws};
+  ADVMIL_TRY((launch_gemm<false, false>(g, epi, splits, st)));
+  return splitk_reduce(ws, splits, (size_t)N1 * N2, dW, accumulate, st);
+}
+
+}  // namespace advmil

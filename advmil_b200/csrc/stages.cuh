@@ -1,0 +1,75 @@
+// Internal stage launchers shared by the C-ABI composites (api.cu).  All asynchronous on `st`.
+#pragma once
+#include "common.cuh"
+
+namespace advmil {
+
+// ---- gemm_stages.cu ---------------------------------------------------------------------------
+int linear_fwd(const float* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+               float* y, int precision, cudaStream_t st);
+// packed gate weights Wp [abw, L], bp [abw] (zero padded) must have been built by gate_pack_weights
+int gated_score_fwd(const float* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
+                    int D, const Drop& da, const Drop& db, float* ab, float* s, float* part_ws, int precision,
+                    cudaStream_t st);
+int region_embed_fwd(const float* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows,
+                     int C, int d, float eps, float* y_pre, float* emb, int precision, cudaStream_t st);
+// dX[rows,Nx] = (dY[rows,Ny] . W[Ny,Nx] + pool terms) * relu'  (W row-major [Ny, Nx])
+struct BwdDataExtras {
+  const float* w = nullptr; const float* dz = nullptr; const float* dmean = nullptr;
+  const int32_t* offsets = nullptr; int bags = 0;
+  const float* relu_src = nullptr; int ld_src = 0; float inv_keep = 1.f;
+  int accumulate = 0;
+};
+int bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* dX, const BwdDataExtras& ex,
+             int precision, cudaStream_t st);
+// dW[N1,N2] (+)= dY[rows,N1]^T . X[rows,N2]   (split-K over rows; ws >= bwd_weight_ws_floats floats)
+size_t bwd_weight_ws_floats(int rows, int N1, int N2);
+int bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+               int precision, cudaStream_t st);
+
+// ---- seg_kernels.cu ---------------------------------------------------------------------------
+int gate_pack_weights(const float* Wa, const float* ba, const float* Wb, const float* bb, int L, int D, float* Wp,
+                      float* bp, cudaStream_t st);
+int gate_unpack_grads(const float* dWp, const float* dbp, int L, int D, float* dWa, float* dba, float* dWb, float* dbb,
+                      int accumulate, cudaStream_t st);
+int gate_score_finish(const float* part, int ntiles, int rows, const float* bc, float* s, cudaStream_t st);
+size_t seg_pool_ws_floats(int rows, int bags, int width);
+int seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets, const int32_t* offsets_host, int rows,
+                         int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st);
+// rows_per_cta used by the row-chunked backward kernels (partials are [nchunks, ...])
+constexpr int ROWS_PER_CTA = 128;
+inline int row_chunks(int rows) { return cdiv(rows, ROWS_PER_CTA); }
+// pooling + gate backward: ds = w (dz.v - dz.z); dAB packed; partial dwc/dbc per chunk -> reduced into dwc, dbc
+int pool_gate_bwd(const float* v, const float* w, const float* z, const float* dz, const float* ab, const float* wc,
+                  const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, float* dAB,
+                  float* dwc, float* dbc, int accumulate, float* ws /* >= row_chunks*(D+1) + bags floats */,
+                  cudaStream_t st);
+// LayerNorm + ReLU + region-mean backward per row; partials of dgamma/dbeta/dbias reduced into the outputs
+int ln_pool_bwd(const float* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
+                float eps, float* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate,
+                float* ws /* >= row_chunks*3*d floats */, cudaStream_t st);
+int colsum(const float* dY, int rows, int N, int ld, float* out, int accumulate, float* ws /* >= row_chunks*N */,
+           cudaStream_t st);
+int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st);
+int apply_dropout(const float* src, int rows, int width, const Drop& drop, float* dst, cudaStream_t st);
+int fill_zero(float* p, size_t n, cudaStream_t st);
+
+// ---- tail_kernels.cu --------------------------------------------------------------------------
+int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, const float* noise1, int bags,
+                 int samples, const Drop& drho, const Drop& dmlp0, float* H, float* H1, float* pre, float* pred,
+                 cudaStream_t st);
+// per-bag vector backward; writes dz [bags,h], dHpre [bags,o], dH1pre [bags,hid], dpre [bags]
+int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, const float* H1, const float* pred,
+                 int bags, float inv_keep_rho, float inv_keep_mlp0, float* dz, float* dHpre, float* dH1pre, float* dpre,
+                 cudaStream_t st);
+// dW[out, in1+in2] (+)= sum_b dy[b,out] * concat(x1[b,:in1], x2[b,:in2]);  db[out] (+)= sum_b dy[b,out]
+int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in2, int bags, int out, float* dW,
+              float* db, int accumulate, cudaStream_t st);
+int rlip_tail_fwd(const AdvmilDiscParams& p, const float* bagv, const float* fbar, const float* t, int bags,
+                  const Drop& dfc2, float* g1, float* hx, float* u1, float* ht, float* out, cudaStream_t st);
+int rlip_tail_bwd(const AdvmilDiscParams& p, const float* d_out, const float* bagv, const float* fbar, const float* g1,
+                  const float* hx, const float* u1, const float* ht, int bags, float inv_keep_fc2, float* d_fbar,
+                  float* d_bagv, float* d_hx, float* d_g1pre, float* d_htpre, float* d_u1pre, float* d_t,
+                  cudaStream_t st);
+
+}  // namespace advmil

@@ -1,0 +1,601 @@
+// Per-bag "tail" kernels (latency-bound: one CTA per bag), losses, fused Adam, DeepAttMISL cluster pooling and the
+// region index map.  All vectors live in shared memory; mat-vecs are warp-per-output-row with coalesced weight reads.
+#include "stages.cuh"
+
+namespace advmil {
+
+// out[r] = dot(W[r, 0:n], v) for r handled by this warp; caller adds bias/activation
+__device__ __forceinline__ float warp_dot(const float* __restrict__ Wrow, const float* __restrict__ v, int n, int lane) {
+  float acc = 0.f;
+  for (int c = lane; c < n; c += 32) acc = fmaf(Wrow[c], v[c], acc);
+  return warp_sum(acc);
+}
+
+// =============================================================================================
+// K4: generator head  (model/backbone.py:73-77,85; model/GANSurv.py:32-49; model/model_utils.py:116-133)
+// grid (bags, samples)
+// =============================================================================================
+__global__ void __launch_bounds__(256) gen_head_fwd_kernel(AdvmilGenParams p, const float* __restrict__ z,
+                                                           const float* __restrict__ noise0,
+                                                           const float* __restrict__ noise1, int bags, Drop drho,
+                                                           Drop dmlp0, float* __restrict__ H, float* __restrict__ H1,
+                                                           float* __restrict__ pre, float* __restrict__ pred) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, smp = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int h = p.h, o = p.o, hid = p.hid;
+  float* zs = sm;            // [h]
+  float* Hs = zs + h;        // [2*o]   (H | noise0)
+  float* H1s = Hs + 2 * o;   // [2*hid] (H1 | noise1)
+  float* red = H1s + 2 * hid;  // [33]
+  for (int c = threadIdx.x; c < h; c += blockDim.x) zs[c] = z[(size_t)b * h + c];
+  __syncthreads();
+  if (p.Wrho) {
+    for (int i = wid; i < o; i += nw) {
+      float v = warp_dot(p.Wrho + (size_t)i * h, zs, h, lane);
+      if (lane == 0) Hs[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale((uint64_t)b * o + i);
+    }
+  } else {
+    for (int c = threadIdx.x; c < o; c += blockDim.x) Hs[c] = zs[c];
+  }
+  const int in0 = o * (1 + p.noise0);
+  if (p.noise0)
+    for (int c = threadIdx.x; c < o; c += blockDim.x)
+      Hs[o + c] = noise0 ? noise0[((size_t)smp * bags + b) * o + c] : 0.f;
+  __syncthreads();
+  if (H && smp == 0) for (int c = threadIdx.x; c < o; c += blockDim.x) H[(size_t)b * o + c] = Hs[c];
+  if (p.W0 == nullptr) return;  // backbone-only mode (ABMIL.forward without the Generator head)
+  for (int j = wid; j < hid; j += nw) {
+    float v = warp_dot(p.W0 + (size_t)j * in0, Hs, in0, lane);
+    if (lane == 0) H1s[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale((uint64_t)b * hid + j);
+  }
+  const int in1 = hid * (1 + p.noise1);
+  if (p.noise1)
+    for (int c = threadIdx.x; c < hid; c += blockDim.x)
+      H1s[hid + c] = noise1 ? noise1[((size_t)smp * bags + b) * hid + c] : 0.f;
+  __syncthreads();
+  if (H1 && smp == 0) for (int c = threadIdx.x; c < hid; c += blockDim.x) H1[(size_t)b * hid + c] = H1s[c];
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < in1; c += blockDim.x) acc = fmaf(p.Wl[c], H1s[c], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    float v = acc + p.bl[0];
+    if (pre && smp == 0) pre[b] = v;
+    float out = v;
+    if (p.out_scale == 1) out = sigmoidf_(v);
+    else if (p.out_scale == 2) out = expf(v);
+    pred[(size_t)smp * bags + b] = out;
+  }
+}
+
+int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, const float* noise1, int bags,
+                 int samples, const Drop& drho, const Drop& dmlp0, float* H, float* H1, float* pre, float* pred,
+                 cudaStream_t st) {
+  ADVMIL_REQUIRE(p.Wrho != nullptr || p.o == p.h, "gen_head: no rho layer requires o == h");
+  size_t smem = (size_t)(p.h + 2 * p.o + 2 * p.hid + 40) * sizeof(float);
+  ADVMIL_REQUIRE(smem <= 48 * 1024, "gen_head: dims too large for the head kernel (h=%d o=%d)", p.h, p.o);
+  gen_head_fwd_kernel<<<dim3(bags, samples), 256, smem, st>>>(p, z, noise0, noise1, bags, drho, dmlp0, H, H1, pre, pred);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+__global__ void __launch_bounds__(256) gen_head_bwd_kernel(AdvmilGenParams p, const float* __restrict__ d_pred,
+                                                           const float* __restrict__ H, const float* __restrict__ H1,
+                                                           const float* __restrict__ pred, float inv_keep_rho,
+                                                           float inv_keep_mlp0, float* __restrict__ dz,
+                                                           float* __restrict__ dHpre, float* __restrict__ dH1pre,
+                                                           float* __restrict__ dpre) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int h = p.h, o = p.o, hid = p.hid;
+  float* d1 = sm;        // [hid]
+  float* dH = d1 + hid;  // [o]
+  const bool head = p.W0 != nullptr;  // else d_pred is dL/dH [bags,o] (backbone-only mode)
+  if (head) {
+    float dp = d_pred[b];
+    float pr = pred[b];
+    if (p.out_scale == 1) dp *= pr * (1.f - pr);
+    else if (p.out_scale == 2) dp *= pr;
+    if (threadIdx.x == 0) dpre[b] = dp;
+    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+      float hv = H1[(size_t)b * hid + j];
+      float g = hv > 0.f ? dp * p.Wl[j] * inv_keep_mlp0 : 0.f;
+      d1[j] = g;
+      dH1pre[(size_t)b * hid + j] = g;
+    }
+  }
+  __syncthreads();
+  const int in0 = o * (1 + p.noise0);
+  for (int i = threadIdx.x; i < o; i += blockDim.x) {
+    float acc = 0.f;
+    if (head) for (int j = 0; j < hid; ++j) acc = fmaf(p.W0[(size_t)j * in0 + i], d1[j], acc);
+    else acc = d_pred[(size_t)b * o + i];
+    if (p.Wrho) acc = H[(size_t)b * o + i] > 0.f ? acc * inv_keep_rho : 0.f;
+    dH[i] = acc;
+    dHpre[(size_t)b * o + i] = acc;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < h; k += blockDim.x) {
+    float acc;
+    if (p.Wrho) {
+      acc = 0.f;
+      for (int i = 0; i < o; ++i) acc = fmaf(p.Wrho[(size_t)i * h + k], dH[i], acc);
+    } else {
+      acc = dH[k];
+    }
+    dz[(size_t)b * h + k] = acc;
+  }
+}
+
+int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, const float* H1, const float* pred,
+                 int bags, float inv_keep_rho, float inv_keep_mlp0, float* dz, float* dHpre, float* dH1pre, float* dpre,
+                 cudaStream_t st) {
+  size_t smem = (size_t)(p.hid + p.o) * sizeof(float);
+  gen_head_bwd_kernel<<<bags, 256, smem, st>>>(p, d_pred, H, H1, pred, inv_keep_rho, inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+// dW[o, i] (+)= sum_b dy[b,o] * xcat[b,i];  db[o] (+)= sum_b dy[b,o]
+__global__ void outer_sum_kernel(const float* __restrict__ dy, const float* __restrict__ x1, int in1,
+                                 const float* __restrict__ x2, int in2, int bags, int out, float* __restrict__ dW,
+                                 float* __restrict__ db, int accumulate) {
+  const int in = in1 + in2;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)out * in) return;
+  int o = (int)(idx / in), i = (int)(idx % in);
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < bags; ++b) {
+    float g = dy[(size_t)b * out + o];
+    float xv = i < in1 ? x1[(size_t)b * in1 + i] : (x2 ? x2[(size_t)b * in2 + (i - in1)] : 0.f);
+    acc = fmaf(g, xv, acc);
+    accb += g;
+  }
+  if (dW) dW[idx] = accumulate ? dW[idx] + acc : acc;
+  if (db && i == 0) db[o] = accumulate ? db[o] + accb : accb;
+}
+int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in2, int bags, int out, float* dW,
+              float* db, int accumulate, cudaStream_t st) {
+  size_t n = (size_t)out * (in1 + in2);
+  outer_sum_kernel<<<cdiv(n, 256), 256, 0, st>>>(dy, x1, in1, x2, in2, bags, out, dW, db, accumulate);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+// =============================================================================================
+// K7/K8 tail: bag MLP fc2, time embedding, inner product, projection
+// (model/model_utils.py:200-206; model/GANSurv.py:89-105)
+// =============================================================================================
+__global__ void __launch_bounds__(128) rlip_tail_fwd_kernel(AdvmilDiscParams p, const float* __restrict__ bagv,
+                                                            const float* __restrict__ fbar, const float* __restrict__ t,
+                                                            Drop dfc2, float* __restrict__ g1, float* __restrict__ hx,
+                                                            float* __restrict__ u1, float* __restrict__ ht,
+                                                            float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int d = p.d, dh = p.d / 2, t1 = p.t1, t2 = p.t2;
+  float* bv = sm;           // [d]
+  float* g1s = bv + d;      // [dh]
+  float* hxs = g1s + dh;    // [d]
+  float* u1s = hxs + d;     // [t1]
+  float* hts = u1s + t1;    // [t2]
+  float* red = hts + t2;    // [33]
+  for (int c = threadIdx.x; c < d; c += blockDim.x) bv[c] = bagv[(size_t)b * d + c];
+  const float tv = t[b];
+  for (int c = threadIdx.x; c < t1; c += blockDim.x) {
+    float v = fmaxf(fmaf(p.T1_w[c], tv, p.T1_b[c]), 0.f);
+    u1s[c] = v;
+    u1[(size_t)b * t1 + c] = v;
+  }
+  __syncthreads();
+  for (int j = wid; j < dh; j += nw) {
+    float v = warp_dot(p.F2a_w + (size_t)j * d, bv, d, lane);
+    if (lane == 0) {
+      v = fmaxf(v + p.F2a_b[j], 0.f) * dfc2.scale((uint64_t)b * dh + j);
+      g1s[j] = v;
+      g1[(size_t)b * dh + j] = v;
+    }
+  }
+  for (int j = wid; j < t2; j += nw) {
+    float v = warp_dot(p.T2_w + (size_t)j * t1, u1s, t1, lane);
+    if (lane == 0) {
+      v = fmaxf(v + p.T2_b[j], 0.f);
+      hts[j] = v;
+      ht[(size_t)b * t2 + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int j = wid; j < d; j += nw) {
+    float v = warp_dot(p.F2b_w + (size_t)j * dh, g1s, dh, lane);
+    if (lane == 0) {
+      v += p.F2b_b[j];
+      hxs[j] = v;
+      hx[(size_t)b * d + j] = v;
+    }
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float left = p.inner_instance ? fbar[(size_t)b * d + c] : hxs[c];
+    acc = fmaf(left, hts[c], acc);
+    if (p.prj_path == 1) acc = fmaf(p.Pr_w[c], hxs[c], acc);
+    else if (p.prj_path == 2) acc = fmaf(p.Pr_w[c], hts[c], acc);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[b] = acc + (p.prj_path ? p.Pr_b[0] : 0.f);
+}
+
+int rlip_tail_fwd(const AdvmilDiscParams& p, const float* bagv, const float* fbar, const float* t, int bags,
+                  const Drop& dfc2, float* g1, float* hx, float* u1, float* ht, float* out, cudaStream_t st) {
+  ADVMIL_REQUIRE(p.t2 == p.d, "rlip_tail: time embedding width %d must equal d %d", p.t2, p.d);
+  size_t smem = (size_t)(p.d * 2 + p.d / 2 + p.t1 + p.t2 + 40) * sizeof(float);
+  rlip_tail_fwd_kernel<<<bags, 128, smem, st>>>(p, bagv, fbar, t, dfc2, g1, hx, u1, ht, out);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+__global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
+    AdvmilDiscParams p, const float* __restrict__ d_out, const float* __restrict__ bagv, const float* __restrict__ fbar,
+    const float* __restrict__ g1, const float* __restrict__ hx, const float* __restrict__ u1,
+    const float* __restrict__ ht, float inv_keep_fc2, float* __restrict__ d_fbar, float* __restrict__ d_bagv,
+    float* __restrict__ d_hx, float* __restrict__ d_g1pre, float* __restrict__ d_htpre, float* __restrict__ d_u1pre,
+    float* __restrict__ d_t) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int d = p.d, dh = p.d / 2, t1 = p.t1, t2 = p.t2;
+  float* dhx = sm;          // [d]
+  float* dg1 = dhx + d;     // [dh]
+  float* dht = dg1 + dh;    // [t2]
+  float* du1 = dht + t2;    // [t1]
+  float* red = du1 + t1;    // [33]
+  const float go = d_out[b];
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float hxv = hx[(size_t)b * d + c], htv = ht[(size_t)b * t2 + c], fb = fbar[(size_t)b * d + c];
+    float g_hx = 0.f, g_ht = 0.f, g_fb = 0.f;
+    if (p.inner_instance) { g_fb = go * htv; g_ht = go * fb; }
+    else { g_hx = go * htv; g_ht = go * hxv; }
+    if (p.prj_path == 1) g_hx += go * p.Pr_w[c];
+    else if (p.prj_path == 2) g_ht += go * p.Pr_w[c];
+    g_ht = htv > 0.f ? g_ht : 0.f;  // ReLU of the last time-MLP layer
+    dhx[c] = g_hx; dht[c] = g_ht;
+    d_hx[(size_t)b * d + c] = g_hx;
+    d_htpre[(size_t)b * t2 + c] = g_ht;
+    d_fbar[(size_t)b * d + c] = g_fb;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < dh; j += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < d; ++c) acc = fmaf(p.F2b_w[(size_t)c * dh + j], dhx[c], acc);
+    acc = g1[(size_t)b * dh + j] > 0.f ? acc * inv_keep_fc2 : 0.f;
+    dg1[j] = acc;
+    d_g1pre[(size_t)b * dh + j] = acc;
+  }
+  for (int k = threadIdx.x; k < t1; k += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < t2; ++c) acc = fmaf(p.T2_w[(size_t)c * t1 + k], dht[c], acc);
+    acc = u1[(size_t)b * t1 + k] > 0.f ? acc : 0.f;
+    du1[k] = acc;
+    d_u1pre[(size_t)b * t1 + k] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < dh; ++j) acc = fmaf(p.F2a_w[(size_t)j * d + c], dg1[j], acc);
+    d_bagv[(size_t)b * d + c] = acc;
+  }
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < t1; k += blockDim.x) acc = fmaf(p.T1_w[k], du1[k], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && d_t) d_t[b] = acc;
+}
+
+int rlip_tail_bwd(const AdvmilDiscParams& p, const float* d_out, const float* bagv, const float* fbar, const float* g1,
+                  const float* hx, const float* u1, const float* ht, int bags, float inv_keep_fc2, float* d_fbar,
+                  float* d_bagv, float* d_hx, float* d_g1pre, float* d_htpre, float* d_u1pre, float* d_t,
+                  cudaStream_t st) {
+  size_t smem = (size_t)(p.d + p.d / 2 + p.t2 + p.t1 + 40) * sizeof(float);
+  rlip_tail_bwd_kernel<<<bags, 128, smem, st>>>(p, d_out, bagv, fbar, g1, hx, u1, ht, inv_keep_fc2, d_fbar, d_bagv,
+                                                 d_hx, d_g1pre, d_htpre, d_u1pre, d_t);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+// =============================================================================================
+// losses (loss/utils.py:21-41,182-208) — one CTA, bags <= a few thousand
+// =============================================================================================
+__global__ void disc_loss_kernel(const float* __restrict__ f_real, const float* __restrict__ f_fake,
+                                 const uint8_t* __restrict__ real_mask, int bags, int which, float n_real, float n_fake,
+                                 float* __restrict__ loss_out, float* __restrict__ d_real, float* __restrict__ d_fake) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < bags; b += blockDim.x) {
+    float f = f_fake[b];
+    float lf, gf;
+    if (which == 0) {
+      float sg = sigmoidf_(f);
+      lf = -(1.0f - logf(sg + 1e-8f));
+      gf = sg * (1.f - sg) / (sg + 1e-8f);
+    } else if (which == 1) {
+      lf = fmaxf(1.f + f, 0.f);
+      gf = (1.f + f) > 0.f ? 1.f : 0.f;
+    } else {
+      lf = f; gf = 1.f;
+    }
+    acc += lf / n_fake;
+    if (d_fake) d_fake[b] = gf / n_fake;
+    float gr = 0.f;
+    if (real_mask && real_mask[b] && n_real > 0.f) {
+      float r = f_real[b];
+      float lr;
+      if (which == 0) {
+        float sg = sigmoidf_(r);
+        lr = -logf(sg + 1e-8f);
+        gr = -sg * (1.f - sg) / (sg + 1e-8f);
+      } else if (which == 1) {
+        lr = fmaxf(1.f - r, 0.f);
+        gr = (1.f - r) > 0.f ? -1.f : 0.f;
+      } else {
+        lr = -r; gr = -1.f;
+      }
+      acc += lr / n_real;
+      gr /= n_real;
+    }
+    if (d_real) d_real[b] = gr;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) loss_out[0] += acc;
+}
+
+__global__ void gen_loss_kernel(const float* __restrict__ pred, const float* __restrict__ t, const float* __restrict__ e,
+                                const uint8_t* __restrict__ visible, const float* __restrict__ f_fake, int bags,
+                                float n_visible, float n_fake, float coef_gan, float alpha, float gamma, int norm,
+                                float* __restrict__ losses, float* __restrict__ d_pred, float* __restrict__ d_fake) {
+  __shared__ float red[33];
+  float rec = 0.f, gen = 0.f;
+  for (int b = threadIdx.x; b < bags; b += blockDim.x) {
+    float g = 0.f;
+    if (visible[b] && n_visible > 0.f) {
+      float diff = pred[b] - t[b], ev = e[b];
+      float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      float lo = ev * fabsf(diff);
+      float glo = ev * sgn;
+      float marg = gamma - diff;
+      float lc = (1.f - ev) * fmaxf(marg, 0.f);
+      float glc = marg > 0.f ? -(1.f - ev) : 0.f;
+      if (norm == 1) { glo = 2.f * lo * glo; glc = 2.f * lc * glc; lo = lo * lo; lc = lc * lc; }
+      rec += ((1.f - alpha) * (lo + lc) + alpha * lo) / n_visible;
+      g = ((1.f - alpha) * (glo + glc) + alpha * glo) / n_visible;
+    }
+    d_pred[b] = g;
+    gen += -f_fake[b] / n_fake;
+    d_fake[b] = coef_gan == 0.f ? 0.f : -coef_gan / n_fake;
+  }
+  rec = block_sum(rec, red);
+  gen = block_sum(gen, red);
+  if (threadIdx.x == 0) {
+    losses[0] += rec;
+    losses[1] += gen;
+    losses[2] += coef_gan == 0.f ? rec : rec + coef_gan * gen;
+  }
+}
+
+// =============================================================================================
+// fused Adam (+L2 weight decay mask, +L1 sub-gradient) over a flat buffer
+// =============================================================================================
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, const uint8_t* __restrict__ wd_mask, int64_t n, float step_size,
+                            float beta1, float beta2, float eps, float weight_decay, float l1_coef, float inv_sqrt_bc2,
+                            float grad_scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float pv = p[i];
+  float gv = g[i] * grad_scale;
+  if (l1_coef != 0.f) gv += l1_coef * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f));
+  if (wd_mask && wd_mask[i]) gv = fmaf(weight_decay, pv, gv);
+  float mv = beta1 * m[i] + (1.f - beta1) * gv;
+  float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
+  m[i] = mv; v[i] = vv;
+  float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+  p[i] = pv - step_size * (mv / denom);
+}
+
+__global__ void abs_sum_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
+  __shared__ float red[33];
+  float a0 = 0.f, a1 = 0.f;
+  int64_t i = threadIdx.x;
+  for (; i + blockDim.x < n; i += 2 * (int64_t)blockDim.x) { a0 += fabsf(p[i]); a1 += fabsf(p[i + blockDim.x]); }
+  for (; i < n; i += blockDim.x) a0 += fabsf(p[i]);
+  float acc = block_sum(a0 + a1, red);
+  if (threadIdx.x == 0) out[0] += acc;
+}
+
+// =============================================================================================
+// K9: DeepAttMISL cluster pooling (model/backbone.py:105-117): per (bag, cluster) mean of rows
+// =============================================================================================
+constexpr int CL_CH = 128;
+__global__ void __launch_bounds__(256) seg_mean_id_partial_kernel(const float* __restrict__ v,
+                                                                  const int32_t* __restrict__ cid,
+                                                                  const int32_t* __restrict__ offsets, int width,
+                                                                  int ncl, float* __restrict__ part,
+                                                                  int32_t* __restrict__ part_cnt) {
+  extern __shared__ float sm[];  // [ncl][width] sums
+  __shared__ int cnt_s[64];
+  __shared__ int cid_s[CL_CH];
+  int b = blockIdx.y, chunk = blockIdx.x;
+  int beg = offsets[b] + chunk * CL_CH, end = min(offsets[b + 1], beg + CL_CH);
+  if (beg >= offsets[b + 1]) return;
+  int nrows = end - beg;
+  for (int i = threadIdx.x; i < ncl * width; i += blockDim.x) sm[i] = 0.f;
+  if (threadIdx.x < ncl) cnt_s[threadIdx.x] = 0;
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x) cid_s[r] = cid[beg + r];
+  __syncthreads();
+  // each thread owns a fixed set of columns -> no conflicts while rows are visited in order
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    for (int r = 0; r < nrows; ++r) {
+      int k = cid_s[r];
+      if (k >= 0 && k < ncl) sm[k * width + c] += v[(size_t)(beg + r) * width + c];
+    }
+  }
+  if (threadIdx.x == 0)
+    for (int r = 0; r < nrows; ++r) { int k = cid_s[r]; if (k >= 0 && k < ncl) cnt_s[k]++; }
+  __syncthreads();
+  size_t o = ((size_t)(offsets[b] / CL_CH + b + chunk)) * ncl;
+  for (int i = threadIdx.x; i < ncl * width; i += blockDim.x) part[o * width + i] = sm[i];
+  if (threadIdx.x < ncl) part_cnt[o + threadIdx.x] = cnt_s[threadIdx.x];
+}
+__global__ void seg_mean_id_final_kernel(const float* __restrict__ part, const int32_t* __restrict__ part_cnt,
+                                         const int32_t* __restrict__ offsets, int width, int ncl,
+                                         float* __restrict__ out, int32_t* __restrict__ counts) {
+  int b = blockIdx.x / ncl, k = blockIdx.x % ncl;
+  int len = offsets[b + 1] - offsets[b];
+  int nch = (len + CL_CH - 1) / CL_CH;
+  int cnt = 0;
+  const size_t pbase = (size_t)(offsets[b] / CL_CH + b);
+  for (int ch = 0; ch < nch; ++ch) cnt += part_cnt[(pbase + ch) * ncl + k];
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float t = 0.f;
+    for (int ch = 0; ch < nch; ++ch) t += part[((pbase + ch) * ncl + k) * width + c];
+    out[((size_t)b * ncl + k) * width + c] = cnt > 0 ? t / (float)cnt : 0.f;  // zeros for an empty cluster (backbone.py:114-115)
+  }
+  if (threadIdx.x == 0) counts[b * ncl + k] = cnt;
+}
+__global__ void seg_mean_id_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ v,
+                                       const int32_t* __restrict__ cid, const int32_t* __restrict__ offsets,
+                                       const int32_t* __restrict__ counts, int rows, int bags, int width, int ncl,
+                                       int relu_mask, float* __restrict__ d_v) {
+  int row = blockIdx.x;
+  int b = bag_of_row(offsets, bags, row);
+  int k = cid[row];
+  bool ok = k >= 0 && k < ncl;
+  float inv = ok ? 1.0f / (float)max(counts[b * ncl + k], 1) : 0.f;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float g = ok ? d_out[((size_t)b * ncl + k) * width + c] * inv : 0.f;
+    if (relu_mask && !(v[(size_t)row * width + c] > 0.f)) g = 0.f;
+    d_v[(size_t)row * width + c] = g;
+  }
+}
+
+// =============================================================================================
+// region <-> patch index map (tools/big_to_small_patching.py:40-46,59-76)
+// =============================================================================================
+__global__ void region_index_map_kernel(const int64_t* __restrict__ c2, int m, int psize, int scale, double* __restrict__ c1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int s2 = scale * scale;
+  if (i >= m * s2) return;
+  int k = i / s2, within = i % s2;
+  int jj = within / scale, ii = within % scale;  // j outer (y), i inner (x)
+  c1[2 * (size_t)i + 0] = (double)c2[2 * (size_t)k + 0] + (double)(ii * psize);
+  c1[2 * (size_t)i + 1] = (double)c2[2 * (size_t)k + 1] + (double)(jj * psize);
+}
+__global__ void region_of_rows_kernel(int rows, int scale, int32_t* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  int s2 = scale * scale;
+  out[3 * (size_t)n + 0] = n / s2;
+  out[3 * (size_t)n + 1] = (n % s2) / scale;
+  out[3 * (size_t)n + 2] = n % scale;
+}
+
+}  // namespace advmil
+
+// =============================================================================================
+// C ABI for the kernels of this file
+// =============================================================================================
+using namespace advmil;
+
+extern "C" int advmil_disc_loss(const float* f_real, const float* f_fake, const uint8_t* real_mask, int32_t bags,
+                                int32_t which, float n_real, float n_fake, float* loss_out, float* d_real, float* d_fake,
+                                void* stream) {
+  ADVMIL_REQUIRE(bags > 0 && which >= 0 && which <= 2 && n_fake > 0.f, "disc_loss: bad arguments");
+  disc_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(f_real, f_fake, real_mask, bags, which, n_real, n_fake, loss_out, d_real, d_fake);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_gen_loss(const float* pred, const float* t, const float* e, const uint8_t* visible,
+                               const float* f_fake, int32_t bags, float n_visible, float n_fake, float coef_gan,
+                               float alpha, float gamma, int32_t norm, float* losses, float* d_pred, float* d_fake,
+                               void* stream) {
+  ADVMIL_REQUIRE(bags > 0 && n_fake > 0.f && (norm == 0 || norm == 1), "gen_loss: bad arguments");
+  gen_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, t, e, visible, f_fake, bags, n_visible, n_fake, coef_gan, alpha, gamma, norm, losses, d_pred, d_fake);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_adam_step(float* param, const float* grad, float* m, float* v, const uint8_t* wd_mask, int64_t n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, float l1_coef,
+                                int32_t step, float grad_scale, void* stream) {
+  ADVMIL_REQUIRE(n >= 0 && step >= 1, "adam_step: bad arguments");
+  if (n == 0) return ADVMIL_OK;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, wd_mask, n, (float)(lr / bc1), beta1,
+                                                                beta2, eps, weight_decay, l1_coef,
+                                                                (float)(1.0 / sqrt(bc2)), grad_scale);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream) {
+  if (n <= 0) return ADVMIL_OK;
+  abs_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p, n, out);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" size_t advmil_segment_mean_workspace_bytes(int32_t rows, int32_t bags, int32_t width, int32_t num_clusters) {
+  size_t nparts = (size_t)rows / CL_CH + bags + 1;
+  return align_up(nparts * num_clusters * width * sizeof(float), 256) + align_up(nparts * num_clusters * sizeof(int32_t), 256);
+}
+
+extern "C" int advmil_segment_mean_by_id_fwd(const float* v, const int32_t* cid, const int32_t* offsets,
+                                             const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width,
+                                             int32_t num_clusters, float* out, int32_t* counts, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  ADVMIL_REQUIRE(num_clusters > 0 && num_clusters <= 64 && width > 0, "segment_mean_by_id: bad arguments");
+  ADVMIL_REQUIRE((size_t)num_clusters * width * sizeof(float) <= 96 * 1024, "segment_mean_by_id: clusters*width too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t nparts = (size_t)rows / CL_CH + bags + 1;
+  Workspace ws(workspace, workspace_bytes);
+  float* part = ws.take<float>(nparts * num_clusters * width);
+  int32_t* part_cnt = ws.take<int32_t>(nparts * num_clusters);
+  if (!part || !part_cnt) { set_error("segment_mean_by_id: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  int maxlen = 0;
+  for (int b = 0; b < bags; ++b) maxlen = max(maxlen, offsets_host[b + 1] - offsets_host[b]);
+  int maxchunks = max(1, cdiv(maxlen, CL_CH));
+  size_t smem = (size_t)num_clusters * width * sizeof(float);
+  if (smem > 48 * 1024)
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(seg_mean_id_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  seg_mean_id_partial_kernel<<<dim3(maxchunks, bags), 256, smem, st>>>(v, cid, offsets, width, num_clusters, part, part_cnt);
+  ADVMIL_CHECK_LAUNCH();
+  seg_mean_id_final_kernel<<<bags * num_clusters, 128, 0, st>>>(part, part_cnt, offsets, width, num_clusters, out, counts);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_segment_mean_by_id_bwd(const float* d_out, const float* v, const int32_t* cid,
+                                             const int32_t* offsets, const int32_t* counts, int32_t rows, int32_t bags,
+                                             int32_t width, int32_t num_clusters, int32_t relu_mask, float* d_v,
+                                             void* stream) {
+  if (rows == 0) return ADVMIL_OK;
+  seg_mean_id_bwd_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, d_v);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_region_index_map(const int64_t* coords_l2, int32_t m, int32_t patch_size, int32_t scale,
+                                       double* coords_l1, void* stream) {
+  ADVMIL_REQUIRE(m >= 0 && scale > 0, "region_index_map: bad arguments");
+  if (m == 0) return ADVMIL_OK;
+  region_index_map_kernel<<<cdiv((long long)m * scale * scale, 256), 256, 0, (cudaStream_t)stream>>>(coords_l2, m, patch_size, scale, coords_l1);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_region_of_rows(int32_t rows, int32_t scale, int32_t* out, void* stream) {
+  if (rows == 0) return ADVMIL_OK;
+  region_of_rows_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(rows, scale, out);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}

@@ -1,0 +1,261 @@
+/*
+ * advmil_b200 — C ABI of the B200-native AdvMIL hot path (libadvmil_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (liupei101/AdvMIL) is pure Python/PyTorch and has no FFI of its own; each entry point below
+ * replaces the named reference interface (file:line relative to the reference root) and is bound
+ * from Python with ctypes (advmil_b200/_lib.py; INTEGRATION.md shows the stub).
+ *
+ * Conventions:
+ *   - every entry point returns int: 0 = ok, non-zero = AdvmilStatus; never throws;
+ *   - no entry point allocates device memory: all outputs, saved activations and scratch are
+ *     caller-owned (sizes via advmil_*_workspace_bytes);
+ *   - every entry point takes an explicit cudaStream_t (passed as void*) and is asynchronous;
+ *   - all device tensors are dense row-major fp32 unless stated; "bags" are packed:
+ *     x[rows, C] with int32 offsets[bags+1] (offsets[0] = 0, offsets[bags] = rows), which is
+ *     dataset/PatchWSI.py:65-94's per-patient [N,1024] tensors concatenated.
+ *   - dropout sites take either an injected keep-mask (uint8, 1 = keep; parity tests) or, when the
+ *     mask pointer is NULL and train != 0, a counter-based in-kernel generator keyed by `seed`
+ *     (forward and backward regenerate identical bits).
+ */
+#ifndef ADVMIL_B200_H_
+#define ADVMIL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum AdvmilStatus {
+  ADVMIL_OK = 0,
+  ADVMIL_ERR_INVALID = 1,   /* bad argument / unsupported shape (reference: AssertionError / ValueError) */
+  ADVMIL_ERR_CUDA = 2,      /* a CUDA runtime call or launch failed; advmil_last_error() has the text */
+  ADVMIL_ERR_WORKSPACE = 3, /* workspace too small */
+  ADVMIL_ERR_NO_DEVICE = 4  /* no sm_100 device */
+} AdvmilStatus;
+
+#define ADVMIL_ABI_VERSION 1
+#if defined(__GNUC__)
+#define ADVMIL_API __attribute__((visibility("default")))
+#else
+#define ADVMIL_API
+#endif
+
+/* GEMM engine selection for the N-row contractions (K1/K2/K5 and their backward):
+ *   0 = fp32 FFMA tiles (exact-fp32 mode, rtol 1e-5 parity)
+ *   1 = tcgen05 kind::tf32 single pass, TMA-fed, TMEM accumulators (fast mode, <= 2e-2 parity)
+ *   2 = tcgen05 3xTF32 error-compensated (fp32-grade accuracy on tensor cores)                  */
+typedef enum AdvmilPrecision { ADVMIL_FP32 = 0, ADVMIL_TF32 = 1, ADVMIL_TF32X3 = 2 } AdvmilPrecision;
+
+/* ---- packed bags ------------------------------------------------------------------------- */
+typedef struct AdvmilBags {
+  const float* x;              /* [rows, C] device */
+  const int32_t* offsets;      /* [bags+1] device */
+  const int32_t* offsets_host; /* [bags+1] host copy (grid sizing, validation) */
+  int32_t rows, bags, C, max_bag_rows;
+} AdvmilBags;
+
+/* ---- generator: ABMIL encoder + noise head (model/GANSurv.py:13-49, model/backbone.py:54-86,
+ *      model/backbone_utils.py:11-29, model/model_utils.py:116-133) ------------------------- */
+typedef struct AdvmilGenParams {
+  const float *W1, *b1;       /* backbone.attention_net.0        [h,C],[h]  */
+  const float *Wa, *ba;       /* ...attention_net.3.attention_a.0 [h,h],[h] */
+  const float *Wb, *bb;       /* ...attention_net.3.attention_b.0 [h,h],[h] */
+  const float *wc, *bc;       /* ...attention_net.3.attention_c   [1,h],[1] */
+  const float *Wrho, *brho;   /* backbone.rho.0                   [o,h],[o] (NULL for DeepAttMISL) */
+  const float *W0, *b0;       /* MLPs.0.0  [hid, o*(1+noise0)],[hid] */
+  const float *Wl, *bl;       /* MLPs.1.0  [1, hid*(1+noise1)],[1]   */
+  int32_t C, h, o, hid;
+  int32_t noise0, noise1;     /* gen_noi_noise "n0-n1" (config/cfg_nlst.yaml:30) */
+  int32_t out_scale;          /* 0 none, 1 sigmoid, 2 exp (GANSurv.py:43-48) */
+  float p_backbone, p_head;   /* dropout probabilities 0.25 / gen_dropout */
+} AdvmilGenParams;
+
+typedef struct AdvmilGenGrads { /* same tensors as AdvmilGenParams, written (not accumulated) */
+  float *W1, *b1, *Wa, *ba, *Wb, *bb, *wc, *bc, *Wrho, *brho, *W0, *b0, *Wl, *bl;
+  float *dx; /* optional [rows,C]: gradient w.r.t. the bag features (NULL = skipped; the WSI features never need it,
+                the DeepAttMISL cluster path does for its pooled cluster rows) */
+} AdvmilGenGrads;
+
+typedef struct AdvmilGenActs {
+  float* h;     /* [rows,h]   relu(+dropout) of the projection; pooled tensor (backbone.py:81-84) */
+  float* ab;    /* [rows,abw] tanh|sigmoid gate activations, packed column order (see advmil_gate_packed_width); NULL = not saved */
+  float* s;     /* [rows] attention logits */
+  float* w;     /* [rows] softmax weights within each bag */
+  float* z;     /* [bags,h] pooled */
+  float* H;     /* [bags,o] rho output (post dropout) */
+  float* H1;    /* [bags,hid] MLPs.0 output (post dropout) */
+  float* pre;   /* [bags] last-layer pre-activation */
+  float* pred;  /* [bags] output */
+  const float* noise0; /* [bags,o]   or NULL (zero / unused) */
+  const float* noise1; /* [bags,hid] or NULL */
+  const float* h_eval; /* optional [rows,h]: eval-mode h of the same x and W1 (dropout is applied to it instead of recomputing K1) */
+  const uint8_t *mask_h, *mask_a, *mask_b, *mask_rho, *mask_mlp0; /* optional injected keep masks */
+  uint64_t seed;
+  int32_t train;       /* 0 eval (no dropout), 1 train */
+  int32_t precision;   /* AdvmilPrecision */
+  void* workspace; size_t workspace_bytes;
+} AdvmilGenActs;
+
+/* ---- discriminator: RLIP (model/GANSurv.py:71-105, model/model_utils.py:157-210,
+ *      model/backbone_utils.py:31-77,129-168) ----------------------------------------------- */
+typedef struct AdvmilDiscParams {
+  const float *Wc, *bc;        /* net_pair_one.embedding.conv [d,C(,1,1)],[d] */
+  const float *ln_g, *ln_b;    /* net_pair_one.embedding.norm [d],[d] */
+  const float *F1a_w, *F1a_b;  /* net_pair_one.fc1.0 [d/2,d] */
+  const float *F1b_w, *F1b_b;  /* net_pair_one.fc1.3 [d,d/2] */
+  const float *Pg_w, *Pg_b;    /* net_pair_one.pool.fc1.0   [d,d] (tanh branch)    */
+  const float *Ps_w, *Ps_b;    /* net_pair_one.pool.score.0 [d,d] (sigmoid branch) */
+  const float *Pc_w, *Pc_b;    /* net_pair_one.pool.fc2     [1,d],[1] */
+  const float *F2a_w, *F2a_b;  /* net_pair_one.fc2.0 [d/2,d] */
+  const float *F2b_w, *F2b_b;  /* net_pair_one.fc2.3 [d,d/2] */
+  const float *T1_w, *T1_b;    /* net_pair_two.0.0 [t1,1] */
+  const float *T2_w, *T2_b;    /* net_pair_two.1.0 [t2,t1] */
+  const float *Pr_w, *Pr_b;    /* prj_layer [1,d] (or NULL) */
+  int32_t C, d, t1, t2;
+  int32_t inner_instance;      /* 1 = 'instance' (RLIP), 0 = 'bag' (GANSurv.py:92-98) */
+  int32_t prj_path;            /* 0 none, 1 'x', 2 'y' */
+  float p;                     /* disc_netx_dropout */
+  float ln_eps;
+} AdvmilDiscParams;
+
+typedef struct AdvmilDiscGrads {
+  float *Wc, *bc, *ln_g, *ln_b, *F1a_w, *F1a_b, *F1b_w, *F1b_b, *Pg_w, *Pg_b, *Ps_w, *Ps_b, *Pc_w, *Pc_b,
+        *F2a_w, *F2a_b, *F2b_w, *F2b_b, *T1_w, *T1_b, *T2_w, *T2_b, *Pr_w, *Pr_b;
+} AdvmilDiscGrads;
+
+typedef struct AdvmilEmbedActs {      /* K5+K6: region embedding */
+  float* emb;    /* [rows/16, d] */
+  float* y_pre;  /* [rows, d] pre-LayerNorm projection, NULL = not saved (no D-param backward) */
+  int32_t precision;
+  void* workspace; size_t workspace_bytes;
+} AdvmilEmbedActs;
+
+typedef struct AdvmilHeadActs {       /* K7+K8: region MLP, GAPool, bag MLP, time embedding, inner product */
+  const float* emb; /* [R,d] */
+  const float* t;   /* [bags] time fed to D (real label or generator output) */
+  float* f1;    /* [R,d/2] fc1 hidden (post relu+dropout) */
+  float* fi;    /* [R,d] instance embeddings (post fc1; quirk A.4#2) */
+  float* ab;    /* [R,abw] GAPool gate activations packed */
+  float* rep;   /* [R] GAPool logits */
+  float* attn;  /* [R] GAPool softmax */
+  float* bagv;  /* [bags,d] attention-pooled */
+  float* fbar;  /* [bags,d] mean_r fi */
+  float* g1;    /* [bags,d/2] fc2 hidden (post relu+dropout) */
+  float* hx;    /* [bags,d] */
+  float* u1;    /* [bags,t1] */
+  float* ht;    /* [bags,t2] */
+  float* out;   /* [bags] */
+  const uint8_t *mask_fc1, *mask_ga, *mask_gs, *mask_fc2;
+  uint64_t seed;
+  int32_t train;
+  void* workspace; size_t workspace_bytes;
+} AdvmilHeadActs;
+
+/* ---- version / diagnostics ---------------------------------------------------------------- */
+ADVMIL_API int advmil_abi_version(void);
+ADVMIL_API const char* advmil_last_error(void);
+/* sizeof() of the ABI structs, for binding self-checks: which = 0 Bags, 1 GenParams, 2 GenGrads, 3 GenActs,
+ * 4 DiscParams, 5 DiscGrads, 6 EmbedActs, 7 HeadActs */
+ADVMIL_API size_t advmil_abi_sizeof(int which);
+/* counts kernel launches issued by this library since the last reset (bench "gpu_launches") */
+ADVMIL_API int64_t advmil_launch_count(int reset);
+/* packed gate width: 128 * ceil(D/64) columns; column of tanh_j = 128*(j/64)+j%64, sigmoid_j = +64 */
+ADVMIL_API int32_t advmil_gate_packed_width(int32_t D);
+
+/* ---- generator (replaces Generator.forward, model/GANSurv.py:30-49, with backbone ABMIL.forward,
+ *      model/backbone.py:79-86) over packed bags; backward = autograd of the same (K10) ---------- */
+ADVMIL_API size_t advmil_generator_workspace_bytes(const AdvmilGenParams* p, int32_t rows, int32_t bags, int32_t backward);
+ADVMIL_API int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* bags, AdvmilGenActs* acts, void* stream);
+/* d_pred: [bags] dL/dpred. Writes all parameter gradients (summed over the bags).
+ * Backbone-only mode: when p->W0 == NULL the forward stops at H (ABMIL.forward, model/backbone.py:79-86) and d_pred is
+ * dL/dH [bags,o]. */
+ADVMIL_API int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* bags, const AdvmilGenActs* acts,
+                         const float* d_pred, AdvmilGenGrads* grads, void* stream);
+/* Head only: S noise draws per bag from one backbone pass (replaces the 30 redundant Generator forwards of
+ * MyHandler.test_model, model/model_handler.py:624-636).  H: [bags,o]; noise1: [S,bags,hid]; out: [S,bags] */
+ADVMIL_API int advmil_generator_sample(const AdvmilGenParams* p, const float* H, const float* noise0, const float* noise1,
+                            int32_t bags, int32_t samples, float* out, void* stream);
+
+/* ---- discriminator ------------------------------------------------------------------------ */
+/* K5+K6 (AVGPoolPatchEmbedding.forward, model/backbone_utils.py:158-168): emb[r] = mean_{k<16} relu(LN(x[16r+k]Wc^T+bc)).
+ * Every bag length must be a multiple of 16 (backbone_utils.py:65) else ADVMIL_ERR_INVALID. */
+ADVMIL_API size_t advmil_disc_workspace_bytes(const AdvmilDiscParams* p, int32_t rows, int32_t bags, int32_t backward);
+ADVMIL_API int advmil_disc_embed_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilEmbedActs* acts, void* stream);
+/* d_emb [R,d] -> dWc, dbc, dln_g, dln_b (accumulate != 0 adds into grads) */
+ADVMIL_API int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilEmbedActs* acts,
+                          const float* d_emb, AdvmilDiscGrads* grads, int32_t accumulate, void* stream);
+/* K7+K8 (EmbedXLayer.forward model/model_utils.py:202-210 after the embedding; PrjDiscriminator.forward
+ * model/GANSurv.py:89-105) */
+ADVMIL_API int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilHeadActs* acts, void* stream);
+/* d_out [bags] -> d_emb [R,d] (NULL = skip), d_t [bags] (NULL = skip), parameter grads (NULL = skip).
+ * accumulate != 0 adds into d_emb and grads instead of overwriting. */
+ADVMIL_API int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilHeadActs* acts,
+                         const float* d_out, float* d_emb, float* d_t, AdvmilDiscGrads* grads,
+                         int32_t accumulate, void* stream);
+
+/* ---- DeepAttMISL cluster pooling (model/backbone.py:105-117): hc[b,c] = mean_{n in bag b, cid[n]==c} v[n,:], zeros if empty.
+ * v: [rows,width]; cid: [rows] int32 in [0,num_clusters); out: [bags*num_clusters,width]; counts: [bags*num_clusters] int32 */
+ADVMIL_API size_t advmil_segment_mean_workspace_bytes(int32_t rows, int32_t bags, int32_t width, int32_t num_clusters);
+ADVMIL_API int advmil_segment_mean_by_id_fwd(const float* v, const int32_t* cid, const int32_t* offsets, const int32_t* offsets_host,
+                                  int32_t rows, int32_t bags, int32_t width, int32_t num_clusters, float* out,
+                                  int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+/* d_v[n,:] = d_out[bag(n), cid[n], :] / count, optionally masked by (v > 0) (ReLU before the mean) */
+ADVMIL_API int advmil_segment_mean_by_id_bwd(const float* d_out, const float* v, const int32_t* cid, const int32_t* offsets,
+                                  const int32_t* counts, int32_t rows, int32_t bags, int32_t width, int32_t num_clusters,
+                                  int32_t relu_mask, float* d_v, void* stream);
+
+/* ---- stage-level entry points (also used by the DeepAttMISL path and by the kernel unit tests) ---- */
+/* y = act(x W^T + b): act 0 none, 1 relu; optional dropout (p, mask or seed/site) -> y [rows,N].  W: [N,K] */
+ADVMIL_API int advmil_linear_fwd(const float* x, const float* W, const float* b, int32_t rows, int32_t K, int32_t N, int32_t act,
+                      float p_drop, const uint8_t* mask, uint64_t seed, int32_t site, int32_t train,
+                      int32_t precision, float* y, void* stream);
+/* dX = dY W (optionally * (y_fwd>0)/(1-p) when relu_y != NULL), dW = dY^T X, db = colsum(dY); any output may be NULL */
+ADVMIL_API int advmil_linear_bwd(const float* dY, const float* X, const float* W, int32_t rows, int32_t K, int32_t N,
+                      float* dX, float* dW, float* db, int32_t accumulate, int32_t precision,
+                      void* workspace, size_t workspace_bytes, void* stream);
+ADVMIL_API size_t advmil_linear_bwd_workspace_bytes(int32_t rows, int32_t K, int32_t N);
+/* gated attention scores (Attn_Net_Gated.forward, model/backbone_utils.py:24-29) */
+ADVMIL_API int advmil_gated_score_fwd(const float* v, const float* Wa, const float* ba, const float* Wb, const float* bb,
+                           const float* wc, const float* bc, int32_t rows, int32_t L, int32_t D, float p_drop,
+                           const uint8_t* mask_a, const uint8_t* mask_b, uint64_t seed, int32_t site, int32_t train,
+                           int32_t precision, float* ab, float* s, void* workspace, size_t workspace_bytes, void* stream);
+/* segmented softmax + attention pooling (model/backbone.py:82-84): w = softmax over each bag of s; z[b] = sum w v */
+ADVMIL_API int advmil_seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets, const int32_t* offsets_host,
+                                int32_t rows, int32_t bags, int32_t width, float* w, float* z, float* mean,
+                                void* workspace, size_t workspace_bytes, void* stream);
+ADVMIL_API size_t advmil_seg_pool_workspace_bytes(int32_t rows, int32_t bags, int32_t width);
+
+/* ---- region <-> patch index map (tools/big_to_small_patching.py:40-46,59-76) ---------------- */
+/* coords_l2 [m,2] int64 (device) -> coords_l1 [16m,2] float64 (device): row 16k+4j+i = c_k + (i*psize, j*psize) */
+ADVMIL_API int advmil_region_index_map(const int64_t* coords_l2, int32_t m, int32_t patch_size, int32_t scale, double* coords_l1, void* stream);
+/* region id (n / scale^2) and in-region (j,i) of every level-1 row: out [rows,3] int32 */
+ADVMIL_API int advmil_region_of_rows(int32_t rows, int32_t scale, int32_t* out, void* stream);
+
+/* ---- losses (loss/utils.py:21-41,182-208) with gradients, over the per-bag scores of one step ---- */
+/* which: 0 bce (the reference's non-standard form), 1 hinge, 2 wasserstein.  real_mask[b] != 0 marks bags that
+ * contribute a real pair (e==1 && label visible, model_handler.py:373-377).  n_real / n_fake are GLOBAL counts (data
+ * parallel: sums over ranks) used as the mean denominators.  Outputs: loss_out[0] += local contribution (caller zeroes). */
+ADVMIL_API int advmil_disc_loss(const float* f_real, const float* f_fake, const uint8_t* real_mask, int32_t bags, int32_t which,
+                     float n_real, float n_fake, float* loss_out, float* d_real, float* d_fake, void* stream);
+/* G loss: recon (norm 0=l1,1=l2; alpha; gamma) over visible bags + coef_gan * (-mean f_fake).  Outputs: losses[3] =
+ * {recon, gen, total-without-L1} local contributions, d_pred (recon part) and d_fake. */
+ADVMIL_API int advmil_gen_loss(const float* pred, const float* t, const float* e, const uint8_t* visible, const float* f_fake,
+                    int32_t bags, float n_visible, float n_fake, float coef_gan, float alpha, float gamma, int32_t norm,
+                    float* losses, float* d_pred, float* d_fake, void* stream);
+
+/* ---- fused multi-tensor Adam on a flat parameter buffer (torch.optim.Adam semantics as configured at
+ *      model/model_handler.py:104-107, optim/optim_factory.py:25-37): g += wd[i]*p (L2) + l1*sign(p) (loss_reg_l1,
+ *      loss/utils.py:6-14), then Adam with bias correction.  wd_mask: per-element uint8 (1 = decayed). -------------- */
+ADVMIL_API int advmil_adam_step(float* param, const float* grad, float* m, float* v, const uint8_t* wd_mask, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, float l1_coef, int32_t step,
+                     float grad_scale, void* stream);
+/* sum |p| over a flat buffer (the L1 term's value), out[0] += result */
+ADVMIL_API int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVMIL_B200_H_ */

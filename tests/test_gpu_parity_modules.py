@@ -1,0 +1,186 @@
+"""GPU parity: the CUDA path behind the reference's module surface vs. the CPU oracle and the golden fixtures
+produced by the live reference.  Tolerance (north_star): fp32 mode rtol 1e-5 — applied as |a-e| <= 1e-5*|e| +
+1e-5*max|e| per tensor (entries that cancel to ~0 are bounded norm-wise); index work bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import advmil_oracle as O
+from tests.util import (assert_close, build_D, build_G, d_masks, g_masks, golden, grad_floor, sub, to_dev_masks)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _load(mod, sd):
+    mod.load_state_dict({k: v.clone() for k, v in sd.items()})
+
+
+def _cmp_grads(mod, sdr, rtol=RTOL):
+    floor = grad_floor([None if v.grad is None else v.grad.numpy() for v in sdr.values()])
+    for k, p in mod.named_parameters():
+        ref = sdr[k].grad
+        assert p.grad is not None, k
+        if ref is None or float(ref.abs().max()) < 1e-7:
+            # unused branch (autograd gives None) or mathematically-zero gradient (softmax-shift bias of the gate)
+            assert float(p.grad.abs().max()) < 1e-6, k
+            continue
+        assert_close(p.grad.cpu(), ref, rtol, name="grad " + k, atol=floor)
+
+
+def _cmp_grads_golden(mod, g, rtol=RTOL):
+    names = [k for k, _ in mod.named_parameters()]
+    floor = grad_floor([g["grad." + k] for k in names])
+    for k, p in mod.named_parameters():
+        ref = g["grad." + k]
+        if float(np.abs(ref).max()) < 1e-7:
+            assert float(p.grad.abs().max()) < 1e-6, k
+            continue
+        assert_close(sub(p.grad), ref, rtol, "grad " + k, atol=floor)
+
+
+@pytest.mark.parametrize("dims,N,train,seed,nonneg", [
+    ((1024, 384, 384), 1600, False, 1, False),
+    ((1024, 384, 384), 640, True, 2, False),
+    ((64, 32, 32), 208, False, 3, False),
+    ((64, 32, 32), 96, True, 4, True),
+    ((1024, 384, 384), 1000, True, 21, True),   # N not a multiple of 16 or 128: the generator accepts any length
+])
+def test_generator_vs_oracle(dims, N, train, seed, nonneg):
+    C, h, o = dims
+    sd = O.synth_state_dict(O.G_SHAPES(C, h, o), seed)
+    G = build_G(dims)
+    _load(G, sd)
+    x = O.synth_bag(N, seed, C, nonneg)
+    noise = torch.tensor(np.random.default_rng(seed + 7).uniform(size=(1, o // 2)), dtype=torch.float32)
+    masks = g_masks(N, h, o, seed * 10) if train else None
+    G.train(train)
+    if train:
+        G._inject_masks = to_dev_masks(masks)
+    bags_x = x.cuda().unsqueeze(0)
+    from advmil_b200 import ops
+    pred = G.forward_packed(ops.PackedBags.from_single(bags_x), noise=[None, noise.cuda()])
+    pred.sum().backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    og = O.generator_forward(sdr, x, [None, noise], (0, 1), masks)
+    og["pred"].sum().backward()
+    assert_close(pred.detach().cpu(), og["pred"].detach(), RTOL, "pred")
+    _cmp_grads(G, sdr)
+
+
+@pytest.mark.parametrize("name", ["g_abmil_eval_full", "g_abmil_train_full", "g_abmil_eval_small", "g_abmil_train_small"])
+def test_generator_vs_golden(name):
+    g = golden(name)
+    C, h, o, N, train, seed, nonneg = [int(v) for v in g["cfg"]]
+    sd = O.synth_state_dict(O.G_SHAPES(C, h, o), seed)
+    G = build_G((C, h, o))
+    _load(G, sd)
+    x = O.synth_bag(N, seed, C, bool(nonneg))
+    noise = torch.tensor(np.random.default_rng(seed + 7).uniform(size=(1, o // 2)), dtype=torch.float32)
+    G.train(bool(train))
+    if train:
+        G._inject_masks = to_dev_masks(g_masks(N, h, o, seed * 10))
+    from advmil_b200 import ops
+    pred = G.forward_packed(ops.PackedBags.from_single(x.cuda()), noise=[None, noise.cuda()])
+    pred.sum().backward()
+    assert_close(pred.detach().cpu(), g["pred"], RTOL, "pred")
+    _cmp_grads_golden(G, g)
+
+
+@pytest.mark.parametrize("C,d,N,train,seed,iprd,prj", [
+    (1024, 128, 1600, False, 5, "instance", "x"),
+    (1024, 128, 640, True, 6, "instance", "x"),
+    (64, 32, 208, False, 7, "instance", "x"),
+    (64, 32, 96, True, 8, "bag", "x"),
+    (64, 32, 96, True, 9, "instance", "y"),
+    (1024, 128, 16, True, 10, "instance", "x"),     # a single region
+])
+def test_discriminator_vs_oracle(C, d, N, train, seed, iprd, prj):
+    ty = (64, 128) if d == 128 else (d // 2, d)
+    sd = O.synth_state_dict(O.D_SHAPES(C, d, ty), seed + 50)
+    D = build_D(C, d, iprd, prj)
+    _load(D, sd)
+    x = O.synth_bag(N, seed, C)
+    masks = d_masks(N // 16, d, seed * 10 + 5) if train else None
+    D.train(train)
+    if train:
+        D._inject_masks = to_dev_masks(masks)
+    t = torch.tensor([[0.37]], device="cuda", requires_grad=True)
+    out = D(x.cuda().unsqueeze(0), t)
+    out.sum().backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    t2 = torch.tensor([[0.37]], requires_grad=True)
+    od = O.prjdisc_forward(sdr, x, t2, masks, iprd, prj)
+    od["out"].sum().backward()
+    assert_close(out.detach().cpu(), od["out"].detach(), RTOL, "out", atol_scale=max(1e-2, float(od["out"].abs().max())))
+    assert_close(t.grad.cpu(), t2.grad, RTOL, "dt", atol_scale=max(1e-3, float(t2.grad.abs().max())))
+    _cmp_grads(D, sdr)
+
+
+@pytest.mark.parametrize("name", ["d_rlip_eval_full", "d_rlip_train_full", "d_rlip_eval_small", "d_bag_train_small"])
+def test_discriminator_vs_golden(name):
+    g = golden(name)
+    C, d, N, train, seed, inst, prjx = [int(v) for v in g["cfg"]]
+    ty = (64, 128) if d == 128 else (d // 2, d)
+    sd = O.synth_state_dict(O.D_SHAPES(C, d, ty), seed + 50)
+    D = build_D(C, d, "instance" if inst else "bag", "x" if prjx else "y")
+    _load(D, sd)
+    x = O.synth_bag(N, seed, C)
+    D.train(bool(train))
+    if train:
+        D._inject_masks = to_dev_masks(d_masks(N // 16, d, seed * 10 + 5))
+    t = torch.tensor([[0.37]], device="cuda", requires_grad=True)
+    out = D(x.cuda().unsqueeze(0), t)
+    out.sum().backward()
+    assert_close(out.detach().cpu(), g["out"], RTOL, "out", atol_scale=max(1e-2, float(np.abs(g["out"]).max())))
+    assert_close(t.grad.cpu(), g["dt"], RTOL, "dt", atol_scale=max(1e-3, float(np.abs(g["dt"]).max())))
+    _cmp_grads_golden(D, g)
+
+
+def test_discriminator_rejects_ragged_region():
+    D = build_D(64, 32)
+    x = torch.randn(1, 40, 64, device="cuda")
+    with pytest.raises(AssertionError):
+        D(x, torch.tensor([[0.5]], device="cuda"))
+
+
+def test_packed_equals_single():
+    """Packed variable-length bags give the same per-bag result as one call per bag (bit-identical launches per bag
+    are not required; tolerance as above)."""
+    from advmil_b200 import ops
+    dims = (64, 32, 32)
+    G = build_G(dims).eval()
+    D = build_D(64, 32).eval()
+    _load(G, O.synth_state_dict(O.G_SHAPES(*dims), 1))
+    _load(D, O.synth_state_dict(O.D_SHAPES(64, 32, (16, 32)), 2))
+    Ns = [48, 208, 16, 1024, 96]
+    xs = [O.synth_bag(n, 30 + i, 64).cuda() for i, n in enumerate(Ns)]
+    noise = torch.rand(len(Ns), 16).cuda()
+    bags = ops.PackedBags.from_list(xs)
+    with torch.no_grad():
+        pp = G.forward_packed(bags, noise=[None, noise])
+        fp = D.forward_packed(bags, pp)
+        for i, x in enumerate(xs):
+            p1 = G.forward_packed(ops.PackedBags.from_single(x), noise=[None, noise[i:i + 1]])
+            f1 = D.forward_packed(ops.PackedBags.from_single(x), p1)
+            assert_close(pp[i].cpu(), p1.cpu().reshape(-1), RTOL, f"pred bag {i}")
+            assert_close(fp[i].cpu(), f1.cpu().reshape(-1), RTOL, f"score bag {i}", atol_scale=1e-2)
+
+
+@pytest.mark.parametrize("name", ["g_cluster_full", "g_cluster_empty_small"])
+def test_cluster_generator_vs_golden_and_oracle(name):
+    g = golden(name)
+    C, h, N, seed, empty = [int(v) for v in g["cfg"]]
+    sd = O.synth_state_dict(O.G_CLUSTER_SHAPES(C, h), seed + 20)
+    G = build_G((C, h, h), mode="cluster").eval()
+    _load(G, sd)
+    x = O.synth_bag(N, seed, C)
+    cid = torch.tensor(g["cid"], dtype=torch.float32)
+    noise = torch.tensor(np.random.default_rng(seed + 7).uniform(size=(1, h // 2)), dtype=torch.float32)
+    # drive through the reference-shaped forward: patch the noise draw
+    G.draw_noise = lambda nb, dev, zero: [None, noise.to(dev)]
+    pred = G(x.cuda().unsqueeze(0), cid.cuda())
+    pred.sum().backward()
+    assert_close(pred.detach().cpu(), g["pred"], RTOL, "pred")
+    _cmp_grads_golden(G, g)
