@@ -78,6 +78,8 @@ SYMBOLS = {
     "advmil_abi_sizeof": (_sz, [C.c_int]),
     "advmil_launch_count": (_i64, [C.c_int]),
     "advmil_gate_packed_width": (_i32, [_i32]),
+    "advmil_profile_enable": (C.c_int, [C.c_int]),
+    "advmil_profile_read": (C.c_int, [_P(C.c_double), _P(C.c_int64), _i32]),
     "advmil_generator_workspace_bytes": (_sz, [_P(GenParams), _i32, _i32, _i32]),
     "advmil_generator_fwd": (C.c_int, [_P(GenParams), _P(Bags), _P(GenActs), _vp]),
     "advmil_generator_bwd": (C.c_int, [_P(GenParams), _P(Bags), _P(GenActs), _vp, _P(GenGrads), _vp]),
@@ -104,6 +106,9 @@ SYMBOLS = {
     "advmil_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _i32, _f, _vp]),
     "advmil_abs_sum": (C.c_int, [_vp, _i64, _vp, _vp]),
 }
+
+PROF_TAGS = ["proj_fwd", "gate_fwd", "pool_fwd", "embed_fwd", "pool_gate_bwd", "bwd_data", "bwd_w_gate", "bwd_w_proj",
+             "ln_bwd", "bwd_w_embed", "colsum", "dropout"]
 
 _lib = None
 

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 #include <vector>
 #include "stages.cuh"
 
@@ -18,6 +19,26 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-stage event profiling ------------------------------------------------------------------
+struct ProfRec { int tag; cudaEvent_t a, b; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec*> g_prof;
+ProfScope::ProfScope(int tag_, cudaStream_t st_) : tag(tag_), st(st_), rec(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec* r = new ProfRec{tag, nullptr, nullptr};
+  if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+  cudaEventRecord(r->a, st);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  ProfRec* r = (ProfRec*)rec;
+  cudaEventRecord(r->b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
 
 __global__ void scale_offsets_kernel(const int32_t* __restrict__ in, int n, int div, int32_t* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,6 +87,20 @@ extern "C" int64_t advmil_launch_count(int reset) {
   return v;
 }
 extern "C" int32_t advmil_gate_packed_width(int32_t D) { return gate_width(D); }
+extern "C" int advmil_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); return ADVMIL_OK; }
+extern "C" int advmil_profile_read(double* ms, int64_t* counts, int32_t ntags) {
+  ADVMIL_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < ntags; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  for (ProfRec* r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r->a, r->b) == cudaSuccess && r->tag < ntags) { ms[r->tag] += t; counts[r->tag] += 1; }
+    cudaEventDestroy(r->a); cudaEventDestroy(r->b);
+    delete r;
+  }
+  g_prof.clear();
+  return ADVMIL_OK;
+}
 
 // =============================================================================================
 // generator
@@ -106,11 +141,13 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
   Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train);
   Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train);
   Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train);
-  if (a->h_eval) ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, st));
-  else ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st));
+  if (a->h_eval) { ProfScope ps(PROF_DROPOUT, st); ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, st)); }
+  else { ProfScope ps(PROF_PROJ, st); ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st)); }
   ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
-  ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, a->s, part, a->precision, st));
-  ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st));
+  { ProfScope ps(PROF_GATE, st);
+    ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, a->s, part, a->precision, st)); }
+  { ProfScope ps(PROF_POOL, st);
+    ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st)); }
   ADVMIL_TRY(gen_head_fwd(*p, a->z, a->noise0, a->noise1, nb, 1, drho, dmlp0, a->H, a->H1, a->pre, a->pred, st));
   return ADVMIL_OK;
 }
@@ -151,16 +188,17 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   if (p->Wrho) ADVMIL_TRY(outer_sum(dHpre, a->z, h, nullptr, 0, nb, o, g->Wrho, g->brho, 0, st));
   // pooling + gate
   ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
-  ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, 0, pgws, st));
+  { ProfScope ps(PROF_POOL_BWD, st);
+    ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, 0, pgws, st)); }
   BwdDataExtras ex;
   ex.w = a->w; ex.dz = dz; ex.offsets = bags->offsets; ex.bags = nb; ex.relu_src = a->h; ex.ld_src = h; ex.inv_keep = ik_bb;
-  ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st));
-  ADVMIL_TRY(bwd_weight(dAB, a->h, rows, abw, h, dWp, 0, bwws, prec, st));
-  ADVMIL_TRY(colsum(dAB, rows, abw, abw, dbp, 0, csws, st));
+  { ProfScope ps(PROF_BWD_DATA, st); ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st)); }
+  { ProfScope ps(PROF_BWD_W_GATE, st); ADVMIL_TRY(bwd_weight(dAB, a->h, rows, abw, h, dWp, 0, bwws, prec, st)); }
+  { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dAB, rows, abw, abw, dbp, 0, csws, st)); }
   ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st));
   // first layer
-  ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st));
-  ADVMIL_TRY(colsum(dhpre, rows, h, h, g->b1, 0, csws, st));
+  { ProfScope ps(PROF_BWD_W_PROJ, st); ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st)); }
+  { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dhpre, rows, h, h, g->b1, 0, csws, st)); }
   if (g->dx) {
     BwdDataExtras exx;
     ADVMIL_TRY(bwd_data(dhpre, p->W1, rows, h, C, g->dx, exx, prec, st));
@@ -204,6 +242,7 @@ extern "C" size_t advmil_disc_workspace_bytes(const AdvmilDiscParams* p, int32_t
 extern "C" int advmil_disc_embed_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilEmbedActs* a, void* stream) {
   ADVMIL_REQUIRE(p && a && a->emb, "disc_embed_fwd: null argument");
   ADVMIL_TRY(check_bags(bags, p->C, true));
+  ProfScope ps(PROF_EMBED, (cudaStream_t)stream);
   return region_embed_fwd(bags->x, p->Wc, p->bc, p->ln_g, p->ln_b, bags->rows, p->C, p->d, p->ln_eps, a->y_pre, a->emb,
                           a->precision, (cudaStream_t)stream);
 }
@@ -219,8 +258,9 @@ extern "C" int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags
   WS_TAKE(d_y, float, (size_t)rows * d);
   WS_TAKE(lnws, float, (size_t)row_chunks(rows) * 3 * d);
   WS_TAKE(bwws, float, bwd_weight_ws_floats(rows, d, C));
-  ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws, st));
-  ADVMIL_TRY(bwd_weight(d_y, bags->x, rows, d, C, g->Wc, accumulate, bwws, a->precision, st));
+  { ProfScope ps(PROF_LN_BWD, st);
+    ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws, st)); }
+  { ProfScope ps(PROF_BWD_W_EMBED, st); ADVMIL_TRY(bwd_weight(d_y, bags->x, rows, d, C, g->Wc, accumulate, bwws, a->precision, st)); }
   return ADVMIL_OK;
 }
 

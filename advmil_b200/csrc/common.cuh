@@ -45,6 +45,28 @@ void count_launch(int n = 1);
     if (_s != ADVMIL_OK) return _s;                                                    \
   } while (0)
 
+// ---- optional per-stage CUDA-event profiling (bench.py roofline) ---------------------------------
+enum ProfTag : int {
+  PROF_PROJ = 0,        // K1  x.W1^T + bias + ReLU (+dropout)
+  PROF_GATE = 1,        // K2  gated attention scores
+  PROF_POOL = 2,        // K3  segmented softmax + pooling
+  PROF_EMBED = 3,       // K5+K6 projection + LN + ReLU + region mean
+  PROF_POOL_BWD = 4,    // pooling + gate backward (row stream)
+  PROF_BWD_DATA = 5,    // dh = dAB.[Wa;Wb] (+pool term, ReLU mask)
+  PROF_BWD_W_GATE = 6,  // d[Wa;Wb] = dAB^T h
+  PROF_BWD_W_PROJ = 7,  // dW1 = dh^T x
+  PROF_LN_BWD = 8,      // LN/ReLU/region-mean backward (row stream)
+  PROF_BWD_W_EMBED = 9, // dWc = dy^T x
+  PROF_COLSUM = 10,     // bias gradients
+  PROF_DROPOUT = 11,    // dropout re-application on cached eval activations
+  PROF_NTAGS = 12
+};
+struct ProfScope {
+  int tag; cudaStream_t st; void* rec;
+  ProfScope(int tag, cudaStream_t st);
+  ~ProfScope();
+};
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -1,0 +1,203 @@
+"""Packed, pinned, offset-indexed bag storage and an asynchronous device feeder.
+
+Rebuilds the role of the reference's WSIPatch dataset + DataLoader + `.cuda()` (dataset/PatchWSI.py:65-94;
+model/model_handler.py:158-165,315-316) for the B200 path:
+
+  reference : per-slide torch.load -> torch.cat per patient -> default_collate -> pageable, synchronous H2D per bag
+  here      : bags of one optimiser step are packed once into a pinned [rows, C] buffer + int32 offsets
+              (`PinnedStep`), and `DeviceFeeder` copies step k+1 on a side stream while step k computes
+              (ring of device buffers, event hand-off, no host sync in the steady state).
+
+Patch mode yields (feats, zeros(1)) and cluster mode (feats, cluster ids) like WSIPatch.__getitem__ (:82-94).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..ops import PackedBags
+
+
+@dataclass
+class PinnedStep:
+    """The bags of one optimiser step (`bp_every_batch` of them, config/cfg_nlst.yaml:71) in pinned host memory."""
+    x: torch.Tensor            # [rows, C] float32, pinned
+    lengths: List[int]
+    t: torch.Tensor            # [bags] float32, pinned
+    e: torch.Tensor            # [bags] float32, pinned
+    idx: torch.Tensor          # [bags] int32 (dataset indices)
+    visible: torch.Tensor      # [bags] uint8 (label_visible_mask, model_handler.py:591-596)
+    cluster_id: Optional[torch.Tensor] = None   # [rows] int32 (cluster mode)
+
+    @property
+    def nbytes(self) -> int:
+        return self.x.numel() * 4 + (self.t.numel() + self.e.numel()) * 4 + self.visible.numel()
+
+
+def _pin(t: torch.Tensor) -> torch.Tensor:
+    try:
+        return t.pin_memory()
+    except RuntimeError:      # no CUDA runtime (CPU-only container): keep pageable memory, same layout
+        return t
+
+
+def pack_step(bags: Sequence[torch.Tensor], labels: Sequence[Sequence[float]], idx: Optional[Sequence[int]] = None,
+              visible: Optional[Sequence[bool]] = None, cluster_ids: Optional[Sequence[torch.Tensor]] = None,
+              require_multiple_of: int = 16, pin: bool = True) -> PinnedStep:
+    """Packs per-patient feature tensors ([N_i, C], as WSIPatch returns them after torch.cat, :79) into one buffer."""
+    assert len(bags) == len(labels) and len(bags) > 0
+    lengths = [int(b.shape[0]) for b in bags]
+    for i, n in enumerate(lengths):
+        assert n > 0, f"bag {i} is empty"
+        if require_multiple_of:
+            assert n % require_multiple_of == 0, \
+                f"bag {i} has {n} instances: the RLIP discriminator needs a multiple of 16 (model/backbone_utils.py:65)"
+    C = int(bags[0].shape[1])
+    rows = sum(lengths)
+    x = torch.empty(rows, C, dtype=torch.float32)
+    if pin:
+        x = _pin(x)
+    off = 0
+    for b in bags:
+        assert b.shape[1] == C
+        x[off:off + b.shape[0]].copy_(b.to(torch.float32))     # dataset/PatchWSI.py:79 `.to(torch.float)`
+        off += b.shape[0]
+    lab = torch.tensor(np.asarray(labels, dtype=np.float32).reshape(len(bags), 2))
+    mk = (lambda v: _pin(v)) if pin else (lambda v: v)
+    cid = None
+    if cluster_ids is not None:
+        cid = mk(torch.cat([torch.as_tensor(c).reshape(-1).to(torch.int32) for c in cluster_ids]))
+        assert cid.shape[0] == rows, "one cluster id per instance (dataset/PatchWSI.py:93)"
+    return PinnedStep(
+        x=x, lengths=lengths, t=mk(lab[:, 0].contiguous()), e=mk(lab[:, 1].contiguous()),
+        idx=torch.tensor(list(range(len(bags))) if idx is None else list(idx), dtype=torch.int32),
+        visible=mk(torch.tensor([1 if (visible is None or v) else 0 for v in (visible or [True] * len(bags))],
+                                dtype=torch.uint8)),
+        cluster_id=cid)
+
+
+def group_steps(n_items: int, bags_per_step: int) -> List[List[int]]:
+    """Reference batching: bags are collected 16 at a time; a trailing partial group is dropped each epoch
+    (model_handler.py:321)."""
+    return [list(range(s, s + bags_per_step)) for s in range(0, n_items - bags_per_step + 1, bags_per_step)]
+
+
+def shard_bags_balanced(lengths: Sequence[int], world: int) -> List[List[int]]:
+    """Data-parallel partition of one step's bags by greedy row balancing (bag sizes vary 100x).
+    Deterministic: largest first, ties by index; every rank gets at least one bag when len(lengths) >= world."""
+    order = sorted(range(len(lengths)), key=lambda i: (-lengths[i], i))
+    loads = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        empties = [r for r in range(world) if not out[r]]
+        remaining = len(lengths) - sum(len(o) for o in out)
+        if empties and remaining <= len(empties):
+            r = empties[0]
+        else:
+            r = min(range(world), key=lambda k: (loads[k], k))
+        out[r].append(i)
+        loads[r] += lengths[i]
+    return [sorted(o) for o in out]
+
+
+@dataclass
+class DeviceStep:
+    bags: PackedBags
+    t: torch.Tensor
+    e: torch.Tensor
+    visible: torch.Tensor
+    idx: torch.Tensor
+    cluster_id: Optional[torch.Tensor]
+    h2d_bytes: int
+    counts: tuple = (0.0, 0.0, 0.0)   # local (n_real, n_fake, n_visible) from the host labels (no device sync needed)
+    _slot: int = -1
+
+
+class DeviceFeeder:
+    """Double-buffered asynchronous H2D of PinnedSteps: `for step in DeviceFeeder(steps): ...`.
+
+    Slot s holds a device buffer sized for the largest step; the copy of item k+depth-1 is issued on a side stream as soon
+    as the consumer releases slot (k-1) (an event recorded on the compute stream when the next item is requested)."""
+
+    def __init__(self, steps: Iterable[PinnedStep], device="cuda", depth: int = 2):
+        self.steps = steps
+        self.device = torch.device(device)
+        self.depth = max(2, depth)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._xbuf: List[Optional[torch.Tensor]] = [None] * self.depth
+        self._ready = [torch.cuda.Event() for _ in range(self.depth)]
+        self._free = [torch.cuda.Event() for _ in range(self.depth)]
+
+    def _issue(self, slot: int, st: PinnedStep) -> DeviceStep:
+        rows, C = st.x.shape
+        buf = self._xbuf[slot]
+        if buf is None or buf.shape[0] < rows or buf.shape[1] != C:
+            buf = torch.empty(rows, C, dtype=torch.float32, device=self.device)
+            self._xbuf[slot] = buf
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._free[slot])          # consumer finished with this slot
+            xd = buf[:rows]
+            xd.copy_(st.x, non_blocking=True)
+            t = st.t.to(self.device, non_blocking=True)
+            e = st.e.to(self.device, non_blocking=True)
+            vis = st.visible.to(self.device, non_blocking=True)
+            cid = None if st.cluster_id is None else st.cluster_id.to(self.device, non_blocking=True)
+            bags = PackedBags(xd, st.lengths)                        # offsets: small H2D on the copy stream
+            self._ready[slot].record(self.copy_stream)
+        n_real = float(((st.e == 1) & (st.visible != 0)).sum())
+        counts = (n_real, float(len(st.lengths)), float(st.visible.sum()))
+        return DeviceStep(bags, t, e, vis, st.idx, cid, st.nbytes, counts, slot)
+
+    def __iter__(self) -> Iterator[DeviceStep]:
+        it = iter(self.steps)
+        pending: List[DeviceStep] = []
+        k = 0
+        for _ in range(self.depth - 1):
+            st = next(it, None)
+            if st is None:
+                break
+            pending.append(self._issue(k % self.depth, st))
+            k += 1
+        prev: Optional[DeviceStep] = None
+        while pending:
+            cur = pending.pop(0)
+            torch.cuda.current_stream().wait_event(self._ready[cur._slot])
+            if prev is not None:
+                self._free[prev._slot].record(torch.cuda.current_stream())
+            st = next(it, None)
+            if st is not None:
+                pending.append(self._issue(k % self.depth, st))
+                k += 1
+            yield cur
+            prev = cur
+        if prev is not None:
+            self._free[prev._slot].record(torch.cuda.current_stream())
+
+
+def synthetic_steps(n_steps: int, bags_per_step: int, rows_per_bag, C: int = 1024, seed: int = 42, pin: bool = True,
+                    event_rate: float = 0.347, labeled_ratio: float = 1.0, distinct: Optional[int] = None) -> List[PinnedStep]:
+    """Synthetic NLST-shaped steps: randn features (model_stats.py:93), t~U(0,1), e~Bernoulli(0.347).
+    rows_per_bag: int or callable(rng) -> int (multiple of 16).  `distinct` < n_steps re-uses buffers cyclically so a long
+    run does not need n_steps GiB of host memory."""
+    distinct = n_steps if distinct is None else min(distinct, n_steps)
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    made: List[PinnedStep] = []
+    for _ in range(distinct):
+        lens = [int(rows_per_bag(rng)) if callable(rows_per_bag) else int(rows_per_bag) for _ in range(bags_per_step)]
+        bags = [torch.randn(n, C, generator=g) for n in lens]
+        labels = [(float(rng.uniform(0.02, 0.98)), float(rng.uniform() < event_rate)) for _ in lens]
+        vis = [bool(rng.uniform() < labeled_ratio) for _ in lens]
+        made.append(pack_step(bags, labels, visible=vis, pin=pin))
+    return [made[i % distinct] for i in range(n_steps)]
+
+
+def loguniform_rows(lo: int = 1024, hi: int = 100000):
+    """cfg3 bag sizes: log-uniform in [lo, hi], rounded down to a multiple of 16."""
+    def draw(rng):
+        n = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
+        return max(16, n // 16 * 16)
+    return draw

@@ -1,0 +1,222 @@
+"""Fused adversarial step over packed bags: one D update + one G update, the semantics of
+MyHandler._update_disc + _update_gen (reference model/model_handler.py:349-498), without the handler's redundant work:
+
+  * the D-step generator forward (eval) and the G-step generator forward (train) share the x.W1^T projection
+    (G's parameters do not change in between; dropout is applied to the cached eval activations);
+  * real and fake pairs of the D step share one region-embedding pass (the embedding has no dropout);
+  * no boolean-mask copies of x (model_handler.py:376,400,461), no per-bag .cpu()/.item() syncs, no empty_cache;
+  * the G step asks D only for dL/dt and never accumulates D-parameter gradients;
+  * parameters and gradients live in flat fp32 buffers: one NCCL all-reduce and one fused Adam launch per network.
+
+Data parallel: every rank holds a shard of the step's bags; losses are normalised by GLOBAL pair counts so that the
+sum of per-rank gradients is the single-process gradient; L1 / weight decay are applied once, inside the Adam kernel,
+after the all-reduce.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import check
+from .utils.func import next_dropout_seed
+
+
+class FlatParams:
+    """Re-homes a module's parameters as views of one flat fp32 buffer (and a matching flat gradient buffer)."""
+
+    def __init__(self, module: nn.Module, tensors: Sequence[Optional[torch.Tensor]], weight_decay_rule: bool):
+        named = {id(p): n for n, p in module.named_parameters()}
+        self.order = [t for t in tensors if t is not None]
+        dev = self.order[0].device
+        total = sum((t.numel() + 3) // 4 * 4 for t in self.order)  # keep every tensor 16-byte aligned
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.wd_mask = torch.zeros(total, dtype=torch.uint8, device=dev)
+        self.views, self.grad_views = [], []
+        off = 0
+        for t in self.order:
+            n = t.numel()
+            v = self.flat[off:off + n].view_as(t)
+            v.copy_(t.data)
+            t.data = v
+            self.views.append(v)
+            self.grad_views.append(self.grad[off:off + n].view_as(t))
+            name = named.get(id(t), "")
+            # add_weight_decay rule (reference optim/optim_factory.py:25-37): 1-D tensors and *.bias get no decay
+            if weight_decay_rule and not (t.dim() == 1 or name.endswith(".bias")):
+                self.wd_mask[off:off + n] = 1
+            off += (n + 3) // 4 * 4
+        self.total = total
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.step_count = 0
+
+    def grads_for(self, tensors: Sequence[Optional[torch.Tensor]]):
+        idx = {id(t): i for i, t in enumerate(self.order)}
+        return [None if t is None else self.grad_views[idx[id(t)]] for t in tensors]
+
+    def adam(self, lr, weight_decay=0.0, l1_coef=0.0, betas=(0.9, 0.999), eps=1e-8):
+        lib = _lib.load()
+        self.step_count += 1
+        check(lib.advmil_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                   self.wd_mask.data_ptr() if weight_decay else None, self.total, lr, betas[0], betas[1],
+                                   eps, weight_decay, l1_coef, self.step_count, 1.0,
+                                   torch.cuda.current_stream().cuda_stream), "advmil_adam_step")
+
+
+class AdvStep:
+    def __init__(self, netG, netD, lr_g=8e-5, lr_d=8e-5, weight_decay_g=5e-4, coef_gan=0.004, coef_l1=1e-5,
+                 loss_d="bce", recon_norm="l1", recon_alpha=0.0, recon_gamma=0.0, precision="fp32",
+                 process_group=None):
+        assert netG.backbone.kind == "abmil", "the fused step covers the ABMIL generator"
+        self.netG, self.netD = netG, netD
+        self.gcfg, self.dcfg = netG.config(), netD.config()
+        self.gparams, self.dparams = netG.gen_params(), netD.disc_params()
+        self.G = FlatParams(netG, self.gparams, weight_decay_rule=True)
+        self.D = FlatParams(netD, self.dparams, weight_decay_rule=False)
+        self.ggrads, self.dgrads = self.G.grads_for(self.gparams), self.D.grads_for(self.dparams)
+        self.lr_g, self.lr_d, self.wd_g = lr_g, lr_d, weight_decay_g
+        self.coef_gan, self.coef_l1 = coef_gan, coef_l1
+        self.loss_d = {"bce": 0, "hinge": 1, "wasserstein": 2}[loss_d]
+        self.recon = ({"l1": 0, "l2": 1}[recon_norm], recon_alpha, recon_gamma)
+        self.precision = ops.PRECISIONS[precision]
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+
+    # ---------------------------------------------------------------------------------------------
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def step(self, bags: ops.PackedBags, t: torch.Tensor, e: torch.Tensor, visible: torch.Tensor,
+             noise_d: Optional[torch.Tensor] = None, noise_g: Optional[torch.Tensor] = None,
+             masks_d_real=None, masks_d_fake=None, masks_g=None, global_counts=None, return_debug=False) -> Dict:
+        """t, e: [bags] float32 device; visible: [bags] uint8 device (label_visible_mask).  noise_*: [bags, hid] device
+        (drawn like utils/func.generate_noise when None).  Returns device tensors only (no host sync)."""
+        lib = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        dev = bags.x.device
+        nb = bags.bags
+        G, D = self.netG, self.netD
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = t.reshape(-1).contiguous().float()
+        e = e.reshape(-1).contiguous().float()
+        visible = visible.reshape(-1).to(torch.uint8).contiguous()
+        real_mask = ((e == 1) & (visible != 0)).to(torch.uint8)          # model_handler.py:373-375
+        if global_counts is None:
+            cnt = torch.stack([real_mask.sum(), torch.tensor(nb, device=dev), visible.sum()]).float()
+            self._allreduce(cnt)
+            n_real, n_fake, n_vis = [float(v) for v in cnt.tolist()]
+        else:
+            n_real, n_fake, n_vis = [float(v) for v in global_counts]
+        hid = self.gcfg.hid
+        if noise_d is None:
+            noise_d = G.draw_noise(nb, dev, False)[1]
+        if noise_g is None:
+            noise_g = G.draw_noise(nb, dev, False)[1]
+
+        # ---------------- D step: D.train / G.eval (model_handler.py:355-356) ----------------
+        ga = ops.generator_forward(self.gcfg, self.gparams, bags, None, noise_d, train=False, precision=self.precision,
+                                   save=False)
+        pred_d = ga["pred"]
+        emb = ops.disc_embed_forward(self.dcfg, self.dparams, bags, self.precision, save=True)
+        d_emb = torch.empty_like(emb["emb"])
+        losses = torch.zeros(8, **f32)   # [0] dis_loss, [1] recon, [2] gen, [3] total w/o L1, [4] sum|W_G|
+        d_real = torch.empty(nb, **f32)
+        d_fake = torch.empty(nb, **f32)
+        hf = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb["emb"], pred_d, train=True,
+                                   seed=next_dropout_seed(), masks=masks_d_fake)
+        hr = None
+        if n_real > 0:
+            hr = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb["emb"], t, train=True,
+                                       seed=next_dropout_seed(), masks=masks_d_real)
+        check(lib.advmil_disc_loss(None if hr is None else hr["out"].data_ptr(), hf["out"].data_ptr(),
+                                   real_mask.data_ptr(), nb, self.loss_d, n_real, n_fake, losses.data_ptr(),
+                                   d_real.data_ptr(), d_fake.data_ptr(), st), "advmil_disc_loss")
+        ops.disc_head_backward(self.dcfg, self.dparams, bags, hf, d_fake, d_emb, None, self.dgrads, accumulate=False)
+        if hr is not None:
+            ops.disc_head_backward(self.dcfg, self.dparams, bags, hr, d_real, d_emb, None, self.dgrads, accumulate=True)
+        ops.disc_embed_backward(self.dcfg, self.dparams, bags, emb, d_emb, self.dgrads, accumulate=False)
+        self._allreduce(self.D.grad)
+        self.D.adam(self.lr_d)
+
+        # ---------------- G step: D.eval / G.train (model_handler.py:432-433) ----------------
+        gt = ops.generator_forward(self.gcfg, self.gparams, bags, None, noise_g, train=True, seed=next_dropout_seed(),
+                                   masks=masks_g, precision=self.precision, save=True, h_eval=ga["h"])
+        pred_g = gt["pred"]
+        emb2 = ops.disc_embed_forward(self.dcfg, self.dparams, bags, self.precision, save=False)
+        hg = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb2["emb"], pred_g, train=False)
+        d_pred = torch.empty(nb, **f32)
+        d_fake_g = torch.empty(nb, **f32)
+        norm, alpha, gamma = self.recon
+        check(lib.advmil_gen_loss(pred_g.data_ptr(), t.data_ptr(), e.data_ptr(), visible.data_ptr(), hg["out"].data_ptr(),
+                                  nb, n_vis, n_fake, self.coef_gan, alpha, gamma, norm, losses[1:].data_ptr(),
+                                  d_pred.data_ptr(), d_fake_g.data_ptr(), st), "advmil_gen_loss")
+        d_t = torch.empty(nb, **f32)
+        ops.disc_head_backward(self.dcfg, self.dparams, bags, hg, d_fake_g, None, d_t, None)
+        d_pred += d_t
+        grads, _ = None, None
+        self._gen_backward_into_flat(bags, gt, d_pred)
+        if self.coef_l1 > 1e-8:
+            check(lib.advmil_abs_sum(self.G.flat.data_ptr(), self.G.total, losses[4:].data_ptr(), st), "advmil_abs_sum")
+        self._allreduce(self.G.grad)
+        self.G.adam(self.lr_g, weight_decay=self.wd_g, l1_coef=self.coef_l1 if self.coef_l1 > 1e-8 else 0.0)
+        out = {"losses": losses, "pred_d": pred_d, "pred_g": pred_g, "f_fake_d": hf["out"], "f_fake_g": hg["out"],
+               "f_real": None if hr is None else hr["out"], "real_mask": real_mask}
+        if return_debug:
+            out.update({"gen_acts": gt, "emb": emb})
+        return out
+
+    def _gen_backward_into_flat(self, bags, acts, d_pred):
+        lib = _lib.load()
+        p = self.gcfg.c(self.gparams)
+        g = _lib.GenGrads()
+        for name, tns in zip(_lib.GEN_TENSORS, self.ggrads):
+            setattr(g, name, None if tns is None else tns.data_ptr())
+        g.dx = None
+        ws = torch.empty(lib.advmil_generator_workspace_bytes(C.byref(p), bags.rows, bags.bags, 1), dtype=torch.uint8,
+                         device=bags.x.device)
+        a = ops._gen_acts_struct(acts, ws)
+        b = bags.c()
+        check(lib.advmil_generator_bwd(C.byref(p), C.byref(b), C.byref(a), d_pred.data_ptr(), C.byref(g),
+                                       torch.cuda.current_stream().cuda_stream), "advmil_generator_bwd")
+
+    def loss_dict(self, out) -> Dict[str, float]:
+        """Host copy of the step's scalars (one sync): the values the handler prints (model_handler.py:413,486-494)."""
+        v = out["losses"].tolist()
+        l1 = self.coef_l1 * v[4] if self.coef_l1 > 1e-8 else 0.0
+        return {"dis_loss": v[0], "t_reg_loss": v[1], "gen_loss": v[2], "gen_total_loss": v[3] + l1}
+
+
+@torch.no_grad()
+def sample_inference(netG, netD, bags: ops.PackedBags, times_test_sample: int = 30, zero_noise: bool = False,
+                     precision: str = "fp32"):
+    """MyHandler.test_model for a batch of bags (reference model/model_handler.py:598-643) from ONE backbone pass:
+    y_hat [bags,1] with its own noise draw, f_fake = D(x, y_hat) [bags,1], dist_y_hat [bags,S,1] from S more draws,
+    avg_y_hat = lower median over the S draws (torch.median semantics)."""
+    cfg, params = netG.config(), netG.gen_params()
+    nb, dev = bags.bags, bags.x.device
+    n0, n1 = netG.draw_noise(nb, dev, zero_noise)
+    acts = ops.generator_forward(cfg, params, bags, n0, n1, train=False, precision=ops.PRECISIONS[precision], save=False)
+    y_hat = acts["pred"].reshape(nb, 1)
+    f_fake = netD.forward_packed(bags, y_hat)
+    res = {"y_hat": y_hat, "f_fake": f_fake}
+    if times_test_sample > 1:
+        S = times_test_sample
+        draws0, draws1 = [], []
+        for _ in range(S):      # same CPU-RNG call order as the reference's loop (:626-635)
+            a, b = netG.draw_noise(nb, dev, zero_noise)
+            draws0.append(a)
+            draws1.append(b)
+        N0 = None if draws0[0] is None else torch.stack(draws0)
+        N1 = None if draws1[0] is None else torch.stack(draws1)
+        ys = ops.generator_sample(cfg, params, acts["H"], N1, S, noise0=N0)      # [S, bags]
+        res["dist_y_hat"] = ys.transpose(0, 1).unsqueeze(-1).contiguous()        # [bags, S, 1]
+        res["avg_y_hat"] = torch.median(ys, dim=0)[0].reshape(nb, 1)
+    return res

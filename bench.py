@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bags/sec of one full adversarial G+D train step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32|tf32x3] [--impl reference]
+
+Workload (BASELINE.json configs[1]): AdvMIL-ABMIL, synthetic bags of 16,384 x 1024 fp32 features, 16 bags per optimiser
+step and per GPU (bp_every_batch, config/cfg_nlst.yaml:71) = 1 GiB of features per step per GPU (>> 126 MB L2, so no
+L2 flush is needed between iterations).  A "step" = _update_disc + _update_gen (model/model_handler.py:349-498): both
+forward/backward passes and both Adam updates.  Weak scaling: every rank owns 16 bags; gradients all-reduced (NCCL).
+
+Printed JSON line: value = device-timed bags/s with inputs resident in HBM; e2e = the same through the public API
+(DeviceFeeder + AdvStep) including the pinned-host -> device copy of every step's bags and a device -> host read of
+the losses; roofline = dominant kernel class from live CUDA events; cpu_baseline = the oracle port of the reference's
+CPU path on this box's host cores (bounded sample).  `--impl reference` times only that CPU path.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "bags/sec per G+D train step (16k x 1024 bags)"
+N_ROWS, C_IN, BAGS_PER_STEP = 16384, 1024, 16
+FLOP_PER_ROW = {  # algorithmic FLOPs per instance row per launch
+    "proj_fwd": 2 * 1024 * 384, "gate_fwd": 2 * 384 * 768 + 768, "embed_fwd": 2 * 1024 * 128,
+    "bwd_data": 2 * 768 * 384, "bwd_w_gate": 2 * 768 * 384, "bwd_w_proj": 2 * 384 * 1024, "bwd_w_embed": 2 * 128 * 1024,
+}
+BYTES_PER_ROW = {  # algorithmic HBM bytes per instance row per launch for the streaming kernels
+    "pool_fwd": 384 * 4 + 8, "pool_gate_bwd": 384 * 4 + 2 * 768 * 4 + 8, "ln_bwd": 2 * 128 * 4 + 32, "colsum": 576 * 4,
+    "dropout": 2 * 384 * 4,
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's PyTorch path; the reference is pure Python and cannot travel)
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(n_rows, bags_per_sample, steps, warmup, threads=None):
+    from oracle import advmil_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sdG = O.synth_state_dict(O.G_SHAPES(), 42)
+    sdD = O.synth_state_dict(O.D_SHAPES(), 43)
+    tr = O.CpuTrainer(sdG, sdD)
+    gen = torch.Generator().manual_seed(42)
+    bags = [torch.randn(n_rows, C_IN, generator=gen) for _ in range(bags_per_sample)]
+    ts, es = O.synth_labels(bags_per_sample, 42)
+    es[0] = 1.0
+    vis = [True] * bags_per_sample
+    times = []
+    for it in range(warmup + steps):
+        nzd = [torch.rand(1, 192) for _ in bags]
+        nzg = [torch.rand(1, 192) for _ in bags]
+        gm = [O.random_g_masks(n_rows, 384, 384, gen) for _ in bags]
+        dmr = [O.random_d_masks(n_rows // 16, 128, gen) for _ in bags]
+        dmf = [O.random_d_masks(n_rows // 16, 128, gen) for _ in bags]
+        t0 = time.perf_counter()
+        tr.step(bags, ts, es, vis, nzd, nzg, dmr, dmf, gm)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), float(np.min(times)), threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    mean_s, best_s, threads = cpu_reference_step_time(N_ROWS, 1, args.steps, args.warmup)
+    val = 1.0 / mean_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "bags/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "AdvMIL-ABMIL G+D step, synthetic bags 16384x1024 fp32 (configs[1])",
+                   "sample": "1 bag per step (the reference loops over bags one at a time, so bags/s is per-bag time)"},
+        "cpu_baseline": {"value": val, "unit": "bags/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 bag of 16384x1024 (D step + G step, Adam), torch CPU fp32"},
+        "e2e": {"value": val, "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="advmil_b200")
+    ap.add_argument("--precision", default=os.environ.get("ADVMIL_PRECISION", "fp32"))
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--bags", type=int, default=BAGS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert args.warmup >= 3, "timing rule: at least 3 warm-up steps"
+
+    import advmil_b200
+    from advmil_b200 import _lib, ops
+    from advmil_b200.dataset.packed import DeviceFeeder, synthetic_steps
+    from advmil_b200.step import AdvStep
+    from tests.util import build_D, build_G
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    advmil_b200.set_precision(args.precision)
+    torch.manual_seed(42)
+    G, D = build_G(device=dev), build_D(device=dev)
+    from advmil_b200.model.model_utils import init_weights
+    G.apply(init_weights)                                     # model_handler.py:81
+    engine = AdvStep(G, D, precision=args.precision)
+
+    # ---- synthetic bags in pinned host memory: 2 distinct steps (2 GiB) cycled ----
+    n_total = args.warmup + args.steps
+    steps = synthetic_steps(n_total, args.bags, args.rows, C_IN, seed=42 + rank, distinct=2)
+    counts = None  # global pair counts come from a tiny all-reduce inside step()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ================= (A) device-resident timing: `value` =================
+    resident = []
+    for st in steps[:2]:
+        resident.append((ops.PackedBags(st.x.to(dev), st.lengths), st.t.to(dev), st.e.to(dev), st.visible.to(dev)))
+    nz = [torch.rand(args.bags, 192, device=dev) for _ in range(2)]
+    hostcounts = [(float(((s.e == 1) & (s.visible != 0)).sum()) * world, float(args.bags * world), float(s.visible.sum()) * world)
+                  for s in steps[:2]]
+
+    def one_step(i):
+        b, t, e, v = resident[i % 2]
+        return engine.step(b, t, e, v, noise_d=nz[0], noise_g=nz[1], global_counts=hostcounts[i % 2])
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    lib.advmil_launch_count(1)
+    lib.advmil_profile_enable(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = one_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = int(lib.advmil_launch_count(0))
+    ntags = len(_lib.PROF_TAGS)
+    pms, pcnt = (C.c_double * ntags)(), (C.c_int64 * ntags)()
+    lib.advmil_profile_enable(0)
+    lib.advmil_profile_read(pms, pcnt, ntags)
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+    ms_dev = float(tms.item())
+    value = args.bags * world * args.steps / (ms_dev / 1e3)
+    losses = engine.loss_dict(out)
+
+    # ================= (B) end-to-end through the public API: pinned host -> device every step =================
+    feeder = DeviceFeeder(steps, device=dev, depth=2)
+    it = iter(feeder)
+    h2d = steps[0].nbytes
+    for i in range(args.warmup):
+        s = next(it)
+        o = engine.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)
+        engine.loss_dict(o)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2h = 0
+    for i in range(args.steps):
+        s = next(it)
+        o = engine.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)
+        host = o["losses"].tolist()      # device -> host read of the step's result
+        d2h = len(host) * 4
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = args.bags * world * args.steps / (float(ems.item()) / 1e3)
+
+    # ================= roofline of the dominant kernel class =================
+    peaks = load_peaks()
+    rows_per_launch = args.rows * args.bags
+    kern = {}
+    for i, tag in enumerate(_lib.PROF_TAGS):
+        if pcnt[i] == 0:
+            continue
+        avg_ms = pms[i] / pcnt[i]
+        ent = {"ms_per_launch": avg_ms, "launches": int(pcnt[i]), "share_of_step": pms[i] / ms}
+        if tag in FLOP_PER_ROW:
+            ent["tflops"] = FLOP_PER_ROW[tag] * rows_per_launch / (avg_ms * 1e-3) / 1e12
+        if tag in BYTES_PER_ROW:
+            ent["gbs"] = BYTES_PER_ROW[tag] * rows_per_launch / (avg_ms * 1e-3) / 1e9
+        kern[tag] = ent
+    top = max(kern, key=lambda k: kern[k]["share_of_step"]) if kern else None
+    roof = None
+    if top is not None:
+        if top in FLOP_PER_ROW:
+            roof = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": peaks["tflops"],
+                    "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peaks["tflops"], "traffic": None,
+                    "peak_source": peaks["src"] + " bf16 sustained"}
+        else:
+            roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": kern[top]["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"]}
+
+    # ================= CPU baseline (rank 0, N=1 only; bounded sample) =================
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        mean_s, best_s, threads = cpu_reference_step_time(args.rows, 1, 3, 1)
+        cpu = {"value": 1.0 / mean_s, "unit": "bags/s", "cores": threads, "kind": "port",
+               "sample": f"3 steps x 1 bag of {args.rows}x1024 after 1 warm-up (D step + G step + Adam), oracle port, torch CPU fp32"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
+            "config": {"workload": f"AdvMIL-ABMIL G+D step, {args.bags} synthetic bags of {args.rows}x1024 fp32 per step per GPU "
+                                   "(configs[1]); D step + G step + both Adam updates",
+                       "precision_mode": args.precision, "l2": "inputs (1 GiB/step) larger than L2; no flush",
+                       "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
+            "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+            "losses_last_step": losses,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

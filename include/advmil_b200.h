@@ -162,6 +162,15 @@ ADVMIL_API const char* advmil_last_error(void);
 ADVMIL_API size_t advmil_abi_sizeof(int which);
 /* counts kernel launches issued by this library since the last reset (bench "gpu_launches") */
 ADVMIL_API int64_t advmil_launch_count(int reset);
+/* per-stage CUDA-event profiling of the N-row kernels (bench.py roofline): enable, run steps, read.  read() synchronises
+ * the device and returns accumulated milliseconds / launch counts per AdvmilProfTag, then clears the records. */
+typedef enum AdvmilProfTag {
+  ADVMIL_PROF_PROJ = 0, ADVMIL_PROF_GATE = 1, ADVMIL_PROF_POOL = 2, ADVMIL_PROF_EMBED = 3, ADVMIL_PROF_POOL_BWD = 4,
+  ADVMIL_PROF_BWD_DATA = 5, ADVMIL_PROF_BWD_W_GATE = 6, ADVMIL_PROF_BWD_W_PROJ = 7, ADVMIL_PROF_LN_BWD = 8,
+  ADVMIL_PROF_BWD_W_EMBED = 9, ADVMIL_PROF_COLSUM = 10, ADVMIL_PROF_DROPOUT = 11, ADVMIL_PROF_NTAGS = 12
+} AdvmilProfTag;
+ADVMIL_API int advmil_profile_enable(int on);
+ADVMIL_API int advmil_profile_read(double* ms, int64_t* counts, int32_t ntags);
 /* packed gate width: 128 * ceil(D/64) columns; column of tanh_j = 128*(j/64)+j%64, sigmoid_j = +64 */
 ADVMIL_API int32_t advmil_gate_packed_width(int32_t D);
 

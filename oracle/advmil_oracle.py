@@ -473,3 +473,53 @@ def synth_labels(n_bags: int, seed: int, event_rate: float = 0.347):
 def synth_masks(shape, keep_prob: float, seed: int) -> Tensor:
     rng = np.random.default_rng(3000 + seed)
     return torch.tensor((rng.uniform(size=shape) < keep_prob).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------------------------
+# one full adversarial step on CPU (used as the timed CPU baseline and by the step parity tests)
+# ----------------------------------------------------------------------------------------------
+class CpuTrainer:
+    """Restates MyHandler's optimiser setup (model/model_handler.py:104-107; optim/optim_factory.py:25-37,76-77) and one
+    `_update_disc` + `_update_gen` round (:349-498) on top of the functional forward above, with torch.optim.Adam —
+    the same ATen kernels the reference's modules dispatch to on CPU."""
+
+    def __init__(self, sdG: SD, sdD: SD, lr: float = 8e-5, wd_g: float = 5e-4, coef_gan: float = 0.004,
+                 coef_l1: float = 1e-5, which: str = "bce"):
+        self.sdG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
+        self.sdD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+        no_decay = [v for k, v in self.sdG.items() if v.ndim == 1 or k.endswith(".bias")]
+        decay = [v for k, v in self.sdG.items() if not (v.ndim == 1 or k.endswith(".bias"))]
+        self.optG = torch.optim.Adam([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": wd_g}], lr=lr)
+        self.optD = torch.optim.Adam(list(self.sdD.values()), lr=lr, betas=(0.9, 0.999), weight_decay=0.0)
+        self.coef_gan, self.coef_l1, self.which = coef_gan, coef_l1, which
+
+    def step(self, bags, ts, es, visible, noise_d, noise_g, d_masks_real=None, d_masks_fake=None, g_masks=None):
+        nzd = [[None, n.reshape(1, -1)] for n in noise_d]
+        nzg = [[None, n.reshape(1, -1)] for n in noise_g]
+        d = disc_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzd, d_masks_real, d_masks_fake, self.which)
+        self.optD.zero_grad()
+        d["loss"].backward()
+        d_grads = {k: v.grad.clone() for k, v in self.sdD.items()}
+        self.optD.step()
+        g = gen_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzg, g_masks, self.coef_gan, self.coef_l1)
+        self.optG.zero_grad()
+        for v in self.sdD.values():
+            v.grad = None
+        g["loss"].backward()
+        g_grads = {k: v.grad.clone() for k, v in self.sdG.items()}
+        self.optG.step()
+        return {"dis_loss": float(d["loss"]), "gen_loss": float(g["gen_loss"]), "t_reg": float(g["t_reg"]),
+                "total": float(g["loss"]), "pred_d": d["pred"].detach(), "pred_g": g["pred"].detach(),
+                "fake_d": d["fake"].detach(), "fake_g": g["fake"].detach(), "d_grads": d_grads, "g_grads": g_grads}
+
+
+def random_g_masks(n_rows: int, h: int, o: int, gen: torch.Generator):
+    """Bernoulli keep masks for the five generator dropout sites (p = 0.25 backbone, 0.6 head)."""
+    r = lambda shp, keep: (torch.rand(shp, generator=gen) < keep).float()  # noqa: E731
+    return {"h": r((n_rows, h), 0.75), "a": r((n_rows, h), 0.75), "b": r((n_rows, h), 0.75), "rho": r((1, o), 0.75),
+            "mlp0": r((1, o // 2), 0.4)}
+
+
+def random_d_masks(n_regions: int, d: int, gen: torch.Generator):
+    r = lambda shp: (torch.rand(shp, generator=gen) < 0.75).float()  # noqa: E731
+    return {"fc1": r((n_regions, d // 2)), "ga": r((n_regions, d)), "gs": r((n_regions, d)), "fc2": r((1, d // 2))}

@@ -1,0 +1,111 @@
+"""GPU parity of the fused adversarial step (AdvStep) against fixtures produced by the live reference's modules,
+losses and optimisers (tests/golden/step_*.npz, oracle/make_golden.py:case_step) — D step + G step + both Adam
+updates, train-mode dropout with injected masks."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import advmil_oracle as O
+from tests.util import assert_close, build_D, build_G, d_masks, g_masks, golden, grad_floor, sub
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+ZERO_GRAD = ("pool.fc2.bias", "attention_c.bias")   # mathematically-zero gradients: Adam amplifies their rounding noise
+
+
+def _cat_masks(per_bag, keys):
+    return {k: torch.cat([m[k] for m in per_bag], dim=0).to(torch.uint8).contiguous().cuda() for k in keys}
+
+
+@pytest.mark.parametrize("name", ["step_small", "step_full"])
+def test_fused_step_vs_reference_golden(name):
+    from advmil_b200 import ops
+    from advmil_b200.step import AdvStep
+    g = golden(name)
+    C, h, o, d, seed, n_steps = [int(v) for v in g["cfg"][:6]]
+    Ns = [int(v) for v in g["cfg"][6:]]
+    B = len(Ns)
+    sdG = O.synth_state_dict(O.G_SHAPES(C, h, o), seed)
+    sdD = O.synth_state_dict(O.D_SHAPES(C, d, (64, 128) if d == 128 else (d // 2, d)), seed + 50)
+    G, D = build_G((C, h, o)), build_D(C, d)
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    eng = AdvStep(G, D)
+    bags = ops.PackedBags.from_list([O.synth_bag(n, seed + i, C).cuda() for i, n in enumerate(Ns)])
+    t, e = torch.tensor(g["t"]).cuda(), torch.tensor(g["e"]).cuda()
+    vis = torch.tensor(g["visible"].astype(np.uint8)).cuda()
+    for step in range(n_steps):
+        rng = np.random.default_rng(seed + 100 * step)
+        nzD = torch.tensor(np.concatenate([rng.uniform(size=(1, o // 2)) for _ in range(B)]), dtype=torch.float32).cuda()
+        nzG = torch.tensor(np.concatenate([rng.uniform(size=(1, o // 2)) for _ in range(B)]), dtype=torch.float32).cuda()
+        mr = _cat_masks([d_masks(Ns[i] // 16, d, seed + 1000 * step + 10 * i) for i in range(B)], ["fc1", "ga", "gs", "fc2"])
+        mf = _cat_masks([d_masks(Ns[i] // 16, d, seed + 1000 * step + 10 * i + 5) for i in range(B)], ["fc1", "ga", "gs", "fc2"])
+        mg = _cat_masks([g_masks(Ns[i], h, o, seed + 2000 * step + 10 * i) for i in range(B)], ["h", "a", "b", "rho", "mlp0"])
+        out = eng.step(bags, t, e, vis, noise_d=nzD, noise_g=nzG, masks_d_real=mr, masks_d_fake=mf, masks_g=mg)
+        L = eng.loss_dict(out)
+        assert_close(out["pred_d"].cpu(), g[f"pred_d{step}"], RTOL, f"pred_d step {step}")
+        assert_close(out["pred_g"].cpu(), g[f"pred_g{step}"], RTOL, f"pred_g step {step}")
+        assert_close(out["f_fake_d"].cpu(), g[f"fake_d{step}"], RTOL, f"fake_d step {step}", atol_scale=1e-1)
+        assert_close(out["f_fake_g"].cpu(), g[f"fake_g{step}"], RTOL, f"fake_g step {step}", atol_scale=1e-1)
+        assert abs(L["dis_loss"] - float(g[f"dis_loss{step}"])) < 2e-5
+        assert abs(L["gen_loss"] - float(g[f"gen_loss{step}"])) < 2e-5
+        assert abs(L["t_reg_loss"] - float(g[f"t_reg{step}"])) < 2e-5
+        assert abs(L["gen_total_loss"] - float(g[f"total{step}"])) < 2e-5
+        if step == 0:
+            dnames = [k for k, _ in D.named_parameters()]
+            floor = grad_floor([g["dgrad." + k] for k in dnames])
+            grads = dict(zip(dnames, [eng.dgrads[i] for i in _order(D, eng.dparams)]))
+            for k in dnames:
+                if k.endswith(ZERO_GRAD):
+                    continue
+                assert_close(sub(grads[k]), g["dgrad." + k], RTOL, "D grad " + k, atol=floor)
+            gnames = [k for k, _ in G.named_parameters()]
+            floor = grad_floor([g["ggrad." + k] for k in gnames])
+            ggr = dict(zip(gnames, [eng.ggrads[i] for i in _order(G, eng.gparams)]))
+            for k in gnames:
+                if k.endswith(ZERO_GRAD):
+                    continue
+                full = ggr[k].cpu() + 1e-5 * torch.sign(sdG[k])   # loss_reg_l1 (loss/utils.py:6-14) is folded into Adam
+                assert_close(sub(full), g["ggrad." + k], RTOL, "G grad " + k, atol=floor)
+    # parameters after the Adam updates (lr 8e-5): compare the UPDATE, |delta - delta_ref| <= 1e-3 * lr-scale
+    for k, p in G.named_parameters():
+        if k.endswith(ZERO_GRAD):
+            continue
+        assert_close(sub(p), g["gparam." + k], RTOL, "G param " + k, atol=8e-5 * n_steps * 2e-2)
+    for k, p in D.named_parameters():
+        if k.endswith(ZERO_GRAD):
+            continue
+        assert_close(sub(p), g["dparam." + k], RTOL, "D param " + k, atol=8e-5 * n_steps * 2e-2)
+
+
+def _order(mod, tensors):
+    """indices into `tensors` (engine order, Nones dropped) following mod.named_parameters() order"""
+    pos = {id(t): i for i, t in enumerate(tensors) if t is not None}
+    return [pos[id(p)] for _, p in mod.named_parameters()]
+
+
+def test_sample_inference_matches_oracle_and_lower_median():
+    from advmil_b200 import ops
+    from advmil_b200.step import sample_inference
+    dims = (1024, 384, 384)
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(*dims), 3), O.synth_state_dict(O.D_SHAPES(), 4)
+    G, D = build_G(dims).eval(), build_D().eval()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    Ns = [320, 640, 160]
+    xs = [O.synth_bag(n, 70 + i) for i, n in enumerate(Ns)]
+    torch.manual_seed(99)
+    res = sample_inference(G, D, ops.PackedBags.from_list([x.cuda() for x in xs]), times_test_sample=30)
+    # replay the same CPU RNG stream through the oracle: first draw -> y_hat, then 30 draws -> distribution
+    torch.manual_seed(99)
+    first = torch.rand(len(Ns), 192)
+    draws = [torch.rand(len(Ns), 192) for _ in range(30)]
+    for b, x in enumerate(xs):
+        y = O.generator_forward(sdG, x, [None, first[b:b + 1]], (0, 1))["pred"]
+        assert_close(res["y_hat"][b].cpu(), y.reshape(-1), RTOL, f"y_hat {b}")
+        f = O.prjdisc_forward(sdD, x, y)["out"]
+        assert_close(res["f_fake"][b].cpu(), f.reshape(-1), RTOL, f"f_fake {b}", atol_scale=1e-1)
+        dist = O.sample_times(sdG, x, [d_[b:b + 1] for d_ in draws])
+        assert_close(res["dist_y_hat"][b, :, 0].cpu(), dist, RTOL, f"dist {b}")
+        med = O.lower_median(dist)
+        assert abs(float(res["avg_y_hat"][b]) - float(med)) < 1e-6

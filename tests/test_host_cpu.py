@@ -1,0 +1,180 @@
+"""CPU tests: the C-ABI library loads and exports what include/advmil_b200.h declares (no compute calls), the module
+surface matches the reference's state_dict contract, host-side packing/sharding logic, and the data-parallel gradient
+maths over a world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import advmil_oracle as O
+from tests.util import build_D, build_G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from advmil_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "advmil_b200.h")).read()
+    declared = set(re.findall(r"ADVMIL_API\s+[\w\s\*]+?\b(advmil_\w+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype"
+    assert lib.advmil_abi_version() == 1
+    for i, st in enumerate(_lib.ABI_STRUCTS):
+        assert lib.advmil_abi_sizeof(i) == ctypes.sizeof(st)
+    assert lib.advmil_gate_packed_width(384) == 768 and lib.advmil_gate_packed_width(128) == 256
+    assert lib.advmil_gate_packed_width(32) == 128
+
+
+def test_product_path_does_not_import_oracle_or_reference():
+    for root, _, files in os.walk(os.path.join(ROOT, "advmil_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"
+                assert "/root/reference" not in src, f"{f} references the reference tree"
+
+
+def test_state_dict_contract_matches_reference_names_and_shapes():
+    G, D = build_G(device="cpu"), build_D(device="cpu")
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == O.G_SHAPES()
+    assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == O.D_SHAPES()
+    assert sum(p.numel() for p in G.parameters()) == 911810
+    assert sum(p.numel() for p in D.parameters()) == 206338
+    Gc = build_G((1024, 384, 384), mode="cluster", device="cpu")
+    assert {k: tuple(v.shape) for k, v in Gc.state_dict().items()} == O.G_CLUSTER_SHAPES()
+    from advmil_b200.model.model_utils import init_weights
+    G.apply(init_weights)
+    assert float(G.backbone.rho[0].bias.abs().max()) == 0.0
+    # parameter order handed to the C ABI
+    from advmil_b200 import _lib
+    assert len(G.gen_params()) == len(_lib.GEN_TENSORS) and len(D.disc_params()) == len(_lib.DISC_TENSORS)
+
+
+def test_unsupported_configurations_raise_like_the_reference():
+    from advmil_b200.model.backbone import load_backbone
+    from advmil_b200.model.backbone_utils import make_embedding_layer
+    from types import SimpleNamespace
+    with pytest.raises(NotImplementedError):
+        load_backbone("graph", [1024, 384, 384])
+    with pytest.raises(NotImplementedError):
+        make_embedding_layer("nope", SimpleNamespace())
+    with pytest.raises(AssertionError):
+        load_backbone("abmil", [1024, 384])
+
+
+def test_no_cpu_fallback():
+    from advmil_b200 import _lib, ops
+    with pytest.raises(_lib.AdvmilError):
+        ops.PackedBags(torch.zeros(16, 8), [16])
+
+
+def test_pack_and_shard_logic():
+    from advmil_b200.dataset.packed import group_steps, pack_step, shard_bags_balanced
+    bags = [torch.full((n, 8), float(i)) for i, n in enumerate([32, 16, 48])]
+    st = pack_step(bags, [(0.1, 1), (0.2, 0), (0.3, 1)], visible=[True, False, True], pin=False)
+    assert st.lengths == [32, 16, 48] and st.x.shape == (96, 8)
+    assert float(st.x[31, 0]) == 0.0 and float(st.x[32, 0]) == 1.0 and float(st.x[48, 0]) == 2.0
+    assert st.visible.tolist() == [1, 0, 1] and st.e.tolist() == [1.0, 0.0, 1.0]
+    with pytest.raises(AssertionError):
+        pack_step([torch.zeros(40, 8)], [(0.5, 1)], pin=False)          # not a multiple of 16
+    assert group_steps(35, 16) == [list(range(0, 16)), list(range(16, 32))]   # trailing partial group dropped
+    lens = [100000, 1024, 2048, 50000, 30000, 16, 4096, 70000]
+    sh = shard_bags_balanced(lens, 4)
+    assert sorted(i for s in sh for i in s) == list(range(8)) and all(len(s) > 0 for s in sh)
+    loads = [sum(lens[i] for i in s) for s in sh]
+    assert max(loads) == 100000       # the largest bag alone bounds the step; everything else is spread below it
+    assert shard_bags_balanced([16, 16], 2) == [[0], [1]]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, q):
+    """Each rank: D-step and G-step gradients of ITS bags with GLOBAL-count loss normalisation, then all-reduce(sum)."""
+    import torch.distributed as dist
+    from advmil_b200.dataset.packed import shard_bags_balanced
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    dims, d = (64, 32, 32), 32
+    Ns = [48, 160, 96, 32, 208]
+    sdG = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(O.G_SHAPES(*dims), 5).items()}
+    sdD = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(O.D_SHAPES(64, d, (16, 32)), 6).items()}
+    bags = [O.synth_bag(n, 40 + i, 64) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(len(Ns), 3)
+    es[1] = 1.0
+    vis = [True, True, False, True, True]
+    nz = [torch.tensor(np.random.default_rng(50 + i).uniform(size=(1, 16)), dtype=torch.float32) for i in range(len(Ns))]
+    mine = shard_bags_balanced(Ns, world)[rank]
+    n_real = sum(1 for i in range(len(Ns)) if es[i] == 1 and vis[i])
+    n_fake, n_vis = len(Ns), sum(vis)
+    # local loss contributions with global denominators (what advmil_disc_loss / advmil_gen_loss compute per rank)
+    dl = torch.zeros(())
+    gl = torch.zeros(())
+    for i in mine:
+        x = bags[i]
+        with torch.no_grad():
+            pred = O.generator_forward(sdG, x, [None, nz[i]], (0, 1))["pred"]
+        f_fake = O.prjdisc_forward(sdD, x, pred)["out"].reshape(())
+        dl = dl - (1.0 - torch.log(torch.sigmoid(f_fake) + 1e-8)) / n_fake
+        if es[i] == 1 and vis[i]:
+            f_real = O.prjdisc_forward(sdD, x, ts[i].reshape(1, 1))["out"].reshape(())
+            dl = dl - torch.log(torch.sigmoid(f_real) + 1e-8) / n_real
+        p2 = O.generator_forward(sdG, x, [None, nz[i]], (0, 1))["pred"]
+        ff = O.prjdisc_forward(sdD, x, p2)["out"].reshape(())
+        gl = gl + 0.004 * (-ff / n_fake)
+        if vis[i]:
+            diff = p2.reshape(()) - ts[i]
+            gl = gl + (es[i] * diff.abs() + (1 - es[i]) * torch.relu(-diff)) / n_vis
+    gD = torch.autograd.grad(dl, list(sdD.values()), allow_unused=True)
+    gG = torch.autograd.grad(gl, list(sdG.values()), allow_unused=True)
+    flatD = torch.cat([torch.zeros_like(p).reshape(-1) if g_ is None else g_.reshape(-1) for g_, p in zip(gD, sdD.values())])
+    flatG = torch.cat([torch.zeros_like(p).reshape(-1) if g_ is None else g_.reshape(-1) for g_, p in zip(gG, sdG.values())])
+    dist.all_reduce(flatD)
+    dist.all_reduce(flatG)
+    if rank == 0:
+        q.put((flatD.numpy(), flatG.numpy()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradients_equal_single_process_gloo():
+    """N-rank gradients == 1-rank gradients on the concatenated bag list (global-count normalisation)."""
+    ctx = mp.get_context("spawn")
+    res = {}
+    for world in (1, 2):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res[world] = q.get()
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+    for a, b in zip(res[1], res[2]):
+        assert float(np.abs(a - b).max()) <= 1e-6 * max(1.0, float(np.abs(a).max()))
+    # and the single-process value is the reference loss' gradient (oracle disc_step_loss with the same inputs)
+    dims, d = (64, 32, 32), 32
+    Ns = [48, 160, 96, 32, 208]
+    sdG = O.synth_state_dict(O.G_SHAPES(*dims), 5)
+    sdD = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(O.D_SHAPES(64, d, (16, 32)), 6).items()}
+    bags = [O.synth_bag(n, 40 + i, 64) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(len(Ns), 3)
+    es[1] = 1.0
+    nz = [[None, torch.tensor(np.random.default_rng(50 + i).uniform(size=(1, 16)), dtype=torch.float32)] for i in range(len(Ns))]
+    out = O.disc_step_loss(sdG, sdD, bags, ts, es, [True, True, False, True, True], nz)
+    out["loss"].backward()
+    ref = torch.cat([torch.zeros_like(p).reshape(-1) if p.grad is None else p.grad.reshape(-1) for p in sdD.values()]).numpy()
+    assert float(np.abs(ref - res[2][0]).max()) <= 2e-6 * max(1.0, float(np.abs(ref).max()))
