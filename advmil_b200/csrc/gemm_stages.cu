@@ -29,7 +29,7 @@ int gated_score_fwd(const float* v, const float* Wp, const float* bp, const floa
   if (rows == 0) return ADVMIL_OK;
   int abw = gate_width(D);
   if (precision != ADVMIL_FP32 && tc_gate_supported(rows, L, D))
-    return tc_gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, precision, st);
+    return tc_gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, part_ws, precision, st);
   GemmArgs g{v, Wp, rows, abw, L, L, L, L};
   EpiGate epi{ab, abw, bp, wc, part_ws, D, da, db};
   ADVMIL_TRY((launch_gemm<true, true>(g, epi, 1, st)));
@@ -52,7 +52,7 @@ int bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* d
              int precision, cudaStream_t st) {
   ADVMIL_REQUIRE(gemm_ok(Ny, Nx, dY, W), "bwd_data: Ny=%d Nx=%d must be multiples of 4", Ny, Nx);
   if (rows == 0) return ADVMIL_OK;
-  if (precision != ADVMIL_FP32 && tc_bwd_data_supported(rows, Ny, Nx))
+  if (precision != ADVMIL_FP32 && !ex.accumulate && !ex.dmean && tc_bwd_data_supported(rows, Ny, Nx))
     return tc_bwd_data(dY, W, rows, Ny, Nx, dX, ex, precision, st);
   GemmArgs g{dY, W, rows, Nx, Ny, Ny, Nx, Ny};
   EpiBwdData epi{dX, Nx, ex.w, ex.dz, ex.dmean, ex.offsets, ex.bags, ex.relu_src, ex.ld_src, ex.inv_keep, ex.accumulate};
@@ -67,7 +67,9 @@ static int pick_splits(int rows, int N1, int N2) {
   return max(1, min(s, 256));
 }
 size_t bwd_weight_ws_floats(int rows, int N1, int N2) {
-  return (size_t)pick_splits(rows, N1, N2) * N1 * N2;
+  size_t simt = (size_t)pick_splits(rows, N1, N2) * N1 * N2;
+  size_t tcw = tc_bwd_weight_ws_floats(rows, N1, N2);
+  return simt > tcw ? simt : tcw;
 }
 int bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
                int precision, cudaStream_t st) {

@@ -1,30 +1,624 @@
-// tcgen05 engine — placeholder until the TMA/TMEM kernels land: reports "unsupported" so every shape
-// runs on the fp32 FFMA engine.  (Replaced in the next milestone.)
+// tcgen05 / TMEM / TMA engine for the N-row contractions (sm_100a).
+//
+//  tc_rows_kernel   C[rows, N] = A[rows, K] . W[N, K]^T with a fused epilogue.  A (activations, fp32 in HBM) and W are
+//                   K-major; 128 x BLOCK_N output tiles; TMA (SWIZZLE_128B boxes of 32 fp32 = 128 B per row) feeds a 4-stage
+//                   shared-memory ring; one elected thread issues tcgen05.mma.kind::tf32 (fp32 bits are consumed directly:
+//                   no conversion pass over x); accumulators are double-buffered in TMEM so the epilogue of tile i overlaps
+//                   the MMAs of tile i+1; persistent over tiles with the N-tiles of one row block adjacent in time so x is
+//                   fetched from HBM once and re-read from L2.
+//                   Epilogues: bias+ReLU+dropout (K1), tanh*sigmoid gate + w_c score (K2), LayerNorm+ReLU+16-row region mean
+//                   (K5+K6), backward-data with pooling term and ReLU mask.
+//  tc_wgrad_kernel  dW[N1, N2] = dY[rows, N1]^T . X[rows, N2]: both operands MN-major straight from their row-major
+//                   activations (no transposes of the big tensors), split-K over rows, fp32 partial tiles reduced afterwards.
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+// (TMEM lane quarter = warp % 4).
 #include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace advmil {
+using namespace tc;
 
-bool tc_linear_supported(int, int, int) { return false; }
-int tc_linear_fwd(const float*, const float*, const float*, int, int, int, int, const Drop&, float*, int, cudaStream_t) {
-  set_error("tc_linear_fwd: not built"); return ADVMIL_ERR_INVALID;
+// ------------------------------------------------------------------------------------------------
+// tensor maps (driver entry point resolved at run time: no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
 }
-bool tc_gate_supported(int, int, int) { return false; }
-int tc_gated_score_fwd(const float*, const float*, const float*, const float*, const float*, int, int, int, const Drop&,
-                       const Drop&, float*, float*, int, cudaStream_t) {
-  set_error("tc_gated_score_fwd: not built"); return ADVMIL_ERR_INVALID;
+// row-major fp32 matrix [rows, cols]; box = box_rows x 32 floats (128 B), SWIZZLE_128B, OOB reads return zeros
+static int make_tmap(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADVMIL_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return ADVMIL_ERR_CUDA; }
+  return ADVMIL_OK;
 }
-bool tc_embed_supported(int, int, int) { return false; }
-int tc_region_embed_fwd(const float*, const float*, const float*, const float*, const float*, int, int, int, float,
-                        float*, float*, int, cudaStream_t) {
-  set_error("tc_region_embed_fwd: not built"); return ADVMIL_ERR_INVALID;
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
 }
-bool tc_bwd_data_supported(int, int, int) { return false; }
-int tc_bwd_data(const float*, const float*, int, int, int, float*, const BwdDataExtras&, int, cudaStream_t) {
-  set_error("tc_bwd_data: not built"); return ADVMIL_ERR_INVALID;
+
+// ------------------------------------------------------------------------------------------------
+// epilogue parameter block
+// ------------------------------------------------------------------------------------------------
+enum RowEpiKind : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_LN = 2, EPI_BWD = 3 };
+
+struct RowEpi {
+  float* out; int ldo; const float* bias;
+  int relu; Drop drop;                                                           // EPI_LINEAR
+  float* ab; const float* wc; float* part; int D; Drop drop_a, drop_b;           // EPI_GATE (bias = packed gate bias)
+  float* y_pre; float* emb; const float* gamma; const float* beta; float eps;    // EPI_LN
+  const float* w; const float* dz; const int32_t* offsets; int bags;             // EPI_BWD
+  const float* relu_src; int ld_src; float inv_keep;
+};
+
+constexpr int TILE_M = 128, KBLK = 32;                 // 32 fp32 = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * KBLK * 4;       // 16 KB
+constexpr int STG_LD = 36;                             // staging row stride (floats) for 32-column chunks
+constexpr int STG_LD_LN = 132;                         // staging row stride for full 128-column rows
+
+template <int BLOCK_N, int EPI> struct RowCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * KBLK * 4;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : 32 * STG_LD;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 4 * STG_FLOATS_PER_WARP * 4 +
+                                 4 * 32 * 8 /*rowbag,roww*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float fast_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// stage one 32-column chunk: thread `lane` owns row `lane`
+__device__ __forceinline__ void stage_chunk(float* stg, int ld, int col0, const float (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * ld + col0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
-bool tc_bwd_weight_supported(int, int, int) { return false; }
-int tc_bwd_weight(const float*, const float*, int, int, int, float*, int, float*, int, cudaStream_t) {
-  set_error("tc_bwd_weight: not built"); return ADVMIL_ERR_INVALID;
+
+template <int BLOCK_N, int EPI, bool FAST>
+__global__ void __launch_bounds__(256, 1)
+tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
+  using Cfg = RowCfg<BLOCK_N, EPI>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* A_s = smem;
+  uint8_t* B_s = smem + STAGES * A_STAGE_BYTES;
+  float* stg_all = (float*)(B_s + STAGES * Cfg::B_STAGE_BYTES);
+  int* rowbag = (int*)(stg_all + 4 * Cfg::STG_FLOATS_PER_WARP);
+  float* roww = (float*)(rowbag + 4 * 32);
+  uint64_t* bars = (uint64_t*)(roww + 4 * 32);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + TILE_M - 1) / TILE_M, num_n = N / BLOCK_N;
+  const int total = num_m * num_n, kblocks = K / KBLK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * TILE_M, n0 = (tile % num_n) * BLOCK_N;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(A_s + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * KBLK, m0);
+          tma_load_2d(B_s + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kb * KBLK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_tf32(TILE_M, BLOCK_N, 0, 0);
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(A_s + stage * A_STAGE_BYTES), b_addr = smem_u32(B_s + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < KBLK / 8; ++kk) {   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            uint64_t ad = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+            uint64_t bd = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
+            mma_tf32(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+          }
+          mma_commit(&empty[stage]);                 // smem slot is free once these MMAs retire
+          if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int wq = warp & 3;
+    float* stg = stg_all + wq * Cfg::STG_FLOATS_PER_WARP;
+    int* mybag = rowbag + wq * 32;
+    float* myw = roww + wq * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      const int mt = tile / num_n, nt = tile % num_n;
+      const int m_base = mt * TILE_M + wq * 32, n0 = nt * BLOCK_N;
+      const int m_row = m_base + lane;                     // the row this thread owns in TMEM
+      mbar_wait(&tfull[acc], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
+
+      if constexpr (EPI == EPI_LINEAR || EPI == EPI_BWD) {
+        if constexpr (EPI == EPI_BWD) {
+          int bg = 0; float wv = 0.f;
+          if (ea.dz && m_row < M) { bg = bag_of_row(ea.offsets, ea.bags, m_row); wv = ea.w[m_row]; }
+          mybag[lane] = bg; myw[lane] = wv;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          if (ch == BLOCK_N / 32 - 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          stage_chunk(stg, STG_LD, 0, v, lane);
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int r = (lane >> 3) + 4 * i8, c4 = lane & 7;
+            const int m = m_base + r, col = n0 + ch * 32 + c4 * 4;
+            if (m < M) {
+              float4 q = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
+              float o[4] = {q.x, q.y, q.z, q.w};
+              if constexpr (EPI == EPI_LINEAR) {
+                if (ea.bias) { float4 b4 = *reinterpret_cast<const float4*>(ea.bias + col); o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (ea.relu) o[e] = fmaxf(o[e], 0.f);
+                  o[e] *= ea.drop.scale((uint64_t)m * N + col + e);
+                }
+              } else {
+                if (ea.dz) {
+                  float4 d4 = *reinterpret_cast<const float4*>(ea.dz + (size_t)mybag[r] * N + col);
+                  const float wv = myw[r];
+                  o[0] = fmaf(wv, d4.x, o[0]); o[1] = fmaf(wv, d4.y, o[1]); o[2] = fmaf(wv, d4.z, o[2]); o[3] = fmaf(wv, d4.w, o[3]);
+                }
+                if (ea.relu_src) {
+                  float4 s4 = *reinterpret_cast<const float4*>(ea.relu_src + (size_t)m * ea.ld_src + col);
+                  o[0] = s4.x > 0.f ? o[0] * ea.inv_keep : 0.f; o[1] = s4.y > 0.f ? o[1] * ea.inv_keep : 0.f;
+                  o[2] = s4.z > 0.f ? o[2] * ea.inv_keep : 0.f; o[3] = s4.w > 0.f ? o[3] * ea.inv_keep : 0.f;
+                }
+              }
+              *reinterpret_cast<float4*>(ea.out + (size_t)m * ea.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_GATE) {
+        // BLOCK_N = 256 = two packed gate blocks (64 tanh | 64 sigmoid columns each)
+        float partial = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < BLOCK_N / 128; ++g) {
+#pragma unroll 1
+          for (int jc = 0; jc < 2; ++jc) {
+            const int ca = g * 128 + jc * 32, cb = ca + 64;
+            const int j0 = (n0 >> 1) + g * 64 + jc * 32;     // logical gate column of element 0
+            float va[32], vb[32];
+            tmem_ld32(taddr + ca, va);
+            tmem_ld32(taddr + cb, vb);
+            if (g == BLOCK_N / 128 - 1 && jc == 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float xa = va[i] + __ldg(ea.bias + n0 + ca + i), xb = vb[i] + __ldg(ea.bias + n0 + cb + i);
+              float a, b;
+              if (FAST) { a = fast_tanh(xa); b = fmaf(0.5f, fast_tanh(0.5f * xb), 0.5f); }
+              else { a = tanhf(xa); b = sigmoidf_(xb); }
+              va[i] = a; vb[i] = b;
+              const int j = j0 + i;
+              if (j < ea.D && m_row < M) {
+                const float ad = a * ea.drop_a.scale((uint64_t)m_row * ea.D + j), bd = b * ea.drop_b.scale((uint64_t)m_row * ea.D + j);
+                partial = fmaf(ad * bd, __ldg(ea.wc + j), partial);
+              }
+            }
+            if (ea.ab) {
+#pragma unroll 1
+              for (int half = 0; half < 2; ++half) {
+                if (half == 0) stage_chunk(stg, STG_LD, 0, va, lane); else stage_chunk(stg, STG_LD, 0, vb, lane);
+                __syncwarp();
+                const int cbase = n0 + (half == 0 ? ca : cb);
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                  const int r = (lane >> 3) + 4 * i8, c4 = lane & 7, m = m_base + r;
+                  if (m < M)
+                    *reinterpret_cast<float4*>(ea.ab + (size_t)m * ea.ldo + cbase + c4 * 4) =
+                        *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+        if (m_row < M) ea.part[(size_t)nt * M + m_row] = partial;
+      } else if constexpr (EPI == EPI_LN) {
+        // BLOCK_N == 128 == d: the whole row lives in this thread's registers
+        float v[128];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float t[32];
+          tmem_ld32(taddr + ch * 32, t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[ch * 32 + i] = t[i] + __ldg(ea.bias + ch * 32 + i);
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[acc]);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) s += v[i];
+        const float mean = s * (1.0f / 128.0f);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) { const float c = v[i] - mean; q = fmaf(c, c, q); }
+        const float rstd = rsqrtf(q * (1.0f / 128.0f) + ea.eps);
+        if (ea.y_pre) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<float4*>(stg + lane * STG_LD_LN + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int m = m_base + r;
+            if (m < M)
+              *reinterpret_cast<float4*>(ea.y_pre + (size_t)m * 128 + lane * 4) = *reinterpret_cast<const float4*>(stg + r * STG_LD_LN + lane * 4);
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float e[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = 4 * j + k;
+            e[k] = (m_row < M) ? fmaxf(fmaf((v[c] - mean) * rstd, __ldg(ea.gamma + c), __ldg(ea.beta + c)), 0.f) : 0.f;
+          }
+          *reinterpret_cast<float4*>(stg + lane * STG_LD_LN + 4 * j) = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rg = 0; rg < 2; ++rg) {          // two 16-row regions per warp
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + (rg * 16 + r) * STG_LD_LN + lane * 4);
+            a4.x += t4.x; a4.y += t4.y; a4.z += t4.z; a4.w += t4.w;
+          }
+          const int m = m_base + rg * 16;
+          if (m < M)
+            *reinterpret_cast<float4*>(ea.emb + (size_t)(m >> 4) * 128 + lane * 4) =
+                make_float4(a4.x * 0.0625f, a4.y * 0.0625f, a4.z * 0.0625f, a4.w * 0.0625f);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+template <int BLOCK_N, int EPI, bool FAST>
+static int launch_rows(const float* A, const float* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
+  using Cfg = RowCfg<BLOCK_N, EPI>;
+  CUtensorMap tmA, tmB;
+  ADVMIL_TRY(make_tmap(&tmA, A, rows, K, TILE_M));
+  ADVMIL_TRY(make_tmap(&tmB, W, N, K, BLOCK_N));
+  auto kern = tc_rows_kernel<BLOCK_N, EPI, FAST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  const int total = cdiv(rows, TILE_M) * (N / BLOCK_N);
+  const int grid = min(total, sm_count());
+  kern<<<grid, 256, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient kernel: dW[N1,N2] partial over a row range; both operands MN-major
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N> struct WgCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = 4 * KBLK * 128;                 // 4 MN-groups x (32 rows x 128 B) = 16 KB
+  static constexpr int B_BYTES = (BLOCK_N / 32) * KBLK * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BLOCK_N <= 128 ? 128 : 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + 4 * 32 * STG_LD * 4 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const __grid_constant__ CUtensorMap tmB /*X*/,
+                int rows, int N1, int N2, int rows_per_split, float* __restrict__ ws) {
+  using Cfg = WgCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* A_s = smem;
+  uint8_t* B_s = smem + STAGES * Cfg::A_BYTES;
+  float* stg_all = (float*)(B_s + STAGES * Cfg::B_BYTES);
+  uint64_t* bars = (uint64_t*)(stg_all + 4 * 32 * STG_LD);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint32_t* tmem_ptr = (uint32_t*)(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_n = N2 / BLOCK_N;
+  const int mt = blockIdx.x / num_n, nt = blockIdx.x % num_n;
+  const int m0 = mt * TILE_M, n0 = nt * BLOCK_N;
+  const int r_beg = blockIdx.y * rows_per_split, r_end = min(rows, r_beg + rows_per_split);
+  const int kblocks = (r_end - r_beg + KBLK - 1) / KBLK;     // rows past `rows` are zero-filled by TMA
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int r0 = r_beg + kb * KBLK;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(A_s + stage * Cfg::A_BYTES + g * (KBLK * 128), &tmA, &full[stage], m0 + g * 32, r0);
+#pragma unroll
+        for (int g = 0; g < BLOCK_N / 32; ++g)
+          tma_load_2d(B_s + stage * Cfg::B_BYTES + g * (KBLK * 128), &tmB, &full[stage], n0 + g * 32, r0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = idesc_tf32(TILE_M, BLOCK_N, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(A_s + stage * Cfg::A_BYTES), b_addr = smem_u32(B_s + stage * Cfg::B_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < KBLK / 8; ++kk) {   // 8 k-rows (one 1024-byte swizzle atom) per MMA
+          uint64_t ad = smem_desc_sw128(a_addr + kk * 1024, KBLK * 128, 1024);
+          uint64_t bd = smem_desc_sw128(b_addr + kk * 1024, KBLK * 128, 1024);
+          mma_tf32(tmem_base, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+        }
+        mma_commit(&empty[stage]);
+        if (kb == kblocks - 1) mma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    float* stg = stg_all + wq * 32 * STG_LD;
+    float* out = ws + (size_t)blockIdx.y * N1 * N2;
+    const int m_base = m0 + wq * 32;
+    if (kblocks > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      float v[32];
+      if (kblocks > 0) tmem_ld32(taddr + ch * 32, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      stage_chunk(stg, STG_LD, 0, v, lane);
+      __syncwarp();
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int r = (lane >> 3) + 4 * i8, c4 = lane & 7, m = m_base + r;
+        if (m < N1)
+          *reinterpret_cast<float4*>(out + (size_t)m * N2 + n0 + ch * 32 + c4 * 4) = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static int pick_block_n(int N) {
+  if (N % 192 == 0 && N % 256 != 0) return 192;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  return 0;
+}
+
+bool tc_linear_supported(int rows, int K, int N) { return rows >= TILE_M && K % KBLK == 0 && K >= KBLK && pick_block_n(N) != 0; }
+
+template <int EPI, bool FAST>
+static int launch_rows_any(const float* A, const float* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
+  switch (pick_block_n(N)) {
+    case 128: return launch_rows<128, EPI, FAST>(A, W, rows, K, N, ea, st);
+    case 192: return launch_rows<192, EPI, FAST>(A, W, rows, K, N, ea, st);
+    case 256: return launch_rows<256, EPI, FAST>(A, W, rows, K, N, ea, st);
+  }
+  set_error("tc: unsupported N=%d", N);
+  return ADVMIL_ERR_INVALID;
+}
+
+int tc_linear_fwd(const float* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+                  float* y, int precision, cudaStream_t st) {
+  RowEpi ea{};
+  ea.out = y; ea.ldo = N; ea.bias = b; ea.relu = relu; ea.drop = drop;
+  return launch_rows_any<EPI_LINEAR, true>(x, W, rows, K, N, ea, st);
+}
+
+bool tc_gate_supported(int rows, int L, int D) { return rows >= TILE_M && L % KBLK == 0 && D % 128 == 0; }
+
+int tc_gated_score_fwd(const float* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows,
+                       int L, int D, const Drop& da, const Drop& db, float* ab, float* s, float* part, int precision,
+                       cudaStream_t st) {
+  const int abw = gate_width(D);
+  RowEpi ea{};
+  ea.bias = bp; ea.ab = ab; ea.ldo = abw; ea.wc = wc; ea.part = part; ea.D = D; ea.drop_a = da; ea.drop_b = db;
+  if (precision == ADVMIL_TF32) ADVMIL_TRY((launch_rows<256, EPI_GATE, true>(v, Wp, rows, L, abw, ea, st)));
+  else ADVMIL_TRY((launch_rows<256, EPI_GATE, false>(v, Wp, rows, L, abw, ea, st)));
+  return gate_score_finish(part, abw / 256, rows, bc, s, st);
+}
+
+bool tc_embed_supported(int rows, int C, int d) { return rows >= TILE_M && C % KBLK == 0 && d == 128; }
+
+int tc_region_embed_fwd(const float* x, const float* Wc, const float* bc, const float* gamma, const float* beta,
+                        int rows, int C, int d, float eps, float* y_pre, float* emb, int precision, cudaStream_t st) {
+  RowEpi ea{};
+  ea.bias = bc; ea.y_pre = y_pre; ea.emb = emb; ea.gamma = gamma; ea.beta = beta; ea.eps = eps;
+  return launch_rows<128, EPI_LN, true>(x, Wc, rows, C, d, ea, st);
+}
+
+// dX = dY . W with W [Ny, Nx] row-major: needs W^T [Nx, Ny] K-major; the transpose of the (small) weight is made by
+// the caller-provided scratch through tc_transpose
+__global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, float* __restrict__ out) {
+  __shared__ float t[32][33];
+  int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (x < Cc && y0 + j < R) t[j][threadIdx.x] = in[(size_t)(y0 + j) * Cc + x];
+  __syncthreads();
+  int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (ox < R && oy0 + j < Cc) out[(size_t)(oy0 + j) * R + ox] = t[threadIdx.x][j];
+}
+
+bool tc_bwd_data_supported(int rows, int Ny, int Nx) {
+  return rows >= TILE_M && Ny % KBLK == 0 && pick_block_n(Nx) != 0 && (size_t)Ny * Nx <= (size_t)1 << 20;
+}
+
+int tc_bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* dX, const BwdDataExtras& ex,
+                int precision, cudaStream_t st) {
+  // W^T scratch: library-owned, grow-only, at most 4 MB (weights only; the "no allocation" rule is about activations)
+  static float* wt = nullptr; static size_t cap = 0;
+  size_t need = (size_t)Ny * Nx;
+  if (need > cap) {
+    ADVMIL_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (wt) cudaFree(wt);
+    ADVMIL_CHECK_CUDA(cudaMalloc(&wt, need * sizeof(float)));
+    cap = need;
+  }
+  ADVMIL_REQUIRE(!ex.accumulate && !ex.dmean, "tc_bwd_data: accumulate/dmean are served by the FFMA engine");
+  transpose_kernel<<<dim3(cdiv(Nx, 32), cdiv(Ny, 32)), dim3(32, 8), 0, st>>>(W, Ny, Nx, wt);
+  ADVMIL_CHECK_LAUNCH();
+  RowEpi ea{};
+  ea.out = dX; ea.ldo = Nx; ea.w = ex.w; ea.dz = ex.dz; ea.offsets = ex.offsets; ea.bags = ex.bags;
+  ea.relu_src = ex.relu_src; ea.ld_src = ex.ld_src; ea.inv_keep = ex.inv_keep;
+  return launch_rows_any<EPI_BWD, true>(dY, wt, rows, Ny, Nx, ea, st);
+}
+
+static int wgrad_block_n(int N2) {
+  if (N2 % 256 == 0) return 256;
+  if (N2 % 128 == 0) return 128;
+  return 0;
+}
+static int wgrad_splits(int rows, int N1, int N2) {
+  int bn = wgrad_block_n(N2);
+  int tiles = cdiv(N1, TILE_M) * (N2 / bn);
+  int s = max(1, sm_count() / tiles);
+  int max_by_rows = max(1, rows / 1024);
+  return min(s, max_by_rows);
+}
+bool tc_bwd_weight_supported(int rows, int N1, int N2) {
+  return rows >= 4096 && N1 % 32 == 0 && N1 >= 128 && wgrad_block_n(N2) != 0;
+}
+size_t tc_bwd_weight_ws_floats(int rows, int N1, int N2) {
+  if (!tc_bwd_weight_supported(rows, N1, N2)) return 0;
+  return (size_t)wgrad_splits(rows, N1, N2) * N1 * N2;
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const float* dY, const float* X, int rows, int N1, int N2, int rows_per_split, int nsplit, float* ws,
+                        cudaStream_t st) {
+  using Cfg = WgCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  ADVMIL_TRY(make_tmap(&tmA, dY, rows, N1, KBLK));
+  ADVMIL_TRY(make_tmap(&tmB, X, rows, N2, KBLK));
+  auto kern = tc_wgrad_kernel<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(N1, TILE_M) * (N2 / BLOCK_N), nsplit);
+  kern<<<grid, 256, Cfg::SMEM, st>>>(tmA, tmB, rows, N1, N2, rows_per_split, ws);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+int tc_bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+                  int precision, cudaStream_t st) {
+  const int splits = wgrad_splits(rows, N1, N2);
+  const int rows_per_split = cdiv(cdiv(rows, splits), KBLK) * KBLK;
+  const int nsplit = cdiv(rows, rows_per_split);
+  if (wgrad_block_n(N2) == 256) ADVMIL_TRY((launch_wgrad<256>(dY, X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
+  else ADVMIL_TRY((launch_wgrad<128>(dY, X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
+  return splitk_reduce(ws, nsplit, (size_t)N1 * N2, dW, accumulate, st);
 }
 
 }  // namespace advmil

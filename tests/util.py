@@ -65,12 +65,13 @@ def assert_close(actual, expected, rtol, name="", atol_scale=None, atol=0.0):
 
 
 def grad_floor(ref_grads) -> float:
-    """Absolute floor for gradient comparisons: 1e-9 x the largest gradient entry of the whole network.  Gradients that
-    pass through the softmax Jacobian w_n (g.v_n - g.z) of a nearly-uniform attention are differences of nearly equal
-    numbers; their fp32 rounding error is set by the size of the cancelled terms, not of the result, so two correct fp32
-    evaluations (e.g. the reference on CPU and on GPU) differ there by more than 1e-5 of the tiny result."""
+    """Absolute floor for gradient comparisons: one fp32 ulp (2^-23) of the largest gradient entry of the whole network.
+    Gradients that pass through the softmax Jacobian w_n (g.v_n - g.z) of a nearly-uniform attention, or that sum real
+    and fake pair contributions of opposite sign, are differences of nearly equal numbers; their fp32 rounding error is
+    set by the size of the cancelled terms, not of the result, so two correct fp32 evaluations (e.g. the reference on
+    CPU and on GPU) differ there by more than 1e-5 of the tiny result."""
     m = 0.0
     for g in ref_grads:
         if g is not None:
             m = max(m, float(np.abs(np.asarray(g)).max()))
-    return 1e-9 * m
+    return 2.0 ** -23 * m
