@@ -37,7 +37,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 // row-major fp32 matrix [rows, cols]; box = box_rows x 32 floats (128 B), SWIZZLE_128B, OOB reads return zeros
-static int make_tmap(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows) {
+static int make_tmap(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADVMIL_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -45,7 +46,7 @@ static int make_tmap(CUtensorMap* m, const float* base, long long rows, long lon
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return ADVMIL_ERR_CUDA; }
   return ADVMIL_OK;
 }
@@ -436,9 +437,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(A_s + stage * Cfg::A_BYTES), b_addr = smem_u32(B_s + stage * Cfg::B_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < KBLK / 8; ++kk) {   // 8 k-rows (one 1024-byte swizzle atom) per MMA
-          uint64_t ad = smem_desc_sw128(a_addr + kk * 1024, KBLK * 128, 1024);
-          uint64_t bd = smem_desc_sw128(b_addr + kk * 1024, KBLK * 128, 1024);
+        for (int kk = 0; kk < KBLK / 8; ++kk) {   // 8 k-rows = two 4-row (512-byte) SW128/32B-atom groups per MMA
+          uint64_t ad = smem_desc_sw128(a_addr + kk * 1024, KBLK * 128, 512, 1);
+          uint64_t bd = smem_desc_sw128(b_addr + kk * 1024, KBLK * 128, 512, 1);
           mma_tf32(tmem_base, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
         }
         mma_commit(&empty[stage]);
@@ -597,8 +598,9 @@ static int launch_wgrad(const float* dY, const float* X, int rows, int N1, int N
                         cudaStream_t st) {
   using Cfg = WgCfg<BLOCK_N>;
   CUtensorMap tmA, tmB;
-  ADVMIL_TRY(make_tmap(&tmA, dY, rows, N1, KBLK));
-  ADVMIL_TRY(make_tmap(&tmB, X, rows, N2, KBLK));
+  // MN-major tf32 operands need the 128-byte swizzle with 32-byte atoms on both the TMA and the UMMA side
+  ADVMIL_TRY(make_tmap(&tmA, dY, rows, N1, KBLK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  ADVMIL_TRY(make_tmap(&tmB, X, rows, N2, KBLK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   auto kern = tc_wgrad_kernel<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
