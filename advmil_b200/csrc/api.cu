@@ -116,7 +116,7 @@ extern "C" size_t advmil_generator_workspace_bytes(const AdvmilGenParams* p, int
     f += (size_t)bags * (h + o + hid + 1) + 1024;             // per-bag gradient vectors
     f += (size_t)rows * abw + (size_t)rows * h + 512;         // dAB, dh_pre
     f += abw * h + abw + 512;                                 // packed gate weight grads
-    f += align_up((size_t)bags, 64) + (size_t)row_chunks(rows) * (h + 1) + 256;  // pool_gate partials
+    f += pool_gate_ws_floats(rows, bags, (int)h) + 256;       // pool_gate partials
     f += max(bwd_weight_ws_floats(rows, (int)abw, (int)h), bwd_weight_ws_floats(rows, (int)h, (int)C)) + 256;
     f += (size_t)row_chunks(rows) * max(abw, h) + 256;        // colsum partials
   }
@@ -172,7 +172,7 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   WS_TAKE(dhpre, float, (size_t)rows * h);
   WS_TAKE(dWp, float, (size_t)abw * h);
   WS_TAKE(dbp, float, abw);
-  WS_TAKE(pgws, float, align_up((size_t)nb, 64) + (size_t)row_chunks(rows) * (h + 1));
+  WS_TAKE(pgws, float, pool_gate_ws_floats(rows, nb, h));
   WS_TAKE(bwws, float, max(bwd_weight_ws_floats(rows, abw, h), bwd_weight_ws_floats(rows, h, C)));
   WS_TAKE(csws, float, (size_t)row_chunks(rows) * max(abw, h));
   const float ik_bb = (a->train && p->p_backbone > 0.f) ? 1.f / (1.f - p->p_backbone) : 1.f;
@@ -189,12 +189,11 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   // pooling + gate
   ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
   { ProfScope ps(PROF_POOL_BWD, st);
-    ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, 0, pgws, st)); }
+    ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, dbp, 0, pgws, st)); }
   BwdDataExtras ex;
   ex.w = a->w; ex.dz = dz; ex.offsets = bags->offsets; ex.bags = nb; ex.relu_src = a->h; ex.ld_src = h; ex.inv_keep = ik_bb;
   { ProfScope ps(PROF_BWD_DATA, st); ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st)); }
   { ProfScope ps(PROF_BWD_W_GATE, st); ADVMIL_TRY(bwd_weight(dAB, a->h, rows, abw, h, dWp, 0, bwws, prec, st)); }
-  { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dAB, rows, abw, abw, dbp, 0, csws, st)); }
   ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st));
   // first layer
   { ProfScope ps(PROF_BWD_W_PROJ, st); ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st)); }
@@ -231,7 +230,7 @@ extern "C" size_t advmil_disc_workspace_bytes(const AdvmilDiscParams* p, int32_t
     // head backward
     size_t hb = (size_t)bags * (3 * d + dh + p->t2 + p->t1 + 2) + 2048;
     hb += R * abw + R * d + R * dh + abw * d + abw + 1024;
-    hb += align_up((size_t)bags, 64) + (size_t)row_chunks((int)R) * (d + 1) + 256;
+    hb += pool_gate_ws_floats((int)R, bags, (int)d) + 256;
     hb += max(bwd_weight_ws_floats((int)R, (int)abw, (int)d), bwd_weight_ws_floats((int)R, (int)d, (int)dh)) + 256;
     hb += (size_t)row_chunks((int)R) * abw + 256;
     f += max(e, hb);
@@ -349,20 +348,19 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   WS_TAKE(dWp, float, (size_t)abw * d);
   WS_TAKE(dbp, float, abw);
   WS_TAKE(dwc_scratch, float, d + 1);
-  WS_TAKE(pgws, float, align_up((size_t)nb, 64) + (size_t)row_chunks(R) * (d + 1));
+  WS_TAKE(pgws, float, pool_gate_ws_floats(R, nb, d));
   WS_TAKE(bwws, float, max(bwd_weight_ws_floats(R, abw, d), bwd_weight_ws_floats(R, d, dh)));
   WS_TAKE(csws, float, (size_t)row_chunks(R) * abw);
   Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train);
   Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train);
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
   ADVMIL_TRY(pool_gate_bwd(a->fi, a->attn, a->bagv, d_bagv, a->ab, p->Pc_w, ro.dev, R, nb, d, d, dga, dgs, dAB,
-                           g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? accumulate : 0, pgws, st));
+                           g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? dbp : nullptr, g ? accumulate : 0, pgws, st));
   BwdDataExtras ex;
   ex.w = a->attn; ex.dz = d_bagv; ex.dmean = p->inner_instance ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
   ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, ADVMIL_FP32, st));
   if (g) {
     ADVMIL_TRY(bwd_weight(dAB, a->fi, R, abw, d, dWp, 0, bwws, ADVMIL_FP32, st));
-    ADVMIL_TRY(colsum(dAB, R, abw, abw, dbp, 0, csws, st));
     ADVMIL_TRY(gate_unpack_grads(dWp, dbp, d, d, g->Pg_w, g->Pg_b, g->Ps_w, g->Ps_b, accumulate, st));
   }
   BwdDataExtras ex1;

@@ -112,18 +112,30 @@ struct Drop {          // one dropout site
   float inv_keep;      // 1/(1-p)
   int site;
   int active;          // train && p > 0
+  uint32_t key;        // per-(seed, site) 32-bit key of the counter-based generator
+  uint32_t thresh;     // drop when hash < thresh (= p * 2^32)
   __host__ static Drop make(const uint8_t* mask, uint64_t seed, int site, float p, int train) {
     Drop d;
     d.mask = mask; d.seed = seed; d.site = site; d.p = p;
     d.active = (train && p > 0.f) ? 1 : 0;
     d.inv_keep = d.active ? 1.0f / (1.0f - p) : 1.0f;
+    d.key = (uint32_t)(mix64(seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1)) >> 32);
+    double t = (double)p * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
     return d;
   }
-  // multiplicative factor for element idx (= row*width + col): 0 or 1/(1-p); 1 when inactive
+  // keep bit of element idx (= row*width + col): ~10 integer instructions (multiply-xorshift hash of the counter), the
+  // same bits in forward and backward
+  __device__ __forceinline__ bool keep(uint64_t idx) const {
+    if (mask) return mask[idx] != 0;
+    uint32_t x = ((uint32_t)idx * 0x9E3779B1u) ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ key;
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x >= thresh;
+  }
+  // multiplicative factor: 0 or 1/(1-p); 1 when inactive
   __device__ __forceinline__ float scale(uint64_t idx) const {
     if (!active) return 1.0f;
-    bool keep = mask ? (mask[idx] != 0) : (rng_uniform(seed, site, idx) >= p);
-    return keep ? inv_keep : 0.0f;
+    return keep(idx) ? inv_keep : 0.0f;
   }
 };
 

@@ -77,13 +77,16 @@ constexpr int STG_LD = 36;                             // staging row stride (fl
 constexpr int STG_LD_LN = 132;                         // staging row stride for full 128-column rows
 
 template <int BLOCK_N, int EPI> struct RowCfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 3 : 4;
+  static constexpr int EPI_WARPS = (EPI == EPI_LN) ? 4 : 8;       // 2 warps per TMEM lane quarter except for LN
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int B_STAGE_BYTES = BLOCK_N * KBLK * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : 32 * STG_LD;
+  static constexpr int COEF_FLOATS_PER_WARP = 192;                // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 4 * STG_FLOATS_PER_WARP * 4 +
-                                 4 * 32 * 8 /*rowbag,roww*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
+                                 (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 64) * 4 + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float fast_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -95,8 +98,30 @@ __device__ __forceinline__ void stage_chunk(float* stg, int ld, int col0, const 
     *reinterpret_cast<float4*>(stg + lane * ld + col0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
+// gate math on one 32-pair chunk: va/vb hold pre-activations on entry and tanh / sigmoid values on exit
+template <bool FAST, bool TRAIN>
+__device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], const float* __restrict__ cba,
+                                            const float* __restrict__ cbb, const float* __restrict__ cwc, const Drop& da,
+                                            const Drop& db, uint64_t idx0, float partial) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float xa = va[i] + cba[i], xb = vb[i] + cbb[i];
+    float a, b;
+    if (FAST) { a = fast_tanh(xa); b = fmaf(0.5f, fast_tanh(0.5f * xb), 0.5f); }
+    else { a = tanhf(xa); b = sigmoidf_(xb); }
+    va[i] = a; vb[i] = b;
+    float ad = a, bd = b;
+    if (TRAIN) {
+      ad = da.keep(idx0 + i) ? a * da.inv_keep : 0.f;
+      bd = db.keep(idx0 + i) ? b * db.inv_keep : 0.f;
+    }
+    partial = fmaf(ad * bd, cwc[i], partial);
+  }
+  return partial;
+}
+
 template <int BLOCK_N, int EPI, bool FAST>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(RowCfg<BLOCK_N, EPI>::THREADS, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
   using Cfg = RowCfg<BLOCK_N, EPI>;
   constexpr int STAGES = Cfg::STAGES;
@@ -105,9 +130,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* A_s = smem;
   uint8_t* B_s = smem + STAGES * A_STAGE_BYTES;
   float* stg_all = (float*)(B_s + STAGES * Cfg::B_STAGE_BYTES);
-  int* rowbag = (int*)(stg_all + 4 * Cfg::STG_FLOATS_PER_WARP);
-  float* roww = (float*)(rowbag + 4 * 32);
-  uint64_t* bars = (uint64_t*)(roww + 4 * 32);
+  float* coef_all = stg_all + Cfg::EPI_WARPS * Cfg::STG_FLOATS_PER_WARP;
+  int* rowbag = (int*)(coef_all + Cfg::EPI_WARPS * Cfg::COEF_FLOATS_PER_WARP);
+  float* roww = (float*)(rowbag + Cfg::EPI_WARPS * 32);
+  uint64_t* bars = (uint64_t*)(roww + Cfg::EPI_WARPS * 32);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
@@ -122,7 +148,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
@@ -175,31 +201,55 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int wq = warp & 3;
-    float* stg = stg_all + wq * Cfg::STG_FLOATS_PER_WARP;
-    int* mybag = rowbag + wq * 32;
-    float* myw = roww + wq * 32;
+    const int ew = warp - 4;               // 0..EPI_WARPS-1
+    const int wq = warp & 3;               // TMEM lane quarter this warp may read
+    const int half = ew >> 2;              // which half of the tile's columns this warp drains (0 when EPI_WARPS == 4)
+    float* stg = stg_all + ew * Cfg::STG_FLOATS_PER_WARP;
+    float* coef = coef_all + ew * Cfg::COEF_FLOATS_PER_WARP;
+    int* mybag = rowbag + ew * 32;
+    float* myw = roww + ew * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
       const int mt = tile / num_n, nt = tile % num_n;
       const int m_base = mt * TILE_M + wq * 32, n0 = nt * BLOCK_N;
       const int m_row = m_base + lane;                     // the row this thread owns in TMEM
+      if constexpr (EPI == EPI_BWD) {                      // per-row pooling operands (independent of the accumulator)
+        int bg = 0; float wv = 0.f;
+        if (ea.dz && m_row < M) { bg = bag_of_row(ea.offsets, ea.bags, m_row); wv = ea.w[m_row]; }
+        mybag[lane] = bg; myw[lane] = wv;
+      }
+      if constexpr (EPI == EPI_GATE) {                     // this warp's gate block: biases and w_c into shared memory
+        const int cb0 = n0 + half * 128, j0 = (n0 >> 1) + half * 64;
+        for (int t = lane; t < 64; t += 32) {
+          coef[t] = __ldg(ea.bias + cb0 + t);
+          coef[64 + t] = __ldg(ea.bias + cb0 + 64 + t);
+          coef[128 + t] = (j0 + t < ea.D) ? __ldg(ea.wc + j0 + t) : 0.f;
+        }
+      }
+      __syncwarp();
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
 
       if constexpr (EPI == EPI_LINEAR || EPI == EPI_BWD) {
-        if constexpr (EPI == EPI_BWD) {
-          int bg = 0; float wv = 0.f;
-          if (ea.dz && m_row < M) { bg = bag_of_row(ea.offsets, ea.bags, m_row); wv = ea.w[m_row]; }
-          mybag[lane] = bg; myw[lane] = wv;
-        }
+        constexpr int NCH = BLOCK_N / 32;
 #pragma unroll 1
-        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        for (int ch = half; ch < NCH; ch += 2) {
+          float4 src[8];
+          if constexpr (EPI == EPI_BWD) {                  // issue the ReLU-mask loads before touching TMEM
+            if (ea.relu_src) {
+#pragma unroll
+              for (int i8 = 0; i8 < 8; ++i8) {
+                const int r = (lane >> 3) + 4 * i8, m = m_base + r, col = n0 + ch * 32 + (lane & 7) * 4;
+                src[i8] = (m < M) ? *reinterpret_cast<const float4*>(ea.relu_src + (size_t)m * ea.ld_src + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
-          if (ch == BLOCK_N / 32 - 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          if (ch + 2 >= NCH) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
           stage_chunk(stg, STG_LD, 0, v, lane);
           __syncwarp();
 #pragma unroll
@@ -211,10 +261,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float o[4] = {q.x, q.y, q.z, q.w};
               if constexpr (EPI == EPI_LINEAR) {
                 if (ea.bias) { float4 b4 = *reinterpret_cast<const float4*>(ea.bias + col); o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
+                if (ea.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+                if (ea.drop.active) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (ea.relu) o[e] = fmaxf(o[e], 0.f);
-                  o[e] *= ea.drop.scale((uint64_t)m * N + col + e);
+                  for (int e = 0; e < 4; ++e) o[e] = ea.drop.keep((uint64_t)m * N + col + e) ? o[e] * ea.drop.inv_keep : 0.f;
                 }
               } else {
                 if (ea.dz) {
@@ -223,7 +273,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   o[0] = fmaf(wv, d4.x, o[0]); o[1] = fmaf(wv, d4.y, o[1]); o[2] = fmaf(wv, d4.z, o[2]); o[3] = fmaf(wv, d4.w, o[3]);
                 }
                 if (ea.relu_src) {
-                  float4 s4 = *reinterpret_cast<const float4*>(ea.relu_src + (size_t)m * ea.ld_src + col);
+                  const float4 s4 = src[i8];
                   o[0] = s4.x > 0.f ? o[0] * ea.inv_keep : 0.f; o[1] = s4.y > 0.f ? o[1] * ea.inv_keep : 0.f;
                   o[2] = s4.z > 0.f ? o[2] * ea.inv_keep : 0.f; o[3] = s4.w > 0.f ? o[3] * ea.inv_keep : 0.f;
                 }
@@ -234,50 +284,39 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
       } else if constexpr (EPI == EPI_GATE) {
-        // BLOCK_N = 256 = two packed gate blocks (64 tanh | 64 sigmoid columns each)
+        // BLOCK_N = 256 = two packed gate blocks (64 tanh | 64 sigmoid columns); this warp owns block `half`
+        static_assert(EPI != EPI_GATE || BLOCK_N == 256, "gate epilogue expects 256-column tiles");
         float partial = 0.f;
+        const bool train = ea.drop_a.active != 0;
 #pragma unroll 1
-        for (int g = 0; g < BLOCK_N / 128; ++g) {
+        for (int jc = 0; jc < 2; ++jc) {
+          const int ca = half * 128 + jc * 32, cb = ca + 64;
+          const int j0 = (n0 >> 1) + half * 64 + jc * 32;   // logical gate column of element 0
+          float va[32], vb[32];
+          tmem_ld32(taddr + ca, va);
+          tmem_ld32(taddr + cb, vb);
+          if (jc == 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          const uint64_t idx0 = (uint64_t)m_row * ea.D + j0;
+          if (train) partial = gate_chunk<FAST, true>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, idx0, partial);
+          else partial = gate_chunk<FAST, false>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, idx0, partial);
+          if (ea.ab) {
 #pragma unroll 1
-          for (int jc = 0; jc < 2; ++jc) {
-            const int ca = g * 128 + jc * 32, cb = ca + 64;
-            const int j0 = (n0 >> 1) + g * 64 + jc * 32;     // logical gate column of element 0
-            float va[32], vb[32];
-            tmem_ld32(taddr + ca, va);
-            tmem_ld32(taddr + cb, vb);
-            if (g == BLOCK_N / 128 - 1 && jc == 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+            for (int hb = 0; hb < 2; ++hb) {
+              if (hb == 0) stage_chunk(stg, STG_LD, 0, va, lane); else stage_chunk(stg, STG_LD, 0, vb, lane);
+              __syncwarp();
+              const int cbase = n0 + (hb == 0 ? ca : cb);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float xa = va[i] + __ldg(ea.bias + n0 + ca + i), xb = vb[i] + __ldg(ea.bias + n0 + cb + i);
-              float a, b;
-              if (FAST) { a = fast_tanh(xa); b = fmaf(0.5f, fast_tanh(0.5f * xb), 0.5f); }
-              else { a = tanhf(xa); b = sigmoidf_(xb); }
-              va[i] = a; vb[i] = b;
-              const int j = j0 + i;
-              if (j < ea.D && m_row < M) {
-                const float ad = a * ea.drop_a.scale((uint64_t)m_row * ea.D + j), bd = b * ea.drop_b.scale((uint64_t)m_row * ea.D + j);
-                partial = fmaf(ad * bd, __ldg(ea.wc + j), partial);
+              for (int i8 = 0; i8 < 8; ++i8) {
+                const int r = (lane >> 3) + 4 * i8, c4 = lane & 7, m = m_base + r;
+                if (m < M)
+                  *reinterpret_cast<float4*>(ea.ab + (size_t)m * ea.ldo + cbase + c4 * 4) =
+                      *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
               }
-            }
-            if (ea.ab) {
-#pragma unroll 1
-              for (int half = 0; half < 2; ++half) {
-                if (half == 0) stage_chunk(stg, STG_LD, 0, va, lane); else stage_chunk(stg, STG_LD, 0, vb, lane);
-                __syncwarp();
-                const int cbase = n0 + (half == 0 ? ca : cb);
-#pragma unroll
-                for (int i8 = 0; i8 < 8; ++i8) {
-                  const int r = (lane >> 3) + 4 * i8, c4 = lane & 7, m = m_base + r;
-                  if (m < M)
-                    *reinterpret_cast<float4*>(ea.ab + (size_t)m * ea.ldo + cbase + c4 * 4) =
-                        *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
-                }
-                __syncwarp();
-              }
+              __syncwarp();
             }
           }
         }
-        if (m_row < M) ea.part[(size_t)nt * M + m_row] = partial;
+        if (m_row < M) ea.part[(size_t)(nt * 2 + half) * M + m_row] = partial;   // one partial per 128-column gate block
       } else if constexpr (EPI == EPI_LN) {
         // BLOCK_N == 128 == d: the whole row lives in this thread's registers
         float v[128];
@@ -358,7 +397,7 @@ static int launch_rows(const float* A, const float* W, int rows, int K, int N, c
   }
   const int total = cdiv(rows, TILE_M) * (N / BLOCK_N);
   const int grid = min(total, sm_count());
-  kern<<<grid, 256, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -524,7 +563,7 @@ int tc_gated_score_fwd(const float* v, const float* Wp, const float* bp, const f
   ea.bias = bp; ea.ab = ab; ea.ldo = abw; ea.wc = wc; ea.part = part; ea.D = D; ea.drop_a = da; ea.drop_b = db;
   if (precision == ADVMIL_TF32) ADVMIL_TRY((launch_rows<256, EPI_GATE, true>(v, Wp, rows, L, abw, ea, st)));
   else ADVMIL_TRY((launch_rows<256, EPI_GATE, false>(v, Wp, rows, L, abw, ea, st)));
-  return gate_score_finish(part, abw / 256, rows, bc, s, st);
+  return gate_score_finish(part, abw / 128, rows, bc, s, st);
 }
 
 bool tc_embed_supported(int rows, int C, int d) { return rows >= TILE_M && C % KBLK == 0 && d == 128; }

@@ -24,29 +24,29 @@ int fill_zero(float* p, size_t n, cudaStream_t st) {
 // out[c] (+)= sum_p part[p][c]; block (32,8): 8 row groups per column
 __global__ void reduce_rows_kernel(const float* __restrict__ part, int nparts, int width /*row stride*/, int ncols,
                                    float* __restrict__ out, int accumulate) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
   if (c < ncols) {
     int p = threadIdx.y;
-    for (; p + 24 < nparts; p += 32) {
-      float a0 = part[(size_t)p * width + c], a1 = part[(size_t)(p + 8) * width + c];
-      float a2 = part[(size_t)(p + 16) * width + c], a3 = part[(size_t)(p + 24) * width + c];
+    for (; p + 96 < nparts; p += 128) {
+      float a0 = part[(size_t)p * width + c], a1 = part[(size_t)(p + 32) * width + c];
+      float a2 = part[(size_t)(p + 64) * width + c], a3 = part[(size_t)(p + 96) * width + c];
       acc += (a0 + a1) + (a2 + a3);
     }
-    for (; p < nparts; p += 8) acc += part[(size_t)p * width + c];
+    for (; p < nparts; p += 32) acc += part[(size_t)p * width + c];
   }
   sm[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && c < ncols) {
     float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x];
+    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
     out[c] = accumulate ? out[c] + t : t;
   }
 }
 static int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
-  reduce_rows_kernel<<<cdiv(width, 32), dim3(32, 8), 0, st>>>(part, nparts, width, width, out, accumulate);
+  reduce_rows_kernel<<<cdiv(width, 32), dim3(32, 32), 0, st>>>(part, nparts, width, width, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -183,7 +183,7 @@ __global__ void seg_stats_kernel(const float* __restrict__ s, const int32_t* __r
 }
 
 // grid (maxchunks, bags), 256 threads = RG row groups x W4 float4 columns
-__global__ void __launch_bounds__(256) seg_pool_partial_kernel(
+__global__ void __launch_bounds__(512) seg_pool_partial_kernel(
     const float* __restrict__ s, const float* __restrict__ v, const int32_t* __restrict__ offsets,
     const float* __restrict__ stats, int width, int want_mean, float* __restrict__ w,
     float* __restrict__ part /*[offsets[b]/POOL_CH + b + chunk][width]*/, float* __restrict__ part_mean) {
@@ -250,10 +250,11 @@ __global__ void seg_pool_final_kernel(const float* __restrict__ part, const floa
   int nch = (len + POOL_CH - 1) / POOL_CH;
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float t = 0.f, tm = 0.f;
+    const size_t base = ((size_t)(offsets[b] / POOL_CH + b)) * width + c;
+#pragma unroll 8
     for (int k = 0; k < nch; ++k) {
-      size_t o = ((size_t)(offsets[b] / POOL_CH + b + k)) * width + c;
-      t += part[o];
-      if (mean) tm += part_mean[o];
+      t += part[base + (size_t)k * width];
+      if (mean) tm += part_mean[base + (size_t)k * width];
     }
     z[(size_t)b * width + c] = t;
     if (mean) mean[(size_t)b * width + c] = tm / (float)len;
@@ -278,12 +279,13 @@ int seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets,
   float* stats = ws;
   float* part = ws + align_up(2 * (size_t)bags, 64);
   float* part_mean = part + ((size_t)rows / POOL_CH + bags + 1) * width;
-  seg_stats_kernel<<<bags, 256, 0, st>>>(s, offsets, stats);
+  seg_stats_kernel<<<bags, 1024, 0, st>>>(s, offsets, stats);
   ADVMIL_CHECK_LAUNCH();
   int W4 = width / 4;
-  int RG = min(256 / W4, POOL_CH);
+  int threads = (W4 % 32 == 0 && 4 * W4 <= 512) ? 4 * W4 : 256;      // 384 threads for width 384: 4 full row groups
+  int RG = min(threads / W4, POOL_CH);
   size_t smem = (POOL_CH + (size_t)RG * width * (mean ? 2 : 1)) * sizeof(float);
-  seg_pool_partial_kernel<<<dim3(maxchunks, bags), 256, smem, st>>>(s, v, offsets, stats, width, mean ? 1 : 0, w,
+  seg_pool_partial_kernel<<<dim3(maxchunks, bags), threads, smem, st>>>(s, v, offsets, stats, width, mean ? 1 : 0, w,
                                                                      part, part_mean);
   ADVMIL_CHECK_LAUNCH();
   seg_pool_final_kernel<<<bags, 256, 0, st>>>(part, mean ? part_mean : nullptr, offsets, width, z, mean);
@@ -304,20 +306,22 @@ __global__ void bag_dot_kernel(const float* __restrict__ a, const float* __restr
   if (threadIdx.x == 0) out[bag] = acc;
 }
 
-__global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
+// one thread per gate-column pair (blockDim = abw/2 rounded up to a warp multiple, <= 512), rows of the chunk unrolled x4;
+// also accumulates the column sums of dAB (the packed gate-bias gradient) so no separate pass over dAB is needed
+__global__ void __launch_bounds__(512) pool_gate_bwd_kernel(
     const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ dz,
     const float* __restrict__ gz, const float* __restrict__ ab, const float* __restrict__ wc,
     const int32_t* __restrict__ offsets, int rows, int bags, int L, int D, int abw, Drop da, Drop db,
-    float* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/) {
+    float* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
   __shared__ float ds_s[ROWS_PER_CTA];
   __shared__ float red[33];
-  int row0 = blockIdx.x * ROWS_PER_CTA;
-  int nrows = min(ROWS_PER_CTA, rows - row0);
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * ROWS_PER_CTA;
+  const int nrows = min(ROWS_PER_CTA, rows - row0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // phase 1: one warp per row: g = dz[bag] . v[row]
-  for (int r = wid; r < nrows; r += 8) {
-    int row = row0 + r;
-    int bag = bag_of_row(offsets, bags, row);
+  for (int r = wid; r < nrows; r += nw) {
+    const int row = row0 + r;
+    const int bag = bag_of_row(offsets, bags, row);
     const float* vr = v + (size_t)row * L;
     const float* dzr = dz + (size_t)bag * L;
     float acc = 0.f;
@@ -330,30 +334,51 @@ __global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
     if (lane == 0) ds_s[r] = w[row] * (acc - gz[bag]);
   }
   __syncthreads();
-  // phase 2: thread per gate column pair, loop over the rows of this chunk
-  int npairs = abw >> 1;
+  // phase 2
+  const int npairs = abw >> 1;
   for (int q = threadIdx.x; q < npairs; q += blockDim.x) {
-    int ca = gate_col_a(q);
-    bool valid = q < D;
-    float wcj = valid ? wc[q] : 0.f;
-    float dwc = 0.f;
-    for (int r = 0; r < nrows; ++r) {
-      size_t row = (size_t)(row0 + r);
-      float oa = 0.f, ob = 0.f;
-      if (valid) {
-        float a = ab[row * abw + ca], b = ab[row * abw + ca + 64];
-        float sa = da.scale(row * D + q), sb = db.scale(row * D + q);
-        float ad = a * sa, bd = b * sb;
-        float ds = ds_s[r];
-        float du = ds * wcj;
-        oa = du * bd * sa * (1.f - a * a);
-        ob = du * ad * sb * b * (1.f - b);
-        dwc = fmaf(ds, ad * bd, dwc);
+    const int ca = gate_col_a(q);
+    const bool valid = q < D;
+    const float wcj = valid ? wc[q] : 0.f;
+    float dwc = 0.f, sa_sum = 0.f, sb_sum = 0.f;
+    const bool tr = da.active != 0;
+    int r = 0;
+    for (; r + 3 < nrows; r += 4) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t row = (size_t)(row0 + r + u);
+        a[u] = valid ? ab[row * abw + ca] : 0.f;
+        b[u] = valid ? ab[row * abw + ca + 64] : 0.f;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t row = (size_t)(row0 + r + u);
+        float sa = 1.f, sb = 1.f;
+        if (tr && valid) { sa = da.keep(row * D + q) ? da.inv_keep : 0.f; sb = db.keep(row * D + q) ? db.inv_keep : 0.f; }
+        const float ad = a[u] * sa, bd = b[u] * sb, ds = ds_s[r + u], du = ds * wcj;
+        const float oa = du * bd * sa * (1.f - a[u] * a[u]);
+        const float ob = du * ad * sb * b[u] * (1.f - b[u]);
+        dwc = fmaf(ds, ad * bd, dwc);
+        sa_sum += oa; sb_sum += ob;
+        dAB[row * abw + ca] = oa;
+        dAB[row * abw + ca + 64] = ob;
+      }
+    }
+    for (; r < nrows; ++r) {
+      const size_t row = (size_t)(row0 + r);
+      const float a = valid ? ab[row * abw + ca] : 0.f, b = valid ? ab[row * abw + ca + 64] : 0.f;
+      float sa = 1.f, sb = 1.f;
+      if (tr && valid) { sa = da.keep(row * D + q) ? da.inv_keep : 0.f; sb = db.keep(row * D + q) ? db.inv_keep : 0.f; }
+      const float ad = a * sa, bd = b * sb, ds = ds_s[r], du = ds * wcj;
+      const float oa = du * bd * sa * (1.f - a * a), ob = du * ad * sb * b * (1.f - b);
+      dwc = fmaf(ds, ad * bd, dwc);
+      sa_sum += oa; sb_sum += ob;
       dAB[row * abw + ca] = oa;
       dAB[row * abw + ca + 64] = ob;
     }
     if (valid) part[(size_t)blockIdx.x * (D + 1) + q] = dwc;
+    if (part_b) { part_b[(size_t)blockIdx.x * abw + ca] = sa_sum; part_b[(size_t)blockIdx.x * abw + ca + 64] = sb_sum; }
   }
   float t = 0.f;
   for (int r = threadIdx.x; r < nrows; r += blockDim.x) t += ds_s[r];
@@ -363,21 +388,26 @@ __global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
 
 int pool_gate_bwd(const float* v, const float* w, const float* z, const float* dz, const float* ab, const float* wc,
                   const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, float* dAB,
-                  float* dwc, float* dbc, int accumulate, float* ws, cudaStream_t st) {
+                  float* dwc, float* dbc, float* dbp, int accumulate, float* ws, cudaStream_t st) {
   ADVMIL_REQUIRE(L % 4 == 0, "pool_gate_bwd: L %d must be a multiple of 4", L);
-  int chunks = row_chunks(rows);
+  const int chunks = row_chunks(rows);
+  const int abw = gate_width(D);
   float* gz = ws;
   float* part = ws + align_up((size_t)bags, 64);
+  float* part_b = dbp ? part + align_up((size_t)chunks * (D + 1), 64) : nullptr;
   bag_dot_kernel<<<bags, 128, 0, st>>>(dz, z, L, gz);
   ADVMIL_CHECK_LAUNCH();
-  pool_gate_bwd_kernel<<<chunks, 256, 0, st>>>(v, w, dz, gz, ab, wc, offsets, rows, bags, L, D, gate_width(D), da, db,
-                                                dAB, part);
+  const int threads = min(512, ((abw / 2 + 31) / 32) * 32);
+  pool_gate_bwd_kernel<<<chunks, threads, 0, st>>>(v, w, dz, gz, ab, wc, offsets, rows, bags, L, D, abw, da, db, dAB, part, part_b);
   ADVMIL_CHECK_LAUNCH();
-  // dwc: columns [0,D) of the partials; dbc: column D
-  reduce_rows_kernel<<<cdiv(D, 32), dim3(32, 8), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
+  reduce_rows_kernel<<<cdiv(D, 32), dim3(32, 32), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<1, dim3(32, 8), 0, st>>>(part + D, chunks, D + 1, 1, dbc, accumulate);
+  reduce_rows_kernel<<<1, dim3(32, 32), 0, st>>>(part + D, chunks, D + 1, 1, dbc, accumulate);
   ADVMIL_CHECK_LAUNCH();
+  if (dbp) {   // packed gate-bias gradient (never accumulated: the caller unpacks it with its own accumulate flag)
+    reduce_rows_kernel<<<cdiv(abw, 32), dim3(32, 32), 0, st>>>(part_b, chunks, abw, abw, dbp, 0);
+    ADVMIL_CHECK_LAUNCH();
+  }
   return ADVMIL_OK;
 }
 
@@ -459,20 +489,85 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
   }
 }
 
+// d == 128: one float4 per lane per row, two rows in flight per warp
+__global__ void __launch_bounds__(256) ln_pool_bwd128_kernel(
+    const float* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int rows, float eps, float* __restrict__ d_y, float* __restrict__ part) {
+  __shared__ float sm[8 * 3 * 128];
+  const int row0 = blockIdx.x * ROWS_PER_CTA;
+  const int nrows = min(ROWS_PER_CTA, rows - row0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4), b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
+  const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+  float pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f}, pbias[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = wid * 2; r < nrows; r += 16) {
+    float4 y4[2], e4[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ok[u] = r + u < nrows;
+      const size_t row = (size_t)(row0 + r + u);
+      y4[u] = ok[u] ? *reinterpret_cast<const float4*>(y_pre + row * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      e4[u] = ok[u] ? *reinterpret_cast<const float4*>(d_emb + (row >> 4) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t row = (size_t)(row0 + r + u);
+      const float y[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w}, ge[4] = {e4[u].x, e4[u].y, e4[u].z, e4[u].w};
+      const float mean = warp_sum(y[0] + y[1] + y[2] + y[3]) * (1.0f / 128.0f);
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float c = y[k] - mean; q = fmaf(c, c, q); }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
+      float xh[4], dxh[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xh[k] = (y[k] - mean) * rstd;
+        const float e = fmaf(xh[k], g[k], be[k]);
+        const float de = (e > 0.f && ok[u]) ? ge[k] * (1.0f / 16.0f) : 0.f;
+        pg[k] = fmaf(de, xh[k], pg[k]);
+        pb[k] += de;
+        dxh[k] = de * g[k];
+        s1 += dxh[k];
+        s2 = fmaf(dxh[k], xh[k], s2);
+      }
+      const float m1 = warp_sum(s1) * (1.0f / 128.0f), m2 = warp_sum(s2) * (1.0f / 128.0f);
+      float dy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { dy[k] = rstd * (dxh[k] - m1 - xh[k] * m2); if (ok[u]) pbias[k] += dy[k]; }
+      if (ok[u]) *reinterpret_cast<float4*>(d_y + row * 128 + lane * 4) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sm[(wid * 3 + 0) * 128 + lane * 4 + k] = pg[k];
+    sm[(wid * 3 + 1) * 128 + lane * 4 + k] = pb[k];
+    sm[(wid * 3 + 2) * 128 + lane * 4 + k] = pbias[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += sm[wv * 3 * 128 + i];
+    part[(size_t)blockIdx.x * 3 * 128 + i] = t;
+  }
+}
+
 int ln_pool_bwd(const float* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
                 float eps, float* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate, float* ws,
                 cudaStream_t st) {
   ADVMIL_REQUIRE(d <= 256, "ln_pool_bwd: d %d > 256 unsupported", d);
   int chunks = row_chunks(rows);
   size_t smem = (size_t)8 * 3 * d * sizeof(float);
-  if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>(y_pre, d_emb, gamma, beta, rows, d, eps, d_y, ws);
+  if (d == 128) ln_pool_bwd128_kernel<<<chunks, 256, 0, st>>>(y_pre, d_emb, gamma, beta, rows, eps, d_y, ws);
+  else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>(y_pre, d_emb, gamma, beta, rows, d, eps, d_y, ws);
   else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>(y_pre, d_emb, gamma, beta, rows, d, eps, d_y, ws);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 8), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
+  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 8), 0, st>>>(ws + d, chunks, 3 * d, d, dbeta, accumulate);
+  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws + d, chunks, 3 * d, d, dbeta, accumulate);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 8), 0, st>>>(ws + 2 * d, chunks, 3 * d, d, dbias, accumulate);
+  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws + 2 * d, chunks, 3 * d, d, dbias, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

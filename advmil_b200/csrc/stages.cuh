@@ -42,8 +42,11 @@ inline int row_chunks(int rows) { return cdiv(rows, ROWS_PER_CTA); }
 // pooling + gate backward: ds = w (dz.v - dz.z); dAB packed; partial dwc/dbc per chunk -> reduced into dwc, dbc
 int pool_gate_bwd(const float* v, const float* w, const float* z, const float* dz, const float* ab, const float* wc,
                   const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, float* dAB,
-                  float* dwc, float* dbc, int accumulate, float* ws /* >= row_chunks*(D+1) + bags floats */,
-                  cudaStream_t st);
+                  float* dwc, float* dbc, float* dbp /* packed gate-bias grad [abw] or null */, int accumulate,
+                  float* ws /* >= pool_gate_ws_floats */, cudaStream_t st);
+inline size_t pool_gate_ws_floats(int rows, int bags, int D) {
+  return align_up((size_t)bags, 64) + align_up((size_t)row_chunks(rows) * (D + 1), 64) + (size_t)row_chunks(rows) * gate_width(D) + 64;
+}
 // LayerNorm + ReLU + region-mean backward per row; partials of dgamma/dbeta/dbias reduced into the outputs
 int ln_pool_bwd(const float* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
                 float eps, float* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate,

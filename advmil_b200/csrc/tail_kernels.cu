@@ -15,7 +15,7 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ Wrow, const 
 // K4: generator head  (model/backbone.py:73-77,85; model/GANSurv.py:32-49; model/model_utils.py:116-133)
 // grid (bags, samples)
 // =============================================================================================
-__global__ void __launch_bounds__(256) gen_head_fwd_kernel(AdvmilGenParams p, const float* __restrict__ z,
+__global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, const float* __restrict__ z,
                                                            const float* __restrict__ noise0,
                                                            const float* __restrict__ noise1, int bags, Drop drho,
                                                            Drop dmlp0, float* __restrict__ H, float* __restrict__ H1,
@@ -74,12 +74,12 @@ int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, 
   ADVMIL_REQUIRE(p.Wrho != nullptr || p.o == p.h, "gen_head: no rho layer requires o == h");
   size_t smem = (size_t)(p.h + 2 * p.o + 2 * p.hid + 40) * sizeof(float);
   ADVMIL_REQUIRE(smem <= 48 * 1024, "gen_head: dims too large for the head kernel (h=%d o=%d)", p.h, p.o);
-  gen_head_fwd_kernel<<<dim3(bags, samples), 256, smem, st>>>(p, z, noise0, noise1, bags, drho, dmlp0, H, H1, pre, pred);
+  gen_head_fwd_kernel<<<dim3(bags, samples), 1024, smem, st>>>(p, z, noise0, noise1, bags, drho, dmlp0, H, H1, pre, pred);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
-__global__ void __launch_bounds__(256) gen_head_bwd_kernel(AdvmilGenParams p, const float* __restrict__ d_pred,
+__global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, const float* __restrict__ d_pred,
                                                            const float* __restrict__ H, const float* __restrict__ H1,
                                                            const float* __restrict__ pred, float inv_keep_rho,
                                                            float inv_keep_mlp0, float* __restrict__ dz,
@@ -108,8 +108,18 @@ __global__ void __launch_bounds__(256) gen_head_bwd_kernel(AdvmilGenParams p, co
   const int in0 = o * (1 + p.noise0);
   for (int i = threadIdx.x; i < o; i += blockDim.x) {
     float acc = 0.f;
-    if (head) for (int j = 0; j < hid; ++j) acc = fmaf(p.W0[(size_t)j * in0 + i], d1[j], acc);
-    else acc = d_pred[(size_t)b * o + i];
+    if (head) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int j = 0;
+      for (; j + 3 < hid; j += 4) {
+        a0 = fmaf(p.W0[(size_t)j * in0 + i], d1[j], a0);
+        a1 = fmaf(p.W0[(size_t)(j + 1) * in0 + i], d1[j + 1], a1);
+        a2 = fmaf(p.W0[(size_t)(j + 2) * in0 + i], d1[j + 2], a2);
+        a3 = fmaf(p.W0[(size_t)(j + 3) * in0 + i], d1[j + 3], a3);
+      }
+      for (; j < hid; ++j) a0 = fmaf(p.W0[(size_t)j * in0 + i], d1[j], a0);
+      acc = (a0 + a1) + (a2 + a3);
+    } else acc = d_pred[(size_t)b * o + i];
     if (p.Wrho) acc = H[(size_t)b * o + i] > 0.f ? acc * inv_keep_rho : 0.f;
     dH[i] = acc;
     dHpre[(size_t)b * o + i] = acc;
@@ -118,8 +128,16 @@ __global__ void __launch_bounds__(256) gen_head_bwd_kernel(AdvmilGenParams p, co
   for (int k = threadIdx.x; k < h; k += blockDim.x) {
     float acc;
     if (p.Wrho) {
-      acc = 0.f;
-      for (int i = 0; i < o; ++i) acc = fmaf(p.Wrho[(size_t)i * h + k], dH[i], acc);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int i = 0;
+      for (; i + 3 < o; i += 4) {
+        a0 = fmaf(p.Wrho[(size_t)i * h + k], dH[i], a0);
+        a1 = fmaf(p.Wrho[(size_t)(i + 1) * h + k], dH[i + 1], a1);
+        a2 = fmaf(p.Wrho[(size_t)(i + 2) * h + k], dH[i + 2], a2);
+        a3 = fmaf(p.Wrho[(size_t)(i + 3) * h + k], dH[i + 3], a3);
+      }
+      for (; i < o; ++i) a0 = fmaf(p.Wrho[(size_t)i * h + k], dH[i], a0);
+      acc = (a0 + a1) + (a2 + a3);
     } else {
       acc = dH[k];
     }
@@ -131,7 +149,7 @@ int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, 
                  int bags, float inv_keep_rho, float inv_keep_mlp0, float* dz, float* dHpre, float* dH1pre, float* dpre,
                  cudaStream_t st) {
   size_t smem = (size_t)(p.hid + p.o) * sizeof(float);
-  gen_head_bwd_kernel<<<bags, 256, smem, st>>>(p, d_pred, H, H1, pred, inv_keep_rho, inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
+  gen_head_bwd_kernel<<<bags, 512, smem, st>>>(p, d_pred, H, H1, pred, inv_keep_rho, inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -166,7 +184,7 @@ int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in
 // K7/K8 tail: bag MLP fc2, time embedding, inner product, projection
 // (model/model_utils.py:200-206; model/GANSurv.py:89-105)
 // =============================================================================================
-__global__ void __launch_bounds__(128) rlip_tail_fwd_kernel(AdvmilDiscParams p, const float* __restrict__ bagv,
+__global__ void __launch_bounds__(512) rlip_tail_fwd_kernel(AdvmilDiscParams p, const float* __restrict__ bagv,
                                                             const float* __restrict__ fbar, const float* __restrict__ t,
                                                             Drop dfc2, float* __restrict__ g1, float* __restrict__ hx,
                                                             float* __restrict__ u1, float* __restrict__ ht,
@@ -230,7 +248,7 @@ int rlip_tail_fwd(const AdvmilDiscParams& p, const float* bagv, const float* fba
                   const Drop& dfc2, float* g1, float* hx, float* u1, float* ht, float* out, cudaStream_t st) {
   ADVMIL_REQUIRE(p.t2 == p.d, "rlip_tail: time embedding width %d must equal d %d", p.t2, p.d);
   size_t smem = (size_t)(p.d * 2 + p.d / 2 + p.t1 + p.t2 + 40) * sizeof(float);
-  rlip_tail_fwd_kernel<<<bags, 128, smem, st>>>(p, bagv, fbar, t, dfc2, g1, hx, u1, ht, out);
+  rlip_tail_fwd_kernel<<<bags, 512, smem, st>>>(p, bagv, fbar, t, dfc2, g1, hx, u1, ht, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -266,6 +284,7 @@ __global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
   __syncthreads();
   for (int j = threadIdx.x; j < dh; j += blockDim.x) {
     float acc = 0.f;
+#pragma unroll 8
     for (int c = 0; c < d; ++c) acc = fmaf(p.F2b_w[(size_t)c * dh + j], dhx[c], acc);
     acc = g1[(size_t)b * dh + j] > 0.f ? acc * inv_keep_fc2 : 0.f;
     dg1[j] = acc;
@@ -273,6 +292,7 @@ __global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
   }
   for (int k = threadIdx.x; k < t1; k += blockDim.x) {
     float acc = 0.f;
+#pragma unroll 8
     for (int c = 0; c < t2; ++c) acc = fmaf(p.T2_w[(size_t)c * t1 + k], dht[c], acc);
     acc = u1[(size_t)b * t1 + k] > 0.f ? acc : 0.f;
     du1[k] = acc;
@@ -281,6 +301,7 @@ __global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float acc = 0.f;
+#pragma unroll 8
     for (int j = 0; j < dh; ++j) acc = fmaf(p.F2a_w[(size_t)j * d + c], dg1[j], acc);
     d_bagv[(size_t)b * d + c] = acc;
   }
@@ -403,11 +424,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void abs_sum_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
   __shared__ float red[33];
   float a0 = 0.f, a1 = 0.f;
-  int64_t i = threadIdx.x;
-  for (; i + blockDim.x < n; i += 2 * (int64_t)blockDim.x) { a0 += fabsf(p[i]); a1 += fabsf(p[i + blockDim.x]); }
-  for (; i < n; i += blockDim.x) a0 += fabsf(p[i]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) { a0 += fabsf(p[i]); a1 += fabsf(p[i + stride]); }
+  for (; i < n; i += stride) a0 += fabsf(p[i]);
   float acc = block_sum(a0 + a1, red);
-  if (threadIdx.x == 0) out[0] += acc;
+  if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
 // =============================================================================================
@@ -539,7 +561,7 @@ extern "C" int advmil_adam_step(float* param, const float* grad, float* m, float
 
 extern "C" int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream) {
   if (n <= 0) return ADVMIL_OK;
-  abs_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p, n, out);
+  abs_sum_kernel<<<(int)min((int64_t)148, (n + 2047) / 2048), 256, 0, (cudaStream_t)stream>>>(p, n, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
