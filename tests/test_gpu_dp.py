@@ -1,0 +1,93 @@
+"""GPU data parallel: a 2-rank NCCL AdvStep on sharded bags updates the parameters exactly like one rank on all bags
+(SURVEY.md §8e correctness check).  Needs >= 2 GPUs (skipped otherwise): run with `gpurun --gpus 2`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+NS = [320, 1600, 160, 640, 96, 2048]
+
+
+def _build(dev):
+    from oracle import advmil_oracle as O
+    from tests.util import build_D, build_G
+    G, D = build_G(device=dev), build_D(device=dev)
+    G.load_state_dict(O.synth_state_dict(O.G_SHAPES(), 1))
+    D.load_state_dict(O.synth_state_dict(O.D_SHAPES(), 2))
+    G.backbone.p = 0.0          # dropout off so that sharded and single-process runs see identical arithmetic
+    G.p_head = 0.0
+    D.net_pair_one.p = 0.0
+    return G, D
+
+
+def _inputs():
+    from oracle import advmil_oracle as O
+    xs = [O.synth_bag(n, 80 + i) for i, n in enumerate(NS)]
+    t, e = O.synth_labels(len(NS), 5)
+    e[0] = 1.0
+    vis = torch.tensor([1, 1, 0, 1, 1, 1], dtype=torch.uint8)
+    rng = np.random.default_rng(6)
+    nd = torch.tensor(rng.uniform(size=(len(NS), 192)), dtype=torch.float32)
+    ng = torch.tensor(rng.uniform(size=(len(NS), 192)), dtype=torch.float32)
+    return xs, t, e, vis, nd, ng
+
+
+def _run(rank, world, port, q):
+    from advmil_b200 import ops
+    from advmil_b200.dataset.packed import shard_bags_balanced
+    from advmil_b200.step import AdvStep
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                             device_id=dev)
+    G, D = _build(dev)
+    eng = AdvStep(G, D)
+    xs, t, e, vis, nd, ng = _inputs()
+    mine = shard_bags_balanced(NS, world)[rank]
+    bags = ops.PackedBags.from_list([xs[i].to(dev) for i in mine])
+    out = eng.step(bags, t[mine].to(dev), e[mine].to(dev), vis[mine].to(dev), noise_d=nd[mine].to(dev),
+                   noise_g=ng[mine].to(dev))
+    torch.cuda.synchronize()
+    losses = out["losses"].clone()
+    if world > 1:
+        torch.distributed.all_reduce(losses[:4])          # loss kernels write rank-local contributions
+    if rank == 0:
+        q.put((eng.G.grad.cpu().numpy(), eng.D.grad.cpu().numpy(), losses.cpu().numpy()))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_step_equals_single_rank():
+    ctx = mp.get_context("spawn")
+    res = {}
+    for world in (1, 2):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_run, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res[world] = q.get()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+    g1, d1, l1 = res[1]
+    g2, d2, l2 = res[2]
+    # all-reduced gradients of both networks and the global losses; only the fp32 reduction order differs
+    assert float(np.abs(g1 - g2).max()) <= 1e-5 * float(np.abs(g1).max())
+    assert float(np.abs(d1 - d2).max()) <= 1e-5 * float(np.abs(d1).max())
+    assert float(np.abs(l1[:4] - l2[:4]).max()) < 1e-5
