@@ -13,6 +13,7 @@
 //
 // Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
 // (TMEM lane quarter = warp % 4).
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -120,7 +121,10 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
   return partial;
 }
 
-template <int BLOCK_N, int EPI, bool FAST>
+// CL = cluster size (1 or 2).  CL == 2: the two CTAs of a cluster work on two consecutive 128-row blocks of the SAME
+// N-tile in lock step; each loads half of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the
+// L2 -> SM traffic of the (per-tile re-streamed) weights, which is what bounds these kernels once the epilogues are cheap.
+template <int BLOCK_N, int EPI, bool FAST, int CL>
 __global__ void __launch_bounds__(RowCfg<BLOCK_N, EPI>::THREADS, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
   using Cfg = RowCfg<BLOCK_N, EPI>;
@@ -142,18 +146,23 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + TILE_M - 1) / TILE_M, num_n = N / BLOCK_N;
-  const int total = num_m * num_n, kblocks = K / KBLK;
+  const int num_mg = (num_m + CL - 1) / CL;              // groups of CL consecutive row blocks
+  const int total = num_mg * num_n, kblocks = K / KBLK;   // work items per cluster (= per CTA when CL == 1)
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int work0 = blockIdx.x / CL, work_stride = gridDim.x / CL;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peer barriers must be initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -161,13 +170,19 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * TILE_M, n0 = (tile % num_n) * BLOCK_N;
+      for (int tile = work0; tile < total; tile += work_stride) {
+        const int m0 = ((tile / num_n) * CL + crank) * TILE_M, n0 = (tile % num_n) * BLOCK_N;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait(&empty[stage], phase ^ 1);          // CL == 2: both CTAs have retired their MMAs on this slot
           mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(A_s + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * KBLK, m0);
-          tma_load_2d(B_s + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kb * KBLK, n0);
+          if (CL == 1) {
+            tma_load_2d(B_s + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kb * KBLK, n0);
+          } else {                                      // my half of the weight tile, multicast to both CTAs
+            constexpr int HALF_ROWS = BLOCK_N / CL;
+            tma_load_2d_mcast(B_s + stage * Cfg::B_STAGE_BYTES + crank * (HALF_ROWS * KBLK * 4), &tmB, &full[stage], kb * KBLK,
+                              n0 + crank * HALF_ROWS, CMASK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -176,7 +191,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_tf32(TILE_M, BLOCK_N, 0, 0);
     int stage = 0; uint32_t phase = 0; int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int tile = work0; tile < total; tile += work_stride, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty[acc], aphase ^ 1);
       tc_fence_after();
@@ -192,7 +207,8 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint64_t bd = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
             mma_tf32(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
           }
-          mma_commit(&empty[stage]);                 // smem slot is free once these MMAs retire
+          if (CL == 1) mma_commit(&empty[stage]);    // smem slot is free once these MMAs retire
+          else mma_commit_mcast(&empty[stage], CMASK);   // ... in BOTH CTAs (each producer writes into both)
           if (kb == kblocks - 1) mma_commit(&tfull[acc]);
         }
         __syncwarp();
@@ -209,9 +225,9 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int* mybag = rowbag + ew * 32;
     float* myw = roww + ew * 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int tile = work0; tile < total; tile += work_stride, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
-      const int mt = tile / num_n, nt = tile % num_n;
+      const int mt = (tile / num_n) * CL + crank, nt = tile % num_n;
       const int m_base = mt * TILE_M + wq * 32, n0 = nt * BLOCK_N;
       const int m_row = m_base + lane;                     // the row this thread owns in TMEM
       if constexpr (EPI == EPI_BWD) {                      // per-row pooling operands (independent of the accumulator)
@@ -380,24 +396,52 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // nobody exits while a peer may still multicast into / arrive on its shared memory
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ADVMIL_TC_CLUSTER=2 enables the 2-CTA multicast variant.  Measured on B200 (round 1): no gain over single-CTA launches
+// (K1 380 vs 377 us, K2 310 vs 318 us) -- TMA multicast de-duplicates L2 reads only for clusters larger than 4 -- so the
+// default stays 1.
+static int g_cluster = -1;
+static int cluster_size() {
+  if (g_cluster < 0) { const char* e = getenv("ADVMIL_TC_CLUSTER"); g_cluster = (e && atoi(e) == 2) ? 2 : 1; }
+  return g_cluster;
 }
 
 template <int BLOCK_N, int EPI, bool FAST>
 static int launch_rows(const float* A, const float* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
   using Cfg = RowCfg<BLOCK_N, EPI>;
+  const int num_m = cdiv(rows, TILE_M), num_n = N / BLOCK_N;
+  const int CL = (cluster_size() == 2 && num_m >= 2) ? 2 : 1;
   CUtensorMap tmA, tmB;
   ADVMIL_TRY(make_tmap(&tmA, A, rows, K, TILE_M));
-  ADVMIL_TRY(make_tmap(&tmB, W, N, K, BLOCK_N));
-  auto kern = tc_rows_kernel<BLOCK_N, EPI, FAST>;
+  ADVMIL_TRY(make_tmap(&tmB, W, N, K, BLOCK_N / CL));
   static bool attr_set = false;
   if (!attr_set) {
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<BLOCK_N, EPI, FAST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<BLOCK_N, EPI, FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
-  const int total = cdiv(rows, TILE_M) * (N / BLOCK_N);
-  const int grid = min(total, sm_count());
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+  if (CL == 1) {
+    const int grid = min(num_m * num_n, sm_count());
+    tc_rows_kernel<BLOCK_N, EPI, FAST, 1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+    ADVMIL_CHECK_LAUNCH();
+    return ADVMIL_OK;
+  }
+  const int work = cdiv(num_m, 2) * num_n;
+  const int clusters = min(work, sm_count() / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int M_ = rows, N_ = N, K_ = K;
+  ADVMIL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<BLOCK_N, EPI, FAST, 2>, tmA, tmB, M_, N_, K_, ea));
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

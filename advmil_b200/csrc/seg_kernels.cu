@@ -245,19 +245,29 @@ __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
 __global__ void seg_pool_final_kernel(const float* __restrict__ part, const float* __restrict__ part_mean,
                                       const int32_t* __restrict__ offsets, int width,
                                       float* __restrict__ z, float* __restrict__ mean) {
-  int b = blockIdx.x;
-  int len = offsets[b + 1] - offsets[b];
-  int nch = (len + POOL_CH - 1) / POOL_CH;
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float t = 0.f, tm = 0.f;
+  // blockDim = (128 columns, 8 chunk groups); grid = (ceil(width/128), bags)
+  __shared__ float sm[2][8][128];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int len = offsets[b + 1] - offsets[b];
+  const int nch = (len + POOL_CH - 1) / POOL_CH;
+  float t = 0.f, tm = 0.f;
+  if (c < width) {
     const size_t base = ((size_t)(offsets[b] / POOL_CH + b)) * width + c;
-#pragma unroll 8
-    for (int k = 0; k < nch; ++k) {
+    for (int k = threadIdx.y; k < nch; k += 8) {
       t += part[base + (size_t)k * width];
       if (mean) tm += part_mean[base + (size_t)k * width];
     }
-    z[(size_t)b * width + c] = t;
-    if (mean) mean[(size_t)b * width + c] = tm / (float)len;
+  }
+  sm[0][threadIdx.y][threadIdx.x] = t;
+  sm[1][threadIdx.y][threadIdx.x] = tm;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < width) {
+    float a = 0.f, am = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { a += sm[0][g][threadIdx.x]; am += sm[1][g][threadIdx.x]; }
+    z[(size_t)b * width + c] = a;
+    if (mean) mean[(size_t)b * width + c] = am / (float)len;
   }
 }
 
@@ -288,7 +298,7 @@ int seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets,
   seg_pool_partial_kernel<<<dim3(maxchunks, bags), threads, smem, st>>>(s, v, offsets, stats, width, mean ? 1 : 0, w,
                                                                      part, part_mean);
   ADVMIL_CHECK_LAUNCH();
-  seg_pool_final_kernel<<<bags, 256, 0, st>>>(part, mean ? part_mean : nullptr, offsets, width, z, mean);
+  seg_pool_final_kernel<<<dim3(cdiv(width, 128), bags), dim3(128, 8), 0, st>>>(part, mean ? part_mean : nullptr, offsets, width, z, mean);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

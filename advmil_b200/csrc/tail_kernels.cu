@@ -4,6 +4,23 @@
 
 namespace advmil {
 
+// sum_r W[r*ld + col] * v[r], r < n: transposed mat-vec column owned by one thread (coalesced across threads);
+// four independent accumulators so the loads of consecutive rows are in flight together
+__device__ __forceinline__ float col_dot(const float* __restrict__ W, int ld, int col, const float* __restrict__ v, int n) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = 0;
+  for (; r + 7 < n; r += 8) {
+    const float w0 = __ldg(W + (size_t)r * ld + col), w1 = __ldg(W + (size_t)(r + 1) * ld + col);
+    const float w2 = __ldg(W + (size_t)(r + 2) * ld + col), w3 = __ldg(W + (size_t)(r + 3) * ld + col);
+    const float w4 = __ldg(W + (size_t)(r + 4) * ld + col), w5 = __ldg(W + (size_t)(r + 5) * ld + col);
+    const float w6 = __ldg(W + (size_t)(r + 6) * ld + col), w7 = __ldg(W + (size_t)(r + 7) * ld + col);
+    a0 = fmaf(w0, v[r], a0); a1 = fmaf(w1, v[r + 1], a1); a2 = fmaf(w2, v[r + 2], a2); a3 = fmaf(w3, v[r + 3], a3);
+    a0 = fmaf(w4, v[r + 4], a0); a1 = fmaf(w5, v[r + 5], a1); a2 = fmaf(w6, v[r + 6], a2); a3 = fmaf(w7, v[r + 7], a3);
+  }
+  for (; r < n; ++r) a0 = fmaf(__ldg(W + (size_t)r * ld + col), v[r], a0);
+  return (a0 + a1) + (a2 + a3);
+}
+
 // out[r] = dot(W[r, 0:n], v) for r handled by this warp; caller adds bias/activation
 __device__ __forceinline__ float warp_dot(const float* __restrict__ Wrow, const float* __restrict__ v, int n, int lane) {
   float acc = 0.f;
@@ -109,16 +126,7 @@ __global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, co
   for (int i = threadIdx.x; i < o; i += blockDim.x) {
     float acc = 0.f;
     if (head) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int j = 0;
-      for (; j + 3 < hid; j += 4) {
-        a0 = fmaf(p.W0[(size_t)j * in0 + i], d1[j], a0);
-        a1 = fmaf(p.W0[(size_t)(j + 1) * in0 + i], d1[j + 1], a1);
-        a2 = fmaf(p.W0[(size_t)(j + 2) * in0 + i], d1[j + 2], a2);
-        a3 = fmaf(p.W0[(size_t)(j + 3) * in0 + i], d1[j + 3], a3);
-      }
-      for (; j < hid; ++j) a0 = fmaf(p.W0[(size_t)j * in0 + i], d1[j], a0);
-      acc = (a0 + a1) + (a2 + a3);
+      acc = col_dot(p.W0, in0, i, d1, hid);
     } else acc = d_pred[(size_t)b * o + i];
     if (p.Wrho) acc = H[(size_t)b * o + i] > 0.f ? acc * inv_keep_rho : 0.f;
     dH[i] = acc;
@@ -128,16 +136,7 @@ __global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, co
   for (int k = threadIdx.x; k < h; k += blockDim.x) {
     float acc;
     if (p.Wrho) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int i = 0;
-      for (; i + 3 < o; i += 4) {
-        a0 = fmaf(p.Wrho[(size_t)i * h + k], dH[i], a0);
-        a1 = fmaf(p.Wrho[(size_t)(i + 1) * h + k], dH[i + 1], a1);
-        a2 = fmaf(p.Wrho[(size_t)(i + 2) * h + k], dH[i + 2], a2);
-        a3 = fmaf(p.Wrho[(size_t)(i + 3) * h + k], dH[i + 3], a3);
-      }
-      for (; i < o; ++i) a0 = fmaf(p.Wrho[(size_t)i * h + k], dH[i], a0);
-      acc = (a0 + a1) + (a2 + a3);
+      acc = col_dot(p.Wrho, h, k, dH, o);
     } else {
       acc = dH[k];
     }
@@ -283,26 +282,20 @@ __global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
   }
   __syncthreads();
   for (int j = threadIdx.x; j < dh; j += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < d; ++c) acc = fmaf(p.F2b_w[(size_t)c * dh + j], dhx[c], acc);
+    float acc = col_dot(p.F2b_w, dh, j, dhx, d);
     acc = g1[(size_t)b * dh + j] > 0.f ? acc * inv_keep_fc2 : 0.f;
     dg1[j] = acc;
     d_g1pre[(size_t)b * dh + j] = acc;
   }
   for (int k = threadIdx.x; k < t1; k += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < t2; ++c) acc = fmaf(p.T2_w[(size_t)c * t1 + k], dht[c], acc);
+    float acc = col_dot(p.T2_w, t1, k, dht, t2);
     acc = u1[(size_t)b * t1 + k] > 0.f ? acc : 0.f;
     du1[k] = acc;
     d_u1pre[(size_t)b * t1 + k] = acc;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < dh; ++j) acc = fmaf(p.F2a_w[(size_t)j * d + c], dg1[j], acc);
+    float acc = col_dot(p.F2a_w, d, c, dg1, dh);
     d_bagv[(size_t)b * d + c] = acc;
   }
   float acc = 0.f;

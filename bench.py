@@ -261,14 +261,20 @@ def main():
         kern[tag] = ent
     top = max(kern, key=lambda k: kern[k]["share_of_step"]) if kern else None
     roof = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if top is not None and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("rows_per_launch") == rows_per_launch and top in tj:
+            traffic = tj[top]["read"] + tj[top]["write"]   # bytes per launch from the committed ncu --set full capture
     if top is not None:
         if top in FLOP_PER_ROW:
             roof = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": peaks["tflops"],
-                    "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peaks["tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": kern[top]["tflops"] / peaks["tflops"], "traffic": traffic,
                     "peak_source": peaks["src"] + " bf16 sustained"}
         else:
             roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": kern[top]["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"]}
+                    "frac": kern[top]["gbs"] / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["src"]}
 
     # ================= CPU baseline (rank 0, N=1 only; bounded sample) =================
     cpu = None
