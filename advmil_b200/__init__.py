@@ -11,9 +11,10 @@ _PRECISION = os.environ.get("ADVMIL_PRECISION", "fp32")
 
 
 def set_precision(mode: str) -> None:
-    """'fp32' (FFMA, exact-fp32 parity), 'tf32' (tcgen05 single pass) or 'tf32x3' (tcgen05 error-compensated)."""
+    """'fp32' (FFMA, exact-fp32 parity), 'tf32' (tcgen05 kind::tf32 on the fp32 data as stored) or 'bf16' (bf16 storage of
+    x and the [rows, *] activations, tcgen05 kind::f16, fp32 accumulation / statistics / parameters)."""
     global _PRECISION
-    assert mode in ("fp32", "tf32", "tf32x3")
+    assert mode in ("fp32", "tf32", "tf32x3", "bf16")
     _PRECISION = mode
 
 

@@ -15,7 +15,8 @@ c_ip = C.c_void_p   # int32*
 
 class Bags(C.Structure):
     _fields_ = [("x", c_fp), ("offsets", c_ip), ("offsets_host", C.POINTER(C.c_int32)),
-                ("rows", C.c_int32), ("bags", C.c_int32), ("C", C.c_int32), ("max_bag_rows", C.c_int32)]
+                ("rows", C.c_int32), ("bags", C.c_int32), ("C", C.c_int32), ("max_bag_rows", C.c_int32),
+                ("elem", C.c_int32)]
 
 
 GEN_TENSORS = ["W1", "b1", "Wa", "ba", "Wb", "bb", "wc", "bc", "Wrho", "brho", "W0", "b0", "Wl", "bl"]
@@ -90,14 +91,15 @@ SYMBOLS = {
     "advmil_disc_head_fwd": (C.c_int, [_P(DiscParams), _P(Bags), _P(HeadActs), _vp]),
     "advmil_disc_head_bwd": (C.c_int, [_P(DiscParams), _P(Bags), _P(HeadActs), _vp, _vp, _vp, _P(DiscGrads), _i32, _vp]),
     "advmil_segment_mean_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
-    "advmil_segment_mean_by_id_fwd": (C.c_int, [_vp, _vp, _vp, _P(C.c_int32), _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "advmil_segment_mean_by_id_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "advmil_segment_mean_by_id_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _P(C.c_int32), _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "advmil_segment_mean_by_id_bwd": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "advmil_linear_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f, _vp, _u64, _i32, _i32, _i32, _vp, _vp]),
     "advmil_linear_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     "advmil_linear_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "advmil_gated_score_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _vp, _vp, _u64, _i32,
                                          _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "advmil_seg_softmax_pool_fwd": (C.c_int, [_vp, _vp, _vp, _P(C.c_int32), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "advmil_seg_softmax_pool_fwd": (C.c_int, [_vp, _vp, _i32, _vp, _P(C.c_int32), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "advmil_cast_f32_to_bf16": (C.c_int, [_vp, _i64, _vp, _vp]),
     "advmil_seg_pool_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "advmil_region_index_map": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "advmil_region_of_rows": (C.c_int, [_i32, _i32, _vp, _vp]),
@@ -130,7 +132,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.advmil_abi_version() != 1:
+    if lib.advmil_abi_version() != 2:
         raise AdvmilError("libadvmil_b200.so ABI version mismatch")
     for i, st in enumerate(ABI_STRUCTS):
         if lib.advmil_abi_sizeof(i) != C.sizeof(st):

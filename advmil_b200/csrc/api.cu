@@ -45,8 +45,11 @@ __global__ void scale_offsets_kernel(const int32_t* __restrict__ in, int n, int 
   if (i < n) out[i] = in[i] / div;
 }
 
-static int check_bags(const AdvmilBags* b, int C, bool need16) {
+static int check_bags(const AdvmilBags* b, int C, bool need16, int precision) {
   ADVMIL_REQUIRE(b && b->x && b->offsets && b->offsets_host, "bags: null pointer");
+  ADVMIL_REQUIRE(precision >= ADVMIL_FP32 && precision <= ADVMIL_BF16, "unknown precision mode %d", precision);
+  ADVMIL_REQUIRE(b->elem == elem_of_precision(precision), "bags: x element type %d does not match precision mode %d (bf16 x <=> ADVMIL_BF16)",
+                 b->elem, precision);
   ADVMIL_REQUIRE(b->bags > 0 && b->rows > 0, "bags: empty batch (rows=%d bags=%d)", b->rows, b->bags);
   ADVMIL_REQUIRE(b->C == C, "bags: feature width %d != model input width %d", b->C, C);
   ADVMIL_REQUIRE(b->offsets_host[0] == 0 && b->offsets_host[b->bags] == b->rows, "bags: offsets must span [0, rows]");
@@ -125,7 +128,7 @@ extern "C" size_t advmil_generator_workspace_bytes(const AdvmilGenParams* p, int
 
 extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* bags, AdvmilGenActs* a, void* stream) {
   ADVMIL_REQUIRE(p && a, "generator_fwd: null argument");
-  ADVMIL_TRY(check_bags(bags, p->C, false));
+  ADVMIL_TRY(check_bags(bags, p->C, false, a->precision));
   ADVMIL_REQUIRE(p->h % 4 == 0 && p->C % 4 == 0, "generator_fwd: C=%d and h=%d must be multiples of 4", p->C, p->h);
   ADVMIL_REQUIRE(a->h && a->s && a->w && a->z && (a->pred || !p->W0), "generator_fwd: missing output buffers");
   cudaStream_t st = (cudaStream_t)stream;
@@ -141,13 +144,14 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
   Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train);
   Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train);
   Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train);
-  if (a->h_eval) { ProfScope ps(PROF_DROPOUT, st); ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, st)); }
+  const int dt = elem_of_precision(a->precision);
+  if (a->h_eval) { ProfScope ps(PROF_DROPOUT, st); ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, dt, st)); }
   else { ProfScope ps(PROF_PROJ, st); ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st)); }
   ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
   { ProfScope ps(PROF_GATE, st);
     ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, a->s, part, a->precision, st)); }
   { ProfScope ps(PROF_POOL, st);
-    ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st)); }
+    ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, dt, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st)); }
   ADVMIL_TRY(gen_head_fwd(*p, a->z, a->noise0, a->noise1, nb, 1, drho, dmlp0, a->H, a->H1, a->pre, a->pred, st));
   return ADVMIL_OK;
 }
@@ -155,12 +159,13 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
 extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* bags, const AdvmilGenActs* a,
                                     const float* d_pred, AdvmilGenGrads* g, void* stream) {
   ADVMIL_REQUIRE(p && a && g && d_pred, "generator_bwd: null argument");
-  ADVMIL_TRY(check_bags(bags, p->C, false));
+  ADVMIL_TRY(check_bags(bags, p->C, false, a->precision));
+  ADVMIL_REQUIRE(!(g->dx && a->precision == ADVMIL_BF16), "generator_bwd: dx is not available in the bf16 mode");
   ADVMIL_REQUIRE(a->ab && a->H && (a->H1 || !p->W0), "generator_bwd: forward was run without saving activations (ab/H/H1)");
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = bags->rows, nb = bags->bags, h = p->h, o = p->o, hid = p->hid, C = p->C;
   const int abw = gate_width(h);
-  const int prec = a->precision;
+  const int prec = a->precision, dt = elem_of_precision(a->precision);
   Workspace ws(a->workspace, a->workspace_bytes);
   WS_TAKE(Wp, float, (size_t)abw * h);
   WS_TAKE(bp, float, abw);
@@ -189,7 +194,7 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   // pooling + gate
   ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
   { ProfScope ps(PROF_POOL_BWD, st);
-    ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, dbp, 0, pgws, st)); }
+    ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, dbp, 0, pgws, dt, st)); }
   BwdDataExtras ex;
   ex.w = a->w; ex.dz = dz; ex.offsets = bags->offsets; ex.bags = nb; ex.relu_src = a->h; ex.ld_src = h; ex.inv_keep = ik_bb;
   { ProfScope ps(PROF_BWD_DATA, st); ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st)); }
@@ -197,7 +202,7 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st));
   // first layer
   { ProfScope ps(PROF_BWD_W_PROJ, st); ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st)); }
-  { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dhpre, rows, h, h, g->b1, 0, csws, st)); }
+  { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dhpre, dt, rows, h, h, g->b1, 0, csws, st)); }
   if (g->dx) {
     BwdDataExtras exx;
     ADVMIL_TRY(bwd_data(dhpre, p->W1, rows, h, C, g->dx, exx, prec, st));
@@ -240,7 +245,7 @@ extern "C" size_t advmil_disc_workspace_bytes(const AdvmilDiscParams* p, int32_t
 
 extern "C" int advmil_disc_embed_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilEmbedActs* a, void* stream) {
   ADVMIL_REQUIRE(p && a && a->emb, "disc_embed_fwd: null argument");
-  ADVMIL_TRY(check_bags(bags, p->C, true));
+  ADVMIL_TRY(check_bags(bags, p->C, true, a->precision));
   ProfScope ps(PROF_EMBED, (cudaStream_t)stream);
   return region_embed_fwd(bags->x, p->Wc, p->bc, p->ln_g, p->ln_b, bags->rows, p->C, p->d, p->ln_eps, a->y_pre, a->emb,
                           a->precision, (cudaStream_t)stream);
@@ -250,7 +255,7 @@ extern "C" int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags
                                      const float* d_emb, AdvmilDiscGrads* g, int32_t accumulate, void* stream) {
   ADVMIL_REQUIRE(p && a && d_emb && g, "disc_embed_bwd: null argument");
   ADVMIL_REQUIRE(a->y_pre, "disc_embed_bwd: forward was run without saving y_pre");
-  ADVMIL_TRY(check_bags(bags, p->C, true));
+  ADVMIL_TRY(check_bags(bags, p->C, true, a->precision));
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = bags->rows, d = p->d, C = p->C;
   Workspace ws(a->workspace, a->workspace_bytes);
@@ -258,7 +263,8 @@ extern "C" int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags
   WS_TAKE(lnws, float, (size_t)row_chunks(rows) * 3 * d);
   WS_TAKE(bwws, float, bwd_weight_ws_floats(rows, d, C));
   { ProfScope ps(PROF_LN_BWD, st);
-    ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws, st)); }
+    ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws,
+                           elem_of_precision(a->precision), st)); }
   { ProfScope ps(PROF_BWD_W_EMBED, st); ADVMIL_TRY(bwd_weight(d_y, bags->x, rows, d, C, g->Wc, accumulate, bwws, a->precision, st)); }
   return ADVMIL_OK;
 }
@@ -282,7 +288,7 @@ static int make_region_offsets(const AdvmilBags* bags, Workspace& ws, cudaStream
 
 extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags* bags, AdvmilHeadActs* a, void* stream) {
   ADVMIL_REQUIRE(p && a && a->emb && a->t && a->out, "disc_head_fwd: null argument");
-  ADVMIL_TRY(check_bags(bags, p->C, true));
+  ADVMIL_TRY(check_bags(bags, p->C, true, bags ? (bags->elem == ELEM_BF16 ? ADVMIL_BF16 : ADVMIL_FP32) : 0));
   ADVMIL_REQUIRE(a->f1 && a->fi && a->rep && a->attn && a->bagv && a->fbar && a->g1 && a->hx && a->u1 && a->ht,
                  "disc_head_fwd: missing activation buffers");
   cudaStream_t st = (cudaStream_t)stream;
@@ -305,7 +311,7 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, ADVMIL_FP32, st));
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
   ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, a->rep, part, ADVMIL_FP32, st));
-  ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, a->fi, ro.dev, ro.host.data(), R, nb, d, a->attn, a->bagv, a->fbar, poolws, st));
+  ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, a->fi, ELEM_F32, ro.dev, ro.host.data(), R, nb, d, a->attn, a->bagv, a->fbar, poolws, st));
   ADVMIL_TRY(rlip_tail_fwd(*p, a->bagv, a->fbar, a->t, nb, dfc2, a->g1, a->hx, a->u1, a->ht, a->out, st));
   return ADVMIL_OK;
 }
@@ -314,7 +320,7 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
                                     const float* d_out, float* d_emb, float* d_t, AdvmilDiscGrads* g,
                                     int32_t accumulate, void* stream) {
   ADVMIL_REQUIRE(p && a && d_out, "disc_head_bwd: null argument");
-  ADVMIL_TRY(check_bags(bags, p->C, true));
+  ADVMIL_TRY(check_bags(bags, p->C, true, bags ? (bags->elem == ELEM_BF16 ? ADVMIL_BF16 : ADVMIL_FP32) : 0));
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = bags->bags, d = p->d, dh = p->d / 2, R = bags->rows / 16, t1 = p->t1, t2 = p->t2;
   const int abw = gate_width(d);
@@ -355,7 +361,8 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train);
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
   ADVMIL_TRY(pool_gate_bwd(a->fi, a->attn, a->bagv, d_bagv, a->ab, p->Pc_w, ro.dev, R, nb, d, d, dga, dgs, dAB,
-                           g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? dbp : nullptr, g ? accumulate : 0, pgws, st));
+                           g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? dbp : nullptr, g ? accumulate : 0, pgws,
+                           ELEM_F32, st));
   BwdDataExtras ex;
   ex.w = a->attn; ex.dz = d_bagv; ex.dmean = p->inner_instance ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
   ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, ADVMIL_FP32, st));
@@ -368,9 +375,9 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   ADVMIL_TRY(bwd_data(d_fi, p->F1b_w, R, d, dh, d_f1pre, ex1, ADVMIL_FP32, st));
   if (g) {
     ADVMIL_TRY(bwd_weight(d_fi, a->f1, R, d, dh, g->F1b_w, accumulate, bwws, ADVMIL_FP32, st));
-    ADVMIL_TRY(colsum(d_fi, R, d, d, g->F1b_b, accumulate, csws, st));
+    ADVMIL_TRY(colsum(d_fi, ELEM_F32, R, d, d, g->F1b_b, accumulate, csws, st));
     ADVMIL_TRY(bwd_weight(d_f1pre, a->emb, R, dh, d, g->F1a_w, accumulate, bwws, ADVMIL_FP32, st));
-    ADVMIL_TRY(colsum(d_f1pre, R, dh, dh, g->F1a_b, accumulate, csws, st));
+    ADVMIL_TRY(colsum(d_f1pre, ELEM_F32, R, dh, dh, g->F1a_b, accumulate, csws, st));
   }
   if (d_emb) {
     BwdDataExtras ex2;
@@ -383,9 +390,9 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
 // =============================================================================================
 // stage-level entry points
 // =============================================================================================
-extern "C" int advmil_linear_fwd(const float* x, const float* W, const float* b, int32_t rows, int32_t K, int32_t N,
+extern "C" int advmil_linear_fwd(const void* x, const float* W, const float* b, int32_t rows, int32_t K, int32_t N,
                                  int32_t act, float p_drop, const uint8_t* mask, uint64_t seed, int32_t site,
-                                 int32_t train, int32_t precision, float* y, void* stream) {
+                                 int32_t train, int32_t precision, void* y, void* stream) {
   ADVMIL_REQUIRE(x && W && y && rows >= 0, "linear_fwd: null argument");
   Drop dr = Drop::make(mask, seed, SITE_USER + site, p_drop, train);
   return linear_fwd(x, W, b, rows, K, N, act, dr, y, precision, (cudaStream_t)stream);
@@ -395,8 +402,8 @@ extern "C" size_t advmil_linear_bwd_workspace_bytes(int32_t rows, int32_t K, int
   return (bwd_weight_ws_floats(rows, N, K) + (size_t)row_chunks(rows) * N + 1024) * sizeof(float);
 }
 
-extern "C" int advmil_linear_bwd(const float* dY, const float* X, const float* W, int32_t rows, int32_t K, int32_t N,
-                                 float* dX, float* dW, float* db, int32_t accumulate, int32_t precision, void* workspace,
+extern "C" int advmil_linear_bwd(const void* dY, const void* X, const float* W, int32_t rows, int32_t K, int32_t N,
+                                 void* dX, float* dW, float* db, int32_t accumulate, int32_t precision, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   ADVMIL_REQUIRE(dY, "linear_bwd: null dY");
   cudaStream_t st = (cudaStream_t)stream;
@@ -413,15 +420,15 @@ extern "C" int advmil_linear_bwd(const float* dY, const float* X, const float* W
   }
   if (db) {
     WS_TAKE(csws, float, (size_t)row_chunks(rows) * N);
-    ADVMIL_TRY(colsum(dY, rows, N, N, db, accumulate, csws, st));
+    ADVMIL_TRY(colsum(dY, elem_of_precision(precision), rows, N, N, db, accumulate, csws, st));
   }
   return ADVMIL_OK;
 }
 
-extern "C" int advmil_gated_score_fwd(const float* v, const float* Wa, const float* ba, const float* Wb, const float* bb,
+extern "C" int advmil_gated_score_fwd(const void* v, const float* Wa, const float* ba, const float* Wb, const float* bb,
                                       const float* wc, const float* bc, int32_t rows, int32_t L, int32_t D, float p_drop,
                                       const uint8_t* mask_a, const uint8_t* mask_b, uint64_t seed, int32_t site,
-                                      int32_t train, int32_t precision, float* ab, float* s, void* workspace,
+                                      int32_t train, int32_t precision, void* ab, float* s, void* workspace,
                                       size_t workspace_bytes, void* stream) {
   ADVMIL_REQUIRE(v && Wa && Wb && wc && bc && s, "gated_score_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -436,16 +443,22 @@ extern "C" int advmil_gated_score_fwd(const float* v, const float* Wa, const flo
   return gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, part, precision, st);
 }
 
+extern "C" int advmil_cast_f32_to_bf16(const float* in, int64_t n, void* out_bf16, void* stream) {
+  ADVMIL_REQUIRE(in && out_bf16 && n >= 0, "cast_f32_to_bf16: bad arguments");
+  return cast_f32_to_bf16(in, (size_t)n, out_bf16, (cudaStream_t)stream);
+}
+
 extern "C" size_t advmil_seg_pool_workspace_bytes(int32_t rows, int32_t bags, int32_t width) {
   return seg_pool_ws_floats(rows, bags, width) * sizeof(float) + 1024;
 }
 
-extern "C" int advmil_seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets,
+extern "C" int advmil_seg_softmax_pool_fwd(const float* s, const void* v, int32_t elem, const int32_t* offsets,
                                            const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width,
                                            float* w, float* z, float* mean, void* workspace, size_t workspace_bytes,
                                            void* stream) {
   ADVMIL_REQUIRE(s && v && offsets && offsets_host && w && z, "seg_softmax_pool_fwd: null argument");
   Workspace ws(workspace, workspace_bytes);
   WS_TAKE(poolws, float, seg_pool_ws_floats(rows, bags, width));
-  return seg_softmax_pool_fwd(s, v, offsets, offsets_host, rows, bags, width, w, z, mean, poolws, (cudaStream_t)stream);
+  ADVMIL_REQUIRE(elem == ELEM_F32 || elem == ELEM_BF16, "seg_softmax_pool_fwd: unknown element type %d", elem);
+  return seg_softmax_pool_fwd(s, v, elem, offsets, offsets_host, rows, bags, width, w, z, mean, poolws, (cudaStream_t)stream);
 }

@@ -1,6 +1,7 @@
 // Shared device/host helpers for the advmil_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -139,7 +140,68 @@ struct Drop {          // one dropout site
   }
 };
 
+// ---- element types of the [rows, width] activation tensors ------------------------------------------
+// fp32 / tf32 modes keep them in fp32; the bf16 mode (ADVMIL_BF16) keeps x, h, ab, dAB, dh, y_pre, d_y in bfloat16
+// (half the HBM bytes, kind::f16 tensor-core rate) while every accumulation, statistic and parameter stays fp32.
+typedef __nv_bfloat16 bf16;
+enum ElemType : int { ELEM_F32 = 0, ELEM_BF16 = 1 };
+template <typename T> struct ElemOf;
+template <> struct ElemOf<float> { static constexpr int value = ELEM_F32; };
+template <> struct ElemOf<bf16> { static constexpr int value = ELEM_BF16; };
+static inline size_t elem_bytes(int dt) { return dt == ELEM_BF16 ? 2 : 4; }
+static inline int elem_of_precision(int precision) { return precision == ADVMIL_BF16 ? ELEM_BF16 : ELEM_F32; }
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+// 4 consecutive elements (16-byte / 8-byte aligned)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf_lo(u.x), bf_hi(u.x), bf_lo(u.y), bf_hi(u.y));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf2(v.x, v.y), pack_bf2(v.z, v.w));
+}
+// one 16-byte vector = VecN<T>::N consecutive elements
+template <typename T> struct VecN { static constexpr int N = 16 / (int)sizeof(T); };
+__device__ __forceinline__ void ldv(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void ldv(const bf16* p, float (&o)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  o[0] = bf_lo(u.x); o[1] = bf_hi(u.x); o[2] = bf_lo(u.y); o[3] = bf_hi(u.y);
+  o[4] = bf_lo(u.z); o[5] = bf_hi(u.z); o[6] = bf_lo(u.w); o[7] = bf_hi(u.w);
+}
+__device__ __forceinline__ void stv(float* p, const float (&o)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void stv(bf16* p, const float (&o)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf2(o[0], o[1]), pack_bf2(o[2], o[3]), pack_bf2(o[4], o[5]), pack_bf2(o[6], o[7]));
+}
+
+// one 4-byte word = 1 fp32 or 2 bf16 consecutive elements
+__device__ __forceinline__ void ldw(const float* p, float (&o)[1]) { o[0] = *p; }
+__device__ __forceinline__ void ldw(const bf16* p, float (&o)[2]) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  o[0] = bf_lo(u); o[1] = bf_hi(u);
+}
+
 // ---- warp helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float oct_sum(float v) {  // over 8 consecutive lanes (aligned groups)
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

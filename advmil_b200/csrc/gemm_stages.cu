@@ -11,51 +11,57 @@ static bool gemm_ok(int K, int N, const void* a, const void* b) {
   return (K % 4 == 0) && (N % 4 == 0) && (((uintptr_t)a | (uintptr_t)b) % 16 == 0);
 }
 
-int linear_fwd(const float* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-               float* y, int precision, cudaStream_t st) {
+static const char* kBf16Shape = "%s: the bf16 mode runs only on the tcgen05 engine and this shape is unsupported by it (rows=%d K=%d N=%d)";
+
+int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+               void* y, int precision, cudaStream_t st) {
   ADVMIL_REQUIRE(gemm_ok(K, N, x, W), "linear_fwd: K=%d N=%d must be multiples of 4 and pointers 16B aligned", K, N);
   if (rows == 0) return ADVMIL_OK;
-  if (precision != ADVMIL_FP32 && tc_linear_supported(rows, K, N))
+  if (precision != ADVMIL_FP32 && tc_linear_supported(rows, K, N, elem_of_precision(precision)))
     return tc_linear_fwd(x, W, b, rows, K, N, relu, drop, y, precision, st);
-  GemmArgs g{x, W, rows, N, K, K, K, K};
-  EpiLinear epi{y, N, b, relu, drop, N};
+  ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "linear_fwd", rows, K, N);
+  GemmArgs g{(const float*)x, W, rows, N, K, K, K, K};
+  EpiLinear epi{(float*)y, N, b, relu, drop, N};
   return launch_gemm<true, true>(g, epi, 1, st);
 }
 
-int gated_score_fwd(const float* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
-                    int D, const Drop& da, const Drop& db, float* ab, float* s, float* part_ws, int precision,
+int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
+                    int D, const Drop& da, const Drop& db, void* ab, float* s, float* part_ws, int precision,
                     cudaStream_t st) {
   ADVMIL_REQUIRE(L % 4 == 0, "gated_score_fwd: L=%d must be a multiple of 4", L);
   if (rows == 0) return ADVMIL_OK;
   int abw = gate_width(D);
-  if (precision != ADVMIL_FP32 && tc_gate_supported(rows, L, D))
+  if (precision != ADVMIL_FP32 && tc_gate_supported(rows, L, D, elem_of_precision(precision)))
     return tc_gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, part_ws, precision, st);
-  GemmArgs g{v, Wp, rows, abw, L, L, L, L};
-  EpiGate epi{ab, abw, bp, wc, part_ws, D, da, db};
+  ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "gated_score_fwd", rows, L, D);
+  GemmArgs g{(const float*)v, Wp, rows, abw, L, L, L, L};
+  EpiGate epi{(float*)ab, abw, bp, wc, part_ws, D, da, db};
   ADVMIL_TRY((launch_gemm<true, true>(g, epi, 1, st)));
   return gate_score_finish(part_ws, abw / 128, rows, bc, s, st);
 }
 
-int region_embed_fwd(const float* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows,
-                     int C, int d, float eps, float* y_pre, float* emb, int precision, cudaStream_t st) {
+int region_embed_fwd(const void* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows,
+                     int C, int d, float eps, void* y_pre, float* emb, int precision, cudaStream_t st) {
   ADVMIL_REQUIRE(rows % 16 == 0, "region_embed: rows %d not a multiple of 16 (backbone_utils.py:65)", rows);
   ADVMIL_REQUIRE(d <= 128 && d % 4 == 0 && C % 4 == 0, "region_embed: d=%d (<=128, %%4) C=%d (%%4) unsupported", d, C);
   if (rows == 0) return ADVMIL_OK;
-  if (precision != ADVMIL_FP32 && tc_embed_supported(rows, C, d))
+  if (precision != ADVMIL_FP32 && tc_embed_supported(rows, C, d, elem_of_precision(precision)))
     return tc_region_embed_fwd(x, Wc, bc, gamma, beta, rows, C, d, eps, y_pre, emb, precision, st);
-  GemmArgs g{x, Wc, rows, d, C, C, C, C};
-  EpiLNPool epi{y_pre, emb, bc, gamma, beta, d, eps};
+  ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "region_embed_fwd", rows, C, d);
+  GemmArgs g{(const float*)x, Wc, rows, d, C, C, C, C};
+  EpiLNPool epi{(float*)y_pre, emb, bc, gamma, beta, d, eps};
   return launch_gemm<true, true>(g, epi, 1, st);
 }
 
-int bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* dX, const BwdDataExtras& ex,
+int bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX, const BwdDataExtras& ex,
              int precision, cudaStream_t st) {
   ADVMIL_REQUIRE(gemm_ok(Ny, Nx, dY, W), "bwd_data: Ny=%d Nx=%d must be multiples of 4", Ny, Nx);
   if (rows == 0) return ADVMIL_OK;
-  if (precision != ADVMIL_FP32 && !ex.accumulate && !ex.dmean && tc_bwd_data_supported(rows, Ny, Nx))
+  if (precision != ADVMIL_FP32 && !ex.accumulate && !ex.dmean && tc_bwd_data_supported(rows, Ny, Nx, elem_of_precision(precision)))
     return tc_bwd_data(dY, W, rows, Ny, Nx, dX, ex, precision, st);
-  GemmArgs g{dY, W, rows, Nx, Ny, Ny, Nx, Ny};
-  EpiBwdData epi{dX, Nx, ex.w, ex.dz, ex.dmean, ex.offsets, ex.bags, ex.relu_src, ex.ld_src, ex.inv_keep, ex.accumulate};
+  ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "bwd_data", rows, Ny, Nx);
+  GemmArgs g{(const float*)dY, W, rows, Nx, Ny, Ny, Nx, Ny};
+  EpiBwdData epi{(float*)dX, Nx, ex.w, ex.dz, ex.dmean, ex.offsets, ex.bags, (const float*)ex.relu_src, ex.ld_src, ex.inv_keep, ex.accumulate};
   return launch_gemm<true, false>(g, epi, 1, st);
 }
 
@@ -71,16 +77,17 @@ size_t bwd_weight_ws_floats(int rows, int N1, int N2) {
   size_t tcw = tc_bwd_weight_ws_floats(rows, N1, N2);
   return simt > tcw ? simt : tcw;
 }
-int bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+int bwd_weight(const void* dY, const void* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
                int precision, cudaStream_t st) {
   ADVMIL_REQUIRE(gemm_ok(N1, N2, dY, X), "bwd_weight: N1=%d N2=%d must be multiples of 4", N1, N2);
   if (rows == 0) { if (!accumulate) return fill_zero(dW, (size_t)N1 * N2, st); return ADVMIL_OK; }
-  if (precision != ADVMIL_FP32 && tc_bwd_weight_supported(rows, N1, N2))
+  if (precision != ADVMIL_FP32 && tc_bwd_weight_supported(rows, N1, N2, elem_of_precision(precision)))
     return tc_bwd_weight(dY, X, rows, N1, N2, dW, accumulate, ws, precision, st);
+  ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "bwd_weight", rows, N1, N2);
   int splits = pick_splits(rows, N1, N2);
   int kchunk = cdiv(cdiv(rows, splits), BK) * BK;
   splits = cdiv(rows, kchunk);
-  GemmArgs g{dY, X, N1, N2, rows, N1, N2, kchunk};
+  GemmArgs g{(const float*)dY, (const float*)X, N1, N2, rows, N1, N2, kchunk};
   EpiPartial epi{ws};
   ADVMIL_TRY((launch_gemm<false, false>(g, epi, splits, st)));
   return splitk_reduce(ws, splits, (size_t)N1 * N2, dW, accumulate, st);

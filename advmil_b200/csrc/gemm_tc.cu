@@ -37,16 +37,38 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// row-major fp32 matrix [rows, cols]; box = box_rows x 32 floats (128 B), SWIZZLE_128B, OOB reads return zeros
-static int make_tmap(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows,
+// per-element-type constants of the engine: one 128-byte swizzle row holds KBLK elements; one MMA consumes 32 bytes of K
+template <typename T> struct TcElem;
+template <> struct TcElem<float> {
+  static constexpr int KBLK = 32;
+  static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  static constexpr CUtensorMapSwizzle MN_SWZ = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;   // MN-major 32-bit operands
+  static constexpr uint32_t MN_LAYOUT = 1;      // SWIZZLE_128B_BASE32B
+  static constexpr int MN_SBO = 512;            // 4 k-rows x 128 B per swizzle group
+  __host__ __device__ static constexpr uint32_t idesc(int M, int N, int am, int bm) { return idesc_tf32(M, N, am, bm); }
+  __device__ __forceinline__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_tf32(d, a, b, i, acc); }
+};
+template <> struct TcElem<bf16> {
+  static constexpr int KBLK = 64;
+  static constexpr CUtensorMapDataType DT = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  static constexpr CUtensorMapSwizzle MN_SWZ = CU_TENSOR_MAP_SWIZZLE_128B;
+  static constexpr uint32_t MN_LAYOUT = 2;      // SWIZZLE_128B
+  static constexpr int MN_SBO = 1024;           // 8 k-rows x 128 B per swizzle atom
+  __host__ __device__ static constexpr uint32_t idesc(int M, int N, int am, int bm) { return idesc_bf16(M, N, am, bm); }
+  __device__ __forceinline__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_f16(d, a, b, i, acc); }
+};
+
+// row-major matrix [rows, cols] of T; box = box_rows x (128 B of elements), 128-byte swizzle, OOB reads return zeros
+template <typename T>
+static int make_tmap(CUtensorMap* m, const T* base, long long rows, long long cols, int box_rows,
                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ADVMIL_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * sizeof(T)};
+  cuuint32_t box[2] = {(cuuint32_t)TcElem<T>::KBLK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(m, TcElem<T>::DT, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return ADVMIL_ERR_CUDA; }
   return ADVMIL_OK;
@@ -63,17 +85,18 @@ static int sm_count() {
 // ------------------------------------------------------------------------------------------------
 enum RowEpiKind : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_LN = 2, EPI_BWD = 3 };
 
+// out / ab / y_pre / relu_src are [rows, *] activation tensors of the kernel's element type T (fp32 or bf16)
 struct RowEpi {
-  float* out; int ldo; const float* bias;
+  void* out; int ldo; const float* bias;
   int relu; Drop drop;                                                           // EPI_LINEAR
-  float* ab; const float* wc; float* part; int D; Drop drop_a, drop_b;           // EPI_GATE (bias = packed gate bias)
-  float* y_pre; float* emb; const float* gamma; const float* beta; float eps;    // EPI_LN
+  void* ab; const float* wc; float* part; int D; Drop drop_a, drop_b;            // EPI_GATE (bias = packed gate bias)
+  void* y_pre; float* emb; const float* gamma; const float* beta; float eps;     // EPI_LN
   const float* w; const float* dz; const int32_t* offsets; int bags;             // EPI_BWD
-  const float* relu_src; int ld_src; float inv_keep;
+  const void* relu_src; int ld_src; float inv_keep;
 };
 
-constexpr int TILE_M = 128, KBLK = 32;                 // 32 fp32 = one 128-byte swizzle row
-constexpr int A_STAGE_BYTES = TILE_M * KBLK * 4;       // 16 KB
+constexpr int TILE_M = 128;
+constexpr int A_STAGE_BYTES = TILE_M * 128;            // 128 rows x one 128-byte swizzle row = 16 KB
 constexpr int STG_LD = 36;                             // staging row stride (floats) for 32-column chunks
 constexpr int STG_LD_LN = 132;                         // staging row stride for full 128-column rows
 
@@ -81,7 +104,7 @@ template <int BLOCK_N, int EPI> struct RowCfg {
   static constexpr int STAGES = (BLOCK_N >= 256) ? 3 : 4;
   static constexpr int EPI_WARPS = (EPI == EPI_LN) ? 4 : 8;       // 2 warps per TMEM lane quarter except for LN
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
-  static constexpr int B_STAGE_BYTES = BLOCK_N * KBLK * 4;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : 32 * STG_LD;
   static constexpr int COEF_FLOATS_PER_WARP = 192;                // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c
@@ -97,6 +120,35 @@ __device__ __forceinline__ void stage_chunk(float* stg, int ld, int col0, const 
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(stg + lane * ld + col0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// raw 16-byte vector -> floats
+__device__ __forceinline__ void raw_floats(const uint4& u, float (&o)[4]) {
+  o[0] = __uint_as_float(u.x); o[1] = __uint_as_float(u.y); o[2] = __uint_as_float(u.z); o[3] = __uint_as_float(u.w);
+}
+__device__ __forceinline__ void raw_floats(const uint4& u, float (&o)[8]) {
+  o[0] = bf_lo(u.x); o[1] = bf_hi(u.x); o[2] = bf_lo(u.y); o[3] = bf_hi(u.y);
+  o[4] = bf_lo(u.z); o[5] = bf_hi(u.z); o[6] = bf_lo(u.w); o[7] = bf_hi(u.w);
+}
+// staged [32 rows][ncols] fp32 block (row stride ld floats) -> global rows of T, 16-byte stores, consecutive lanes along a row
+template <typename T, int NCOLS>
+__device__ __forceinline__ void store_staged(const float* stg, int ld, T* __restrict__ out, size_t ldo, int m_base, int M,
+                                             int col0, int lane) {
+  constexpr int VEC = VecN<T>::N, LPR = NCOLS / VEC, RPI = 32 / LPR, NIT = 32 / RPI;
+  static_assert(LPR <= 32 && 32 % LPR == 0, "row must be covered by at most one warp");
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int r = lane / LPR + RPI * it, cv = lane % LPR, m = m_base + r;
+    if (m < M) {
+      float o[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(stg + r * ld + cv * VEC + 4 * q);
+        o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+      }
+      stv(out + (size_t)m * ldo + col0 + cv * VEC, o);
+    }
+  }
 }
 
 // gate math on one 32-pair chunk: va/vb hold pre-activations on entry and tanh / sigmoid values on exit
@@ -124,11 +176,13 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
 // CL = cluster size (1 or 2).  CL == 2: the two CTAs of a cluster work on two consecutive 128-row blocks of the SAME
 // N-tile in lock step; each loads half of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the
 // L2 -> SM traffic of the (per-tile re-streamed) weights, which is what bounds these kernels once the epilogues are cheap.
-template <int BLOCK_N, int EPI, bool FAST, int CL>
+template <typename T, int BLOCK_N, int EPI, bool FAST, int CL>
 __global__ void __launch_bounds__(RowCfg<BLOCK_N, EPI>::THREADS, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
   using Cfg = RowCfg<BLOCK_N, EPI>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int KBLK = TcElem<T>::KBLK;
+  constexpr int VEC = VecN<T>::N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* A_s = smem;
@@ -180,7 +234,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(B_s + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kb * KBLK, n0);
           } else {                                      // my half of the weight tile, multicast to both CTAs
             constexpr int HALF_ROWS = BLOCK_N / CL;
-            tma_load_2d_mcast(B_s + stage * Cfg::B_STAGE_BYTES + crank * (HALF_ROWS * KBLK * 4), &tmB, &full[stage], kb * KBLK,
+            tma_load_2d_mcast(B_s + stage * Cfg::B_STAGE_BYTES + crank * (HALF_ROWS * 128), &tmB, &full[stage], kb * KBLK,
                               n0 + crank * HALF_ROWS, CMASK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -189,7 +243,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t IDESC = idesc_tf32(TILE_M, BLOCK_N, 0, 0);
+    constexpr uint32_t IDESC = TcElem<T>::idesc(TILE_M, BLOCK_N, 0, 0);
     int stage = 0; uint32_t phase = 0; int it = 0;
     for (int tile = work0; tile < total; tile += work_stride, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -202,10 +256,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(A_s + stage * A_STAGE_BYTES), b_addr = smem_u32(B_s + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < KBLK / 8; ++kk) {   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          for (int kk = 0; kk < 4; ++kk) {   // one MMA = 32 bytes of K (8 tf32 / 16 bf16) inside the 128-byte swizzle row
             uint64_t ad = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
             uint64_t bd = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            mma_tf32(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+            TcElem<T>::mma(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
           }
           if (CL == 1) mma_commit(&empty[stage]);    // smem slot is free once these MMAs retire
           else mma_commit_mcast(&empty[stage], CMASK);   // ... in BOTH CTAs (each producer writes into both)
@@ -250,16 +304,18 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (EPI == EPI_LINEAR || EPI == EPI_BWD) {
         constexpr int NCH = BLOCK_N / 32;
+        constexpr int LPR = 32 / VEC, RPI = 32 / LPR, NIT = 32 / RPI;   // lanes per row, rows per pass, passes per chunk
+        T* outp = reinterpret_cast<T*>(ea.out);
+        const T* srcp = reinterpret_cast<const T*>(ea.relu_src);
 #pragma unroll 1
         for (int ch = half; ch < NCH; ch += 2) {
-          float4 src[8];
+          uint4 src[NIT];
           if constexpr (EPI == EPI_BWD) {                  // issue the ReLU-mask loads before touching TMEM
-            if (ea.relu_src) {
+            if (srcp) {
 #pragma unroll
-              for (int i8 = 0; i8 < 8; ++i8) {
-                const int r = (lane >> 3) + 4 * i8, m = m_base + r, col = n0 + ch * 32 + (lane & 7) * 4;
-                src[i8] = (m < M) ? *reinterpret_cast<const float4*>(ea.relu_src + (size_t)m * ea.ld_src + col)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int it2 = 0; it2 < NIT; ++it2) {
+                const int r = lane / LPR + RPI * it2, m = m_base + r, col = n0 + ch * 32 + (lane % LPR) * VEC;
+                src[it2] = (m < M) ? *reinterpret_cast<const uint4*>(srcp + (size_t)m * ea.ld_src + col) : make_uint4(0u, 0u, 0u, 0u);
               }
             }
           }
@@ -269,32 +325,50 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           stage_chunk(stg, STG_LD, 0, v, lane);
           __syncwarp();
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int r = (lane >> 3) + 4 * i8, c4 = lane & 7;
-            const int m = m_base + r, col = n0 + ch * 32 + c4 * 4;
+          for (int it2 = 0; it2 < NIT; ++it2) {
+            const int r = lane / LPR + RPI * it2, cv = lane % LPR;
+            const int m = m_base + r, col = n0 + ch * 32 + cv * VEC;
             if (m < M) {
-              float4 q = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
-              float o[4] = {q.x, q.y, q.z, q.w};
+              float o[VEC];
+#pragma unroll
+              for (int q = 0; q < VEC / 4; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(stg + r * STG_LD + cv * VEC + 4 * q);
+                o[4 * q] = t4.x; o[4 * q + 1] = t4.y; o[4 * q + 2] = t4.z; o[4 * q + 3] = t4.w;
+              }
               if constexpr (EPI == EPI_LINEAR) {
-                if (ea.bias) { float4 b4 = *reinterpret_cast<const float4*>(ea.bias + col); o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
-                if (ea.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+                if (ea.bias) {
+#pragma unroll
+                  for (int q = 0; q < VEC / 4; ++q) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(ea.bias + col + 4 * q);
+                    o[4 * q] += b4.x; o[4 * q + 1] += b4.y; o[4 * q + 2] += b4.z; o[4 * q + 3] += b4.w;
+                  }
+                }
+                if (ea.relu) {
+#pragma unroll
+                  for (int e = 0; e < VEC; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
                 if (ea.drop.active) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) o[e] = ea.drop.keep((uint64_t)m * N + col + e) ? o[e] * ea.drop.inv_keep : 0.f;
+                  for (int e = 0; e < VEC; ++e) o[e] = ea.drop.keep((uint64_t)m * N + col + e) ? o[e] * ea.drop.inv_keep : 0.f;
                 }
               } else {
                 if (ea.dz) {
-                  float4 d4 = *reinterpret_cast<const float4*>(ea.dz + (size_t)mybag[r] * N + col);
                   const float wv = myw[r];
-                  o[0] = fmaf(wv, d4.x, o[0]); o[1] = fmaf(wv, d4.y, o[1]); o[2] = fmaf(wv, d4.z, o[2]); o[3] = fmaf(wv, d4.w, o[3]);
+#pragma unroll
+                  for (int q = 0; q < VEC / 4; ++q) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(ea.dz + (size_t)mybag[r] * N + col + 4 * q);
+                    o[4 * q] = fmaf(wv, d4.x, o[4 * q]); o[4 * q + 1] = fmaf(wv, d4.y, o[4 * q + 1]);
+                    o[4 * q + 2] = fmaf(wv, d4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(wv, d4.w, o[4 * q + 3]);
+                  }
                 }
-                if (ea.relu_src) {
-                  const float4 s4 = src[i8];
-                  o[0] = s4.x > 0.f ? o[0] * ea.inv_keep : 0.f; o[1] = s4.y > 0.f ? o[1] * ea.inv_keep : 0.f;
-                  o[2] = s4.z > 0.f ? o[2] * ea.inv_keep : 0.f; o[3] = s4.w > 0.f ? o[3] * ea.inv_keep : 0.f;
+                if (srcp) {
+                  float sv[VEC];
+                  raw_floats(src[it2], sv);
+#pragma unroll
+                  for (int e = 0; e < VEC; ++e) o[e] = sv[e] > 0.f ? o[e] * ea.inv_keep : 0.f;
                 }
               }
-              *reinterpret_cast<float4*>(ea.out + (size_t)m * ea.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
+              stv(outp + (size_t)m * ea.ldo + col, o);
             }
           }
           __syncwarp();
@@ -320,14 +394,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int hb = 0; hb < 2; ++hb) {
               if (hb == 0) stage_chunk(stg, STG_LD, 0, va, lane); else stage_chunk(stg, STG_LD, 0, vb, lane);
               __syncwarp();
-              const int cbase = n0 + (hb == 0 ? ca : cb);
-#pragma unroll
-              for (int i8 = 0; i8 < 8; ++i8) {
-                const int r = (lane >> 3) + 4 * i8, c4 = lane & 7, m = m_base + r;
-                if (m < M)
-                  *reinterpret_cast<float4*>(ea.ab + (size_t)m * ea.ldo + cbase + c4 * 4) =
-                      *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
-              }
+              store_staged<T, 32>(stg, STG_LD, reinterpret_cast<T*>(ea.ab), ea.ldo, m_base, M, n0 + (hb == 0 ? ca : cb), lane);
               __syncwarp();
             }
           }
@@ -341,7 +408,13 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float t[32];
           tmem_ld32(taddr + ch * 32, t);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[ch * 32 + i] = t[i] + __ldg(ea.bias + ch * 32 + i);
+          for (int i = 0; i < 32; ++i) {
+            float y = t[i] + __ldg(ea.bias + ch * 32 + i);
+            // bf16 mode: y_pre IS a bf16 tensor -- LayerNorm sees the rounded values, so that the backward pass (which
+            // re-derives the statistics and the ReLU mask from the stored y_pre) sees exactly what the forward saw
+            if constexpr (sizeof(T) == 2) y = __bfloat162float(__float2bfloat16_rn(y));
+            v[ch * 32 + i] = y;
+          }
         }
         tc_fence_before();
         mbar_arrive(&tempty[acc]);
@@ -358,12 +431,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j)
             *reinterpret_cast<float4*>(stg + lane * STG_LD_LN + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
-#pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int m = m_base + r;
-            if (m < M)
-              *reinterpret_cast<float4*>(ea.y_pre + (size_t)m * 128 + lane * 4) = *reinterpret_cast<const float4*>(stg + r * STG_LD_LN + lane * 4);
-          }
+          store_staged<T, 128>(stg, STG_LD_LN, reinterpret_cast<T*>(ea.y_pre), 128, m_base, M, 0, lane);
           __syncwarp();
         }
 #pragma unroll
@@ -409,23 +477,23 @@ static int cluster_size() {
   return g_cluster;
 }
 
-template <int BLOCK_N, int EPI, bool FAST>
-static int launch_rows(const float* A, const float* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
+template <typename T, int BLOCK_N, int EPI, bool FAST>
+static int launch_rows(const T* A, const T* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
   using Cfg = RowCfg<BLOCK_N, EPI>;
   const int num_m = cdiv(rows, TILE_M), num_n = N / BLOCK_N;
   const int CL = (cluster_size() == 2 && num_m >= 2) ? 2 : 1;
   CUtensorMap tmA, tmB;
-  ADVMIL_TRY(make_tmap(&tmA, A, rows, K, TILE_M));
-  ADVMIL_TRY(make_tmap(&tmB, W, N, K, BLOCK_N / CL));
+  ADVMIL_TRY(make_tmap<T>(&tmA, A, rows, K, TILE_M));
+  ADVMIL_TRY(make_tmap<T>(&tmB, W, N, K, BLOCK_N / CL));
   static bool attr_set = false;
   if (!attr_set) {
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<BLOCK_N, EPI, FAST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<BLOCK_N, EPI, FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
   if (CL == 1) {
     const int grid = min(num_m * num_n, sm_count());
-    tc_rows_kernel<BLOCK_N, EPI, FAST, 1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+    tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
     ADVMIL_CHECK_LAUNCH();
     return ADVMIL_OK;
   }
@@ -441,29 +509,38 @@ static int launch_rows(const float* A, const float* W, int rows, int K, int N, c
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int M_ = rows, N_ = N, K_ = K;
-  ADVMIL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<BLOCK_N, EPI, FAST, 2>, tmA, tmB, M_, N_, K_, ea));
+  ADVMIL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_rows_kernel<T, BLOCK_N, EPI, FAST, 2>, tmA, tmB, M_, N_, K_, ea));
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight-gradient kernel: dW[N1,N2] partial over a row range; both operands MN-major
+//   fp32 (tf32): MN groups of 32 elements, 32 k-rows per stage, SWIZZLE_128B with 32-byte atoms (the only swizzle the
+//                hardware accepts for MN-major 32-bit operands), 8 k-rows (two 512-byte groups) per MMA;
+//   bf16:        MN groups of 64 elements, 64 k-rows per stage, plain SWIZZLE_128B, 16 k-rows (two 1024-byte atoms) per MMA.
+// Either way one MN group of one stage is a TMA box of KR rows x 128 bytes and a stage holds 4 MMAs.
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N> struct WgCfg {
+template <typename T, int BLOCK_N> struct WgCfg {
   static constexpr int STAGES = 4;
-  static constexpr int A_BYTES = 4 * KBLK * 128;                 // 4 MN-groups x (32 rows x 128 B) = 16 KB
-  static constexpr int B_BYTES = (BLOCK_N / 32) * KBLK * 128;
+  static constexpr int MNG = TcElem<T>::KBLK;                    // elements per 128-byte MN group
+  static constexpr int KR = TcElem<T>::KBLK;                     // k-rows (= instance rows) per stage
+  static constexpr int A_GROUPS = TILE_M / MNG, B_GROUPS = BLOCK_N / MNG;
+  static constexpr int GROUP_BYTES = KR * 128;
+  static constexpr int A_BYTES = A_GROUPS * GROUP_BYTES;         // 16 KB
+  static constexpr int B_BYTES = B_GROUPS * GROUP_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int MMA_BYTES = (KR / 4) * 128;               // k-rows per MMA x 128 B
   static constexpr int TMEM_COLS = BLOCK_N <= 128 ? 128 : 256;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + 4 * 32 * STG_LD * 4 + 256;
 };
 
-template <int BLOCK_N>
+template <typename T, int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
-tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const __grid_constant__ CUtensorMap tmB /*X*/,
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY*/, const __grid_constant__ CUtensorMap tmB /*X*/,
                 int rows, int N1, int N2, int rows_per_split, float* __restrict__ ws) {
-  using Cfg = WgCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
+  using Cfg = WgCfg<T, BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES, KR = Cfg::KR, MNG = Cfg::MNG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* A_s = smem;
@@ -480,7 +557,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const
   const int mt = blockIdx.x / num_n, nt = blockIdx.x % num_n;
   const int m0 = mt * TILE_M, n0 = nt * BLOCK_N;
   const int r_beg = blockIdx.y * rows_per_split, r_end = min(rows, r_beg + rows_per_split);
-  const int kblocks = (r_end - r_beg + KBLK - 1) / KBLK;     // rows past `rows` are zero-filled by TMA
+  const int kblocks = (r_end - r_beg + KR - 1) / KR;     // rows past `rows` are zero-filled by TMA
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -499,20 +576,20 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int r0 = r_beg + kb * KBLK;
+        const int r0 = r_beg + kb * KR;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          tma_load_2d(A_s + stage * Cfg::A_BYTES + g * (KBLK * 128), &tmA, &full[stage], m0 + g * 32, r0);
+        for (int g = 0; g < Cfg::A_GROUPS; ++g)
+          tma_load_2d(A_s + stage * Cfg::A_BYTES + g * Cfg::GROUP_BYTES, &tmA, &full[stage], m0 + g * MNG, r0);
 #pragma unroll
-        for (int g = 0; g < BLOCK_N / 32; ++g)
-          tma_load_2d(B_s + stage * Cfg::B_BYTES + g * (KBLK * 128), &tmB, &full[stage], n0 + g * 32, r0);
+        for (int g = 0; g < Cfg::B_GROUPS; ++g)
+          tma_load_2d(B_s + stage * Cfg::B_BYTES + g * Cfg::GROUP_BYTES, &tmB, &full[stage], n0 + g * MNG, r0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t IDESC = idesc_tf32(TILE_M, BLOCK_N, 1, 1);
+    constexpr uint32_t IDESC = TcElem<T>::idesc(TILE_M, BLOCK_N, 1, 1);
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < kblocks; ++kb) {
       mbar_wait(&full[stage], phase);
@@ -520,10 +597,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(A_s + stage * Cfg::A_BYTES), b_addr = smem_u32(B_s + stage * Cfg::B_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < KBLK / 8; ++kk) {   // 8 k-rows = two 4-row (512-byte) SW128/32B-atom groups per MMA
-          uint64_t ad = smem_desc_sw128(a_addr + kk * 1024, KBLK * 128, 512, 1);
-          uint64_t bd = smem_desc_sw128(b_addr + kk * 1024, KBLK * 128, 512, 1);
-          mma_tf32(tmem_base, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) {   // LBO = stride between MN groups, SBO = stride between k-row swizzle groups
+          uint64_t ad = smem_desc_sw128(a_addr + kk * Cfg::MMA_BYTES, Cfg::GROUP_BYTES, TcElem<T>::MN_SBO, TcElem<T>::MN_LAYOUT);
+          uint64_t bd = smem_desc_sw128(b_addr + kk * Cfg::MMA_BYTES, Cfg::GROUP_BYTES, TcElem<T>::MN_SBO, TcElem<T>::MN_LAYOUT);
+          TcElem<T>::mma(tmem_base, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
         }
         mma_commit(&empty[stage]);
         if (kb == kblocks - 1) mma_commit(tfull);
@@ -551,12 +628,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const
       }
       stage_chunk(stg, STG_LD, 0, v, lane);
       __syncwarp();
-#pragma unroll
-      for (int i8 = 0; i8 < 8; ++i8) {
-        const int r = (lane >> 3) + 4 * i8, c4 = lane & 7, m = m_base + r;
-        if (m < N1)
-          *reinterpret_cast<float4*>(out + (size_t)m * N2 + n0 + ch * 32 + c4 * 4) = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4 * 4);
-      }
+      store_staged<float, 32>(stg, STG_LD, out, N2, m_base, N1, n0 + ch * 32, lane);
       __syncwarp();
     }
   }
@@ -568,60 +640,125 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY, box 32x32*/, const
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
-
 static int pick_block_n(int N) {
   if (N % 192 == 0 && N % 256 != 0) return 192;
   if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
   return 0;
 }
+static int kblk_of(int dt) { return dt == ELEM_BF16 ? TcElem<bf16>::KBLK : TcElem<float>::KBLK; }
 
-bool tc_linear_supported(int rows, int K, int N) { return rows >= TILE_M && K % KBLK == 0 && K >= KBLK && pick_block_n(N) != 0; }
+// library-owned, grow-only scratch for operand copies of the (small) weights: bf16 conversions and W^T.  At most a few
+// MB; the "no allocation" rule of the ABI is about activations.  One slot per use so that two operands of one call never
+// alias; reuse across calls is ordered by the stream.
+enum WSlot : int { WS_LINEAR = 0, WS_GATE = 1, WS_EMBED = 2, WS_BWD_T = 3, WS_NSLOTS = 4 };
+static int weight_scratch(int slot, size_t bytes, cudaStream_t st, void** out) {
+  static void* buf[WS_NSLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  static size_t cap[WS_NSLOTS] = {0, 0, 0, 0};
+  if (bytes > cap[slot]) {
+    ADVMIL_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (buf[slot]) cudaFree(buf[slot]);
+    buf[slot] = nullptr; cap[slot] = 0;
+    ADVMIL_CHECK_CUDA(cudaMalloc(&buf[slot], bytes));
+    cap[slot] = bytes;
+  }
+  *out = buf[slot];
+  return ADVMIL_OK;
+}
 
-template <int EPI, bool FAST>
-static int launch_rows_any(const float* A, const float* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
+__global__ void to_bf16_kernel(const float* __restrict__ in, size_t n, bf16* __restrict__ out) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) st4(out + i, *reinterpret_cast<const float4*>(in + i));
+  else for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i]);
+}
+// operand copy of a weight matrix for element type T: fp32 weights are used in place, bf16 gets a converted copy
+template <typename T>
+static int weight_operand(const float* W, size_t n, int slot, cudaStream_t st, const T** out);
+template <>
+int weight_operand<float>(const float* W, size_t, int, cudaStream_t, const float** out) { *out = W; return ADVMIL_OK; }
+template <>
+int weight_operand<bf16>(const float* W, size_t n, int slot, cudaStream_t st, const bf16** out) {
+  void* p = nullptr;
+  ADVMIL_TRY(weight_scratch(slot, n * sizeof(bf16), st, &p));
+  to_bf16_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(W, n, (bf16*)p);
+  ADVMIL_CHECK_LAUNCH();
+  *out = (const bf16*)p;
+  return ADVMIL_OK;
+}
+
+// TMA zero-fills rows past the end of the tensor, so the engine is correct for any rows >= 1; below one tile the fp32 modes
+// prefer the FFMA engine (exact fp32), the bf16 mode has no other engine
+static bool rows_ok(int rows, int dt) { return dt == ELEM_BF16 ? rows >= 1 : rows >= TILE_M; }
+bool tc_linear_supported(int rows, int K, int N, int dt) { return rows_ok(rows, dt) && K % kblk_of(dt) == 0 && pick_block_n(N) != 0; }
+
+template <typename T, int EPI, bool FAST>
+static int launch_rows_any(const T* A, const T* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
   switch (pick_block_n(N)) {
-    case 128: return launch_rows<128, EPI, FAST>(A, W, rows, K, N, ea, st);
-    case 192: return launch_rows<192, EPI, FAST>(A, W, rows, K, N, ea, st);
-    case 256: return launch_rows<256, EPI, FAST>(A, W, rows, K, N, ea, st);
+    case 128: return launch_rows<T, 128, EPI, FAST>(A, W, rows, K, N, ea, st);
+    case 192: return launch_rows<T, 192, EPI, FAST>(A, W, rows, K, N, ea, st);
+    case 256: return launch_rows<T, 256, EPI, FAST>(A, W, rows, K, N, ea, st);
   }
   set_error("tc: unsupported N=%d", N);
   return ADVMIL_ERR_INVALID;
 }
 
-int tc_linear_fwd(const float* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-                  float* y, int precision, cudaStream_t st) {
+template <typename T>
+static int tc_linear_fwd_t(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+                           void* y, cudaStream_t st) {
+  const T* Wt;
+  ADVMIL_TRY(weight_operand<T>(W, (size_t)N * K, WS_LINEAR, st, &Wt));
   RowEpi ea{};
   ea.out = y; ea.ldo = N; ea.bias = b; ea.relu = relu; ea.drop = drop;
-  return launch_rows_any<EPI_LINEAR, true>(x, W, rows, K, N, ea, st);
+  return launch_rows_any<T, EPI_LINEAR, true>((const T*)x, Wt, rows, K, N, ea, st);
+}
+int tc_linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+                  void* y, int precision, cudaStream_t st) {
+  if (precision == ADVMIL_BF16) return tc_linear_fwd_t<bf16>(x, W, b, rows, K, N, relu, drop, y, st);
+  return tc_linear_fwd_t<float>(x, W, b, rows, K, N, relu, drop, y, st);
 }
 
-bool tc_gate_supported(int rows, int L, int D) { return rows >= TILE_M && L % KBLK == 0 && D % 128 == 0; }
+bool tc_gate_supported(int rows, int L, int D, int dt) { return rows_ok(rows, dt) && L % kblk_of(dt) == 0 && D % 128 == 0; }
 
-int tc_gated_score_fwd(const float* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows,
-                       int L, int D, const Drop& da, const Drop& db, float* ab, float* s, float* part, int precision,
-                       cudaStream_t st) {
+template <typename T, bool FAST>
+static int tc_gate_t(const void* v, const float* Wp, const float* bp, const float* wc, int rows, int L, int D,
+                     const Drop& da, const Drop& db, void* ab, float* part, cudaStream_t st) {
   const int abw = gate_width(D);
+  const T* Wt;
+  ADVMIL_TRY(weight_operand<T>(Wp, (size_t)abw * L, WS_GATE, st, &Wt));
   RowEpi ea{};
   ea.bias = bp; ea.ab = ab; ea.ldo = abw; ea.wc = wc; ea.part = part; ea.D = D; ea.drop_a = da; ea.drop_b = db;
-  if (precision == ADVMIL_TF32) ADVMIL_TRY((launch_rows<256, EPI_GATE, true>(v, Wp, rows, L, abw, ea, st)));
-  else ADVMIL_TRY((launch_rows<256, EPI_GATE, false>(v, Wp, rows, L, abw, ea, st)));
-  return gate_score_finish(part, abw / 128, rows, bc, s, st);
+  return launch_rows<T, 256, EPI_GATE, FAST>((const T*)v, Wt, rows, L, abw, ea, st);
+}
+int tc_gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows,
+                       int L, int D, const Drop& da, const Drop& db, void* ab, float* s, float* part, int precision,
+                       cudaStream_t st) {
+  if (precision == ADVMIL_BF16) ADVMIL_TRY((tc_gate_t<bf16, true>(v, Wp, bp, wc, rows, L, D, da, db, ab, part, st)));
+  else if (precision == ADVMIL_TF32) ADVMIL_TRY((tc_gate_t<float, true>(v, Wp, bp, wc, rows, L, D, da, db, ab, part, st)));
+  else ADVMIL_TRY((tc_gate_t<float, false>(v, Wp, bp, wc, rows, L, D, da, db, ab, part, st)));
+  return gate_score_finish(part, gate_width(D) / 128, rows, bc, s, st);
 }
 
-bool tc_embed_supported(int rows, int C, int d) { return rows >= TILE_M && C % KBLK == 0 && d == 128; }
+bool tc_embed_supported(int rows, int C, int d, int dt) { return rows_ok(rows, dt) && C % kblk_of(dt) == 0 && d == 128; }
 
-int tc_region_embed_fwd(const float* x, const float* Wc, const float* bc, const float* gamma, const float* beta,
-                        int rows, int C, int d, float eps, float* y_pre, float* emb, int precision, cudaStream_t st) {
+template <typename T>
+static int tc_embed_t(const void* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows, int C,
+                      int d, float eps, void* y_pre, float* emb, cudaStream_t st) {
+  const T* Wt;
+  ADVMIL_TRY(weight_operand<T>(Wc, (size_t)d * C, WS_EMBED, st, &Wt));
   RowEpi ea{};
   ea.bias = bc; ea.y_pre = y_pre; ea.emb = emb; ea.gamma = gamma; ea.beta = beta; ea.eps = eps;
-  return launch_rows<128, EPI_LN, true>(x, Wc, rows, C, d, ea, st);
+  return launch_rows<T, 128, EPI_LN, true>((const T*)x, Wt, rows, C, d, ea, st);
+}
+int tc_region_embed_fwd(const void* x, const float* Wc, const float* bc, const float* gamma, const float* beta,
+                        int rows, int C, int d, float eps, void* y_pre, float* emb, int precision, cudaStream_t st) {
+  if (precision == ADVMIL_BF16) return tc_embed_t<bf16>(x, Wc, bc, gamma, beta, rows, C, d, eps, y_pre, emb, st);
+  return tc_embed_t<float>(x, Wc, bc, gamma, beta, rows, C, d, eps, y_pre, emb, st);
 }
 
-// dX = dY . W with W [Ny, Nx] row-major: needs W^T [Nx, Ny] K-major; the transpose of the (small) weight is made by
-// the caller-provided scratch through tc_transpose
-__global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, float* __restrict__ out) {
+// dX = dY . W with W [Ny, Nx] row-major fp32: the engine needs W^T [Nx, Ny] K-major in the operand type; the transpose
+// of the (small) weight goes to library scratch
+template <typename T>
+__global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, T* __restrict__ out) {
   __shared__ float t[32][33];
   int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8)
@@ -629,31 +766,30 @@ __global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, fl
   __syncthreads();
   int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
   for (int j = threadIdx.y; j < 32; j += 8)
-    if (ox < R && oy0 + j < Cc) out[(size_t)(oy0 + j) * R + ox] = t[threadIdx.x][j];
+    if (ox < R && oy0 + j < Cc) st1(out + (size_t)(oy0 + j) * R + ox, t[threadIdx.x][j]);
 }
 
-bool tc_bwd_data_supported(int rows, int Ny, int Nx) {
-  return rows >= TILE_M && Ny % KBLK == 0 && pick_block_n(Nx) != 0 && (size_t)Ny * Nx <= (size_t)1 << 20;
+bool tc_bwd_data_supported(int rows, int Ny, int Nx, int dt) {
+  return rows_ok(rows, dt) && Ny % kblk_of(dt) == 0 && pick_block_n(Nx) != 0 && (size_t)Ny * Nx <= (size_t)1 << 20;
 }
 
-int tc_bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* dX, const BwdDataExtras& ex,
-                int precision, cudaStream_t st) {
-  // W^T scratch: library-owned, grow-only, at most 4 MB (weights only; the "no allocation" rule is about activations)
-  static float* wt = nullptr; static size_t cap = 0;
-  size_t need = (size_t)Ny * Nx;
-  if (need > cap) {
-    ADVMIL_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (wt) cudaFree(wt);
-    ADVMIL_CHECK_CUDA(cudaMalloc(&wt, need * sizeof(float)));
-    cap = need;
-  }
+template <typename T>
+static int tc_bwd_data_t(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX, const BwdDataExtras& ex,
+                         cudaStream_t st) {
+  void* wt = nullptr;
+  ADVMIL_TRY(weight_scratch(WS_BWD_T, (size_t)Ny * Nx * sizeof(T), st, &wt));
   ADVMIL_REQUIRE(!ex.accumulate && !ex.dmean, "tc_bwd_data: accumulate/dmean are served by the FFMA engine");
-  transpose_kernel<<<dim3(cdiv(Nx, 32), cdiv(Ny, 32)), dim3(32, 8), 0, st>>>(W, Ny, Nx, wt);
+  transpose_kernel<T><<<dim3(cdiv(Nx, 32), cdiv(Ny, 32)), dim3(32, 8), 0, st>>>(W, Ny, Nx, (T*)wt);
   ADVMIL_CHECK_LAUNCH();
   RowEpi ea{};
   ea.out = dX; ea.ldo = Nx; ea.w = ex.w; ea.dz = ex.dz; ea.offsets = ex.offsets; ea.bags = ex.bags;
   ea.relu_src = ex.relu_src; ea.ld_src = ex.ld_src; ea.inv_keep = ex.inv_keep;
-  return launch_rows_any<EPI_BWD, true>(dY, wt, rows, Ny, Nx, ea, st);
+  return launch_rows_any<T, EPI_BWD, true>((const T*)dY, (const T*)wt, rows, Ny, Nx, ea, st);
+}
+int tc_bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX, const BwdDataExtras& ex,
+                int precision, cudaStream_t st) {
+  if (precision == ADVMIL_BF16) return tc_bwd_data_t<bf16>(dY, W, rows, Ny, Nx, dX, ex, st);
+  return tc_bwd_data_t<float>(dY, W, rows, Ny, Nx, dX, ex, st);
 }
 
 static int wgrad_block_n(int N2) {
@@ -668,23 +804,22 @@ static int wgrad_splits(int rows, int N1, int N2) {
   int max_by_rows = max(1, rows / 1024);
   return min(s, max_by_rows);
 }
-bool tc_bwd_weight_supported(int rows, int N1, int N2) {
-  return rows >= 4096 && N1 % 32 == 0 && N1 >= 128 && wgrad_block_n(N2) != 0;
+bool tc_bwd_weight_supported(int rows, int N1, int N2, int dt) {
+  return (dt == ELEM_BF16 ? rows >= 1 : rows >= 4096) && N1 % kblk_of(dt) == 0 && N1 >= 128 && wgrad_block_n(N2) != 0;
 }
 size_t tc_bwd_weight_ws_floats(int rows, int N1, int N2) {
-  if (!tc_bwd_weight_supported(rows, N1, N2)) return 0;
+  if (wgrad_block_n(N2) == 0 || N1 < 128) return 0;
   return (size_t)wgrad_splits(rows, N1, N2) * N1 * N2;
 }
 
-template <int BLOCK_N>
-static int launch_wgrad(const float* dY, const float* X, int rows, int N1, int N2, int rows_per_split, int nsplit, float* ws,
+template <typename T, int BLOCK_N>
+static int launch_wgrad(const T* dY, const T* X, int rows, int N1, int N2, int rows_per_split, int nsplit, float* ws,
                         cudaStream_t st) {
-  using Cfg = WgCfg<BLOCK_N>;
+  using Cfg = WgCfg<T, BLOCK_N>;
   CUtensorMap tmA, tmB;
-  // MN-major tf32 operands need the 128-byte swizzle with 32-byte atoms on both the TMA and the UMMA side
-  ADVMIL_TRY(make_tmap(&tmA, dY, rows, N1, KBLK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  ADVMIL_TRY(make_tmap(&tmB, X, rows, N2, KBLK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  auto kern = tc_wgrad_kernel<BLOCK_N>;
+  ADVMIL_TRY(make_tmap<T>(&tmA, dY, rows, N1, Cfg::KR, TcElem<T>::MN_SWZ));
+  ADVMIL_TRY(make_tmap<T>(&tmB, X, rows, N2, Cfg::KR, TcElem<T>::MN_SWZ));
+  auto kern = tc_wgrad_kernel<T, BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
     ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -696,14 +831,21 @@ static int launch_wgrad(const float* dY, const float* X, int rows, int N1, int N
   return ADVMIL_OK;
 }
 
-int tc_bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
-                  int precision, cudaStream_t st) {
+template <typename T>
+static int tc_bwd_weight_t(const void* dY, const void* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+                           cudaStream_t st) {
+  constexpr int KR = TcElem<T>::KBLK;
   const int splits = wgrad_splits(rows, N1, N2);
-  const int rows_per_split = cdiv(cdiv(rows, splits), KBLK) * KBLK;
+  const int rows_per_split = cdiv(cdiv(rows, splits), KR) * KR;
   const int nsplit = cdiv(rows, rows_per_split);
-  if (wgrad_block_n(N2) == 256) ADVMIL_TRY((launch_wgrad<256>(dY, X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
-  else ADVMIL_TRY((launch_wgrad<128>(dY, X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
+  if (wgrad_block_n(N2) == 256) ADVMIL_TRY((launch_wgrad<T, 256>((const T*)dY, (const T*)X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
+  else ADVMIL_TRY((launch_wgrad<T, 128>((const T*)dY, (const T*)X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
   return splitk_reduce(ws, nsplit, (size_t)N1 * N2, dW, accumulate, st);
+}
+int tc_bwd_weight(const void* dY, const void* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+                  int precision, cudaStream_t st) {
+  if (precision == ADVMIL_BF16) return tc_bwd_weight_t<bf16>(dY, X, rows, N1, N2, dW, accumulate, ws, st);
+  return tc_bwd_weight_t<float>(dY, X, rows, N1, N2, dW, accumulate, ws, st);
 }
 
 }  // namespace advmil

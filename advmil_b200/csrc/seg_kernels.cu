@@ -21,6 +21,28 @@ int fill_zero(float* p, size_t n, cudaStream_t st) {
   return ADVMIL_OK;
 }
 
+__global__ void cast_bf16_kernel(const float* __restrict__ in, size_t n, bf16* __restrict__ out) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+  for (; i < n; i += stride) {
+    if (i + 7 < n) {
+      const float4 a = *reinterpret_cast<const float4*>(in + i), b = *reinterpret_cast<const float4*>(in + i + 4);
+      const float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      stv(out + i, o);
+    } else {
+      for (size_t j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+    }
+  }
+}
+int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st) {
+  if (n == 0) return ADVMIL_OK;
+  ADVMIL_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "cast_f32_to_bf16: pointers must be 16-byte aligned");
+  const int grid = (int)min((size_t)148 * 16, (n / 8 + 255) / 256 + 1);
+  cast_bf16_kernel<<<grid, 256, 0, st>>>(in, n, (bf16*)out);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
 // out[c] (+)= sum_p part[p][c]; block (32,8): 8 row groups per column
 __global__ void reduce_rows_kernel(const float* __restrict__ part, int nparts, int width /*row stride*/, int ncols,
                                    float* __restrict__ out, int accumulate) {
@@ -78,17 +100,33 @@ int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumul
   return ADVMIL_OK;
 }
 
-__global__ void apply_dropout_kernel(const float* __restrict__ src, size_t n, Drop drop, float* __restrict__ dst) {
+template <typename T>
+__global__ void apply_dropout_kernel(const T* __restrict__ src, size_t nvec, Drop drop, T* __restrict__ dst) {
+  constexpr int VEC = VecN<T>::N;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] = src[i] * drop.scale(i);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < nvec; i += stride) {
+    float v[VEC];
+    ldv(src + i * VEC, v);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] *= drop.scale(i * VEC + e);
+    stv(dst + i * VEC, v);
+  }
 }
-int apply_dropout(const float* src, int rows, int width, const Drop& drop, float* dst, cudaStream_t st) {
-  size_t n = (size_t)rows * width;
-  int grid = (int)min((size_t)148 * 16, (n + 255) / 256);
-  apply_dropout_kernel<<<grid, 256, 0, st>>>(src, n, drop, dst);
+template <typename T>
+static int apply_dropout_t(const T* src, int rows, int width, const Drop& drop, T* dst, cudaStream_t st) {
+  constexpr int VEC = VecN<T>::N;
+  ADVMIL_REQUIRE(width % VEC == 0, "apply_dropout: width %d must be a multiple of %d", width, VEC);
+  const size_t nvec = (size_t)rows * width / VEC;
+  if (nvec == 0) return ADVMIL_OK;
+  const int grid = (int)min((size_t)148 * 16, (nvec + 255) / 256);
+  apply_dropout_kernel<T><<<grid, 256, 0, st>>>(src, nvec, drop, dst);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
+}
+int apply_dropout(const void* src, int rows, int width, const Drop& drop, void* dst, int dt, cudaStream_t st) {
+  if (dt == ELEM_BF16) return apply_dropout_t<bf16>((const bf16*)src, rows, width, drop, (bf16*)dst, st);
+  return apply_dropout_t<float>((const float*)src, rows, width, drop, (float*)dst, st);
 }
 
 // =============================================================================================
@@ -182,11 +220,13 @@ __global__ void seg_stats_kernel(const float* __restrict__ s, const int32_t* __r
   if (threadIdx.x == 0) { stats[2 * b] = mx; stats[2 * b + 1] = 1.0f / sum; }
 }
 
-// grid (maxchunks, bags), 256 threads = RG row groups x W4 float4 columns
+// grid (maxchunks, bags); threads = RG row groups x WV 16-byte vectors per row
+template <typename T>
 __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
-    const float* __restrict__ s, const float* __restrict__ v, const int32_t* __restrict__ offsets,
+    const float* __restrict__ s, const T* __restrict__ v, const int32_t* __restrict__ offsets,
     const float* __restrict__ stats, int width, int want_mean, float* __restrict__ w,
     float* __restrict__ part /*[offsets[b]/POOL_CH + b + chunk][width]*/, float* __restrict__ part_mean) {
+  constexpr int VEC = VecN<T>::N;
   extern __shared__ float sm[];  // w_s[POOL_CH] + red[RG][width] (+ red_mean)
   int b = blockIdx.y, chunk = blockIdx.x;
   int beg = offsets[b] + chunk * POOL_CH, end = min(offsets[b + 1], beg + POOL_CH);
@@ -200,37 +240,42 @@ __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
     w[beg + r] = wv;
   }
   __syncthreads();
-  int W4 = width >> 2;
-  int RG = blockDim.x / W4; if (RG > POOL_CH) RG = POOL_CH;
-  int c4 = threadIdx.x % W4, rg = threadIdx.x / W4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accm = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int WV = width / VEC;
+  int RG = blockDim.x / WV; if (RG > POOL_CH) RG = POOL_CH;
+  const int cv = threadIdx.x % WV, rg = threadIdx.x / WV;
+  float acc[VEC], accm[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { acc[e] = 0.f; accm[e] = 0.f; }
   if (rg < RG) {
-    const float4* vp = reinterpret_cast<const float4*>(v + (size_t)beg * width) + c4;
+    const T* vp = v + (size_t)beg * width + cv * VEC;
     int r = rg;
     for (; r + 3 * RG < nrows; r += 4 * RG) {
-      float4 x0 = vp[(size_t)r * W4], x1 = vp[(size_t)(r + RG) * W4], x2 = vp[(size_t)(r + 2 * RG) * W4], x3 = vp[(size_t)(r + 3 * RG) * W4];
-      float w0 = w_s[r], w1 = w_s[r + RG], w2 = w_s[r + 2 * RG], w3 = w_s[r + 3 * RG];
-      acc.x += w0 * x0.x + w1 * x1.x + w2 * x2.x + w3 * x3.x;
-      acc.y += w0 * x0.y + w1 * x1.y + w2 * x2.y + w3 * x3.y;
-      acc.z += w0 * x0.z + w1 * x1.z + w2 * x2.z + w3 * x3.z;
-      acc.w += w0 * x0.w + w1 * x1.w + w2 * x2.w + w3 * x3.w;
-      if (want_mean) {
-        accm.x += (x0.x + x1.x) + (x2.x + x3.x); accm.y += (x0.y + x1.y) + (x2.y + x3.y);
-        accm.z += (x0.z + x1.z) + (x2.z + x3.z); accm.w += (x0.w + x1.w) + (x2.w + x3.w);
+      float x0[VEC], x1[VEC], x2[VEC], x3[VEC];
+      ldv(vp + (size_t)r * width, x0); ldv(vp + (size_t)(r + RG) * width, x1);
+      ldv(vp + (size_t)(r + 2 * RG) * width, x2); ldv(vp + (size_t)(r + 3 * RG) * width, x3);
+      const float w0 = w_s[r], w1 = w_s[r + RG], w2 = w_s[r + 2 * RG], w3 = w_s[r + 3 * RG];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        acc[e] += w0 * x0[e] + w1 * x1[e] + w2 * x2[e] + w3 * x3[e];
+        if (want_mean) accm[e] += (x0[e] + x1[e]) + (x2[e] + x3[e]);
       }
     }
     for (; r < nrows; r += RG) {
-      float4 x0 = vp[(size_t)r * W4];
-      float w0 = w_s[r];
-      acc.x += w0 * x0.x; acc.y += w0 * x0.y; acc.z += w0 * x0.z; acc.w += w0 * x0.w;
-      if (want_mean) { accm.x += x0.x; accm.y += x0.y; accm.z += x0.z; accm.w += x0.w; }
+      float x0[VEC];
+      ldv(vp + (size_t)r * width, x0);
+      const float w0 = w_s[r];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { acc[e] += w0 * x0[e]; if (want_mean) accm[e] += x0[e]; }
     }
   }
   float* red = sm + POOL_CH;
   float* redm = red + (size_t)RG * width;
   if (rg < RG) {
-    *reinterpret_cast<float4*>(red + (size_t)rg * width + c4 * 4) = acc;
-    if (want_mean) *reinterpret_cast<float4*>(redm + (size_t)rg * width + c4 * 4) = accm;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      red[(size_t)rg * width + cv * VEC + e] = acc[e];
+      if (want_mean) redm[(size_t)rg * width + cv * VEC + e] = accm[e];
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
@@ -280,9 +325,11 @@ size_t seg_pool_ws_floats(int rows, int bags, int width) {
   size_t nparts = (size_t)rows / POOL_CH + bags + 1;  // sum_b ceil(len_b / POOL_CH) <= rows/POOL_CH + bags
   return align_up(2 * (size_t)bags, 64) + 2 * nparts * width;
 }
-int seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets, const int32_t* offsets_host, int rows,
-                         int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st) {
-  ADVMIL_REQUIRE(width % 4 == 0 && width <= 1024, "seg_softmax_pool: width %d must be a multiple of 4 and <= 1024", width);
+template <typename T>
+static int seg_softmax_pool_fwd_t(const float* s, const T* v, const int32_t* offsets, const int32_t* offsets_host, int rows,
+                                  int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st) {
+  constexpr int VEC = VecN<T>::N;
+  ADVMIL_REQUIRE(width % VEC == 0 && width <= 1024, "seg_softmax_pool: width %d must be a multiple of %d and <= 1024", width, VEC);
   for (int b = 0; b < bags; ++b)
     ADVMIL_REQUIRE(offsets_host[b + 1] > offsets_host[b], "seg_softmax_pool: bag %d is empty", b);
   int maxchunks = pool_maxchunks(offsets_host, bags);
@@ -291,16 +338,24 @@ int seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets,
   float* part_mean = part + ((size_t)rows / POOL_CH + bags + 1) * width;
   seg_stats_kernel<<<bags, 1024, 0, st>>>(s, offsets, stats);
   ADVMIL_CHECK_LAUNCH();
-  int W4 = width / 4;
-  int threads = (W4 % 32 == 0 && 4 * W4 <= 512) ? 4 * W4 : 256;      // 384 threads for width 384: 4 full row groups
-  int RG = min(threads / W4, POOL_CH);
+  const int WV = width / VEC;
+  int threads = 256;                                   // whole row groups when the row divides a 512/384-thread block
+  if ((8 * WV) % 32 == 0 && 8 * WV <= 512) threads = 8 * WV;
+  else if ((4 * WV) % 32 == 0 && 4 * WV <= 512) threads = 4 * WV;
+  int RG = min(threads / WV, POOL_CH);
   size_t smem = (POOL_CH + (size_t)RG * width * (mean ? 2 : 1)) * sizeof(float);
-  seg_pool_partial_kernel<<<dim3(maxchunks, bags), threads, smem, st>>>(s, v, offsets, stats, width, mean ? 1 : 0, w,
-                                                                     part, part_mean);
+  seg_pool_partial_kernel<T><<<dim3(maxchunks, bags), threads, smem, st>>>(s, v, offsets, stats, width, mean ? 1 : 0, w,
+                                                                        part, part_mean);
   ADVMIL_CHECK_LAUNCH();
   seg_pool_final_kernel<<<dim3(cdiv(width, 128), bags), dim3(128, 8), 0, st>>>(part, mean ? part_mean : nullptr, offsets, width, z, mean);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
+}
+int seg_softmax_pool_fwd(const float* s, const void* v, int dt, const int32_t* offsets, const int32_t* offsets_host,
+                         int rows, int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st) {
+  if (dt == ELEM_BF16)
+    return seg_softmax_pool_fwd_t<bf16>(s, (const bf16*)v, offsets, offsets_host, rows, bags, width, w, z, mean, ws, st);
+  return seg_softmax_pool_fwd_t<float>(s, (const float*)v, offsets, offsets_host, rows, bags, width, w, z, mean, ws, st);
 }
 
 // =============================================================================================
@@ -316,79 +371,89 @@ __global__ void bag_dot_kernel(const float* __restrict__ a, const float* __restr
   if (threadIdx.x == 0) out[bag] = acc;
 }
 
-// one thread per gate-column pair (blockDim = abw/2 rounded up to a warp multiple, <= 512), rows of the chunk unrolled x4;
-// also accumulates the column sums of dAB (the packed gate-bias gradient) so no separate pass over dAB is needed
+// Phase 1: one warp per row computes ds.  Phase 2: thread (rg, pv) owns VEC consecutive gate-column pairs of every RGN-th
+// row: 16-byte loads of the tanh / sigmoid vectors, 16-byte stores of dA / dB.  Also accumulates dwc and the column sums
+// of dAB (the packed gate-bias gradient), so no separate pass over dAB is needed.
+template <typename T>
 __global__ void __launch_bounds__(512) pool_gate_bwd_kernel(
-    const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ dz,
-    const float* __restrict__ gz, const float* __restrict__ ab, const float* __restrict__ wc,
-    const int32_t* __restrict__ offsets, int rows, int bags, int L, int D, int abw, Drop da, Drop db,
-    float* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
+    const T* __restrict__ v, const float* __restrict__ w, const float* __restrict__ dz,
+    const float* __restrict__ gz, const T* __restrict__ ab, const float* __restrict__ wc,
+    const int32_t* __restrict__ offsets, int rows, int bags, int L, int D, int abw, int RGN, Drop da, Drop db,
+    T* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
+  constexpr int VEC = VecN<T>::N;
+  extern __shared__ float red3[];              // [RGN][3][npairs]
   __shared__ float ds_s[ROWS_PER_CTA];
   __shared__ float red[33];
   const int row0 = blockIdx.x * ROWS_PER_CTA;
   const int nrows = min(ROWS_PER_CTA, rows - row0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  // phase 1: one warp per row: g = dz[bag] . v[row]
+  // phase 1: g = dz[bag] . v[row]
   for (int r = wid; r < nrows; r += nw) {
     const int row = row0 + r;
     const int bag = bag_of_row(offsets, bags, row);
-    const float* vr = v + (size_t)row * L;
+    const T* vr = v + (size_t)row * L;
     const float* dzr = dz + (size_t)bag * L;
     float acc = 0.f;
-    for (int c = lane * 4; c < L; c += 128) {
-      float4 x = *reinterpret_cast<const float4*>(vr + c);
-      float4 g = *reinterpret_cast<const float4*>(dzr + c);
-      acc += x.x * g.x + x.y * g.y + x.z * g.z + x.w * g.w;
+    for (int c = lane * VEC; c < L; c += 32 * VEC) {
+      float x[VEC];
+      ldv(vr + c, x);
+#pragma unroll
+      for (int q4 = 0; q4 < VEC / 4; ++q4) {
+        const float4 g = *reinterpret_cast<const float4*>(dzr + c + 4 * q4);
+        acc += x[4 * q4] * g.x + x[4 * q4 + 1] * g.y + x[4 * q4 + 2] * g.z + x[4 * q4 + 3] * g.w;
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) ds_s[r] = w[row] * (acc - gz[bag]);
   }
   __syncthreads();
   // phase 2
-  const int npairs = abw >> 1;
-  for (int q = threadIdx.x; q < npairs; q += blockDim.x) {
-    const int ca = gate_col_a(q);
-    const bool valid = q < D;
-    const float wcj = valid ? wc[q] : 0.f;
-    float dwc = 0.f, sa_sum = 0.f, sb_sum = 0.f;
-    const bool tr = da.active != 0;
-    int r = 0;
-    for (; r + 3 < nrows; r += 4) {
-      float a[4], b[4];
+  const int npairs = abw >> 1, TPR = npairs / VEC;
+  const int rg = threadIdx.x / TPR, pv = threadIdx.x % TPR;
+  const bool tr = da.active != 0;
+  if (rg < RGN) {
+    const int q0 = pv * VEC, ca = gate_col_a(q0);
+    float wcj[VEC], dwc[VEC], sa_sum[VEC], sb_sum[VEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const size_t row = (size_t)(row0 + r + u);
-        a[u] = valid ? ab[row * abw + ca] : 0.f;
-        b[u] = valid ? ab[row * abw + ca + 64] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const size_t row = (size_t)(row0 + r + u);
-        float sa = 1.f, sb = 1.f;
-        if (tr && valid) { sa = da.keep(row * D + q) ? da.inv_keep : 0.f; sb = db.keep(row * D + q) ? db.inv_keep : 0.f; }
-        const float ad = a[u] * sa, bd = b[u] * sb, ds = ds_s[r + u], du = ds * wcj;
-        const float oa = du * bd * sa * (1.f - a[u] * a[u]);
-        const float ob = du * ad * sb * b[u] * (1.f - b[u]);
-        dwc = fmaf(ds, ad * bd, dwc);
-        sa_sum += oa; sb_sum += ob;
-        dAB[row * abw + ca] = oa;
-        dAB[row * abw + ca + 64] = ob;
-      }
-    }
-    for (; r < nrows; ++r) {
+    for (int e = 0; e < VEC; ++e) { wcj[e] = (q0 + e < D) ? wc[q0 + e] : 0.f; dwc[e] = 0.f; sa_sum[e] = 0.f; sb_sum[e] = 0.f; }
+#pragma unroll 2
+    for (int r = rg; r < nrows; r += RGN) {
       const size_t row = (size_t)(row0 + r);
-      const float a = valid ? ab[row * abw + ca] : 0.f, b = valid ? ab[row * abw + ca + 64] : 0.f;
-      float sa = 1.f, sb = 1.f;
-      if (tr && valid) { sa = da.keep(row * D + q) ? da.inv_keep : 0.f; sb = db.keep(row * D + q) ? db.inv_keep : 0.f; }
-      const float ad = a * sa, bd = b * sb, ds = ds_s[r], du = ds * wcj;
-      const float oa = du * bd * sa * (1.f - a * a), ob = du * ad * sb * b * (1.f - b);
-      dwc = fmaf(ds, ad * bd, dwc);
-      sa_sum += oa; sb_sum += ob;
-      dAB[row * abw + ca] = oa;
-      dAB[row * abw + ca + 64] = ob;
+      float a[VEC], b[VEC], oa[VEC], ob[VEC];
+      ldv(ab + row * abw + ca, a);
+      ldv(ab + row * abw + ca + 64, b);
+      const float ds = ds_s[r];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const bool valid = q0 + e < D;
+        float sa = 1.f, sb = 1.f;
+        if (tr && valid) { sa = da.keep(row * D + q0 + e) ? da.inv_keep : 0.f; sb = db.keep(row * D + q0 + e) ? db.inv_keep : 0.f; }
+        const float av = valid ? a[e] : 0.f, bv = valid ? b[e] : 0.f;
+        const float ad = av * sa, bd = bv * sb, du = ds * wcj[e];
+        oa[e] = du * bd * sa * (1.f - av * av);
+        ob[e] = du * ad * sb * bv * (1.f - bv);
+        dwc[e] = fmaf(ds, ad * bd, dwc[e]);
+        sa_sum[e] += oa[e]; sb_sum[e] += ob[e];
+      }
+      stv(dAB + row * abw + ca, oa);
+      stv(dAB + row * abw + ca + 64, ob);
     }
-    if (valid) part[(size_t)blockIdx.x * (D + 1) + q] = dwc;
-    if (part_b) { part_b[(size_t)blockIdx.x * abw + ca] = sa_sum; part_b[(size_t)blockIdx.x * abw + ca + 64] = sb_sum; }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      red3[((size_t)rg * 3 + 0) * npairs + q0 + e] = dwc[e];
+      red3[((size_t)rg * 3 + 1) * npairs + q0 + e] = sa_sum[e];
+      red3[((size_t)rg * 3 + 2) * npairs + q0 + e] = sb_sum[e];
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < npairs; q += blockDim.x) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int g = 0; g < RGN; ++g) {
+      t0 += red3[((size_t)g * 3 + 0) * npairs + q]; t1 += red3[((size_t)g * 3 + 1) * npairs + q]; t2 += red3[((size_t)g * 3 + 2) * npairs + q];
+    }
+    const int ca = gate_col_a(q);
+    if (q < D) part[(size_t)blockIdx.x * (D + 1) + q] = t0;
+    if (part_b) { part_b[(size_t)blockIdx.x * abw + ca] = t1; part_b[(size_t)blockIdx.x * abw + ca + 64] = t2; }
   }
   float t = 0.f;
   for (int r = threadIdx.x; r < nrows; r += blockDim.x) t += ds_s[r];
@@ -396,10 +461,12 @@ __global__ void __launch_bounds__(512) pool_gate_bwd_kernel(
   if (threadIdx.x == 0) part[(size_t)blockIdx.x * (D + 1) + D] = t;
 }
 
-int pool_gate_bwd(const float* v, const float* w, const float* z, const float* dz, const float* ab, const float* wc,
-                  const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, float* dAB,
-                  float* dwc, float* dbc, float* dbp, int accumulate, float* ws, cudaStream_t st) {
-  ADVMIL_REQUIRE(L % 4 == 0, "pool_gate_bwd: L %d must be a multiple of 4", L);
+template <typename T>
+static int pool_gate_bwd_t(const T* v, const float* w, const float* z, const float* dz, const T* ab, const float* wc,
+                           const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, T* dAB,
+                           float* dwc, float* dbc, float* dbp, int accumulate, float* ws, cudaStream_t st) {
+  constexpr int VEC = VecN<T>::N;
+  ADVMIL_REQUIRE(L % VEC == 0, "pool_gate_bwd: L %d must be a multiple of %d", L, VEC);
   const int chunks = row_chunks(rows);
   const int abw = gate_width(D);
   float* gz = ws;
@@ -407,8 +474,18 @@ int pool_gate_bwd(const float* v, const float* w, const float* z, const float* d
   float* part_b = dbp ? part + align_up((size_t)chunks * (D + 1), 64) : nullptr;
   bag_dot_kernel<<<bags, 128, 0, st>>>(dz, z, L, gz);
   ADVMIL_CHECK_LAUNCH();
-  const int threads = min(512, ((abw / 2 + 31) / 32) * 32);
-  pool_gate_bwd_kernel<<<chunks, threads, 0, st>>>(v, w, dz, gz, ab, wc, offsets, rows, bags, L, D, abw, da, db, dAB, part, part_b);
+  const int npairs = abw / 2, TPR = npairs / VEC;
+  ADVMIL_REQUIRE(TPR >= 1 && TPR <= 512, "pool_gate_bwd: gate width %d unsupported", abw);
+  const int RGN = max(1, min(384 / TPR, 16));
+  const int threads = max(128, ((TPR * RGN + 31) / 32) * 32);
+  const size_t smem = (size_t)RGN * 3 * npairs * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(pool_gate_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  ADVMIL_REQUIRE(smem <= 96 * 1024, "pool_gate_bwd: gate width %d needs too much shared memory", abw);
+  pool_gate_bwd_kernel<T><<<chunks, threads, smem, st>>>(v, w, dz, gz, ab, wc, offsets, rows, bags, L, D, abw, RGN, da, db, dAB, part, part_b);
   ADVMIL_CHECK_LAUNCH();
   reduce_rows_kernel<<<cdiv(D, 32), dim3(32, 32), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
   ADVMIL_CHECK_LAUNCH();
@@ -419,6 +496,15 @@ int pool_gate_bwd(const float* v, const float* w, const float* z, const float* d
     ADVMIL_CHECK_LAUNCH();
   }
   return ADVMIL_OK;
+}
+int pool_gate_bwd(const void* v, const float* w, const float* z, const float* dz, const void* ab, const float* wc,
+                  const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, void* dAB,
+                  float* dwc, float* dbc, float* dbp, int accumulate, float* ws, int dt, cudaStream_t st) {
+  if (dt == ELEM_BF16)
+    return pool_gate_bwd_t<bf16>((const bf16*)v, w, z, dz, (const bf16*)ab, wc, offsets, rows, bags, L, D, da, db, (bf16*)dAB,
+                                 dwc, dbc, dbp, accumulate, ws, st);
+  return pool_gate_bwd_t<float>((const float*)v, w, z, dz, (const float*)ab, wc, offsets, rows, bags, L, D, da, db,
+                                (float*)dAB, dwc, dbc, dbp, accumulate, ws, st);
 }
 
 // =============================================================================================
@@ -499,60 +585,109 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
   }
 }
 
-// d == 128: one float4 per lane per row, two rows in flight per warp
+// d == 128: 8 lanes per row (16 columns per lane as 16-byte vectors interleaved across the 8 lanes so that every load
+// instruction covers 128 contiguous bytes per row), 4 rows per warp, two such groups in flight
+template <typename T>
 __global__ void __launch_bounds__(256) ln_pool_bwd128_kernel(
-    const float* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ gamma,
-    const float* __restrict__ beta, int rows, float eps, float* __restrict__ d_y, float* __restrict__ part) {
+    const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y, float* __restrict__ part) {
+  constexpr int VEC = VecN<T>::N, NV = 16 / VEC;          // vectors per lane
   __shared__ float sm[8 * 3 * 128];
   const int row0 = blockIdx.x * ROWS_PER_CTA;
   const int nrows = min(ROWS_PER_CTA, rows - row0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4), b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
-  const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
-  float pg[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f}, pbias[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r = wid * 2; r < nrows; r += 16) {
-    float4 y4[2], e4[2];
+  const int sub = lane & 7, slot = lane >> 3;             // column group, row slot within the warp
+  // column of element (k, e): k * 8 * VEC + sub * VEC + e
+  float g[16], be[16], pg[16], pb[16], pbias[16];
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int c = k * 8 * VEC + sub * VEC + e;
+      g[k * VEC + e] = gamma[c]; be[k * VEC + e] = beta[c];
+      pg[k * VEC + e] = 0.f; pb[k * VEC + e] = 0.f; pbias[k * VEC + e] = 0.f;
+    }
+  for (int rb = wid * 8; rb < nrows; rb += 64) {
+    float y[2][16], ge[16];
     bool ok[2];
+    // rb is a multiple of 8: the 8 rows of this warp iteration lie in ONE 16-row region
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int q4 = 0; q4 < VEC / 4; ++q4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(d_emb + ((size_t)(row0 + rb) >> 4) * 128 + k * 8 * VEC + sub * VEC + 4 * q4);
+        ge[k * VEC + 4 * q4] = d4.x; ge[k * VEC + 4 * q4 + 1] = d4.y; ge[k * VEC + 4 * q4 + 2] = d4.z; ge[k * VEC + 4 * q4 + 3] = d4.w;
+      }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      ok[u] = r + u < nrows;
-      const size_t row = (size_t)(row0 + r + u);
-      y4[u] = ok[u] ? *reinterpret_cast<const float4*>(y_pre + row * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      e4[u] = ok[u] ? *reinterpret_cast<const float4*>(d_emb + (row >> 4) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = rb + u * 4 + slot;
+      ok[u] = r < nrows;
+      const size_t row = (size_t)(row0 + r);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float t[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) t[e] = 0.f;
+        if (ok[u]) ldv(y_pre + row * 128 + k * 8 * VEC + sub * VEC, t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) y[u][k * VEC + e] = t[e];
+      }
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const size_t row = (size_t)(row0 + r + u);
-      const float y[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w}, ge[4] = {e4[u].x, e4[u].y, e4[u].z, e4[u].w};
-      const float mean = warp_sum(y[0] + y[1] + y[2] + y[3]) * (1.0f / 128.0f);
+      const size_t row = (size_t)(row0 + rb + u * 4 + slot);
+      float sacc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sacc += y[u][i];
+      const float mean = oct_sum(sacc) * (1.0f / 128.0f);
       float q = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const float c = y[k] - mean; q = fmaf(c, c, q); }
-      const float rstd = rsqrtf(warp_sum(q) * (1.0f / 128.0f) + eps);
-      float xh[4], dxh[4], s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < 16; ++i) { const float c = y[u][i] - mean; q = fmaf(c, c, q); }
+      const float rstd = rsqrtf(oct_sum(q) * (1.0f / 128.0f) + eps);
+      float xh[16], dxh[16], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        xh[k] = (y[k] - mean) * rstd;
-        const float e = fmaf(xh[k], g[k], be[k]);
-        const float de = (e > 0.f && ok[u]) ? ge[k] * (1.0f / 16.0f) : 0.f;
-        pg[k] = fmaf(de, xh[k], pg[k]);
-        pb[k] += de;
-        dxh[k] = de * g[k];
-        s1 += dxh[k];
-        s2 = fmaf(dxh[k], xh[k], s2);
+      for (int i = 0; i < 16; ++i) {
+        xh[i] = (y[u][i] - mean) * rstd;
+        const float e = fmaf(xh[i], g[i], be[i]);
+        const float de = (e > 0.f && ok[u]) ? ge[i] * (1.0f / 16.0f) : 0.f;
+        pg[i] = fmaf(de, xh[i], pg[i]);
+        pb[i] += de;
+        dxh[i] = de * g[i];
+        s1 += dxh[i];
+        s2 = fmaf(dxh[i], xh[i], s2);
       }
-      const float m1 = warp_sum(s1) * (1.0f / 128.0f), m2 = warp_sum(s2) * (1.0f / 128.0f);
-      float dy[4];
+      const float m1 = oct_sum(s1) * (1.0f / 128.0f), m2 = oct_sum(s2) * (1.0f / 128.0f);
+      float dy[16];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { dy[k] = rstd * (dxh[k] - m1 - xh[k] * m2); if (ok[u]) pbias[k] += dy[k]; }
-      if (ok[u]) *reinterpret_cast<float4*>(d_y + row * 128 + lane * 4) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+      for (int i = 0; i < 16; ++i) { dy[i] = rstd * (dxh[i] - m1 - xh[i] * m2); if (ok[u]) pbias[i] += dy[i]; }
+      if (ok[u]) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          float t[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) t[e] = dy[k * VEC + e];
+          stv(d_y + row * 128 + k * 8 * VEC + sub * VEC, t);
+        }
+      }
     }
   }
+  // fold the 4 row slots of the warp, then the 8 warps
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    sm[(wid * 3 + 0) * 128 + lane * 4 + k] = pg[k];
-    sm[(wid * 3 + 1) * 128 + lane * 4 + k] = pb[k];
-    sm[(wid * 3 + 2) * 128 + lane * 4 + k] = pbias[k];
+  for (int i = 0; i < 16; ++i) {
+    pg[i] += __shfl_xor_sync(0xffffffffu, pg[i], 8); pg[i] += __shfl_xor_sync(0xffffffffu, pg[i], 16);
+    pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], 8); pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], 16);
+    pbias[i] += __shfl_xor_sync(0xffffffffu, pbias[i], 8); pbias[i] += __shfl_xor_sync(0xffffffffu, pbias[i], 16);
+  }
+  if (slot == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int c = k * 8 * VEC + sub * VEC + e, i = k * VEC + e;
+        sm[(wid * 3 + 0) * 128 + c] = pg[i];
+        sm[(wid * 3 + 1) * 128 + c] = pb[i];
+        sm[(wid * 3 + 2) * 128 + c] = pbias[i];
+      }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
@@ -563,15 +698,19 @@ __global__ void __launch_bounds__(256) ln_pool_bwd128_kernel(
   }
 }
 
-int ln_pool_bwd(const float* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
-                float eps, float* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate, float* ws,
+int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
+                float eps, void* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate, float* ws, int dt,
                 cudaStream_t st) {
   ADVMIL_REQUIRE(d <= 256, "ln_pool_bwd: d %d > 256 unsupported", d);
+  ADVMIL_REQUIRE(dt == ELEM_F32 || d == 128, "ln_pool_bwd: the bf16 mode supports d == 128 only (d=%d)", d);
   int chunks = row_chunks(rows);
   size_t smem = (size_t)8 * 3 * d * sizeof(float);
-  if (d == 128) ln_pool_bwd128_kernel<<<chunks, 256, 0, st>>>(y_pre, d_emb, gamma, beta, rows, eps, d_y, ws);
-  else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>(y_pre, d_emb, gamma, beta, rows, d, eps, d_y, ws);
-  else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>(y_pre, d_emb, gamma, beta, rows, d, eps, d_y, ws);
+  if (d == 128 && dt == ELEM_BF16)
+    ln_pool_bwd128_kernel<bf16><<<chunks, 256, 0, st>>>((const bf16*)y_pre, d_emb, gamma, beta, rows, eps, (bf16*)d_y, ws);
+  else if (d == 128)
+    ln_pool_bwd128_kernel<float><<<chunks, 256, 0, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, eps, (float*)d_y, ws);
+  else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, d, eps, (float*)d_y, ws);
+  else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();
   reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
   ADVMIL_CHECK_LAUNCH();
@@ -583,26 +722,49 @@ int ln_pool_bwd(const float* y_pre, const float* d_emb, const float* gamma, cons
 }
 
 // =============================================================================================
-// column sums (bias gradients)
+// column sums (bias gradients): each thread owns 4 / sizeof(T) ... one 4-byte word of every row = 1 fp32 or 2 bf16 columns
 // =============================================================================================
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dY, int rows, int N, int ld,
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ dY, int rows, int N, int ld,
                                                              float* __restrict__ part) {
+  constexpr int CPT = 4 / (int)sizeof(T);
   int row0 = blockIdx.x * ROWS_PER_CTA;
   int nrows = min(ROWS_PER_CTA, rows - row0);
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    const float* p = dY + (size_t)row0 * ld + c;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int c = threadIdx.x * CPT; c < N; c += blockDim.x * CPT) {
+    const T* p = dY + (size_t)row0 * ld + c;
+    float a[4][CPT];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int e = 0; e < CPT; ++e) a[u][e] = 0.f;
     int r = 0;
     for (; r + 3 < nrows; r += 4) {
-      a0 += p[(size_t)r * ld]; a1 += p[(size_t)(r + 1) * ld]; a2 += p[(size_t)(r + 2) * ld]; a3 += p[(size_t)(r + 3) * ld];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float t[CPT];
+        ldw(p + (size_t)(r + u) * ld, t);
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) a[u][e] += t[e];
+      }
     }
-    for (; r < nrows; ++r) a0 += p[(size_t)r * ld];
-    part[(size_t)blockIdx.x * N + c] = (a0 + a1) + (a2 + a3);
+    for (; r < nrows; ++r) {
+      float t[CPT];
+      ldw(p + (size_t)r * ld, t);
+#pragma unroll
+      for (int e = 0; e < CPT; ++e) a[0][e] += t[e];
+    }
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) part[(size_t)blockIdx.x * N + c + e] = (a[0][e] + a[1][e]) + (a[2][e] + a[3][e]);
   }
 }
-int colsum(const float* dY, int rows, int N, int ld, float* out, int accumulate, float* ws, cudaStream_t st) {
+int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accumulate, float* ws, cudaStream_t st) {
   int chunks = row_chunks(rows);
-  colsum_partial_kernel<<<chunks, 256, 0, st>>>(dY, rows, N, ld, ws);
+  if (dt == ELEM_BF16) {
+    ADVMIL_REQUIRE(N % 2 == 0 && ld % 2 == 0, "colsum: bf16 needs even N (%d) and ld (%d)", N, ld);
+    colsum_partial_kernel<bf16><<<chunks, 256, 0, st>>>((const bf16*)dY, rows, N, ld, ws);
+  } else {
+    colsum_partial_kernel<float><<<chunks, 256, 0, st>>>((const float*)dY, rows, N, ld, ws);
+  }
   ADVMIL_CHECK_LAUNCH();
   return reduce_rows(ws, chunks, N, out, accumulate, st);
 }

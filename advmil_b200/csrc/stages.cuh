@@ -5,26 +5,29 @@
 namespace advmil {
 
 // ---- gemm_stages.cu ---------------------------------------------------------------------------
-int linear_fwd(const float* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-               float* y, int precision, cudaStream_t st);
+// Activation tensors ([rows, *]: x, y, v, ab, y_pre, dY, dX, X, relu_src) are `const void*` / `void*`: bf16 when
+// precision == ADVMIL_BF16 (or dt == ELEM_BF16), fp32 otherwise.  Weights, biases, statistics and outputs at bag / region
+// granularity are always fp32.
+int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
+               void* y, int precision, cudaStream_t st);
 // packed gate weights Wp [abw, L], bp [abw] (zero padded) must have been built by gate_pack_weights
-int gated_score_fwd(const float* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
-                    int D, const Drop& da, const Drop& db, float* ab, float* s, float* part_ws, int precision,
+int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
+                    int D, const Drop& da, const Drop& db, void* ab, float* s, float* part_ws, int precision,
                     cudaStream_t st);
-int region_embed_fwd(const float* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows,
-                     int C, int d, float eps, float* y_pre, float* emb, int precision, cudaStream_t st);
+int region_embed_fwd(const void* x, const float* Wc, const float* bc, const float* gamma, const float* beta, int rows,
+                     int C, int d, float eps, void* y_pre, float* emb, int precision, cudaStream_t st);
 // dX[rows,Nx] = (dY[rows,Ny] . W[Ny,Nx] + pool terms) * relu'  (W row-major [Ny, Nx])
 struct BwdDataExtras {
   const float* w = nullptr; const float* dz = nullptr; const float* dmean = nullptr;
   const int32_t* offsets = nullptr; int bags = 0;
-  const float* relu_src = nullptr; int ld_src = 0; float inv_keep = 1.f;
+  const void* relu_src = nullptr; int ld_src = 0; float inv_keep = 1.f;
   int accumulate = 0;
 };
-int bwd_data(const float* dY, const float* W, int rows, int Ny, int Nx, float* dX, const BwdDataExtras& ex,
+int bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX, const BwdDataExtras& ex,
              int precision, cudaStream_t st);
 // dW[N1,N2] (+)= dY[rows,N1]^T . X[rows,N2]   (split-K over rows; ws >= bwd_weight_ws_floats floats)
 size_t bwd_weight_ws_floats(int rows, int N1, int N2);
-int bwd_weight(const float* dY, const float* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
+int bwd_weight(const void* dY, const void* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
                int precision, cudaStream_t st);
 
 // ---- seg_kernels.cu ---------------------------------------------------------------------------
@@ -34,28 +37,29 @@ int gate_unpack_grads(const float* dWp, const float* dbp, int L, int D, float* d
                       int accumulate, cudaStream_t st);
 int gate_score_finish(const float* part, int ntiles, int rows, const float* bc, float* s, cudaStream_t st);
 size_t seg_pool_ws_floats(int rows, int bags, int width);
-int seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets, const int32_t* offsets_host, int rows,
-                         int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st);
+int seg_softmax_pool_fwd(const float* s, const void* v, int dt, const int32_t* offsets, const int32_t* offsets_host,
+                         int rows, int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st);
 // rows_per_cta used by the row-chunked backward kernels (partials are [nchunks, ...])
 constexpr int ROWS_PER_CTA = 128;
 inline int row_chunks(int rows) { return cdiv(rows, ROWS_PER_CTA); }
 // pooling + gate backward: ds = w (dz.v - dz.z); dAB packed; partial dwc/dbc per chunk -> reduced into dwc, dbc
-int pool_gate_bwd(const float* v, const float* w, const float* z, const float* dz, const float* ab, const float* wc,
-                  const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, float* dAB,
+int pool_gate_bwd(const void* v, const float* w, const float* z, const float* dz, const void* ab, const float* wc,
+                  const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, void* dAB,
                   float* dwc, float* dbc, float* dbp /* packed gate-bias grad [abw] or null */, int accumulate,
-                  float* ws /* >= pool_gate_ws_floats */, cudaStream_t st);
+                  float* ws /* >= pool_gate_ws_floats */, int dt, cudaStream_t st);
 inline size_t pool_gate_ws_floats(int rows, int bags, int D) {
   return align_up((size_t)bags, 64) + align_up((size_t)row_chunks(rows) * (D + 1), 64) + (size_t)row_chunks(rows) * gate_width(D) + 64;
 }
 // LayerNorm + ReLU + region-mean backward per row; partials of dgamma/dbeta/dbias reduced into the outputs
-int ln_pool_bwd(const float* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
-                float eps, float* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                float* ws /* >= row_chunks*3*d floats */, cudaStream_t st);
-int colsum(const float* dY, int rows, int N, int ld, float* out, int accumulate, float* ws /* >= row_chunks*N */,
+int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
+                float eps, void* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate,
+                float* ws /* >= row_chunks*3*d floats */, int dt, cudaStream_t st);
+int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accumulate, float* ws /* >= row_chunks*N */,
            cudaStream_t st);
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st);
-int apply_dropout(const float* src, int rows, int width, const Drop& drop, float* dst, cudaStream_t st);
+int apply_dropout(const void* src, int rows, int width, const Drop& drop, void* dst, int dt, cudaStream_t st);
 int fill_zero(float* p, size_t n, cudaStream_t st);
+int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st);
 
 // ---- tail_kernels.cu --------------------------------------------------------------------------
 int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, const float* noise1, int bags,

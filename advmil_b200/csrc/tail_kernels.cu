@@ -429,7 +429,8 @@ __global__ void abs_sum_kernel(const float* __restrict__ p, int64_t n, float* __
 // K9: DeepAttMISL cluster pooling (model/backbone.py:105-117): per (bag, cluster) mean of rows
 // =============================================================================================
 constexpr int CL_CH = 128;
-__global__ void __launch_bounds__(256) seg_mean_id_partial_kernel(const float* __restrict__ v,
+template <typename T>
+__global__ void __launch_bounds__(256) seg_mean_id_partial_kernel(const T* __restrict__ v,
                                                                   const int32_t* __restrict__ cid,
                                                                   const int32_t* __restrict__ offsets, int width,
                                                                   int ncl, float* __restrict__ part,
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(256) seg_mean_id_partial_kernel(const float* _
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     for (int r = 0; r < nrows; ++r) {
       int k = cid_s[r];
-      if (k >= 0 && k < ncl) sm[k * width + c] += v[(size_t)(beg + r) * width + c];
+      if (k >= 0 && k < ncl) sm[k * width + c] += ld1(v + (size_t)(beg + r) * width + c);
     }
   }
   if (threadIdx.x == 0)
@@ -475,10 +476,11 @@ __global__ void seg_mean_id_final_kernel(const float* __restrict__ part, const i
   }
   if (threadIdx.x == 0) counts[b * ncl + k] = cnt;
 }
-__global__ void seg_mean_id_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ v,
+template <typename T>
+__global__ void seg_mean_id_bwd_kernel(const float* __restrict__ d_out, const T* __restrict__ v,
                                        const int32_t* __restrict__ cid, const int32_t* __restrict__ offsets,
                                        const int32_t* __restrict__ counts, int rows, int bags, int width, int ncl,
-                                       int relu_mask, float* __restrict__ d_v) {
+                                       int relu_mask, T* __restrict__ d_v) {
   int row = blockIdx.x;
   int b = bag_of_row(offsets, bags, row);
   int k = cid[row];
@@ -486,8 +488,8 @@ __global__ void seg_mean_id_bwd_kernel(const float* __restrict__ d_out, const fl
   float inv = ok ? 1.0f / (float)max(counts[b * ncl + k], 1) : 0.f;
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float g = ok ? d_out[((size_t)b * ncl + k) * width + c] * inv : 0.f;
-    if (relu_mask && !(v[(size_t)row * width + c] > 0.f)) g = 0.f;
-    d_v[(size_t)row * width + c] = g;
+    if (relu_mask && !(ld1(v + (size_t)row * width + c) > 0.f)) g = 0.f;
+    st1(d_v + (size_t)row * width + c, g);
   }
 }
 
@@ -564,7 +566,7 @@ extern "C" size_t advmil_segment_mean_workspace_bytes(int32_t rows, int32_t bags
   return align_up(nparts * num_clusters * width * sizeof(float), 256) + align_up(nparts * num_clusters * sizeof(int32_t), 256);
 }
 
-extern "C" int advmil_segment_mean_by_id_fwd(const float* v, const int32_t* cid, const int32_t* offsets,
+extern "C" int advmil_segment_mean_by_id_fwd(const void* v, int32_t elem, const int32_t* cid, const int32_t* offsets,
                                              const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width,
                                              int32_t num_clusters, float* out, int32_t* counts, void* workspace,
                                              size_t workspace_bytes, void* stream) {
@@ -580,21 +582,29 @@ extern "C" int advmil_segment_mean_by_id_fwd(const float* v, const int32_t* cid,
   for (int b = 0; b < bags; ++b) maxlen = max(maxlen, offsets_host[b + 1] - offsets_host[b]);
   int maxchunks = max(1, cdiv(maxlen, CL_CH));
   size_t smem = (size_t)num_clusters * width * sizeof(float);
-  if (smem > 48 * 1024)
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(seg_mean_id_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  seg_mean_id_partial_kernel<<<dim3(maxchunks, bags), 256, smem, st>>>(v, cid, offsets, width, num_clusters, part, part_cnt);
+  if (smem > 48 * 1024) {
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(seg_mean_id_partial_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(seg_mean_id_partial_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (elem == ELEM_BF16)
+    seg_mean_id_partial_kernel<bf16><<<dim3(maxchunks, bags), 256, smem, st>>>((const bf16*)v, cid, offsets, width, num_clusters, part, part_cnt);
+  else
+    seg_mean_id_partial_kernel<float><<<dim3(maxchunks, bags), 256, smem, st>>>((const float*)v, cid, offsets, width, num_clusters, part, part_cnt);
   ADVMIL_CHECK_LAUNCH();
   seg_mean_id_final_kernel<<<bags * num_clusters, 128, 0, st>>>(part, part_cnt, offsets, width, num_clusters, out, counts);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
-extern "C" int advmil_segment_mean_by_id_bwd(const float* d_out, const float* v, const int32_t* cid,
+extern "C" int advmil_segment_mean_by_id_bwd(const float* d_out, const void* v, int32_t elem, const int32_t* cid,
                                              const int32_t* offsets, const int32_t* counts, int32_t rows, int32_t bags,
-                                             int32_t width, int32_t num_clusters, int32_t relu_mask, float* d_v,
+                                             int32_t width, int32_t num_clusters, int32_t relu_mask, void* d_v,
                                              void* stream) {
   if (rows == 0) return ADVMIL_OK;
-  seg_mean_id_bwd_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, d_v);
+  if (elem == ELEM_BF16)
+    seg_mean_id_bwd_kernel<bf16><<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, (const bf16*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (bf16*)d_v);
+  else
+    seg_mean_id_bwd_kernel<float><<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, (const float*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (float*)d_v);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

@@ -24,7 +24,7 @@ from ..ops import PackedBags
 @dataclass
 class PinnedStep:
     """The bags of one optimiser step (`bp_every_batch` of them, config/cfg_nlst.yaml:71) in pinned host memory."""
-    x: torch.Tensor            # [rows, C] float32, pinned
+    x: torch.Tensor            # [rows, C] float32 (or bfloat16: the bf16 mode's storage format), pinned
     lengths: List[int]
     t: torch.Tensor            # [bags] float32, pinned
     e: torch.Tensor            # [bags] float32, pinned
@@ -34,7 +34,7 @@ class PinnedStep:
 
     @property
     def nbytes(self) -> int:
-        return self.x.numel() * 4 + (self.t.numel() + self.e.numel()) * 4 + self.visible.numel()
+        return self.x.numel() * self.x.element_size() + (self.t.numel() + self.e.numel()) * 4 + self.visible.numel()
 
 
 def _pin(t: torch.Tensor) -> torch.Tensor:
@@ -46,8 +46,11 @@ def _pin(t: torch.Tensor) -> torch.Tensor:
 
 def pack_step(bags: Sequence[torch.Tensor], labels: Sequence[Sequence[float]], idx: Optional[Sequence[int]] = None,
               visible: Optional[Sequence[bool]] = None, cluster_ids: Optional[Sequence[torch.Tensor]] = None,
-              require_multiple_of: int = 16, pin: bool = True) -> PinnedStep:
-    """Packs per-patient feature tensors ([N_i, C], as WSIPatch returns them after torch.cat, :79) into one buffer."""
+              require_multiple_of: int = 16, pin: bool = True, dtype: torch.dtype = torch.float32) -> PinnedStep:
+    """Packs per-patient feature tensors ([N_i, C], as WSIPatch returns them after torch.cat, :79) into one buffer.
+    dtype=torch.bfloat16 stores the features in the bf16 mode's format (rounded once, at packing time: half the host
+    memory and half the H2D bytes of every step)."""
+    assert dtype in (torch.float32, torch.bfloat16)
     assert len(bags) == len(labels) and len(bags) > 0
     lengths = [int(b.shape[0]) for b in bags]
     for i, n in enumerate(lengths):
@@ -57,13 +60,13 @@ def pack_step(bags: Sequence[torch.Tensor], labels: Sequence[Sequence[float]], i
                 f"bag {i} has {n} instances: the RLIP discriminator needs a multiple of 16 (model/backbone_utils.py:65)"
     C = int(bags[0].shape[1])
     rows = sum(lengths)
-    x = torch.empty(rows, C, dtype=torch.float32)
+    x = torch.empty(rows, C, dtype=dtype)
     if pin:
         x = _pin(x)
     off = 0
     for b in bags:
         assert b.shape[1] == C
-        x[off:off + b.shape[0]].copy_(b.to(torch.float32))     # dataset/PatchWSI.py:79 `.to(torch.float)`
+        x[off:off + b.shape[0]].copy_(b.to(torch.float32))     # dataset/PatchWSI.py:79 `.to(torch.float)` (+ rounding to dtype)
         off += b.shape[0]
     lab = torch.tensor(np.asarray(labels, dtype=np.float32).reshape(len(bags), 2))
     mk = (lambda v: _pin(v)) if pin else (lambda v: v)
@@ -134,8 +137,8 @@ class DeviceFeeder:
     def _issue(self, slot: int, st: PinnedStep) -> DeviceStep:
         rows, C = st.x.shape
         buf = self._xbuf[slot]
-        if buf is None or buf.shape[0] < rows or buf.shape[1] != C:
-            buf = torch.empty(rows, C, dtype=torch.float32, device=self.device)
+        if buf is None or buf.shape[0] < rows or buf.shape[1] != C or buf.dtype != st.x.dtype:
+            buf = torch.empty(rows, C, dtype=st.x.dtype, device=self.device)
             self._xbuf[slot] = buf
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._free[slot])          # consumer finished with this slot
@@ -178,7 +181,8 @@ class DeviceFeeder:
 
 
 def synthetic_steps(n_steps: int, bags_per_step: int, rows_per_bag, C: int = 1024, seed: int = 42, pin: bool = True,
-                    event_rate: float = 0.347, labeled_ratio: float = 1.0, distinct: Optional[int] = None) -> List[PinnedStep]:
+                    event_rate: float = 0.347, labeled_ratio: float = 1.0, distinct: Optional[int] = None,
+                    dtype: torch.dtype = torch.float32) -> List[PinnedStep]:
     """Synthetic NLST-shaped steps: randn features (model_stats.py:93), t~U(0,1), e~Bernoulli(0.347).
     rows_per_bag: int or callable(rng) -> int (multiple of 16).  `distinct` < n_steps re-uses buffers cyclically so a long
     run does not need n_steps GiB of host memory."""
@@ -191,7 +195,7 @@ def synthetic_steps(n_steps: int, bags_per_step: int, rows_per_bag, C: int = 102
         bags = [torch.randn(n, C, generator=g) for n in lens]
         labels = [(float(rng.uniform(0.02, 0.98)), float(rng.uniform() < event_rate)) for _ in lens]
         vis = [bool(rng.uniform() < labeled_ratio) for _ in lens]
-        made.append(pack_step(bags, labels, visible=vis, pin=pin))
+        made.append(pack_step(bags, labels, visible=vis, pin=pin, dtype=dtype))
     return [made[i % distinct] for i in range(n_steps)]
 
 

@@ -57,19 +57,20 @@ class Generator(nn.Module):
         """x [1,N,C]; x_ext ignored for ABMIL, cluster ids for DeepAttMISL -> [1,1]."""
         if self.backbone.kind == "cluster":
             hc = self.backbone.cluster_rows(x, x_ext)
-            bags, xg = ops.PackedBags(hc, [self.backbone.num_clusters]), hc
-        else:
-            bags, xg = ops.PackedBags.from_single(x), None
-        return self.forward_packed(bags, zero_noise=zero_noise, x_grad=xg)
+            # the attention stage sees num_clusters rows per bag: always the exact fp32 engine
+            return self.forward_packed(ops.PackedBags(hc, [self.backbone.num_clusters]), zero_noise=zero_noise, x_grad=hc,
+                                       precision=ops.FP32)
+        return self.forward_packed(ops.PackedBags.from_single(x), zero_noise=zero_noise)
 
     def forward_packed(self, bags: ops.PackedBags, noise: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                       zero_noise: bool = False, x_grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       zero_noise: bool = False, x_grad: Optional[torch.Tensor] = None,
+                       precision: Optional[int] = None) -> torch.Tensor:
         """Packed bags -> [bags, 1]."""
+        precision = ops.PRECISIONS[get_precision()] if precision is None else precision
         n0, n1 = noise if noise is not None else self.draw_noise(bags.bags, bags.x.device, zero_noise)
         train = self.training
         pred = ops.GeneratorFn.apply(self.config(), bags, x_grad, n0, n1, train, next_dropout_seed() if train else 0,
-                                     getattr(self, "_inject_masks", None), ops.PRECISIONS[get_precision()],
-                                     *self.gen_params())
+                                     getattr(self, "_inject_masks", None), precision, *self.gen_params())
         return pred.unsqueeze(-1)
 
 

@@ -125,7 +125,7 @@ class DeepAttMISL(_GatedMILBase):
         bags = ops.PackedBags(hc, [self.num_clusters])
         H = ops.GeneratorFn.apply(self.config(), bags, hc, None, None, self.training,
                                   next_dropout_seed() if self.training else 0, getattr(self, "_inject_masks", None),
-                                  ops.PRECISIONS[get_precision()], *self.gen_params())
+                                  ops.FP32, *self.gen_params())   # num_clusters rows: always the exact fp32 engine
         return H
 
 
@@ -137,15 +137,16 @@ class ClusterPoolFn(torch.autograd.Function):
         import ctypes as C
         from .. import _lib
         lib = _lib.load()
-        bags = ops.PackedBags(x.detach(), lengths)
+        bags = ops.PackedBags(x.detach(), lengths).for_precision(precision)
         hx = ops.linear_forward(bags.x, W.detach(), b.detach(), act=1, precision=precision)
+        elem = ops.ELEM_BF16 if hx.dtype == torch.bfloat16 else ops.ELEM_F32
         h = W.shape[0]
         out = torch.empty(bags.bags * ncl, h, dtype=torch.float32, device=x.device)
         counts = torch.empty(bags.bags * ncl, dtype=torch.int32, device=x.device)
         cid = cid.contiguous()
         wsb = lib.advmil_segment_mean_workspace_bytes(bags.rows, bags.bags, h, ncl)
         ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=x.device)
-        _lib.check(lib.advmil_segment_mean_by_id_fwd(hx.data_ptr(), cid.data_ptr(), bags.offsets.data_ptr(), bags.offsets_host,
+        _lib.check(lib.advmil_segment_mean_by_id_fwd(hx.data_ptr(), elem, cid.data_ptr(), bags.offsets.data_ptr(), bags.offsets_host,
                                                      bags.rows, bags.bags, h, ncl, out.data_ptr(), counts.data_ptr(),
                                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
                    "advmil_segment_mean_by_id_fwd")
@@ -159,8 +160,9 @@ class ClusterPoolFn(torch.autograd.Function):
         bags, hx, cid, counts, W, ncl, precision = ctx.saved
         h = W.shape[0]
         d_hx = torch.empty_like(hx)
-        d_out = d_out.contiguous()
-        _lib.check(lib.advmil_segment_mean_by_id_bwd(d_out.data_ptr(), hx.data_ptr(), cid.data_ptr(), bags.offsets.data_ptr(),
+        d_out = d_out.contiguous().float()
+        elem = ops.ELEM_BF16 if hx.dtype == torch.bfloat16 else ops.ELEM_F32
+        _lib.check(lib.advmil_segment_mean_by_id_bwd(d_out.data_ptr(), hx.data_ptr(), elem, cid.data_ptr(), bags.offsets.data_ptr(),
                                                      counts.data_ptr(), bags.rows, bags.bags, h, ncl, 1, d_hx.data_ptr(),
                                                      torch.cuda.current_stream().cuda_stream), "advmil_segment_mean_by_id_bwd")
         _, dW, db = ops.linear_backward(d_hx, bags.x, W.detach(), need_dx=False, precision=precision)

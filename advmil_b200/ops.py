@@ -16,8 +16,14 @@ from . import _lib
 from ._lib import (Bags, DiscGrads, DiscParams, EmbedActs, GenActs, GenGrads, GenParams, HeadActs, DISC_TENSORS,
                    GEN_TENSORS, check)
 
-FP32, TF32, TF32X3 = 0, 1, 2
-PRECISIONS = {"fp32": FP32, "tf32": TF32, "tf32x3": TF32X3}
+FP32, TF32, TF32X3, BF16 = 0, 1, 2, 3
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "tf32x3": TF32X3, "bf16": BF16}
+ELEM_F32, ELEM_BF16 = 0, 1
+
+
+def act_dtype(precision: int) -> torch.dtype:
+    """Element type of the [rows, *] activation tensors (and of x) in a precision mode."""
+    return torch.bfloat16 if int(precision) == BF16 else torch.float32
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -39,13 +45,41 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy of a CUDA tensor with the library's own kernel (advmil_cast_f32_to_bf16)."""
+    lib = _lib.load()
+    _need_cuda(x, "x")
+    x = _f32c(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib.advmil_cast_f32_to_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "advmil_cast_f32_to_bf16")
+    return out
+
+
+_CAST_CACHE: list = []   # [(data_ptr, version, shape, bf16 copy)], newest last
+
+
+def _cached_cast(x: torch.Tensor) -> torch.Tensor:
+    """The drop-in modules are called several times per bag with the same feature tensor (G and D, D step and G step,
+    model/model_handler.py:383-461): keep the last two bf16 copies keyed on (pointer, version, shape)."""
+    key = (x.data_ptr(), x._version, tuple(x.shape))
+    for k in _CAST_CACHE:
+        if k[:3] == key:
+            return k[3]
+    y = cast_bf16(x)
+    _CAST_CACHE.append(key + (y, x))   # holding x keeps its address from being recycled while the entry lives
+    if len(_CAST_CACHE) > 2:
+        _CAST_CACHE.pop(0)
+    return y
+
+
 class PackedBags:
-    """Packed variable-length bags: x [rows, C] fp32 + int32 offsets [bags+1] (AdvmilBags)."""
+    """Packed variable-length bags: x [rows, C] fp32 (or bf16 for the bf16 mode) + int32 offsets [bags+1] (AdvmilBags)."""
 
     def __init__(self, x: torch.Tensor, lengths: Sequence[int]):
         _need_cuda(x, "bag features")
         assert x.dim() == 2, "packed features must be [rows, C]"
-        self.x = _f32c(x)
+        self.x = (x if x.is_contiguous() else x.contiguous()) if x.dtype == torch.bfloat16 else _f32c(x)
+        self._alt = None
         self.lengths = [int(n) for n in lengths]
         assert sum(self.lengths) == self.x.shape[0], "bag lengths do not sum to the number of rows"
         offs = [0]
@@ -70,9 +104,29 @@ class PackedBags:
         xs = [x[0] if x.dim() == 3 else x for x in xs]
         return PackedBags(torch.cat(xs, dim=0) if len(xs) > 1 else xs[0], [x.shape[0] for x in xs])
 
+    @property
+    def elem(self) -> int:
+        return ELEM_BF16 if self.x.dtype == torch.bfloat16 else ELEM_F32
+
+    def for_precision(self, precision: int) -> "PackedBags":
+        """The same bags with x in the element type the precision mode computes on.  fp32 -> bf16 runs the library's cast
+        kernel once and is cached; bf16 features cannot be widened back (load fp32 features for the fp32/tf32 modes)."""
+        want = act_dtype(precision)
+        if self.x.dtype == want:
+            return self
+        if want != torch.bfloat16:
+            raise _lib.AdvmilError("bf16 bag features can only be used with the bf16 precision mode")
+        if self._alt is None:
+            alt = PackedBags.__new__(PackedBags)
+            alt.__dict__.update(self.__dict__)
+            alt.x = _cached_cast(self.x)
+            alt._alt = None
+            self._alt = alt
+        return self._alt
+
     def c(self) -> Bags:
         return Bags(self.x.data_ptr(), self.offsets.data_ptr(), self.offsets_host, self.rows, self.bags, self.C,
-                    max(self.lengths))
+                    max(self.lengths), self.elem)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -111,15 +165,19 @@ def generator_forward(cfg: GenConfig, params: Sequence[Optional[torch.Tensor]], 
                       save: bool = True, h_eval: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """K1+K2+K3+K4 over packed bags.  Returns the activation dict (also what backward needs)."""
     lib = _lib.load()
+    bags = bags.for_precision(precision)
     dev = bags.x.device
     rows, nb = bags.rows, bags.bags
     abw = lib.advmil_gate_packed_width(cfg.h)
     f = dict(dtype=torch.float32, device=dev)
+    fa = dict(dtype=act_dtype(precision), device=dev)
+    if h_eval is not None:
+        assert h_eval.dtype == fa["dtype"], "h_eval must come from a forward in the same precision mode"
     acts = {
-        "h": torch.empty(rows, cfg.h, **f), "s": torch.empty(rows, **f), "w": torch.empty(rows, **f),
+        "h": torch.empty(rows, cfg.h, **fa), "s": torch.empty(rows, **f), "w": torch.empty(rows, **f),
         "z": torch.empty(nb, cfg.h, **f), "H": torch.empty(nb, cfg.o, **f), "H1": torch.empty(nb, max(cfg.hid, 1), **f),
         "pre": torch.empty(nb, **f), "pred": torch.empty(nb, **f),
-        "ab": torch.empty(rows, abw, **f) if save else None,
+        "ab": torch.empty(rows, abw, **fa) if save else None,
         "noise0": None if noise0 is None else _f32c(noise0), "noise1": None if noise1 is None else _f32c(noise1),
         "h_eval": h_eval, "masks": masks or {}, "seed": int(seed), "train": bool(train), "precision": int(precision),
     }
@@ -146,9 +204,12 @@ def _gen_acts_struct(acts, ws) -> GenActs:
 def generator_backward(cfg: GenConfig, params, bags: PackedBags, acts, d_pred: torch.Tensor, need_dx: bool = False):
     """Returns (list of 14 parameter gradients, dx or None).  d_pred: [bags] (or dL/dH [bags,o] in backbone-only mode)."""
     lib = _lib.load()
+    bags = bags.for_precision(acts["precision"])
     dev = bags.x.device
     p = cfg.c(params)
     grads = [None if t is None else torch.empty_like(t, dtype=torch.float32) for t in params]
+    if need_dx and acts["precision"] == BF16:
+        raise _lib.AdvmilError("gradients w.r.t. the bag features are not available in the bf16 mode")
     dx = torch.empty_like(bags.x) if need_dx else None
     g = GenGrads()
     for name, t in zip(GEN_TENSORS, grads):
@@ -223,11 +284,12 @@ class DiscConfig:
 
 def disc_embed_forward(cfg: DiscConfig, params, bags: PackedBags, precision: int = FP32, save: bool = True):
     lib = _lib.load()
+    bags = bags.for_precision(precision)
     dev = bags.x.device
     assert bags.rows % 16 == 0 and all(n % 16 == 0 for n in bags.lengths), \
         "every bag must hold a multiple of 16 instances (model/backbone_utils.py:65)"
     acts = {"emb": torch.empty(bags.rows // 16, cfg.d, dtype=torch.float32, device=dev),
-            "y_pre": torch.empty(bags.rows, cfg.d, dtype=torch.float32, device=dev) if save else None,
+            "y_pre": torch.empty(bags.rows, cfg.d, dtype=act_dtype(precision), device=dev) if save else None,
             "precision": int(precision)}
     p = cfg.c(params)
     a = EmbedActs(acts["emb"].data_ptr(), _ptr(acts["y_pre"]), int(precision), None, 0)
@@ -238,6 +300,7 @@ def disc_embed_forward(cfg: DiscConfig, params, bags: PackedBags, precision: int
 
 def disc_embed_backward(cfg: DiscConfig, params, bags: PackedBags, acts, d_emb: torch.Tensor, grads, accumulate=False):
     lib = _lib.load()
+    bags = bags.for_precision(acts["precision"])
     p = cfg.c(params)
     ws = _ws(lib.advmil_disc_workspace_bytes(C.byref(p), bags.rows, bags.bags, 1), bags.x.device)
     a = EmbedActs(acts["emb"].data_ptr(), _ptr(acts["y_pre"]), acts["precision"], ws.data_ptr(), ws.numel())
@@ -332,13 +395,21 @@ class DiscriminatorFn(torch.autograd.Function):
 # -------------------------------------------------------------------------------------------------
 # small stage-level wrappers (used by the DeepAttMISL path, the loader tools and the kernel tests)
 # -------------------------------------------------------------------------------------------------
+def _act_in(t: torch.Tensor, precision: int) -> torch.Tensor:
+    """Activation operand in the element type of the precision mode (fp32 inputs are cast for the bf16 mode)."""
+    want = act_dtype(precision)
+    if t.dtype != want:
+        t = cast_bf16(t) if want == torch.bfloat16 else t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def linear_forward(x, W, b, act=0, p_drop=0.0, mask=None, seed=0, site=0, train=False, precision=FP32):
     lib = _lib.load()
     _need_cuda(x, "x")
-    x, W = _f32c(x), _f32c(W)
+    x, W = _act_in(x, precision), _f32c(W)
     rows, K = x.shape
     N = W.shape[0]
-    y = torch.empty(rows, N, dtype=torch.float32, device=x.device)
+    y = torch.empty(rows, N, dtype=act_dtype(precision), device=x.device)
     check(lib.advmil_linear_fwd(x.data_ptr(), W.data_ptr(), _ptr(b), rows, K, N, act, p_drop, _ptr(mask), seed, site,
                                 int(train), precision, y.data_ptr(), _stream()), "advmil_linear_fwd")
     return y
@@ -346,11 +417,12 @@ def linear_forward(x, W, b, act=0, p_drop=0.0, mask=None, seed=0, site=0, train=
 
 def linear_backward(dY, X, W, need_dx=True, need_dw=True, need_db=True, precision=FP32):
     lib = _lib.load()
-    dY = _f32c(dY)
+    dY = _act_in(dY, precision)
+    X = None if X is None else _act_in(X, precision)
     rows, N = dY.shape
     K = W.shape[1]
     dev = dY.device
-    dX = torch.empty(rows, K, dtype=torch.float32, device=dev) if need_dx else None
+    dX = torch.empty(rows, K, dtype=act_dtype(precision), device=dev) if need_dx else None
     dW = torch.empty(N, K, dtype=torch.float32, device=dev) if need_dw else None
     db = torch.empty(N, dtype=torch.float32, device=dev) if need_db else None
     ws = _ws(lib.advmil_linear_bwd_workspace_bytes(rows, K, N), dev)
@@ -362,11 +434,11 @@ def linear_backward(dY, X, W, need_dx=True, need_dw=True, need_db=True, precisio
 def gated_score_forward(v, Wa, ba, Wb, bb, wc, bc, p_drop=0.0, mask_a=None, mask_b=None, seed=0, train=False,
                         precision=FP32, save=True):
     lib = _lib.load()
-    v = _f32c(v)
+    v = _act_in(v, precision)
     rows, L = v.shape
     D = Wa.shape[0]
     abw = lib.advmil_gate_packed_width(D)
-    ab = torch.empty(rows, abw, dtype=torch.float32, device=v.device) if save else None
+    ab = torch.empty(rows, abw, dtype=act_dtype(precision), device=v.device) if save else None
     s = torch.empty(rows, dtype=torch.float32, device=v.device)
     ws = _ws((abw * L + abw + (abw // 128) * rows + 1024) * 4 + 4096, v.device)
     check(lib.advmil_gated_score_fwd(v.data_ptr(), Wa.data_ptr(), ba.data_ptr(), Wb.data_ptr(), bb.data_ptr(),
@@ -377,9 +449,9 @@ def gated_score_forward(v, Wa, ba, Wb, bb, wc, bc, p_drop=0.0, mask_a=None, mask
 
 
 def seg_softmax_pool(s, v, bags_like: PackedBags, offsets=None, offsets_host=None, lengths=None, want_mean=False):
-    """w = per-bag softmax(s), z[b] = sum_n w_n v_n (and the plain per-bag mean when want_mean)."""
+    """w = per-bag softmax(s), z[b] = sum_n w_n v_n (and the plain per-bag mean when want_mean).  v: fp32 or bf16."""
     lib = _lib.load()
-    v = _f32c(v)
+    v = v.contiguous() if v.dtype == torch.bfloat16 else _f32c(v)
     rows, width = v.shape
     if offsets is None:
         offsets, offsets_host, nb = bags_like.offsets, bags_like.offsets_host, bags_like.bags
@@ -389,9 +461,9 @@ def seg_softmax_pool(s, v, bags_like: PackedBags, offsets=None, offsets_host=Non
     z = torch.empty(nb, width, dtype=torch.float32, device=v.device)
     mean = torch.empty(nb, width, dtype=torch.float32, device=v.device) if want_mean else None
     ws = _ws(lib.advmil_seg_pool_workspace_bytes(rows, nb, width), v.device)
-    check(lib.advmil_seg_softmax_pool_fwd(_f32c(s).data_ptr(), v.data_ptr(), offsets.data_ptr(), offsets_host, rows, nb,
-                                          width, w.data_ptr(), z.data_ptr(), _ptr(mean), ws.data_ptr(), ws.numel(),
-                                          _stream()), "advmil_seg_softmax_pool_fwd")
+    check(lib.advmil_seg_softmax_pool_fwd(_f32c(s).data_ptr(), v.data_ptr(), ELEM_BF16 if v.dtype == torch.bfloat16 else ELEM_F32,
+                                          offsets.data_ptr(), offsets_host, rows, nb, width, w.data_ptr(), z.data_ptr(),
+                                          _ptr(mean), ws.data_ptr(), ws.numel(), _stream()), "advmil_seg_softmax_pool_fwd")
     return w, z, mean
 
 

@@ -101,6 +101,7 @@ class AdvStep:
         (drawn like utils/func.generate_noise when None).  Returns device tensors only (no host sync)."""
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
+        bags = bags.for_precision(self.precision)   # bf16 mode: bf16 features as packed by the loader, or one cast here
         dev = bags.x.device
         nb = bags.bags
         G, D = self.netG, self.netD
@@ -201,6 +202,7 @@ def sample_inference(netG, netD, bags: ops.PackedBags, times_test_sample: int = 
     y_hat [bags,1] with its own noise draw, f_fake = D(x, y_hat) [bags,1], dist_y_hat [bags,S,1] from S more draws,
     avg_y_hat = lower median over the S draws (torch.median semantics)."""
     cfg, params = netG.config(), netG.gen_params()
+    bags = bags.for_precision(ops.PRECISIONS[precision])
     nb, dev = bags.bags, bags.x.device
     n0, n1 = netG.draw_noise(nb, dev, zero_noise)
     acts = ops.generator_forward(cfg, params, bags, n0, n1, train=False, precision=ops.PRECISIONS[precision], save=False)

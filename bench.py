@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bags/sec of one full adversarial G+D train step (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|tf32|tf32x3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|tf32|fp32] [--impl reference]
 
 Workload (BASELINE.json configs[1]): AdvMIL-ABMIL, synthetic bags of 16,384 x 1024 fp32 features, 16 bags per optimiser
 step and per GPU (bp_every_batch, config/cfg_nlst.yaml:71) = 1 GiB of features per step per GPU (>> 126 MB L2, so no
@@ -34,10 +34,12 @@ FLOP_PER_ROW = {  # algorithmic FLOPs per instance row per launch (SURVEY.md §8
     "proj_fwd": 2 * 1024 * 384, "gate_fwd": 2 * 384 * 768 + 768, "embed_fwd": 2 * 1024 * 128,
     "bwd_data": 2 * 768 * 384, "bwd_w_gate": 2 * 768 * 384, "bwd_w_proj": 2 * 384 * 1024, "bwd_w_embed": 2 * 128 * 1024,
 }
-BYTES_PER_ROW = {  # algorithmic HBM bytes per instance row per launch for the streaming kernels
-    "pool_fwd": 384 * 4 + 8, "pool_gate_bwd": 384 * 4 + 2 * 768 * 4 + 8, "ln_bwd": 2 * 128 * 4 + 32, "colsum": 576 * 4,
-    "dropout": 2 * 384 * 4,
-}
+def bytes_per_row(es):
+    """Algorithmic HBM bytes per instance row per launch for the streaming kernels; es = bytes per activation element
+    (4 in the fp32/tf32 modes, 2 in the bf16 mode).  pool: read h + s, write w; pool_gate_bwd: read h, ab, write dAB;
+    ln_bwd: read y_pre, write dy (+ d_emb/16); colsum: read dh; dropout: read h_eval, write h."""
+    return {"pool_fwd": 384 * es + 8, "pool_gate_bwd": 384 * es + 2 * 768 * es + 8, "ln_bwd": 2 * 128 * es + 32,
+            "colsum": 384 * es, "dropout": 2 * 384 * es}
 
 
 def load_peaks():
@@ -48,8 +50,63 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
 
 
+class NvmlSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML every 10 ms while the timed region runs (the recipe's clocks line,
+    B200_PROFILING.md; nvidia-smi's own start-up is longer than a short timed region)."""
+
+    def __init__(self, gpu_index=0, period=0.01):
+        super().__init__(daemon=True)
+        self.gpu, self.period, self.rows, self._stop_evt, self.ok = gpu_index, period, [], threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if gpu_index < len(ids) and ids[gpu_index].strip().isdigit():
+                    idx = int(ids[gpu_index])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.ok or not self.rows:
+            return None
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80}
+        seen = set()
+        for _, r in self.rows:
+            for name, b in bits.items():
+                if r & b:
+                    seen.add(name)
+        return {"sm_mhz": float(np.median([m for m, _ in self.rows])), "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
+                "samples": len(self.rows), "source": "nvml"}
+
+
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+    """Fallback: samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -134,10 +191,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="advmil_b200")
-    ap.add_argument("--precision", default=os.environ.get("ADVMIL_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("ADVMIL_PRECISION", "bf16"), choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--bags", type=int, default=BAGS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -164,14 +221,17 @@ def main():
     lib = _lib.load()
     advmil_b200.set_precision(args.precision)
     torch.manual_seed(42)
-    G, D = build_G(device=dev), build_D(device=dev)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):              # the modules print the reference's [info] lines
+        G, D = build_G(device=dev), build_D(device=dev)
     from advmil_b200.model.model_utils import init_weights
     G.apply(init_weights)                                     # model_handler.py:81
     engine = AdvStep(G, D, precision=args.precision)
 
     # ---- synthetic bags in pinned host memory: 2 distinct steps (2 GiB) cycled ----
     n_total = args.warmup + args.steps
-    steps = synthetic_steps(n_total, args.bags, args.rows, C_IN, seed=42 + rank, distinct=2)
+    feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32     # the packed loader's storage format
+    steps = synthetic_steps(n_total, args.bags, args.rows, C_IN, seed=42 + rank, distinct=2, dtype=feat_dtype)
     counts = None  # global pair counts come from a tiny all-reduce inside step()
 
     def barrier():
@@ -196,9 +256,12 @@ def main():
     barrier()
     lib.advmil_launch_count(1)
     lib.advmil_profile_enable(1)
-    sampler = ClockSampler(local_rank)
+    sampler = NvmlSampler(local_rank)
+    if not sampler.ok:
+        sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.05)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
@@ -248,6 +311,7 @@ def main():
     # ================= roofline of the dominant kernel class =================
     peaks = load_peaks()
     rows_per_launch = args.rows * args.bags
+    BYTES_PER_ROW = bytes_per_row(2 if args.precision == "bf16" else 4)
     kern = {}
     for i, tag in enumerate(_lib.PROF_TAGS):
         if pcnt[i] == 0:
@@ -287,10 +351,14 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"AdvMIL-ABMIL G+D step, {args.bags} synthetic bags of {args.rows}x1024 fp32 per step per GPU "
+            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "config": {"workload": f"AdvMIL-ABMIL G+D step, {args.bags} synthetic bags of {args.rows}x1024 per step per GPU "
                                    "(configs[1]); D step + G step + both Adam updates",
-                       "precision_mode": args.precision, "l2": "inputs (1 GiB/step) larger than L2; no flush",
+                       "precision_mode": args.precision,
+                       "feature_format": ("bf16 (packed loader's bf16 storage: features rounded once at packing time, fp32 "
+                                          "accumulation/statistics/parameters)" if args.precision == "bf16" else "fp32"),
+                       "l2": f"inputs ({steps[0].x.numel() * steps[0].x.element_size() >> 20} MiB/step, two alternating "
+                             "steps) larger than the 126 MB L2; no flush",
                        "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,

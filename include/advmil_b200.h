@@ -36,7 +36,7 @@ typedef enum AdvmilStatus {
   ADVMIL_ERR_NO_DEVICE = 4  /* no sm_100 device */
 } AdvmilStatus;
 
-#define ADVMIL_ABI_VERSION 1
+#define ADVMIL_ABI_VERSION 2
 #if defined(__GNUC__)
 #define ADVMIL_API __attribute__((visibility("default")))
 #else
@@ -46,15 +46,21 @@ typedef enum AdvmilStatus {
 /* GEMM engine selection for the N-row contractions (K1/K2/K5 and their backward):
  *   0 = fp32 FFMA tiles (exact-fp32 mode, rtol 1e-5 parity)
  *   1 = tcgen05 kind::tf32 single pass, TMA-fed, TMEM accumulators (fast mode, <= 2e-2 parity)
- *   2 = tcgen05 3xTF32 error-compensated (fp32-grade accuracy on tensor cores)                  */
-typedef enum AdvmilPrecision { ADVMIL_FP32 = 0, ADVMIL_TF32 = 1, ADVMIL_TF32X3 = 2 } AdvmilPrecision;
+ *   2 = reserved (3xTF32); currently served by mode 1
+ *   3 = bf16 storage mode: x and every [rows, *] activation tensor that crosses the ABI (h, ab, h_eval, y_pre; and the
+ *       library's own dAB / dh / dy scratch) are bfloat16, tcgen05 kind::f16 with fp32 accumulation in TMEM; all
+ *       statistics, region/bag-level tensors, parameters, gradients and optimiser state stay fp32 (<= 2e-2 parity).
+ * Pointers documented as "T" below are float in modes 0-2 and bfloat16 (2-byte) in mode 3.                    */
+typedef enum AdvmilPrecision { ADVMIL_FP32 = 0, ADVMIL_TF32 = 1, ADVMIL_TF32X3 = 2, ADVMIL_BF16 = 3 } AdvmilPrecision;
+typedef enum AdvmilElem { ADVMIL_ELEM_F32 = 0, ADVMIL_ELEM_BF16 = 1 } AdvmilElem;
 
 /* ---- packed bags ------------------------------------------------------------------------- */
 typedef struct AdvmilBags {
-  const float* x;              /* [rows, C] device */
+  const void* x;               /* [rows, C] device, element type `elem` */
   const int32_t* offsets;      /* [bags+1] device */
   const int32_t* offsets_host; /* [bags+1] host copy (grid sizing, validation) */
   int32_t rows, bags, C, max_bag_rows;
+  int32_t elem;                /* AdvmilElem of x: must be BF16 with precision ADVMIL_BF16 and F32 otherwise */
 } AdvmilBags;
 
 /* ---- generator: ABMIL encoder + noise head (model/GANSurv.py:13-49, model/backbone.py:54-86,
@@ -80,8 +86,8 @@ typedef struct AdvmilGenGrads { /* same tensors as AdvmilGenParams, written (not
 } AdvmilGenGrads;
 
 typedef struct AdvmilGenActs {
-  float* h;     /* [rows,h]   relu(+dropout) of the projection; pooled tensor (backbone.py:81-84) */
-  float* ab;    /* [rows,abw] tanh|sigmoid gate activations, packed column order (see advmil_gate_packed_width); NULL = not saved */
+  void* h;      /* T [rows,h]   relu(+dropout) of the projection; pooled tensor (backbone.py:81-84) */
+  void* ab;     /* T [rows,abw] tanh|sigmoid gate activations, packed column order (see advmil_gate_packed_width); NULL = not saved */
   float* s;     /* [rows] attention logits */
   float* w;     /* [rows] softmax weights within each bag */
   float* z;     /* [bags,h] pooled */
@@ -91,7 +97,7 @@ typedef struct AdvmilGenActs {
   float* pred;  /* [bags] output */
   const float* noise0; /* [bags,o]   or NULL (zero / unused) */
   const float* noise1; /* [bags,hid] or NULL */
-  const float* h_eval; /* optional [rows,h]: eval-mode h of the same x and W1 (dropout is applied to it instead of recomputing K1) */
+  const void* h_eval;  /* optional T [rows,h]: eval-mode h of the same x and W1 (dropout is applied to it instead of recomputing K1) */
   const uint8_t *mask_h, *mask_a, *mask_b, *mask_rho, *mask_mlp0; /* optional injected keep masks */
   uint64_t seed;
   int32_t train;       /* 0 eval (no dropout), 1 train */
@@ -128,7 +134,7 @@ typedef struct AdvmilDiscGrads {
 
 typedef struct AdvmilEmbedActs {      /* K5+K6: region embedding */
   float* emb;    /* [rows/16, d] */
-  float* y_pre;  /* [rows, d] pre-LayerNorm projection, NULL = not saved (no D-param backward) */
+  void* y_pre;   /* T [rows, d] pre-LayerNorm projection, NULL = not saved (no D-param backward) */
   int32_t precision;
   void* workspace; size_t workspace_bytes;
 } AdvmilEmbedActs;
@@ -208,34 +214,40 @@ ADVMIL_API int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
 /* ---- DeepAttMISL cluster pooling (model/backbone.py:105-117): hc[b,c] = mean_{n in bag b, cid[n]==c} v[n,:], zeros if empty.
  * v: [rows,width]; cid: [rows] int32 in [0,num_clusters); out: [bags*num_clusters,width]; counts: [bags*num_clusters] int32 */
 ADVMIL_API size_t advmil_segment_mean_workspace_bytes(int32_t rows, int32_t bags, int32_t width, int32_t num_clusters);
-ADVMIL_API int advmil_segment_mean_by_id_fwd(const float* v, const int32_t* cid, const int32_t* offsets, const int32_t* offsets_host,
-                                  int32_t rows, int32_t bags, int32_t width, int32_t num_clusters, float* out,
-                                  int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+ADVMIL_API int advmil_segment_mean_by_id_fwd(const void* v /*elem*/, int32_t elem, const int32_t* cid, const int32_t* offsets,
+                                  const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width,
+                                  int32_t num_clusters, float* out, int32_t* counts, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 /* d_v[n,:] = d_out[bag(n), cid[n], :] / count, optionally masked by (v > 0) (ReLU before the mean) */
-ADVMIL_API int advmil_segment_mean_by_id_bwd(const float* d_out, const float* v, const int32_t* cid, const int32_t* offsets,
-                                  const int32_t* counts, int32_t rows, int32_t bags, int32_t width, int32_t num_clusters,
-                                  int32_t relu_mask, float* d_v, void* stream);
+ADVMIL_API int advmil_segment_mean_by_id_bwd(const float* d_out, const void* v /*elem*/, int32_t elem, const int32_t* cid,
+                                  const int32_t* offsets, const int32_t* counts, int32_t rows, int32_t bags, int32_t width,
+                                  int32_t num_clusters, int32_t relu_mask, void* d_v /*elem*/, void* stream);
 
 /* ---- stage-level entry points (also used by the DeepAttMISL path and by the kernel unit tests) ---- */
-/* y = act(x W^T + b): act 0 none, 1 relu; optional dropout (p, mask or seed/site) -> y [rows,N].  W: [N,K] */
-ADVMIL_API int advmil_linear_fwd(const float* x, const float* W, const float* b, int32_t rows, int32_t K, int32_t N, int32_t act,
+/* y = act(x W^T + b): act 0 none, 1 relu; optional dropout (p, mask or seed/site) -> y [rows,N].  W: [N,K] fp32.
+ * x, y (and dY, X, dX, v, ab below): element type T of `precision` (bf16 in ADVMIL_BF16, else fp32). */
+ADVMIL_API int advmil_linear_fwd(const void* x, const float* W, const float* b, int32_t rows, int32_t K, int32_t N, int32_t act,
                       float p_drop, const uint8_t* mask, uint64_t seed, int32_t site, int32_t train,
-                      int32_t precision, float* y, void* stream);
+                      int32_t precision, void* y, void* stream);
 /* dX = dY W (optionally * (y_fwd>0)/(1-p) when relu_y != NULL), dW = dY^T X, db = colsum(dY); any output may be NULL */
-ADVMIL_API int advmil_linear_bwd(const float* dY, const float* X, const float* W, int32_t rows, int32_t K, int32_t N,
-                      float* dX, float* dW, float* db, int32_t accumulate, int32_t precision,
+ADVMIL_API int advmil_linear_bwd(const void* dY, const void* X, const float* W, int32_t rows, int32_t K, int32_t N,
+                      void* dX, float* dW, float* db, int32_t accumulate, int32_t precision,
                       void* workspace, size_t workspace_bytes, void* stream);
 ADVMIL_API size_t advmil_linear_bwd_workspace_bytes(int32_t rows, int32_t K, int32_t N);
 /* gated attention scores (Attn_Net_Gated.forward, model/backbone_utils.py:24-29) */
-ADVMIL_API int advmil_gated_score_fwd(const float* v, const float* Wa, const float* ba, const float* Wb, const float* bb,
+ADVMIL_API int advmil_gated_score_fwd(const void* v, const float* Wa, const float* ba, const float* Wb, const float* bb,
                            const float* wc, const float* bc, int32_t rows, int32_t L, int32_t D, float p_drop,
                            const uint8_t* mask_a, const uint8_t* mask_b, uint64_t seed, int32_t site, int32_t train,
-                           int32_t precision, float* ab, float* s, void* workspace, size_t workspace_bytes, void* stream);
+                           int32_t precision, void* ab, float* s, void* workspace, size_t workspace_bytes, void* stream);
 /* segmented softmax + attention pooling (model/backbone.py:82-84): w = softmax over each bag of s; z[b] = sum w v */
-ADVMIL_API int advmil_seg_softmax_pool_fwd(const float* s, const float* v, const int32_t* offsets, const int32_t* offsets_host,
-                                int32_t rows, int32_t bags, int32_t width, float* w, float* z, float* mean,
-                                void* workspace, size_t workspace_bytes, void* stream);
+ADVMIL_API int advmil_seg_softmax_pool_fwd(const float* s, const void* v /*elem*/, int32_t elem, const int32_t* offsets,
+                                const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width, float* w, float* z,
+                                float* mean, void* workspace, size_t workspace_bytes, void* stream);
 ADVMIL_API size_t advmil_seg_pool_workspace_bytes(int32_t rows, int32_t bags, int32_t width);
+
+/* fp32 -> bf16 (round to nearest even) of n contiguous elements: how fp32 features enter the ADVMIL_BF16 mode when the
+ * loader did not already store them as bf16 */
+ADVMIL_API int advmil_cast_f32_to_bf16(const float* in, int64_t n, void* out_bf16, void* stream);
 
 /* ---- region <-> patch index map (tools/big_to_small_patching.py:40-46,59-76) ---------------- */
 /* coords_l2 [m,2] int64 (device) -> coords_l1 [16m,2] float64 (device): row 16k+4j+i = c_k + (i*psize, j*psize) */

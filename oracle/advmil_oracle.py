@@ -44,14 +44,72 @@ def _lin(v: Tensor, sd: SD, name: str) -> Tensor:
     return F.linear(v, sd[name + ".weight"], sd.get(name + ".bias"))
 
 
+# ---- optional emulation of the bf16 STORAGE mode of the CUDA path (tests only) ----------------------------------
+# The reference is fp32 end to end.  The CUDA path's bf16 mode keeps x, the N-row GEMM operands (weights as read by the
+# tensor cores) and the N-row activations / activation gradients it writes to HBM (h, y_pre, dAB, dh, dy) in bfloat16,
+# with fp32 accumulation, statistics, parameters and gradients.  Under `with bf16_storage():` the N-row stages below
+# round at the same points (straight-through), so that a kernel bug cannot hide behind the ReLU-mask flips that ANY
+# bf16 evaluation shows against the fp32 reference.  Off by default: the oracle proper is the fp32 restatement.
+_EMU_BF16 = False
+
+
+class bf16_storage:
+    def __enter__(self):
+        global _EMU_BF16
+        self.prev, _EMU_BF16 = _EMU_BF16, True
+
+    def __exit__(self, *a):
+        global _EMU_BF16
+        _EMU_BF16 = self.prev
+
+
+def _round_bf16(v: Tensor) -> Tensor:
+    return v.to(torch.bfloat16).to(v.dtype)
+
+
+class _RoundSTE(torch.autograd.Function):     # forward: round to bf16; backward: identity
+    @staticmethod
+    def forward(ctx, v):
+        return _round_bf16(v)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):    # forward: identity; backward: gradient rounded to bf16 (dAB / dh / dy)
+    @staticmethod
+    def forward(ctx, v):
+        return v.view_as(v)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _round_bf16(g)
+
+
+def _q(v: Tensor) -> Tensor:
+    return _RoundSTE.apply(v) if _EMU_BF16 else v
+
+
+def _qg(v: Tensor) -> Tensor:
+    return _RoundGrad.apply(v) if _EMU_BF16 else v
+
+
+def _lin_rows(v: Tensor, W: Tensor, b: Optional[Tensor]) -> Tensor:
+    """An N-row contraction: in emulation mode both tensor-core operands are bf16 and the gradient flowing back into the
+    pre-activation is stored as bf16."""
+    return _qg(F.linear(_q(v), _q(W), b))
+
+
 # ----------------------------------------------------------------------------------------------
 # G: ABMIL backbone + gated attention + pooling  (model/backbone.py:54-86, backbone_utils.py:11-29)
 # ----------------------------------------------------------------------------------------------
 def gated_attention_scores(h: Tensor, sd: SD, prefix: str, masks=None, p: float = 0.25) -> Tensor:
     """Attn_Net_Gated.forward (model/backbone_utils.py:24-29): s = (tanh(hWa+ba) * sig(hWb+bb)) wc + bc."""
     masks = masks or {}
-    a = _drop(torch.tanh(_lin(h, sd, prefix + ".attention_a.0")), masks.get("a"), p)
-    b = _drop(torch.sigmoid(_lin(h, sd, prefix + ".attention_b.0")), masks.get("b"), p)
+    rows = _lin_rows if (_EMU_BF16 and prefix.startswith("backbone")) else F.linear   # GAPool of D is region-level: fp32
+    a = _drop(torch.tanh(rows(h, sd[prefix + ".attention_a.0.weight"], sd[prefix + ".attention_a.0.bias"])), masks.get("a"), p)
+    b = _drop(torch.sigmoid(rows(h, sd[prefix + ".attention_b.0.weight"], sd[prefix + ".attention_b.0.bias"])), masks.get("b"), p)
     return _lin(a * b, sd, prefix + ".attention_c")  # [N, 1]
 
 
@@ -62,7 +120,9 @@ def abmil_forward(sd: SD, x: Tensor, masks=None, p: float = 0.25, prefix: str = 
     Returns h (post-dropout, the tensor that is pooled — quirk A.4#4), s, w, z, H.
     """
     masks = masks or {}
-    h = _drop(torch.relu(_lin(x, sd, f"{prefix}.attention_net.0")), masks.get("h"), p)  # backbone.py:67-70
+    h = _drop(torch.relu(_lin_rows(x, sd[f"{prefix}.attention_net.0.weight"], sd[f"{prefix}.attention_net.0.bias"])),
+              masks.get("h"), p)                                                           # backbone.py:67-70
+    h = _q(h)
     s = gated_attention_scores(h, sd, f"{prefix}.attention_net.3", masks, p)              # backbone.py:71
     w = torch.softmax(s.transpose(1, 0), dim=1)                                            # backbone.py:82-83
     z = w @ h                                                                              # backbone.py:84
@@ -148,7 +208,7 @@ def region_embed(sd: SD, x: Tensor, prefix: str = "net_pair_one.embedding", eps:
     assert N % 16 == 0
     Wc = sd[f"{prefix}.conv.weight"]
     Wc = Wc.reshape(Wc.shape[0], -1)
-    y = F.linear(x, Wc, sd[f"{prefix}.conv.bias"])
+    y = _q(_lin_rows(x, Wc, sd[f"{prefix}.conv.bias"]))
     e = torch.relu(F.layer_norm(y, (y.shape[-1],), sd[f"{prefix}.norm.weight"], sd[f"{prefix}.norm.bias"], eps))
     emb = e.reshape(N // 16, 16, -1).mean(dim=1)
     return {"y": y, "e": e, "emb": emb}
