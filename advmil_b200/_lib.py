@@ -64,7 +64,7 @@ class HeadActs(C.Structure):
     _fields_ = [("emb", c_fp), ("t", c_fp), ("f1", c_fp), ("fi", c_fp), ("ab", c_fp), ("rep", c_fp), ("attn", c_fp),
                 ("bagv", c_fp), ("fbar", c_fp), ("g1", c_fp), ("hx", c_fp), ("u1", c_fp), ("ht", c_fp), ("out", c_fp),
                 ("mask_fc1", c_u8p), ("mask_ga", c_u8p), ("mask_gs", c_u8p), ("mask_fc2", c_u8p),
-                ("seed", C.c_uint64), ("train", C.c_int32),
+                ("seed", C.c_uint64), ("train", C.c_int32), ("precision", C.c_int32),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
@@ -100,6 +100,7 @@ SYMBOLS = {
                                          _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "advmil_seg_softmax_pool_fwd": (C.c_int, [_vp, _vp, _i32, _vp, _P(C.c_int32), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "advmil_cast_f32_to_bf16": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "advmil_dropout_mask": (C.c_int, [_u64, _i32, _f, _i32, _i32, _vp, _vp]),
     "advmil_seg_pool_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "advmil_region_index_map": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "advmil_region_of_rows": (C.c_int, [_i32, _i32, _vp, _vp]),
@@ -110,7 +111,7 @@ SYMBOLS = {
 }
 
 PROF_TAGS = ["proj_fwd", "gate_fwd", "pool_fwd", "embed_fwd", "pool_gate_bwd", "bwd_data", "bwd_w_gate", "bwd_w_proj",
-             "ln_bwd", "bwd_w_embed", "colsum", "dropout"]
+             "ln_bwd", "bwd_w_embed", "colsum", "dropout", "head_fwd", "head_bwd", "gen_tail", "loss_opt"]
 
 _lib = None
 

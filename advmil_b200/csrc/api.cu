@@ -139,20 +139,21 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
   WS_TAKE(bp, float, abw);
   WS_TAKE(part, float, (size_t)(abw / 128) * rows);
   WS_TAKE(poolws, float, seg_pool_ws_floats(rows, nb, h));
-  Drop dh = Drop::make(a->mask_h, a->seed, SITE_H, p->p_backbone, a->train);
-  Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train);
-  Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train);
-  Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train);
-  Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train);
+  Drop dh = Drop::make(a->mask_h, a->seed, SITE_H, p->p_backbone, a->train, p->h);
+  Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train, p->h);
+  Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train, p->h);
+  Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train, p->o);
+  Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train, p->hid);
   const int dt = elem_of_precision(a->precision);
   if (a->h_eval) { ProfScope ps(PROF_DROPOUT, st); ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, dt, st)); }
   else { ProfScope ps(PROF_PROJ, st); ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st)); }
-  ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
+  { ProfScope ps(PROF_GEN_TAIL, st); ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st)); }
   { ProfScope ps(PROF_GATE, st);
     ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, a->s, part, a->precision, st)); }
   { ProfScope ps(PROF_POOL, st);
     ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, dt, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st)); }
-  ADVMIL_TRY(gen_head_fwd(*p, a->z, a->noise0, a->noise1, nb, 1, drho, dmlp0, a->H, a->H1, a->pre, a->pred, st));
+  { ProfScope ps(PROF_GEN_TAIL, st);
+    ADVMIL_TRY(gen_head_fwd(*p, a->z, a->noise0, a->noise1, nb, 1, drho, dmlp0, a->H, a->H1, a->pre, a->pred, st)); }
   return ADVMIL_OK;
 }
 
@@ -182,24 +183,26 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   WS_TAKE(csws, float, (size_t)row_chunks(rows) * max(abw, h));
   const float ik_bb = (a->train && p->p_backbone > 0.f) ? 1.f / (1.f - p->p_backbone) : 1.f;
   const float ik_hd = (a->train && p->p_head > 0.f) ? 1.f / (1.f - p->p_head) : 1.f;
-  Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train);
-  Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train);
+  Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train, p->h);
+  Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train, p->h);
   // head
-  ADVMIL_TRY(gen_head_bwd(*p, d_pred, a->H, a->H1, a->pred, nb, ik_bb, ik_hd, dz, dHpre, dH1pre, dpre, st));
-  if (p->W0) {
-    ADVMIL_TRY(outer_sum(dpre, a->H1, hid, a->noise1, p->noise1 ? hid : 0, nb, 1, g->Wl, g->bl, 0, st));
-    ADVMIL_TRY(outer_sum(dH1pre, a->H, o, a->noise0, p->noise0 ? o : 0, nb, hid, g->W0, g->b0, 0, st));
+  { ProfScope ps(PROF_GEN_TAIL, st);
+    ADVMIL_TRY(gen_head_bwd(*p, d_pred, a->H, a->H1, a->pred, nb, ik_bb, ik_hd, dz, dHpre, dH1pre, dpre, st));
+    if (p->W0) {
+      ADVMIL_TRY(outer_sum(dpre, a->H1, hid, a->noise1, p->noise1 ? hid : 0, nb, 1, g->Wl, g->bl, 0, st));
+      ADVMIL_TRY(outer_sum(dH1pre, a->H, o, a->noise0, p->noise0 ? o : 0, nb, hid, g->W0, g->b0, 0, st));
+    }
+    if (p->Wrho) ADVMIL_TRY(outer_sum(dHpre, a->z, h, nullptr, 0, nb, o, g->Wrho, g->brho, 0, st));
+    // pooling + gate
+    ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
   }
-  if (p->Wrho) ADVMIL_TRY(outer_sum(dHpre, a->z, h, nullptr, 0, nb, o, g->Wrho, g->brho, 0, st));
-  // pooling + gate
-  ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
   { ProfScope ps(PROF_POOL_BWD, st);
     ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, dbp, 0, pgws, dt, st)); }
   BwdDataExtras ex;
   ex.w = a->w; ex.dz = dz; ex.offsets = bags->offsets; ex.bags = nb; ex.relu_src = a->h; ex.ld_src = h; ex.inv_keep = ik_bb;
   { ProfScope ps(PROF_BWD_DATA, st); ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st)); }
   { ProfScope ps(PROF_BWD_W_GATE, st); ADVMIL_TRY(bwd_weight(dAB, a->h, rows, abw, h, dWp, 0, bwws, prec, st)); }
-  ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st));
+  { ProfScope ps(PROF_GEN_TAIL, st); ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st)); }
   // first layer
   { ProfScope ps(PROF_BWD_W_PROJ, st); ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st)); }
   { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dhpre, dt, rows, h, h, g->b1, 0, csws, st)); }
@@ -216,7 +219,7 @@ extern "C" int advmil_generator_sample(const AdvmilGenParams* p, const float* H,
   // H is the backbone output (post rho); run only MLPs + out scale: present H as "z" with the rho layer disabled
   AdvmilGenParams q = *p;
   q.Wrho = nullptr; q.brho = nullptr; q.h = p->o;
-  Drop none = Drop::make(nullptr, 0, 0, 0.f, 0);
+  Drop none = Drop::make(nullptr, 0, 0, 0.f, 0, 0);
   return gen_head_fwd(q, H, noise0, noise1, bags, samples, none, none, nullptr, nullptr, nullptr, out, (cudaStream_t)stream);
 }
 
@@ -292,6 +295,7 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   ADVMIL_REQUIRE(a->f1 && a->fi && a->rep && a->attn && a->bagv && a->fbar && a->g1 && a->hx && a->u1 && a->ht,
                  "disc_head_fwd: missing activation buffers");
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(PROF_HEAD_FWD, st);
   const int nb = bags->bags, d = p->d, dh = p->d / 2, R = bags->rows / 16;
   const int abw = gate_width(d);
   Workspace ws(a->workspace, a->workspace_bytes);
@@ -301,16 +305,17 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   WS_TAKE(bp, float, abw);
   WS_TAKE(part, float, (size_t)(abw / 128) * R);
   WS_TAKE(poolws, float, seg_pool_ws_floats(R, nb, d));
-  Drop dfc1 = Drop::make(a->mask_fc1, a->seed, SITE_FC1, p->p, a->train);
-  Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train);
-  Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train);
-  Drop dfc2 = Drop::make(a->mask_fc2, a->seed, SITE_FC2, p->p, a->train);
-  Drop none = Drop::make(nullptr, 0, 0, 0.f, 0);
-  // region-level work is tiny (R = rows/16): always the fp32 FFMA engine
-  ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, ADVMIL_FP32, st));
-  ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, ADVMIL_FP32, st));
+  Drop dfc1 = Drop::make(a->mask_fc1, a->seed, SITE_FC1, p->p, a->train, p->d / 2);
+  Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train, p->d);
+  Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train, p->d);
+  Drop dfc2 = Drop::make(a->mask_fc2, a->seed, SITE_FC2, p->p, a->train, p->d / 2);
+  Drop none = Drop::make(nullptr, 0, 0, 0.f, 0, 0);
+  // region-level tensors are fp32; outside the exact-fp32 mode their contractions run on tcgen05 kind::tf32
+  const int rp = a->precision == ADVMIL_FP32 ? ADVMIL_FP32 : ADVMIL_TF32;
+  ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, rp, st));
+  ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, rp, st));
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
-  ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, a->rep, part, ADVMIL_FP32, st));
+  ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, a->rep, part, rp, st));
   ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, a->fi, ELEM_F32, ro.dev, ro.host.data(), R, nb, d, a->attn, a->bagv, a->fbar, poolws, st));
   ADVMIL_TRY(rlip_tail_fwd(*p, a->bagv, a->fbar, a->t, nb, dfc2, a->g1, a->hx, a->u1, a->ht, a->out, st));
   return ADVMIL_OK;
@@ -322,9 +327,11 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   ADVMIL_REQUIRE(p && a && d_out, "disc_head_bwd: null argument");
   ADVMIL_TRY(check_bags(bags, p->C, true, bags ? (bags->elem == ELEM_BF16 ? ADVMIL_BF16 : ADVMIL_FP32) : 0));
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(PROF_HEAD_BWD, st);
   const int nb = bags->bags, d = p->d, dh = p->d / 2, R = bags->rows / 16, t1 = p->t1, t2 = p->t2;
   const int abw = gate_width(d);
   const float ik = (a->train && p->p > 0.f) ? 1.f / (1.f - p->p) : 1.f;
+  const int rp = a->precision == ADVMIL_FP32 ? ADVMIL_FP32 : ADVMIL_TF32;
   Workspace ws(a->workspace, a->workspace_bytes);
   RegionOffsets ro;
   ADVMIL_TRY(make_region_offsets(bags, ws, st, ro));
@@ -357,32 +364,32 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   WS_TAKE(pgws, float, pool_gate_ws_floats(R, nb, d));
   WS_TAKE(bwws, float, max(bwd_weight_ws_floats(R, abw, d), bwd_weight_ws_floats(R, d, dh)));
   WS_TAKE(csws, float, (size_t)row_chunks(R) * abw);
-  Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train);
-  Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train);
+  Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train, p->d);
+  Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train, p->d);
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
   ADVMIL_TRY(pool_gate_bwd(a->fi, a->attn, a->bagv, d_bagv, a->ab, p->Pc_w, ro.dev, R, nb, d, d, dga, dgs, dAB,
                            g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? dbp : nullptr, g ? accumulate : 0, pgws,
                            ELEM_F32, st));
   BwdDataExtras ex;
   ex.w = a->attn; ex.dz = d_bagv; ex.dmean = p->inner_instance ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
-  ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, ADVMIL_FP32, st));
+  ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, rp, st));
   if (g) {
-    ADVMIL_TRY(bwd_weight(dAB, a->fi, R, abw, d, dWp, 0, bwws, ADVMIL_FP32, st));
+    ADVMIL_TRY(bwd_weight(dAB, a->fi, R, abw, d, dWp, 0, bwws, rp, st));
     ADVMIL_TRY(gate_unpack_grads(dWp, dbp, d, d, g->Pg_w, g->Pg_b, g->Ps_w, g->Ps_b, accumulate, st));
   }
   BwdDataExtras ex1;
   ex1.relu_src = a->f1; ex1.ld_src = dh; ex1.inv_keep = ik;
-  ADVMIL_TRY(bwd_data(d_fi, p->F1b_w, R, d, dh, d_f1pre, ex1, ADVMIL_FP32, st));
+  ADVMIL_TRY(bwd_data(d_fi, p->F1b_w, R, d, dh, d_f1pre, ex1, rp, st));
   if (g) {
-    ADVMIL_TRY(bwd_weight(d_fi, a->f1, R, d, dh, g->F1b_w, accumulate, bwws, ADVMIL_FP32, st));
+    ADVMIL_TRY(bwd_weight(d_fi, a->f1, R, d, dh, g->F1b_w, accumulate, bwws, rp, st));
     ADVMIL_TRY(colsum(d_fi, ELEM_F32, R, d, d, g->F1b_b, accumulate, csws, st));
-    ADVMIL_TRY(bwd_weight(d_f1pre, a->emb, R, dh, d, g->F1a_w, accumulate, bwws, ADVMIL_FP32, st));
+    ADVMIL_TRY(bwd_weight(d_f1pre, a->emb, R, dh, d, g->F1a_w, accumulate, bwws, rp, st));
     ADVMIL_TRY(colsum(d_f1pre, ELEM_F32, R, dh, dh, g->F1a_b, accumulate, csws, st));
   }
   if (d_emb) {
     BwdDataExtras ex2;
     ex2.accumulate = accumulate;
-    ADVMIL_TRY(bwd_data(d_f1pre, p->F1a_w, R, dh, d, d_emb, ex2, ADVMIL_FP32, st));
+    ADVMIL_TRY(bwd_data(d_f1pre, p->F1a_w, R, dh, d, d_emb, ex2, rp, st));
   }
   return ADVMIL_OK;
 }
@@ -394,7 +401,7 @@ extern "C" int advmil_linear_fwd(const void* x, const float* W, const float* b, 
                                  int32_t act, float p_drop, const uint8_t* mask, uint64_t seed, int32_t site,
                                  int32_t train, int32_t precision, void* y, void* stream) {
   ADVMIL_REQUIRE(x && W && y && rows >= 0, "linear_fwd: null argument");
-  Drop dr = Drop::make(mask, seed, SITE_USER + site, p_drop, train);
+  Drop dr = Drop::make(mask, seed, SITE_USER + site, p_drop, train, N);
   return linear_fwd(x, W, b, rows, K, N, act, dr, y, precision, (cudaStream_t)stream);
 }
 
@@ -437,8 +444,8 @@ extern "C" int advmil_gated_score_fwd(const void* v, const float* Wa, const floa
   WS_TAKE(Wp, float, (size_t)abw * L);
   WS_TAKE(bp, float, abw);
   WS_TAKE(part, float, (size_t)(abw / 128) * rows);
-  Drop da = Drop::make(mask_a, seed, SITE_USER + site, p_drop, train);
-  Drop db = Drop::make(mask_b, seed, SITE_USER + site + 1, p_drop, train);
+  Drop da = Drop::make(mask_a, seed, SITE_USER + site, p_drop, train, D);
+  Drop db = Drop::make(mask_b, seed, SITE_USER + site + 1, p_drop, train, D);
   ADVMIL_TRY(gate_pack_weights(Wa, ba, Wb, bb, L, D, Wp, bp, st));
   return gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, part, precision, st);
 }

@@ -60,7 +60,11 @@ enum ProfTag : int {
   PROF_BWD_W_EMBED = 9, // dWc = dy^T x
   PROF_COLSUM = 10,     // bias gradients
   PROF_DROPOUT = 11,    // dropout re-application on cached eval activations
-  PROF_NTAGS = 12
+  PROF_HEAD_FWD = 12,   // RLIP head forward (region MLP, GAPool, bag MLP, time embedding, inner product)
+  PROF_HEAD_BWD = 13,   // RLIP head backward
+  PROF_GEN_TAIL = 14,   // generator per-bag head fwd/bwd, small outer products, gate weight packing
+  PROF_LOSS_OPT = 15,   // losses, Adam, L1 value
+  PROF_NTAGS = 16
 };
 struct ProfScope {
   int tag; cudaStream_t st; void* rec;
@@ -113,32 +117,53 @@ struct Drop {          // one dropout site
   float inv_keep;      // 1/(1-p)
   int site;
   int active;          // train && p > 0
+  int width;           // logical row width of the dropped tensor (index of an injected mask = row * width + col)
   uint32_t key;        // per-(seed, site) 32-bit key of the counter-based generator
-  uint32_t thresh;     // drop when hash < thresh (= p * 2^32)
-  __host__ static Drop make(const uint8_t* mask, uint64_t seed, int site, float p, int train) {
+  uint32_t thresh16;   // an element is dropped when its 16 random bits < thresh16 (= round(p * 2^16))
+  __host__ static Drop make(const uint8_t* mask, uint64_t seed, int site, float p, int train, int width) {
     Drop d;
-    d.mask = mask; d.seed = seed; d.site = site; d.p = p;
+    d.mask = mask; d.seed = seed; d.site = site; d.p = p; d.width = width;
     d.active = (train && p > 0.f) ? 1 : 0;
     d.inv_keep = d.active ? 1.0f / (1.0f - p) : 1.0f;
     d.key = (uint32_t)(mix64(seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1)) >> 32);
-    double t = (double)p * 4294967296.0;
-    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    double t = (double)p * 65536.0 + 0.5;
+    d.thresh16 = t >= 65536.0 ? 65536u : (uint32_t)t;
     return d;
   }
-  // keep bit of element idx (= row*width + col): ~10 integer instructions (multiply-xorshift hash of the counter), the
-  // same bits in forward and backward
-  __device__ __forceinline__ bool keep(uint64_t idx) const {
-    if (mask) return mask[idx] != 0;
-    uint32_t x = ((uint32_t)idx * 0x9E3779B1u) ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ key;
-    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-    return x >= thresh;
+  // 32 random bits of the counter (row, col): 2-D multiply-xor counter + murmur3 finaliser, ~9 integer instructions.
+  // One draw serves TWO elements (16 bits each; the keep probability is quantised to 2^-16, a relative bias < 2e-5):
+  // columns (2k, 2k+1) of a plain site, or the (tanh_j, sigmoid_j) pair of a gate.  Forward and backward regenerate the
+  // same bits from (seed, site, row, col).
+  __device__ __forceinline__ uint32_t bits(uint32_t row, uint32_t col) const {
+    uint32_t x = (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u + key);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+  }
+  __device__ __forceinline__ bool keep(uint32_t row, uint32_t col) const {
+    if (mask) return mask[(size_t)row * width + col] != 0;
+    const uint32_t h = bits(row, col & ~1u);
+    return ((col & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
+  }
+  // columns col (even) and col + 1 from one draw
+  __device__ __forceinline__ void keep2(uint32_t row, uint32_t col_even, bool& k0, bool& k1) const {
+    if (mask) { k0 = mask[(size_t)row * width + col_even] != 0; k1 = mask[(size_t)row * width + col_even + 1] != 0; return; }
+    const uint32_t h = bits(row, col_even);
+    k0 = (h & 0xFFFFu) >= thresh16; k1 = (h >> 16) >= thresh16;
   }
   // multiplicative factor: 0 or 1/(1-p); 1 when inactive
-  __device__ __forceinline__ float scale(uint64_t idx) const {
+  __device__ __forceinline__ float scale(uint32_t row, uint32_t col) const {
     if (!active) return 1.0f;
-    return keep(idx) ? inv_keep : 0.0f;
+    return keep(row, col) ? inv_keep : 0.0f;
   }
 };
+
+// keep bits of the (tanh_j, sigmoid_j) pair of a gated-attention row from ONE draw keyed by the tanh site
+__device__ __forceinline__ void gate_keep(const Drop& da, const Drop& db, uint32_t row, uint32_t j, bool& ka, bool& kb) {
+  uint32_t h = 0;
+  if (!da.mask || !db.mask) h = da.bits(row, j);
+  ka = da.mask ? da.mask[(size_t)row * da.width + j] != 0 : (h & 0xFFFFu) >= da.thresh16;
+  kb = db.mask ? db.mask[(size_t)row * db.width + j] != 0 : (h >> 16) >= db.thresh16;
+}
 
 // ---- element types of the [rows, width] activation tensors ------------------------------------------
 // fp32 / tf32 modes keep them in fp32; the bf16 mode (ADVMIL_BF16) keeps x, h, ab, dAB, dh, y_pre, d_y in bfloat16

@@ -151,7 +151,7 @@ struct EpiLinear {
           if (n + j < N) {
             if (bias) val += bias[n + j];
             if (relu) val = fmaxf(val, 0.f);
-            val *= drop.scale((uint64_t)m * drop_width + n + j);
+            val *= drop.scale(m, n + j);
           }
           v[j] = val;
         }
@@ -187,8 +187,13 @@ struct EpiGate {
         av[j] = a; bv[j] = b;
         int jj = j0 + j;
         if (jj < D && m < M) {
-          float ad = a * drop_a.scale((uint64_t)m * D + jj);
-          float bd = b * drop_b.scale((uint64_t)m * D + jj);
+          float ad = a, bd = b;
+          if (drop_a.active) {
+            bool ka, kb;
+            gate_keep(drop_a, drop_b, m, jj, ka, kb);
+            ad = ka ? a * drop_a.inv_keep : 0.f;
+            bd = kb ? b * drop_b.inv_keep : 0.f;
+          }
           partial = fmaf(ad * bd, wc[jj], partial);
         }
       }

@@ -57,7 +57,7 @@ int bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX,
              int precision, cudaStream_t st) {
   ADVMIL_REQUIRE(gemm_ok(Ny, Nx, dY, W), "bwd_data: Ny=%d Nx=%d must be multiples of 4", Ny, Nx);
   if (rows == 0) return ADVMIL_OK;
-  if (precision != ADVMIL_FP32 && !ex.accumulate && !ex.dmean && tc_bwd_data_supported(rows, Ny, Nx, elem_of_precision(precision)))
+  if (precision != ADVMIL_FP32 && tc_bwd_data_supported(rows, Ny, Nx, elem_of_precision(precision)))
     return tc_bwd_data(dY, W, rows, Ny, Nx, dX, ex, precision, st);
   ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "bwd_data", rows, Ny, Nx);
   GemmArgs g{(const float*)dY, W, rows, Nx, Ny, Ny, Nx, Ny};

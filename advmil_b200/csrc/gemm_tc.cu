@@ -92,6 +92,7 @@ struct RowEpi {
   void* ab; const float* wc; float* part; int D; Drop drop_a, drop_b;            // EPI_GATE (bias = packed gate bias)
   void* y_pre; float* emb; const float* gamma; const float* beta; float eps;     // EPI_LN
   const float* w; const float* dz; const int32_t* offsets; int bags;             // EPI_BWD
+  const float* dmean; int accumulate;
   const void* relu_src; int ld_src; float inv_keep;
 };
 
@@ -110,7 +111,7 @@ template <int BLOCK_N, int EPI> struct RowCfg {
   static constexpr int COEF_FLOATS_PER_WARP = 192;                // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                                 (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 64) * 4 + 256 /*barriers*/;
+                                 (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 96) * 4 + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float fast_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -155,7 +156,7 @@ __device__ __forceinline__ void store_staged(const float* stg, int ld, T* __rest
 template <bool FAST, bool TRAIN>
 __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], const float* __restrict__ cba,
                                             const float* __restrict__ cbb, const float* __restrict__ cwc, const Drop& da,
-                                            const Drop& db, uint64_t idx0, float partial) {
+                                            const Drop& db, uint32_t row, uint32_t j0, float partial) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const float xa = va[i] + cba[i], xb = vb[i] + cbb[i];
@@ -165,8 +166,10 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
     va[i] = a; vb[i] = b;
     float ad = a, bd = b;
     if (TRAIN) {
-      ad = da.keep(idx0 + i) ? a * da.inv_keep : 0.f;
-      bd = db.keep(idx0 + i) ? b * db.inv_keep : 0.f;
+      bool ka, kb;
+      gate_keep(da, db, row, j0 + i, ka, kb);
+      ad = ka ? a * da.inv_keep : 0.f;
+      bd = kb ? b * db.inv_keep : 0.f;
     }
     partial = fmaf(ad * bd, cwc[i], partial);
   }
@@ -191,7 +194,8 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* coef_all = stg_all + Cfg::EPI_WARPS * Cfg::STG_FLOATS_PER_WARP;
   int* rowbag = (int*)(coef_all + Cfg::EPI_WARPS * Cfg::COEF_FLOATS_PER_WARP);
   float* roww = (float*)(rowbag + Cfg::EPI_WARPS * 32);
-  uint64_t* bars = (uint64_t*)(roww + Cfg::EPI_WARPS * 32);
+  float* rowinv = roww + Cfg::EPI_WARPS * 32;
+  uint64_t* bars = (uint64_t*)(rowinv + Cfg::EPI_WARPS * 32);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
@@ -278,6 +282,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* coef = coef_all + ew * Cfg::COEF_FLOATS_PER_WARP;
     int* mybag = rowbag + ew * 32;
     float* myw = roww + ew * 32;
+    float* myinv = rowinv + ew * 32;
     int it = 0;
     for (int tile = work0; tile < total; tile += work_stride, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -285,9 +290,13 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_base = mt * TILE_M + wq * 32, n0 = nt * BLOCK_N;
       const int m_row = m_base + lane;                     // the row this thread owns in TMEM
       if constexpr (EPI == EPI_BWD) {                      // per-row pooling operands (independent of the accumulator)
-        int bg = 0; float wv = 0.f;
-        if (ea.dz && m_row < M) { bg = bag_of_row(ea.offsets, ea.bags, m_row); wv = ea.w[m_row]; }
-        mybag[lane] = bg; myw[lane] = wv;
+        int bg = 0; float wv = 0.f, inv = 0.f;
+        if ((ea.dz || ea.dmean) && m_row < M) {
+          bg = bag_of_row(ea.offsets, ea.bags, m_row);
+          if (ea.dz) wv = ea.w[m_row];
+          if (ea.dmean) inv = 1.0f / (float)(ea.offsets[bg + 1] - ea.offsets[bg]);
+        }
+        mybag[lane] = bg; myw[lane] = wv; myinv[lane] = inv;
       }
       if constexpr (EPI == EPI_GATE) {                     // this warp's gate block: biases and w_c into shared memory
         const int cb0 = n0 + half * 128, j0 = (n0 >> 1) + half * 64;
@@ -349,7 +358,12 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (ea.drop.active) {
 #pragma unroll
-                  for (int e = 0; e < VEC; ++e) o[e] = ea.drop.keep((uint64_t)m * N + col + e) ? o[e] * ea.drop.inv_keep : 0.f;
+                  for (int e = 0; e < VEC; e += 2) {
+                    bool k0, k1;
+                    ea.drop.keep2(m, col + e, k0, k1);
+                    o[e] = k0 ? o[e] * ea.drop.inv_keep : 0.f;
+                    o[e + 1] = k1 ? o[e + 1] * ea.drop.inv_keep : 0.f;
+                  }
                 }
               } else {
                 if (ea.dz) {
@@ -361,11 +375,26 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     o[4 * q + 2] = fmaf(wv, d4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(wv, d4.w, o[4 * q + 3]);
                   }
                 }
+                if (ea.dmean) {
+                  const float iv = myinv[r];
+#pragma unroll
+                  for (int q = 0; q < VEC / 4; ++q) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(ea.dmean + (size_t)mybag[r] * N + col + 4 * q);
+                    o[4 * q] = fmaf(iv, d4.x, o[4 * q]); o[4 * q + 1] = fmaf(iv, d4.y, o[4 * q + 1]);
+                    o[4 * q + 2] = fmaf(iv, d4.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(iv, d4.w, o[4 * q + 3]);
+                  }
+                }
                 if (srcp) {
                   float sv[VEC];
                   raw_floats(src[it2], sv);
 #pragma unroll
                   for (int e = 0; e < VEC; ++e) o[e] = sv[e] > 0.f ? o[e] * ea.inv_keep : 0.f;
+                }
+                if (ea.accumulate) {
+                  float pv[VEC];
+                  ldv(outp + (size_t)m * ea.ldo + col, pv);
+#pragma unroll
+                  for (int e = 0; e < VEC; ++e) o[e] += pv[e];
                 }
               }
               stv(outp + (size_t)m * ea.ldo + col, o);
@@ -386,9 +415,8 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(taddr + ca, va);
           tmem_ld32(taddr + cb, vb);
           if (jc == 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
-          const uint64_t idx0 = (uint64_t)m_row * ea.D + j0;
-          if (train) partial = gate_chunk<FAST, true>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, idx0, partial);
-          else partial = gate_chunk<FAST, false>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, idx0, partial);
+          if (train) partial = gate_chunk<FAST, true>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
+          else partial = gate_chunk<FAST, false>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
           if (ea.ab) {
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
@@ -644,6 +672,7 @@ static int pick_block_n(int N) {
   if (N % 192 == 0 && N % 256 != 0) return 192;
   if (N % 256 == 0) return 256;
   if (N % 128 == 0) return 128;
+  if (N == 64) return 64;
   return 0;
 }
 static int kblk_of(int dt) { return dt == ELEM_BF16 ? TcElem<bf16>::KBLK : TcElem<float>::KBLK; }
@@ -694,6 +723,7 @@ bool tc_linear_supported(int rows, int K, int N, int dt) { return rows_ok(rows, 
 template <typename T, int EPI, bool FAST>
 static int launch_rows_any(const T* A, const T* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
   switch (pick_block_n(N)) {
+    case 64: return launch_rows<T, 64, EPI, FAST>(A, W, rows, K, N, ea, st);
     case 128: return launch_rows<T, 128, EPI, FAST>(A, W, rows, K, N, ea, st);
     case 192: return launch_rows<T, 192, EPI, FAST>(A, W, rows, K, N, ea, st);
     case 256: return launch_rows<T, 256, EPI, FAST>(A, W, rows, K, N, ea, st);
@@ -778,11 +808,11 @@ static int tc_bwd_data_t(const void* dY, const float* W, int rows, int Ny, int N
                          cudaStream_t st) {
   void* wt = nullptr;
   ADVMIL_TRY(weight_scratch(WS_BWD_T, (size_t)Ny * Nx * sizeof(T), st, &wt));
-  ADVMIL_REQUIRE(!ex.accumulate && !ex.dmean, "tc_bwd_data: accumulate/dmean are served by the FFMA engine");
   transpose_kernel<T><<<dim3(cdiv(Nx, 32), cdiv(Ny, 32)), dim3(32, 8), 0, st>>>(W, Ny, Nx, (T*)wt);
   ADVMIL_CHECK_LAUNCH();
   RowEpi ea{};
   ea.out = dX; ea.ldo = Nx; ea.w = ex.w; ea.dz = ex.dz; ea.offsets = ex.offsets; ea.bags = ex.bags;
+  ea.dmean = ex.dmean; ea.accumulate = ex.accumulate;
   ea.relu_src = ex.relu_src; ea.ld_src = ex.ld_src; ea.inv_keep = ex.inv_keep;
   return launch_rows_any<T, EPI_BWD, true>((const T*)dY, (const T*)wt, rows, Ny, Nx, ea, st);
 }
@@ -795,6 +825,7 @@ int tc_bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* 
 static int wgrad_block_n(int N2) {
   if (N2 % 256 == 0) return 256;
   if (N2 % 128 == 0) return 128;
+  if (N2 == 64) return 64;
   return 0;
 }
 static int wgrad_splits(int rows, int N1, int N2) {
@@ -805,10 +836,10 @@ static int wgrad_splits(int rows, int N1, int N2) {
   return min(s, max_by_rows);
 }
 bool tc_bwd_weight_supported(int rows, int N1, int N2, int dt) {
-  return (dt == ELEM_BF16 ? rows >= 1 : rows >= 4096) && N1 % kblk_of(dt) == 0 && N1 >= 128 && wgrad_block_n(N2) != 0;
+  return (dt == ELEM_BF16 ? rows >= 1 : rows >= 4096) && N1 % kblk_of(dt) == 0 && N1 >= 64 && wgrad_block_n(N2) != 0;
 }
 size_t tc_bwd_weight_ws_floats(int rows, int N1, int N2) {
-  if (wgrad_block_n(N2) == 0 || N1 < 128) return 0;
+  if (wgrad_block_n(N2) == 0 || N1 < 64) return 0;
   return (size_t)wgrad_splits(rows, N1, N2) * N1 * N2;
 }
 
@@ -839,6 +870,7 @@ static int tc_bwd_weight_t(const void* dY, const void* X, int rows, int N1, int 
   const int rows_per_split = cdiv(cdiv(rows, splits), KR) * KR;
   const int nsplit = cdiv(rows, rows_per_split);
   if (wgrad_block_n(N2) == 256) ADVMIL_TRY((launch_wgrad<T, 256>((const T*)dY, (const T*)X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
+  else if (wgrad_block_n(N2) == 64) ADVMIL_TRY((launch_wgrad<T, 64>((const T*)dY, (const T*)X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
   else ADVMIL_TRY((launch_wgrad<T, 128>((const T*)dY, (const T*)X, rows, N1, N2, rows_per_split, nsplit, ws, st)));
   return splitk_reduce(ws, nsplit, (size_t)N1 * N2, dW, accumulate, st);
 }

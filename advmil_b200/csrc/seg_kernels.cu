@@ -101,15 +101,23 @@ int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumul
 }
 
 template <typename T>
-__global__ void apply_dropout_kernel(const T* __restrict__ src, size_t nvec, Drop drop, T* __restrict__ dst) {
+__global__ void apply_dropout_kernel(const T* __restrict__ src, size_t nvec, int vec_per_row, Drop drop, T* __restrict__ dst) {
   constexpr int VEC = VecN<T>::N;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < nvec; i += stride) {
     float v[VEC];
     ldv(src + i * VEC, v);
+    const uint32_t row = (uint32_t)(i / vec_per_row), col = (uint32_t)(i % vec_per_row) * VEC;
+    if (drop.active) {
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) v[e] *= drop.scale(i * VEC + e);
+      for (int e = 0; e < VEC; e += 2) {
+        bool k0, k1;
+        drop.keep2(row, col + e, k0, k1);
+        v[e] = k0 ? v[e] * drop.inv_keep : 0.f;
+        v[e + 1] = k1 ? v[e + 1] * drop.inv_keep : 0.f;
+      }
+    }
     stv(dst + i * VEC, v);
   }
 }
@@ -120,7 +128,7 @@ static int apply_dropout_t(const T* src, int rows, int width, const Drop& drop, 
   const size_t nvec = (size_t)rows * width / VEC;
   if (nvec == 0) return ADVMIL_OK;
   const int grid = (int)min((size_t)148 * 16, (nvec + 255) / 256);
-  apply_dropout_kernel<T><<<grid, 256, 0, st>>>(src, nvec, drop, dst);
+  apply_dropout_kernel<T><<<grid, 256, 0, st>>>(src, nvec, width / VEC, drop, dst);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -371,43 +379,70 @@ __global__ void bag_dot_kernel(const float* __restrict__ a, const float* __restr
   if (threadIdx.x == 0) out[bag] = acc;
 }
 
-// Phase 1: one warp per row computes ds.  Phase 2: thread (rg, pv) owns VEC consecutive gate-column pairs of every RGN-th
-// row: 16-byte loads of the tanh / sigmoid vectors, 16-byte stores of dA / dB.  Also accumulates dwc and the column sums
-// of dAB (the packed gate-bias gradient), so no separate pass over dAB is needed.
+// pass 1: ds[row] = w[row] (dz[bag] . v[row] - dz[bag] . z[bag]); one warp per row, 4 rows in flight per warp
 template <typename T>
-__global__ void __launch_bounds__(512) pool_gate_bwd_kernel(
-    const T* __restrict__ v, const float* __restrict__ w, const float* __restrict__ dz,
-    const float* __restrict__ gz, const T* __restrict__ ab, const float* __restrict__ wc,
-    const int32_t* __restrict__ offsets, int rows, int bags, int L, int D, int abw, int RGN, Drop da, Drop db,
-    T* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
+__global__ void __launch_bounds__(256) pool_ds_kernel(const T* __restrict__ v, const float* __restrict__ w,
+                                                      const float* __restrict__ dz, const float* __restrict__ gz,
+                                                      const int32_t* __restrict__ offsets, int rows, int bags, int L,
+                                                      float* __restrict__ ds) {
+  constexpr int VEC = VecN<T>::N;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * ROWS_PER_CTA + wid * (ROWS_PER_CTA / 8);
+  const int rend = min(rows, row0 + ROWS_PER_CTA / 8);
+  if (row0 >= rend) return;
+  int cur = bag_of_row(offsets, bags, row0);       // one search per warp, then a monotone walk over its 16 rows
+  int cur_end = offsets[cur + 1];
+  for (int rb = row0; rb < rend; rb += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int bag[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (rb + u < rend) { while (rb + u >= cur_end) { ++cur; cur_end = offsets[cur + 1]; } }
+      bag[u] = cur;
+    }
+    for (int c = lane * VEC; c < L; c += 32 * VEC) {
+      float x[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rb + u < rend) ldv(v + (size_t)(rb + u) * L + c, x[u]);
+        else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) x[u][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* dzr = dz + (size_t)bag[u] * L + c;
+#pragma unroll
+        for (int q4 = 0; q4 < VEC / 4; ++q4) {
+          const float4 g = *reinterpret_cast<const float4*>(dzr + 4 * q4);
+          acc[u] += x[u][4 * q4] * g.x + x[u][4 * q4 + 1] * g.y + x[u][4 * q4 + 2] * g.z + x[u][4 * q4 + 3] * g.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(acc[u]);
+      if (lane == 0 && rb + u < rend) ds[rb + u] = w[rb + u] * (t - gz[bag[u]]);
+    }
+  }
+}
+
+// pass 2 (pure stream): thread (rg, pv) owns VEC consecutive gate-column pairs of every RGN-th row of a 128-row chunk:
+// 16-byte loads of the tanh / sigmoid vectors, 16-byte stores of dA / dB.  Also accumulates dwc and the column sums of
+// dAB (the packed gate-bias gradient), so no separate pass over dAB is needed.
+template <typename T>
+__global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
+    const float* __restrict__ ds_g, const T* __restrict__ ab, const float* __restrict__ wc, int rows, int D, int abw, int RGN,
+    Drop da, Drop db, T* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
   constexpr int VEC = VecN<T>::N;
   extern __shared__ float red3[];              // [RGN][3][npairs]
   __shared__ float ds_s[ROWS_PER_CTA];
   __shared__ float red[33];
   const int row0 = blockIdx.x * ROWS_PER_CTA;
   const int nrows = min(ROWS_PER_CTA, rows - row0);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  // phase 1: g = dz[bag] . v[row]
-  for (int r = wid; r < nrows; r += nw) {
-    const int row = row0 + r;
-    const int bag = bag_of_row(offsets, bags, row);
-    const T* vr = v + (size_t)row * L;
-    const float* dzr = dz + (size_t)bag * L;
-    float acc = 0.f;
-    for (int c = lane * VEC; c < L; c += 32 * VEC) {
-      float x[VEC];
-      ldv(vr + c, x);
-#pragma unroll
-      for (int q4 = 0; q4 < VEC / 4; ++q4) {
-        const float4 g = *reinterpret_cast<const float4*>(dzr + c + 4 * q4);
-        acc += x[4 * q4] * g.x + x[4 * q4 + 1] * g.y + x[4 * q4 + 2] * g.z + x[4 * q4 + 3] * g.w;
-      }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) ds_s[r] = w[row] * (acc - gz[bag]);
-  }
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x) ds_s[r] = ds_g[row0 + r];
   __syncthreads();
-  // phase 2
   const int npairs = abw >> 1, TPR = npairs / VEC;
   const int rg = threadIdx.x / TPR, pv = threadIdx.x % TPR;
   const bool tr = da.active != 0;
@@ -427,7 +462,11 @@ __global__ void __launch_bounds__(512) pool_gate_bwd_kernel(
       for (int e = 0; e < VEC; ++e) {
         const bool valid = q0 + e < D;
         float sa = 1.f, sb = 1.f;
-        if (tr && valid) { sa = da.keep(row * D + q0 + e) ? da.inv_keep : 0.f; sb = db.keep(row * D + q0 + e) ? db.inv_keep : 0.f; }
+        if (tr && valid) {
+          bool ka, kb;
+          gate_keep(da, db, (uint32_t)row, (uint32_t)(q0 + e), ka, kb);
+          sa = ka ? da.inv_keep : 0.f; sb = kb ? db.inv_keep : 0.f;
+        }
         const float av = valid ? a[e] : 0.f, bv = valid ? b[e] : 0.f;
         const float ad = av * sa, bd = bv * sb, du = ds * wcj[e];
         oa[e] = du * bd * sa * (1.f - av * av);
@@ -438,19 +477,21 @@ __global__ void __launch_bounds__(512) pool_gate_bwd_kernel(
       stv(dAB + row * abw + ca, oa);
       stv(dAB + row * abw + ca + 64, ob);
     }
+    // element e of thread pv at [e][pv]-style offsets: consecutive lanes hit consecutive banks
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      red3[((size_t)rg * 3 + 0) * npairs + q0 + e] = dwc[e];
-      red3[((size_t)rg * 3 + 1) * npairs + q0 + e] = sa_sum[e];
-      red3[((size_t)rg * 3 + 2) * npairs + q0 + e] = sb_sum[e];
+      red3[((size_t)rg * 3 + 0) * npairs + e * TPR + pv] = dwc[e];
+      red3[((size_t)rg * 3 + 1) * npairs + e * TPR + pv] = sa_sum[e];
+      red3[((size_t)rg * 3 + 2) * npairs + e * TPR + pv] = sb_sum[e];
     }
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < npairs; q += blockDim.x) {
+  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {   // i = e * TPR + pv  ->  pair q = pv * VEC + e
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
     for (int g = 0; g < RGN; ++g) {
-      t0 += red3[((size_t)g * 3 + 0) * npairs + q]; t1 += red3[((size_t)g * 3 + 1) * npairs + q]; t2 += red3[((size_t)g * 3 + 2) * npairs + q];
+      t0 += red3[((size_t)g * 3 + 0) * npairs + i]; t1 += red3[((size_t)g * 3 + 1) * npairs + i]; t2 += red3[((size_t)g * 3 + 2) * npairs + i];
     }
+    const int q = (i % TPR) * VEC + i / TPR;
     const int ca = gate_col_a(q);
     if (q < D) part[(size_t)blockIdx.x * (D + 1) + q] = t0;
     if (part_b) { part_b[(size_t)blockIdx.x * abw + ca] = t1; part_b[(size_t)blockIdx.x * abw + ca + 64] = t2; }
@@ -472,20 +513,18 @@ static int pool_gate_bwd_t(const T* v, const float* w, const float* z, const flo
   float* gz = ws;
   float* part = ws + align_up((size_t)bags, 64);
   float* part_b = dbp ? part + align_up((size_t)chunks * (D + 1), 64) : nullptr;
+  float* ds = part + align_up((size_t)chunks * (D + 1), 64) + (size_t)chunks * abw;
   bag_dot_kernel<<<bags, 128, 0, st>>>(dz, z, L, gz);
   ADVMIL_CHECK_LAUNCH();
+  pool_ds_kernel<T><<<chunks, 256, 0, st>>>(v, w, dz, gz, offsets, rows, bags, L, ds);
+  ADVMIL_CHECK_LAUNCH();
   const int npairs = abw / 2, TPR = npairs / VEC;
-  ADVMIL_REQUIRE(TPR >= 1 && TPR <= 512, "pool_gate_bwd: gate width %d unsupported", abw);
-  const int RGN = max(1, min(384 / TPR, 16));
-  const int threads = max(128, ((TPR * RGN + 31) / 32) * 32);
+  ADVMIL_REQUIRE(TPR >= 1 && TPR <= 256, "pool_gate_bwd: gate width %d unsupported", abw);
+  const int RGN = max(1, min(192 / TPR, 16));
+  const int threads = max(64, ((TPR * RGN + 31) / 32) * 32);
   const size_t smem = (size_t)RGN * 3 * npairs * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(pool_gate_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
-  ADVMIL_REQUIRE(smem <= 96 * 1024, "pool_gate_bwd: gate width %d needs too much shared memory", abw);
-  pool_gate_bwd_kernel<T><<<chunks, threads, smem, st>>>(v, w, dz, gz, ab, wc, offsets, rows, bags, L, D, abw, RGN, da, db, dAB, part, part_b);
+  ADVMIL_REQUIRE(smem <= 48 * 1024, "pool_gate_bwd: gate width %d needs too much shared memory", abw);
+  pool_gate_bwd_kernel<T><<<chunks, threads, smem, st>>>(ds, ab, wc, rows, D, abw, RGN, da, db, dAB, part, part_b);
   ADVMIL_CHECK_LAUNCH();
   reduce_rows_kernel<<<cdiv(D, 32), dim3(32, 32), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
   ADVMIL_CHECK_LAUNCH();
@@ -588,26 +627,29 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
 // d == 128: 8 lanes per row (16 columns per lane as 16-byte vectors interleaved across the 8 lanes so that every load
 // instruction covers 128 contiguous bytes per row), 4 rows per warp, two such groups in flight
 template <typename T>
-__global__ void __launch_bounds__(256) ln_pool_bwd128_kernel(
+__global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
     const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ gamma,
     const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y, float* __restrict__ part) {
   constexpr int VEC = VecN<T>::N, NV = 16 / VEC;          // vectors per lane
-  __shared__ float sm[8 * 3 * 128];
+  __shared__ float sm[4 * 3 * 128];
+  __shared__ __align__(16) float gb_s[2 * 128];           // gamma | beta, permuted so that my 16 columns are contiguous
   const int row0 = blockIdx.x * ROWS_PER_CTA;
   const int nrows = min(ROWS_PER_CTA, rows - row0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane & 7, slot = lane >> 3;             // column group, row slot within the warp
   // column of element (k, e): k * 8 * VEC + sub * VEC + e
-  float g[16], be[16], pg[16], pb[16], pbias[16];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {   // i = sub' * 16 + k * VEC + e
+    const int sb = i >> 4, k = (i & 15) / VEC, e = (i & 15) % VEC;
+    const int c = k * 8 * VEC + sb * VEC + e;
+    gb_s[i] = gamma[c]; gb_s[128 + i] = beta[c];
+  }
+  __syncthreads();
+  float pg[16], pb[16], pbias[16];
 #pragma unroll
-  for (int k = 0; k < NV; ++k)
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int c = k * 8 * VEC + sub * VEC + e;
-      g[k * VEC + e] = gamma[c]; be[k * VEC + e] = beta[c];
-      pg[k * VEC + e] = 0.f; pb[k * VEC + e] = 0.f; pbias[k * VEC + e] = 0.f;
-    }
-  for (int rb = wid * 8; rb < nrows; rb += 64) {
+  for (int i = 0; i < 16; ++i) { pg[i] = 0.f; pb[i] = 0.f; pbias[i] = 0.f; }
+  const float* g = gb_s + sub * 16;
+  const float* be = gb_s + 128 + sub * 16;
+  for (int rb = wid * 8; rb < nrows; rb += 32) {
     float y[2][16], ge[16];
     bool ok[2];
     // rb is a multiple of 8: the 8 rows of this warp iteration lie in ONE 16-row region
@@ -693,7 +735,7 @@ __global__ void __launch_bounds__(256) ln_pool_bwd128_kernel(
   for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
     float t = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += sm[wv * 3 * 128 + i];
+    for (int wv = 0; wv < 4; ++wv) t += sm[wv * 3 * 128 + i];
     part[(size_t)blockIdx.x * 3 * 128 + i] = t;
   }
 }
@@ -706,9 +748,9 @@ int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* gamma, const
   int chunks = row_chunks(rows);
   size_t smem = (size_t)8 * 3 * d * sizeof(float);
   if (d == 128 && dt == ELEM_BF16)
-    ln_pool_bwd128_kernel<bf16><<<chunks, 256, 0, st>>>((const bf16*)y_pre, d_emb, gamma, beta, rows, eps, (bf16*)d_y, ws);
+    ln_pool_bwd128_kernel<bf16><<<chunks, 128, 0, st>>>((const bf16*)y_pre, d_emb, gamma, beta, rows, eps, (bf16*)d_y, ws);
   else if (d == 128)
-    ln_pool_bwd128_kernel<float><<<chunks, 256, 0, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, eps, (float*)d_y, ws);
+    ln_pool_bwd128_kernel<float><<<chunks, 128, 0, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, eps, (float*)d_y, ws);
   else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, d, eps, (float*)d_y, ws);
   else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();

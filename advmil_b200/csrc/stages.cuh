@@ -48,7 +48,8 @@ int pool_gate_bwd(const void* v, const float* w, const float* z, const float* dz
                   float* dwc, float* dbc, float* dbp /* packed gate-bias grad [abw] or null */, int accumulate,
                   float* ws /* >= pool_gate_ws_floats */, int dt, cudaStream_t st);
 inline size_t pool_gate_ws_floats(int rows, int bags, int D) {
-  return align_up((size_t)bags, 64) + align_up((size_t)row_chunks(rows) * (D + 1), 64) + (size_t)row_chunks(rows) * gate_width(D) + 64;
+  return align_up((size_t)bags, 64) + align_up((size_t)row_chunks(rows) * (D + 1), 64) + (size_t)row_chunks(rows) * gate_width(D) +
+         align_up((size_t)rows, 64) + 64;
 }
 // LayerNorm + ReLU + region-mean backward per row; partials of dgamma/dbeta/dbias reduced into the outputs
 int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,

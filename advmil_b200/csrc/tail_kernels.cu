@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
   if (p.Wrho) {
     for (int i = wid; i < o; i += nw) {
       float v = warp_dot(p.Wrho + (size_t)i * h, zs, h, lane);
-      if (lane == 0) Hs[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale((uint64_t)b * o + i);
+      if (lane == 0) Hs[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale(b, i);
     }
   } else {
     for (int c = threadIdx.x; c < o; c += blockDim.x) Hs[c] = zs[c];
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
   if (p.W0 == nullptr) return;  // backbone-only mode (ABMIL.forward without the Generator head)
   for (int j = wid; j < hid; j += nw) {
     float v = warp_dot(p.W0 + (size_t)j * in0, Hs, in0, lane);
-    if (lane == 0) H1s[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale((uint64_t)b * hid + j);
+    if (lane == 0) H1s[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale(b, j);
   }
   const int in1 = hid * (1 + p.noise1);
   if (p.noise1)
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(512) rlip_tail_fwd_kernel(AdvmilDiscParams p, 
   for (int j = wid; j < dh; j += nw) {
     float v = warp_dot(p.F2a_w + (size_t)j * d, bv, d, lane);
     if (lane == 0) {
-      v = fmaxf(v + p.F2a_b[j], 0.f) * dfc2.scale((uint64_t)b * dh + j);
+      v = fmaxf(v + p.F2a_b[j], 0.f) * dfc2.scale(b, j);
       g1s[j] = v;
       g1[(size_t)b * dh + j] = v;
     }
@@ -524,6 +524,7 @@ using namespace advmil;
 extern "C" int advmil_disc_loss(const float* f_real, const float* f_fake, const uint8_t* real_mask, int32_t bags,
                                 int32_t which, float n_real, float n_fake, float* loss_out, float* d_real, float* d_fake,
                                 void* stream) {
+  ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   ADVMIL_REQUIRE(bags > 0 && which >= 0 && which <= 2 && n_fake > 0.f, "disc_loss: bad arguments");
   disc_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(f_real, f_fake, real_mask, bags, which, n_real, n_fake, loss_out, d_real, d_fake);
   ADVMIL_CHECK_LAUNCH();
@@ -534,6 +535,7 @@ extern "C" int advmil_gen_loss(const float* pred, const float* t, const float* e
                                const float* f_fake, int32_t bags, float n_visible, float n_fake, float coef_gan,
                                float alpha, float gamma, int32_t norm, float* losses, float* d_pred, float* d_fake,
                                void* stream) {
+  ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   ADVMIL_REQUIRE(bags > 0 && n_fake > 0.f && (norm == 0 || norm == 1), "gen_loss: bad arguments");
   gen_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, t, e, visible, f_fake, bags, n_visible, n_fake, coef_gan, alpha, gamma, norm, losses, d_pred, d_fake);
   ADVMIL_CHECK_LAUNCH();
@@ -543,6 +545,7 @@ extern "C" int advmil_gen_loss(const float* pred, const float* t, const float* e
 extern "C" int advmil_adam_step(float* param, const float* grad, float* m, float* v, const uint8_t* wd_mask, int64_t n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, float l1_coef,
                                 int32_t step, float grad_scale, void* stream) {
+  ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   ADVMIL_REQUIRE(n >= 0 && step >= 1, "adam_step: bad arguments");
   if (n == 0) return ADVMIL_OK;
   double bc1 = 1.0 - pow((double)beta1, (double)step);
@@ -555,6 +558,7 @@ extern "C" int advmil_adam_step(float* param, const float* grad, float* m, float
 }
 
 extern "C" int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream) {
+  ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   if (n <= 0) return ADVMIL_OK;
   abs_sum_kernel<<<(int)min((int64_t)148, (n + 2047) / 2048), 256, 0, (cudaStream_t)stream>>>(p, n, out);
   ADVMIL_CHECK_LAUNCH();
@@ -605,6 +609,28 @@ extern "C" int advmil_segment_mean_by_id_bwd(const float* d_out, const void* v, 
     seg_mean_id_bwd_kernel<bf16><<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, (const bf16*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (bf16*)d_v);
   else
     seg_mean_id_bwd_kernel<float><<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, (const float*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (float*)d_v);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+__global__ void dropout_mask_kernel(Drop d, Drop d2, int role, int rows, int width, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * width) return;
+  const uint32_t row = (uint32_t)(i / width), col = (uint32_t)(i % width);
+  bool k;
+  if (role == 0) k = d.keep(row, col);
+  else { bool ka, kb; gate_keep(d, d2, row, col, ka, kb); k = role == 1 ? ka : kb; }
+  out[i] = k ? 1 : 0;
+}
+extern "C" int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t rows, int32_t width, uint8_t* out, void* stream) {
+  ADVMIL_REQUIRE(out && rows >= 0 && width > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  const bool gate_a = site == SITE_A || site == SITE_GA, gate_b = site == SITE_B || site == SITE_GS;
+  const int role = gate_a ? 1 : gate_b ? 2 : 0;
+  Drop d = Drop::make(nullptr, seed, gate_b ? site - 1 : site, p, 1, width);   // the pair is keyed by the tanh site
+  Drop d2 = Drop::make(nullptr, seed, gate_b ? site : site + 1, p, 1, width);
+  const size_t n = (size_t)rows * width;
+  if (n == 0) return ADVMIL_OK;
+  dropout_mask_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d, d2, role, rows, width, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

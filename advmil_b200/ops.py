@@ -324,13 +324,13 @@ def _head_struct(acts, ws) -> HeadActs:
     m = acts["masks"]
     for k in ("fc1", "ga", "gs", "fc2"):
         setattr(a, "mask_" + k, _ptr(m.get(k)))
-    a.seed, a.train = acts["seed"], int(acts["train"])
+    a.seed, a.train, a.precision = acts["seed"], int(acts["train"]), int(acts.get("precision", FP32))
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     return a
 
 
 def disc_head_forward(cfg: DiscConfig, params, bags: PackedBags, emb: torch.Tensor, t: torch.Tensor,
-                      train: bool = False, seed: int = 0, masks=None):
+                      train: bool = False, seed: int = 0, masks=None, precision: int = FP32):
     lib = _lib.load()
     dev = bags.x.device
     R, nb, d, dh = bags.rows // 16, bags.bags, cfg.d, cfg.d // 2
@@ -340,7 +340,8 @@ def disc_head_forward(cfg: DiscConfig, params, bags: PackedBags, emb: torch.Tens
             "ab": torch.empty(R, abw, **f), "rep": torch.empty(R, **f), "attn": torch.empty(R, **f),
             "bagv": torch.empty(nb, d, **f), "fbar": torch.empty(nb, d, **f), "g1": torch.empty(nb, dh, **f),
             "hx": torch.empty(nb, d, **f), "u1": torch.empty(nb, cfg.t1, **f), "ht": torch.empty(nb, cfg.t2, **f),
-            "out": torch.empty(nb, **f), "masks": masks or {}, "seed": int(seed), "train": bool(train)}
+            "out": torch.empty(nb, **f), "masks": masks or {}, "seed": int(seed), "train": bool(train),
+            "precision": int(precision)}
     p = cfg.c(params)
     ws = _ws(lib.advmil_disc_workspace_bytes(C.byref(p), bags.rows, nb, 0), dev)
     a = _head_struct(acts, ws)
@@ -370,7 +371,7 @@ class DiscriminatorFn(torch.autograd.Function):
     def forward(ctx, cfg, bags, t, train, seed, masks, precision, *params):
         need_param_grads = any(p is not None and p.requires_grad for p in params)
         emb = disc_embed_forward(cfg, params, bags, precision, save=need_param_grads)
-        head = disc_head_forward(cfg, params, bags, emb["emb"], t.detach(), train, seed, masks)
+        head = disc_head_forward(cfg, params, bags, emb["emb"], t.detach(), train, seed, masks, precision)
         ctx.cfg, ctx.bags, ctx.emb, ctx.head, ctx.params = cfg, bags, emb, head, params
         ctx.need_param_grads = need_param_grads
         ctx.t_shape = t.shape
@@ -482,6 +483,18 @@ def region_of_rows(rows: int, scale: int = 4, device="cuda") -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(rows, 3, dtype=torch.int32, device=device)
     check(lib.advmil_region_of_rows(rows, scale, out.data_ptr(), _stream()), "advmil_region_of_rows")
+    return out
+
+
+DROP_SITES = {"h": 1, "a": 2, "b": 3, "rho": 4, "mlp0": 5, "fc1": 11, "ga": 12, "gs": 13, "fc2": 14}
+
+
+def dropout_mask(seed: int, site: str, p: float, rows: int, width: int, device="cuda") -> torch.Tensor:
+    """The uint8 keep mask the kernels generate on the fly for `site` under `seed` (test / debugging aid)."""
+    lib = _lib.load()
+    out = torch.empty(rows, width, dtype=torch.uint8, device=device)
+    check(lib.advmil_dropout_mask(int(seed), DROP_SITES[site], float(p), rows, width, out.data_ptr(), _stream()),
+          "advmil_dropout_mask")
     return out
 
 

@@ -132,11 +132,11 @@ class AdvStep:
         d_real = torch.empty(nb, **f32)
         d_fake = torch.empty(nb, **f32)
         hf = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb["emb"], pred_d, train=True,
-                                   seed=next_dropout_seed(), masks=masks_d_fake)
+                                   seed=next_dropout_seed(), masks=masks_d_fake, precision=self.precision)
         hr = None
         if n_real > 0:
             hr = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb["emb"], t, train=True,
-                                       seed=next_dropout_seed(), masks=masks_d_real)
+                                       seed=next_dropout_seed(), masks=masks_d_real, precision=self.precision)
         check(lib.advmil_disc_loss(None if hr is None else hr["out"].data_ptr(), hf["out"].data_ptr(),
                                    real_mask.data_ptr(), nb, self.loss_d, n_real, n_fake, losses.data_ptr(),
                                    d_real.data_ptr(), d_fake.data_ptr(), st), "advmil_disc_loss")
@@ -152,7 +152,7 @@ class AdvStep:
                                    masks=masks_g, precision=self.precision, save=True, h_eval=ga["h"])
         pred_g = gt["pred"]
         emb2 = ops.disc_embed_forward(self.dcfg, self.dparams, bags, self.precision, save=False)
-        hg = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb2["emb"], pred_g, train=False)
+        hg = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb2["emb"], pred_g, train=False, precision=self.precision)
         d_pred = torch.empty(nb, **f32)
         d_fake_g = torch.empty(nb, **f32)
         norm, alpha, gamma = self.recon

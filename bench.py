@@ -264,8 +264,10 @@ def main():
         time.sleep(0.05)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    th0 = time.perf_counter()
     for i in range(args.steps):
         out = one_step(args.warmup + i)
+    host_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # CPU time to ISSUE one step (no sync inside the loop)
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -323,7 +325,8 @@ def main():
         if tag in BYTES_PER_ROW:
             ent["gbs"] = BYTES_PER_ROW[tag] * rows_per_launch / (avg_ms * 1e-3) / 1e9
         kern[tag] = ent
-    top = max(kern, key=lambda k: kern[k]["share_of_step"]) if kern else None
+    rated = [k for k in kern if k in FLOP_PER_ROW or k in BYTES_PER_ROW]      # composites (latency-bound) have no roofline
+    top = max(rated, key=lambda k: kern[k]["share_of_step"]) if rated else None
     roof = None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
@@ -361,7 +364,7 @@ def main():
                              "steps) larger than the 126 MB L2; no flush",
                        "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches, "host_issue_ms_per_step": host_ms, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
             "losses_last_step": losses,
         }
         print(json.dumps(line), flush=True)

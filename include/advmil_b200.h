@@ -157,6 +157,8 @@ typedef struct AdvmilHeadActs {       /* K7+K8: region MLP, GAPool, bag MLP, tim
   const uint8_t *mask_fc1, *mask_ga, *mask_gs, *mask_fc2;
   uint64_t seed;
   int32_t train;
+  int32_t precision;  /* AdvmilPrecision of the step: FP32 = exact FFMA; any other mode runs the region-level contractions
+                         (all tensors here are fp32) on tcgen05 kind::tf32 */
   void* workspace; size_t workspace_bytes;
 } AdvmilHeadActs;
 
@@ -173,7 +175,10 @@ ADVMIL_API int64_t advmil_launch_count(int reset);
 typedef enum AdvmilProfTag {
   ADVMIL_PROF_PROJ = 0, ADVMIL_PROF_GATE = 1, ADVMIL_PROF_POOL = 2, ADVMIL_PROF_EMBED = 3, ADVMIL_PROF_POOL_BWD = 4,
   ADVMIL_PROF_BWD_DATA = 5, ADVMIL_PROF_BWD_W_GATE = 6, ADVMIL_PROF_BWD_W_PROJ = 7, ADVMIL_PROF_LN_BWD = 8,
-  ADVMIL_PROF_BWD_W_EMBED = 9, ADVMIL_PROF_COLSUM = 10, ADVMIL_PROF_DROPOUT = 11, ADVMIL_PROF_NTAGS = 12
+  ADVMIL_PROF_BWD_W_EMBED = 9, ADVMIL_PROF_COLSUM = 10, ADVMIL_PROF_DROPOUT = 11,
+  /* composites of the region-level / bag-level (latency-bound) work, reported in microseconds, not as roofline fractions */
+  ADVMIL_PROF_HEAD_FWD = 12, ADVMIL_PROF_HEAD_BWD = 13, ADVMIL_PROF_GEN_TAIL = 14, ADVMIL_PROF_LOSS_OPT = 15,
+  ADVMIL_PROF_NTAGS = 16
 } AdvmilProfTag;
 ADVMIL_API int advmil_profile_enable(int on);
 ADVMIL_API int advmil_profile_read(double* ms, int64_t* counts, int32_t ntags);
@@ -244,6 +249,12 @@ ADVMIL_API int advmil_seg_softmax_pool_fwd(const float* s, const void* v /*elem*
                                 const int32_t* offsets_host, int32_t rows, int32_t bags, int32_t width, float* w, float* z,
                                 float* mean, void* workspace, size_t workspace_bytes, void* stream);
 ADVMIL_API size_t advmil_seg_pool_workspace_bytes(int32_t rows, int32_t bags, int32_t width);
+
+/* Materialises the keep mask (uint8, 1 = keep) that the kernels generate on the fly for one dropout site when no mask is
+ * injected: out[rows, width].  site: 1 h, 2 gate tanh, 3 gate sigmoid, 4 rho, 5 MLPs.0 (generator); 11 fc1, 12 GAPool
+ * tanh, 13 GAPool sigmoid, 14 fc2 (discriminator).  The two gate sites of a row share one draw keyed by the tanh site.
+ * Test / debugging aid: feeding these masks back through the mask_* pointers must reproduce the seeded run exactly. */
+ADVMIL_API int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t rows, int32_t width, uint8_t* out, void* stream);
 
 /* fp32 -> bf16 (round to nearest even) of n contiguous elements: how fp32 features enter the ADVMIL_BF16 mode when the
  * loader did not already store them as bf16 */

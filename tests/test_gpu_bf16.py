@@ -127,10 +127,11 @@ def test_bf16_mode_generator_and_discriminator_vs_oracle(N, train):
         #     bf16 rounding of zero, each flip adds/removes one full term of a sum of random-sign terms -- ANY bf16
         #     evaluation shows this (the emulating oracle below reproduces the same 3-9e-2) -- so they get 1e-1 here and
         #     the tight check in (2).
-        # (2) against the oracle emulating the bf16 storage points (oracle.bf16_storage): 4e-3, every tensor.
+        # (2) against the oracle emulating the bf16 storage points (oracle.bf16_storage): 1e-2, every tensor (the region-level
+        #     contractions run on tf32 tensor cores in this mode, which the emulation does not model).
         FLIP = ("backbone.attention_net.0.weight", "net_pair_one.embedding.conv.weight", "backbone.attention_net.0.bias",
                 "net_pair_one.embedding.conv.bias", "net_pair_one.embedding.norm.weight", "net_pair_one.embedding.norm.bias")
-        for emulate, tol in ((False, TOL), (True, 4e-3)):
+        for emulate, tol in ((False, TOL), (True, 1e-2)):
             rG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
             rD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
             if emulate:

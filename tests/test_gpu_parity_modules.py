@@ -184,3 +184,59 @@ def test_cluster_generator_vs_golden_and_oracle(name):
     pred.sum().backward()
     assert_close(pred.detach().cpu(), g["pred"], RTOL, "pred")
     _cmp_grads_golden(G, g)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_in_kernel_dropout_equals_injected_masks_of_the_same_bits(monkeypatch, precision):
+    """Train-mode forward/backward with the in-kernel counter-based generator (no masks injected) == the oracle fed with
+    the masks that advmil_dropout_mask materialises for the same seeds: forward and backward regenerate identical bits,
+    every site scales by 1/(1-p), and the keep rates are right."""
+    import advmil_b200
+    from advmil_b200 import ops
+    from advmil_b200.model import GANSurv
+    dims, N = (1024, 384, 384), 1920
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(*dims), 11), O.synth_state_dict(O.D_SHAPES(), 12)
+    G, D = build_G(dims).train(), build_D().train()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    seeds = iter([0x1234567, 0x7654321])
+    monkeypatch.setattr(GANSurv, "next_dropout_seed", lambda: next(seeds))
+    x = O.synth_bag(N, 13)
+    noise = torch.tensor(np.random.default_rng(14).uniform(size=(1, 192)), dtype=torch.float32)
+    advmil_b200.set_precision(precision)
+    try:
+        bags = ops.PackedBags.from_single(x.cuda())
+        pred = G.forward_packed(bags, noise=[None, noise.cuda()])
+        f = D.forward_packed(bags, pred)
+        (f.sum() + pred.sum()).backward()
+    finally:
+        advmil_b200.set_precision("fp32")
+    R = N // 16
+    gm = {k: ops.dropout_mask(0x1234567, k, p, r, w).cpu().float()
+          for k, p, r, w in (("h", .25, N, 384), ("a", .25, N, 384), ("b", .25, N, 384), ("rho", .25, 1, 384), ("mlp0", .6, 1, 192))}
+    dm = {k: ops.dropout_mask(0x7654321, k, .25, r, w).cpu().float()
+          for k, r, w in (("fc1", R, 64), ("ga", R, 128), ("gs", R, 128), ("fc2", 1, 64))}
+    for k in ("h", "a", "b"):
+        assert abs(float(gm[k].mean()) - 0.75) < 3e-3, (k, float(gm[k].mean()))
+    assert abs(float((gm["a"] * gm["b"]).mean()) - 0.5625) < 3e-3          # the two gate sites are independent
+    assert abs(float((gm["h"][:, 0::2] * gm["h"][:, 1::2]).mean()) - 0.5625) < 3e-3   # ... and so are paired columns
+    rG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
+    rD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
+    tol = 1e-5 if precision == "fp32" else 1e-2
+    if precision == "bf16":
+        with O.bf16_storage():
+            og = O.generator_forward(rG, x, [None, noise], (0, 1), gm)
+            of = O.prjdisc_forward(rD, x, og["pred"], dm)["out"]
+            (of.sum() + og["pred"].sum()).backward()
+    else:
+        og = O.generator_forward(rG, x, [None, noise], (0, 1), gm)
+        of = O.prjdisc_forward(rD, x, og["pred"], dm)["out"]
+        (of.sum() + og["pred"].sum()).backward()
+    assert_close(pred.detach().cpu(), og["pred"].detach(), tol, "pred")
+    assert_close(f.detach().cpu(), of.detach(), tol, "f", atol_scale=0.1)
+    gmax = max(float(v.grad.abs().max()) for v in list(rG.values()) + list(rD.values()) if v.grad is not None)
+    for mod, ref in ((G, rG), (D, rD)):
+        for k, p in mod.named_parameters():
+            if ref[k].grad is None or k.endswith(("attention_c.bias", "pool.fc2.bias")):
+                continue
+            assert_close(p.grad.cpu(), ref[k].grad, tol, "grad " + k, atol=2e-5 * gmax if precision == "bf16" else 2.0 ** -22 * gmax)
