@@ -68,7 +68,21 @@ class HeadActs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
-ABI_STRUCTS = [Bags, GenParams, GenGrads, GenActs, DiscParams, DiscGrads, EmbedActs, HeadActs]
+class StepArgs(C.Structure):
+    _fields_ = [("gen", C.POINTER(GenParams)), ("disc", C.POINTER(DiscParams)), ("gen_grads", C.POINTER(GenGrads)),
+                ("disc_grads", C.POINTER(DiscGrads)), ("bags", C.POINTER(Bags)),
+                ("t", c_fp), ("e", c_fp), ("visible", c_u8p), ("noise_d", c_fp), ("noise_g", c_fp),
+                ("g_mask_h", c_u8p), ("g_mask_a", c_u8p), ("g_mask_b", c_u8p), ("g_mask_rho", c_u8p), ("g_mask_mlp0", c_u8p),
+                ("d_mask_fc1", c_u8p), ("d_mask_ga", c_u8p), ("d_mask_gs", c_u8p), ("d_mask_fc2", c_u8p),
+                ("seed_d", C.c_uint64), ("seed_g", C.c_uint64),
+                ("n_real", C.c_float), ("n_fake", C.c_float), ("n_visible", C.c_float), ("loss_d", C.c_int32),
+                ("coef_gan", C.c_float), ("recon_alpha", C.c_float), ("recon_gamma", C.c_float), ("recon_norm", C.c_int32),
+                ("precision", C.c_int32),
+                ("losses", c_fp), ("pred_d", c_fp), ("f_fake_d", c_fp), ("real_mask", c_u8p), ("pred_g", c_fp), ("f_fake_g", c_fp),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+ABI_STRUCTS = [Bags, GenParams, GenGrads, GenActs, DiscParams, DiscGrads, EmbedActs, HeadActs, StepArgs]
 
 # every symbol include/advmil_b200.h declares: name -> (restype, argtypes)
 _i32, _i64, _f, _vp, _sz, _u64 = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t, C.c_uint64
@@ -101,6 +115,9 @@ SYMBOLS = {
     "advmil_seg_softmax_pool_fwd": (C.c_int, [_vp, _vp, _i32, _vp, _P(C.c_int32), _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "advmil_cast_f32_to_bf16": (C.c_int, [_vp, _i64, _vp, _vp]),
     "advmil_dropout_mask": (C.c_int, [_u64, _i32, _f, _i32, _i32, _vp, _vp]),
+    "advmil_adv_step_workspace_bytes": (_sz, [_P(GenParams), _P(DiscParams), _i32, _i32, _i32]),
+    "advmil_adv_step_disc": (C.c_int, [_P(StepArgs), _vp]),
+    "advmil_adv_step_gen": (C.c_int, [_P(StepArgs), _vp]),
     "advmil_seg_pool_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "advmil_region_index_map": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "advmil_region_of_rows": (C.c_int, [_i32, _i32, _vp, _vp]),

@@ -81,6 +81,7 @@ extern "C" size_t advmil_abi_sizeof(int which) {
     case 5: return sizeof(AdvmilDiscGrads);
     case 6: return sizeof(AdvmilEmbedActs);
     case 7: return sizeof(AdvmilHeadActs);
+    case 8: return sizeof(AdvmilStepArgs);
     default: return 0;
   }
 }
@@ -254,22 +255,28 @@ extern "C" int advmil_disc_embed_fwd(const AdvmilDiscParams* p, const AdvmilBags
                           a->precision, (cudaStream_t)stream);
 }
 
-extern "C" int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilEmbedActs* a,
-                                     const float* d_emb, AdvmilDiscGrads* g, int32_t accumulate, void* stream) {
+namespace advmil {
+int disc_embed_bwd_impl(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilEmbedActs* a, const float* d_emb,
+                        const float* d_emb2, AdvmilDiscGrads* g, int accumulate, cudaStream_t st) {
   ADVMIL_REQUIRE(p && a && d_emb && g, "disc_embed_bwd: null argument");
   ADVMIL_REQUIRE(a->y_pre, "disc_embed_bwd: forward was run without saving y_pre");
   ADVMIL_TRY(check_bags(bags, p->C, true, a->precision));
-  cudaStream_t st = (cudaStream_t)stream;
   const int rows = bags->rows, d = p->d, C = p->C;
   Workspace ws(a->workspace, a->workspace_bytes);
   WS_TAKE(d_y, float, (size_t)rows * d);
   WS_TAKE(lnws, float, (size_t)row_chunks(rows) * 3 * d);
   WS_TAKE(bwws, float, bwd_weight_ws_floats(rows, d, C));
   { ProfScope ps(PROF_LN_BWD, st);
-    ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws,
+    ADVMIL_TRY(ln_pool_bwd(a->y_pre, d_emb, d_emb2, p->ln_g, p->ln_b, rows, d, p->ln_eps, d_y, g->ln_g, g->ln_b, g->bc, accumulate, lnws,
                            elem_of_precision(a->precision), st)); }
   { ProfScope ps(PROF_BWD_W_EMBED, st); ADVMIL_TRY(bwd_weight(d_y, bags->x, rows, d, C, g->Wc, accumulate, bwws, a->precision, st)); }
   return ADVMIL_OK;
+}
+}  // namespace advmil
+
+extern "C" int advmil_disc_embed_bwd(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilEmbedActs* a,
+                                     const float* d_emb, AdvmilDiscGrads* g, int32_t accumulate, void* stream) {
+  return disc_embed_bwd_impl(p, bags, a, d_emb, nullptr, g, accumulate, (cudaStream_t)stream);
 }
 
 namespace {

@@ -551,8 +551,8 @@ int pool_gate_bwd(const void* v, const float* w, const float* z, const float* dz
 // =============================================================================================
 template <int VPL>  // values per lane: d <= 32*VPL
 __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
-    const float* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ gamma,
-    const float* __restrict__ beta, int rows, int d, float eps, float* __restrict__ d_y,
+    const float* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ d_emb2,
+    const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d, float eps, float* __restrict__ d_y,
     float* __restrict__ part /*[chunks][3][d]*/) {
   extern __shared__ float sm[];  // [8 warps][3][d]
   int row0 = blockIdx.x * ROWS_PER_CTA;
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
       if (c < d) {
         xh[k] = (y[k] - mean) * rstd;
         float e = fmaf(xh[k], g[k], be[k]);
-        float de = e > 0.f ? d_emb[(row >> 4) * d + c] * (1.0f / 16.0f) : 0.f;
+        float de = e > 0.f ? (d_emb[(row >> 4) * d + c] + (d_emb2 ? d_emb2[(row >> 4) * d + c] : 0.f)) * (1.0f / 16.0f) : 0.f;
         pg[k] = fmaf(de, xh[k], pg[k]);
         pb[k] += de;
         dxh[k] = de * g[k];
@@ -628,8 +628,9 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
 // instruction covers 128 contiguous bytes per row), 4 rows per warp, two such groups in flight
 template <typename T>
 __global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
-    const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ gamma,
-    const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y, float* __restrict__ part) {
+    const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ d_emb2,
+    const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y,
+    float* __restrict__ part) {
   constexpr int VEC = VecN<T>::N, NV = 16 / VEC;          // vectors per lane
   __shared__ float sm[4 * 3 * 128];
   __shared__ __align__(16) float gb_s[2 * 128];           // gamma | beta, permuted so that my 16 columns are contiguous
@@ -657,7 +658,9 @@ __global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
     for (int k = 0; k < NV; ++k)
 #pragma unroll
       for (int q4 = 0; q4 < VEC / 4; ++q4) {
-        const float4 d4 = *reinterpret_cast<const float4*>(d_emb + ((size_t)(row0 + rb) >> 4) * 128 + k * 8 * VEC + sub * VEC + 4 * q4);
+        const size_t go = ((size_t)(row0 + rb) >> 4) * 128 + k * 8 * VEC + sub * VEC + 4 * q4;
+        float4 d4 = *reinterpret_cast<const float4*>(d_emb + go);
+        if (d_emb2) { const float4 e4 = *reinterpret_cast<const float4*>(d_emb2 + go); d4.x += e4.x; d4.y += e4.y; d4.z += e4.z; d4.w += e4.w; }
         ge[k * VEC + 4 * q4] = d4.x; ge[k * VEC + 4 * q4 + 1] = d4.y; ge[k * VEC + 4 * q4 + 2] = d4.z; ge[k * VEC + 4 * q4 + 3] = d4.w;
       }
 #pragma unroll
@@ -740,19 +743,19 @@ __global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
   }
 }
 
-int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
-                float eps, void* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate, float* ws, int dt,
+int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, const float* gamma, const float* beta, int rows,
+                int d, float eps, void* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate, float* ws, int dt,
                 cudaStream_t st) {
   ADVMIL_REQUIRE(d <= 256, "ln_pool_bwd: d %d > 256 unsupported", d);
   ADVMIL_REQUIRE(dt == ELEM_F32 || d == 128, "ln_pool_bwd: the bf16 mode supports d == 128 only (d=%d)", d);
   int chunks = row_chunks(rows);
   size_t smem = (size_t)8 * 3 * d * sizeof(float);
   if (d == 128 && dt == ELEM_BF16)
-    ln_pool_bwd128_kernel<bf16><<<chunks, 128, 0, st>>>((const bf16*)y_pre, d_emb, gamma, beta, rows, eps, (bf16*)d_y, ws);
+    ln_pool_bwd128_kernel<bf16><<<chunks, 128, 0, st>>>((const bf16*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (bf16*)d_y, ws);
   else if (d == 128)
-    ln_pool_bwd128_kernel<float><<<chunks, 128, 0, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, eps, (float*)d_y, ws);
-  else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, d, eps, (float*)d_y, ws);
-  else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, gamma, beta, rows, d, eps, (float*)d_y, ws);
+    ln_pool_bwd128_kernel<float><<<chunks, 128, 0, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (float*)d_y, ws);
+  else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
+  else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();
   reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
   ADVMIL_CHECK_LAUNCH();

@@ -52,9 +52,14 @@ inline size_t pool_gate_ws_floats(int rows, int bags, int D) {
          align_up((size_t)rows, 64) + 64;
 }
 // LayerNorm + ReLU + region-mean backward per row; partials of dgamma/dbeta/dbias reduced into the outputs
-int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d,
-                float eps, void* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate,
+// d_emb2 (optional): a second upstream gradient that is added to d_emb (real + fake halves of a batched D step)
+int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, const float* gamma, const float* beta, int rows,
+                int d, float eps, void* d_y, float* dgamma, float* dbeta, float* dbias, int accumulate,
                 float* ws /* >= row_chunks*3*d floats */, int dt, cudaStream_t st);
+
+// ---- api.cu ---------------------------------------------------------------------------------
+int disc_embed_bwd_impl(const AdvmilDiscParams* p, const AdvmilBags* bags, const AdvmilEmbedActs* a, const float* d_emb,
+                        const float* d_emb2, AdvmilDiscGrads* g, int accumulate, cudaStream_t st);
 int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accumulate, float* ws /* >= row_chunks*N */,
            cudaStream_t st);
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st);

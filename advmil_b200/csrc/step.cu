@@ -1,0 +1,197 @@
+// Fused adversarial step: the launch sequence of one D update + one G update (model/model_handler.py:349-498) issued from
+// C in two host calls (advmil_adv_step_disc / advmil_adv_step_gen) over one caller-owned workspace.
+//
+//  * real and fake pairs of the D step share one region-embedding pass and run through ONE batched RLIP head pass: the
+//    head sees 2 x bags "virtual bags" (fake pairs first, then real pairs) over a duplicated [2R, d] embedding;
+//  * the D-step generator forward (eval) and the G-step generator forward (train) share relu(x W1^T + b1): the eval
+//    projection stays in the workspace between the two calls and the G step applies its dropout draw to it;
+//  * the G step asks D only for dL/dt and never touches D-parameter gradients.
+#include <vector>
+#include "stages.cuh"
+
+namespace advmil {
+
+__global__ void real_mask_kernel(const float* __restrict__ e, const uint8_t* __restrict__ visible, int n, uint8_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (e[i] == 1.0f && visible[i] != 0) ? 1 : 0;   // model_handler.py:373-375
+}
+__global__ void dup_offsets_kernel(const int32_t* __restrict__ offs, int nb, int rows, int32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= nb) { out[i] = offs[i]; out[nb + i] = offs[i] + rows; }
+}
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+// head activation buffers for nr region rows / nbv (virtual) bags
+static bool take_head(Workspace& ws, const AdvmilDiscParams& p, size_t nr, size_t nbv, AdvmilHeadActs& h) {
+  const size_t d = p.d, dh = p.d / 2, abw = gate_width(p.d);
+  h.f1 = ws.take<float>(nr * dh); h.fi = ws.take<float>(nr * d); h.ab = ws.take<float>(nr * abw);
+  h.rep = ws.take<float>(nr); h.attn = ws.take<float>(nr);
+  h.bagv = ws.take<float>(nbv * d); h.fbar = ws.take<float>(nbv * d); h.g1 = ws.take<float>(nbv * dh);
+  h.hx = ws.take<float>(nbv * d); h.u1 = ws.take<float>(nbv * p.t1); h.ht = ws.take<float>(nbv * p.t2);
+  return h.f1 && h.fi && h.ab && h.rep && h.attn && h.bagv && h.fbar && h.g1 && h.hx && h.u1 && h.ht;
+}
+static size_t head_bytes(const AdvmilDiscParams& p, size_t nr, size_t nbv) {
+  const size_t d = p.d, dh = p.d / 2, abw = gate_width(p.d);
+  const size_t f = nr * (dh + d + abw + 2) + nbv * (3 * d + dh + p.t1 + p.t2);
+  return f * sizeof(float) + 16 * 256;
+}
+
+struct GenBufs { float *s, *w, *z, *H, *H1, *pre; };
+static bool take_gen(Workspace& ws, const AdvmilGenParams& g, size_t rows, size_t nb, GenBufs& b) {
+  b.s = ws.take<float>(rows); b.w = ws.take<float>(rows); b.z = ws.take<float>(nb * g.h); b.H = ws.take<float>(nb * g.o);
+  b.H1 = ws.take<float>(nb * (g.hid > 0 ? g.hid : 1)); b.pre = ws.take<float>(nb);
+  return b.s && b.w && b.z && b.H && b.H1 && b.pre;
+}
+static size_t gen_bufs_bytes(const AdvmilGenParams& g, size_t rows, size_t nb) {
+  return (2 * rows + nb * (g.h + g.o + g.hid + 2)) * sizeof(float) + 8 * 256;
+}
+
+#define STEP_TAKE(var, type, count)                                                                         \
+  type* var = ws.take<type>(count);                                                                         \
+  if (!var) { set_error("%s: workspace too small (have %zu bytes)", __func__, ws.cap); return ADVMIL_ERR_WORKSPACE; }
+
+}  // namespace advmil
+
+using namespace advmil;
+
+extern "C" size_t advmil_adv_step_workspace_bytes(const AdvmilGenParams* g, const AdvmilDiscParams* d, int32_t rows,
+                                                  int32_t bags, int32_t precision) {
+  const size_t es = elem_bytes(elem_of_precision(precision));
+  const size_t R = rows / 16, nb = bags, abw = gate_width(g->h);
+  size_t persistent = align_up((size_t)rows * g->h * es, 256) + align_up((2 * nb + 2) * sizeof(int32_t), 256) + 1024;
+  size_t disc = gen_bufs_bytes(*g, rows, nb) + advmil_generator_workspace_bytes(g, rows, bags, 0) + 256 +
+                align_up(2 * R * d->d * sizeof(float), 256) + align_up((size_t)rows * d->d * es, 256) + head_bytes(*d, 2 * R, 2 * nb) +
+                align_up(2 * R * d->d * sizeof(float), 256) + 8 * 256 + 6 * nb * sizeof(float) +
+                advmil_disc_workspace_bytes(d, 2 * rows, 2 * bags, 1) + 256;
+  size_t gen = align_up((size_t)rows * g->h * es, 256) + align_up((size_t)rows * abw * es, 256) + gen_bufs_bytes(*g, rows, nb) +
+               advmil_generator_workspace_bytes(g, rows, bags, 1) + 256 + align_up(R * d->d * sizeof(float), 256) +
+               head_bytes(*d, R, nb) + 8 * 256 + 4 * nb * sizeof(float) + advmil_disc_workspace_bytes(d, rows, bags, 1) + 256;
+  return persistent + (disc > gen ? disc : gen) + 4096;
+}
+
+static int step_check(const AdvmilStepArgs* a) {
+  ADVMIL_REQUIRE(a && a->gen && a->disc && a->bags && a->t && a->e && a->visible && a->losses, "adv_step: null argument");
+  ADVMIL_REQUIRE(a->gen->W0 && a->gen->Wrho, "adv_step: the fused step covers the ABMIL generator with its noise head");
+  ADVMIL_REQUIRE(a->gen->noise0 == 0, "adv_step: noise on the first head layer (gen_noi_noise '1-*') is not covered by the fused step");
+  ADVMIL_REQUIRE(a->workspace, "adv_step: workspace missing");
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
+  ADVMIL_TRY(step_check(a));
+  ADVMIL_REQUIRE(a->disc_grads && a->pred_d && a->f_fake_d && a->real_mask, "adv_step_disc: missing output buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdvmilGenParams& gp = *a->gen;
+  const AdvmilDiscParams& dp = *a->disc;
+  const AdvmilBags* bags = a->bags;
+  const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = dp.d;
+  const size_t es = elem_bytes(elem_of_precision(a->precision));
+  const bool batched = a->n_real > 0.f;                 // no real pair anywhere: only the fake half runs
+  const int nbv = batched ? 2 * nb : nb, Rv = batched ? 2 * R : R;
+  Workspace ws(a->workspace, a->workspace_bytes);
+  STEP_TAKE(h_eval, char, (size_t)rows * gp.h * es);
+  STEP_TAKE(offs2, int32_t, 2 * nb + 2);
+  // ---- generator, eval mode, detached (model_handler.py:383-387) ----
+  GenBufs gb;
+  if (!take_gen(ws, gp, rows, nb, gb)) { set_error("adv_step_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  const size_t gws_bytes = advmil_generator_workspace_bytes(&gp, rows, nb, 0);
+  STEP_TAKE(gws, char, gws_bytes);
+  AdvmilGenActs ga{};
+  ga.h = h_eval; ga.ab = nullptr; ga.s = gb.s; ga.w = gb.w; ga.z = gb.z; ga.H = gb.H; ga.H1 = gb.H1; ga.pre = gb.pre;
+  ga.pred = a->pred_d; ga.noise0 = nullptr; ga.noise1 = a->noise_d; ga.h_eval = nullptr;
+  ga.seed = 0; ga.train = 0; ga.precision = a->precision; ga.workspace = gws; ga.workspace_bytes = gws_bytes;
+  ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
+  // ---- shared region embedding (K5+K6), duplicated for the batched head ----
+  STEP_TAKE(emb2, float, (size_t)2 * R * d);
+  STEP_TAKE(y_pre, char, (size_t)rows * d * es);
+  AdvmilEmbedActs ea{};
+  ea.emb = emb2; ea.y_pre = y_pre; ea.precision = a->precision;
+  ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
+  // ---- batched head over the virtual bags [fake pairs | real pairs] ----
+  AdvmilHeadActs ha{};
+  if (!take_head(ws, dp, 2 * (size_t)R, 2 * (size_t)nb, ha)) { set_error("adv_step_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  STEP_TAKE(d_emb2, float, (size_t)2 * R * d);
+  STEP_TAKE(t2, float, 2 * nb);
+  STEP_TAKE(d_out2, float, 2 * nb);
+  const size_t dws_bytes = advmil_disc_workspace_bytes(&dp, 2 * rows, 2 * nb, 1);
+  STEP_TAKE(dws, char, dws_bytes);
+  std::vector<int32_t> offs2_host(2 * nb + 1);
+  for (int i = 0; i <= nb; ++i) { offs2_host[i] = bags->offsets_host[i]; offs2_host[nb + i] = bags->offsets_host[i] + rows; }
+  dup_offsets_kernel<<<cdiv(nb + 1, 128), 128, 0, st>>>(bags->offsets, nb, rows, offs2);
+  ADVMIL_CHECK_LAUNCH();
+  real_mask_kernel<<<cdiv(nb, 128), 128, 0, st>>>(a->e, a->visible, nb, a->real_mask);
+  ADVMIL_CHECK_LAUNCH();
+  ADVMIL_CHECK_CUDA(cudaMemcpyAsync(t2, a->pred_d, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (batched) {
+    ADVMIL_CHECK_CUDA(cudaMemcpyAsync(t2 + nb, a->t, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ADVMIL_CHECK_CUDA(cudaMemcpyAsync(emb2 + (size_t)R * d, emb2, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  AdvmilBags vb = *bags;
+  vb.offsets = offs2; vb.offsets_host = offs2_host.data(); vb.rows = batched ? 2 * rows : rows; vb.bags = nbv;
+  ha.emb = emb2; ha.t = t2; ha.out = a->f_fake_d;
+  ha.mask_fc1 = a->d_mask_fc1; ha.mask_ga = a->d_mask_ga; ha.mask_gs = a->d_mask_gs; ha.mask_fc2 = a->d_mask_fc2;
+  ha.seed = a->seed_d; ha.train = 1; ha.precision = a->precision; ha.workspace = dws; ha.workspace_bytes = dws_bytes;
+  ADVMIL_TRY(advmil_disc_head_fwd(&dp, &vb, &ha, stream));
+  // ---- loss (loss/utils.py:182-203) and backward ----
+  ADVMIL_TRY(advmil_disc_loss(a->f_fake_d + nb, a->f_fake_d, a->real_mask, nb, a->loss_d, a->n_real, a->n_fake, a->losses,
+                              d_out2 + nb, d_out2, stream));
+  ADVMIL_TRY(advmil_disc_head_bwd(&dp, &vb, &ha, d_out2, d_emb2, nullptr, a->disc_grads, 0, stream));
+  ea.workspace = dws; ea.workspace_bytes = dws_bytes;
+  ADVMIL_TRY(disc_embed_bwd_impl(&dp, bags, &ea, d_emb2, batched ? d_emb2 + (size_t)R * d : nullptr, a->disc_grads, 0, st));
+  (void)Rv;
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
+  ADVMIL_TRY(step_check(a));
+  ADVMIL_REQUIRE(a->gen_grads && a->pred_g && a->f_fake_g, "adv_step_gen: missing output buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdvmilGenParams& gp = *a->gen;
+  const AdvmilDiscParams& dp = *a->disc;
+  const AdvmilBags* bags = a->bags;
+  const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = dp.d;
+  const size_t es = elem_bytes(elem_of_precision(a->precision));
+  const size_t abw = gate_width(gp.h);
+  Workspace ws(a->workspace, a->workspace_bytes);
+  STEP_TAKE(h_eval, char, (size_t)rows * gp.h * es);      // written by advmil_adv_step_disc on this workspace
+  STEP_TAKE(offs2, int32_t, 2 * nb + 2);
+  (void)offs2;
+  // ---- generator, train mode, on the cached eval projection ----
+  STEP_TAKE(h, char, (size_t)rows * gp.h * es);
+  STEP_TAKE(ab, char, (size_t)rows * abw * es);
+  GenBufs gb;
+  if (!take_gen(ws, gp, rows, nb, gb)) { set_error("adv_step_gen: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  const size_t gws_bytes = advmil_generator_workspace_bytes(&gp, rows, nb, 1);
+  STEP_TAKE(gws, char, gws_bytes);
+  AdvmilGenActs ga{};
+  ga.h = h; ga.ab = ab; ga.s = gb.s; ga.w = gb.w; ga.z = gb.z; ga.H = gb.H; ga.H1 = gb.H1; ga.pre = gb.pre;
+  ga.pred = a->pred_g; ga.noise0 = nullptr; ga.noise1 = a->noise_g; ga.h_eval = h_eval;
+  ga.mask_h = a->g_mask_h; ga.mask_a = a->g_mask_a; ga.mask_b = a->g_mask_b; ga.mask_rho = a->g_mask_rho; ga.mask_mlp0 = a->g_mask_mlp0;
+  ga.seed = a->seed_g; ga.train = 1; ga.precision = a->precision; ga.workspace = gws; ga.workspace_bytes = gws_bytes;
+  ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
+  // ---- D(x, pred_g) with the updated discriminator, eval mode ----
+  STEP_TAKE(emb, float, (size_t)R * d);
+  AdvmilEmbedActs ea{};
+  ea.emb = emb; ea.y_pre = nullptr; ea.precision = a->precision;
+  ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
+  AdvmilHeadActs ha{};
+  if (!take_head(ws, dp, R, nb, ha)) { set_error("adv_step_gen: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  STEP_TAKE(d_pred, float, nb);
+  STEP_TAKE(d_fake, float, nb);
+  STEP_TAKE(d_t, float, nb);
+  const size_t dws_bytes = advmil_disc_workspace_bytes(&dp, rows, nb, 1);
+  STEP_TAKE(dws, char, dws_bytes);
+  ha.emb = emb; ha.t = a->pred_g; ha.out = a->f_fake_g; ha.seed = 0; ha.train = 0; ha.precision = a->precision;
+  ha.workspace = dws; ha.workspace_bytes = dws_bytes;
+  ADVMIL_TRY(advmil_disc_head_fwd(&dp, bags, &ha, stream));
+  // ---- loss (loss/utils.py:21-41,205-208) and backward: D hands back only dL/dt ----
+  ADVMIL_TRY(advmil_gen_loss(a->pred_g, a->t, a->e, a->visible, a->f_fake_g, nb, a->n_visible, a->n_fake, a->coef_gan,
+                             a->recon_alpha, a->recon_gamma, a->recon_norm, a->losses + 1, d_pred, d_fake, stream));
+  ADVMIL_TRY(advmil_disc_head_bwd(&dp, bags, &ha, d_fake, nullptr, d_t, nullptr, 0, stream));
+  add_inplace_kernel<<<cdiv(nb, 128), 128, 0, st>>>(d_pred, d_t, nb);
+  ADVMIL_CHECK_LAUNCH();
+  return advmil_generator_bwd(&gp, bags, &ga, d_pred, a->gen_grads, stream);
+}

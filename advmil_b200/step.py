@@ -94,99 +94,100 @@ class AdvStep:
         if self.world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
+    def _structs(self):
+        """C views of the parameter / gradient tensors (their storage is the flat buffers and never moves)."""
+        if getattr(self, "_c", None) is None:
+            gp, dp = self.gcfg.c(self.gparams), self.dcfg.c(self.dparams)
+            gg, dg = _lib.GenGrads(), _lib.DiscGrads()
+            for name, tns in zip(_lib.GEN_TENSORS, self.ggrads):
+                setattr(gg, name, None if tns is None else tns.data_ptr())
+            gg.dx = None
+            for name, tns in zip(_lib.DISC_TENSORS, self.dgrads):
+                setattr(dg, name, None if tns is None else tns.data_ptr())
+            self._c = (gp, dp, gg, dg)
+        return self._c
+
+    def _workspace(self, lib, gp, dp, rows, nb, dev) -> torch.Tensor:
+        need = lib.advmil_adv_step_workspace_bytes(C.byref(gp), C.byref(dp), rows, nb, self.precision)
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            self._ws = ws = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=dev)   # grow-only
+        return ws
+
+    @staticmethod
+    def _cat_masks(fake, real, keys):
+        """Injected discriminator masks of the batched head pass: FAKE pairs first, then REAL pairs."""
+        if not fake and not real:
+            return {}
+        assert fake and real, "inject masks for both the real and the fake pairs (or for neither)"
+        return {k: torch.cat([fake[k], real[k]], dim=0).contiguous() for k in keys}
+
     def step(self, bags: ops.PackedBags, t: torch.Tensor, e: torch.Tensor, visible: torch.Tensor,
              noise_d: Optional[torch.Tensor] = None, noise_g: Optional[torch.Tensor] = None,
              masks_d_real=None, masks_d_fake=None, masks_g=None, global_counts=None, return_debug=False) -> Dict:
         """t, e: [bags] float32 device; visible: [bags] uint8 device (label_visible_mask).  noise_*: [bags, hid] device
-        (drawn like utils/func.generate_noise when None).  Returns device tensors only (no host sync)."""
+        (drawn like utils/func.generate_noise when None).  Returns device tensors only (no host sync when
+        global_counts is given).  Two C calls (advmil_adv_step_disc / _gen) issue the whole launch sequence."""
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         bags = bags.for_precision(self.precision)   # bf16 mode: bf16 features as packed by the loader, or one cast here
         dev = bags.x.device
         nb = bags.bags
-        G, D = self.netG, self.netD
+        G = self.netG
         f32 = dict(dtype=torch.float32, device=dev)
         t = t.reshape(-1).contiguous().float()
         e = e.reshape(-1).contiguous().float()
         visible = visible.reshape(-1).to(torch.uint8).contiguous()
-        real_mask = ((e == 1) & (visible != 0)).to(torch.uint8)          # model_handler.py:373-375
         if global_counts is None:
+            real_mask = ((e == 1) & (visible != 0))                      # model_handler.py:373-375
             cnt = torch.stack([real_mask.sum(), torch.tensor(nb, device=dev), visible.sum()]).float()
             self._allreduce(cnt)
             n_real, n_fake, n_vis = [float(v) for v in cnt.tolist()]
         else:
             n_real, n_fake, n_vis = [float(v) for v in global_counts]
-        hid = self.gcfg.hid
         if noise_d is None:
             noise_d = G.draw_noise(nb, dev, False)[1]
         if noise_g is None:
             noise_g = G.draw_noise(nb, dev, False)[1]
-
+        noise_d, noise_g = noise_d.contiguous().float(), noise_g.contiguous().float()
+        gp, dp, gg, dg = self._structs()
+        ws = self._workspace(lib, gp, dp, bags.rows, nb, dev)
+        out = {"losses": torch.zeros(8, **f32), "pred_d": torch.empty(nb, **f32), "pred_g": torch.empty(nb, **f32),
+               "f_d": torch.empty(2 * nb, **f32), "f_fake_g": torch.empty(nb, **f32),
+               "real_mask": torch.empty(nb, dtype=torch.uint8, device=dev)}
+        md = self._cat_masks(masks_d_fake, masks_d_real, ("fc1", "ga", "gs", "fc2"))
+        mg = masks_g or {}
+        b = bags.c()
+        a = _lib.StepArgs()
+        a.gen, a.disc, a.gen_grads, a.disc_grads, a.bags = C.pointer(gp), C.pointer(dp), C.pointer(gg), C.pointer(dg), C.pointer(b)
+        a.t, a.e, a.visible = t.data_ptr(), e.data_ptr(), visible.data_ptr()
+        a.noise_d, a.noise_g = noise_d.data_ptr(), noise_g.data_ptr()
+        for k in ("h", "a", "b", "rho", "mlp0"):
+            setattr(a, "g_mask_" + k, ops._ptr(mg.get(k)))
+        for k in ("fc1", "ga", "gs", "fc2"):
+            setattr(a, "d_mask_" + k, ops._ptr(md.get(k)))
+        a.seed_d, a.seed_g = next_dropout_seed(), next_dropout_seed()
+        a.n_real, a.n_fake, a.n_visible, a.loss_d = n_real, n_fake, n_vis, self.loss_d
+        a.recon_norm, a.recon_alpha, a.recon_gamma = self.recon
+        a.coef_gan, a.precision = self.coef_gan, self.precision
+        a.losses, a.pred_d, a.f_fake_d, a.real_mask = (out["losses"].data_ptr(), out["pred_d"].data_ptr(),
+                                                       out["f_d"].data_ptr(), out["real_mask"].data_ptr())
+        a.pred_g, a.f_fake_g = out["pred_g"].data_ptr(), out["f_fake_g"].data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         # ---------------- D step: D.train / G.eval (model_handler.py:355-356) ----------------
-        ga = ops.generator_forward(self.gcfg, self.gparams, bags, None, noise_d, train=False, precision=self.precision,
-                                   save=False)
-        pred_d = ga["pred"]
-        emb = ops.disc_embed_forward(self.dcfg, self.dparams, bags, self.precision, save=True)
-        d_emb = torch.empty_like(emb["emb"])
-        losses = torch.zeros(8, **f32)   # [0] dis_loss, [1] recon, [2] gen, [3] total w/o L1, [4] sum|W_G|
-        d_real = torch.empty(nb, **f32)
-        d_fake = torch.empty(nb, **f32)
-        hf = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb["emb"], pred_d, train=True,
-                                   seed=next_dropout_seed(), masks=masks_d_fake, precision=self.precision)
-        hr = None
-        if n_real > 0:
-            hr = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb["emb"], t, train=True,
-                                       seed=next_dropout_seed(), masks=masks_d_real, precision=self.precision)
-        check(lib.advmil_disc_loss(None if hr is None else hr["out"].data_ptr(), hf["out"].data_ptr(),
-                                   real_mask.data_ptr(), nb, self.loss_d, n_real, n_fake, losses.data_ptr(),
-                                   d_real.data_ptr(), d_fake.data_ptr(), st), "advmil_disc_loss")
-        ops.disc_head_backward(self.dcfg, self.dparams, bags, hf, d_fake, d_emb, None, self.dgrads, accumulate=False)
-        if hr is not None:
-            ops.disc_head_backward(self.dcfg, self.dparams, bags, hr, d_real, d_emb, None, self.dgrads, accumulate=True)
-        ops.disc_embed_backward(self.dcfg, self.dparams, bags, emb, d_emb, self.dgrads, accumulate=False)
+        check(lib.advmil_adv_step_disc(C.byref(a), st), "advmil_adv_step_disc")
         self._allreduce(self.D.grad)
         self.D.adam(self.lr_d)
-
         # ---------------- G step: D.eval / G.train (model_handler.py:432-433) ----------------
-        gt = ops.generator_forward(self.gcfg, self.gparams, bags, None, noise_g, train=True, seed=next_dropout_seed(),
-                                   masks=masks_g, precision=self.precision, save=True, h_eval=ga["h"])
-        pred_g = gt["pred"]
-        emb2 = ops.disc_embed_forward(self.dcfg, self.dparams, bags, self.precision, save=False)
-        hg = ops.disc_head_forward(self.dcfg, self.dparams, bags, emb2["emb"], pred_g, train=False, precision=self.precision)
-        d_pred = torch.empty(nb, **f32)
-        d_fake_g = torch.empty(nb, **f32)
-        norm, alpha, gamma = self.recon
-        check(lib.advmil_gen_loss(pred_g.data_ptr(), t.data_ptr(), e.data_ptr(), visible.data_ptr(), hg["out"].data_ptr(),
-                                  nb, n_vis, n_fake, self.coef_gan, alpha, gamma, norm, losses[1:].data_ptr(),
-                                  d_pred.data_ptr(), d_fake_g.data_ptr(), st), "advmil_gen_loss")
-        d_t = torch.empty(nb, **f32)
-        ops.disc_head_backward(self.dcfg, self.dparams, bags, hg, d_fake_g, None, d_t, None)
-        d_pred += d_t
-        grads, _ = None, None
-        self._gen_backward_into_flat(bags, gt, d_pred)
+        check(lib.advmil_adv_step_gen(C.byref(a), st), "advmil_adv_step_gen")
         if self.coef_l1 > 1e-8:
-            check(lib.advmil_abs_sum(self.G.flat.data_ptr(), self.G.total, losses[4:].data_ptr(), st), "advmil_abs_sum")
+            check(lib.advmil_abs_sum(self.G.flat.data_ptr(), self.G.total, out["losses"][4:].data_ptr(), st), "advmil_abs_sum")
         self._allreduce(self.G.grad)
         self.G.adam(self.lr_g, weight_decay=self.wd_g, l1_coef=self.coef_l1 if self.coef_l1 > 1e-8 else 0.0)
-        out = {"losses": losses, "pred_d": pred_d, "pred_g": pred_g, "f_fake_d": hf["out"], "f_fake_g": hg["out"],
-               "f_real": None if hr is None else hr["out"], "real_mask": real_mask}
-        if return_debug:
-            out.update({"gen_acts": gt, "emb": emb})
+        out["f_fake_d"] = out["f_d"][:nb]
+        out["f_real"] = out["f_d"][nb:] if n_real > 0 else None
+        out["_keep"] = (t, e, visible, noise_d, noise_g, md, mg, bags)     # inputs stay alive until the stream is done with them
         return out
-
-    def _gen_backward_into_flat(self, bags, acts, d_pred):
-        lib = _lib.load()
-        p = self.gcfg.c(self.gparams)
-        g = _lib.GenGrads()
-        for name, tns in zip(_lib.GEN_TENSORS, self.ggrads):
-            setattr(g, name, None if tns is None else tns.data_ptr())
-        g.dx = None
-        ws = torch.empty(lib.advmil_generator_workspace_bytes(C.byref(p), bags.rows, bags.bags, 1), dtype=torch.uint8,
-                         device=bags.x.device)
-        a = ops._gen_acts_struct(acts, ws)
-        b = bags.c()
-        check(lib.advmil_generator_bwd(C.byref(p), C.byref(b), C.byref(a), d_pred.data_ptr(), C.byref(g),
-                                       torch.cuda.current_stream().cuda_stream), "advmil_generator_bwd")
 
     def loss_dict(self, out) -> Dict[str, float]:
         """Host copy of the step's scalars (one sync): the values the handler prints (model_handler.py:413,486-494)."""

@@ -255,7 +255,6 @@ def main():
         one_step(i)
     barrier()
     lib.advmil_launch_count(1)
-    lib.advmil_profile_enable(1)
     sampler = NvmlSampler(local_rank)
     if not sampler.ok:
         sampler = ClockSampler(local_rank)
@@ -273,10 +272,21 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = int(lib.advmil_launch_count(0))
+    # per-kernel-class CUDA-event timing in a SEPARATE pass (the event records perturb the step, so they stay out of the
+    # timed region above); shares are relative to this pass's own step time
     ntags = len(_lib.PROF_TAGS)
     pms, pcnt = (C.c_double * ntags)(), (C.c_int64 * ntags)()
+    prof_steps = min(args.steps, 10)
+    lib.advmil_profile_enable(1)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for i in range(prof_steps):
+        one_step(args.warmup + args.steps + i)
+    pe1.record()
+    torch.cuda.synchronize()
     lib.advmil_profile_enable(0)
     lib.advmil_profile_read(pms, pcnt, ntags)
+    prof_ms = pe0.elapsed_time(pe1)
     tms = torch.tensor([ms], device=dev)
     if world > 1:
         torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
@@ -319,7 +329,7 @@ def main():
         if pcnt[i] == 0:
             continue
         avg_ms = pms[i] / pcnt[i]
-        ent = {"ms_per_launch": avg_ms, "launches": int(pcnt[i]), "share_of_step": pms[i] / ms}
+        ent = {"ms_per_launch": avg_ms, "launches_per_step": pcnt[i] / prof_steps, "share_of_step": pms[i] / prof_ms}
         if tag in FLOP_PER_ROW:
             ent["tflops"] = FLOP_PER_ROW[tag] * rows_per_launch / (avg_ms * 1e-3) / 1e12
         if tag in BYTES_PER_ROW:
@@ -364,7 +374,8 @@ def main():
                              "steps) larger than the 126 MB L2; no flush",
                        "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "host_issue_ms_per_step": host_ms, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches, "host_issue_ms_per_step": host_ms, "profiled_pass_ms_per_step": prof_ms / prof_steps,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
             "losses_last_step": losses,
         }
         print(json.dumps(line), flush=True)

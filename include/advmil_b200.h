@@ -166,7 +166,7 @@ typedef struct AdvmilHeadActs {       /* K7+K8: region MLP, GAPool, bag MLP, tim
 ADVMIL_API int advmil_abi_version(void);
 ADVMIL_API const char* advmil_last_error(void);
 /* sizeof() of the ABI structs, for binding self-checks: which = 0 Bags, 1 GenParams, 2 GenGrads, 3 GenActs,
- * 4 DiscParams, 5 DiscGrads, 6 EmbedActs, 7 HeadActs */
+ * 4 DiscParams, 5 DiscGrads, 6 EmbedActs, 7 HeadActs, 8 StepArgs */
 ADVMIL_API size_t advmil_abi_sizeof(int which);
 /* counts kernel launches issued by this library since the last reset (bench "gpu_launches") */
 ADVMIL_API int64_t advmil_launch_count(int reset);
@@ -286,6 +286,46 @@ ADVMIL_API int advmil_adam_step(float* param, const float* grad, float* m, float
                      float grad_scale, void* stream);
 /* sum |p| over a flat buffer (the L1 term's value), out[0] += result */
 ADVMIL_API int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream);
+
+/* ---- fused adversarial step (replaces the bodies of MyHandler._update_disc / _update_gen, model/model_handler.py:349-498,
+ *      for one optimiser step of `bags`; the Adam updates and the data-parallel gradient all-reduce stay with the caller,
+ *      between the two phases).  One host call per phase instead of ~70: the launch sequence is issued from C.
+ *
+ *  advmil_adv_step_disc: D.train / G.eval (:355-356).  pred_d = G(x, noise_d) (detached); the real pair (x, t) of every
+ *      bag with real_mask and the fake pair (x, pred_d) of every bag run through ONE batched RLIP head pass over a shared
+ *      region embedding; D loss (loss/utils.py:182-203) with GLOBAL pair counts; writes all 24 D gradients.
+ *  advmil_adv_step_gen:  D.eval / G.train (:432-433), D already updated by the caller.  Re-uses the eval projection of the
+ *      disc phase (kept in the workspace: call both phases with the SAME workspace), new dropout draw; G loss = recon +
+ *      coef_gan * (-mean f_fake) (:478-484; the L1 term lives in advmil_adam_step); writes all 14 G gradients.          */
+typedef struct AdvmilStepArgs {
+  const AdvmilGenParams* gen; const AdvmilDiscParams* disc;
+  AdvmilGenGrads* gen_grads; AdvmilDiscGrads* disc_grads;
+  const AdvmilBags* bags;
+  const float* t; const float* e;      /* [bags] time label in [0,1], event indicator */
+  const uint8_t* visible;              /* [bags] label_visible_mask (model_handler.py:591-596) */
+  const float* noise_d; const float* noise_g;   /* [bags, hid] noise of the last head layer for the two generator passes */
+  /* optional injected dropout keep masks (parity tests); NULL = in-kernel generator keyed by the seeds below.
+   * d_masks_*: fc1 [2R, d/2] | ga [2R, d] | gs [2R, d] | fc2 [2*bags, d/2] with the FAKE pairs first, then the REAL pairs */
+  const uint8_t *g_mask_h, *g_mask_a, *g_mask_b, *g_mask_rho, *g_mask_mlp0;
+  const uint8_t *d_mask_fc1, *d_mask_ga, *d_mask_gs, *d_mask_fc2;
+  uint64_t seed_d, seed_g;
+  float n_real, n_fake, n_visible;     /* GLOBAL counts (sums over data-parallel ranks) */
+  int32_t loss_d;                      /* 0 bce (reference form), 1 hinge, 2 wasserstein */
+  float coef_gan, recon_alpha, recon_gamma; int32_t recon_norm;
+  int32_t precision;
+  /* outputs (device) */
+  float* losses;      /* [8]: [0] dis_loss, [1] recon, [2] gen, [3] recon + coef_gan*gen; the caller zeroes it per step */
+  float* pred_d;      /* [bags] G output of the disc phase */
+  float* f_fake_d;    /* [2*bags]: D(x, pred_d) then D(x, t) (the real half is meaningful where real_mask != 0) */
+  uint8_t* real_mask; /* [bags] e == 1 && visible */
+  float* pred_g;      /* [bags] G output of the gen phase */
+  float* f_fake_g;    /* [bags] D(x, pred_g) */
+  void* workspace; size_t workspace_bytes;
+} AdvmilStepArgs;
+ADVMIL_API size_t advmil_adv_step_workspace_bytes(const AdvmilGenParams* gen, const AdvmilDiscParams* disc, int32_t rows,
+                                       int32_t bags, int32_t precision);
+ADVMIL_API int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream);
+ADVMIL_API int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream);
 
 #ifdef __cplusplus
 }
