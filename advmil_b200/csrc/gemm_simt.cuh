@@ -193,6 +193,7 @@ struct EpiGate {
             gate_keep(drop_a, drop_b, m, jj, ka, kb);
             ad = ka ? a * drop_a.inv_keep : 0.f;
             bd = kb ? b * drop_b.inv_keep : 0.f;
+            if (!(ka && kb)) bv[j] = -b;      // joint keep bit in the sign of the stored sigmoid (see gemm_tc.cu)
           }
           partial = fmaf(ad * bd, wc[jj], partial);
         }

@@ -152,11 +152,14 @@ __device__ __forceinline__ void store_staged(const float* stg, int ld, T* __rest
   }
 }
 
-// gate math on one 32-pair chunk: va/vb hold pre-activations on entry and tanh / sigmoid values on exit
-template <bool FAST, bool TRAIN>
+// gate math on one 32-pair chunk: va/vb hold pre-activations on entry and tanh / sigmoid values on exit.
+// MODE 0 = eval; 1 = train, in-kernel generator; 2 = train, injected masks (kept out of the hot instantiation: the
+// compiler otherwise issues both paths predicated for every element)
+template <bool FAST, int MODE>
 __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], const float* __restrict__ cba,
                                             const float* __restrict__ cbb, const float* __restrict__ cwc, const Drop& da,
                                             const Drop& db, uint32_t row, uint32_t j0, float partial) {
+  const uint32_t rowterm = row * 0x9E3779B1u, ta = da.thresh16, tb = db.thresh16, key = da.key;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const float xa = va[i] + cba[i], xb = vb[i] + cbb[i];
@@ -164,14 +167,24 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
     if (FAST) { a = fast_tanh(xa); b = fmaf(0.5f, fast_tanh(0.5f * xb), 0.5f); }
     else { a = tanhf(xa); b = sigmoidf_(xb); }
     va[i] = a; vb[i] = b;
-    float ad = a, bd = b;
-    if (TRAIN) {
-      bool ka, kb;
-      gate_keep(da, db, row, j0 + i, ka, kb);
-      ad = ka ? a * da.inv_keep : 0.f;
-      bd = kb ? b * db.inv_keep : 0.f;
+    if (MODE != 0) {
+      // either unit dropped => the pair contributes nothing forward or backward: the stored sigmoid carries the joint
+      // keep bit in its (otherwise unused) sign, so the backward pass needs no generator
+      bool keep;
+      if (MODE == 1) {
+        uint32_t x = rowterm ^ ((j0 + i) * 0x85EBCA77u + key);     // == Drop::bits(row, j0 + i)
+        x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+        keep = ((x & 0xFFFFu) >= ta) && ((x >> 16) >= tb);
+      } else {
+        bool ka, kb;
+        gate_keep(da, db, row, j0 + i, ka, kb);
+        keep = ka && kb;
+      }
+      vb[i] = keep ? b : -b;
+      partial = fmaf(keep ? a * b : 0.f, cwc[i], partial);
+    } else {
+      partial = fmaf(a * b, cwc[i], partial);
     }
-    partial = fmaf(ad * bd, cwc[i], partial);
   }
   return partial;
 }
@@ -187,7 +200,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int KBLK = TcElem<T>::KBLK;
   constexpr int VEC = VecN<T>::N;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   uint8_t* A_s = smem;
   uint8_t* B_s = smem + STAGES * A_STAGE_BYTES;
   float* stg_all = (float*)(B_s + STAGES * Cfg::B_STAGE_BYTES);
@@ -357,12 +370,16 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   for (int e = 0; e < VEC; ++e) o[e] = fmaxf(o[e], 0.f);
                 }
                 if (ea.drop.active) {
+                  if (ea.drop.mask == nullptr) {
 #pragma unroll
-                  for (int e = 0; e < VEC; e += 2) {
-                    bool k0, k1;
-                    ea.drop.keep2(m, col + e, k0, k1);
-                    o[e] = k0 ? o[e] * ea.drop.inv_keep : 0.f;
-                    o[e + 1] = k1 ? o[e + 1] * ea.drop.inv_keep : 0.f;
+                    for (int e = 0; e < VEC; e += 2) {
+                      const uint32_t hb = ea.drop.bits(m, col + e);
+                      o[e] = (hb & 0xFFFFu) >= ea.drop.thresh16 ? o[e] * ea.drop.inv_keep : 0.f;
+                      o[e + 1] = (hb >> 16) >= ea.drop.thresh16 ? o[e + 1] * ea.drop.inv_keep : 0.f;
+                    }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) o[e] = ea.drop.keep(m, col + e) ? o[e] * ea.drop.inv_keep : 0.f;
                   }
                 }
               } else {
@@ -407,6 +424,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         static_assert(EPI != EPI_GATE || BLOCK_N == 256, "gate epilogue expects 256-column tiles");
         float partial = 0.f;
         const bool train = ea.drop_a.active != 0;
+        const bool masked = ea.drop_a.mask != nullptr || ea.drop_b.mask != nullptr;
 #pragma unroll 1
         for (int jc = 0; jc < 2; ++jc) {
           const int ca = half * 128 + jc * 32, cb = ca + 64;
@@ -415,8 +433,9 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(taddr + ca, va);
           tmem_ld32(taddr + cb, vb);
           if (jc == 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
-          if (train) partial = gate_chunk<FAST, true>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
-          else partial = gate_chunk<FAST, false>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
+          if (!train) partial = gate_chunk<FAST, 0>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
+          else if (!masked) partial = gate_chunk<FAST, 1>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
+          else partial = gate_chunk<FAST, 2>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
           if (ea.ab) {
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
@@ -427,6 +446,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (train) partial *= ea.drop_a.inv_keep * ea.drop_b.inv_keep;
         if (m_row < M) ea.part[(size_t)(nt * 2 + half) * M + m_row] = partial;   // one partial per 128-column gate block
       } else if constexpr (EPI == EPI_LN) {
         // BLOCK_N == 128 == d: the whole row lives in this thread's registers
@@ -570,7 +590,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY*/, const __grid_con
   using Cfg = WgCfg<T, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES, KR = Cfg::KR, MNG = Cfg::MNG;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   uint8_t* A_s = smem;
   uint8_t* B_s = smem + STAGES * Cfg::A_BYTES;
   float* stg_all = (float*)(B_s + STAGES * Cfg::B_BYTES);

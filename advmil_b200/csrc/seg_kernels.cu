@@ -110,12 +110,16 @@ __global__ void apply_dropout_kernel(const T* __restrict__ src, size_t nvec, int
     ldv(src + i * VEC, v);
     const uint32_t row = (uint32_t)(i / vec_per_row), col = (uint32_t)(i % vec_per_row) * VEC;
     if (drop.active) {
+      if (drop.mask == nullptr) {
 #pragma unroll
-      for (int e = 0; e < VEC; e += 2) {
-        bool k0, k1;
-        drop.keep2(row, col + e, k0, k1);
-        v[e] = k0 ? v[e] * drop.inv_keep : 0.f;
-        v[e + 1] = k1 ? v[e + 1] * drop.inv_keep : 0.f;
+        for (int e = 0; e < VEC; e += 2) {
+          const uint32_t hb = drop.bits(row, col + e);
+          v[e] = (hb & 0xFFFFu) >= drop.thresh16 ? v[e] * drop.inv_keep : 0.f;
+          v[e + 1] = (hb >> 16) >= drop.thresh16 ? v[e + 1] * drop.inv_keep : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] = drop.keep(row, col + e) ? v[e] * drop.inv_keep : 0.f;
       }
     }
     stv(dst + i * VEC, v);
@@ -445,7 +449,6 @@ __global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
   __syncthreads();
   const int npairs = abw >> 1, TPR = npairs / VEC;
   const int rg = threadIdx.x / TPR, pv = threadIdx.x % TPR;
-  const bool tr = da.active != 0;
   if (rg < RGN) {
     const int q0 = pv * VEC, ca = gate_col_a(q0);
     float wcj[VEC], dwc[VEC], sa_sum[VEC], sb_sum[VEC];
@@ -461,13 +464,10 @@ __global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const bool valid = q0 + e < D;
-        float sa = 1.f, sb = 1.f;
-        if (tr && valid) {
-          bool ka, kb;
-          gate_keep(da, db, (uint32_t)row, (uint32_t)(q0 + e), ka, kb);
-          sa = ka ? da.inv_keep : 0.f; sb = kb ? db.inv_keep : 0.f;
-        }
-        const float av = valid ? a[e] : 0.f, bv = valid ? b[e] : 0.f;
+        // train mode: the forward stored the joint keep bit of the pair in the sign of the sigmoid
+        const bool keep = (__float_as_uint(b[e]) >> 31) == 0u;
+        const float sa = keep ? da.inv_keep : 0.f, sb = keep ? db.inv_keep : 0.f;
+        const float av = valid ? a[e] : 0.f, bv = valid ? fabsf(b[e]) : 0.f;
         const float ad = av * sa, bd = bv * sb, du = ds * wcj[e];
         oa[e] = du * bd * sa * (1.f - av * av);
         ob[e] = du * ad * sb * bv * (1.f - bv);

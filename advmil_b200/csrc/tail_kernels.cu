@@ -28,6 +28,62 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ Wrow, const 
   return warp_sum(acc);
 }
 
+// Four output rows r0..r0+3 of y = W v at once (W row-major [*, ld], n % 4 == 0, rows and v 16-byte aligned): 4 x n/128
+// independent 16-byte loads in flight per lane instead of one dependent 4-byte chain per row.  Rows >= rmax are skipped.
+__device__ __forceinline__ void warp_dot4(const float* __restrict__ W, int ld, int r0, int rmax, const float* __restrict__ v,
+                                          int n, int lane, float (&out)[4]) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane * 4; c < n; c += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(v + c);
+    float4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      w[u] = (r0 + u < rmax) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(r0 + u) * ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] += w[u].x * x.x + w[u].y * x.y + w[u].z * x.z + w[u].w * x.w;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) out[u] = warp_sum(acc[u]);
+}
+
+// y[c] = sum_{r<n} W[r*ld + c] v[r] for c < ncols (ncols % 4 == 0, W 16-byte aligned): the whole block cooperates, thread
+// (g, cv) accumulates column vector cv over rows g, g+G, ...; partials meet in `scratch` ([G][ncols] floats).  v, scratch
+// and out live in shared memory; ends with a __syncthreads().
+__device__ __forceinline__ void block_colmat(const float* __restrict__ W, int ld, int ncols, const float* __restrict__ v,
+                                             int n, float* __restrict__ scratch, float* __restrict__ out) {
+  const int CV = ncols >> 2;
+  const int G = max(1, min((int)blockDim.x / CV, n));
+  const int cv = threadIdx.x % CV, g = threadIdx.x / CV;
+  if (g < G) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = g;
+    for (; r + 3 * G < n; r += 4 * G) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)r * ld) + cv);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(r + G) * ld) + cv);
+      const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(r + 2 * G) * ld) + cv);
+      const float4 w3 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(r + 3 * G) * ld) + cv);
+      const float v0 = v[r], v1 = v[r + G], v2 = v[r + 2 * G], v3 = v[r + 3 * G];
+      acc.x += w0.x * v0 + w1.x * v1 + w2.x * v2 + w3.x * v3;
+      acc.y += w0.y * v0 + w1.y * v1 + w2.y * v2 + w3.y * v3;
+      acc.z += w0.z * v0 + w1.z * v1 + w2.z * v2 + w3.z * v3;
+      acc.w += w0.w * v0 + w1.w * v1 + w2.w * v2 + w3.w * v3;
+    }
+    for (; r < n; r += G) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)r * ld) + cv);
+      const float v0 = v[r];
+      acc.x += w0.x * v0; acc.y += w0.y * v0; acc.z += w0.z * v0; acc.w += w0.w * v0;
+    }
+    *reinterpret_cast<float4*>(scratch + (size_t)g * ncols + cv * 4) = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < G; ++k) t += scratch[(size_t)k * ncols + c];
+    out[c] = t;
+  }
+  __syncthreads();
+}
+
 // =============================================================================================
 // K4: generator head  (model/backbone.py:73-77,85; model/GANSurv.py:32-49; model/model_utils.py:116-133)
 // grid (bags, samples)
@@ -37,7 +93,7 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
                                                            const float* __restrict__ noise1, int bags, Drop drho,
                                                            Drop dmlp0, float* __restrict__ H, float* __restrict__ H1,
                                                            float* __restrict__ pre, float* __restrict__ pred) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, smp = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int h = p.h, o = p.o, hid = p.hid;
@@ -47,10 +103,20 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
   float* red = H1s + 2 * hid;  // [33]
   for (int c = threadIdx.x; c < h; c += blockDim.x) zs[c] = z[(size_t)b * h + c];
   __syncthreads();
+  const bool vec_ok = (h % 4 == 0) && (o % 4 == 0) && (hid % 4 == 0);   // 16-byte aligned rows for warp_dot4
   if (p.Wrho) {
-    for (int i = wid; i < o; i += nw) {
-      float v = warp_dot(p.Wrho + (size_t)i * h, zs, h, lane);
-      if (lane == 0) Hs[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale(b, i);
+    if (vec_ok) {
+      for (int i0 = wid * 4; i0 < o; i0 += nw * 4) {
+        float v4[4];
+        warp_dot4(p.Wrho, h, i0, o, zs, h, lane, v4);
+        const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
+        if (lane < 4 && i0 + lane < o) Hs[i0 + lane] = fmaxf(vv + p.brho[i0 + lane], 0.f) * drho.scale(b, i0 + lane);
+      }
+    } else {
+      for (int i = wid; i < o; i += nw) {
+        float v = warp_dot(p.Wrho + (size_t)i * h, zs, h, lane);
+        if (lane == 0) Hs[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale(b, i);
+      }
     }
   } else {
     for (int c = threadIdx.x; c < o; c += blockDim.x) Hs[c] = zs[c];
@@ -62,9 +128,18 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
   __syncthreads();
   if (H && smp == 0) for (int c = threadIdx.x; c < o; c += blockDim.x) H[(size_t)b * o + c] = Hs[c];
   if (p.W0 == nullptr) return;  // backbone-only mode (ABMIL.forward without the Generator head)
-  for (int j = wid; j < hid; j += nw) {
-    float v = warp_dot(p.W0 + (size_t)j * in0, Hs, in0, lane);
-    if (lane == 0) H1s[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale(b, j);
+  if (vec_ok) {
+    for (int j0 = wid * 4; j0 < hid; j0 += nw * 4) {
+      float v4[4];
+      warp_dot4(p.W0, in0, j0, hid, Hs, in0, lane, v4);
+      const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
+      if (lane < 4 && j0 + lane < hid) H1s[j0 + lane] = fmaxf(vv + p.b0[j0 + lane], 0.f) * dmlp0.scale(b, j0 + lane);
+    }
+  } else {
+    for (int j = wid; j < hid; j += nw) {
+      float v = warp_dot(p.W0 + (size_t)j * in0, Hs, in0, lane);
+      if (lane == 0) H1s[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale(b, j);
+    }
   }
   const int in1 = hid * (1 + p.noise1);
   if (p.noise1)
@@ -102,11 +177,11 @@ __global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, co
                                                            float inv_keep_mlp0, float* __restrict__ dz,
                                                            float* __restrict__ dHpre, float* __restrict__ dH1pre,
                                                            float* __restrict__ dpre) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   const int h = p.h, o = p.o, hid = p.hid;
-  float* d1 = sm;        // [hid]
-  float* dH = d1 + hid;  // [o]
+  float* d1 = sm;                      // [hid]
+  float* dH = d1 + ((hid + 3) & ~3);   // [o]
   const bool head = p.W0 != nullptr;  // else d_pred is dL/dH [bags,o] (backbone-only mode)
   if (head) {
     float dp = d_pred[b];
@@ -123,32 +198,39 @@ __global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, co
   }
   __syncthreads();
   const int in0 = o * (1 + p.noise0);
+  float* scratch = dH + o;   // [G][max(o, h)] partials of the transposed mat-vecs
+  const bool vec_ok = (o % 4 == 0) && (h % 4 == 0) && (in0 % 4 == 0);
+  if (head && vec_ok) {
+    block_colmat(p.W0, in0, o, d1, hid, scratch, dH);          // dH = W0[:, :o]^T d1
+  } else if (head) {
+    for (int i = threadIdx.x; i < o; i += blockDim.x) dH[i] = col_dot(p.W0, in0, i, d1, hid);
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < o; i += blockDim.x) {
-    float acc = 0.f;
-    if (head) {
-      acc = col_dot(p.W0, in0, i, d1, hid);
-    } else acc = d_pred[(size_t)b * o + i];
+    float acc = head ? dH[i] : d_pred[(size_t)b * o + i];
     if (p.Wrho) acc = H[(size_t)b * o + i] > 0.f ? acc * inv_keep_rho : 0.f;
     dH[i] = acc;
     dHpre[(size_t)b * o + i] = acc;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < h; k += blockDim.x) {
-    float acc;
-    if (p.Wrho) {
-      acc = col_dot(p.Wrho, h, k, dH, o);
-    } else {
-      acc = dH[k];
-    }
-    dz[(size_t)b * h + k] = acc;
+  if (p.Wrho && vec_ok) {
+    float* dzs = scratch + (size_t)(blockDim.x / (h >> 2) > 0 ? blockDim.x / (h >> 2) : 1) * h;
+    block_colmat(p.Wrho, h, h, dH, o, scratch, dzs);           // dz = Wrho^T dH
+    for (int k = threadIdx.x; k < h; k += blockDim.x) dz[(size_t)b * h + k] = dzs[k];
+  } else {
+    for (int k = threadIdx.x; k < h; k += blockDim.x)
+      dz[(size_t)b * h + k] = p.Wrho ? col_dot(p.Wrho, h, k, dH, o) : dH[k];
   }
 }
 
 int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, const float* H1, const float* pred,
                  int bags, float inv_keep_rho, float inv_keep_mlp0, float* dz, float* dHpre, float* dH1pre, float* dpre,
                  cudaStream_t st) {
-  size_t smem = (size_t)(p.hid + p.o) * sizeof(float);
-  gen_head_bwd_kernel<<<bags, 512, smem, st>>>(p, d_pred, H, H1, pred, inv_keep_rho, inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
+  const int wmax = max(p.o, p.h), threads = 512;
+  const int gmax = max(1, threads / (min(p.o, p.h) / 4 > 0 ? min(p.o, p.h) / 4 : 1));
+  size_t smem = ((size_t)(p.hid + p.o) + 16 + (size_t)(gmax + 1) * wmax + 16) * sizeof(float);
+  ADVMIL_REQUIRE(smem <= 48 * 1024, "gen_head_bwd: dims too large for the head kernel (h=%d o=%d)", p.h, p.o);
+  gen_head_bwd_kernel<<<bags, threads, smem, st>>>(p, d_pred, H, H1, pred, inv_keep_rho, inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -188,7 +270,7 @@ __global__ void __launch_bounds__(512) rlip_tail_fwd_kernel(AdvmilDiscParams p, 
                                                             Drop dfc2, float* __restrict__ g1, float* __restrict__ hx,
                                                             float* __restrict__ u1, float* __restrict__ ht,
                                                             float* __restrict__ out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int d = p.d, dh = p.d / 2, t1 = p.t1, t2 = p.t2;
@@ -206,27 +288,40 @@ __global__ void __launch_bounds__(512) rlip_tail_fwd_kernel(AdvmilDiscParams p, 
     u1[(size_t)b * t1 + c] = v;
   }
   __syncthreads();
-  for (int j = wid; j < dh; j += nw) {
-    float v = warp_dot(p.F2a_w + (size_t)j * d, bv, d, lane);
-    if (lane == 0) {
-      v = fmaxf(v + p.F2a_b[j], 0.f) * dfc2.scale(b, j);
+  const bool vec_ok = (d % 8 == 0) && (t1 % 4 == 0) && (t2 % 4 == 0);
+  for (int j0 = wid * 4; j0 < dh; j0 += nw * 4) {
+    float v4[4];
+    if (vec_ok) warp_dot4(p.F2a_w, d, j0, dh, bv, d, lane, v4);
+    else for (int u = 0; u < 4; ++u) v4[u] = j0 + u < dh ? warp_dot(p.F2a_w + (size_t)(j0 + u) * d, bv, d, lane) : 0.f;
+    const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
+    const int j = j0 + lane;
+    if (lane < 4 && j < dh) {
+      const float v = fmaxf(vv + p.F2a_b[j], 0.f) * dfc2.scale(b, j);
       g1s[j] = v;
       g1[(size_t)b * dh + j] = v;
     }
   }
-  for (int j = wid; j < t2; j += nw) {
-    float v = warp_dot(p.T2_w + (size_t)j * t1, u1s, t1, lane);
-    if (lane == 0) {
-      v = fmaxf(v + p.T2_b[j], 0.f);
+  for (int j0 = wid * 4; j0 < t2; j0 += nw * 4) {
+    float v4[4];
+    if (vec_ok) warp_dot4(p.T2_w, t1, j0, t2, u1s, t1, lane, v4);
+    else for (int u = 0; u < 4; ++u) v4[u] = j0 + u < t2 ? warp_dot(p.T2_w + (size_t)(j0 + u) * t1, u1s, t1, lane) : 0.f;
+    const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
+    const int j = j0 + lane;
+    if (lane < 4 && j < t2) {
+      const float v = fmaxf(vv + p.T2_b[j], 0.f);
       hts[j] = v;
       ht[(size_t)b * t2 + j] = v;
     }
   }
   __syncthreads();
-  for (int j = wid; j < d; j += nw) {
-    float v = warp_dot(p.F2b_w + (size_t)j * dh, g1s, dh, lane);
-    if (lane == 0) {
-      v += p.F2b_b[j];
+  for (int j0 = wid * 4; j0 < d; j0 += nw * 4) {
+    float v4[4];
+    if (vec_ok) warp_dot4(p.F2b_w, dh, j0, d, g1s, dh, lane, v4);
+    else for (int u = 0; u < 4; ++u) v4[u] = j0 + u < d ? warp_dot(p.F2b_w + (size_t)(j0 + u) * dh, g1s, dh, lane) : 0.f;
+    const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
+    const int j = j0 + lane;
+    if (lane < 4 && j < d) {
+      const float v = vv + p.F2b_b[j];
       hxs[j] = v;
       hx[(size_t)b * d + j] = v;
     }
@@ -252,13 +347,13 @@ int rlip_tail_fwd(const AdvmilDiscParams& p, const float* bagv, const float* fba
   return ADVMIL_OK;
 }
 
-__global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
+__global__ void __launch_bounds__(512) rlip_tail_bwd_kernel(
     AdvmilDiscParams p, const float* __restrict__ d_out, const float* __restrict__ bagv, const float* __restrict__ fbar,
     const float* __restrict__ g1, const float* __restrict__ hx, const float* __restrict__ u1,
     const float* __restrict__ ht, float inv_keep_fc2, float* __restrict__ d_fbar, float* __restrict__ d_bagv,
     float* __restrict__ d_hx, float* __restrict__ d_g1pre, float* __restrict__ d_htpre, float* __restrict__ d_u1pre,
     float* __restrict__ d_t) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   const int d = p.d, dh = p.d / 2, t1 = p.t1, t2 = p.t2;
   float* dhx = sm;          // [d]
@@ -281,22 +376,33 @@ __global__ void __launch_bounds__(128) rlip_tail_bwd_kernel(
     d_fbar[(size_t)b * d + c] = g_fb;
   }
   __syncthreads();
+  float* scratch = red + 40;      // [G][ncols] partials of the transposed mat-vecs (<= 2048 floats when vec_ok)
+  const bool vec_ok = (d % 8 == 0) && (t1 % 4 == 0) && (t2 % 4 == 0);
+  if (vec_ok) {
+    block_colmat(p.F2b_w, dh, dh, dhx, d, scratch, dg1);       // dg1 = F2b_w^T dhx
+    block_colmat(p.T2_w, t1, t1, dht, t2, scratch, du1);       // du1 = T2_w^T dht
+  } else {
+    for (int j = threadIdx.x; j < dh; j += blockDim.x) dg1[j] = col_dot(p.F2b_w, dh, j, dhx, d);
+    for (int k = threadIdx.x; k < t1; k += blockDim.x) du1[k] = col_dot(p.T2_w, t1, k, dht, t2);
+    __syncthreads();
+  }
   for (int j = threadIdx.x; j < dh; j += blockDim.x) {
-    float acc = col_dot(p.F2b_w, dh, j, dhx, d);
-    acc = g1[(size_t)b * dh + j] > 0.f ? acc * inv_keep_fc2 : 0.f;
+    const float acc = g1[(size_t)b * dh + j] > 0.f ? dg1[j] * inv_keep_fc2 : 0.f;
     dg1[j] = acc;
     d_g1pre[(size_t)b * dh + j] = acc;
   }
   for (int k = threadIdx.x; k < t1; k += blockDim.x) {
-    float acc = col_dot(p.T2_w, t1, k, dht, t2);
-    acc = u1[(size_t)b * t1 + k] > 0.f ? acc : 0.f;
+    const float acc = u1[(size_t)b * t1 + k] > 0.f ? du1[k] : 0.f;
     du1[k] = acc;
     d_u1pre[(size_t)b * t1 + k] = acc;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = col_dot(p.F2a_w, d, c, dg1, dh);
-    d_bagv[(size_t)b * d + c] = acc;
+  if (vec_ok) {
+    float* dbv = scratch + 2048;
+    block_colmat(p.F2a_w, d, d, dg1, dh, scratch, dbv);        // d_bagv = F2a_w^T dg1
+    for (int c = threadIdx.x; c < d; c += blockDim.x) d_bagv[(size_t)b * d + c] = dbv[c];
+  } else {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) d_bagv[(size_t)b * d + c] = col_dot(p.F2a_w, d, c, dg1, dh);
   }
   float acc = 0.f;
   for (int k = threadIdx.x; k < t1; k += blockDim.x) acc = fmaf(p.T1_w[k], du1[k], acc);
@@ -308,8 +414,10 @@ int rlip_tail_bwd(const AdvmilDiscParams& p, const float* d_out, const float* ba
                   const float* hx, const float* u1, const float* ht, int bags, float inv_keep_fc2, float* d_fbar,
                   float* d_bagv, float* d_hx, float* d_g1pre, float* d_htpre, float* d_u1pre, float* d_t,
                   cudaStream_t st) {
-  size_t smem = (size_t)(p.d + p.d / 2 + p.t2 + p.t1 + 40) * sizeof(float);
-  rlip_tail_bwd_kernel<<<bags, 128, smem, st>>>(p, d_out, bagv, fbar, g1, hx, u1, ht, inv_keep_fc2, d_fbar, d_bagv,
+  // scratch of block_colmat: G * ncols <= threads * 4 floats per call, + one [d] result vector
+  size_t smem = (size_t)(p.d + p.d / 2 + p.t2 + p.t1 + 40 + 40 + 2048 + p.d + 16) * sizeof(float);
+  ADVMIL_REQUIRE(smem <= 48 * 1024 && p.d <= 2048, "rlip_tail_bwd: d=%d too large", p.d);
+  rlip_tail_bwd_kernel<<<bags, 512, smem, st>>>(p, d_out, bagv, fbar, g1, hx, u1, ht, inv_keep_fc2, d_fbar, d_bagv,
                                                  d_hx, d_g1pre, d_htpre, d_u1pre, d_t);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;

@@ -87,7 +87,9 @@ typedef struct AdvmilGenGrads { /* same tensors as AdvmilGenParams, written (not
 
 typedef struct AdvmilGenActs {
   void* h;      /* T [rows,h]   relu(+dropout) of the projection; pooled tensor (backbone.py:81-84) */
-  void* ab;     /* T [rows,abw] tanh|sigmoid gate activations, packed column order (see advmil_gate_packed_width); NULL = not saved */
+  void* ab;     /* T [rows,abw] tanh|sigmoid gate activations, packed column order (see advmil_gate_packed_width); NULL = not
+                   saved.  Train mode: the sign of a stored sigmoid is the joint dropout keep bit of its (tanh, sigmoid)
+                   pair (negative = the pair was dropped); its magnitude is the undropped activation. */
   float* s;     /* [rows] attention logits */
   float* w;     /* [rows] softmax weights within each bag */
   float* z;     /* [bags,h] pooled */
