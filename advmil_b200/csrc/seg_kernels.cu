@@ -43,32 +43,31 @@ int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st) {
   return ADVMIL_OK;
 }
 
-// out[c] (+)= sum_p part[p][c]; block (32,8): 8 row groups per column
-__global__ void reduce_rows_kernel(const float* __restrict__ part, int nparts, int width /*row stride*/, int ncols,
-                                   float* __restrict__ out, int accumulate) {
-  __shared__ float sm[32][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.f;
+// out[c] (+)= sum_p part[p][c]; block (8 columns, 128 part lanes): one 32-byte sector per part row, every thread's
+// <= 16 loads independent, grid = ceil(ncols / 8) CTAs
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restrict__ part, int nparts, int width /*row stride*/,
+                                                           int ncols, float* __restrict__ out, int accumulate) {
+  __shared__ float sm[128][9];
+  const int c = blockIdx.x * 8 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < ncols) {
     int p = threadIdx.y;
-    for (; p + 96 < nparts; p += 128) {
-      float a0 = part[(size_t)p * width + c], a1 = part[(size_t)(p + 32) * width + c];
-      float a2 = part[(size_t)(p + 64) * width + c], a3 = part[(size_t)(p + 96) * width + c];
-      acc += (a0 + a1) + (a2 + a3);
+    for (; p + 384 < nparts; p += 512) {
+      a0 += part[(size_t)p * width + c]; a1 += part[(size_t)(p + 128) * width + c];
+      a2 += part[(size_t)(p + 256) * width + c]; a3 += part[(size_t)(p + 384) * width + c];
     }
-    for (; p < nparts; p += 32) acc += part[(size_t)p * width + c];
+    for (; p < nparts; p += 128) a0 += part[(size_t)p * width + c];
   }
-  sm[threadIdx.y][threadIdx.x] = acc;
+  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
   __syncthreads();
-  if (threadIdx.y == 0 && c < ncols) {
-    float t = 0.f;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+  for (int s = 64; s > 0; s >>= 1) {
+    if (threadIdx.y < s) sm[threadIdx.y][threadIdx.x] += sm[threadIdx.y + s][threadIdx.x];
+    __syncthreads();
   }
+  if (threadIdx.y == 0 && c < ncols) out[c] = accumulate ? out[c] + sm[0][threadIdx.x] : sm[0][threadIdx.x];
 }
 static int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
-  reduce_rows_kernel<<<cdiv(width, 32), dim3(32, 32), 0, st>>>(part, nparts, width, width, out, accumulate);
+  reduce_rows_kernel<<<cdiv(width, 8), dim3(8, 128), 0, st>>>(part, nparts, width, width, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -383,7 +382,8 @@ __global__ void bag_dot_kernel(const float* __restrict__ a, const float* __restr
   if (threadIdx.x == 0) out[bag] = acc;
 }
 
-// pass 1: ds[row] = w[row] (dz[bag] . v[row] - dz[bag] . z[bag]); one warp per row, 4 rows in flight per warp
+// pass 1: ds[row] = w[row] (dz[bag] . v[row] - dz[bag] . z[bag]).  8 lanes per row (16-byte vectors interleaved across
+// the 8 lanes: 128 contiguous bytes per row per load instruction), 8 rows in flight per warp, 16 rows per warp in total
 template <typename T>
 __global__ void __launch_bounds__(256) pool_ds_kernel(const T* __restrict__ v, const float* __restrict__ w,
                                                       const float* __restrict__ dz, const float* __restrict__ gz,
@@ -391,31 +391,34 @@ __global__ void __launch_bounds__(256) pool_ds_kernel(const T* __restrict__ v, c
                                                       float* __restrict__ ds) {
   constexpr int VEC = VecN<T>::N;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sub = lane & 7, slot = lane >> 3;
   const int row0 = blockIdx.x * ROWS_PER_CTA + wid * (ROWS_PER_CTA / 8);
   const int rend = min(rows, row0 + ROWS_PER_CTA / 8);
   if (row0 >= rend) return;
-  int cur = bag_of_row(offsets, bags, row0);       // one search per warp, then a monotone walk over its 16 rows
-  int cur_end = offsets[cur + 1];
-  for (int rb = row0; rb < rend; rb += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int bag[4];
+  const int bag0 = bag_of_row(offsets, bags, row0);          // one search per warp; rows are visited in order
+#pragma unroll 1
+  for (int rb = row0; rb < rend; rb += 8) {
+    int r[2], bag[2];
+    bool ok[2];
+    float acc[2] = {0.f, 0.f};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (rb + u < rend) { while (rb + u >= cur_end) { ++cur; cur_end = offsets[cur + 1]; } }
-      bag[u] = cur;
+    for (int u = 0; u < 2; ++u) {
+      r[u] = rb + u * 4 + slot;
+      ok[u] = r[u] < rend;
+      int bg = bag0;
+      if (ok[u]) { while (r[u] >= offsets[bg + 1]) ++bg; }
+      bag[u] = bg;
     }
-    for (int c = lane * VEC; c < L; c += 32 * VEC) {
-      float x[4][VEC];
+    for (int c = sub * VEC; c < L; c += 8 * VEC) {
+      float x[2][VEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (rb + u < rend) ldv(v + (size_t)(rb + u) * L + c, x[u]);
-        else {
+      for (int u = 0; u < 2; ++u) {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) x[u][e] = 0.f;
-        }
+        for (int e = 0; e < VEC; ++e) x[u][e] = 0.f;
+        if (ok[u]) ldv(v + (size_t)r[u] * L + c, x[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const float* dzr = dz + (size_t)bag[u] * L + c;
 #pragma unroll
         for (int q4 = 0; q4 < VEC / 4; ++q4) {
@@ -425,9 +428,9 @@ __global__ void __launch_bounds__(256) pool_ds_kernel(const T* __restrict__ v, c
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float t = warp_sum(acc[u]);
-      if (lane == 0 && rb + u < rend) ds[rb + u] = w[rb + u] * (t - gz[bag[u]]);
+    for (int u = 0; u < 2; ++u) {
+      const float t = oct_sum(acc[u]);
+      if (sub == 0 && ok[u]) ds[r[u]] = w[r[u]] * (t - gz[bag[u]]);
     }
   }
 }
@@ -526,12 +529,12 @@ static int pool_gate_bwd_t(const T* v, const float* w, const float* z, const flo
   ADVMIL_REQUIRE(smem <= 48 * 1024, "pool_gate_bwd: gate width %d needs too much shared memory", abw);
   pool_gate_bwd_kernel<T><<<chunks, threads, smem, st>>>(ds, ab, wc, rows, D, abw, RGN, da, db, dAB, part, part_b);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(D, 32), dim3(32, 32), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
+  reduce_rows_kernel<<<cdiv(D, 8), dim3(8, 128), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<1, dim3(32, 32), 0, st>>>(part + D, chunks, D + 1, 1, dbc, accumulate);
+  reduce_rows_kernel<<<1, dim3(8, 128), 0, st>>>(part + D, chunks, D + 1, 1, dbc, accumulate);
   ADVMIL_CHECK_LAUNCH();
   if (dbp) {   // packed gate-bias gradient (never accumulated: the caller unpacks it with its own accumulate flag)
-    reduce_rows_kernel<<<cdiv(abw, 32), dim3(32, 32), 0, st>>>(part_b, chunks, abw, abw, dbp, 0);
+    reduce_rows_kernel<<<cdiv(abw, 8), dim3(8, 128), 0, st>>>(part_b, chunks, abw, abw, dbp, 0);
     ADVMIL_CHECK_LAUNCH();
   }
   return ADVMIL_OK;
@@ -757,11 +760,11 @@ int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, cons
   else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
+  reduce_rows_kernel<<<cdiv(d, 8), dim3(8, 128), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws + d, chunks, 3 * d, d, dbeta, accumulate);
+  reduce_rows_kernel<<<cdiv(d, 8), dim3(8, 128), 0, st>>>(ws + d, chunks, 3 * d, d, dbeta, accumulate);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 32), dim3(32, 32), 0, st>>>(ws + 2 * d, chunks, 3 * d, d, dbias, accumulate);
+  reduce_rows_kernel<<<cdiv(d, 8), dim3(8, 128), 0, st>>>(ws + 2 * d, chunks, 3 * d, d, dbias, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

@@ -31,6 +31,14 @@ class PinnedStep:
     idx: torch.Tensor          # [bags] int32 (dataset indices)
     visible: torch.Tensor      # [bags] uint8 (label_visible_mask, model_handler.py:591-596)
     cluster_id: Optional[torch.Tensor] = None   # [rows] int32 (cluster mode)
+    offsets: Optional[torch.Tensor] = None      # [bags+1] int32 prefix sums of lengths, pinned
+
+    def __post_init__(self):
+        if self.offsets is None:
+            offs = [0]
+            for n in self.lengths:
+                offs.append(offs[-1] + int(n))
+            self.offsets = _pin(torch.tensor(offs, dtype=torch.int32))
 
     @property
     def nbytes(self) -> int:
@@ -141,14 +149,16 @@ class DeviceFeeder:
             buf = torch.empty(rows, C, dtype=st.x.dtype, device=self.device)
             self._xbuf[slot] = buf
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self._free[slot])          # consumer finished with this slot
-            xd = buf[:rows]
-            xd.copy_(st.x, non_blocking=True)
+            # labels and offsets first (pinned, asynchronous: nothing here blocks the host), then the features
             t = st.t.to(self.device, non_blocking=True)
             e = st.e.to(self.device, non_blocking=True)
             vis = st.visible.to(self.device, non_blocking=True)
+            offs = st.offsets.to(self.device, non_blocking=True)
             cid = None if st.cluster_id is None else st.cluster_id.to(self.device, non_blocking=True)
-            bags = PackedBags(xd, st.lengths)                        # offsets: small H2D on the copy stream
+            self.copy_stream.wait_event(self._free[slot])          # consumer finished with this slot
+            xd = buf[:rows]
+            xd.copy_(st.x, non_blocking=True)
+            bags = PackedBags(xd, st.lengths, offsets=offs)
             self._ready[slot].record(self.copy_stream)
         n_real = float(((st.e == 1) & (st.visible != 0)).sum())
         counts = (n_real, float(len(st.lengths)), float(st.visible.sum()))
@@ -168,6 +178,9 @@ class DeviceFeeder:
         while pending:
             cur = pending.pop(0)
             torch.cuda.current_stream().wait_event(self._ready[cur._slot])
+            for ten in (cur.t, cur.e, cur.visible, cur.bags.offsets, cur.cluster_id):
+                if ten is not None:
+                    ten.record_stream(torch.cuda.current_stream())   # allocated on the copy stream, consumed here
             if prev is not None:
                 self._free[prev._slot].record(torch.cuda.current_stream())
             st = next(it, None)

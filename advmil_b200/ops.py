@@ -75,7 +75,9 @@ def _cached_cast(x: torch.Tensor) -> torch.Tensor:
 class PackedBags:
     """Packed variable-length bags: x [rows, C] fp32 (or bf16 for the bf16 mode) + int32 offsets [bags+1] (AdvmilBags)."""
 
-    def __init__(self, x: torch.Tensor, lengths: Sequence[int]):
+    def __init__(self, x: torch.Tensor, lengths: Sequence[int], offsets: Optional[torch.Tensor] = None):
+        """offsets: optional int32 device tensor [bags+1] already holding the prefix sums of `lengths` (the asynchronous
+        feeder copies it from pinned memory; building it here costs a synchronous pageable H2D copy)."""
         _need_cuda(x, "bag features")
         assert x.dim() == 2, "packed features must be [rows, C]"
         self.x = (x if x.is_contiguous() else x.contiguous()) if x.dtype == torch.bfloat16 else _f32c(x)
@@ -87,7 +89,7 @@ class PackedBags:
             offs.append(offs[-1] + n)
         self.offsets_list = offs
         self.offsets_host = (C.c_int32 * len(offs))(*offs)
-        self.offsets = torch.tensor(offs, dtype=torch.int32, device=x.device)
+        self.offsets = torch.tensor(offs, dtype=torch.int32, device=x.device) if offsets is None else offsets
         self.rows, self.C = self.x.shape
         self.bags = len(self.lengths)
 
