@@ -122,7 +122,7 @@ extern "C" size_t advmil_generator_workspace_bytes(const AdvmilGenParams* p, int
     f += abw * h + abw + 512;                                 // packed gate weight grads
     f += pool_gate_ws_floats(rows, bags, (int)h) + 256;       // pool_gate partials
     f += max(bwd_weight_ws_floats(rows, (int)abw, (int)h), bwd_weight_ws_floats(rows, (int)h, (int)C)) + 256;
-    f += (size_t)row_chunks(rows) * max(abw, h) + 256;        // colsum partials
+    f += (size_t)4 * row_chunks(rows) * max(abw, h) + 256;    // colsum partials
   }
   return f * sizeof(float) + 64 * 256;
 }
@@ -150,9 +150,10 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
   else { ProfScope ps(PROF_PROJ, st); ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st)); }
   { ProfScope ps(PROF_GEN_TAIL, st); ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st)); }
   { ProfScope ps(PROF_GATE, st);
-    ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, a->s, part, a->precision, st)); }
+    ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, nullptr, part, a->precision, st)); }
   { ProfScope ps(PROF_POOL, st);
-    ADVMIL_TRY(seg_softmax_pool_fwd(a->s, a->h, dt, bags->offsets, bags->offsets_host, rows, nb, h, a->w, a->z, nullptr, poolws, st)); }
+    ADVMIL_TRY(seg_softmax_pool_fwd(a->s, part, abw / 128, p->bc, a->h, dt, bags->offsets, bags->offsets_host, rows, nb, h, a->w,
+                                    a->z, nullptr, poolws, st)); }
   { ProfScope ps(PROF_GEN_TAIL, st);
     ADVMIL_TRY(gen_head_fwd(*p, a->z, a->noise0, a->noise1, nb, 1, drho, dmlp0, a->H, a->H1, a->pre, a->pred, st)); }
   return ADVMIL_OK;
@@ -181,7 +182,7 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   WS_TAKE(dbp, float, abw);
   WS_TAKE(pgws, float, pool_gate_ws_floats(rows, nb, h));
   WS_TAKE(bwws, float, max(bwd_weight_ws_floats(rows, abw, h), bwd_weight_ws_floats(rows, h, C)));
-  WS_TAKE(csws, float, (size_t)row_chunks(rows) * max(abw, h));
+  WS_TAKE(csws, float, (size_t)4 * row_chunks(rows) * max(abw, h));
   const float ik_bb = (a->train && p->p_backbone > 0.f) ? 1.f / (1.f - p->p_backbone) : 1.f;
   const float ik_hd = (a->train && p->p_head > 0.f) ? 1.f / (1.f - p->p_head) : 1.f;
   Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train, p->h);
@@ -201,12 +202,16 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
     ADVMIL_TRY(pool_gate_bwd(a->h, a->w, a->z, dz, a->ab, p->wc, bags->offsets, rows, nb, h, h, da, db, dAB, g->wc, g->bc, dbp, 0, pgws, dt, st)); }
   BwdDataExtras ex;
   ex.w = a->w; ex.dz = dz; ex.offsets = bags->offsets; ex.bags = nb; ex.relu_src = a->h; ex.ld_src = h; ex.inv_keep = ik_bb;
+  const bool fused_b1 = bwd_data_fuses_colsum(rows, abw, h, prec);   // db1 = column sums of dh: from the GEMM epilogue
+  if (fused_b1) ex.colsum_part = csws;
   { ProfScope ps(PROF_BWD_DATA, st); ADVMIL_TRY(bwd_data(dAB, Wp, rows, abw, h, dhpre, ex, prec, st)); }
   { ProfScope ps(PROF_BWD_W_GATE, st); ADVMIL_TRY(bwd_weight(dAB, a->h, rows, abw, h, dWp, 0, bwws, prec, st)); }
   { ProfScope ps(PROF_GEN_TAIL, st); ADVMIL_TRY(gate_unpack_grads(dWp, dbp, h, h, g->Wa, g->ba, g->Wb, g->bb, 0, st)); }
   // first layer
   { ProfScope ps(PROF_BWD_W_PROJ, st); ADVMIL_TRY(bwd_weight(dhpre, bags->x, rows, h, C, g->W1, 0, bwws, prec, st)); }
-  { ProfScope ps(PROF_COLSUM, st); ADVMIL_TRY(colsum(dhpre, dt, rows, h, h, g->b1, 0, csws, st)); }
+  { ProfScope ps(PROF_COLSUM, st);
+    if (fused_b1) ADVMIL_TRY(reduce_rows(csws, 4 * cdiv(rows, 128), h, g->b1, 0, st));
+    else ADVMIL_TRY(colsum(dhpre, dt, rows, h, h, g->b1, 0, csws, st)); }
   if (g->dx) {
     BwdDataExtras exx;
     ADVMIL_TRY(bwd_data(dhpre, p->W1, rows, h, C, g->dx, exx, prec, st));
@@ -322,8 +327,9 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, rp, st));
   ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, rp, st));
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
-  ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, a->rep, part, rp, st));
-  ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, a->fi, ELEM_F32, ro.dev, ro.host.data(), R, nb, d, a->attn, a->bagv, a->fbar, poolws, st));
+  ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, nullptr, part, rp, st));
+  ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, part, abw / 128, p->Pc_b, a->fi, ELEM_F32, ro.dev, ro.host.data(), R, nb, d, a->attn,
+                                  a->bagv, a->fbar, poolws, st));
   ADVMIL_TRY(rlip_tail_fwd(*p, a->bagv, a->fbar, a->t, nb, dfc2, a->g1, a->hx, a->u1, a->ht, a->out, st));
   return ADVMIL_OK;
 }
@@ -474,5 +480,6 @@ extern "C" int advmil_seg_softmax_pool_fwd(const float* s, const void* v, int32_
   Workspace ws(workspace, workspace_bytes);
   WS_TAKE(poolws, float, seg_pool_ws_floats(rows, bags, width));
   ADVMIL_REQUIRE(elem == ELEM_F32 || elem == ELEM_BF16, "seg_softmax_pool_fwd: unknown element type %d", elem);
-  return seg_softmax_pool_fwd(s, v, elem, offsets, offsets_host, rows, bags, width, w, z, mean, poolws, (cudaStream_t)stream);
+  return seg_softmax_pool_fwd(const_cast<float*>(s), nullptr, 0, nullptr, v, elem, offsets, offsets_host, rows, bags, width, w, z,
+                              mean, poolws, (cudaStream_t)stream);
 }

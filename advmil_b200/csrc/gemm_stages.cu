@@ -37,6 +37,7 @@ int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float
   GemmArgs g{(const float*)v, Wp, rows, abw, L, L, L, L};
   EpiGate epi{(float*)ab, abw, bp, wc, part_ws, D, da, db};
   ADVMIL_TRY((launch_gemm<true, true>(g, epi, 1, st)));
+  if (s == nullptr) return ADVMIL_OK;
   return gate_score_finish(part_ws, abw / 128, rows, bc, s, st);
 }
 
@@ -51,6 +52,10 @@ int region_embed_fwd(const void* x, const float* Wc, const float* bc, const floa
   GemmArgs g{(const float*)x, Wc, rows, d, C, C, C, C};
   EpiLNPool epi{(float*)y_pre, emb, bc, gamma, beta, d, eps};
   return launch_gemm<true, true>(g, epi, 1, st);
+}
+
+bool bwd_data_fuses_colsum(int rows, int Ny, int Nx, int precision) {
+  return rows > 0 && precision != ADVMIL_FP32 && tc_bwd_data_supported(rows, Ny, Nx, elem_of_precision(precision));
 }
 
 int bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX, const BwdDataExtras& ex,

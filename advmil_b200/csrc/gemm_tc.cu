@@ -93,6 +93,7 @@ struct RowEpi {
   void* y_pre; float* emb; const float* gamma; const float* beta; float eps;     // EPI_LN
   const float* w; const float* dz; const int32_t* offsets; int bags;             // EPI_BWD
   const float* dmean; int accumulate;
+  float* colpart;                                                                // EPI_BWD: [4 * num_m][N] column sums of dX per 32 rows
   const void* relu_src; int ld_src; float inv_keep;
 };
 
@@ -346,6 +347,9 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ch + 2 >= NCH) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
           stage_chunk(stg, STG_LD, 0, v, lane);
           __syncwarp();
+          float cs[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) cs[e] = 0.f;
 #pragma unroll
           for (int it2 = 0; it2 < NIT; ++it2) {
             const int r = lane / LPR + RPI * it2, cv = lane % LPR;
@@ -413,8 +417,25 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int e = 0; e < VEC; ++e) o[e] += pv[e];
                 }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) cs[e] += o[e];
               }
               stv(outp + (size_t)m * ea.ldo + col, o);
+            }
+          }
+          if constexpr (EPI == EPI_BWD) {
+            if (ea.colpart) {     // bias gradient for free: column sums of this warp's 32 rows (lanes with equal cv fold)
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) {
+#pragma unroll
+                for (int sh = LPR; sh < 32; sh <<= 1) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], sh);
+              }
+              if (lane < LPR) {
+                float* dst = ea.colpart + (size_t)(mt * 4 + wq) * N + n0 + ch * 32 + lane * VEC;
+#pragma unroll
+                for (int q = 0; q < VEC / 4; ++q)
+                  *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(cs[4 * q], cs[4 * q + 1], cs[4 * q + 2], cs[4 * q + 3]);
+              }
             }
           }
           __syncwarp();
@@ -785,6 +806,7 @@ int tc_gated_score_fwd(const void* v, const float* Wp, const float* bp, const fl
   if (precision == ADVMIL_BF16) ADVMIL_TRY((tc_gate_t<bf16, true>(v, Wp, bp, wc, rows, L, D, da, db, ab, part, st)));
   else if (precision == ADVMIL_TF32) ADVMIL_TRY((tc_gate_t<float, true>(v, Wp, bp, wc, rows, L, D, da, db, ab, part, st)));
   else ADVMIL_TRY((tc_gate_t<float, false>(v, Wp, bp, wc, rows, L, D, da, db, ab, part, st)));
+  if (s == nullptr) return ADVMIL_OK;      // the pooling kernel assembles the logits from the partials
   return gate_score_finish(part, gate_width(D) / 128, rows, bc, s, st);
 }
 
@@ -832,7 +854,7 @@ static int tc_bwd_data_t(const void* dY, const float* W, int rows, int Ny, int N
   ADVMIL_CHECK_LAUNCH();
   RowEpi ea{};
   ea.out = dX; ea.ldo = Nx; ea.w = ex.w; ea.dz = ex.dz; ea.offsets = ex.offsets; ea.bags = ex.bags;
-  ea.dmean = ex.dmean; ea.accumulate = ex.accumulate;
+  ea.dmean = ex.dmean; ea.accumulate = ex.accumulate; ea.colpart = ex.colsum_part;
   ea.relu_src = ex.relu_src; ea.ld_src = ex.ld_src; ea.inv_keep = ex.inv_keep;
   return launch_rows_any<T, EPI_BWD, true>((const T*)dY, (const T*)wt, rows, Ny, Nx, ea, st);
 }

@@ -52,9 +52,12 @@ __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restri
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < ncols) {
     int p = threadIdx.y;
-    for (; p + 384 < nparts; p += 512) {
-      a0 += part[(size_t)p * width + c]; a1 += part[(size_t)(p + 128) * width + c];
-      a2 += part[(size_t)(p + 256) * width + c]; a3 += part[(size_t)(p + 384) * width + c];
+    for (; p + 7 * 128 < nparts; p += 8 * 128) {     // 8 independent loads in flight
+      const float v0 = part[(size_t)p * width + c], v1 = part[(size_t)(p + 128) * width + c];
+      const float v2 = part[(size_t)(p + 256) * width + c], v3 = part[(size_t)(p + 384) * width + c];
+      const float v4 = part[(size_t)(p + 512) * width + c], v5 = part[(size_t)(p + 640) * width + c];
+      const float v6 = part[(size_t)(p + 768) * width + c], v7 = part[(size_t)(p + 896) * width + c];
+      a0 += v0 + v4; a1 += v1 + v5; a2 += v2 + v6; a3 += v3 + v7;
     }
     for (; p < nparts; p += 128) a0 += part[(size_t)p * width + c];
   }
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restri
   }
   if (threadIdx.y == 0 && c < ncols) out[c] = accumulate ? out[c] + sm[0][threadIdx.x] : sm[0][threadIdx.x];
 }
-static int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
+int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
   reduce_rows_kernel<<<cdiv(width, 8), dim3(8, 128), 0, st>>>(part, nparts, width, width, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
@@ -215,42 +218,50 @@ int gate_score_finish(const float* part, int ntiles, int rows, const float* bc, 
 // =============================================================================================
 // K3: segmented softmax + attention pooling (model/backbone.py:82-84; backbone_utils.py:53-55)
 // =============================================================================================
-constexpr int POOL_CH = 128;  // rows per pooling chunk
+constexpr int POOL_CH = 256;  // rows per pooling chunk (1024 CTAs at the benchmark size: ~7 per SM)
 
-__global__ void seg_stats_kernel(const float* __restrict__ s, const int32_t* __restrict__ offsets,
-                                 float* __restrict__ stats /*[bags][2] = max, 1/sum*/) {
-  __shared__ float red[33];
-  int b = blockIdx.x;
-  int beg = offsets[b], end = offsets[b + 1];
-  float mx = -INFINITY;
-  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) mx = fmaxf(mx, s[i]);
-  mx = block_max(mx, red);
-  float sum = 0.f;
-  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) sum += expf(s[i] - mx);
-  sum = block_sum(sum, red);
-  if (threadIdx.x == 0) { stats[2 * b] = mx; stats[2 * b + 1] = 1.0f / sum; }
-}
-
+// One pass over v (online softmax): chunk c of a bag computes its own max m_c, l_c = sum exp(s - m_c) and the partial
+// z_c = sum exp(s - m_c) v; the final kernel rescales by exp(m_c - M).  When `sparts` is given the logits are first
+// assembled from the gate kernel's per-tile partial scores (s = sum_t sparts[t][row] + bc) and written to s.
 // grid (maxchunks, bags); threads = RG row groups x WV 16-byte vectors per row
 template <typename T>
 __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
-    const float* __restrict__ s, const T* __restrict__ v, const int32_t* __restrict__ offsets,
-    const float* __restrict__ stats, int width, int want_mean, float* __restrict__ w,
-    float* __restrict__ part /*[offsets[b]/POOL_CH + b + chunk][width]*/, float* __restrict__ part_mean) {
+    float* __restrict__ s, const float* __restrict__ sparts, int ntiles, int rows, const float* __restrict__ bc,
+    const T* __restrict__ v, const int32_t* __restrict__ offsets, int width, int want_mean,
+    float* __restrict__ cstats /*[chunk][2] = m_c, l_c*/, float* __restrict__ part /*[offsets[b]/POOL_CH + b + chunk][width]*/,
+    float* __restrict__ part_mean) {
   constexpr int VEC = VecN<T>::N;
   extern __shared__ float sm[];  // w_s[POOL_CH] + red[RG][width] (+ red_mean)
+  __shared__ float redb[33];
   int b = blockIdx.y, chunk = blockIdx.x;
   int beg = offsets[b] + chunk * POOL_CH, end = min(offsets[b + 1], beg + POOL_CH);
   if (beg >= offsets[b + 1]) return;
   int nrows = end - beg;
+  const size_t ci = (size_t)(offsets[b] / POOL_CH + b + chunk);
   float* w_s = sm;
-  float mx = stats[2 * b], inv = stats[2 * b + 1];
+  float mx = -INFINITY;
   for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
-    float wv = expf(s[beg + r] - mx) * inv;
-    w_s[r] = wv;
-    w[beg + r] = wv;
+    float sv;
+    if (sparts) {
+      float acc = 0.f;
+      for (int t = 0; t < ntiles; ++t) acc += sparts[(size_t)t * rows + beg + r];
+      sv = acc + bc[0];
+      s[beg + r] = sv;
+    } else {
+      sv = s[beg + r];
+    }
+    w_s[r] = sv;
+    mx = fmaxf(mx, sv);
   }
-  __syncthreads();
+  mx = block_max(mx, redb);
+  float lsum = 0.f;
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+    const float pv = expf(w_s[r] - mx);
+    w_s[r] = pv;
+    lsum += pv;
+  }
+  lsum = block_sum(lsum, redb);   // (ends with a barrier: w_s is visible to every thread below)
+  if (threadIdx.x == 0) { cstats[2 * ci] = mx; cstats[2 * ci + 1] = lsum; }
   const int WV = width / VEC;
   int RG = blockDim.x / WV; if (RG > POOL_CH) RG = POOL_CH;
   const int cv = threadIdx.x % WV, rg = threadIdx.x / WV;
@@ -292,38 +303,56 @@ __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float t = 0.f, tm = 0.f;
     for (int g = 0; g < RG; ++g) { t += red[(size_t)g * width + c]; if (want_mean) tm += redm[(size_t)g * width + c]; }
-    size_t o = ((size_t)(offsets[b] / POOL_CH + b + chunk)) * width + c;
-    part[o] = t;
-    if (want_mean) part_mean[o] = tm;
+    part[ci * width + c] = t;
+    if (want_mean) part_mean[ci * width + c] = tm;
   }
 }
 
-__global__ void seg_pool_final_kernel(const float* __restrict__ part, const float* __restrict__ part_mean,
-                                      const int32_t* __restrict__ offsets, int width,
-                                      float* __restrict__ z, float* __restrict__ mean) {
-  // blockDim = (128 columns, 8 chunk groups); grid = (ceil(width/128), bags)
-  __shared__ float sm[2][8][128];
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  const int len = offsets[b + 1] - offsets[b];
+// grid (max(maxchunks, ceil(width/32)), bags), 256 threads.  Every CTA derives the bag statistics M = max m_c,
+// L = sum l_c exp(m_c - M) from the chunk statistics; CTA x < #chunks writes the softmax weights of chunk x; CTA
+// x < ceil(width/32) combines 32 columns of z (8 chunk groups, then a shared-memory fold).
+__global__ void __launch_bounds__(256) seg_pool_final_kernel(const float* __restrict__ s, const float* __restrict__ cstats,
+                                                             const float* __restrict__ part, const float* __restrict__ part_mean,
+                                                             const int32_t* __restrict__ offsets, int width,
+                                                             float* __restrict__ w, float* __restrict__ z, float* __restrict__ mean) {
+  __shared__ float redb[33];
+  __shared__ float sm[2][8][33];
+  const int b = blockIdx.y, x = blockIdx.x;
+  const int beg_bag = offsets[b], len = offsets[b + 1] - beg_bag;
   const int nch = (len + POOL_CH - 1) / POOL_CH;
-  float t = 0.f, tm = 0.f;
-  if (c < width) {
-    const size_t base = ((size_t)(offsets[b] / POOL_CH + b)) * width + c;
-    for (int k = threadIdx.y; k < nch; k += 8) {
-      t += part[base + (size_t)k * width];
-      if (mean) tm += part_mean[base + (size_t)k * width];
-    }
+  const size_t base = (size_t)(beg_bag / POOL_CH + b);
+  const bool wrole = x < nch, zrole = x * 32 < width;
+  if (!wrole && !zrole) return;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) mx = fmaxf(mx, cstats[2 * (base + c)]);
+  mx = block_max(mx, redb);
+  float L = 0.f;
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) L += cstats[2 * (base + c) + 1] * expf(cstats[2 * (base + c)] - mx);
+  L = block_sum(L, redb);
+  const float invL = 1.0f / L;
+  if (wrole) {
+    const int beg = beg_bag + x * POOL_CH, nrows = min(POOL_CH, len - x * POOL_CH);
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) w[beg + r] = expf(s[beg + r] - mx) * invL;
   }
-  sm[0][threadIdx.y][threadIdx.x] = t;
-  sm[1][threadIdx.y][threadIdx.x] = tm;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < width) {
-    float a = 0.f, am = 0.f;
+  if (zrole) {
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5, col = x * 32 + lane;
+    float t = 0.f, tm = 0.f;
+    if (col < width) {
+      for (int c = g; c < nch; c += 8) {
+        const float f = expf(cstats[2 * (base + c)] - mx);
+        t = fmaf(part[(base + c) * width + col], f, t);
+        if (mean) tm += part_mean[(base + c) * width + col];
+      }
+    }
+    sm[0][g][lane] = t; sm[1][g][lane] = tm;
+    __syncthreads();
+    if (g == 0 && col < width) {
+      float a = 0.f, am = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) { a += sm[0][g][threadIdx.x]; am += sm[1][g][threadIdx.x]; }
-    z[(size_t)b * width + c] = a;
-    if (mean) mean[(size_t)b * width + c] = am / (float)len;
+      for (int k = 0; k < 8; ++k) { a += sm[0][k][lane]; am += sm[1][k][lane]; }
+      z[(size_t)b * width + col] = a * invL;
+      if (mean) mean[(size_t)b * width + col] = am / (float)len;
+    }
   }
 }
 
@@ -334,39 +363,41 @@ static int pool_maxchunks(const int32_t* offsets_host, int bags) {
 }
 size_t seg_pool_ws_floats(int rows, int bags, int width) {
   size_t nparts = (size_t)rows / POOL_CH + bags + 1;  // sum_b ceil(len_b / POOL_CH) <= rows/POOL_CH + bags
-  return align_up(2 * (size_t)bags, 64) + 2 * nparts * width;
+  return align_up(2 * nparts, 64) + 2 * nparts * width;
 }
 template <typename T>
-static int seg_softmax_pool_fwd_t(const float* s, const T* v, const int32_t* offsets, const int32_t* offsets_host, int rows,
-                                  int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st) {
+static int seg_softmax_pool_fwd_t(float* s, const float* sparts, int ntiles, const float* bc, const T* v, const int32_t* offsets,
+                                  const int32_t* offsets_host, int rows, int bags, int width, float* w, float* z, float* mean,
+                                  float* ws, cudaStream_t st) {
   constexpr int VEC = VecN<T>::N;
   ADVMIL_REQUIRE(width % VEC == 0 && width <= 1024, "seg_softmax_pool: width %d must be a multiple of %d and <= 1024", width, VEC);
   for (int b = 0; b < bags; ++b)
     ADVMIL_REQUIRE(offsets_host[b + 1] > offsets_host[b], "seg_softmax_pool: bag %d is empty", b);
   int maxchunks = pool_maxchunks(offsets_host, bags);
-  float* stats = ws;
-  float* part = ws + align_up(2 * (size_t)bags, 64);
-  float* part_mean = part + ((size_t)rows / POOL_CH + bags + 1) * width;
-  seg_stats_kernel<<<bags, 1024, 0, st>>>(s, offsets, stats);
-  ADVMIL_CHECK_LAUNCH();
+  const size_t nparts = (size_t)rows / POOL_CH + bags + 1;
+  float* cstats = ws;
+  float* part = ws + align_up(2 * nparts, 64);
+  float* part_mean = part + nparts * width;
   const int WV = width / VEC;
   int threads = 256;                                   // whole row groups when the row divides a 512/384-thread block
   if ((8 * WV) % 32 == 0 && 8 * WV <= 512) threads = 8 * WV;
   else if ((4 * WV) % 32 == 0 && 4 * WV <= 512) threads = 4 * WV;
   int RG = min(threads / WV, POOL_CH);
   size_t smem = (POOL_CH + (size_t)RG * width * (mean ? 2 : 1)) * sizeof(float);
-  seg_pool_partial_kernel<T><<<dim3(maxchunks, bags), threads, smem, st>>>(s, v, offsets, stats, width, mean ? 1 : 0, w,
-                                                                        part, part_mean);
+  seg_pool_partial_kernel<T><<<dim3(maxchunks, bags), threads, smem, st>>>(s, sparts, ntiles, rows, bc, v, offsets, width,
+                                                                        mean ? 1 : 0, cstats, part, part_mean);
   ADVMIL_CHECK_LAUNCH();
-  seg_pool_final_kernel<<<dim3(cdiv(width, 128), bags), dim3(128, 8), 0, st>>>(part, mean ? part_mean : nullptr, offsets, width, z, mean);
+  seg_pool_final_kernel<<<dim3(max(maxchunks, cdiv(width, 32)), bags), 256, 0, st>>>(s, cstats, part, mean ? part_mean : nullptr,
+                                                                                     offsets, width, w, z, mean);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
-int seg_softmax_pool_fwd(const float* s, const void* v, int dt, const int32_t* offsets, const int32_t* offsets_host,
-                         int rows, int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st) {
+int seg_softmax_pool_fwd(float* s, const float* sparts, int ntiles, const float* bc, const void* v, int dt, const int32_t* offsets,
+                         const int32_t* offsets_host, int rows, int bags, int width, float* w, float* z, float* mean, float* ws,
+                         cudaStream_t st) {
   if (dt == ELEM_BF16)
-    return seg_softmax_pool_fwd_t<bf16>(s, (const bf16*)v, offsets, offsets_host, rows, bags, width, w, z, mean, ws, st);
-  return seg_softmax_pool_fwd_t<float>(s, (const float*)v, offsets, offsets_host, rows, bags, width, w, z, mean, ws, st);
+    return seg_softmax_pool_fwd_t<bf16>(s, sparts, ntiles, bc, (const bf16*)v, offsets, offsets_host, rows, bags, width, w, z, mean, ws, st);
+  return seg_softmax_pool_fwd_t<float>(s, sparts, ntiles, bc, (const float*)v, offsets, offsets_host, rows, bags, width, w, z, mean, ws, st);
 }
 
 // =============================================================================================

@@ -10,7 +10,8 @@ namespace advmil {
 // granularity are always fp32.
 int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
                void* y, int precision, cudaStream_t st);
-// packed gate weights Wp [abw, L], bp [abw] (zero padded) must have been built by gate_pack_weights
+// packed gate weights Wp [abw, L], bp [abw] (zero padded) must have been built by gate_pack_weights.
+// s == nullptr: only the per-tile partial scores part_ws [abw/128][rows] are produced (seg_softmax_pool_fwd finishes them)
 int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
                     int D, const Drop& da, const Drop& db, void* ab, float* s, float* part_ws, int precision,
                     cudaStream_t st);
@@ -22,7 +23,10 @@ struct BwdDataExtras {
   const int32_t* offsets = nullptr; int bags = 0;
   const void* relu_src = nullptr; int ld_src = 0; float inv_keep = 1.f;
   int accumulate = 0;
+  float* colsum_part = nullptr;   // tcgen05 engine only: [4 * ceil(rows/128)][Nx] column sums of dX per 32 rows (bias gradient)
 };
+// true when bwd_data(..., precision) will run on the tcgen05 engine and therefore fills ex.colsum_part
+bool bwd_data_fuses_colsum(int rows, int Ny, int Nx, int precision);
 int bwd_data(const void* dY, const float* W, int rows, int Ny, int Nx, void* dX, const BwdDataExtras& ex,
              int precision, cudaStream_t st);
 // dW[N1,N2] (+)= dY[rows,N1]^T . X[rows,N2]   (split-K over rows; ws >= bwd_weight_ws_floats floats)
@@ -37,8 +41,11 @@ int gate_unpack_grads(const float* dWp, const float* dbp, int L, int D, float* d
                       int accumulate, cudaStream_t st);
 int gate_score_finish(const float* part, int ntiles, int rows, const float* bc, float* s, cudaStream_t st);
 size_t seg_pool_ws_floats(int rows, int bags, int width);
-int seg_softmax_pool_fwd(const float* s, const void* v, int dt, const int32_t* offsets, const int32_t* offsets_host,
-                         int rows, int bags, int width, float* w, float* z, float* mean, float* ws, cudaStream_t st);
+// sparts != nullptr: the logits are assembled here from the gate kernel's per-tile partial scores (sparts [ntiles][rows],
+// + bc[0]) and written to s (gated_score_fwd was called with s == nullptr); else s is read.
+int seg_softmax_pool_fwd(float* s, const float* sparts, int ntiles, const float* bc, const void* v, int dt, const int32_t* offsets,
+                         const int32_t* offsets_host, int rows, int bags, int width, float* w, float* z, float* mean, float* ws,
+                         cudaStream_t st);
 // rows_per_cta used by the row-chunked backward kernels (partials are [nchunks, ...])
 constexpr int ROWS_PER_CTA = 128;
 inline int row_chunks(int rows) { return cdiv(rows, ROWS_PER_CTA); }
@@ -62,6 +69,7 @@ int disc_embed_bwd_impl(const AdvmilDiscParams* p, const AdvmilBags* bags, const
                         const float* d_emb2, AdvmilDiscGrads* g, int accumulate, cudaStream_t st);
 int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accumulate, float* ws /* >= row_chunks*N */,
            cudaStream_t st);
+int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st);
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st);
 int apply_dropout(const void* src, int rows, int width, const Drop& drop, void* dst, int dt, cudaStream_t st);
 int fill_zero(float* p, size_t n, cudaStream_t st);
