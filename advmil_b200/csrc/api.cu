@@ -365,6 +365,7 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
     ADVMIL_TRY(outer_sum(d_u1pre, a->t, 1, nullptr, 0, nb, t1, g->T1_w, g->T1_b, accumulate, st));
     if (p->prj_path == 1) ADVMIL_TRY(outer_sum(d_out, a->hx, d, nullptr, 0, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
     else if (p->prj_path == 2) ADVMIL_TRY(outer_sum(d_out, a->ht, t2, nullptr, 0, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
+    else if (p->prj_path == 3) ADVMIL_TRY(outer_sum(d_out, a->hx, d, a->ht, t2, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
   }
   WS_TAKE(Wp, float, (size_t)abw * d);
   WS_TAKE(bp, float, abw);
@@ -384,7 +385,7 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
                            g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? dbp : nullptr, g ? accumulate : 0, pgws,
                            ELEM_F32, st));
   BwdDataExtras ex;
-  ex.w = a->attn; ex.dz = d_bagv; ex.dmean = p->inner_instance ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
+  ex.w = a->attn; ex.dz = d_bagv; ex.dmean = (p->inner_instance && p->prj_path != 3) ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
   ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, rp, st));
   if (g) {
     ADVMIL_TRY(bwd_weight(dAB, a->fi, R, abw, d, dWp, 0, bwws, rp, st));

@@ -329,6 +329,11 @@ __global__ void __launch_bounds__(512) rlip_tail_fwd_kernel(AdvmilDiscParams p, 
   __syncthreads();
   float acc = 0.f;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (p.prj_path == 3) {      // concat discriminator (model/GANSurv.py:52-68): out = fc([hx | ht]), no inner product
+      acc = fmaf(p.Pr_w[c], hxs[c], acc);
+      acc = fmaf(p.Pr_w[d + c], hts[c], acc);
+      continue;
+    }
     float left = p.inner_instance ? fbar[(size_t)b * d + c] : hxs[c];
     acc = fmaf(left, hts[c], acc);
     if (p.prj_path == 1) acc = fmaf(p.Pr_w[c], hxs[c], acc);
@@ -365,7 +370,8 @@ __global__ void __launch_bounds__(512) rlip_tail_bwd_kernel(
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float hxv = hx[(size_t)b * d + c], htv = ht[(size_t)b * t2 + c], fb = fbar[(size_t)b * d + c];
     float g_hx = 0.f, g_ht = 0.f, g_fb = 0.f;
-    if (p.inner_instance) { g_fb = go * htv; g_ht = go * fb; }
+    if (p.prj_path == 3) { g_hx = go * p.Pr_w[c]; g_ht = go * p.Pr_w[d + c]; }
+    else if (p.inner_instance) { g_fb = go * htv; g_ht = go * fb; }
     else { g_hx = go * htv; g_ht = go * hxv; }
     if (p.prj_path == 1) g_hx += go * p.Pr_w[c];
     else if (p.prj_path == 2) g_ht += go * p.Pr_w[c];
@@ -739,6 +745,50 @@ extern "C" int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t
   const size_t n = (size_t)rows * width;
   if (n == 0) return ADVMIL_OK;
   dropout_mask_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d, d2, role, rows, width, out);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
+// =============================================================================================
+// Harrell's C (eval/cindex.py:82-143): one thread per event sample i, all j; integer counts via block reduce + atomics
+// =============================================================================================
+__global__ void __launch_bounds__(256) cindex_kernel(const float* __restrict__ t, const float* __restrict__ e,
+                                                     const float* __restrict__ pred, int n, float tol,
+                                                     unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long sm[3][8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long con = 0, tie = 0, cmp = 0;
+  if (i < n && e[i] != 0.f) {
+    const float ti = t[i], ri = -pred[i];
+    for (int j = 0; j < n; ++j) {
+      const float tj = t[j];
+      const bool comparable = (tj > ti) || (tj == ti && e[j] == 0.f);   // j == i: equal time and an event -> false
+      if (!comparable) continue;
+      const float rj = -pred[j];
+      const bool is_tie = fabsf(rj - ri) <= tol;
+      cmp += 1;
+      tie += is_tie ? 1 : 0;
+      con += (!is_tie && rj < ri) ? 1 : 0;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    con += __shfl_xor_sync(0xffffffffu, con, o); tie += __shfl_xor_sync(0xffffffffu, tie, o); cmp += __shfl_xor_sync(0xffffffffu, cmp, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][wid] = con; sm[1][wid] = tie; sm[2][wid] = cmp; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long c0 = 0, c1 = 0, c2 = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { c0 += sm[0][w]; c1 += sm[1][w]; c2 += sm[2][w]; }
+    atomicAdd(counts + 0, c0); atomicAdd(counts + 1, c1); atomicAdd(counts + 2, c2); atomicAdd(counts + 3, c2 - c0 - c1);
+  }
+}
+extern "C" int advmil_cindex_counts(const float* t, const float* e, const float* pred, int32_t n, float tied_tol,
+                                    int64_t* counts, void* stream) {
+  ADVMIL_REQUIRE(t && e && pred && counts && n >= 2, "cindex_counts: need at least two samples (eval/cindex.py:72-73)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ADVMIL_CHECK_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), st));
+  cindex_kernel<<<cdiv(n, 256), 256, 0, st>>>(t, e, pred, n, tied_tol, (unsigned long long*)counts);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

@@ -1,0 +1,160 @@
+"""On-disk packed bag format: ONE mmap-able blob per dataset split instead of one `torch.load` per slide.
+
+The reference reads every slide of a patient with `torch.load`, concatenates them and moves the result to the GPU through
+pageable memory, once per bag per epoch (dataset/PatchWSI.py:65-94, utils/io.py:78-101, model/model_handler.py:315-316).
+Here the features of all bags live in one file, row-major `[rows, C]` in fp32 or bf16 (the bf16 mode's storage format:
+rounded to nearest-even once, at packing time), preceded by int64 bag offsets and the (t, e) labels.  A step's bags are
+copied from the page cache straight into a pinned `PinnedStep` buffer (`PackedFile.step`), which `DeviceFeeder` then moves
+with one asynchronous H2D copy.
+
+Layout (little endian):
+    0    8   magic  b"ADVMILPK"
+    8    4   version (1)          12  4  dtype (0 = float32, 1 = bfloat16)
+    16   4   C                    20  4  n_bags
+    24   8   rows                 32  8  offsets_pos   40  8  labels_pos   48  8  names_pos   56  8  feats_pos
+    offsets_pos : int64[n_bags + 1]       labels_pos : float32[n_bags, 2] = (t, e)
+    names_pos   : utf-8, one patient id per line (may be empty)
+    feats_pos   : 4096-byte aligned, rows * C elements
+"""
+from __future__ import annotations
+
+import os
+import struct
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .packed import PinnedStep, _pin
+
+MAGIC = b"ADVMILPK"
+VERSION = 1
+_HDR = struct.Struct("<8sIIIIQQQQQ")
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+_NP = {0: np.float32, 1: np.uint16}
+_TORCH = {0: torch.float32, 1: torch.bfloat16}
+PAGE = 4096
+
+
+def write_packed(path: str, bags: Iterable[torch.Tensor], labels: Sequence[Sequence[float]],
+                 dtype: torch.dtype = torch.float32, names: Optional[Sequence[str]] = None,
+                 require_multiple_of: int = 16) -> Dict[str, int]:
+    """Streams `bags` ([N_i, C] tensors, e.g. the torch.cat of a patient's slides, PatchWSI.py:79) into `path`."""
+    assert dtype in _DT, "features are stored as float32 or bfloat16"
+    labels = np.asarray(labels, dtype=np.float32).reshape(-1, 2)
+    n_bags = labels.shape[0]
+    names_blob = ("\n".join(names)).encode() if names is not None else b""
+    if names is not None:
+        assert len(names) == n_bags
+    offsets_pos = _HDR.size
+    labels_pos = offsets_pos + 8 * (n_bags + 1)
+    names_pos = labels_pos + labels.nbytes
+    feats_pos = (names_pos + len(names_blob) + PAGE - 1) // PAGE * PAGE
+    offsets = [0]
+    C = None
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        f.seek(feats_pos)
+        count = 0
+        for b in bags:
+            b = b[0] if b.dim() == 3 else b
+            assert b.dim() == 2, "a bag is [N, C]"
+            if C is None:
+                C = int(b.shape[1])
+            assert b.shape[1] == C, "all bags share the feature width"
+            n = int(b.shape[0])
+            assert n > 0, f"bag {count} is empty"
+            if require_multiple_of:
+                assert n % require_multiple_of == 0, \
+                    f"bag {count} has {n} instances: the RLIP discriminator needs a multiple of 16 (model/backbone_utils.py:65)"
+            v = b.detach().to("cpu", torch.float32).contiguous()
+            if dtype == torch.bfloat16:
+                f.write(v.to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+            else:
+                f.write(v.numpy().tobytes())
+            offsets.append(offsets[-1] + n)
+            count += 1
+        assert count == n_bags, f"{count} bags for {n_bags} labels"
+        f.seek(0)
+        f.write(_HDR.pack(MAGIC, VERSION, _DT[dtype], C, n_bags, offsets[-1], offsets_pos, labels_pos, names_pos, feats_pos))
+        f.write(np.asarray(offsets, dtype=np.int64).tobytes())
+        f.write(labels.tobytes())
+        f.write(names_blob)
+    os.replace(tmp, path)
+    return {"bags": n_bags, "rows": offsets[-1], "C": C, "bytes": os.path.getsize(path)}
+
+
+def pack_reference_layout(patient_slides: Dict[str, List[str]], labels: Dict[str, Tuple[float, float]], out_path: str,
+                          dtype: torch.dtype = torch.float32, trim_to_multiple_of: int = 16) -> Dict[str, int]:
+    """Converts the reference's per-slide `.pt` feature files (utils/io.py:78-101 `read_patch_data`, one [n, C] tensor per
+    slide) into one packed file: per patient the slides are concatenated in the given order (PatchWSI.py:74-79).
+    trim_to_multiple_of drops the trailing rows that do not fill a 16-row region (level-1 features produced by
+    tools/big_to_small_patching.py are already multiples of 16)."""
+    pids = list(patient_slides.keys())
+
+    def gen():
+        for pid in pids:
+            feats = [torch.load(p, map_location="cpu") for p in patient_slides[pid]]
+            x = torch.cat([f.to(torch.float32) for f in feats], dim=0)
+            if trim_to_multiple_of:
+                x = x[: x.shape[0] // trim_to_multiple_of * trim_to_multiple_of]
+            yield x
+
+    return write_packed(out_path, gen(), [labels[p] for p in pids], dtype=dtype, names=pids,
+                        require_multiple_of=trim_to_multiple_of)
+
+
+class PackedFile:
+    """Read side: zero-copy views of the bags (np.memmap) and pinned per-step buffers for the device feeder."""
+
+    def __init__(self, path: str):
+        self.path = path
+        with open(path, "rb") as f:
+            hdr = f.read(_HDR.size)
+            magic, ver, dt, C, n_bags, rows, opos, lpos, npos, fpos = _HDR.unpack(hdr)
+            if magic != MAGIC or ver != VERSION:
+                raise ValueError(f"{path}: not an advmil_b200 packed file (magic {magic!r}, version {ver})")
+            f.seek(opos)
+            self.offsets = np.frombuffer(f.read(8 * (n_bags + 1)), dtype=np.int64).copy()
+            f.seek(lpos)
+            self.labels = np.frombuffer(f.read(8 * n_bags), dtype=np.float32).reshape(n_bags, 2).copy()
+            f.seek(npos)
+            blob = f.read(fpos - npos).rstrip(b"\x00")
+            self.names = blob.decode().split("\n") if blob else None
+        if int(self.offsets[-1]) != rows or os.path.getsize(path) < fpos + rows * C * (4 if dt == 0 else 2):
+            raise ValueError(f"{path}: truncated or inconsistent packed file")
+        self.C, self.n_bags, self.rows, self.code = int(C), int(n_bags), int(rows), int(dt)
+        self.dtype = _TORCH[dt]
+        self._mm = np.memmap(path, dtype=_NP[dt], mode="r", offset=fpos, shape=(self.rows, self.C))
+
+    def __len__(self) -> int:
+        return self.n_bags
+
+    @property
+    def lengths(self) -> List[int]:
+        return [int(b - a) for a, b in zip(self.offsets[:-1], self.offsets[1:])]
+
+    def bag(self, i: int) -> torch.Tensor:
+        """[N_i, C] copy of bag i in the stored dtype (what WSIPatch.__getitem__ returns as `feats`, PatchWSI.py:79)."""
+        a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        v = torch.from_numpy(np.array(self._mm[a:b]))
+        return v.view(torch.bfloat16) if self.code == 1 else v
+
+    def step(self, indices: Sequence[int], visible: Optional[Sequence[bool]] = None, pin: bool = True) -> PinnedStep:
+        """The bags `indices` of one optimiser step as a pinned, packed buffer (page cache -> pinned memory, one copy)."""
+        lens = [int(self.offsets[i + 1] - self.offsets[i]) for i in indices]
+        x = torch.empty(sum(lens), self.C, dtype=self.dtype)
+        if pin:
+            x = _pin(x)
+        dst = x.view(torch.int16).numpy() if self.code == 1 else x.numpy()
+        off = 0
+        for i, n in zip(indices, lens):
+            a = int(self.offsets[i])
+            np.copyto(dst[off:off + n], self._mm[a:a + n].view(np.int16) if self.code == 1 else self._mm[a:a + n])
+            off += n
+        lab = torch.from_numpy(self.labels[list(indices)].copy())
+        mk = _pin if pin else (lambda v: v)
+        vis = [True] * len(lens) if visible is None else list(visible)
+        return PinnedStep(x=x, lengths=lens, t=mk(lab[:, 0].contiguous()), e=mk(lab[:, 1].contiguous()),
+                          idx=torch.tensor(list(indices), dtype=torch.int32),
+                          visible=mk(torch.tensor([1 if v else 0 for v in vis], dtype=torch.uint8)))

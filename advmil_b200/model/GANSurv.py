@@ -121,9 +121,30 @@ class PrjDiscriminator(nn.Module):
         return out.unsqueeze(-1)
 
 
-class Discriminator(nn.Module):
-    """Concat discriminator (reference model/GANSurv.py:52-68) — a "next" row of the scope table, not built yet."""
+class Discriminator(PrjDiscriminator):
+    """Concat discriminator (reference model/GANSurv.py:52-68): out = fc(cat[EmbedX(x), time_embed(t)]).  Same fused RLIP
+    embedding / head kernels as PrjDiscriminator; only the per-bag tail differs (C ABI prj_path 3)."""
 
     def __init__(self, args_netx, args_nety, **kws):
-        super().__init__()
-        raise NotImplementedError("disc_type 'cat' is not on the built hot path; use disc_type 'prj' (PrjDiscriminator)")
+        nn.Module.__init__(self)
+        self.inner_product = "bag"
+        self.net_pair_one = EmbedXLayer(args_netx)
+        self.net_pair_two = make_embedding_y_layer(args_nety)
+        dim_x, dim_y = args_netx.out_dim, args_nety.hid_dims[-1]
+        if len(args_nety.hid_dims) != 2 or args_nety.norm or args_nety.dropout or args_nety.in_dim != 1 or dim_x != dim_y:
+            raise NotImplementedError("the fused RLIP head covers disc_nety: in_dim 1, two hidden dims, no norm/dropout, "
+                                      "last dim == disc_netx_out_dim (config/cfg_nlst.yaml:44-47)")
+        self.prj_path = "cat"
+        self.fc = nn.Linear(dim_x + dim_y, 1)
+        self.dims = (args_netx.in_dim, dim_x, args_nety.hid_dims[0], dim_y)
+        print("[info] Typical discriminator without projection")
+
+    def config(self) -> ops.DiscConfig:
+        C, d, t1, t2 = self.dims
+        return ops.DiscConfig(C=C, d=d, t1=t1, t2=t2, inner_instance=0, prj_path=3, p=self.net_pair_one.p,
+                              ln_eps=self.net_pair_one.embedding.norm.eps)
+
+    def disc_params(self):
+        y = self.net_pair_two
+        return self.net_pair_one.disc_params() + [y[0][0].weight, y[0][0].bias, y[1][0].weight, y[1][0].bias,
+                                                  self.fc.weight, self.fc.bias]

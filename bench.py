@@ -83,25 +83,29 @@ class NvmlSampler(threading.Thread):
                     reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
                     reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.rows.append((mhz, reasons))
+                self.rows.append((mhz, reasons, time.perf_counter()))
             except Exception:
                 pass
             time.sleep(self.period)
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: perf_counter bounds of the timed region; only samples taken inside it are reported."""
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=1.0)
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[2] <= t1]
+            self.rows = inside if inside else self.rows[-3:]
         if not self.ok or not self.rows:
             return None
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
                 "hw_power_brake_slowdown": 0x80}
         seen = set()
-        for _, r in self.rows:
+        for _, r, _t in self.rows:
             for name, b in bits.items():
                 if r & b:
                     seen.add(name)
-        return {"sm_mhz": float(np.median([m for m, _ in self.rows])), "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
+        return {"sm_mhz": float(np.median([m for m, _, _t in self.rows])), "sm_max_mhz": self.max_mhz, "reasons": sorted(seen),
                 "samples": len(self.rows), "source": "nvml"}
 
 
@@ -123,7 +127,7 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is not None:
             self.proc.terminate()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
@@ -251,16 +255,15 @@ def main():
         b, t, e, v = resident[i % 2]
         return engine.step(b, t, e, v, noise_d=nz[0], noise_g=nz[1], global_counts=hostcounts[i % 2])
 
-    for i in range(args.warmup):
-        one_step(i)
-    barrier()
-    lib.advmil_launch_count(1)
     sampler = NvmlSampler(local_rank)
     if not sampler.ok:
         sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.05)
+        sampler.start()             # started before the warm-up: nothing but the timed loop sits between the barriers
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    lib.advmil_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     th0 = time.perf_counter()
@@ -269,7 +272,7 @@ def main():
     host_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # CPU time to ISSUE one step (no sync inside the loop)
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(th0, time.perf_counter()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = int(lib.advmil_launch_count(0))
     # per-kernel-class CUDA-event timing in a SEPARATE pass (the event records perturb the step, so they stay out of the
@@ -373,7 +376,10 @@ def main():
                        "l2": f"inputs ({steps[0].x.numel() * steps[0].x.element_size() >> 20} MiB/step, two alternating "
                              "steps) larger than the 126 MB L2; no flush",
                        "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
-            "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_gbs_per_gpu": h2d * args.steps / (float(ems.item()) / 1e3) / 1e9,
+                    "note": "pinned host -> device copy of every step's features overlapped with the previous step's compute "
+                            "(DeviceFeeder); bound by the PCIe link when h2d_gbs_per_gpu is ~55 GB/s"},
             "gpu_launches": launches, "host_issue_ms_per_step": host_ms, "profiled_pass_ms_per_step": prof_ms / prof_steps,
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
             "losses_last_step": losses,

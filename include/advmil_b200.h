@@ -121,10 +121,11 @@ typedef struct AdvmilDiscParams {
   const float *F2b_w, *F2b_b;  /* net_pair_one.fc2.3 [d,d/2] */
   const float *T1_w, *T1_b;    /* net_pair_two.0.0 [t1,1] */
   const float *T2_w, *T2_b;    /* net_pair_two.1.0 [t2,t1] */
-  const float *Pr_w, *Pr_b;    /* prj_layer [1,d] (or NULL) */
+  const float *Pr_w, *Pr_b;    /* prj_layer [1,d] (or NULL); prj_path 3: the concat discriminator's fc [1, d + t2] */
   int32_t C, d, t1, t2;
   int32_t inner_instance;      /* 1 = 'instance' (RLIP), 0 = 'bag' (GANSurv.py:92-98) */
-  int32_t prj_path;            /* 0 none, 1 'x', 2 'y' */
+  int32_t prj_path;            /* 0 none, 1 'x', 2 'y' (PrjDiscriminator); 3 = Discriminator (GANSurv.py:52-68):
+                                  out = fc(cat[hx, ht]) with no inner product (inner_instance ignored) */
   float p;                     /* disc_netx_dropout */
   float ln_eps;
 } AdvmilDiscParams;
@@ -288,6 +289,14 @@ ADVMIL_API int advmil_adam_step(float* param, const float* grad, float* m, float
                      float grad_scale, void* stream);
 /* sum |p| over a flat buffer (the L1 term's value), out[0] += result */
 ADVMIL_API int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream);
+
+/* ---- Harrell's C on the device (replaces eval/cindex.py:106-143 `_estimate_concordance_index` with unit weights, as
+ *      reached from concordance_index(y_true, y_pred) :10-40 with estimate = -y_pred).  t, e, pred: [n] fp32 device.
+ *      counts (device int64[4], overwritten): concordant, tied_risk, comparable, discordant -- integer exact;
+ *      C = (concordant + 0.5 * tied_risk) / comparable.  Pair (i, j) is comparable when e_i and (t_j > t_i or
+ *      (t_j == t_i and !e_j)); concordant when pred_j > pred_i (risk = -pred), tied when |pred_i - pred_j| <= tied_tol. */
+ADVMIL_API int advmil_cindex_counts(const float* t, const float* e, const float* pred, int32_t n, float tied_tol,
+                         int64_t* counts, void* stream);
 
 /* ---- fused adversarial step (replaces the bodies of MyHandler._update_disc / _update_gen, model/model_handler.py:349-498,
  *      for one optimiser step of `bags`; the Adam updates and the data-parallel gradient all-reduce stay with the caller,

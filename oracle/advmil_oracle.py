@@ -267,6 +267,15 @@ def prjdisc_forward(sd: SD, x: Tensor, t: Tensor, masks=None, inner_product: str
     return ex
 
 
+def catdisc_forward(sd: SD, x: Tensor, t: Tensor, masks=None, p: float = 0.25) -> Dict[str, Tensor]:
+    """Discriminator.forward (model/GANSurv.py:61-68): out = fc(cat[EmbedX(x), time_embed(t)]). x: [N,C]; t: [1,1]."""
+    ht = time_embed(sd, t)                                                 # GANSurv.py:63
+    ex = embedx_forward(sd, x, masks, p)                                   # GANSurv.py:64
+    ex["ht"] = ht
+    ex["out"] = _lin(torch.cat([ex["hx"], ht], dim=1), sd, "fc")           # GANSurv.py:65-67
+    return ex
+
+
 # ----------------------------------------------------------------------------------------------
 # losses (loss/utils.py)
 # ----------------------------------------------------------------------------------------------
@@ -477,6 +486,13 @@ G_CLUSTER_SHAPES = lambda C=1024, h=384: {  # noqa: E731  DeepAttMISL generator
     "backbone.attention_net.3.attention_b.0.weight": (h, h), "backbone.attention_net.3.attention_b.0.bias": (h,),
     "backbone.attention_net.3.attention_c.weight": (1, h), "backbone.attention_net.3.attention_c.bias": (1,),
 }
+
+def DCAT_SHAPES(C=1024, d=128, ty=(64, 128)):
+    """State dict of the concat Discriminator (model/GANSurv.py:52-60): PrjDiscriminator's minus prj_layer, plus fc."""
+    sh = {k: v for k, v in D_SHAPES(C, d, ty).items() if not k.startswith("prj_layer")}
+    sh["fc.weight"], sh["fc.bias"] = (1, d + ty[1]), (1,)
+    return sh
+
 
 D_SHAPES = lambda C=1024, d=128, ty=(64, 128): {  # noqa: E731
     "net_pair_one.embedding.conv.weight": (d, C, 1, 1), "net_pair_one.embedding.conv.bias": (d,),

@@ -194,6 +194,48 @@ def case_disc(ref, name, C, d, N, train, seed, iprd="instance", prj="x"):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def case_disc_cat(ref, name, C, d, N, train, seed):
+    """The concat Discriminator (model/GANSurv.py:52-68) built like model_handler.py:83-86 builds it.  The embedding
+    gradients of this variant flow only through the attention pooling and are ill-conditioned in fp32 (the reference's
+    own fp32 conv2d path is off by ~2e-2 of the tensor maximum from its float64 evaluation), so the stored gradients come
+    from the reference modules run in float64; the output is the fp32 one."""
+    ax = SimpleNamespace(in_dim=C, out_dim=d, ksize=1, backbone="avgpool", dropout=0.25)
+    ty = (64, 128) if d == 128 else (d // 2, d)
+    ay = SimpleNamespace(in_dim=1, hid_dims=list(ty), norm=False, dropout=0.0)
+    sd = O.synth_state_dict(O.DCAT_SHAPES(C, d, ty), seed + 50)
+    x = O.synth_bag(N, seed, C)
+    masks = d_masks(N // 16, d, seed * 10 + 5) if train else None
+    runs = {}
+    for dt in (torch.float32, torch.float64):
+        D = ref.GANSurv.Discriminator(ax, ay).to(dt)
+        D.load_state_dict({k: v.to(dt) for k, v in sd.items()})
+        t = torch.tensor([[0.61]], dtype=dt, requires_grad=True)
+        drops = swap_dropouts_D(D)
+        D.train(bool(train))
+        if train:
+            for k, m in drops.items():
+                m.mask = masks[k]
+        out_t = D(x.to(dt).unsqueeze(0), t)
+        D.zero_grad()
+        out_t.sum().backward()
+        runs[dt] = (out_t.detach(), t.grad.detach(), {k: p.grad.detach() for k, p in D.named_parameters()})
+    out32, _, _ = runs[torch.float32]
+    _, dt64, g64 = runs[torch.float64]
+    out = {"out": out32.double().numpy(), "dt": dt64.double().numpy(), "cfg": np.array([C, d, N, int(train), seed])}
+    for k, g in g64.items():
+        out["grad." + k] = sub(g)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    t2 = torch.tensor([[0.61]], dtype=torch.float32, requires_grad=True)
+    od = O.catdisc_forward(sdr, x, t2, masks)
+    od["out"].sum().backward()
+    err = float((od["out"].detach() - out32).abs().max())
+    gerr = max(float((sdr[k].grad.double() - g).abs().max() / (g.abs().max() + 1e-6)) for k, g in g64.items()
+               if float(g.abs().max()) > 1e-8)       # pool.fc2.bias: mathematically zero (softmax shift invariance)
+    print(f"[golden] {name}: out {float(out32):.8f} oracle|d|={err:.2e} grad rel err vs float64 reference={gerr:.2e}")
+    assert err < 1e-6 and gerr < 1e-4
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def case_cluster(ref, name, dims, N, seed, empty_cluster):
     C, h, _ = dims
     G = build_ref_G(ref, dims, mode="cluster")
@@ -412,6 +454,8 @@ def main():
     case_disc(ref, "d_rlip_train_full", 1024, 128, 640, True, 6)
     case_disc(ref, "d_rlip_eval_small", 64, 32, 208, False, 7)
     case_disc(ref, "d_bag_train_small", 64, 32, 96, True, 8, iprd="bag")
+    case_disc_cat(ref, "d_cat_train_full", 1024, 128, 640, True, 13)
+    case_disc_cat(ref, "d_cat_eval_small", 64, 32, 208, False, 14)
     case_cluster(ref, "g_cluster_full", full, 800, 9, False)
     case_cluster(ref, "g_cluster_empty_small", small, 160, 10, True)
     case_step(ref, "step_small", small, 32, [96, 160, 48, 208], 11)

@@ -111,3 +111,29 @@ def test_sample_inference_matches_oracle_and_lower_median():
         assert_close(res["dist_y_hat"][b, :, 0].cpu(), dist, RTOL, f"dist {b}")
         med = O.lower_median(dist)
         assert abs(float(res["avg_y_hat"][b]) - float(med)) < 1e-6
+
+
+def test_device_cindex_matches_reference_golden_and_oracle_counts():
+    """eval/cindex.py on the device: the value of the reference's concordance_index on 447 patients with tied times and
+    tied predictions (tests/golden/misc.npz, written by the live reference) is reproduced exactly (integer pair counts,
+    one double division); random cases against the oracle's pair loop."""
+    from advmil_b200.eval.cindex import concordance_counts, concordance_index
+    g = golden("misc")
+    y_true = np.stack([g["ci_t"], g["ci_e"]], axis=1)
+    ci = concordance_index(y_true, g["ci_pred"].reshape(-1, 1))
+    assert ci == float(g["ci"]), (ci, float(g["ci"]))
+    rng = np.random.default_rng(3)
+    for n in (2, 17, 300, 1500):
+        t = np.round(rng.uniform(size=n), 2).astype(np.float32)
+        e = (rng.uniform(size=n) < 0.4).astype(np.float32)
+        e[0] = 1.0
+        p = np.round(rng.uniform(size=n), 2).astype(np.float32)
+        c = concordance_counts(t, e, p)
+        if c["comparable"] == 0:
+            continue
+        want = O.concordance_index(t, e, p)
+        got = (c["concordant"] + 0.5 * c["tied_risk"]) / c["comparable"]
+        assert got == want, (n, got, want)
+        assert c["concordant"] + c["tied_risk"] + c["discordant"] == c["comparable"]
+    with pytest.raises(ValueError):
+        concordance_index(np.array([[0.5, 0.0], [0.7, 0.0]], dtype=np.float32), np.array([[0.1], [0.2]], dtype=np.float32))

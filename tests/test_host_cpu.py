@@ -178,3 +178,47 @@ def test_data_parallel_gradients_equal_single_process_gloo():
     out["loss"].backward()
     ref = torch.cat([torch.zeros_like(p).reshape(-1) if p.grad is None else p.grad.reshape(-1) for p in sdD.values()]).numpy()
     assert float(np.abs(ref - res[2][0]).max()) <= 2e-6 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_packed_file_round_trip_fp32_and_bf16(tmp_path):
+    """On-disk packed format (dataset/packed_file.py): bit-exact round trip in fp32, round-to-nearest-even bf16, ragged bags,
+    steps assembled from arbitrary bag indices, and conversion from the reference's per-slide .pt layout."""
+    from advmil_b200.dataset.packed import group_steps
+    from advmil_b200.dataset.packed_file import PackedFile, pack_reference_layout, write_packed
+    g = torch.Generator().manual_seed(5)
+    lens = [16, 320, 48, 1600, 16, 96]
+    bags = [torch.randn(n, 64, generator=g) for n in lens]
+    labels = [(0.1 * i + 0.05, float(i % 2)) for i in range(len(lens))]
+    for dt in (torch.float32, torch.bfloat16):
+        path = str(tmp_path / f"split_{dt}.advmil")
+        info = write_packed(path, iter(bags), labels, dtype=dt, names=[f"pat{i}" for i in range(len(lens))])
+        assert info["rows"] == sum(lens) and info["C"] == 64
+        pf = PackedFile(path)
+        assert len(pf) == len(lens) and pf.lengths == lens and pf.names[3] == "pat3" and pf.dtype == dt
+        assert np.array_equal(pf.labels, np.asarray(labels, dtype=np.float32))
+        for i, b in enumerate(bags):
+            assert torch.equal(pf.bag(i), b.to(dt))
+        st = pf.step([3, 0, 5], visible=[True, False, True], pin=False)
+        assert st.lengths == [1600, 16, 96] and st.x.dtype == dt
+        assert torch.equal(st.x, torch.cat([bags[3], bags[0], bags[5]]).to(dt))
+        assert st.offsets.tolist() == [0, 1600, 1616, 1712] and st.visible.tolist() == [1, 0, 1]
+        assert torch.allclose(st.t, torch.tensor([labels[3][0], labels[0][0], labels[5][0]]))
+        assert st.nbytes == st.x.numel() * st.x.element_size() + 3 * 8 + 3
+    assert group_steps(len(lens), 4) == [[0, 1, 2, 3]]      # the trailing partial group is dropped (model_handler.py:321)
+    with pytest.raises(AssertionError):
+        write_packed(str(tmp_path / "bad.advmil"), iter([torch.randn(17, 8)]), [(0.5, 1.0)])
+    with pytest.raises(ValueError):
+        open(tmp_path / "junk.advmil", "wb").write(b"x" * 128)
+        PackedFile(str(tmp_path / "junk.advmil"))
+    # reference layout: one .pt per slide, several slides per patient, concatenated in order; ragged tail trimmed to 16
+    slides = {"p0": [], "p1": []}
+    for pid, ns in (("p0", [40, 24]), ("p1", [35])):
+        for k, n in enumerate(ns):
+            f = str(tmp_path / f"{pid}_{k}.pt")
+            torch.save(torch.randn(n, 32, generator=g), f)
+            slides[pid].append(f)
+    info = pack_reference_layout(slides, {"p0": (0.3, 1.0), "p1": (0.8, 0.0)}, str(tmp_path / "ref.advmil"))
+    pf = PackedFile(str(tmp_path / "ref.advmil"))
+    assert pf.lengths == [64, 32] and pf.names == ["p0", "p1"]
+    assert torch.equal(pf.bag(0), torch.cat([torch.load(f) for f in slides["p0"]]))
+    assert torch.equal(pf.bag(1), torch.load(slides["p1"][0])[:32])

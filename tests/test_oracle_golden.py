@@ -50,6 +50,27 @@ def test_discriminator_oracle_vs_reference(name):
     _grads_match(sd, g)
 
 
+@pytest.mark.parametrize("name", ["d_cat_train_full", "d_cat_eval_small"])
+def test_concat_discriminator_oracle_vs_reference(name):
+    """Discriminator (disc_type 'cat', model/GANSurv.py:52-68); gradients pinned by the reference run in float64."""
+    g = golden(name)
+    C, d, N, train, seed = [int(v) for v in g["cfg"]]
+    ty = (64, 128) if d == 128 else (d // 2, d)
+    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(O.DCAT_SHAPES(C, d, ty), seed + 50).items()}
+    x = O.synth_bag(N, seed, C)
+    t = torch.tensor([[0.61]], requires_grad=True)
+    masks = d_masks(N // 16, d, seed * 10 + 5) if train else None
+    out = O.catdisc_forward(sd, x, t, masks)
+    out["out"].sum().backward()
+    assert float(np.abs(out["out"].detach().numpy() - g["out"]).max()) < 1e-6
+    assert float(np.abs(t.grad.numpy() - g["dt"]).max()) < 1e-6
+    for k, v in sd.items():
+        ref = g["grad." + k]
+        if float(np.abs(ref).max()) < 1e-8:
+            continue
+        assert float(np.abs(sub(v.grad) - ref).max()) <= 1e-4 * float(np.abs(ref).max()), k
+
+
 @pytest.mark.parametrize("name", ["g_cluster_full", "g_cluster_empty_small"])
 def test_cluster_oracle_vs_reference(name):
     g = golden(name)
