@@ -211,3 +211,33 @@ def test_precision_and_element_type_must_agree():
     G = build_G().eval()
     with pytest.raises(_lib.AdvmilError):
         G.forward_packed(bags, precision=ops.TF32)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_cluster_generator_reduced_precision_vs_golden(mode):
+    """DeepAttMISL (cfg4): the N-row phi projection and the per-cluster segment mean run on the tensor-core engine in the
+    reduced-precision modes (bf16: x and relu(phi(x)) stored in bf16); the 8-row attention stage always runs in fp32."""
+    g = golden("g_cluster_full")
+    C, h, N, seed, empty = [int(v) for v in g["cfg"]]
+    sd = O.synth_state_dict(O.G_CLUSTER_SHAPES(C, h), seed + 20)
+    G = build_G((C, h, h), mode="cluster").eval()
+    G.load_state_dict({k: v.clone() for k, v in sd.items()})
+    x = O.synth_bag(N, seed, C)
+    cid = torch.tensor(g["cid"], dtype=torch.float32)
+    noise = torch.tensor(np.random.default_rng(seed + 7).uniform(size=(1, h // 2)), dtype=torch.float32)
+    G.draw_noise = lambda nb, dev, zero: [None, noise.to(dev)]
+    advmil_b200.set_precision(mode)
+    try:
+        pred = G(x.cuda().unsqueeze(0), cid.cuda())
+        pred.sum().backward()
+    finally:
+        advmil_b200.set_precision("fp32")
+    assert_close(pred.detach().cpu(), g["pred"], TOL, "pred")
+    from tests.util import sub
+    gmax = max(float(np.abs(g["grad." + k]).max()) for k, _ in G.named_parameters())
+    for k, p in G.named_parameters():
+        ref = g["grad." + k]
+        if float(np.abs(ref).max()) < 1e-7:
+            continue
+        flip = k.startswith("backbone.phis.0")     # first-layer ReLU-mask flips (see the ABMIL test above)
+        assert_close(sub(p.grad), ref, 1e-1 if (flip and mode == "bf16") else TOL, "grad " + k, atol=1e-4 * gmax)
