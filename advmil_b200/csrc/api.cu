@@ -190,11 +190,14 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   // head
   { ProfScope ps(PROF_GEN_TAIL, st);
     ADVMIL_TRY(gen_head_bwd(*p, d_pred, a->H, a->H1, a->pred, nb, ik_bb, ik_hd, dz, dHpre, dH1pre, dpre, st));
+    OuterProb op[OUTER_MAX];
+    int nop = 0;
     if (p->W0) {
-      ADVMIL_TRY(outer_sum(dpre, a->H1, hid, a->noise1, p->noise1 ? hid : 0, nb, 1, g->Wl, g->bl, 0, st));
-      ADVMIL_TRY(outer_sum(dH1pre, a->H, o, a->noise0, p->noise0 ? o : 0, nb, hid, g->W0, g->b0, 0, st));
+      op[nop++] = OuterProb{dpre, a->H1, hid, a->noise1, p->noise1 ? hid : 0, 1, g->Wl, g->bl};
+      op[nop++] = OuterProb{dH1pre, a->H, o, a->noise0, p->noise0 ? o : 0, hid, g->W0, g->b0};
     }
-    if (p->Wrho) ADVMIL_TRY(outer_sum(dHpre, a->z, h, nullptr, 0, nb, o, g->Wrho, g->brho, 0, st));
+    if (p->Wrho) op[nop++] = OuterProb{dHpre, a->z, h, nullptr, 0, o, g->Wrho, g->brho};
+    ADVMIL_TRY(outer_sum_multi(op, nop, nb, 0, st));
     // pooling + gate
     ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st));
   }
@@ -246,7 +249,7 @@ extern "C" size_t advmil_disc_workspace_bytes(const AdvmilDiscParams* p, int32_t
     hb += R * abw + R * d + R * dh + abw * d + abw + 1024;
     hb += pool_gate_ws_floats((int)R, bags, (int)d) + 256;
     hb += max(bwd_weight_ws_floats((int)R, (int)abw, (int)d), bwd_weight_ws_floats((int)R, (int)d, (int)dh)) + 256;
-    hb += (size_t)row_chunks((int)R) * abw + 256;
+    hb += (size_t)row_chunks((int)R) * abw + 256 + (size_t)8 * row_chunks((int)R) * d + 512;
     f += max(e, hb);
   }
   return f * sizeof(float) + 64 * 256;
@@ -359,13 +362,16 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
                            d_htpre, d_u1pre, d_t ? d_t : d_t_scratch, st));
   if (!d_emb && !g) return ADVMIL_OK;  // G step: only dL/dt is needed from D
   if (g) {
-    ADVMIL_TRY(outer_sum(d_hx, a->g1, dh, nullptr, 0, nb, d, g->F2b_w, g->F2b_b, accumulate, st));
-    ADVMIL_TRY(outer_sum(d_g1pre, a->bagv, d, nullptr, 0, nb, dh, g->F2a_w, g->F2a_b, accumulate, st));
-    ADVMIL_TRY(outer_sum(d_htpre, a->u1, t1, nullptr, 0, nb, t2, g->T2_w, g->T2_b, accumulate, st));
-    ADVMIL_TRY(outer_sum(d_u1pre, a->t, 1, nullptr, 0, nb, t1, g->T1_w, g->T1_b, accumulate, st));
-    if (p->prj_path == 1) ADVMIL_TRY(outer_sum(d_out, a->hx, d, nullptr, 0, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
-    else if (p->prj_path == 2) ADVMIL_TRY(outer_sum(d_out, a->ht, t2, nullptr, 0, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
-    else if (p->prj_path == 3) ADVMIL_TRY(outer_sum(d_out, a->hx, d, a->ht, t2, nb, 1, g->Pr_w, g->Pr_b, accumulate, st));
+    OuterProb op[OUTER_MAX];
+    int nop = 0;
+    op[nop++] = OuterProb{d_hx, a->g1, dh, nullptr, 0, d, g->F2b_w, g->F2b_b};
+    op[nop++] = OuterProb{d_g1pre, a->bagv, d, nullptr, 0, dh, g->F2a_w, g->F2a_b};
+    op[nop++] = OuterProb{d_htpre, a->u1, t1, nullptr, 0, t2, g->T2_w, g->T2_b};
+    op[nop++] = OuterProb{d_u1pre, a->t, 1, nullptr, 0, t1, g->T1_w, g->T1_b};
+    if (p->prj_path == 1) op[nop++] = OuterProb{d_out, a->hx, d, nullptr, 0, 1, g->Pr_w, g->Pr_b};
+    else if (p->prj_path == 2) op[nop++] = OuterProb{d_out, a->ht, t2, nullptr, 0, 1, g->Pr_w, g->Pr_b};
+    else if (p->prj_path == 3) op[nop++] = OuterProb{d_out, a->hx, d, a->ht, t2, 1, g->Pr_w, g->Pr_b};
+    ADVMIL_TRY(outer_sum_multi(op, nop, nb, accumulate, st));
   }
   WS_TAKE(Wp, float, (size_t)abw * d);
   WS_TAKE(bp, float, abw);
@@ -378,6 +384,8 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   WS_TAKE(pgws, float, pool_gate_ws_floats(R, nb, d));
   WS_TAKE(bwws, float, max(bwd_weight_ws_floats(R, abw, d), bwd_weight_ws_floats(R, d, dh)));
   WS_TAKE(csws, float, (size_t)row_chunks(R) * abw);
+  WS_TAKE(cp_fi, float, (size_t)4 * row_chunks(R) * d);      // column-sum partials from the backward-data epilogues
+  WS_TAKE(cp_f1, float, (size_t)4 * row_chunks(R) * d);
   Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train, p->d);
   Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train, p->d);
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
@@ -386,6 +394,8 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
                            ELEM_F32, st));
   BwdDataExtras ex;
   ex.w = a->attn; ex.dz = d_bagv; ex.dmean = (p->inner_instance && p->prj_path != 3) ? d_fbar : nullptr; ex.offsets = ro.dev; ex.bags = nb;
+  const bool fuse_fi = g && bwd_data_fuses_colsum(R, abw, d, rp), fuse_f1 = g && bwd_data_fuses_colsum(R, d, dh, rp);
+  if (fuse_fi) ex.colsum_part = cp_fi;
   ADVMIL_TRY(bwd_data(dAB, Wp, R, abw, d, d_fi, ex, rp, st));
   if (g) {
     ADVMIL_TRY(bwd_weight(dAB, a->fi, R, abw, d, dWp, 0, bwws, rp, st));
@@ -393,12 +403,15 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   }
   BwdDataExtras ex1;
   ex1.relu_src = a->f1; ex1.ld_src = dh; ex1.inv_keep = ik;
+  if (fuse_f1) ex1.colsum_part = cp_f1;
   ADVMIL_TRY(bwd_data(d_fi, p->F1b_w, R, d, dh, d_f1pre, ex1, rp, st));
   if (g) {
     ADVMIL_TRY(bwd_weight(d_fi, a->f1, R, d, dh, g->F1b_w, accumulate, bwws, rp, st));
-    ADVMIL_TRY(colsum(d_fi, ELEM_F32, R, d, d, g->F1b_b, accumulate, csws, st));
+    if (fuse_fi) ADVMIL_TRY(reduce_rows(cp_fi, 4 * cdiv(R, 128), d, g->F1b_b, accumulate, st));
+    else ADVMIL_TRY(colsum(d_fi, ELEM_F32, R, d, d, g->F1b_b, accumulate, csws, st));
     ADVMIL_TRY(bwd_weight(d_f1pre, a->emb, R, dh, d, g->F1a_w, accumulate, bwws, rp, st));
-    ADVMIL_TRY(colsum(d_f1pre, ELEM_F32, R, dh, dh, g->F1a_b, accumulate, csws, st));
+    if (fuse_f1) ADVMIL_TRY(reduce_rows(cp_f1, 4 * cdiv(R, 128), dh, g->F1a_b, accumulate, st));
+    else ADVMIL_TRY(colsum(d_f1pre, ELEM_F32, R, dh, dh, g->F1a_b, accumulate, csws, st));
   }
   if (d_emb) {
     BwdDataExtras ex2;

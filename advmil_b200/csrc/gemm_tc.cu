@@ -424,18 +424,44 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if constexpr (EPI == EPI_BWD) {
-            if (ea.colpart) {     // bias gradient for free: column sums of this warp's 32 rows (lanes with equal cv fold)
+            if (ea.colpart) {
+              // bias gradient for free: column sums of this warp's 32 rows.  The RPI lanes that share a column vector
+              // (lane = cv + LPR * k) fold with a halving butterfly: each step exchanges half of the remaining values, so
+              // VEC - 1 shuffles leave ONE column sum per lane and the 32 lanes store 32 distinct columns (128 bytes).
+              int colsel = 0;
+              if constexpr (VEC == 8) {
+                const bool up0 = (lane / LPR) & 1;
+                float k4[4];
 #pragma unroll
-              for (int e = 0; e < VEC; ++e) {
+                for (int e = 0; e < 4; ++e) {
+                  const float recv = __shfl_xor_sync(0xffffffffu, up0 ? cs[e] : cs[e + 4], LPR);
+                  k4[e] = (up0 ? cs[e + 4] : cs[e]) + recv;
+                }
+                const bool up1 = (lane / (2 * LPR)) & 1;
+                float k2[2];
 #pragma unroll
-                for (int sh = LPR; sh < 32; sh <<= 1) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], sh);
+                for (int e = 0; e < 2; ++e) {
+                  const float recv = __shfl_xor_sync(0xffffffffu, up1 ? k4[e] : k4[e + 2], 2 * LPR);
+                  k2[e] = (up1 ? k4[e + 2] : k4[e]) + recv;
+                }
+                const bool up2 = (lane / (4 * LPR)) & 1;
+                const float recv = __shfl_xor_sync(0xffffffffu, up2 ? k2[0] : k2[1], 4 * LPR);
+                cs[0] = (up2 ? k2[1] : k2[0]) + recv;
+                colsel = (up0 ? 4 : 0) + (up1 ? 2 : 0) + (up2 ? 1 : 0);
+              } else {
+                const bool up0 = (lane / LPR) & 1;
+                float k2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const float recv = __shfl_xor_sync(0xffffffffu, up0 ? cs[e] : cs[e + 2], LPR);
+                  k2[e] = (up0 ? cs[e + 2] : cs[e]) + recv;
+                }
+                const bool up1 = (lane / (2 * LPR)) & 1;
+                const float recv = __shfl_xor_sync(0xffffffffu, up1 ? k2[0] : k2[1], 2 * LPR);
+                cs[0] = (up1 ? k2[1] : k2[0]) + recv;
+                colsel = (up0 ? 2 : 0) + (up1 ? 1 : 0);
               }
-              if (lane < LPR) {
-                float* dst = ea.colpart + (size_t)(mt * 4 + wq) * N + n0 + ch * 32 + lane * VEC;
-#pragma unroll
-                for (int q = 0; q < VEC / 4; ++q)
-                  *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(cs[4 * q], cs[4 * q + 1], cs[4 * q + 2], cs[4 * q + 3]);
-              }
+              ea.colpart[(size_t)(mt * 4 + wq) * N + n0 + ch * 32 + (lane % LPR) * VEC + colsel] = cs[0];
             }
           }
           __syncwarp();
@@ -880,9 +906,14 @@ static int wgrad_splits(int rows, int N1, int N2) {
 bool tc_bwd_weight_supported(int rows, int N1, int N2, int dt) {
   return (dt == ELEM_BF16 ? rows >= 1 : rows >= 4096) && N1 % kblk_of(dt) == 0 && N1 >= 64 && wgrad_block_n(N2) != 0;
 }
+// dW^T = X^T dY is computed instead (and transposed in the split-K reduce) when that turns 128-wide N tiles, which are
+// bound by shared-memory operand bandwidth, into 256-wide ones: d[Wa;Wb] (N1 = 768, N2 = 384) -> 128 x 256 tiles
+static bool wgrad_swap(int N1, int N2) { return wgrad_block_n(N2) == 128 && N1 % 256 == 0 && N2 % 128 == 0; }
 size_t tc_bwd_weight_ws_floats(int rows, int N1, int N2) {
   if (wgrad_block_n(N2) == 0 || N1 < 64) return 0;
-  return (size_t)wgrad_splits(rows, N1, N2) * N1 * N2;
+  size_t a = (size_t)wgrad_splits(rows, N1, N2) * N1 * N2;
+  size_t b = wgrad_swap(N1, N2) ? (size_t)wgrad_splits(rows, N2, N1) * N1 * N2 : 0;
+  return a > b ? a : b;
 }
 
 template <typename T, int BLOCK_N>
@@ -908,6 +939,13 @@ template <typename T>
 static int tc_bwd_weight_t(const void* dY, const void* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
                            cudaStream_t st) {
   constexpr int KR = TcElem<T>::KBLK;
+  if (wgrad_swap(N1, N2) && N2 % TcElem<T>::KBLK == 0) {
+    const int splits = wgrad_splits(rows, N2, N1);
+    const int rows_per_split = cdiv(cdiv(rows, splits), KR) * KR;
+    const int nsplit = cdiv(rows, rows_per_split);
+    ADVMIL_TRY((launch_wgrad<T, 256>((const T*)X, (const T*)dY, rows, N2, N1, rows_per_split, nsplit, ws, st)));
+    return splitk_reduce_t(ws, nsplit, N2, N1, dW, accumulate, st);
+  }
   const int splits = wgrad_splits(rows, N1, N2);
   const int rows_per_split = cdiv(cdiv(rows, splits), KR) * KR;
   const int nsplit = cdiv(rows, rows_per_split);

@@ -96,6 +96,40 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, s
     }
   }
 }
+// out[c][r] (+)= sum_z ws[z][r][c]  (ws slices are [R][Cc]; out is [Cc][R]): split-K reduce of a product computed transposed
+__global__ void splitk_reduce_t_kernel(const float* __restrict__ ws, int splits, int R, int Cc, float* __restrict__ out,
+                                       int accumulate) {
+  __shared__ float t[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int z = 0; z < splits; ++z) {
+    const float* src = ws + (size_t)z * R * Cc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + threadIdx.y + 8 * j;
+      if (r < R && c < Cc) acc[j] += src[(size_t)r * Cc + c];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) t[threadIdx.y + 8 * j][threadIdx.x] = acc[j];
+  __syncthreads();
+  const int orr = r0 + threadIdx.x;           // output column (= input row)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int oc = blockIdx.x * 32 + threadIdx.y + 8 * j;   // output row (= input column)
+    if (oc < Cc && orr < R) {
+      float* dst = out + (size_t)oc * R + orr;
+      const float v = t[threadIdx.x][threadIdx.y + 8 * j];
+      *dst = accumulate ? *dst + v : v;
+    }
+  }
+}
+int splitk_reduce_t(const float* ws, int splits, int R, int Cc, float* out, int accumulate, cudaStream_t st) {
+  splitk_reduce_t_kernel<<<dim3(cdiv(Cc, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(ws, splits, R, Cc, out, accumulate);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st) {
   splitk_reduce_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(ws, splits, n, out, accumulate);
   ADVMIL_CHECK_LAUNCH();

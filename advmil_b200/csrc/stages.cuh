@@ -71,6 +71,7 @@ int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accu
            cudaStream_t st);
 int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st);
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st);
+int splitk_reduce_t(const float* ws, int splits, int R, int Cc, float* out, int accumulate, cudaStream_t st);
 int apply_dropout(const void* src, int rows, int width, const Drop& drop, void* dst, int dt, cudaStream_t st);
 int fill_zero(float* p, size_t n, cudaStream_t st);
 int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st);
@@ -86,6 +87,10 @@ int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, 
 // dW[out, in1+in2] (+)= sum_b dy[b,out] * concat(x1[b,:in1], x2[b,:in2]);  db[out] (+)= sum_b dy[b,out]
 int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in2, int bags, int out, float* dW,
               float* db, int accumulate, cudaStream_t st);
+// up to OUTER_MAX outer-sum problems (same bags, same accumulate flag) in one launch
+constexpr int OUTER_MAX = 6;
+struct OuterProb { const float* dy; const float* x1; int in1; const float* x2; int in2; int out; float* dW; float* db; };
+int outer_sum_multi(const OuterProb* probs, int n, int bags, int accumulate, cudaStream_t st);
 int rlip_tail_fwd(const AdvmilDiscParams& p, const float* bagv, const float* fbar, const float* t, int bags,
                   const Drop& dfc2, float* g1, float* hx, float* u1, float* ht, float* out, cudaStream_t st);
 int rlip_tail_bwd(const AdvmilDiscParams& p, const float* d_out, const float* bagv, const float* fbar, const float* g1,

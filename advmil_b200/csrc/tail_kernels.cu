@@ -261,6 +261,43 @@ int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in
   return ADVMIL_OK;
 }
 
+// several outer-sum problems in one launch (the per-bag head layers of one backward pass)
+struct OuterBatch { OuterProb p[OUTER_MAX]; int first_block[OUTER_MAX + 1]; int n; };
+__global__ void outer_sum_multi_kernel(OuterBatch ob, int bags, int accumulate) {
+  int k = 0;
+  while (k + 1 < ob.n && (int)blockIdx.x >= ob.first_block[k + 1]) ++k;
+  const OuterProb q = ob.p[k];
+  const int in = q.in1 + q.in2;
+  const size_t idx = (size_t)(blockIdx.x - ob.first_block[k]) * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)q.out * in) return;
+  const int o = (int)(idx / in), i = (int)(idx % in);
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < bags; ++b) {
+    const float g = q.dy[(size_t)b * q.out + o];
+    const float xv = i < q.in1 ? q.x1[(size_t)b * q.in1 + i] : (q.x2 ? q.x2[(size_t)b * q.in2 + (i - q.in1)] : 0.f);
+    acc = fmaf(g, xv, acc);
+    accb += g;
+  }
+  if (q.dW) q.dW[idx] = accumulate ? q.dW[idx] + acc : acc;
+  if (q.db && i == 0) q.db[o] = accumulate ? q.db[o] + accb : accb;
+}
+int outer_sum_multi(const OuterProb* probs, int n, int bags, int accumulate, cudaStream_t st) {
+  ADVMIL_REQUIRE(n >= 0 && n <= OUTER_MAX, "outer_sum_multi: at most %d problems", OUTER_MAX);
+  if (n == 0) return ADVMIL_OK;
+  OuterBatch ob;
+  ob.n = n;
+  int blocks = 0;
+  for (int k = 0; k < n; ++k) {
+    ob.p[k] = probs[k];
+    ob.first_block[k] = blocks;
+    blocks += cdiv((size_t)probs[k].out * (probs[k].in1 + probs[k].in2), 256);
+  }
+  ob.first_block[n] = blocks;
+  outer_sum_multi_kernel<<<blocks, 256, 0, st>>>(ob, bags, accumulate);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
 // =============================================================================================
 // K7/K8 tail: bag MLP fc2, time embedding, inner product, projection
 // (model/model_utils.py:200-206; model/GANSurv.py:89-105)
