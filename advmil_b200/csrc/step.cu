@@ -6,6 +6,7 @@
 //  * the D-step generator forward (eval) and the G-step generator forward (train) share relu(x W1^T + b1): the eval
 //    projection stays in the workspace between the two calls and the G step applies its dropout draw to it;
 //  * the G step asks D only for dL/dt and never touches D-parameter gradients.
+#include <stdlib.h>
 #include <vector>
 #include "stages.cuh"
 
@@ -49,6 +50,31 @@ static size_t gen_bufs_bytes(const AdvmilGenParams& g, size_t rows, size_t nb) {
   return (2 * rows + nb * (g.h + g.o + g.hid + 2)) * sizeof(float) + 8 * 256;
 }
 
+// ---- overlap of the D phase's region-level chain with the G phase's first half --------------------------------------
+// After the eval projection exists, the train-mode generator forward of the G step (dropout on the cached projection, gate
+// GEMM, pooling, head) depends on nothing the D phase still has to do, while the D phase's head forward/backward is a
+// chain of small region-level kernels that leaves most SMs idle.  The disc call therefore issues that forward on a side
+// stream; the gen call joins it.  ADVMIL_STEP_OVERLAP=0 disables the fork (the gen call then runs the forward itself).
+struct SideState {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, done = nullptr;
+  const void* pending_ws = nullptr;     // workspace whose train forward is in flight / finished on the side stream
+  int enabled = -1;
+};
+static SideState g_side;
+static int side_init() {
+  if (g_side.enabled < 0) {
+    const char* e = getenv("ADVMIL_STEP_OVERLAP");
+    g_side.enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (g_side.enabled && !g_side.stream) {
+    ADVMIL_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking));
+    ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
+    ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.done, cudaEventDisableTiming));
+  }
+  return ADVMIL_OK;
+}
+
 #define STEP_TAKE(var, type, count)                                                                         \
   type* var = ws.take<type>(count);                                                                         \
   if (!var) { set_error("%s: workspace too small (have %zu bytes)", __func__, ws.cap); return ADVMIL_ERR_WORKSPACE; }
@@ -57,18 +83,44 @@ static size_t gen_bufs_bytes(const AdvmilGenParams& g, size_t rows, size_t nb) {
 
 using namespace advmil;
 
+// persistent region (same layout in both calls): eval projection, virtual-bag offsets, and everything the G step's train
+// forward writes (it may run on the side stream while the D phase uses the scratch region)
+struct Persist {
+  char* h_eval; int32_t* offs2; char* h; char* ab; GenBufs gb; char* gws; size_t gws_bytes;
+};
+static int take_persist(Workspace& ws, const AdvmilGenParams& gp, int rows, int nb, size_t es, Persist& P) {
+  const size_t abw = gate_width(gp.h);
+  P.h_eval = ws.take<char>((size_t)rows * gp.h * es);
+  P.offs2 = ws.take<int32_t>(2 * nb + 2);
+  P.h = ws.take<char>((size_t)rows * gp.h * es);
+  P.ab = ws.take<char>((size_t)rows * abw * es);
+  const bool ok = take_gen(ws, gp, rows, nb, P.gb);
+  P.gws_bytes = advmil_generator_workspace_bytes(&gp, rows, nb, 1);
+  P.gws = ws.take<char>(P.gws_bytes);
+  if (!P.h_eval || !P.offs2 || !P.h || !P.ab || !ok || !P.gws) { set_error("adv_step: workspace too small (have %zu bytes)", ws.cap); return ADVMIL_ERR_WORKSPACE; }
+  return ADVMIL_OK;
+}
+static void fill_train_acts(const AdvmilStepArgs* a, const Persist& P, AdvmilGenActs& ga) {
+  ga = AdvmilGenActs{};
+  ga.h = P.h; ga.ab = P.ab; ga.s = P.gb.s; ga.w = P.gb.w; ga.z = P.gb.z; ga.H = P.gb.H; ga.H1 = P.gb.H1; ga.pre = P.gb.pre;
+  ga.pred = a->pred_g; ga.noise0 = nullptr; ga.noise1 = a->noise_g; ga.h_eval = P.h_eval;
+  ga.mask_h = a->g_mask_h; ga.mask_a = a->g_mask_a; ga.mask_b = a->g_mask_b; ga.mask_rho = a->g_mask_rho; ga.mask_mlp0 = a->g_mask_mlp0;
+  ga.seed = a->seed_g; ga.train = 1; ga.precision = a->precision; ga.workspace = P.gws; ga.workspace_bytes = P.gws_bytes;
+}
+
 extern "C" size_t advmil_adv_step_workspace_bytes(const AdvmilGenParams* g, const AdvmilDiscParams* d, int32_t rows,
                                                   int32_t bags, int32_t precision) {
   const size_t es = elem_bytes(elem_of_precision(precision));
   const size_t R = rows / 16, nb = bags, abw = gate_width(g->h);
-  size_t persistent = align_up((size_t)rows * g->h * es, 256) + align_up((2 * nb + 2) * sizeof(int32_t), 256) + 1024;
+  size_t persistent = 2 * align_up((size_t)rows * g->h * es, 256) + align_up((2 * nb + 2) * sizeof(int32_t), 256) +
+                      align_up((size_t)rows * abw * es, 256) + gen_bufs_bytes(*g, rows, nb) +
+                      advmil_generator_workspace_bytes(g, rows, bags, 1) + 2048;
   size_t disc = gen_bufs_bytes(*g, rows, nb) + advmil_generator_workspace_bytes(g, rows, bags, 0) + 256 +
                 align_up(2 * R * d->d * sizeof(float), 256) + align_up((size_t)rows * d->d * es, 256) + head_bytes(*d, 2 * R, 2 * nb) +
                 align_up(2 * R * d->d * sizeof(float), 256) + 8 * 256 + 6 * nb * sizeof(float) +
                 advmil_disc_workspace_bytes(d, 2 * rows, 2 * bags, 1) + 256;
-  size_t gen = align_up((size_t)rows * g->h * es, 256) + align_up((size_t)rows * abw * es, 256) + gen_bufs_bytes(*g, rows, nb) +
-               advmil_generator_workspace_bytes(g, rows, bags, 1) + 256 + align_up(R * d->d * sizeof(float), 256) +
-               head_bytes(*d, R, nb) + 8 * 256 + 4 * nb * sizeof(float) + advmil_disc_workspace_bytes(d, rows, bags, 1) + 256;
+  size_t gen = align_up(R * d->d * sizeof(float), 256) + head_bytes(*d, R, nb) + 8 * 256 + 4 * nb * sizeof(float) +
+               advmil_disc_workspace_bytes(d, rows, bags, 1) + 256;
   return persistent + (disc > gen ? disc : gen) + 4096;
 }
 
@@ -92,8 +144,12 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   const bool batched = a->n_real > 0.f;                 // no real pair anywhere: only the fake half runs
   const int nbv = batched ? 2 * nb : nb, Rv = batched ? 2 * R : R;
   Workspace ws(a->workspace, a->workspace_bytes);
-  STEP_TAKE(h_eval, char, (size_t)rows * gp.h * es);
-  STEP_TAKE(offs2, int32_t, 2 * nb + 2);
+  Persist P;
+  ADVMIL_TRY(take_persist(ws, gp, rows, nb, es, P));
+  char* h_eval = P.h_eval;
+  int32_t* offs2 = P.offs2;
+  ADVMIL_TRY(side_init());
+  g_side.pending_ws = nullptr;
   // ---- generator, eval mode, detached (model_handler.py:383-387) ----
   GenBufs gb;
   if (!take_gen(ws, gp, rows, nb, gb)) { set_error("adv_step_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
@@ -110,6 +166,16 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   AdvmilEmbedActs ea{};
   ea.emb = emb2; ea.y_pre = y_pre; ea.precision = a->precision;
   ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
+  // ---- fork: the G step's train-mode generator forward runs on the side stream from here on ----
+  if (g_side.enabled && a->gen_grads && a->pred_g && a->noise_g) {
+    ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.fork, st));
+    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(g_side.stream, g_side.fork, 0));
+    AdvmilGenActs gt;
+    fill_train_acts(a, P, gt);
+    ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &gt, (void*)g_side.stream));
+    ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.done, g_side.stream));
+    g_side.pending_ws = a->workspace;
+  }
   // ---- batched head over the virtual bags [fake pairs | real pairs] ----
   AdvmilHeadActs ha{};
   if (!take_head(ws, dp, 2 * (size_t)R, 2 * (size_t)nb, ha)) { set_error("adv_step_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
@@ -154,24 +220,18 @@ extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
   const AdvmilBags* bags = a->bags;
   const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = dp.d;
   const size_t es = elem_bytes(elem_of_precision(a->precision));
-  const size_t abw = gate_width(gp.h);
   Workspace ws(a->workspace, a->workspace_bytes);
-  STEP_TAKE(h_eval, char, (size_t)rows * gp.h * es);      // written by advmil_adv_step_disc on this workspace
-  STEP_TAKE(offs2, int32_t, 2 * nb + 2);
-  (void)offs2;
-  // ---- generator, train mode, on the cached eval projection ----
-  STEP_TAKE(h, char, (size_t)rows * gp.h * es);
-  STEP_TAKE(ab, char, (size_t)rows * abw * es);
-  GenBufs gb;
-  if (!take_gen(ws, gp, rows, nb, gb)) { set_error("adv_step_gen: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
-  const size_t gws_bytes = advmil_generator_workspace_bytes(&gp, rows, nb, 1);
-  STEP_TAKE(gws, char, gws_bytes);
-  AdvmilGenActs ga{};
-  ga.h = h; ga.ab = ab; ga.s = gb.s; ga.w = gb.w; ga.z = gb.z; ga.H = gb.H; ga.H1 = gb.H1; ga.pre = gb.pre;
-  ga.pred = a->pred_g; ga.noise0 = nullptr; ga.noise1 = a->noise_g; ga.h_eval = h_eval;
-  ga.mask_h = a->g_mask_h; ga.mask_a = a->g_mask_a; ga.mask_b = a->g_mask_b; ga.mask_rho = a->g_mask_rho; ga.mask_mlp0 = a->g_mask_mlp0;
-  ga.seed = a->seed_g; ga.train = 1; ga.precision = a->precision; ga.workspace = gws; ga.workspace_bytes = gws_bytes;
-  ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
+  Persist P;                                                  // h_eval was written by advmil_adv_step_disc on this workspace
+  ADVMIL_TRY(take_persist(ws, gp, rows, nb, es, P));
+  // ---- generator, train mode, on the cached eval projection: join the side stream, or run it here ----
+  AdvmilGenActs ga;
+  fill_train_acts(a, P, ga);
+  if (g_side.pending_ws == a->workspace && g_side.stream) {
+    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(st, g_side.done, 0));
+    g_side.pending_ws = nullptr;
+  } else {
+    ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
+  }
   // ---- D(x, pred_g) with the updated discriminator, eval mode ----
   STEP_TAKE(emb, float, (size_t)R * d);
   AdvmilEmbedActs ea{};
