@@ -102,17 +102,24 @@ constexpr int A_STAGE_BYTES = TILE_M * 128;            // 128 rows x one 128-byt
 constexpr int STG_LD = 36;                             // staging row stride (floats) for 32-column chunks
 constexpr int STG_LD_LN = 132;                         // staging row stride for full 128-column rows
 
-template <int BLOCK_N, int EPI> struct RowCfg {
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 3 : 4;
+// ES = element size of the activation type.  The smem ring takes whatever the epilogue's staging leaves: the TMA -> MMA
+// pipeline is latency-bound (ncu: tensor pipe ~50 % busy with no memory level saturated), so depth matters more than
+// anything else here; the bf16 epilogues stage 80-byte rows (2.5 KB per warp) and leave room for 5 / 4 stages at
+// BLOCK_N = 192 / 256.
+template <int ES, int BLOCK_N, int EPI> struct RowCfg {
   static constexpr int EPI_WARPS = (EPI == EPI_LN) ? 4 : 8;       // 2 warps per TMEM lane quarter except for LN
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : 32 * STG_LD;
-  static constexpr int COEF_FLOATS_PER_WARP = 192;                // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c
-  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                                 (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 96) * 4 + 256 /*barriers*/;
+  static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : (ES == 2 ? 32 * 80 / 4 : 32 * STG_LD);
+  static constexpr int COEF_FLOATS_PER_WARP = (EPI == EPI_GATE) ? 192 : 0;   // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr size_t FIXED = 1024 /*align slack*/ + (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 96) * 4 +
+                                  256 /*barriers*/;
+  static constexpr int FIT = (int)((227 * 1024 - FIXED) / STAGE_BYTES);
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static_assert(STAGES >= 3, "shared-memory ring too shallow");
+  static constexpr size_t SMEM = FIXED + (size_t)STAGES * STAGE_BYTES;
 };
 
 __device__ __forceinline__ float fast_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -151,6 +158,31 @@ __device__ __forceinline__ void store_staged(const float* stg, int ld, T* __rest
       stv(out + (size_t)m * ldo + col0 + cv * VEC, o);
     }
   }
+}
+
+// bf16 outputs: a warp's [32 rows][32 columns] chunk, one row per lane in registers, is rounded to bf16 FIRST and staged
+// as 64-byte rows (80-byte stride: conflict-free 16-byte accesses), i.e. half the shared-memory traffic of fp32 staging --
+// the tensor pipe's operand fetch already uses most of the shared-memory bandwidth.  Lane l then stores 16 bytes of row
+// l/4 + 8*it: 4 lanes cover one 64-byte row segment.  Returns the 8 values this lane stored in pass `it` via `back`.
+constexpr int STGB_LD = 80;
+__device__ __forceinline__ void stage_rows_bf16(uint8_t* stgb, const float (&v)[32], int lane) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(stgb + lane * STGB_LD + q * 16) =
+        make_uint4(pack_bf2(v[8 * q], v[8 * q + 1]), pack_bf2(v[8 * q + 2], v[8 * q + 3]), pack_bf2(v[8 * q + 4], v[8 * q + 5]),
+                   pack_bf2(v[8 * q + 6], v[8 * q + 7]));
+}
+__device__ __forceinline__ void store_rows_bf16(uint8_t* stgb, const float (&v)[32], bf16* __restrict__ out, size_t ldo, int m_base,
+                                                int M, int col0, int lane) {
+  stage_rows_bf16(stgb, v, lane);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = (lane >> 2) + 8 * it, cv = lane & 3, m = m_base + r;
+    const uint4 qv = *reinterpret_cast<const uint4*>(stgb + r * STGB_LD + cv * 16);
+    if (m < M) *reinterpret_cast<uint4*>(out + (size_t)m * ldo + col0 + cv * 8) = qv;
+  }
+  __syncwarp();
 }
 
 // gate math on one 32-pair chunk: va/vb hold pre-activations on entry and tanh / sigmoid values on exit.
@@ -194,9 +226,9 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
 // N-tile in lock step; each loads half of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the
 // L2 -> SM traffic of the (per-tile re-streamed) weights, which is what bounds these kernels once the epilogues are cheap.
 template <typename T, int BLOCK_N, int EPI, bool FAST, int CL>
-__global__ void __launch_bounds__(RowCfg<BLOCK_N, EPI>::THREADS, 1)
+__global__ void __launch_bounds__(RowCfg<(int)sizeof(T), BLOCK_N, EPI>::THREADS, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
-  using Cfg = RowCfg<BLOCK_N, EPI>;
+  using Cfg = RowCfg<(int)sizeof(T), BLOCK_N, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KBLK = TcElem<T>::KBLK;
   constexpr int VEC = VecN<T>::N;
@@ -321,11 +353,152 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       __syncwarp();
+      // bf16 backward-data: the ReLU-mask operand (this lane's own row of the forward activation, 64 bytes per chunk) does
+      // not depend on the accumulator: fetch it for every chunk of the tile BEFORE waiting for the MMAs
+      constexpr int NCHW = (BLOCK_N / 32 + 1) / 2;      // chunks this warp drains per tile
+      uint4 hpre[(EPI == EPI_BWD && sizeof(T) == 2) ? NCHW : 1][4];
+      if constexpr (EPI == EPI_BWD && sizeof(T) == 2) {
+        const bf16* srcp0 = reinterpret_cast<const bf16*>(ea.relu_src);
+        if (srcp0) {
+#pragma unroll
+          for (int k = 0; k < NCHW; ++k) {
+            const int chk = half + 2 * k;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              hpre[k][q] = (m_row < M && chk < BLOCK_N / 32)
+                               ? *reinterpret_cast<const uint4*>(srcp0 + (size_t)m_row * ea.ld_src + n0 + chk * 32 + q * 8)
+                               : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
       mbar_wait(&tfull[acc], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * BLOCK_N;
 
-      if constexpr (EPI == EPI_LINEAR || EPI == EPI_BWD) {
+      if constexpr ((EPI == EPI_LINEAR || EPI == EPI_BWD) && sizeof(T) == 2) {
+        // bf16: all epilogue math in the TMEM (row-per-lane) layout, then bf16 staging (see stage_rows_bf16)
+        constexpr int NCH = BLOCK_N / 32;
+        bf16* outp = reinterpret_cast<bf16*>(ea.out);
+        const bf16* srcp = reinterpret_cast<const bf16*>(ea.relu_src);
+        uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
+        const bool rowok = m_row < M;
+        int bg = 0; float wv = 0.f, inv = 0.f;
+        if constexpr (EPI == EPI_BWD) { bg = mybag[lane]; wv = myw[lane]; inv = myinv[lane]; }
+#pragma unroll
+        for (int kk = 0; kk < NCHW; ++kk) {
+          const int ch = half + 2 * kk;
+          if (ch >= NCH) break;
+          const int col0 = n0 + ch * 32;
+          uint4 hsrc[4];
+          if constexpr (EPI == EPI_BWD) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hsrc[q] = hpre[kk][q];
+          }
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          if (ch + 2 >= NCH) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          if constexpr (EPI == EPI_LINEAR) {
+            if (ea.bias) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col0) + q);
+                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+              }
+            }
+            if (ea.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (ea.drop.active) {
+              if (ea.drop.mask == nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const uint32_t hb = ea.drop.bits(m_row, col0 + i);
+                  v[i] = (hb & 0xFFFFu) >= ea.drop.thresh16 ? v[i] * ea.drop.inv_keep : 0.f;
+                  v[i + 1] = (hb >> 16) >= ea.drop.thresh16 ? v[i + 1] * ea.drop.inv_keep : 0.f;
+                }
+              } else if (rowok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = ea.drop.keep(m_row, col0 + i) ? v[i] * ea.drop.inv_keep : 0.f;
+              }
+            }
+          } else {
+            if (ea.dz) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 d4 = *(reinterpret_cast<const float4*>(ea.dz + (size_t)bg * N + col0) + q);
+                v[4 * q] = fmaf(wv, d4.x, v[4 * q]); v[4 * q + 1] = fmaf(wv, d4.y, v[4 * q + 1]);
+                v[4 * q + 2] = fmaf(wv, d4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(wv, d4.w, v[4 * q + 3]);
+              }
+            }
+            if (ea.dmean) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 d4 = *(reinterpret_cast<const float4*>(ea.dmean + (size_t)bg * N + col0) + q);
+                v[4 * q] = fmaf(inv, d4.x, v[4 * q]); v[4 * q + 1] = fmaf(inv, d4.y, v[4 * q + 1]);
+                v[4 * q + 2] = fmaf(inv, d4.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(inv, d4.w, v[4 * q + 3]);
+              }
+            }
+            if (srcp) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float sv[8];
+                raw_floats(hsrc[q], sv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[8 * q + e] = sv[e] > 0.f ? v[8 * q + e] * ea.inv_keep : 0.f;
+              }
+            }
+            if (ea.accumulate && rowok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float pv[8];
+                ldv(outp + (size_t)m_row * ea.ldo + col0 + q * 8, pv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[8 * q + e] += pv[e];
+              }
+            }
+          }
+          stage_rows_bf16(stgb, v, lane);
+          __syncwarp();
+          float cs[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+#pragma unroll
+          for (int it2 = 0; it2 < 4; ++it2) {
+            const int r = (lane >> 2) + 8 * it2, cv = lane & 3, m = m_base + r;
+            const uint4 qv = *reinterpret_cast<const uint4*>(stgb + r * STGB_LD + cv * 16);
+            if (m < M) {
+              *reinterpret_cast<uint4*>(outp + (size_t)m * ea.ldo + col0 + cv * 8) = qv;
+              if constexpr (EPI == EPI_BWD) {
+                float o[8];
+                raw_floats(qv, o);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) cs[e] += o[e];
+              }
+            }
+          }
+          if constexpr (EPI == EPI_BWD) {
+            if (ea.colpart) {      // column sums of this warp's 32 rows: halving butterfly over the 8 lanes that share cv
+              const bool up0 = (lane >> 2) & 1, up1 = (lane >> 3) & 1, up2 = (lane >> 4) & 1;
+              float k4[4], k2[2];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float recv = __shfl_xor_sync(0xffffffffu, up0 ? cs[e] : cs[e + 4], 4);
+                k4[e] = (up0 ? cs[e + 4] : cs[e]) + recv;
+              }
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float recv = __shfl_xor_sync(0xffffffffu, up1 ? k4[e] : k4[e + 2], 8);
+                k2[e] = (up1 ? k4[e + 2] : k4[e]) + recv;
+              }
+              const float recv = __shfl_xor_sync(0xffffffffu, up2 ? k2[0] : k2[1], 16);
+              const float tot = (up2 ? k2[1] : k2[0]) + recv;
+              ea.colpart[(size_t)(mt * 4 + wq) * N + col0 + (lane & 3) * 8 + (up0 ? 4 : 0) + (up1 ? 2 : 0) + (up2 ? 1 : 0)] = tot;
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_LINEAR || EPI == EPI_BWD) {
         constexpr int NCH = BLOCK_N / 32;
         constexpr int LPR = 32 / VEC, RPI = 32 / LPR, NIT = 32 / RPI;   // lanes per row, rows per pass, passes per chunk
         T* outp = reinterpret_cast<T*>(ea.out);
@@ -483,7 +656,12 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!train) partial = gate_chunk<FAST, 0>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
           else if (!masked) partial = gate_chunk<FAST, 1>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
           else partial = gate_chunk<FAST, 2>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
-          if (ea.ab) {
+          if constexpr (sizeof(T) == 2) {
+            if (ea.ab) {
+              store_rows_bf16(reinterpret_cast<uint8_t*>(stg), va, reinterpret_cast<bf16*>(ea.ab), ea.ldo, m_base, M, n0 + ca, lane);
+              store_rows_bf16(reinterpret_cast<uint8_t*>(stg), vb, reinterpret_cast<bf16*>(ea.ab), ea.ldo, m_base, M, n0 + cb, lane);
+            }
+          } else if (ea.ab) {
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
               if (hb == 0) stage_chunk(stg, STG_LD, 0, va, lane); else stage_chunk(stg, STG_LD, 0, vb, lane);
@@ -574,7 +752,7 @@ static int cluster_size() {
 
 template <typename T, int BLOCK_N, int EPI, bool FAST>
 static int launch_rows(const T* A, const T* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
-  using Cfg = RowCfg<BLOCK_N, EPI>;
+  using Cfg = RowCfg<(int)sizeof(T), BLOCK_N, EPI>;
   const int num_m = cdiv(rows, TILE_M), num_n = N / BLOCK_N;
   const int CL = (cluster_size() == 2 && num_m >= 2) ? 2 : 1;
   CUtensorMap tmA, tmB;
