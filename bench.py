@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--bags", type=int, default=BAGS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ragged", action="store_true",
+                    help="configs[2] instead of configs[1]: bag lengths log-uniform in [1024, 100000] (multiples of 16)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,7 +237,9 @@ def main():
     # ---- synthetic bags in pinned host memory: 2 distinct steps (2 GiB) cycled ----
     n_total = args.warmup + args.steps
     feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32     # the packed loader's storage format
-    steps = synthetic_steps(n_total, args.bags, args.rows, C_IN, seed=42 + rank, distinct=2, dtype=feat_dtype)
+    from advmil_b200.dataset.packed import loguniform_rows
+    steps = synthetic_steps(n_total, args.bags, loguniform_rows() if args.ragged else args.rows, C_IN, seed=42 + rank,
+                            distinct=2, dtype=feat_dtype)
     counts = None  # global pair counts come from a tiny all-reduce inside step()
 
     def barrier():
@@ -325,7 +329,7 @@ def main():
 
     # ================= roofline of the dominant kernel class =================
     peaks = load_peaks()
-    rows_per_launch = args.rows * args.bags
+    rows_per_launch = int(np.mean([sum(st.lengths) for st in steps[:2]]))
     BYTES_PER_ROW = bytes_per_row(2 if args.precision == "bf16" else 4)
     kern = {}
     for i, tag in enumerate(_lib.PROF_TAGS):
@@ -345,8 +349,9 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if top is not None and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("rows_per_launch") == rows_per_launch and top in tj:
-            traffic = tj[top]["read"] + tj[top]["write"]   # bytes per launch from the committed ncu --set full capture
+        tm = tj.get(args.precision, {})
+        if tj.get("rows_per_launch") == rows_per_launch and top in tm:
+            traffic = tm[top]["read"] + tm[top]["write"]   # bytes per launch from the committed ncu --set full capture
     if top is not None:
         if top in FLOP_PER_ROW:
             roof = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": peaks["tflops"],
@@ -368,8 +373,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"AdvMIL-ABMIL G+D step, {args.bags} synthetic bags of {args.rows}x1024 per step per GPU "
-                                   "(configs[1]); D step + G step + both Adam updates",
+            "config": {"workload": (f"AdvMIL-ABMIL G+D step, {args.bags} synthetic bags of {args.rows}x1024 per step per GPU "
+                                    "(configs[1]); D step + G step + both Adam updates") if not args.ragged else
+                                   (f"AdvMIL-ABMIL G+D step, {args.bags} packed bags per step per GPU with lengths log-uniform in "
+                                    f"[1024, 100000] (configs[2]; mean {rows_per_launch} rows per step)"),
+                       "rows_per_step_per_gpu": rows_per_launch,
                        "precision_mode": args.precision,
                        "feature_format": ("bf16 (packed loader's bf16 storage: features rounded once at packing time, fp32 "
                                           "accumulation/statistics/parameters)" if args.precision == "bf16" else "fp32"),
