@@ -38,7 +38,8 @@ class GenActs(C.Structure):
                 ("pre", c_fp), ("pred", c_fp), ("noise0", c_fp), ("noise1", c_fp), ("h_eval", c_fp),
                 ("mask_h", c_u8p), ("mask_a", c_u8p), ("mask_b", c_u8p), ("mask_rho", c_u8p), ("mask_mlp0", c_u8p),
                 ("seed", C.c_uint64), ("train", C.c_int32), ("precision", C.c_int32),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("h_drop_out", c_fp), ("seed_drop", C.c_uint64), ("mask_h_drop", c_u8p), ("h_ready", C.c_int32)]
 
 
 DISC_TENSORS = ["Wc", "bc", "ln_g", "ln_b", "F1a_w", "F1a_b", "F1b_w", "F1b_b", "Pg_w", "Pg_b", "Ps_w", "Ps_b",

@@ -146,8 +146,14 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
   Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train, p->o);
   Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train, p->hid);
   const int dt = elem_of_precision(a->precision);
-  if (a->h_eval) { ProfScope ps(PROF_DROPOUT, st); ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, dt, st)); }
-  else { ProfScope ps(PROF_PROJ, st); ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st)); }
+  if (a->h_ready) { /* `h` was written by an earlier eval pass (h_drop_out) */ }
+  else if (a->h_eval) { ProfScope ps(PROF_DROPOUT, st); ADVMIL_TRY(apply_dropout(a->h_eval, rows, h, dh, a->h, dt, st)); }
+  else {
+    ProfScope ps(PROF_PROJ, st);
+    Drop d2 = Drop::make(a->mask_h_drop, a->seed_drop, SITE_H, p->p_backbone, 1, p->h);
+    ADVMIL_TRY(linear_fwd(bags->x, p->W1, p->b1, rows, p->C, h, 1, dh, a->h, a->precision, st, a->h_drop_out,
+                          a->h_drop_out ? &d2 : nullptr));
+  }
   { ProfScope ps(PROF_GEN_TAIL, st); ADVMIL_TRY(gate_pack_weights(p->Wa, p->ba, p->Wb, p->bb, h, h, Wp, bp, st)); }
   { ProfScope ps(PROF_GATE, st);
     ADVMIL_TRY(gated_score_fwd(a->h, Wp, bp, p->wc, p->bc, rows, h, h, da, db, a->ab, nullptr, part, a->precision, st)); }

@@ -14,15 +14,17 @@ static bool gemm_ok(int K, int N, const void* a, const void* b) {
 static const char* kBf16Shape = "%s: the bf16 mode runs only on the tcgen05 engine and this shape is unsupported by it (rows=%d K=%d N=%d)";
 
 int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-               void* y, int precision, cudaStream_t st) {
+               void* y, int precision, cudaStream_t st, void* y2, const Drop* drop2) {
   ADVMIL_REQUIRE(gemm_ok(K, N, x, W), "linear_fwd: K=%d N=%d must be multiples of 4 and pointers 16B aligned", K, N);
   if (rows == 0) return ADVMIL_OK;
   if (precision != ADVMIL_FP32 && tc_linear_supported(rows, K, N, elem_of_precision(precision)))
-    return tc_linear_fwd(x, W, b, rows, K, N, relu, drop, y, precision, st);
+    return tc_linear_fwd(x, W, b, rows, K, N, relu, drop, y, precision, st, y2, drop2);
   ADVMIL_REQUIRE(precision != ADVMIL_BF16, kBf16Shape, "linear_fwd", rows, K, N);
   GemmArgs g{(const float*)x, W, rows, N, K, K, K, K};
   EpiLinear epi{(float*)y, N, b, relu, drop, N};
-  return launch_gemm<true, true>(g, epi, 1, st);
+  ADVMIL_TRY((launch_gemm<true, true>(g, epi, 1, st)));
+  if (y2 && drop2) return apply_dropout(y, rows, N, *drop2, y2, ELEM_F32, st);
+  return ADVMIL_OK;
 }
 
 int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,

@@ -89,6 +89,7 @@ enum RowEpiKind : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_LN = 2, EPI_BWD = 3 };
 struct RowEpi {
   void* out; int ldo; const float* bias;
   int relu; Drop drop;                                                           // EPI_LINEAR
+  void* out2; Drop drop2;                                                        // EPI_LINEAR: optional second output = dropout(out) under drop2
   void* ab; const float* wc; float* part; int D; Drop drop_a, drop_b;            // EPI_GATE (bias = packed gate bias)
   void* y_pre; float* emb; const float* gamma; const float* beta; float eps;     // EPI_LN
   const float* w; const float* dz; const int32_t* offsets; int bags;             // EPI_BWD
@@ -458,6 +459,24 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if constexpr (EPI == EPI_LINEAR) {
+            if (ea.out2) {     // second output: the same activations under another dropout draw (the G step's train pass)
+              store_rows_bf16(stgb, v, outp, ea.ldo, m_base, M, col0, lane);
+              if (ea.drop2.mask == nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const uint32_t hb = ea.drop2.bits(m_row, col0 + i);
+                  v[i] = (hb & 0xFFFFu) >= ea.drop2.thresh16 ? v[i] * ea.drop2.inv_keep : 0.f;
+                  v[i + 1] = (hb >> 16) >= ea.drop2.thresh16 ? v[i + 1] * ea.drop2.inv_keep : 0.f;
+                }
+              } else if (rowok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = ea.drop2.keep(m_row, col0 + i) ? v[i] * ea.drop2.inv_keep : 0.f;
+              }
+              store_rows_bf16(stgb, v, reinterpret_cast<bf16*>(ea.out2), ea.ldo, m_base, M, col0, lane);
+              continue;
+            }
+          }
           stage_rows_bf16(stgb, v, lane);
           __syncwarp();
           float cs[8];
@@ -594,6 +613,13 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int e = 0; e < VEC; ++e) cs[e] += o[e];
               }
               stv(outp + (size_t)m * ea.ldo + col, o);
+              if constexpr (EPI == EPI_LINEAR) {
+                if (ea.out2) {
+#pragma unroll
+                  for (int e = 0; e < VEC; ++e) o[e] = ea.drop2.keep(m, col + e) ? o[e] * ea.drop2.inv_keep : 0.f;
+                  stv(reinterpret_cast<T*>(ea.out2) + (size_t)m * ea.ldo + col, o);
+                }
+              }
             }
           }
           if constexpr (EPI == EPI_BWD) {
@@ -979,17 +1005,18 @@ static int launch_rows_any(const T* A, const T* W, int rows, int K, int N, const
 
 template <typename T>
 static int tc_linear_fwd_t(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-                           void* y, cudaStream_t st) {
+                           void* y, void* y2, const Drop* drop2, cudaStream_t st) {
   const T* Wt;
   ADVMIL_TRY(weight_operand<T>(W, (size_t)N * K, WS_LINEAR, st, &Wt));
   RowEpi ea{};
   ea.out = y; ea.ldo = N; ea.bias = b; ea.relu = relu; ea.drop = drop;
+  if (y2 && drop2) { ea.out2 = y2; ea.drop2 = *drop2; }
   return launch_rows_any<T, EPI_LINEAR, true>((const T*)x, Wt, rows, K, N, ea, st);
 }
 int tc_linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-                  void* y, int precision, cudaStream_t st) {
-  if (precision == ADVMIL_BF16) return tc_linear_fwd_t<bf16>(x, W, b, rows, K, N, relu, drop, y, st);
-  return tc_linear_fwd_t<float>(x, W, b, rows, K, N, relu, drop, y, st);
+                  void* y, int precision, cudaStream_t st, void* y2, const Drop* drop2) {
+  if (precision == ADVMIL_BF16) return tc_linear_fwd_t<bf16>(x, W, b, rows, K, N, relu, drop, y, y2, drop2, st);
+  return tc_linear_fwd_t<float>(x, W, b, rows, K, N, relu, drop, y, y2, drop2, st);
 }
 
 bool tc_gate_supported(int rows, int L, int D, int dt) { return rows_ok(rows, dt) && L % kblk_of(dt) == 0 && D % 128 == 0; }

@@ -692,48 +692,47 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
   }
 }
 
-// d == 128: 8 lanes per row (16 columns per lane as 16-byte vectors interleaved across the 8 lanes so that every load
-// instruction covers 128 contiguous bytes per row), 4 rows per warp, two such groups in flight
+// d == 128: 16 lanes per row (8 columns per lane as 16-byte vectors interleaved across the 16 lanes, so every load
+// instruction covers 256 contiguous bytes per row), 2 rows per warp and 4 such pairs in flight: 8 rows = half a region
+// per warp iteration; 24 partial-sum registers per lane keep the occupancy at 4+ CTAs per SM
 template <typename T>
 __global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
     const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ d_emb2,
     const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y,
     float* __restrict__ part) {
-  constexpr int VEC = VecN<T>::N, NV = 16 / VEC;          // vectors per lane
+  constexpr int VEC = VecN<T>::N, NV = 8 / VEC;           // vectors per lane (2 for fp32, 1 for bf16)
   __shared__ float sm[4 * 3 * 128];
-  __shared__ __align__(16) float gb_s[2 * 128];           // gamma | beta, permuted so that my 16 columns are contiguous
   const int row0 = blockIdx.x * ROWS_PER_CTA;
   const int nrows = min(ROWS_PER_CTA, rows - row0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int sub = lane & 7, slot = lane >> 3;             // column group, row slot within the warp
-  // column of element (k, e): k * 8 * VEC + sub * VEC + e
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) {   // i = sub' * 16 + k * VEC + e
-    const int sb = i >> 4, k = (i & 15) / VEC, e = (i & 15) % VEC;
-    const int c = k * 8 * VEC + sb * VEC + e;
-    gb_s[i] = gamma[c]; gb_s[128 + i] = beta[c];
-  }
-  __syncthreads();
-  float pg[16], pb[16], pbias[16];
+  const int sub = lane & 15, slot = lane >> 4;            // column group, row slot within the warp
+  // column of element (k, e): k * 16 * VEC + sub * VEC + e
+  float g[8], be[8], pg[8], pb[8], pbias[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { pg[i] = 0.f; pb[i] = 0.f; pbias[i] = 0.f; }
-  const float* g = gb_s + sub * 16;
-  const float* be = gb_s + 128 + sub * 16;
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int c = k * 16 * VEC + sub * VEC + e, i = k * VEC + e;
+      g[i] = gamma[c]; be[i] = beta[c]; pg[i] = 0.f; pb[i] = 0.f; pbias[i] = 0.f;
+    }
   for (int rb = wid * 8; rb < nrows; rb += 32) {
-    float y[2][16], ge[16];
-    bool ok[2];
     // rb is a multiple of 8: the 8 rows of this warp iteration lie in ONE 16-row region
+    float ge[8];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
       for (int q4 = 0; q4 < VEC / 4; ++q4) {
-        const size_t go = ((size_t)(row0 + rb) >> 4) * 128 + k * 8 * VEC + sub * VEC + 4 * q4;
+        const size_t go = ((size_t)(row0 + rb) >> 4) * 128 + k * 16 * VEC + sub * VEC + 4 * q4;
         float4 d4 = *reinterpret_cast<const float4*>(d_emb + go);
         if (d_emb2) { const float4 e4 = *reinterpret_cast<const float4*>(d_emb2 + go); d4.x += e4.x; d4.y += e4.y; d4.z += e4.z; d4.w += e4.w; }
-        ge[k * VEC + 4 * q4] = d4.x; ge[k * VEC + 4 * q4 + 1] = d4.y; ge[k * VEC + 4 * q4 + 2] = d4.z; ge[k * VEC + 4 * q4 + 3] = d4.w;
+        const int i = k * VEC + 4 * q4;
+        ge[i] = d4.x * 0.0625f; ge[i + 1] = d4.y * 0.0625f; ge[i + 2] = d4.z * 0.0625f; ge[i + 3] = d4.w * 0.0625f;
       }
+    float y[4][8];
+    bool ok[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int r = rb + u * 4 + slot;
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * 2 + slot;
       ok[u] = r < nrows;
       const size_t row = (size_t)(row0 + r);
 #pragma unroll
@@ -741,62 +740,62 @@ __global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
         float t[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) t[e] = 0.f;
-        if (ok[u]) ldv(y_pre + row * 128 + k * 8 * VEC + sub * VEC, t);
+        if (ok[u]) ldv(y_pre + row * 128 + k * 16 * VEC + sub * VEC, t);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) y[u][k * VEC + e] = t[e];
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const size_t row = (size_t)(row0 + rb + u * 4 + slot);
+    for (int u = 0; u < 4; ++u) {
+      const size_t row = (size_t)(row0 + rb + u * 2 + slot);
       float sacc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) sacc += y[u][i];
-      const float mean = oct_sum(sacc) * (1.0f / 128.0f);
+      for (int i = 0; i < 8; ++i) sacc += y[u][i];
+      const float mean = half_warp_sum(sacc) * (1.0f / 128.0f);
       float q = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { const float c = y[u][i] - mean; q = fmaf(c, c, q); }
-      const float rstd = rsqrtf(oct_sum(q) * (1.0f / 128.0f) + eps);
-      float xh[16], dxh[16], s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < 8; ++i) { const float c = y[u][i] - mean; q = fmaf(c, c, q); }
+      const float rstd = rsqrtf(half_warp_sum(q) * (1.0f / 128.0f) + eps);
+      float xh[8], dxh[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
         xh[i] = (y[u][i] - mean) * rstd;
         const float e = fmaf(xh[i], g[i], be[i]);
-        const float de = (e > 0.f && ok[u]) ? ge[i] * (1.0f / 16.0f) : 0.f;
+        const float de = (e > 0.f && ok[u]) ? ge[i] : 0.f;
         pg[i] = fmaf(de, xh[i], pg[i]);
         pb[i] += de;
         dxh[i] = de * g[i];
         s1 += dxh[i];
         s2 = fmaf(dxh[i], xh[i], s2);
       }
-      const float m1 = oct_sum(s1) * (1.0f / 128.0f), m2 = oct_sum(s2) * (1.0f / 128.0f);
-      float dy[16];
+      const float m1 = half_warp_sum(s1) * (1.0f / 128.0f), m2 = half_warp_sum(s2) * (1.0f / 128.0f);
+      float dy[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { dy[i] = rstd * (dxh[i] - m1 - xh[i] * m2); if (ok[u]) pbias[i] += dy[i]; }
+      for (int i = 0; i < 8; ++i) { dy[i] = rstd * (dxh[i] - m1 - xh[i] * m2); if (ok[u]) pbias[i] += dy[i]; }
       if (ok[u]) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           float t[VEC];
 #pragma unroll
           for (int e = 0; e < VEC; ++e) t[e] = dy[k * VEC + e];
-          stv(d_y + row * 128 + k * 8 * VEC + sub * VEC, t);
+          stv(d_y + row * 128 + k * 16 * VEC + sub * VEC, t);
         }
       }
     }
   }
-  // fold the 4 row slots of the warp, then the 8 warps
+  // fold the 2 row slots of the warp, then the 4 warps
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    pg[i] += __shfl_xor_sync(0xffffffffu, pg[i], 8); pg[i] += __shfl_xor_sync(0xffffffffu, pg[i], 16);
-    pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], 8); pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], 16);
-    pbias[i] += __shfl_xor_sync(0xffffffffu, pbias[i], 8); pbias[i] += __shfl_xor_sync(0xffffffffu, pbias[i], 16);
+  for (int i = 0; i < 8; ++i) {
+    pg[i] += __shfl_xor_sync(0xffffffffu, pg[i], 16);
+    pb[i] += __shfl_xor_sync(0xffffffffu, pb[i], 16);
+    pbias[i] += __shfl_xor_sync(0xffffffffu, pbias[i], 16);
   }
   if (slot == 0) {
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const int c = k * 8 * VEC + sub * VEC + e, i = k * VEC + e;
+        const int c = k * 16 * VEC + sub * VEC + e, i = k * VEC + e;
         sm[(wid * 3 + 0) * 128 + c] = pg[i];
         sm[(wid * 3 + 1) * 128 + c] = pb[i];
         sm[(wid * 3 + 2) * 128 + c] = pbias[i];

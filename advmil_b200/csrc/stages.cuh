@@ -8,8 +8,10 @@ namespace advmil {
 // Activation tensors ([rows, *]: x, y, v, ab, y_pre, dY, dX, X, relu_src) are `const void*` / `void*`: bf16 when
 // precision == ADVMIL_BF16 (or dt == ELEM_BF16), fp32 otherwise.  Weights, biases, statistics and outputs at bag / region
 // granularity are always fp32.
+// y2 / drop2 (optional): a second output y2 = dropout(y) under drop2, written by the same pass (the tcgen05 epilogue
+// stores both; the FFMA engine adds an apply_dropout pass)
 int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
-               void* y, int precision, cudaStream_t st);
+               void* y, int precision, cudaStream_t st, void* y2 = nullptr, const Drop* drop2 = nullptr);
 // packed gate weights Wp [abw, L], bp [abw] (zero padded) must have been built by gate_pack_weights.
 // s == nullptr: only the per-tile partial scores part_ws [abw/128][rows] are produced (seg_softmax_pool_fwd finishes them)
 int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,

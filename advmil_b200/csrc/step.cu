@@ -3,8 +3,8 @@
 //
 //  * real and fake pairs of the D step share one region-embedding pass and run through ONE batched RLIP head pass: the
 //    head sees 2 x bags "virtual bags" (fake pairs first, then real pairs) over a duplicated [2R, d] embedding;
-//  * the D-step generator forward (eval) and the G-step generator forward (train) share relu(x W1^T + b1): the eval
-//    projection stays in the workspace between the two calls and the G step applies its dropout draw to it;
+//  * the D-step generator forward (eval) and the G-step generator forward (train) share relu(x W1^T + b1): the projection
+//    kernel of the D phase writes both the eval activations and the G step's dropped copy (its seed is known up front);
 //  * the G step asks D only for dL/dt and never touches D-parameter gradients.
 #include <stdlib.h>
 #include <vector>
@@ -103,7 +103,8 @@ static int take_persist(Workspace& ws, const AdvmilGenParams& gp, int rows, int 
 static void fill_train_acts(const AdvmilStepArgs* a, const Persist& P, AdvmilGenActs& ga) {
   ga = AdvmilGenActs{};
   ga.h = P.h; ga.ab = P.ab; ga.s = P.gb.s; ga.w = P.gb.w; ga.z = P.gb.z; ga.H = P.gb.H; ga.H1 = P.gb.H1; ga.pre = P.gb.pre;
-  ga.pred = a->pred_g; ga.noise0 = nullptr; ga.noise1 = a->noise_g; ga.h_eval = P.h_eval;
+  ga.pred = a->pred_g; ga.noise0 = nullptr; ga.noise1 = a->noise_g;
+  ga.h_eval = nullptr; ga.h_ready = 1;   // the disc phase's projection kernel already wrote dropout(h_eval) into P.h
   ga.mask_h = a->g_mask_h; ga.mask_a = a->g_mask_a; ga.mask_b = a->g_mask_b; ga.mask_rho = a->g_mask_rho; ga.mask_mlp0 = a->g_mask_mlp0;
   ga.seed = a->seed_g; ga.train = 1; ga.precision = a->precision; ga.workspace = P.gws; ga.workspace_bytes = P.gws_bytes;
 }
@@ -159,6 +160,7 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   ga.h = h_eval; ga.ab = nullptr; ga.s = gb.s; ga.w = gb.w; ga.z = gb.z; ga.H = gb.H; ga.H1 = gb.H1; ga.pre = gb.pre;
   ga.pred = a->pred_d; ga.noise0 = nullptr; ga.noise1 = a->noise_d; ga.h_eval = nullptr;
   ga.seed = 0; ga.train = 0; ga.precision = a->precision; ga.workspace = gws; ga.workspace_bytes = gws_bytes;
+  ga.h_drop_out = P.h; ga.seed_drop = a->seed_g; ga.mask_h_drop = a->g_mask_h;   // the G step's dropped projection, same pass
   ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
   // ---- shared region embedding (K5+K6), duplicated for the batched head ----
   STEP_TAKE(emb2, float, (size_t)2 * R * d);

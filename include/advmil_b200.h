@@ -105,6 +105,11 @@ typedef struct AdvmilGenActs {
   int32_t train;       /* 0 eval (no dropout), 1 train */
   int32_t precision;   /* AdvmilPrecision */
   void* workspace; size_t workspace_bytes;
+  /* projection sharing between an eval pass and a later train pass over the same x and W1 (the fused step):
+   *   eval pass : h_drop_out != NULL -> the projection kernel also writes dropout(h) under (seed_drop | mask_h_drop) there;
+   *   train pass: h_ready != 0       -> `h` already holds that dropped projection: neither K1 nor a dropout pass runs.   */
+  void* h_drop_out; uint64_t seed_drop; const uint8_t* mask_h_drop;
+  int32_t h_ready;
 } AdvmilGenActs;
 
 /* ---- discriminator: RLIP (model/GANSurv.py:71-105, model/model_utils.py:157-210,
