@@ -130,7 +130,7 @@ SYMBOLS = {
 }
 
 PROF_TAGS = ["proj_fwd", "gate_fwd", "pool_fwd", "embed_fwd", "pool_gate_bwd", "bwd_data", "bwd_w_gate", "bwd_w_proj",
-             "ln_bwd", "bwd_w_embed", "colsum", "dropout", "head_fwd", "head_bwd", "gen_tail", "loss_opt"]
+             "ln_bwd", "bwd_w_embed", "colsum", "dropout", "head_fwd", "head_bwd", "gen_tail", "loss_opt", "proj_embed_fwd"]
 
 _lib = None
 

@@ -64,7 +64,8 @@ enum ProfTag : int {
   PROF_HEAD_BWD = 13,   // RLIP head backward
   PROF_GEN_TAIL = 14,   // generator per-bag head fwd/bwd, small outer products, gate weight packing
   PROF_LOSS_OPT = 15,   // losses, Adam, L1 value
-  PROF_NTAGS = 16
+  PROF_PROJ_EMBED = 16, // K1 + K5/K6 fused over stacked weights (bf16 fused step)
+  PROF_NTAGS = 17
 };
 struct ProfScope {
   int tag; cudaStream_t st; void* rec;

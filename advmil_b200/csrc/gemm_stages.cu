@@ -27,6 +27,16 @@ int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, i
   return ADVMIL_OK;
 }
 
+bool proj_embed_supported(int rows, int C, int h, int d, int precision) {
+  return precision == ADVMIL_BF16 && rows % 16 == 0 && tc_proj_embed_supported(rows, C, h, d, ELEM_BF16);
+}
+int proj_embed_fwd(const void* x, const float* W1, const float* b1, const float* Wc, const float* bc, const float* gamma,
+                   const float* beta, int rows, int C, int h, int d, float eps, void* hout, void* hdrop, const Drop* drop2,
+                   void* y_pre, float* emb, cudaStream_t st) {
+  ADVMIL_REQUIRE(tc_proj_embed_supported(rows, C, h, d, ELEM_BF16) && rows % 16 == 0, "proj_embed_fwd: unsupported shape rows=%d C=%d h=%d d=%d", rows, C, h, d);
+  return tc_proj_embed_fwd(x, W1, b1, Wc, bc, gamma, beta, rows, C, h, d, eps, hout, hdrop, drop2, y_pre, emb, st);
+}
+
 int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,
                     int D, const Drop& da, const Drop& db, void* ab, float* s, float* part_ws, int precision,
                     cudaStream_t st) {

@@ -83,7 +83,7 @@ static int sm_count() {
 // ------------------------------------------------------------------------------------------------
 // epilogue parameter block
 // ------------------------------------------------------------------------------------------------
-enum RowEpiKind : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_LN = 2, EPI_BWD = 3 };
+enum RowEpiKind : int { EPI_LINEAR = 0, EPI_GATE = 1, EPI_LN = 2, EPI_BWD = 3, EPI_PE = 4 /* K1 + K5/K6 on stacked weights */ };
 
 // out / ab / y_pre / relu_src are [rows, *] activation tensors of the kernel's element type T (fp32 or bf16)
 struct RowEpi {
@@ -92,6 +92,7 @@ struct RowEpi {
   void* out2; Drop drop2;                                                        // EPI_LINEAR: optional second output = dropout(out) under drop2
   void* ab; const float* wc; float* part; int D; Drop drop_a, drop_b;            // EPI_GATE (bias = packed gate bias)
   void* y_pre; float* emb; const float* gamma; const float* beta; float eps;     // EPI_LN
+  int h_cols; const float* bias2;                                                // EPI_PE: columns [0, h_cols) = K1, last 128 = K5 (bias2 = conv bias)
   const float* w; const float* dz; const int32_t* offsets; int bags;             // EPI_BWD
   const float* dmean; int accumulate;
   float* colpart;                                                                // EPI_BWD: [4 * num_m][N] column sums of dX per 32 rows
@@ -112,8 +113,9 @@ template <int ES, int BLOCK_N, int EPI> struct RowCfg {
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : (ES == 2 ? 32 * 80 / 4 : 32 * STG_LD);
-  static constexpr int COEF_FLOATS_PER_WARP = (EPI == EPI_GATE) ? 192 : 0;   // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c
+  static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : ((ES == 2 && EPI != EPI_PE) ? 32 * 80 / 4 : 32 * STG_LD);
+  // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c;  proj+embed: conv bias | gamma | beta (128 each)
+  static constexpr int COEF_FLOATS_PER_WARP = (EPI == EPI_GATE) ? 192 : (EPI == EPI_PE) ? 384 : 0;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr size_t FIXED = 1024 /*align slack*/ + (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 96) * 4 +
                                   256 /*barriers*/;
@@ -330,6 +332,14 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int* mybag = rowbag + ew * 32;
     float* myw = roww + ew * 32;
     float* myinv = rowinv + ew * 32;
+    if constexpr (EPI == EPI_PE) {           // LayerNorm coefficients of the embed block: constant for the whole launch
+      if (half == 1) {
+        for (int t = lane; t < 128; t += 32) {
+          coef[t] = __ldg(ea.bias2 + t); coef[128 + t] = __ldg(ea.gamma + t); coef[256 + t] = __ldg(ea.beta + t);
+        }
+      }
+      __syncwarp();
+    }
     int it = 0;
     for (int tile = work0; tile < total; tile += work_stride, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -664,6 +674,94 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_PE) {
+        // Stacked weights [W1; Wc]: this warp owns 128 columns of the 256-wide tile.  Columns below h_cols are the
+        // generator projection h = relu(x W1^T + b1) (plus the G step's dropped copy); the last 128 columns are the
+        // discriminator's y = x Wc^T + bc -> LayerNorm -> ReLU -> 16-row region mean.  x is read from HBM once for both.
+        static_assert(EPI != EPI_PE || (BLOCK_N == 256 && sizeof(T) == 2), "proj+embed epilogue: bf16, 256-column tiles");
+        const int cb = n0 + half * 128;
+        uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
+        const bool rowok = m_row < M;
+        const uint32_t tcol = taddr + half * 128;
+        if (cb < ea.h_cols) {
+          bf16* outp = reinterpret_cast<bf16*>(ea.out);
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            const int col0 = cb + k * 32;
+            float v[32];
+            tmem_ld32(tcol + k * 32, v);
+            if (k == 3) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col0) + q);
+              v[4 * q] = fmaxf(v[4 * q] + b4.x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + b4.y, 0.f);
+              v[4 * q + 2] = fmaxf(v[4 * q + 2] + b4.z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + b4.w, 0.f);
+            }
+            store_rows_bf16(stgb, v, outp, ea.ldo, m_base, M, col0, lane);
+            if (ea.out2) {
+              if (ea.drop2.mask == nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const uint32_t hb = ea.drop2.bits(m_row, col0 + i);
+                  v[i] = (hb & 0xFFFFu) >= ea.drop2.thresh16 ? v[i] * ea.drop2.inv_keep : 0.f;
+                  v[i + 1] = (hb >> 16) >= ea.drop2.thresh16 ? v[i + 1] * ea.drop2.inv_keep : 0.f;
+                }
+              } else if (rowok) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = ea.drop2.keep(m_row, col0 + i) ? v[i] * ea.drop2.inv_keep : 0.f;
+              }
+              store_rows_bf16(stgb, v, reinterpret_cast<bf16*>(ea.out2), ea.ldo, m_base, M, col0, lane);
+            }
+          }
+        } else {
+          // three sweeps over the 128 TMEM columns of this row (sum -> mean, squares -> rstd, normalise) keep the register
+          // footprint at one 32-column chunk; y is rounded to bf16 first: y_pre IS a bf16 tensor (see EPI_LN)
+          float ssum = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            float v[32];
+            tmem_ld32(tcol + k * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ssum += __bfloat162float(__float2bfloat16_rn(v[i] + coef[k * 32 + i]));
+          }
+          const float mean = ssum * (1.0f / 128.0f);
+          float qsum = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            float v[32];
+            tmem_ld32(tcol + k * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float c = __bfloat162float(__float2bfloat16_rn(v[i] + coef[k * 32 + i])) - mean;
+              qsum = fmaf(c, c, qsum);
+            }
+          }
+          const float rstd = rsqrtf(qsum * (1.0f / 128.0f) + ea.eps);
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            float v[32];
+            tmem_ld32(tcol + k * 32, v);
+            if (k == 3) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i] + coef[k * 32 + i]));
+            if (ea.y_pre) store_rows_bf16(stgb, v, reinterpret_cast<bf16*>(ea.y_pre), 128, m_base, M, k * 32, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              v[i] = rowok ? fmaxf(fmaf((v[i] - mean) * rstd, coef[128 + k * 32 + i], coef[256 + k * 32 + i]), 0.f) : 0.f;
+            stage_chunk(stg, STG_LD, 0, v, lane);
+            __syncwarp();
+            const int rg = lane >> 4, c2 = (lane & 15) * 2;      // two 16-row regions per warp, two columns per lane
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const float2 t2 = *reinterpret_cast<const float2*>(stg + (rg * 16 + r) * STG_LD + c2);
+              a0 += t2.x; a1 += t2.y;
+            }
+            const int m = m_base + rg * 16;
+            if (m < M) *reinterpret_cast<float2*>(ea.emb + (size_t)(m >> 4) * 128 + k * 32 + c2) = make_float2(a0 * 0.0625f, a1 * 0.0625f);
+            __syncwarp();
+          }
         }
       } else if constexpr (EPI == EPI_GATE) {
         // BLOCK_N = 256 = two packed gate blocks (64 tanh | 64 sigmoid columns); this warp owns block `half`
@@ -1017,6 +1115,28 @@ int tc_linear_fwd(const void* x, const float* W, const float* b, int rows, int K
                   void* y, int precision, cudaStream_t st, void* y2, const Drop* drop2) {
   if (precision == ADVMIL_BF16) return tc_linear_fwd_t<bf16>(x, W, b, rows, K, N, relu, drop, y, y2, drop2, st);
   return tc_linear_fwd_t<float>(x, W, b, rows, K, N, relu, drop, y, y2, drop2, st);
+}
+
+// K1 + K5/K6 in one pass over x (bf16 mode): stacked weights [W1; Wc] -> 256-wide tiles, the widest the single-CTA pipeline
+// can feed (profiles/exp_tile_width.py: 1.2 PFLOP/s vs 1.05 at 192), and x leaves HBM once instead of twice
+bool tc_proj_embed_supported(int rows, int C, int h, int d, int dt) {
+  return dt == ELEM_BF16 && rows >= 1 && C % TcElem<bf16>::KBLK == 0 && d == 128 && h % 128 == 0 && (h + d) % 256 == 0;
+}
+int tc_proj_embed_fwd(const void* x, const float* W1, const float* b1, const float* Wc, const float* bc, const float* gamma,
+                      const float* beta, int rows, int C, int h, int d, float eps, void* hout, void* hdrop, const Drop* drop2,
+                      void* y_pre, float* emb, cudaStream_t st) {
+  void* wp = nullptr;
+  ADVMIL_TRY(weight_scratch(WS_LINEAR, (size_t)(h + d) * C * sizeof(bf16), st, &wp));
+  bf16* Wt = (bf16*)wp;
+  to_bf16_kernel<<<cdiv(((size_t)h * C + 3) / 4, 256), 256, 0, st>>>(W1, (size_t)h * C, Wt);
+  ADVMIL_CHECK_LAUNCH();
+  to_bf16_kernel<<<cdiv(((size_t)d * C + 3) / 4, 256), 256, 0, st>>>(Wc, (size_t)d * C, Wt + (size_t)h * C);
+  ADVMIL_CHECK_LAUNCH();
+  RowEpi ea{};
+  ea.out = hout; ea.ldo = h; ea.bias = b1; ea.relu = 1;
+  if (hdrop && drop2) { ea.out2 = hdrop; ea.drop2 = *drop2; }
+  ea.h_cols = h; ea.bias2 = bc; ea.gamma = gamma; ea.beta = beta; ea.eps = eps; ea.y_pre = y_pre; ea.emb = emb;
+  return launch_rows<bf16, 256, EPI_PE, true>((const bf16*)x, Wt, rows, C, h + d, ea, st);
 }
 
 bool tc_gate_supported(int rows, int L, int D, int dt) { return rows_ok(rows, dt) && L % kblk_of(dt) == 0 && D % 128 == 0; }

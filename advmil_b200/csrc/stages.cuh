@@ -12,6 +12,12 @@ namespace advmil {
 // stores both; the FFMA engine adds an apply_dropout pass)
 int linear_fwd(const void* x, const float* W, const float* b, int rows, int K, int N, int relu, const Drop& drop,
                void* y, int precision, cudaStream_t st, void* y2 = nullptr, const Drop* drop2 = nullptr);
+// K1 (generator projection) and K5+K6 (discriminator region embedding) of the same x in ONE pass (bf16 mode, tcgen05 only):
+// hout = relu(x W1^T + b1), hdrop = dropout(hout) under drop2 (optional), y_pre / emb as region_embed_fwd
+bool proj_embed_supported(int rows, int C, int h, int d, int precision);
+int proj_embed_fwd(const void* x, const float* W1, const float* b1, const float* Wc, const float* bc, const float* gamma,
+                   const float* beta, int rows, int C, int h, int d, float eps, void* hout, void* hdrop, const Drop* drop2,
+                   void* y_pre, float* emb, cudaStream_t st);
 // packed gate weights Wp [abw, L], bp [abw] (zero padded) must have been built by gate_pack_weights.
 // s == nullptr: only the per-tile partial scores part_ws [abw/128][rows] are produced (seg_softmax_pool_fwd finishes them)
 int gated_score_fwd(const void* v, const float* Wp, const float* bp, const float* wc, const float* bc, int rows, int L,

@@ -161,13 +161,26 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   ga.pred = a->pred_d; ga.noise0 = nullptr; ga.noise1 = a->noise_d; ga.h_eval = nullptr;
   ga.seed = 0; ga.train = 0; ga.precision = a->precision; ga.workspace = gws; ga.workspace_bytes = gws_bytes;
   ga.h_drop_out = P.h; ga.seed_drop = a->seed_g; ga.mask_h_drop = a->g_mask_h;   // the G step's dropped projection, same pass
-  ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
   // ---- shared region embedding (K5+K6), duplicated for the batched head ----
   STEP_TAKE(emb2, float, (size_t)2 * R * d);
   STEP_TAKE(y_pre, char, (size_t)rows * d * es);
   AdvmilEmbedActs ea{};
   ea.emb = emb2; ea.y_pre = y_pre; ea.precision = a->precision;
-  ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
+  const char* fuse_env = getenv("ADVMIL_FUSE_PROJ_EMBED");          // "0" = separate K1 and K5 launches (debugging / A-B tests)
+  const int fuse_pe = (fuse_env && atoi(fuse_env) == 0) ? 0 : 1;
+  const bool fused = fuse_pe && gp.C == dp.C && proj_embed_supported(rows, gp.C, gp.h, d, a->precision);
+  if (fused) {     // K1 and K5+K6 read the same x: one pass over stacked weights, then the generator forward skips K1
+    for (int i = 0; i < nb; ++i)
+      ADVMIL_REQUIRE((bags->offsets_host[i + 1] - bags->offsets_host[i]) % 16 == 0,
+                     "bags: bag %d has a length that is not a multiple of 16 (model/backbone_utils.py:65)", i);
+    Drop d2 = Drop::make(a->g_mask_h, a->seed_g, SITE_H, gp.p_backbone, 1, gp.h);
+    { ProfScope ps(PROF_PROJ_EMBED, st);
+      ADVMIL_TRY(proj_embed_fwd(bags->x, gp.W1, gp.b1, dp.Wc, dp.bc, dp.ln_g, dp.ln_b, rows, gp.C, gp.h, d, dp.ln_eps, h_eval, P.h, &d2,
+                                y_pre, emb2, st)); }
+    ga.h_ready = 1; ga.h_drop_out = nullptr;
+  }
+  ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
+  if (!fused) ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
   // ---- fork: the G step's train-mode generator forward runs on the side stream from here on ----
   if (g_side.enabled && a->gen_grads && a->pred_g && a->noise_g) {
     ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.fork, st));

@@ -32,6 +32,7 @@ METRIC = "bags/sec per G+D train step (16k x 1024 bags)"
 N_ROWS, C_IN, BAGS_PER_STEP = 16384, 1024, 16
 FLOP_PER_ROW = {  # algorithmic FLOPs per instance row per launch
     "proj_fwd": 2 * 1024 * 384, "gate_fwd": 2 * 384 * 768 + 768, "embed_fwd": 2 * 1024 * 128,
+    "proj_embed_fwd": 2 * 1024 * (384 + 128),      # K1 + K5 in one pass over x (stacked weights)
     "bwd_data": 2 * 768 * 384, "bwd_w_gate": 2 * 768 * 384, "bwd_w_proj": 2 * 384 * 1024, "bwd_w_embed": 2 * 128 * 1024,
 }
 def bytes_per_row(es):

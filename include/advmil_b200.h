@@ -186,7 +186,8 @@ typedef enum AdvmilProfTag {
   ADVMIL_PROF_BWD_W_EMBED = 9, ADVMIL_PROF_COLSUM = 10, ADVMIL_PROF_DROPOUT = 11,
   /* composites of the region-level / bag-level (latency-bound) work, reported in microseconds, not as roofline fractions */
   ADVMIL_PROF_HEAD_FWD = 12, ADVMIL_PROF_HEAD_BWD = 13, ADVMIL_PROF_GEN_TAIL = 14, ADVMIL_PROF_LOSS_OPT = 15,
-  ADVMIL_PROF_NTAGS = 16
+  ADVMIL_PROF_PROJ_EMBED = 16, /* K1 + K5/K6 in one pass over x (fused step, bf16 mode) */
+  ADVMIL_PROF_NTAGS = 17
 } AdvmilProfTag;
 ADVMIL_API int advmil_profile_enable(int on);
 ADVMIL_API int advmil_profile_read(double* ms, int64_t* counts, int32_t ntags);

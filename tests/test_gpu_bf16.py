@@ -241,3 +241,38 @@ def test_cluster_generator_reduced_precision_vs_golden(mode):
             continue
         flip = k.startswith("backbone.phis.0")     # first-layer ReLU-mask flips (see the ABMIL test above)
         assert_close(sub(p.grad), ref, 1e-1 if (flip and mode == "bf16") else TOL, "grad " + k, atol=1e-4 * gmax)
+
+
+def test_fused_projection_embed_pass_equals_separate_kernels(monkeypatch):
+    """The bf16 fused step computes K1 (generator projection) and K5+K6 (discriminator region embedding) in one pass over
+    x on stacked weights.  Same contraction order per output element as the separate kernels, so one full D+G step must
+    agree with the ADVMIL_FUSE_PROJ_EMBED=0 path to float rounding of the downstream reductions."""
+    from advmil_b200.step import AdvStep
+    import advmil_b200.step as step_mod
+    C, h, o, d = 1024, 384, 384, 128
+    Ns = [320, 1600, 48, 16, 2048]
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(C, h, o), 21), O.synth_state_dict(O.D_SHAPES(C, d), 22)
+    xs = [O.synth_bag(n, 30 + i, C).cuda() for i, n in enumerate(Ns)]
+    t, e = O.synth_labels(len(Ns), 7)
+    e[0] = 1.0
+    vis = torch.ones(len(Ns), dtype=torch.uint8)
+    rng = np.random.default_rng(8)
+    nd = torch.tensor(rng.uniform(size=(len(Ns), o // 2)), dtype=torch.float32).cuda()
+    ng = torch.tensor(rng.uniform(size=(len(Ns), o // 2)), dtype=torch.float32).cuda()
+    results = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("ADVMIL_FUSE_PROJ_EMBED", fuse)
+        seeds = iter([101, 202])
+        monkeypatch.setattr(step_mod, "next_dropout_seed", lambda: next(seeds))
+        G, D = build_G((C, h, o)), build_D(C, d)
+        G.load_state_dict(sdG)
+        D.load_state_dict(sdD)
+        eng = AdvStep(G, D, precision="bf16")
+        out = eng.step(ops.PackedBags.from_list(xs), t.cuda(), e.cuda(), vis.cuda(), noise_d=nd, noise_g=ng)
+        torch.cuda.synchronize()
+        results.append((out, eng.D.grad.clone(), eng.G.grad.clone()))
+    (o1, dg1, gg1), (o0, dg0, gg0) = results
+    for k in ("pred_d", "pred_g", "f_d", "f_fake_g", "losses"):
+        assert_close(o1[k].cpu(), o0[k].cpu(), 1e-4, k, atol=1e-6)
+    assert_close(dg1.cpu(), dg0.cpu(), 1e-3, "D grads", atol=1e-7)
+    assert_close(gg1.cpu(), gg0.cpu(), 1e-3, "G grads", atol=1e-7)
