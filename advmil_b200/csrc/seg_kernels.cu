@@ -69,6 +69,46 @@ __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restri
   }
   if (threadIdx.y == 0 && c < ncols) out[c] = accumulate ? out[c] + sm[0][threadIdx.x] : sm[0][threadIdx.x];
 }
+// several column-sum reductions over the same number of partial rows in one launch
+struct ReduceSeg { const float* part; int width; int ncols; float* out; int accumulate; };
+struct ReduceBatch { ReduceSeg s[4]; int first_block[5]; int n; };
+__global__ void __launch_bounds__(1024) reduce_rows_multi_kernel(ReduceBatch rb, int nparts) {
+  __shared__ float sm[128][9];
+  int k = 0;
+  while (k + 1 < rb.n && (int)blockIdx.x >= rb.first_block[k + 1]) ++k;
+  const ReduceSeg q = rb.s[k];
+  const int c = (blockIdx.x - rb.first_block[k]) * 8 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < q.ncols) {
+    int p = threadIdx.y;
+    for (; p + 7 * 128 < nparts; p += 8 * 128) {
+      const float v0 = q.part[(size_t)p * q.width + c], v1 = q.part[(size_t)(p + 128) * q.width + c];
+      const float v2 = q.part[(size_t)(p + 256) * q.width + c], v3 = q.part[(size_t)(p + 384) * q.width + c];
+      const float v4 = q.part[(size_t)(p + 512) * q.width + c], v5 = q.part[(size_t)(p + 640) * q.width + c];
+      const float v6 = q.part[(size_t)(p + 768) * q.width + c], v7 = q.part[(size_t)(p + 896) * q.width + c];
+      a0 += v0 + v4; a1 += v1 + v5; a2 += v2 + v6; a3 += v3 + v7;
+    }
+    for (; p < nparts; p += 128) a0 += q.part[(size_t)p * q.width + c];
+  }
+  sm[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  for (int s_ = 64; s_ > 0; s_ >>= 1) {
+    if (threadIdx.y < s_) sm[threadIdx.y][threadIdx.x] += sm[threadIdx.y + s_][threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.y == 0 && c < q.ncols) q.out[c] = q.accumulate ? q.out[c] + sm[0][threadIdx.x] : sm[0][threadIdx.x];
+}
+static int reduce_rows_multi(const ReduceSeg* segs, int n, int nparts, cudaStream_t st) {
+  ReduceBatch rb;
+  rb.n = n;
+  int blocks = 0;
+  for (int k = 0; k < n; ++k) { rb.s[k] = segs[k]; rb.first_block[k] = blocks; blocks += cdiv(segs[k].ncols, 8); }
+  rb.first_block[n] = blocks;
+  reduce_rows_multi_kernel<<<blocks, dim3(8, 128), 0, st>>>(rb, nparts);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+
 int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
   reduce_rows_kernel<<<cdiv(width, 8), dim3(8, 128), 0, st>>>(part, nparts, width, width, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
@@ -594,15 +634,9 @@ static int pool_gate_bwd_t(const T* v, const float* w, const float* z, const flo
   ADVMIL_REQUIRE(smem <= 48 * 1024, "pool_gate_bwd: gate width %d needs too much shared memory", abw);
   pool_gate_bwd_kernel<T><<<chunks, threads, smem, st>>>(ds, ab, wc, rows, D, abw, RGN, da, db, dAB, part, part_b);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(D, 8), dim3(8, 128), 0, st>>>(part, chunks, D + 1, D, dwc, accumulate);
-  ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<1, dim3(8, 128), 0, st>>>(part + D, chunks, D + 1, 1, dbc, accumulate);
-  ADVMIL_CHECK_LAUNCH();
-  if (dbp) {   // packed gate-bias gradient (never accumulated: the caller unpacks it with its own accumulate flag)
-    reduce_rows_kernel<<<cdiv(abw, 8), dim3(8, 128), 0, st>>>(part_b, chunks, abw, abw, dbp, 0);
-    ADVMIL_CHECK_LAUNCH();
-  }
-  return ADVMIL_OK;
+  // dwc | dbc | packed gate-bias gradient (never accumulated: the caller unpacks it with its own accumulate flag)
+  ReduceSeg segs[3] = {{part, D + 1, D, dwc, accumulate}, {part + D, D + 1, 1, dbc, accumulate}, {part_b, abw, abw, dbp, 0}};
+  return reduce_rows_multi(segs, dbp ? 3 : 2, chunks, st);
 }
 int pool_gate_bwd(const void* v, const float* w, const float* z, const float* dz, const void* ab, const float* wc,
                   const int32_t* offsets, int rows, int bags, int L, int D, const Drop& da, const Drop& db, void* dAB,
@@ -824,13 +858,8 @@ int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, cons
   else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 8), dim3(8, 128), 0, st>>>(ws, chunks, 3 * d, d, dgamma, accumulate);
-  ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 8), dim3(8, 128), 0, st>>>(ws + d, chunks, 3 * d, d, dbeta, accumulate);
-  ADVMIL_CHECK_LAUNCH();
-  reduce_rows_kernel<<<cdiv(d, 8), dim3(8, 128), 0, st>>>(ws + 2 * d, chunks, 3 * d, d, dbias, accumulate);
-  ADVMIL_CHECK_LAUNCH();
-  return ADVMIL_OK;
+  ReduceSeg segs[3] = {{ws, 3 * d, d, dgamma, accumulate}, {ws + d, 3 * d, d, dbeta, accumulate}, {ws + 2 * d, 3 * d, d, dbias, accumulate}};
+  return reduce_rows_multi(segs, 3, chunks, st);
 }
 
 // =============================================================================================

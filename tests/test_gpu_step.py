@@ -137,3 +137,63 @@ def test_device_cindex_matches_reference_golden_and_oracle_counts():
         assert c["concordant"] + c["tied_risk"] + c["discordant"] == c["comparable"]
     with pytest.raises(ValueError):
         concordance_index(np.array([[0.5, 0.0], [0.7, 0.0]], dtype=np.float32), np.array([[0.1], [0.2]], dtype=np.float32))
+
+
+def test_packed_file_feeder_end_to_end(tmp_path):
+    """dataset/packed_file.py + DeviceFeeder + AdvStep (the e2e path of bench.py): bags written once as a bf16 blob, steps
+    assembled from the mmap into pinned buffers, copied asynchronously (double buffered), consumed by the fused step.  The
+    features that arrive on the device are exactly the stored ones; the step's outputs equal those of the same bags handed
+    over directly."""
+    from advmil_b200 import ops
+    from advmil_b200.dataset.packed import DeviceFeeder, group_steps
+    from advmil_b200.dataset.packed_file import PackedFile, write_packed
+    from advmil_b200.step import AdvStep
+    import advmil_b200.step as step_mod
+    g = torch.Generator().manual_seed(3)
+    lens = [64, 320, 16, 160, 96, 48, 640, 32]
+    bags = [torch.randn(n, 1024, generator=g) for n in lens]
+    labels = [(0.1 + 0.1 * i, float(i % 2 == 0)) for i in range(len(lens))]
+    path = str(tmp_path / "train.advmil")
+    write_packed(path, iter(bags), labels, dtype=torch.bfloat16)
+    pf = PackedFile(path)
+    groups = group_steps(len(pf), 4)
+    assert groups == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(), 5), O.synth_state_dict(O.D_SHAPES(), 6)
+
+    def run(feed):
+        seeds = iter(range(1000, 1100))
+        step_mod.next_dropout_seed, saved = (lambda: next(seeds)), step_mod.next_dropout_seed
+        try:
+            G, D = build_G(), build_D()
+            G.load_state_dict(sdG)
+            D.load_state_dict(sdD)
+            eng = AdvStep(G, D, precision="bf16")
+            torch.manual_seed(11)
+            outs = []
+            for bg, t, e, vis in feed():
+                outs.append(eng.step(bg, t, e, vis)["pred_g"].clone())
+            torch.cuda.synchronize()
+            return outs, [p.detach().clone() for p in G.parameters()]
+        finally:
+            step_mod.next_dropout_seed = saved
+
+    def via_feeder():
+        for s, idx in zip(DeviceFeeder((pf.step(idx) for idx in groups), device="cuda"), groups):
+            want = torch.cat([bags[i] for i in idx]).to(torch.bfloat16)
+            assert s.bags.x.dtype == torch.bfloat16 and torch.equal(s.bags.x.cpu(), want)
+            assert s.bags.offsets.cpu().tolist() == np.cumsum([0] + [lens[i] for i in idx]).tolist()
+            yield s.bags, s.t, s.e, s.visible
+
+    def direct():
+        for idx in groups:
+            x = torch.cat([bags[i] for i in idx]).to(torch.bfloat16).cuda()
+            lab = torch.tensor([labels[i] for i in idx])
+            yield (ops.PackedBags(x, [lens[i] for i in idx]), lab[:, 0].cuda(), lab[:, 1].cuda(),
+                   torch.ones(len(idx), dtype=torch.uint8).cuda())
+
+    o1, p1 = run(via_feeder)
+    o2, p2 = run(direct)
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)
+    for a, b in zip(p1, p2):
+        assert torch.equal(a, b)
