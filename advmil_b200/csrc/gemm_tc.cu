@@ -47,6 +47,7 @@ template <> struct TcElem<float> {
   static constexpr int MN_SBO = 512;            // 4 k-rows x 128 B per swizzle group
   __host__ __device__ static constexpr uint32_t idesc(int M, int N, int am, int bm) { return idesc_tf32(M, N, am, bm); }
   __device__ __forceinline__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_tf32(d, a, b, i, acc); }
+  __device__ __forceinline__ static void mma_pair(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_tf32_pair(d, a, b, i, acc); }
 };
 template <> struct TcElem<bf16> {
   static constexpr int KBLK = 64;
@@ -56,6 +57,7 @@ template <> struct TcElem<bf16> {
   static constexpr int MN_SBO = 1024;           // 8 k-rows x 128 B per swizzle atom
   __host__ __device__ static constexpr uint32_t idesc(int M, int N, int am, int bm) { return idesc_bf16(M, N, am, bm); }
   __device__ __forceinline__ static void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_f16(d, a, b, i, acc); }
+  __device__ __forceinline__ static void mma_pair(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { mma_f16_pair(d, a, b, i, acc); }
 };
 
 // row-major matrix [rows, cols] of T; box = box_rows x (128 B of elements), 128-byte swizzle, OOB reads return zeros
@@ -108,10 +110,10 @@ constexpr int STG_LD_LN = 132;                         // staging row stride for
 // pipeline is latency-bound (ncu: tensor pipe ~50 % busy with no memory level saturated), so depth matters more than
 // anything else here; the bf16 epilogues stage 80-byte rows (2.5 KB per warp) and leave room for 5 / 4 stages at
 // BLOCK_N = 192 / 256.
-template <int ES, int BLOCK_N, int EPI> struct RowCfg {
+template <int ES, int BLOCK_N, int EPI, int CL = 1> struct RowCfg {
   static constexpr int EPI_WARPS = (EPI == EPI_LN) ? 4 : 8;       // 2 warps per TMEM lane quarter except for LN
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
-  static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * 128 / CL;        // CTA pair: each CTA holds half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STG_FLOATS_PER_WARP = (EPI == EPI_LN) ? 32 * STG_LD_LN : ((ES == 2 && EPI != EPI_PE) ? 32 * 80 / 4 : 32 * STG_LD);
   // gate: 64 tanh biases | 64 sigmoid biases | 64 w_c;  proj+embed: conv bias | gamma | beta (128 each)
@@ -119,7 +121,7 @@ template <int ES, int BLOCK_N, int EPI> struct RowCfg {
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr size_t FIXED = 1024 /*align slack*/ + (size_t)EPI_WARPS * (STG_FLOATS_PER_WARP + COEF_FLOATS_PER_WARP + 96) * 4 +
                                   256 /*barriers*/;
-  static constexpr int FIT = (int)((227 * 1024 - FIXED) / STAGE_BYTES);
+  static constexpr int FIT = (int)((227 * 1024 - FIXED - 64) / STAGE_BYTES);
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
   static_assert(STAGES >= 3, "shared-memory ring too shallow");
   static constexpr size_t SMEM = FIXED + (size_t)STAGES * STAGE_BYTES;
@@ -225,13 +227,17 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
   return partial;
 }
 
-// CL = cluster size (1 or 2).  CL == 2: the two CTAs of a cluster work on two consecutive 128-row blocks of the SAME
-// N-tile in lock step; each loads half of the weight tile and TMA-multicasts it into both CTAs' shared memory, halving the
-// L2 -> SM traffic of the (per-tile re-streamed) weights, which is what bounds these kernels once the epilogues are cheap.
+// CL = cluster size (1 or 2).  CL == 2 = CTA pair: the two CTAs of a cluster own two consecutive 128-row blocks of the
+// SAME N-tile; each loads its own A tile and HALF of the weight tile, and the leader (rank 0) issues
+// tcgen05.mma.cta_group::2 with M = 256, which reads both halves of B from the two SMs' shared memories and writes each
+// CTA's 128 accumulator rows into that CTA's TMEM.  Per SM the operand bytes per MMA drop from A + B to A + B/2 -- the
+// L2 -> SM ingress is what bounds the single-CTA kernels (profiles/exp_tile_width.py).
+// Barriers: full (leader: the TMA loads of BOTH CTAs complete their bytes on it), empty and tfull (the leader's
+// tcgen05.commit, multicast to both CTAs), tempty (leader: both CTAs' epilogues drained the accumulator buffer).
 template <typename T, int BLOCK_N, int EPI, bool FAST, int CL>
 __global__ void __launch_bounds__(RowCfg<(int)sizeof(T), BLOCK_N, EPI>::THREADS, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
-  using Cfg = RowCfg<(int)sizeof(T), BLOCK_N, EPI>;
+  using Cfg = RowCfg<(int)sizeof(T), BLOCK_N, EPI, CL>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KBLK = TcElem<T>::KBLK;
   constexpr int VEC = VecN<T>::N;
@@ -247,7 +253,8 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bars = (uint64_t*)(rowinv + Cfg::EPI_WARPS * 32);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* pfull = bars + 2 * STAGES;   // [STAGES] (CTA pair, leader only)
+  uint64_t* tfull = bars + 3 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_ptr = (uint32_t*)(tempty + 2);
 
@@ -262,11 +269,12 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * Cfg::EPI_WARPS); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&pfull[i], 1); }
+    // accumulator release: every epilogue thread arrives (single CTA) / lane 0 of every epilogue warp of BOTH CTAs (pair)
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CL == 1 ? 32 * Cfg::EPI_WARPS : 2 * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  if (warp == 2) { if (CL == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); else tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();      // peer barriers must be initialised before any multicast / remote arrive
@@ -274,37 +282,39 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA: its own A rows, its own share of the B rows) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = work0; tile < total; tile += work_stride) {
         const int m0 = ((tile / num_n) * CL + crank) * TILE_M, n0 = (tile % num_n) * BLOCK_N;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);          // CL == 2: both CTAs have retired their MMAs on this slot
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(A_s + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * KBLK, m0);
+          mbar_wait(&empty[stage], phase ^ 1);          // the MMAs that read this slot (in BOTH shared memories) retired
           if (CL == 1) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(A_s + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * KBLK, m0);
             tma_load_2d(B_s + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kb * KBLK, n0);
-          } else {                                      // my half of the weight tile, multicast to both CTAs
-            constexpr int HALF_ROWS = BLOCK_N / CL;
-            tma_load_2d_mcast(B_s + stage * Cfg::B_STAGE_BYTES + crank * (HALF_ROWS * 128), &tmB, &full[stage], kb * KBLK,
-                              n0 + crank * HALF_ROWS, CMASK);
+          } else {       // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(A_s + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * KBLK, m0);
+            tma_load_2d_pair(B_s + stage * Cfg::B_STAGE_BYTES, &tmB, &full[stage], kb * KBLK, n0 + crank * (BLOCK_N / CL));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
+  } else if (warp == 1 && CL > 1 && crank != 0) {
+    // peer CTA: its MMA warp has nothing to do (the leader issues the pair MMAs for both)
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t IDESC = TcElem<T>::idesc(TILE_M, BLOCK_N, 0, 0);
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
+    constexpr uint32_t IDESC = TcElem<T>::idesc(TILE_M * CL, BLOCK_N, 0, 0);
     int stage = 0; uint32_t phase = 0; int it = 0;
     for (int tile = work0; tile < total; tile += work_stride, ++it) {
       const int acc = it & 1; const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tempty[acc], aphase ^ 1);
+      if (CL == 1) mbar_wait(&tempty[acc], aphase ^ 1); else mbar_wait_cluster(&tempty[acc], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait(&full[stage], phase);                 // CTA pair: covers the operands of BOTH CTAs
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(A_s + stage * A_STAGE_BYTES), b_addr = smem_u32(B_s + stage * Cfg::B_STAGE_BYTES);
@@ -312,11 +322,16 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kk = 0; kk < 4; ++kk) {   // one MMA = 32 bytes of K (8 tf32 / 16 bf16) inside the 128-byte swizzle row
             uint64_t ad = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
             uint64_t bd = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-            TcElem<T>::mma(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+            if (CL == 1) TcElem<T>::mma(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
+            else TcElem<T>::mma_pair(d_tmem, ad, bd, IDESC, (kb | kk) != 0 ? 1u : 0u);
           }
-          if (CL == 1) mma_commit(&empty[stage]);    // smem slot is free once these MMAs retire
-          else mma_commit_mcast(&empty[stage], CMASK);   // ... in BOTH CTAs (each producer writes into both)
-          if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+          if (CL == 1) {
+            mma_commit(&empty[stage]);               // smem slot is free once these MMAs retire
+            if (kb == kblocks - 1) mma_commit(&tfull[acc]);
+          } else {                                   // ... in BOTH CTAs; the accumulators of both are complete
+            mma_commit_pair(&empty[stage], CMASK);
+            if (kb == kblocks - 1) mma_commit_pair(&tfull[acc], CMASK);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -327,6 +342,13 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 4;               // 0..EPI_WARPS-1
     const int wq = warp & 3;               // TMEM lane quarter this warp may read
     const int half = ew >> 2;              // which half of the tile's columns this warp drains (0 when EPI_WARPS == 4)
+    // this warp no longer needs the TMEM accumulator buffer: tell the (leader's) MMA issuer
+    auto release_acc = [&](uint64_t* bar) {
+      tc_fence_before();
+      if (CL == 1) { mbar_arrive(bar); return; }
+      __syncwarp();
+      if (lane == 0) { if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); }
+    };
     float* stg = stg_all + ew * Cfg::STG_FLOATS_PER_WARP;
     float* coef = coef_all + ew * Cfg::COEF_FLOATS_PER_WARP;
     int* mybag = rowbag + ew * 32;
@@ -407,7 +429,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
-          if (ch + 2 >= NCH) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          if (ch + 2 >= NCH) { release_acc(&tempty[acc]); }
           if constexpr (EPI == EPI_LINEAR) {
             if (ea.bias) {
 #pragma unroll
@@ -546,7 +568,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           float v[32];
           tmem_ld32(taddr + ch * 32, v);
-          if (ch + 2 >= NCH) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          if (ch + 2 >= NCH) { release_acc(&tempty[acc]); }
           stage_chunk(stg, STG_LD, 0, v, lane);
           __syncwarp();
           float cs[VEC];
@@ -691,7 +713,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int col0 = cb + k * 32;
             float v[32];
             tmem_ld32(tcol + k * 32, v);
-            if (k == 3) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+            if (k == 3) { release_acc(&tempty[acc]); }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col0) + q);
@@ -742,7 +764,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             float v[32];
             tmem_ld32(tcol + k * 32, v);
-            if (k == 3) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+            if (k == 3) { release_acc(&tempty[acc]); }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i] + coef[k * 32 + i]));
             if (ea.y_pre) store_rows_bf16(stgb, v, reinterpret_cast<bf16*>(ea.y_pre), 128, m_base, M, k * 32, lane);
@@ -776,7 +798,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float va[32], vb[32];
           tmem_ld32(taddr + ca, va);
           tmem_ld32(taddr + cb, vb);
-          if (jc == 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+          if (jc == 1) { release_acc(&tempty[acc]); }
           if (!train) partial = gate_chunk<FAST, 0>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
           else if (!masked) partial = gate_chunk<FAST, 1>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
           else partial = gate_chunk<FAST, 2>(va, vb, coef + jc * 32, coef + 64 + jc * 32, coef + 128 + jc * 32, ea.drop_a, ea.drop_b, m_row, j0, partial);
@@ -813,8 +835,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[ch * 32 + i] = y;
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tempty[acc]);
+        release_acc(&tempty[acc]);
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 128; ++i) s += v[i];
@@ -862,21 +883,24 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();      // nobody exits while a peer may still multicast into / arrive on its shared memory
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  if (warp == 2) { tc_fence_after(); if (CL == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); }
 }
 
-// ADVMIL_TC_CLUSTER=2 enables the 2-CTA multicast variant.  Measured on B200 (round 1): no gain over single-CTA launches
-// (K1 380 vs 377 us, K2 310 vs 318 us) -- TMA multicast de-duplicates L2 reads only for clusters larger than 4 -- so the
-// default stays 1.
-static int g_cluster = -1;
-static int cluster_size() {
-  if (g_cluster < 0) { const char* e = getenv("ADVMIL_TC_CLUSTER"); g_cluster = (e && atoi(e) == 2) ? 2 : 1; }
-  return g_cluster;
+// ADVMIL_TC_CLUSTER=2 selects the CTA-pair (cta_group::2) variant of the rows kernel, 1 (default) the single-CTA one.
+// Measured on B200 (profiles/exp_tile_width.py, bf16, 262144 rows): with the epilogue removed BOTH variants run the
+// mainloop at 1.40 PFLOP/s on 256-wide tiles (= the measured sustained cuBLAS peak of this pool, 1.13 at 192-wide), and
+// with the epilogue they are within 3 % of each other (pair 1008 / 1184 / 1219 vs single 1052 / 1197 / 1237 TFLOP/s at
+// N = 384 / 512 / 768, K = 1024): operand ingress is not what separates these kernels from the peak, the epilogue's
+// HBM writes and latency are.  The single-CTA variant stays the default; the pair variant is kept tested.
+static int cluster_size() {            // read per launch: tests switch the variant inside one process
+  const char* e = getenv("ADVMIL_TC_CLUSTER");
+  return (e && atoi(e) == 2) ? 2 : 1;
 }
 
 template <typename T, int BLOCK_N, int EPI, bool FAST>
 static int launch_rows(const T* A, const T* W, int rows, int K, int N, const RowEpi& ea, cudaStream_t st) {
-  using Cfg = RowCfg<(int)sizeof(T), BLOCK_N, EPI>;
+  using Cfg1 = RowCfg<(int)sizeof(T), BLOCK_N, EPI, 1>;
+  using Cfg2 = RowCfg<(int)sizeof(T), BLOCK_N, EPI, 2>;
   const int num_m = cdiv(rows, TILE_M), num_n = N / BLOCK_N;
   const int CL = (cluster_size() == 2 && num_m >= 2) ? 2 : 1;
   CUtensorMap tmA, tmB;
@@ -884,13 +908,13 @@ static int launch_rows(const T* A, const T* W, int rows, int K, int N, const Row
   ADVMIL_TRY(make_tmap<T>(&tmB, W, N, K, BLOCK_N / CL));
   static bool attr_set = false;
   if (!attr_set) {
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg1::SMEM));
+    ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
     attr_set = true;
   }
   if (CL == 1) {
     const int grid = min(num_m * num_n, sm_count());
-    tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+    tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1><<<grid, Cfg1::THREADS, Cfg1::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
     ADVMIL_CHECK_LAUNCH();
     return ADVMIL_OK;
   }
@@ -898,8 +922,8 @@ static int launch_rows(const T* A, const T* W, int rows, int K, int N, const Row
   const int clusters = min(work, sm_count() / 2);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * 2);
-  cfg.blockDim = dim3(Cfg::THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.blockDim = dim3(Cfg2::THREADS);
+  cfg.dynamicSmemBytes = Cfg2::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
