@@ -197,3 +197,58 @@ def test_packed_file_feeder_end_to_end(tmp_path):
         assert torch.equal(a, b)
     for a, b in zip(p1, p2):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case", ["mixed", "all_unlabelled", "hinge"])
+def test_semi_supervised_steps_vs_oracle_trainer(case):
+    """configs[4]: labelled and unlabelled bags in one step.  Unlabelled bags (label_visible_mask == 0) give the
+    discriminator a fake pair only and the generator no reconstruction term (model_handler.py:373-377,465-470); a step
+    without any real pair takes the un-batched head path.  fp32 mode against the oracle's restatement of
+    _update_disc/_update_gen with torch.optim.Adam, two consecutive steps."""
+    from advmil_b200 import ops
+    from advmil_b200.step import AdvStep
+    Ns = [160, 320, 96, 640, 48]
+    B = len(Ns)
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(), 31), O.synth_state_dict(O.D_SHAPES(), 32)
+    which = "hinge" if case == "hinge" else "bce"
+    tr = O.CpuTrainer(sdG, sdD, which=which)
+    G, D = build_G(), build_D()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    eng = AdvStep(G, D, loss_d=which)
+    xs = [O.synth_bag(n, 40 + i) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(B, 9)
+    es[1] = 1.0
+    vis = [False] * B if case == "all_unlabelled" else [True, True, False, True, False]
+    bags = ops.PackedBags.from_list([x.cuda() for x in xs])
+    for step in range(2):
+        rng = np.random.default_rng(50 + step)
+        nd = torch.tensor(rng.uniform(size=(B, 192)), dtype=torch.float32)
+        ng = torch.tensor(rng.uniform(size=(B, 192)), dtype=torch.float32)
+        mr = [d_masks(n // 16, 128, 300 + 10 * i + step) for i, n in enumerate(Ns)]
+        mf = [d_masks(n // 16, 128, 400 + 10 * i + step) for i, n in enumerate(Ns)]
+        mg = [g_masks(n, 384, 384, 500 + 10 * i + step) for i, n in enumerate(Ns)]
+        ref = tr.step(xs, ts, es, vis, list(nd), list(ng), mr, mf, mg)
+        out = eng.step(bags, ts.cuda(), es.cuda(), torch.tensor(vis, dtype=torch.uint8).cuda(), noise_d=nd.cuda(), noise_g=ng.cuda(),
+                       masks_d_real=_cat_masks(mr, ["fc1", "ga", "gs", "fc2"]), masks_d_fake=_cat_masks(mf, ["fc1", "ga", "gs", "fc2"]),
+                       masks_g=_cat_masks(mg, ["h", "a", "b", "rho", "mlp0"]))
+        L = eng.loss_dict(out)
+        # hinge with every term active: d(loss)/d(prj_layer.bias) = sum(+1/n_fake) + sum(-1/n_real) = 0 exactly, so its
+        # fp32 value is rounding noise whose SIGN Adam turns into a +-lr move of that bias; every score after a D update
+        # then carries an offset of up to lr per update (any two correct fp32 evaluations differ there)
+        slack = 8e-5 if case == "hinge" else 0.0
+        assert_close(out["pred_d"].cpu(), ref["pred_d"].reshape(-1), RTOL, f"pred_d {step}", atol=slack * step * 1e-2)
+        assert_close(out["pred_g"].cpu(), ref["pred_g"].reshape(-1), RTOL, f"pred_g {step}", atol=slack * step * 1e-2)
+        assert_close(out["f_fake_d"].cpu(), ref["fake_d"].reshape(-1), RTOL, f"fake_d {step}", atol_scale=1e-1, atol=slack * step)
+        assert_close(out["f_fake_g"].cpu(), ref["fake_g"].reshape(-1), RTOL, f"fake_g {step}", atol_scale=1e-1, atol=slack * (step + 1))
+        tol = 2e-5 + slack * (step + 1)
+        assert abs(L["dis_loss"] - ref["dis_loss"]) < tol and abs(L["gen_loss"] - ref["gen_loss"]) < tol
+        assert abs(L["t_reg_loss"] - ref["t_reg"]) < tol and abs(L["gen_total_loss"] - ref["total"]) < tol
+        if case == "all_unlabelled":
+            assert out["f_real"] is None and L["t_reg_loss"] == 0.0
+    for k, p in D.named_parameters():
+        if not k.endswith(ZERO_GRAD):     # hinge: the per-bag upstream gradients sum to zero, see `slack` above
+            assert_close(p.detach().cpu(), tr.sdD[k].detach(), RTOL, "D param " + k, atol=8e-5 * 2 * (1.0 if case == "hinge" else 2e-2))
+    for k, p in G.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
