@@ -56,10 +56,12 @@ static size_t gen_bufs_bytes(const AdvmilGenParams& g, size_t rows, size_t nb) {
 // chain of small region-level kernels that leaves most SMs idle.  The disc call therefore issues that forward on a side
 // stream; the gen call joins it.  ADVMIL_STEP_OVERLAP=0 disables the fork (the gen call then runs the forward itself).
 struct SideState {
+  static constexpr int SLOTS = 4;       // engines (workspaces) with a forked forward in flight at the same time
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, done = nullptr;
-  const void* pending_ws = nullptr;     // workspace whose train forward is in flight / finished on the side stream
+  cudaEvent_t fork = nullptr, done[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  const void* pending_ws[SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // workspace whose train forward was forked
   int enabled = -1;
+  int find(const void* ws) const { for (int i = 0; i < SLOTS; ++i) if (pending_ws[i] == ws) return i; return -1; }
 };
 static SideState g_side;
 static int side_init() {
@@ -70,7 +72,7 @@ static int side_init() {
   if (g_side.enabled && !g_side.stream) {
     ADVMIL_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking));
     ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
-    ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.done, cudaEventDisableTiming));
+    for (int i = 0; i < SideState::SLOTS; ++i) ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.done[i], cudaEventDisableTiming));
   }
   return ADVMIL_OK;
 }
@@ -150,7 +152,7 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   char* h_eval = P.h_eval;
   int32_t* offs2 = P.offs2;
   ADVMIL_TRY(side_init());
-  g_side.pending_ws = nullptr;
+  { const int old = g_side.find(a->workspace); if (old >= 0) g_side.pending_ws[old] = nullptr; }   // a gen call never came
   // ---- generator, eval mode, detached (model_handler.py:383-387) ----
   GenBufs gb;
   if (!take_gen(ws, gp, rows, nb, gb)) { set_error("adv_step_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
@@ -182,14 +184,15 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
   if (!fused) ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
   // ---- fork: the G step's train-mode generator forward runs on the side stream from here on ----
-  if (g_side.enabled && a->gen_grads && a->pred_g && a->noise_g) {
+  const int slot = g_side.find(nullptr);      // no free slot: the gen call runs the forward itself
+  if (g_side.enabled && slot >= 0 && a->gen_grads && a->pred_g && a->noise_g) {
     ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.fork, st));
     ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(g_side.stream, g_side.fork, 0));
     AdvmilGenActs gt;
     fill_train_acts(a, P, gt);
     ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &gt, (void*)g_side.stream));
-    ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.done, g_side.stream));
-    g_side.pending_ws = a->workspace;
+    ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.done[slot], g_side.stream));
+    g_side.pending_ws[slot] = a->workspace;
   }
   // ---- batched head over the virtual bags [fake pairs | real pairs] ----
   AdvmilHeadActs ha{};
@@ -241,9 +244,10 @@ extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
   // ---- generator, train mode, on the cached eval projection: join the side stream, or run it here ----
   AdvmilGenActs ga;
   fill_train_acts(a, P, ga);
-  if (g_side.pending_ws == a->workspace && g_side.stream) {
-    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(st, g_side.done, 0));
-    g_side.pending_ws = nullptr;
+  const int slot = g_side.stream ? g_side.find(a->workspace) : -1;
+  if (slot >= 0) {
+    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(st, g_side.done[slot], 0));
+    g_side.pending_ws[slot] = nullptr;
   } else {
     ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
   }
