@@ -19,6 +19,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const int on = [] { const char* e = getenv("ADVMIL_PDL"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  return on != 0;
+}
 
 // ---- per-stage event profiling ------------------------------------------------------------------
 struct ProfRec { int tag; cudaEvent_t a, b; };
@@ -41,6 +45,7 @@ ProfScope::~ProfScope() {
 }
 
 __global__ void scale_offsets_kernel(const int32_t* __restrict__ in, int n, int div, int32_t* __restrict__ out) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] / div;
 }
@@ -305,7 +310,7 @@ static int make_region_offsets(const AdvmilBags* bags, Workspace& ws, cudaStream
   for (int i = 0; i <= bags->bags; ++i) ro.host[i] = bags->offsets_host[i] / 16;
   ro.dev = ws.take<int32_t>(bags->bags + 1);
   if (!ro.dev) { set_error("disc_head: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
-  scale_offsets_kernel<<<cdiv(bags->bags + 1, 128), 128, 0, st>>>(bags->offsets, bags->bags + 1, 16, ro.dev);
+  launch_k(scale_offsets_kernel, dim3(cdiv(bags->bags + 1, 128)), dim3(128), 0, st, bags->offsets, bags->bags + 1, 16, ro.dev);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

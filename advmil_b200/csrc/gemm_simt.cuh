@@ -73,6 +73,7 @@ struct TileLoader {
 
 template <bool A_KC, bool B_KC, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(GemmArgs g, Epi epi) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int t = threadIdx.x;
@@ -330,7 +331,7 @@ struct EpiPartial {
 template <bool A_KC, bool B_KC, class Epi>
 inline int launch_gemm(const GemmArgs& g, const Epi& epi, int splits, cudaStream_t st) {
   dim3 grid(cdiv(g.M, BM), cdiv(g.N, BN), splits);
-  gemm_simt_kernel<A_KC, B_KC, Epi><<<grid, GEMM_THREADS, 0, st>>>(g, epi);
+  launch_k(gemm_simt_kernel<A_KC, B_KC, Epi>, dim3(grid), dim3(GEMM_THREADS), 0, st, g, epi);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

@@ -237,6 +237,7 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
 template <typename T, int BLOCK_N, int EPI, bool FAST, int CL>
 __global__ void __launch_bounds__(RowCfg<(int)sizeof(T), BLOCK_N, EPI>::THREADS, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, RowEpi ea) {
+  pdl_prologue();
   using Cfg = RowCfg<(int)sizeof(T), BLOCK_N, EPI, CL>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int KBLK = TcElem<T>::KBLK;
@@ -914,7 +915,7 @@ static int launch_rows(const T* A, const T* W, int rows, int K, int N, const Row
   }
   if (CL == 1) {
     const int grid = min(num_m * num_n, sm_count());
-    tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1><<<grid, Cfg1::THREADS, Cfg1::SMEM, st>>>(tmA, tmB, rows, N, K, ea);
+    launch_k(tc_rows_kernel<T, BLOCK_N, EPI, FAST, 1>, dim3(grid), dim3(Cfg1::THREADS), Cfg1::SMEM, st, tmA, tmB, rows, N, K, ea);
     ADVMIL_CHECK_LAUNCH();
     return ADVMIL_OK;
   }
@@ -960,6 +961,7 @@ template <typename T, int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA /*dY*/, const __grid_constant__ CUtensorMap tmB /*X*/,
                 int rows, int N1, int N2, int rows_per_split, float* __restrict__ ws) {
+  pdl_prologue();
   using Cfg = WgCfg<T, BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES, KR = Cfg::KR, MNG = Cfg::MNG;
   extern __shared__ uint8_t smem_raw[];
@@ -1089,6 +1091,7 @@ static int weight_scratch(int slot, size_t bytes, cudaStream_t st, void** out) {
 }
 
 __global__ void to_bf16_kernel(const float* __restrict__ in, size_t n, bf16* __restrict__ out) {
+  pdl_prologue();
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) st4(out + i, *reinterpret_cast<const float4*>(in + i));
   else for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i]);
@@ -1102,7 +1105,7 @@ template <>
 int weight_operand<bf16>(const float* W, size_t n, int slot, cudaStream_t st, const bf16** out) {
   void* p = nullptr;
   ADVMIL_TRY(weight_scratch(slot, n * sizeof(bf16), st, &p));
-  to_bf16_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(W, n, (bf16*)p);
+  launch_k(to_bf16_kernel, dim3(cdiv((n + 3) / 4, 256)), dim3(256), 0, st, W, n, (bf16*)p);
   ADVMIL_CHECK_LAUNCH();
   *out = (const bf16*)p;
   return ADVMIL_OK;
@@ -1152,9 +1155,9 @@ int tc_proj_embed_fwd(const void* x, const float* W1, const float* b1, const flo
   void* wp = nullptr;
   ADVMIL_TRY(weight_scratch(WS_LINEAR, (size_t)(h + d) * C * sizeof(bf16), st, &wp));
   bf16* Wt = (bf16*)wp;
-  to_bf16_kernel<<<cdiv(((size_t)h * C + 3) / 4, 256), 256, 0, st>>>(W1, (size_t)h * C, Wt);
+  launch_k(to_bf16_kernel, dim3(cdiv(((size_t)h * C + 3) / 4, 256)), dim3(256), 0, st, W1, (size_t)h * C, Wt);
   ADVMIL_CHECK_LAUNCH();
-  to_bf16_kernel<<<cdiv(((size_t)d * C + 3) / 4, 256), 256, 0, st>>>(Wc, (size_t)d * C, Wt + (size_t)h * C);
+  launch_k(to_bf16_kernel, dim3(cdiv(((size_t)d * C + 3) / 4, 256)), dim3(256), 0, st, Wc, (size_t)d * C, Wt + (size_t)h * C);
   ADVMIL_CHECK_LAUNCH();
   RowEpi ea{};
   ea.out = hout; ea.ldo = h; ea.bias = b1; ea.relu = 1;
@@ -1206,6 +1209,7 @@ int tc_region_embed_fwd(const void* x, const float* Wc, const float* bc, const f
 // of the (small) weight goes to library scratch
 template <typename T>
 __global__ void transpose_kernel(const float* __restrict__ in, int R, int Cc, T* __restrict__ out) {
+  pdl_prologue();
   __shared__ float t[32][33];
   int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8)
@@ -1225,7 +1229,7 @@ static int tc_bwd_data_t(const void* dY, const float* W, int rows, int Ny, int N
                          cudaStream_t st) {
   void* wt = nullptr;
   ADVMIL_TRY(weight_scratch(WS_BWD_T, (size_t)Ny * Nx * sizeof(T), st, &wt));
-  transpose_kernel<T><<<dim3(cdiv(Nx, 32), cdiv(Ny, 32)), dim3(32, 8), 0, st>>>(W, Ny, Nx, (T*)wt);
+  launch_k(transpose_kernel<T>, dim3(dim3(cdiv(Nx, 32), cdiv(Ny, 32))), dim3(dim3(32, 8)), 0, st, W, Ny, Nx, (T*)wt);
   ADVMIL_CHECK_LAUNCH();
   RowEpi ea{};
   ea.out = dX; ea.ldo = Nx; ea.w = ex.w; ea.dz = ex.dz; ea.offsets = ex.offsets; ea.bags = ex.bags;
@@ -1279,7 +1283,7 @@ static int launch_wgrad(const T* dY, const T* X, int rows, int N1, int N2, int r
     attr_set = true;
   }
   dim3 grid(cdiv(N1, TILE_M) * (N2 / BLOCK_N), nsplit);
-  kern<<<grid, 256, Cfg::SMEM, st>>>(tmA, tmB, rows, N1, N2, rows_per_split, ws);
+  launch_k(kern, dim3(grid), dim3(256), Cfg::SMEM, st, tmA, tmB, rows, N1, N2, rows_per_split, ws);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

@@ -9,6 +9,7 @@ namespace advmil {
 // small utilities
 // =============================================================================================
 __global__ void fill_zero_kernel(float* p, size_t n) {
+  pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = 0.f;
@@ -16,12 +17,13 @@ __global__ void fill_zero_kernel(float* p, size_t n) {
 int fill_zero(float* p, size_t n, cudaStream_t st) {
   if (n == 0) return ADVMIL_OK;
   int grid = (int)min((size_t)148 * 8, (n + 255) / 256);
-  fill_zero_kernel<<<grid, 256, 0, st>>>(p, n);
+  launch_k(fill_zero_kernel, dim3(grid), dim3(256), 0, st, p, n);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, size_t n, bf16* __restrict__ out) {
+  pdl_prologue();
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
   for (; i < n; i += stride) {
@@ -38,7 +40,7 @@ int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st) {
   if (n == 0) return ADVMIL_OK;
   ADVMIL_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "cast_f32_to_bf16: pointers must be 16-byte aligned");
   const int grid = (int)min((size_t)148 * 16, (n / 8 + 255) / 256 + 1);
-  cast_bf16_kernel<<<grid, 256, 0, st>>>(in, n, (bf16*)out);
+  launch_k(cast_bf16_kernel, dim3(grid), dim3(256), 0, st, in, n, (bf16*)out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -47,6 +49,7 @@ int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st) {
 // <= 16 loads independent, grid = ceil(ncols / 8) CTAs
 __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restrict__ part, int nparts, int width /*row stride*/,
                                                            int ncols, float* __restrict__ out, int accumulate) {
+  pdl_prologue();
   __shared__ float sm[128][9];
   const int c = blockIdx.x * 8 + threadIdx.x;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restri
 struct ReduceSeg { const float* part; int width; int ncols; float* out; int accumulate; };
 struct ReduceBatch { ReduceSeg s[4]; int first_block[5]; int n; };
 __global__ void __launch_bounds__(1024) reduce_rows_multi_kernel(ReduceBatch rb, int nparts) {
+  pdl_prologue();
   __shared__ float sm[128][9];
   int k = 0;
   while (k + 1 < rb.n && (int)blockIdx.x >= rb.first_block[k + 1]) ++k;
@@ -104,19 +108,20 @@ static int reduce_rows_multi(const ReduceSeg* segs, int n, int nparts, cudaStrea
   int blocks = 0;
   for (int k = 0; k < n; ++k) { rb.s[k] = segs[k]; rb.first_block[k] = blocks; blocks += cdiv(segs[k].ncols, 8); }
   rb.first_block[n] = blocks;
-  reduce_rows_multi_kernel<<<blocks, dim3(8, 128), 0, st>>>(rb, nparts);
+  launch_k(reduce_rows_multi_kernel, dim3(blocks), dim3(dim3(8, 128)), 0, st, rb, nparts);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
-  reduce_rows_kernel<<<cdiv(width, 8), dim3(8, 128), 0, st>>>(part, nparts, width, width, out, accumulate);
+  launch_k(reduce_rows_kernel, dim3(cdiv(width, 8)), dim3(dim3(8, 128)), 0, st, part, nparts, width, width, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, size_t n, float* __restrict__ out,
                                      int accumulate) {
+  pdl_prologue();
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -139,6 +144,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, s
 // out[c][r] (+)= sum_z ws[z][r][c]  (ws slices are [R][Cc]; out is [Cc][R]): split-K reduce of a product computed transposed
 __global__ void splitk_reduce_t_kernel(const float* __restrict__ ws, int splits, int R, int Cc, float* __restrict__ out,
                                        int accumulate) {
+  pdl_prologue();
   __shared__ float t[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -165,19 +171,20 @@ __global__ void splitk_reduce_t_kernel(const float* __restrict__ ws, int splits,
   }
 }
 int splitk_reduce_t(const float* ws, int splits, int R, int Cc, float* out, int accumulate, cudaStream_t st) {
-  splitk_reduce_t_kernel<<<dim3(cdiv(Cc, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(ws, splits, R, Cc, out, accumulate);
+  launch_k(splitk_reduce_t_kernel, dim3(dim3(cdiv(Cc, 32), cdiv(R, 32))), dim3(dim3(32, 8)), 0, st, ws, splits, R, Cc, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st) {
-  splitk_reduce_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(ws, splits, n, out, accumulate);
+  launch_k(splitk_reduce_kernel, dim3(cdiv((n + 3) / 4, 256)), dim3(256), 0, st, ws, splits, n, out, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 template <typename T>
 __global__ void apply_dropout_kernel(const T* __restrict__ src, size_t nvec, int vec_per_row, Drop drop, T* __restrict__ dst) {
+  pdl_prologue();
   constexpr int VEC = VecN<T>::N;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -208,7 +215,7 @@ static int apply_dropout_t(const T* src, int rows, int width, const Drop& drop, 
   const size_t nvec = (size_t)rows * width / VEC;
   if (nvec == 0) return ADVMIL_OK;
   const int grid = (int)min((size_t)148 * 16, (nvec + 255) / 256);
-  apply_dropout_kernel<T><<<grid, 256, 0, st>>>(src, nvec, width / VEC, drop, dst);
+  launch_k(apply_dropout_kernel<T>, dim3(grid), dim3(256), 0, st, src, nvec, width / VEC, drop, dst);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -223,6 +230,7 @@ int apply_dropout(const void* src, int rows, int width, const Drop& drop, void* 
 __global__ void gate_pack_kernel(const float* __restrict__ Wa, const float* __restrict__ ba,
                                  const float* __restrict__ Wb, const float* __restrict__ bb, int L, int D, int abw,
                                  float* __restrict__ Wp, float* __restrict__ bp) {
+  pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n = (size_t)abw * L;
   if (i < n) {
@@ -244,7 +252,7 @@ int gate_pack_weights(const float* Wa, const float* ba, const float* Wb, const f
                       float* bp, cudaStream_t st) {
   int abw = gate_width(D);
   size_t n = (size_t)abw * L;
-  gate_pack_kernel<<<cdiv(n, 256), 256, 0, st>>>(Wa, ba, Wb, bb, L, D, abw, Wp, bp);
+  launch_k(gate_pack_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, Wa, ba, Wb, bb, L, D, abw, Wp, bp);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -252,6 +260,7 @@ int gate_pack_weights(const float* Wa, const float* ba, const float* Wb, const f
 __global__ void gate_unpack_kernel(const float* __restrict__ dWp, const float* __restrict__ dbp, int L, int D,
                                    float* __restrict__ dWa, float* __restrict__ dba, float* __restrict__ dWb,
                                    float* __restrict__ dbb, int accumulate) {
+  pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n = (size_t)D * L;
   if (i < n) {
@@ -270,13 +279,14 @@ __global__ void gate_unpack_kernel(const float* __restrict__ dWp, const float* _
 int gate_unpack_grads(const float* dWp, const float* dbp, int L, int D, float* dWa, float* dba, float* dWb, float* dbb,
                       int accumulate, cudaStream_t st) {
   size_t n = (size_t)D * L;
-  gate_unpack_kernel<<<cdiv(n, 256), 256, 0, st>>>(dWp, dbp, L, D, dWa, dba, dWb, dbb, accumulate);
+  launch_k(gate_unpack_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, dWp, dbp, L, D, dWa, dba, dWb, dbb, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 __global__ void gate_score_finish_kernel(const float* __restrict__ part, int ntiles, int rows,
                                          const float* __restrict__ bc, float* __restrict__ s) {
+  pdl_prologue();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= rows) return;
   float acc = 0.f;
@@ -284,7 +294,7 @@ __global__ void gate_score_finish_kernel(const float* __restrict__ part, int nti
   s[m] = acc + bc[0];
 }
 int gate_score_finish(const float* part, int ntiles, int rows, const float* bc, float* s, cudaStream_t st) {
-  gate_score_finish_kernel<<<cdiv(rows, 256), 256, 0, st>>>(part, ntiles, rows, bc, s);
+  launch_k(gate_score_finish_kernel, dim3(cdiv(rows, 256)), dim3(256), 0, st, part, ntiles, rows, bc, s);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -304,6 +314,7 @@ __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
     const T* __restrict__ v, const int32_t* __restrict__ offsets, int width, int want_mean,
     float* __restrict__ cstats /*[chunk][2] = m_c, l_c*/, float* __restrict__ part /*[offsets[b]/POOL_CH + b + chunk][width]*/,
     float* __restrict__ part_mean) {
+  pdl_prologue();
   constexpr int VEC = VecN<T>::N;
   extern __shared__ float sm[];  // w_s[POOL_CH] + red[RG][width] (+ red_mean)
   __shared__ float redb[33];
@@ -389,6 +400,7 @@ __global__ void __launch_bounds__(256) seg_pool_final_kernel(const float* __rest
                                                              const float* __restrict__ part, const float* __restrict__ part_mean,
                                                              const int32_t* __restrict__ offsets, int width,
                                                              float* __restrict__ w, float* __restrict__ z, float* __restrict__ mean) {
+  pdl_prologue();
   __shared__ float redb[33];
   __shared__ float sm[2][8][33];
   const int b = blockIdx.y, x = blockIdx.x;
@@ -458,10 +470,10 @@ static int seg_softmax_pool_fwd_t(float* s, const float* sparts, int ntiles, con
   else if ((4 * WV) % 32 == 0 && 4 * WV <= 512) threads = 4 * WV;
   int RG = min(threads / WV, POOL_CH);
   size_t smem = (POOL_CH + (size_t)RG * width * (mean ? 2 : 1)) * sizeof(float);
-  seg_pool_partial_kernel<T><<<dim3(maxchunks, bags), threads, smem, st>>>(s, sparts, ntiles, rows, bc, v, offsets, width,
+  launch_k(seg_pool_partial_kernel<T>, dim3(dim3(maxchunks, bags)), dim3(threads), smem, st, s, sparts, ntiles, rows, bc, v, offsets, width,
                                                                         mean ? 1 : 0, cstats, part, part_mean);
   ADVMIL_CHECK_LAUNCH();
-  seg_pool_final_kernel<<<dim3(max(maxchunks, cdiv(width, 32)), bags), 256, 0, st>>>(s, cstats, part, mean ? part_mean : nullptr,
+  launch_k(seg_pool_final_kernel, dim3(dim3(max(maxchunks, cdiv(width, 32)), bags)), dim3(256), 0, st, s, cstats, part, mean ? part_mean : nullptr,
                                                                                      offsets, width, w, z, mean);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
@@ -479,6 +491,7 @@ int seg_softmax_pool_fwd(float* s, const float* sparts, int ntiles, const float*
 //   ds_n = w_n (dz.v_n - dz.z);  du_j = ds wc_j;  da_pre = du b_d sa (1-a^2);  db_pre = du a_d sb b(1-b)
 // =============================================================================================
 __global__ void bag_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int width, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[33];
   int bag = blockIdx.x;
   float acc = 0.f;
@@ -494,6 +507,7 @@ __global__ void __launch_bounds__(256) pool_ds_kernel(const T* __restrict__ v, c
                                                       const float* __restrict__ dz, const float* __restrict__ gz,
                                                       const int32_t* __restrict__ offsets, int rows, int bags, int L,
                                                       float* __restrict__ ds) {
+  pdl_prologue();
   constexpr int VEC = VecN<T>::N;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int sub = lane & 7, slot = lane >> 3;
@@ -547,6 +561,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
     const float* __restrict__ ds_g, const T* __restrict__ ab, const float* __restrict__ wc, int rows, int D, int abw, int RGN,
     Drop da, Drop db, T* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
+  pdl_prologue();
   constexpr int VEC = VecN<T>::N;
   extern __shared__ float red3[];              // [RGN][3][npairs]
   __shared__ float ds_s[ROWS_PER_CTA];
@@ -622,9 +637,9 @@ static int pool_gate_bwd_t(const T* v, const float* w, const float* z, const flo
   float* part = ws + align_up((size_t)bags, 64);
   float* part_b = dbp ? part + align_up((size_t)chunks * (D + 1), 64) : nullptr;
   float* ds = part + align_up((size_t)chunks * (D + 1), 64) + (size_t)chunks * abw;
-  bag_dot_kernel<<<bags, 128, 0, st>>>(dz, z, L, gz);
+  launch_k(bag_dot_kernel, dim3(bags), dim3(128), 0, st, dz, z, L, gz);
   ADVMIL_CHECK_LAUNCH();
-  pool_ds_kernel<T><<<chunks, 256, 0, st>>>(v, w, dz, gz, offsets, rows, bags, L, ds);
+  launch_k(pool_ds_kernel<T>, dim3(chunks), dim3(256), 0, st, v, w, dz, gz, offsets, rows, bags, L, ds);
   ADVMIL_CHECK_LAUNCH();
   const int npairs = abw / 2, TPR = npairs / VEC;
   ADVMIL_REQUIRE(TPR >= 1 && TPR <= 256, "pool_gate_bwd: gate width %d unsupported", abw);
@@ -632,7 +647,7 @@ static int pool_gate_bwd_t(const T* v, const float* w, const float* z, const flo
   const int threads = max(64, ((TPR * RGN + 31) / 32) * 32);
   const size_t smem = (size_t)RGN * 3 * npairs * sizeof(float);
   ADVMIL_REQUIRE(smem <= 48 * 1024, "pool_gate_bwd: gate width %d needs too much shared memory", abw);
-  pool_gate_bwd_kernel<T><<<chunks, threads, smem, st>>>(ds, ab, wc, rows, D, abw, RGN, da, db, dAB, part, part_b);
+  launch_k(pool_gate_bwd_kernel<T>, dim3(chunks), dim3(threads), smem, st, ds, ab, wc, rows, D, abw, RGN, da, db, dAB, part, part_b);
   ADVMIL_CHECK_LAUNCH();
   // dwc | dbc | packed gate-bias gradient (never accumulated: the caller unpacks it with its own accumulate flag)
   ReduceSeg segs[3] = {{part, D + 1, D, dwc, accumulate}, {part + D, D + 1, 1, dbc, accumulate}, {part_b, abw, abw, dbp, 0}};
@@ -656,6 +671,7 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
     const float* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ d_emb2,
     const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int d, float eps, float* __restrict__ d_y,
     float* __restrict__ part /*[chunks][3][d]*/) {
+  pdl_prologue();
   extern __shared__ float sm[];  // [8 warps][3][d]
   int row0 = blockIdx.x * ROWS_PER_CTA;
   int nrows = min(ROWS_PER_CTA, rows - row0);
@@ -734,6 +750,7 @@ __global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
     const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ d_emb2,
     const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y,
     float* __restrict__ part) {
+  pdl_prologue();
   constexpr int VEC = VecN<T>::N, NV = 8 / VEC;           // vectors per lane (2 for fp32, 1 for bf16)
   __shared__ float sm[4 * 3 * 128];
   const int row0 = blockIdx.x * ROWS_PER_CTA;
@@ -852,11 +869,11 @@ int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, cons
   int chunks = row_chunks(rows);
   size_t smem = (size_t)8 * 3 * d * sizeof(float);
   if (d == 128 && dt == ELEM_BF16)
-    ln_pool_bwd128_kernel<bf16><<<chunks, 128, 0, st>>>((const bf16*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (bf16*)d_y, ws);
+    launch_k(ln_pool_bwd128_kernel<bf16>, dim3(chunks), dim3(128), 0, st, (const bf16*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (bf16*)d_y, ws);
   else if (d == 128)
-    ln_pool_bwd128_kernel<float><<<chunks, 128, 0, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (float*)d_y, ws);
-  else if (d <= 128) ln_pool_bwd_kernel<4><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
-  else ln_pool_bwd_kernel<8><<<chunks, 256, smem, st>>>((const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
+    launch_k(ln_pool_bwd128_kernel<float>, dim3(chunks), dim3(128), 0, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (float*)d_y, ws);
+  else if (d <= 128) launch_k(ln_pool_bwd_kernel<4>, dim3(chunks), dim3(256), smem, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
+  else launch_k(ln_pool_bwd_kernel<8>, dim3(chunks), dim3(256), smem, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();
   ReduceSeg segs[3] = {{ws, 3 * d, d, dgamma, accumulate}, {ws + d, 3 * d, d, dbeta, accumulate}, {ws + 2 * d, 3 * d, d, dbias, accumulate}};
   return reduce_rows_multi(segs, 3, chunks, st);
@@ -868,6 +885,7 @@ int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, cons
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ dY, int rows, int N, int ld,
                                                              float* __restrict__ part) {
+  pdl_prologue();
   constexpr int CPT = 4 / (int)sizeof(T);
   int row0 = blockIdx.x * ROWS_PER_CTA;
   int nrows = min(ROWS_PER_CTA, rows - row0);
@@ -902,9 +920,9 @@ int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accu
   int chunks = row_chunks(rows);
   if (dt == ELEM_BF16) {
     ADVMIL_REQUIRE(N % 2 == 0 && ld % 2 == 0, "colsum: bf16 needs even N (%d) and ld (%d)", N, ld);
-    colsum_partial_kernel<bf16><<<chunks, 256, 0, st>>>((const bf16*)dY, rows, N, ld, ws);
+    launch_k(colsum_partial_kernel<bf16>, dim3(chunks), dim3(256), 0, st, (const bf16*)dY, rows, N, ld, ws);
   } else {
-    colsum_partial_kernel<float><<<chunks, 256, 0, st>>>((const float*)dY, rows, N, ld, ws);
+    launch_k(colsum_partial_kernel<float>, dim3(chunks), dim3(256), 0, st, (const float*)dY, rows, N, ld, ws);
   }
   ADVMIL_CHECK_LAUNCH();
   return reduce_rows(ws, chunks, N, out, accumulate, st);

@@ -13,14 +13,17 @@
 namespace advmil {
 
 __global__ void real_mask_kernel(const float* __restrict__ e, const uint8_t* __restrict__ visible, int n, uint8_t* __restrict__ out) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (e[i] == 1.0f && visible[i] != 0) ? 1 : 0;   // model_handler.py:373-375
 }
 __global__ void dup_offsets_kernel(const int32_t* __restrict__ offs, int nb, int rows, int32_t* __restrict__ out) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= nb) { out[i] = offs[i]; out[nb + i] = offs[i] + rows; }
 }
 __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] += b[i];
 }
@@ -204,9 +207,9 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   STEP_TAKE(dws, char, dws_bytes);
   std::vector<int32_t> offs2_host(2 * nb + 1);
   for (int i = 0; i <= nb; ++i) { offs2_host[i] = bags->offsets_host[i]; offs2_host[nb + i] = bags->offsets_host[i] + rows; }
-  dup_offsets_kernel<<<cdiv(nb + 1, 128), 128, 0, st>>>(bags->offsets, nb, rows, offs2);
+  launch_k(dup_offsets_kernel, dim3(cdiv(nb + 1, 128)), dim3(128), 0, st, bags->offsets, nb, rows, offs2);
   ADVMIL_CHECK_LAUNCH();
-  real_mask_kernel<<<cdiv(nb, 128), 128, 0, st>>>(a->e, a->visible, nb, a->real_mask);
+  launch_k(real_mask_kernel, dim3(cdiv(nb, 128)), dim3(128), 0, st, a->e, a->visible, nb, a->real_mask);
   ADVMIL_CHECK_LAUNCH();
   ADVMIL_CHECK_CUDA(cudaMemcpyAsync(t2, a->pred_d, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (batched) {
@@ -270,7 +273,7 @@ extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
   ADVMIL_TRY(advmil_gen_loss(a->pred_g, a->t, a->e, a->visible, a->f_fake_g, nb, a->n_visible, a->n_fake, a->coef_gan,
                              a->recon_alpha, a->recon_gamma, a->recon_norm, a->losses + 1, d_pred, d_fake, stream));
   ADVMIL_TRY(advmil_disc_head_bwd(&dp, bags, &ha, d_fake, nullptr, d_t, nullptr, 0, stream));
-  add_inplace_kernel<<<cdiv(nb, 128), 128, 0, st>>>(d_pred, d_t, nb);
+  launch_k(add_inplace_kernel, dim3(cdiv(nb, 128)), dim3(128), 0, st, d_pred, d_t, nb);
   ADVMIL_CHECK_LAUNCH();
   return advmil_generator_bwd(&gp, bags, &ga, d_pred, a->gen_grads, stream);
 }

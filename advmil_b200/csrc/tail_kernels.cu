@@ -1,6 +1,9 @@
 // Per-bag "tail" kernels (latency-bound: one CTA per bag), losses, fused Adam, DeepAttMISL cluster pooling and the
 // region index map.  All vectors live in shared memory; mat-vecs are warp-per-output-row with coalesced weight reads.
+#include <cooperative_groups.h>
 #include "stages.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace advmil {
 
@@ -86,15 +89,29 @@ __device__ __forceinline__ void block_colmat(const float* __restrict__ W, int ld
 
 // =============================================================================================
 // K4: generator head  (model/backbone.py:73-77,85; model/GANSurv.py:32-49; model/model_utils.py:116-133)
-// grid (bags, samples)
+// One thread-block CLUSTER of HEAD_CS CTAs per (bag, sample): the per-bag chain rho -> MLP0 -> out streams ~0.9 MB of
+// weights through a dependent mat-vec chain, which one CTA can only pull at one SM's L2 bandwidth.  Each CTA of the cluster
+// owns a slice of every layer's output rows and pushes its results into its peers' shared memory (DSMEM).
+// grid (bags * HEAD_CS, samples)
 // =============================================================================================
-__global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, const float* __restrict__ z,
-                                                           const float* __restrict__ noise0,
-                                                           const float* __restrict__ noise1, int bags, Drop drho,
-                                                           Drop dmlp0, float* __restrict__ H, float* __restrict__ H1,
-                                                           float* __restrict__ pre, float* __restrict__ pred) {
+constexpr int HEAD_CS = 8;
+// slice [beg, end) of n outputs owned by cluster rank r (multiples of 4 so that the float4 paths stay 16-byte aligned)
+__device__ __forceinline__ void head_slice(int n, int rank, int& beg, int& end) {
+  const int per = ((n + HEAD_CS - 1) / HEAD_CS + 3) & ~3;
+  beg = min(n, rank * per);
+  end = min(n, beg + per);
+}
+
+__global__ void __launch_bounds__(384) gen_head_fwd_kernel(AdvmilGenParams p, const float* __restrict__ z,
+                                                          const float* __restrict__ noise0,
+                                                          const float* __restrict__ noise1, int bags, Drop drho,
+                                                          Drop dmlp0, float* __restrict__ H, float* __restrict__ H1,
+                                                          float* __restrict__ pre, float* __restrict__ pred) {
+  pdl_prologue();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x, smp = blockIdx.y;
+  const int b = blockIdx.x / HEAD_CS, smp = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int h = p.h, o = p.o, hid = p.hid;
   float* zs = sm;            // [h]
@@ -102,20 +119,23 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
   float* H1s = Hs + 2 * o;   // [2*hid] (H1 | noise1)
   float* red = H1s + 2 * hid;  // [33]
   for (int c = threadIdx.x; c < h; c += blockDim.x) zs[c] = z[(size_t)b * h + c];
-  __syncthreads();
+  cluster.sync();            // zs visible; every CTA of the cluster is running before anyone writes into a peer
   const bool vec_ok = (h % 4 == 0) && (o % 4 == 0) && (hid % 4 == 0);   // 16-byte aligned rows for warp_dot4
   if (p.Wrho) {
+    int ib, ie;
+    head_slice(o, rank, ib, ie);
     if (vec_ok) {
-      for (int i0 = wid * 4; i0 < o; i0 += nw * 4) {
+      for (int i0 = ib + wid * 4; i0 < ie; i0 += nw * 4) {
         float v4[4];
-        warp_dot4(p.Wrho, h, i0, o, zs, h, lane, v4);
-        const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
-        if (lane < 4 && i0 + lane < o) Hs[i0 + lane] = fmaxf(vv + p.brho[i0 + lane], 0.f) * drho.scale(b, i0 + lane);
+        warp_dot4(p.Wrho, h, i0, ie, zs, h, lane, v4);
+        const int u = lane & 3, dst = lane >> 2;             // lane (dst, u) hands output i0 + u to CTA dst
+        const float vv = u == 0 ? v4[0] : u == 1 ? v4[1] : u == 2 ? v4[2] : v4[3];
+        if (i0 + u < ie) cluster.map_shared_rank(Hs, dst)[i0 + u] = fmaxf(vv + p.brho[i0 + u], 0.f) * drho.scale(b, i0 + u);
       }
     } else {
-      for (int i = wid; i < o; i += nw) {
+      for (int i = ib + wid; i < ie; i += nw) {
         float v = warp_dot(p.Wrho + (size_t)i * h, zs, h, lane);
-        if (lane == 0) Hs[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale(b, i);
+        if (lane < HEAD_CS) cluster.map_shared_rank(Hs, lane)[i] = fmaxf(v + p.brho[i], 0.f) * drho.scale(b, i);
       }
     }
   } else {
@@ -125,22 +145,29 @@ __global__ void __launch_bounds__(1024) gen_head_fwd_kernel(AdvmilGenParams p, c
   if (p.noise0)
     for (int c = threadIdx.x; c < o; c += blockDim.x)
       Hs[o + c] = noise0 ? noise0[((size_t)smp * bags + b) * o + c] : 0.f;
-  __syncthreads();
-  if (H && smp == 0) for (int c = threadIdx.x; c < o; c += blockDim.x) H[(size_t)b * o + c] = Hs[c];
+  cluster.sync();            // Hs complete in every CTA
+  if (H && smp == 0 && rank == 0) for (int c = threadIdx.x; c < o; c += blockDim.x) H[(size_t)b * o + c] = Hs[c];
   if (p.W0 == nullptr) return;  // backbone-only mode (ABMIL.forward without the Generator head)
-  if (vec_ok) {
-    for (int j0 = wid * 4; j0 < hid; j0 += nw * 4) {
-      float v4[4];
-      warp_dot4(p.W0, in0, j0, hid, Hs, in0, lane, v4);
-      const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
-      if (lane < 4 && j0 + lane < hid) H1s[j0 + lane] = fmaxf(vv + p.b0[j0 + lane], 0.f) * dmlp0.scale(b, j0 + lane);
-    }
-  } else {
-    for (int j = wid; j < hid; j += nw) {
-      float v = warp_dot(p.W0 + (size_t)j * in0, Hs, in0, lane);
-      if (lane == 0) H1s[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale(b, j);
+  {
+    int jb, je;
+    head_slice(hid, rank, jb, je);
+    float* H1s0 = cluster.map_shared_rank(H1s, 0);           // only rank 0 consumes H1
+    if (vec_ok) {
+      for (int j0 = jb + wid * 4; j0 < je; j0 += nw * 4) {
+        float v4[4];
+        warp_dot4(p.W0, in0, j0, je, Hs, in0, lane, v4);
+        const float vv = lane == 0 ? v4[0] : lane == 1 ? v4[1] : lane == 2 ? v4[2] : v4[3];
+        if (lane < 4 && j0 + lane < je) H1s0[j0 + lane] = fmaxf(vv + p.b0[j0 + lane], 0.f) * dmlp0.scale(b, j0 + lane);
+      }
+    } else {
+      for (int j = jb + wid; j < je; j += nw) {
+        float v = warp_dot(p.W0 + (size_t)j * in0, Hs, in0, lane);
+        if (lane == 0) H1s0[j] = fmaxf(v + p.b0[j], 0.f) * dmlp0.scale(b, j);
+      }
     }
   }
+  cluster.sync();            // H1s complete in rank 0; nobody touches a peer's shared memory after this point
+  if (rank != 0) return;
   const int in1 = hid * (1 + p.noise1);
   if (p.noise1)
     for (int c = threadIdx.x; c < hid; c += blockDim.x)
@@ -166,59 +193,69 @@ int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, 
   ADVMIL_REQUIRE(p.Wrho != nullptr || p.o == p.h, "gen_head: no rho layer requires o == h");
   size_t smem = (size_t)(p.h + 2 * p.o + 2 * p.hid + 40) * sizeof(float);
   ADVMIL_REQUIRE(smem <= 48 * 1024, "gen_head: dims too large for the head kernel (h=%d o=%d)", p.h, p.o);
-  gen_head_fwd_kernel<<<dim3(bags, samples), 1024, smem, st>>>(p, z, noise0, noise1, bags, drho, dmlp0, H, H1, pre, pred);
+  launch_kc(gen_head_fwd_kernel, dim3(bags * HEAD_CS, samples), dim3(384), smem, st, HEAD_CS, p, z, noise0, noise1, bags, drho, dmlp0,
+           H, H1, pre, pred);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
-__global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, const float* __restrict__ d_pred,
+// backward of the head: dz = Wrho^T (relu' (W0[:, :o]^T d1)), one cluster per bag; rank r owns a column slice of each
+// transposed mat-vec (W rows are read as contiguous slices) and pushes its part of dH to every peer.
+__global__ void __launch_bounds__(256) gen_head_bwd_kernel(AdvmilGenParams p, const float* __restrict__ d_pred,
                                                            const float* __restrict__ H, const float* __restrict__ H1,
                                                            const float* __restrict__ pred, float inv_keep_rho,
                                                            float inv_keep_mlp0, float* __restrict__ dz,
                                                            float* __restrict__ dHpre, float* __restrict__ dH1pre,
                                                            float* __restrict__ dpre) {
+  pdl_prologue();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / HEAD_CS;
   const int h = p.h, o = p.o, hid = p.hid;
-  float* d1 = sm;                      // [hid]
-  float* dH = d1 + ((hid + 3) & ~3);   // [o]
+  float* d1 = sm;                        // [hid]
+  float* dH = d1 + ((hid + 3) & ~3);     // [o]      (complete after the exchange)
+  float* loc = dH + ((o + 3) & ~3);      // [slice]  this CTA's part of a transposed mat-vec
+  float* scratch = loc + (((max(o, h) + HEAD_CS - 1) / HEAD_CS + 7) & ~3);   // [4 * blockDim.x] block_colmat partials
   const bool head = p.W0 != nullptr;  // else d_pred is dL/dH [bags,o] (backbone-only mode)
   if (head) {
     float dp = d_pred[b];
     float pr = pred[b];
     if (p.out_scale == 1) dp *= pr * (1.f - pr);
     else if (p.out_scale == 2) dp *= pr;
-    if (threadIdx.x == 0) dpre[b] = dp;
+    if (threadIdx.x == 0 && rank == 0) dpre[b] = dp;
     for (int j = threadIdx.x; j < hid; j += blockDim.x) {
       float hv = H1[(size_t)b * hid + j];
       float g = hv > 0.f ? dp * p.Wl[j] * inv_keep_mlp0 : 0.f;
       d1[j] = g;
-      dH1pre[(size_t)b * hid + j] = g;
+      if (rank == 0) dH1pre[(size_t)b * hid + j] = g;
     }
   }
-  __syncthreads();
+  cluster.sync();            // d1 visible; every CTA of the cluster is running
   const int in0 = o * (1 + p.noise0);
-  float* scratch = dH + o;   // [G][max(o, h)] partials of the transposed mat-vecs
   const bool vec_ok = (o % 4 == 0) && (h % 4 == 0) && (in0 % 4 == 0);
-  if (head && vec_ok) {
-    block_colmat(p.W0, in0, o, d1, hid, scratch, dH);          // dH = W0[:, :o]^T d1
-  } else if (head) {
-    for (int i = threadIdx.x; i < o; i += blockDim.x) dH[i] = col_dot(p.W0, in0, i, d1, hid);
-    __syncthreads();
+  int cb, ce;
+  head_slice(o, rank, cb, ce);
+  if (head && ce > cb) {
+    if (vec_ok) block_colmat(p.W0 + cb, in0, ce - cb, d1, hid, scratch, loc);          // dH[slice] = W0[:, slice]^T d1
+    else { for (int i = cb + threadIdx.x; i < ce; i += blockDim.x) loc[i - cb] = col_dot(p.W0, in0, i, d1, hid); __syncthreads(); }
   }
-  for (int i = threadIdx.x; i < o; i += blockDim.x) {
-    float acc = head ? dH[i] : d_pred[(size_t)b * o + i];
+  for (int i = cb + threadIdx.x; i < ce; i += blockDim.x) {
+    float acc = head ? loc[i - cb] : d_pred[(size_t)b * o + i];
     if (p.Wrho) acc = H[(size_t)b * o + i] > 0.f ? acc * inv_keep_rho : 0.f;
-    dH[i] = acc;
     dHpre[(size_t)b * o + i] = acc;
+#pragma unroll
+    for (int dst = 0; dst < HEAD_CS; ++dst) cluster.map_shared_rank(dH, dst)[i] = acc;
   }
-  __syncthreads();
+  cluster.sync();            // dH complete in every CTA; no peer access after this point
+  int kb, ke;
+  head_slice(h, rank, kb, ke);
+  if (ke <= kb) return;
   if (p.Wrho && vec_ok) {
-    float* dzs = scratch + (size_t)(blockDim.x / (h >> 2) > 0 ? blockDim.x / (h >> 2) : 1) * h;
-    block_colmat(p.Wrho, h, h, dH, o, scratch, dzs);           // dz = Wrho^T dH
-    for (int k = threadIdx.x; k < h; k += blockDim.x) dz[(size_t)b * h + k] = dzs[k];
+    block_colmat(p.Wrho + kb, h, ke - kb, dH, o, scratch, loc);                         // dz[slice] = Wrho[:, slice]^T dH
+    for (int k = kb + threadIdx.x; k < ke; k += blockDim.x) dz[(size_t)b * h + k] = loc[k - kb];
   } else {
-    for (int k = threadIdx.x; k < h; k += blockDim.x)
+    for (int k = kb + threadIdx.x; k < ke; k += blockDim.x)
       dz[(size_t)b * h + k] = p.Wrho ? col_dot(p.Wrho, h, k, dH, o) : dH[k];
   }
 }
@@ -226,11 +263,12 @@ __global__ void __launch_bounds__(512) gen_head_bwd_kernel(AdvmilGenParams p, co
 int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, const float* H1, const float* pred,
                  int bags, float inv_keep_rho, float inv_keep_mlp0, float* dz, float* dHpre, float* dH1pre, float* dpre,
                  cudaStream_t st) {
-  const int wmax = max(p.o, p.h), threads = 512;
-  const int gmax = max(1, threads / (min(p.o, p.h) / 4 > 0 ? min(p.o, p.h) / 4 : 1));
-  size_t smem = ((size_t)(p.hid + p.o) + 16 + (size_t)(gmax + 1) * wmax + 16) * sizeof(float);
+  const int threads = 256;
+  const size_t slice = ((size_t)(max(p.o, p.h) + HEAD_CS - 1) / HEAD_CS + 7) & ~(size_t)3;
+  size_t smem = ((size_t)(p.hid + p.o) + 8 + slice + 4 * (size_t)threads + 16) * sizeof(float);
   ADVMIL_REQUIRE(smem <= 48 * 1024, "gen_head_bwd: dims too large for the head kernel (h=%d o=%d)", p.h, p.o);
-  gen_head_bwd_kernel<<<bags, threads, smem, st>>>(p, d_pred, H, H1, pred, inv_keep_rho, inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
+  launch_kc(gen_head_bwd_kernel, dim3(bags * HEAD_CS), dim3(threads), smem, st, HEAD_CS, p, d_pred, H, H1, pred, inv_keep_rho,
+           inv_keep_mlp0, dz, dHpre, dH1pre, dpre);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -239,6 +277,7 @@ int gen_head_bwd(const AdvmilGenParams& p, const float* d_pred, const float* H, 
 __global__ void outer_sum_kernel(const float* __restrict__ dy, const float* __restrict__ x1, int in1,
                                  const float* __restrict__ x2, int in2, int bags, int out, float* __restrict__ dW,
                                  float* __restrict__ db, int accumulate) {
+  pdl_prologue();
   const int in = in1 + in2;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)out * in) return;
@@ -256,7 +295,7 @@ __global__ void outer_sum_kernel(const float* __restrict__ dy, const float* __re
 int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in2, int bags, int out, float* dW,
               float* db, int accumulate, cudaStream_t st) {
   size_t n = (size_t)out * (in1 + in2);
-  outer_sum_kernel<<<cdiv(n, 256), 256, 0, st>>>(dy, x1, in1, x2, in2, bags, out, dW, db, accumulate);
+  launch_k(outer_sum_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, dy, x1, in1, x2, in2, bags, out, dW, db, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -264,6 +303,7 @@ int outer_sum(const float* dy, const float* x1, int in1, const float* x2, int in
 // several outer-sum problems in one launch (the per-bag head layers of one backward pass)
 struct OuterBatch { OuterProb p[OUTER_MAX]; int first_block[OUTER_MAX + 1]; int n; };
 __global__ void outer_sum_multi_kernel(OuterBatch ob, int bags, int accumulate) {
+  pdl_prologue();
   int k = 0;
   while (k + 1 < ob.n && (int)blockIdx.x >= ob.first_block[k + 1]) ++k;
   const OuterProb q = ob.p[k];
@@ -293,7 +333,7 @@ int outer_sum_multi(const OuterProb* probs, int n, int bags, int accumulate, cud
     blocks += cdiv((size_t)probs[k].out * (probs[k].in1 + probs[k].in2), 256);
   }
   ob.first_block[n] = blocks;
-  outer_sum_multi_kernel<<<blocks, 256, 0, st>>>(ob, bags, accumulate);
+  launch_k(outer_sum_multi_kernel, dim3(blocks), dim3(256), 0, st, ob, bags, accumulate);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -307,6 +347,7 @@ __global__ void __launch_bounds__(512) rlip_tail_fwd_kernel(AdvmilDiscParams p, 
                                                             Drop dfc2, float* __restrict__ g1, float* __restrict__ hx,
                                                             float* __restrict__ u1, float* __restrict__ ht,
                                                             float* __restrict__ out) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -384,7 +425,7 @@ int rlip_tail_fwd(const AdvmilDiscParams& p, const float* bagv, const float* fba
                   const Drop& dfc2, float* g1, float* hx, float* u1, float* ht, float* out, cudaStream_t st) {
   ADVMIL_REQUIRE(p.t2 == p.d, "rlip_tail: time embedding width %d must equal d %d", p.t2, p.d);
   size_t smem = (size_t)(p.d * 2 + p.d / 2 + p.t1 + p.t2 + 40) * sizeof(float);
-  rlip_tail_fwd_kernel<<<bags, 512, smem, st>>>(p, bagv, fbar, t, dfc2, g1, hx, u1, ht, out);
+  launch_k(rlip_tail_fwd_kernel, dim3(bags), dim3(512), smem, st, p, bagv, fbar, t, dfc2, g1, hx, u1, ht, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -395,6 +436,7 @@ __global__ void __launch_bounds__(512) rlip_tail_bwd_kernel(
     const float* __restrict__ ht, float inv_keep_fc2, float* __restrict__ d_fbar, float* __restrict__ d_bagv,
     float* __restrict__ d_hx, float* __restrict__ d_g1pre, float* __restrict__ d_htpre, float* __restrict__ d_u1pre,
     float* __restrict__ d_t) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   const int d = p.d, dh = p.d / 2, t1 = p.t1, t2 = p.t2;
@@ -460,7 +502,7 @@ int rlip_tail_bwd(const AdvmilDiscParams& p, const float* d_out, const float* ba
   // scratch of block_colmat: G * ncols <= threads * 4 floats per call, + one [d] result vector
   size_t smem = (size_t)(p.d + p.d / 2 + p.t2 + p.t1 + 40 + 40 + 2048 + p.d + 16) * sizeof(float);
   ADVMIL_REQUIRE(smem <= 48 * 1024 && p.d <= 2048, "rlip_tail_bwd: d=%d too large", p.d);
-  rlip_tail_bwd_kernel<<<bags, 512, smem, st>>>(p, d_out, bagv, fbar, g1, hx, u1, ht, inv_keep_fc2, d_fbar, d_bagv,
+  launch_k(rlip_tail_bwd_kernel, dim3(bags), dim3(512), smem, st, p, d_out, bagv, fbar, g1, hx, u1, ht, inv_keep_fc2, d_fbar, d_bagv,
                                                  d_hx, d_g1pre, d_htpre, d_u1pre, d_t);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
@@ -472,6 +514,7 @@ int rlip_tail_bwd(const AdvmilDiscParams& p, const float* d_out, const float* ba
 __global__ void disc_loss_kernel(const float* __restrict__ f_real, const float* __restrict__ f_fake,
                                  const uint8_t* __restrict__ real_mask, int bags, int which, float n_real, float n_fake,
                                  float* __restrict__ loss_out, float* __restrict__ d_real, float* __restrict__ d_fake) {
+  pdl_prologue();
   __shared__ float red[33];
   float acc = 0.f;
   for (int b = threadIdx.x; b < bags; b += blockDim.x) {
@@ -516,6 +559,7 @@ __global__ void gen_loss_kernel(const float* __restrict__ pred, const float* __r
                                 const uint8_t* __restrict__ visible, const float* __restrict__ f_fake, int bags,
                                 float n_visible, float n_fake, float coef_gan, float alpha, float gamma, int norm,
                                 float* __restrict__ losses, float* __restrict__ d_pred, float* __restrict__ d_fake) {
+  pdl_prologue();
   __shared__ float red[33];
   float rec = 0.f, gen = 0.f;
   for (int b = threadIdx.x; b < bags; b += blockDim.x) {
@@ -552,6 +596,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, const uint8_t* __restrict__ wd_mask, int64_t n, float step_size,
                             float beta1, float beta2, float eps, float weight_decay, float l1_coef, float inv_sqrt_bc2,
                             float grad_scale) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float pv = p[i];
@@ -565,15 +610,28 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pv - step_size * (mv / denom);
 }
 
-__global__ void abs_sum_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
+// one cluster of ABS_CS CTAs; partial sums meet in rank 0's shared memory and are added in rank order (deterministic,
+// no atomics)
+constexpr int ABS_CS = 8;
+__global__ void __launch_bounds__(1024) abs_sum_kernel(const float* __restrict__ p, int64_t n, float* __restrict__ out) {
+  pdl_prologue();
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[33];
+  __shared__ float parts[ABS_CS];
   float a0 = 0.f, a1 = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + stride < n; i += 2 * stride) { a0 += fabsf(p[i]); a1 += fabsf(p[i + stride]); }
   for (; i < n; i += stride) a0 += fabsf(p[i]);
   float acc = block_sum(a0 + a1, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  cluster.sync();                                     // every CTA of the cluster is running
+  if (threadIdx.x == 0) cluster.map_shared_rank(parts, 0)[cluster.block_rank()] = acc;
+  cluster.sync();
+  if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+    float t = 0.f;
+    for (int r = 0; r < ABS_CS; ++r) t += parts[r];
+    out[0] += t;
+  }
 }
 
 // =============================================================================================
@@ -586,6 +644,7 @@ __global__ void __launch_bounds__(256) seg_mean_id_partial_kernel(const T* __res
                                                                   const int32_t* __restrict__ offsets, int width,
                                                                   int ncl, float* __restrict__ part,
                                                                   int32_t* __restrict__ part_cnt) {
+  pdl_prologue();
   extern __shared__ float sm[];  // [ncl][width] sums
   __shared__ int cnt_s[64];
   __shared__ int cid_s[CL_CH];
@@ -614,6 +673,7 @@ __global__ void __launch_bounds__(256) seg_mean_id_partial_kernel(const T* __res
 __global__ void seg_mean_id_final_kernel(const float* __restrict__ part, const int32_t* __restrict__ part_cnt,
                                          const int32_t* __restrict__ offsets, int width, int ncl,
                                          float* __restrict__ out, int32_t* __restrict__ counts) {
+  pdl_prologue();
   int b = blockIdx.x / ncl, k = blockIdx.x % ncl;
   int len = offsets[b + 1] - offsets[b];
   int nch = (len + CL_CH - 1) / CL_CH;
@@ -632,6 +692,7 @@ __global__ void seg_mean_id_bwd_kernel(const float* __restrict__ d_out, const T*
                                        const int32_t* __restrict__ cid, const int32_t* __restrict__ offsets,
                                        const int32_t* __restrict__ counts, int rows, int bags, int width, int ncl,
                                        int relu_mask, T* __restrict__ d_v) {
+  pdl_prologue();
   int row = blockIdx.x;
   int b = bag_of_row(offsets, bags, row);
   int k = cid[row];
@@ -648,6 +709,7 @@ __global__ void seg_mean_id_bwd_kernel(const float* __restrict__ d_out, const T*
 // region <-> patch index map (tools/big_to_small_patching.py:40-46,59-76)
 // =============================================================================================
 __global__ void region_index_map_kernel(const int64_t* __restrict__ c2, int m, int psize, int scale, double* __restrict__ c1) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int s2 = scale * scale;
   if (i >= m * s2) return;
@@ -657,6 +719,7 @@ __global__ void region_index_map_kernel(const int64_t* __restrict__ c2, int m, i
   c1[2 * (size_t)i + 1] = (double)c2[2 * (size_t)k + 1] + (double)(jj * psize);
 }
 __global__ void region_of_rows_kernel(int rows, int scale, int32_t* __restrict__ out) {
+  pdl_prologue();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= rows) return;
   int s2 = scale * scale;
@@ -677,7 +740,7 @@ extern "C" int advmil_disc_loss(const float* f_real, const float* f_fake, const 
                                 void* stream) {
   ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   ADVMIL_REQUIRE(bags > 0 && which >= 0 && which <= 2 && n_fake > 0.f, "disc_loss: bad arguments");
-  disc_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(f_real, f_fake, real_mask, bags, which, n_real, n_fake, loss_out, d_real, d_fake);
+  launch_k(disc_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, f_real, f_fake, real_mask, bags, which, n_real, n_fake, loss_out, d_real, d_fake);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -688,7 +751,7 @@ extern "C" int advmil_gen_loss(const float* pred, const float* t, const float* e
                                void* stream) {
   ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   ADVMIL_REQUIRE(bags > 0 && n_fake > 0.f && (norm == 0 || norm == 1), "gen_loss: bad arguments");
-  gen_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, t, e, visible, f_fake, bags, n_visible, n_fake, coef_gan, alpha, gamma, norm, losses, d_pred, d_fake);
+  launch_k(gen_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, pred, t, e, visible, f_fake, bags, n_visible, n_fake, coef_gan, alpha, gamma, norm, losses, d_pred, d_fake);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -701,7 +764,7 @@ extern "C" int advmil_adam_step(float* param, const float* grad, float* m, float
   if (n == 0) return ADVMIL_OK;
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, wd_mask, n, (float)(lr / bc1), beta1,
+  launch_k(adam_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, param, grad, m, v, wd_mask, n, (float)(lr / bc1), beta1,
                                                                 beta2, eps, weight_decay, l1_coef,
                                                                 (float)(1.0 / sqrt(bc2)), grad_scale);
   ADVMIL_CHECK_LAUNCH();
@@ -711,7 +774,7 @@ extern "C" int advmil_adam_step(float* param, const float* grad, float* m, float
 extern "C" int advmil_abs_sum(const float* p, int64_t n, float* out, void* stream) {
   ProfScope ps_(PROF_LOSS_OPT, (cudaStream_t)stream);
   if (n <= 0) return ADVMIL_OK;
-  abs_sum_kernel<<<(int)min((int64_t)148, (n + 2047) / 2048), 256, 0, (cudaStream_t)stream>>>(p, n, out);
+  launch_kc(abs_sum_kernel, dim3(ABS_CS), dim3(1024), 0, (cudaStream_t)stream, ABS_CS, p, n, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -742,11 +805,11 @@ extern "C" int advmil_segment_mean_by_id_fwd(const void* v, int32_t elem, const 
     ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(seg_mean_id_partial_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   if (elem == ELEM_BF16)
-    seg_mean_id_partial_kernel<bf16><<<dim3(maxchunks, bags), 256, smem, st>>>((const bf16*)v, cid, offsets, width, num_clusters, part, part_cnt);
+    launch_k(seg_mean_id_partial_kernel<bf16>, dim3(dim3(maxchunks, bags)), dim3(256), smem, st, (const bf16*)v, cid, offsets, width, num_clusters, part, part_cnt);
   else
-    seg_mean_id_partial_kernel<float><<<dim3(maxchunks, bags), 256, smem, st>>>((const float*)v, cid, offsets, width, num_clusters, part, part_cnt);
+    launch_k(seg_mean_id_partial_kernel<float>, dim3(dim3(maxchunks, bags)), dim3(256), smem, st, (const float*)v, cid, offsets, width, num_clusters, part, part_cnt);
   ADVMIL_CHECK_LAUNCH();
-  seg_mean_id_final_kernel<<<bags * num_clusters, 128, 0, st>>>(part, part_cnt, offsets, width, num_clusters, out, counts);
+  launch_k(seg_mean_id_final_kernel, dim3(bags * num_clusters), dim3(128), 0, st, part, part_cnt, offsets, width, num_clusters, out, counts);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -757,14 +820,15 @@ extern "C" int advmil_segment_mean_by_id_bwd(const float* d_out, const void* v, 
                                              void* stream) {
   if (rows == 0) return ADVMIL_OK;
   if (elem == ELEM_BF16)
-    seg_mean_id_bwd_kernel<bf16><<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, (const bf16*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (bf16*)d_v);
+    launch_k(seg_mean_id_bwd_kernel<bf16>, dim3(rows), dim3(128), 0, (cudaStream_t)stream, d_out, (const bf16*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (bf16*)d_v);
   else
-    seg_mean_id_bwd_kernel<float><<<rows, 128, 0, (cudaStream_t)stream>>>(d_out, (const float*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (float*)d_v);
+    launch_k(seg_mean_id_bwd_kernel<float>, dim3(rows), dim3(128), 0, (cudaStream_t)stream, d_out, (const float*)v, cid, offsets, counts, rows, bags, width, num_clusters, relu_mask, (float*)d_v);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 __global__ void dropout_mask_kernel(Drop d, Drop d2, int role, int rows, int width, uint8_t* __restrict__ out) {
+  pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * width) return;
   const uint32_t row = (uint32_t)(i / width), col = (uint32_t)(i % width);
@@ -781,7 +845,7 @@ extern "C" int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t
   Drop d2 = Drop::make(nullptr, seed, gate_b ? site : site + 1, p, 1, width);
   const size_t n = (size_t)rows * width;
   if (n == 0) return ADVMIL_OK;
-  dropout_mask_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(d, d2, role, rows, width, out);
+  launch_k(dropout_mask_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, d, d2, role, rows, width, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -792,6 +856,7 @@ extern "C" int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t
 __global__ void __launch_bounds__(256) cindex_kernel(const float* __restrict__ t, const float* __restrict__ e,
                                                      const float* __restrict__ pred, int n, float tol,
                                                      unsigned long long* __restrict__ counts) {
+  pdl_prologue();
   __shared__ unsigned long long sm[3][8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long con = 0, tie = 0, cmp = 0;
@@ -825,7 +890,7 @@ extern "C" int advmil_cindex_counts(const float* t, const float* e, const float*
   ADVMIL_REQUIRE(t && e && pred && counts && n >= 2, "cindex_counts: need at least two samples (eval/cindex.py:72-73)");
   cudaStream_t st = (cudaStream_t)stream;
   ADVMIL_CHECK_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), st));
-  cindex_kernel<<<cdiv(n, 256), 256, 0, st>>>(t, e, pred, n, tied_tol, (unsigned long long*)counts);
+  launch_k(cindex_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, t, e, pred, n, tied_tol, (unsigned long long*)counts);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
@@ -834,14 +899,14 @@ extern "C" int advmil_region_index_map(const int64_t* coords_l2, int32_t m, int3
                                        double* coords_l1, void* stream) {
   ADVMIL_REQUIRE(m >= 0 && scale > 0, "region_index_map: bad arguments");
   if (m == 0) return ADVMIL_OK;
-  region_index_map_kernel<<<cdiv((long long)m * scale * scale, 256), 256, 0, (cudaStream_t)stream>>>(coords_l2, m, patch_size, scale, coords_l1);
+  launch_k(region_index_map_kernel, dim3(cdiv((long long)m * scale * scale, 256)), dim3(256), 0, (cudaStream_t)stream, coords_l2, m, patch_size, scale, coords_l1);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
 
 extern "C" int advmil_region_of_rows(int32_t rows, int32_t scale, int32_t* out, void* stream) {
   if (rows == 0) return ADVMIL_OK;
-  region_of_rows_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(rows, scale, out);
+  launch_k(region_of_rows_kernel, dim3(cdiv(rows, 256)), dim3(256), 0, (cudaStream_t)stream, rows, scale, out);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }
