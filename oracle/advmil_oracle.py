@@ -157,6 +157,62 @@ def deepattmisl_forward(sd: SD, x: Tensor, cluster_id: Tensor, num_clusters: int
     return {"hc": hc, "g": g, "s": s.squeeze(-1), "w": w.squeeze(0), "H": H}
 
 
+def posemb_sincos_2d(y: Tensor, x: Tensor, dim: int, temperature: float = 10000.0) -> Tensor:
+    """model/backbone_utils.py:79-88: [x.sin | x.cos | y.sin | y.cos] with dim/4 frequencies each."""
+    assert dim % 4 == 0
+    omega = torch.arange(dim // 4) / (dim // 4 - 1)
+    omega = 1.0 / (temperature ** omega)
+    yy = y.flatten()[:, None] * omega[None, :]
+    xx = x.flatten()[:, None] * omega[None, :]
+    return torch.cat((xx.sin(), xx.cos(), yy.sin(), yy.cos()), dim=1)
+
+
+def compute_pe(coord: Tensor, ndim: int = 384, step: int = 1) -> Tensor:
+    """model/backbone_utils.py:90-99 (+ to_relative_coord): coord [R,2] of the level-2 regions (after discretisation) ->
+    PE [R, ndim] of the coordinates relative to their minimum."""
+    ref_xy, _ = torch.min(coord, dim=-2)
+    ncoord = coord - ref_xy
+    y = torch.div(ncoord[:, 1], step, rounding_mode="floor")
+    x = torch.div(ncoord[:, 0], step, rounding_mode="floor")
+    return posemb_sincos_2d(y, x, ndim).to(torch.float32)
+
+
+def encoder_layer(sd: SD, v: Tensor, prefix: str, nhead: int = 8, masks=None, p: float = 0.25, eps: float = 1e-5) -> Dict[str, Tensor]:
+    """nn.TransformerEncoderLayer(d, nhead, dim_feedforward=d, dropout=p, activation='relu', batch_first=True) as built by
+    make_transformer_layer (model/backbone_utils.py:112-127), post-norm: x1 = norm1(x + drop1(SA(x)));
+    x2 = norm2(x1 + drop2(linear2(drop(relu(linear1(x1)))))).  SA = nn.MultiheadAttention: packed in_proj, scaled dot
+    product (1/sqrt(d/nhead)), softmax over keys, dropout on the probabilities, out_proj.  v: [R, d] (one bag).
+    masks: 'attn' [nhead,R,R], 'sa' [R,d], 'ff1' [R,d], 'ff2' [R,d]."""
+    masks = masks or {}
+    R, d = v.shape
+    hd = d // nhead
+    qkv = F.linear(v, sd[prefix + ".self_attn.in_proj_weight"], sd[prefix + ".self_attn.in_proj_bias"])
+    q, k, val = [t.reshape(R, nhead, hd).transpose(0, 1) for t in qkv.split(d, dim=1)]       # [nhead, R, hd]
+    scores = (q @ k.transpose(1, 2)) / math.sqrt(hd)
+    P = _drop(torch.softmax(scores, dim=-1), masks.get("attn"), p)
+    ctx = (P @ val).transpose(0, 1).reshape(R, d)
+    sa = _drop(_lin(ctx, sd, prefix + ".self_attn.out_proj"), masks.get("sa"), p)
+    x1 = F.layer_norm(v + sa, (d,), sd[prefix + ".norm1.weight"], sd[prefix + ".norm1.bias"], eps)
+    f = _drop(torch.relu(_lin(x1, sd, prefix + ".linear1")), masks.get("ff1"), p)
+    f2 = _drop(_lin(f, sd, prefix + ".linear2"), masks.get("ff2"), p)
+    x2 = F.layer_norm(x1 + f2, (d,), sd[prefix + ".norm2.weight"], sd[prefix + ".norm2.bias"], eps)
+    return {"ctx": ctx, "x1": x1, "x2": x2}
+
+
+def esat_forward(sd: SD, x: Tensor, coord: Optional[Tensor] = None, masks=None, p: float = 0.25, nhead: int = 8,
+                 prefix: str = "backbone") -> Dict[str, Tensor]:
+    """DualTrans_HS.forward (model/backbone.py:189-196) with the defaults of load_backbone_param('patch')
+    (:31-35): AVGPoolPatchEmbedding(1024 -> d, scale 4, ksize 1) -> (+ PE) -> 1 TransformerEncoderLayer(d, 8 heads,
+    ffn d, dropout 0.25) -> GAPool(d, d).  x: [N, C], N % 16 == 0; coord: [R, 2] or None.
+    masks (train mode): 'attn', 'sa', 'ff1', 'ff2' (encoder layer), 'ga', 'gs' (GAPool)."""
+    emb = region_embed(sd, x, prefix + ".patch_embedding_layer")["emb"]                      # backbone.py:191
+    if coord is not None:
+        emb = emb + compute_pe(coord, emb.shape[1]).to(emb.dtype)                            # backbone.py:192-194
+    enc = encoder_layer(sd, emb, prefix + ".patch_encoder_layer.layers.0", nhead, masks, p)  # backbone.py:195
+    gp = gapool(sd, enc["x2"], prefix + ".pool", masks, p)                                   # backbone.py:196
+    return {"emb": emb, "x1": enc["x1"], "x2": enc["x2"], "attn": gp["attn"], "H": gp["out"]}
+
+
 def generator_head(sd: SD, H: Tensor, noises: Sequence[Optional[Tensor]], noise_cfg: Sequence[int],
                    masks=None, p: float = 0.6, out_scale: str = "sigmoid") -> Tensor:
     """Noise-concat MLP head: Generator.forward (model/GANSurv.py:32-49) over the layers built by
@@ -179,11 +235,13 @@ def generator_head(sd: SD, H: Tensor, noises: Sequence[Optional[Tensor]], noise_
 
 def generator_forward(sd: SD, x: Tensor, noises, noise_cfg=(0, 1), masks=None, backbone: str = "abmil",
                       cluster_id: Optional[Tensor] = None, gen_dropout: float = 0.6,
-                      out_scale: str = "sigmoid") -> Dict[str, Tensor]:
+                      out_scale: str = "sigmoid", coord: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Generator.forward (model/GANSurv.py:30-49). `noises[i]` is the tensor generate_noise would have
     produced for layer i (utils/func.py:154-164 == torch.rand / torch.randn on the CPU stream)."""
     if backbone == "cluster":
         bb = deepattmisl_forward(sd, x, cluster_id, masks=masks)
+    elif backbone == "patch":
+        bb = esat_forward(sd, x, coord, masks=masks)
     else:
         bb = abmil_forward(sd, x, masks=masks)
     pred = generator_head(sd, bb["H"], noises, noise_cfg, masks, gen_dropout, out_scale)
@@ -487,6 +545,22 @@ G_CLUSTER_SHAPES = lambda C=1024, h=384: {  # noqa: E731  DeepAttMISL generator
     "backbone.attention_net.3.attention_c.weight": (1, h), "backbone.attention_net.3.attention_c.bias": (1,),
 }
 
+def G_ESAT_SHAPES(C=1024, d=384):
+    """State dict of Generator(backbone=DualTrans_HS) as printed from the reference modules (load_backbone('patch'))."""
+    L = "backbone.patch_encoder_layer.layers.0."
+    sh = {"MLPs.0.0.weight": (d // 2, d), "MLPs.0.0.bias": (d // 2,), "MLPs.1.0.weight": (1, d), "MLPs.1.0.bias": (1,),
+          "backbone.patch_embedding_layer.conv.weight": (d, C, 1, 1), "backbone.patch_embedding_layer.conv.bias": (d,),
+          "backbone.patch_embedding_layer.norm.weight": (d,), "backbone.patch_embedding_layer.norm.bias": (d,),
+          L + "self_attn.in_proj_weight": (3 * d, d), L + "self_attn.in_proj_bias": (3 * d,),
+          L + "self_attn.out_proj.weight": (d, d), L + "self_attn.out_proj.bias": (d,),
+          L + "linear1.weight": (d, d), L + "linear1.bias": (d,), L + "linear2.weight": (d, d), L + "linear2.bias": (d,),
+          L + "norm1.weight": (d,), L + "norm1.bias": (d,), L + "norm2.weight": (d,), L + "norm2.bias": (d,),
+          "backbone.pool.fc1.0.weight": (d, d), "backbone.pool.fc1.0.bias": (d,),
+          "backbone.pool.score.0.weight": (d, d), "backbone.pool.score.0.bias": (d,),
+          "backbone.pool.fc2.weight": (1, d), "backbone.pool.fc2.bias": (1,)}
+    return sh
+
+
 def DCAT_SHAPES(C=1024, d=128, ty=(64, 128)):
     """State dict of the concat Discriminator (model/GANSurv.py:52-60): PrjDiscriminator's minus prj_layer, plus fc."""
     sh = {k: v for k, v in D_SHAPES(C, d, ty).items() if not k.startswith("prj_layer")}
@@ -523,7 +597,7 @@ def synth_state_dict(shapes: Dict[str, tuple], seed: int, dtype=torch.float32) -
         else:
             b = 0.1
         v = rng.uniform(-b, b, size=shp)
-        if name.endswith("norm.weight"):
+        if name.endswith(("norm.weight", "norm1.weight", "norm2.weight")):
             v = v + 1.0
         sd[name] = torch.tensor(v, dtype=dtype)
     return sd

@@ -293,6 +293,80 @@ def case_cluster(ref, name, dims, N, seed, empty_cluster):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def esat_masks(R, d, seed, nhead=8):
+    return {"attn": O.synth_masks((nhead, R, R), 0.75, seed), "sa": O.synth_masks((R, d), 0.75, seed + 1),
+            "ff1": O.synth_masks((R, d), 0.75, seed + 2), "ff2": O.synth_masks((R, d), 0.75, seed + 3),
+            "ga": O.synth_masks((R, d), 0.75, seed + 4), "gs": O.synth_masks((R, d), 0.75, seed + 5),
+            "mlp0": O.synth_masks((1, d // 2), 0.4, seed + 6)}
+
+
+def case_esat(ref, name, C, d, N, train, seed, with_coord):
+    """Generator(backbone=DualTrans_HS) as load_backbone('patch') builds it (model/backbone.py:31-35,171-196).  Train
+    mode: the nn.Dropout instances are swapped for fixed-mask modules; the dropout on the attention probabilities lives
+    inside torch's own MultiheadAttention code, so the layer's self_attn is called with need_weights=True (torch's math
+    path, same arithmetic) and torch.nn.functional.dropout is patched for the [nhead, R, R] tensor only."""
+    import torch.nn.functional as F
+    G = build_ref_G(ref, (C, d, d), mode="patch")
+    sd = O.synth_state_dict(O.G_ESAT_SHAPES(C, d), seed)
+    G.load_state_dict(sd)
+    x = O.synth_bag(N, seed, C)
+    R = N // 16
+    noise = torch.tensor(np.random.default_rng(seed + 7).uniform(size=(1, d // 2)), dtype=torch.float32)
+    coord = torch.tensor(np.random.default_rng(seed + 8).integers(0, 60, size=(R, 2)), dtype=torch.int64) if with_coord else None
+    layer = G.backbone.patch_encoder_layer.layers[0]
+    drops = {}
+    layer.dropout1 = drops["sa"] = FixedDropout(0.25)
+    layer.dropout = drops["ff1"] = FixedDropout(0.25)
+    layer.dropout2 = drops["ff2"] = FixedDropout(0.25)
+    G.backbone.pool.fc1[2] = drops["ga"] = FixedDropout(0.25)
+    G.backbone.pool.score[2] = drops["gs"] = FixedDropout(0.25)
+    G.MLPs[0][2] = drops["mlp0"] = FixedDropout(G.MLPs[0][2].p)
+    masks = None
+    orig_dropout, orig_sa = F.dropout, layer.self_attn.forward
+    if train:
+        G.train()
+        masks = esat_masks(R, d, seed * 10)
+        for k, m in drops.items():
+            m.mask = masks[k]
+        layer.self_attn.forward = lambda *a, **k: orig_sa(*a, **{**k, "need_weights": True})
+
+        def fixed_dropout(inp, p=0.5, training=True, inplace=False):
+            if training and tuple(inp.shape) == tuple(masks["attn"].shape):
+                return inp * masks["attn"].to(inp.dtype) / (1.0 - p)
+            return orig_dropout(inp, p, training, inplace)
+        F.dropout = fixed_dropout
+    else:
+        G.eval()
+    inter = {}
+    G.backbone.patch_embedding_layer.register_forward_hook(lambda m, i, out: inter.__setitem__("emb", out))
+    G.backbone.patch_encoder_layer.register_forward_hook(lambda m, i, out: inter.__setitem__("x2", out))
+    G.backbone.register_forward_hook(lambda m, i, out: inter.__setitem__("H", out))
+    orig = ref.GANSurv.generate_noise
+    ref.GANSurv.generate_noise = lambda *dims, to_device="cpu", distribution="uniform": noise.clone()
+    try:
+        pred = G(x.unsqueeze(0), None if coord is None else coord.unsqueeze(0))
+    finally:
+        ref.GANSurv.generate_noise = orig
+        F.dropout = orig_dropout
+    G.zero_grad()
+    pred.sum().backward()
+    out = {"pred": pred.detach().double().numpy(), "H": inter["H"].detach().double().numpy(), "emb": sub(inter["emb"]),
+           "x2": sub(inter["x2"]), "cfg": np.array([C, d, N, int(train), seed, int(with_coord)])}
+    if coord is not None:
+        out["coord"] = coord.numpy()
+    for k, p in G.named_parameters():
+        out["grad." + k] = sub(p.grad)
+        out["gsum." + k] = np.array(p.grad.double().sum().item())
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    og = O.generator_forward(sdr, x, [None, noise], (0, 1), masks, backbone="patch", coord=coord)
+    og["pred"].sum().backward()
+    err = float((og["pred"].detach() - pred.detach()).abs().max())
+    gerr = max(float((sdr[k].grad - p.grad).abs().max() / (p.grad.abs().max() + 1e-3)) for k, p in G.named_parameters())
+    print(f"[golden] {name}: pred {pred.item():.8f} oracle|d|={err:.2e} grad rel err={gerr:.2e}")
+    assert err < 1e-6 and gerr < 1e-4
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def case_step(ref, name, dims, d, Ns, seed, n_steps=2):
     """Full adversarial step(s) with the reference modules, losses and optimisers, restating the loop of
     model_handler.py:349-498 around them (the handler itself hard-codes .cuda() and wandb)."""
@@ -461,6 +535,10 @@ def main():
     case_step(ref, "step_small", small, 32, [96, 160, 48, 208], 11)
     case_step(ref, "step_full", full, 128, [320, 640, 160], 12, n_steps=1)
     case_misc(ref)
+    case_esat(ref, "g_esat_eval_full", 1024, 384, 1600, False, 15, True)
+    case_esat(ref, "g_esat_train_full", 1024, 384, 640, True, 16, False)
+    case_esat(ref, "g_esat_train_small", 64, 32, 208, True, 17, True)
+    case_esat(ref, "g_esat_eval_small", 64, 32, 96, False, 18, False)
 
 
 if __name__ == "__main__":

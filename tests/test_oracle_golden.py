@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import advmil_oracle as O
-from tests.util import d_masks, g_masks, golden, sub
+from tests.util import d_masks, esat_masks, g_masks, golden, sub
 
 
 def _grads_match(sdr, g, prefix="grad."):
@@ -146,3 +146,23 @@ def test_misc_fixtures():
     assert abs(float(O.recon_loss(p_, t_, e_, 0.3, 0.1, "l2")) - float(g["recon_l2"])) < 1e-7
     kept = g["mask_bag_rows_kept"].reshape(10, 16)
     assert np.all(kept.all(axis=1) | (~kept).all(axis=1)) and kept.any()   # whole 16-row regions kept or zeroed
+
+
+@pytest.mark.parametrize("name", ["g_esat_eval_full", "g_esat_train_full", "g_esat_train_small", "g_esat_eval_small"])
+def test_esat_generator_oracle_vs_reference(name):
+    """Generator over DualTrans_HS / ESAT (bcb_mode 'patch', model/backbone.py:171-196): region embedding, sincos PE,
+    one post-norm TransformerEncoderLayer (attention-probability dropout included), GAPool, noise head."""
+    g = golden(name)
+    C, d, N, train, seed, with_coord = [int(v) for v in g["cfg"]]
+    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(O.G_ESAT_SHAPES(C, d), seed).items()}
+    x = O.synth_bag(N, seed, C)
+    noise = torch.tensor(np.random.default_rng(seed + 7).uniform(size=(1, d // 2)), dtype=torch.float32)
+    coord = torch.tensor(g["coord"]) if with_coord else None
+    masks = esat_masks(N // 16, d, seed * 10) if train else None
+    out = O.generator_forward(sd, x, [None, noise], (0, 1), masks, backbone="patch", coord=coord)
+    out["pred"].sum().backward()
+    assert float(np.abs(out["pred"].detach().numpy() - g["pred"]).max()) < 1e-6
+    assert float(np.abs(out["H"].detach().numpy() - g["H"]).max()) < 1e-5
+    assert float(np.abs(sub(out["emb"]) - g["emb"]).max()) < 1e-5
+    assert float(np.abs(sub(out["x2"]) - g["x2"]).max()) < 1e-5
+    _grads_match(sd, g)

@@ -46,6 +46,13 @@ def d_masks(R, d, seed):
             "gs": O.synth_masks((R, d), 0.75, seed + 2), "fc2": O.synth_masks((1, d // 2), 0.75, seed + 3)}
 
 
+def esat_masks(R, d, seed, nhead=8):
+    return {"attn": O.synth_masks((nhead, R, R), 0.75, seed), "sa": O.synth_masks((R, d), 0.75, seed + 1),
+            "ff1": O.synth_masks((R, d), 0.75, seed + 2), "ff2": O.synth_masks((R, d), 0.75, seed + 3),
+            "ga": O.synth_masks((R, d), 0.75, seed + 4), "gs": O.synth_masks((R, d), 0.75, seed + 5),
+            "mlp0": O.synth_masks((1, d // 2), 0.4, seed + 6)}
+
+
 def to_dev_masks(m, device="cuda"):
     return {k: v.to(torch.uint8).contiguous().to(device) for k, v in m.items()}
 
