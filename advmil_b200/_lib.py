@@ -83,7 +83,32 @@ class StepArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
-ABI_STRUCTS = [Bags, GenParams, GenGrads, GenActs, DiscParams, DiscGrads, EmbedActs, HeadActs, StepArgs]
+ESAT_TENSORS = ["Wc", "bc", "ln_g", "ln_b", "Win", "bin", "Wout", "bout", "W1", "b1", "W2", "b2", "n1_g", "n1_b", "n2_g", "n2_b",
+                "Pa_w", "Pa_b", "Ps_w", "Ps_b", "Pc_w", "Pc_b"]
+
+
+class EsatParams(C.Structure):
+    _fields_ = [(n, c_fp) for n in ESAT_TENSORS] + [
+        ("C", C.c_int32), ("d", C.c_int32), ("ff", C.c_int32), ("nhead", C.c_int32), ("p", C.c_float), ("ln_eps", C.c_float)]
+
+
+class EsatGrads(C.Structure):
+    _fields_ = [(n, c_fp) for n in ESAT_TENSORS]
+
+
+ESAT_ACTS = ["y_pre", "emb", "qkv", "lse", "ctx", "s1", "x1", "f", "s2", "x2", "ab", "rep", "attn", "H", "H1", "pre", "pred"]
+
+
+class EsatActs(C.Structure):
+    _fields_ = [(n, c_fp) for n in ESAT_ACTS] + [
+        ("pe", c_fp), ("noise0", c_fp), ("noise1", c_fp), ("mask_attn", c_u8p), ("mask_attn_off", C.c_void_p),
+        ("mask_sa", c_u8p), ("mask_ff1", c_u8p), ("mask_ff2", c_u8p), ("mask_ga", c_u8p), ("mask_gs", c_u8p), ("mask_mlp0", c_u8p),
+        ("seed", C.c_uint64), ("train", C.c_int32), ("precision", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+ABI_STRUCTS = [Bags, GenParams, GenGrads, GenActs, DiscParams, DiscGrads, EmbedActs, HeadActs, StepArgs, EsatParams, EsatGrads,
+               EsatActs]
 
 # every symbol include/advmil_b200.h declares: name -> (restype, argtypes)
 _i32, _i64, _f, _vp, _sz, _u64 = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t, C.c_uint64
@@ -127,6 +152,10 @@ SYMBOLS = {
     "advmil_gen_loss": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _f, _i32, _vp, _vp, _vp, _vp]),
     "advmil_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _i32, _f, _vp]),
     "advmil_abs_sum": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "advmil_esat_workspace_bytes": (_sz, [_P(EsatParams), _P(GenParams), _i32, _i32, _i32]),
+    "advmil_esat_fwd": (C.c_int, [_P(EsatParams), _P(GenParams), _P(Bags), _P(EsatActs), _vp]),
+    "advmil_esat_bwd": (C.c_int, [_P(EsatParams), _P(GenParams), _P(Bags), _P(EsatActs), _vp, _P(EsatGrads), _P(GenGrads), _vp]),
+    "advmil_sincos_pe": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
 }
 
 PROF_TAGS = ["proj_fwd", "gate_fwd", "pool_fwd", "embed_fwd", "pool_gate_bwd", "bwd_data", "bwd_w_gate", "bwd_w_proj",
@@ -152,7 +181,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.advmil_abi_version() != 2:
+    if lib.advmil_abi_version() != 3:
         raise AdvmilError("libadvmil_b200.so ABI version mismatch")
     for i, st in enumerate(ABI_STRUCTS):
         if lib.advmil_abi_sizeof(i) != C.sizeof(st):

@@ -87,6 +87,9 @@ extern "C" size_t advmil_abi_sizeof(int which) {
     case 6: return sizeof(AdvmilEmbedActs);
     case 7: return sizeof(AdvmilHeadActs);
     case 8: return sizeof(AdvmilStepArgs);
+    case 9: return sizeof(AdvmilEsatParams);
+    case 10: return sizeof(AdvmilEsatGrads);
+    case 11: return sizeof(AdvmilEsatActs);
     default: return 0;
   }
 }

@@ -133,6 +133,7 @@ struct Workspace {
 enum DropSite : int {
   SITE_H = 1, SITE_A = 2, SITE_B = 3, SITE_RHO = 4, SITE_MLP0 = 5,           // generator
   SITE_FC1 = 11, SITE_GA = 12, SITE_GS = 13, SITE_FC2 = 14,                   // discriminator
+  SITE_ATT = 21, SITE_SA = 22, SITE_FF1 = 23, SITE_FF2 = 24,                  // ESAT encoder layer
   SITE_USER = 100
 };
 

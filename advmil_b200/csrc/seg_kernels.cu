@@ -113,6 +113,11 @@ static int reduce_rows_multi(const ReduceSeg* segs, int n, int nparts, cudaStrea
   return ADVMIL_OK;
 }
 
+int reduce_rows_strided(const float* part, int nparts, int stride, int ncols, float* out, int accumulate, cudaStream_t st) {
+  launch_k(reduce_rows_kernel, dim3(cdiv(ncols, 8)), dim3(dim3(8, 128)), 0, st, part, nparts, stride, ncols, out, accumulate);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
 int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st) {
   launch_k(reduce_rows_kernel, dim3(cdiv(width, 8)), dim3(dim3(8, 128)), 0, st, part, nparts, width, width, out, accumulate);
   ADVMIL_CHECK_LAUNCH();

@@ -78,11 +78,33 @@ int disc_embed_bwd_impl(const AdvmilDiscParams* p, const AdvmilBags* bags, const
 int colsum(const void* dY, int dt, int rows, int N, int ld, float* out, int accumulate, float* ws /* >= row_chunks*N */,
            cudaStream_t st);
 int reduce_rows(const float* part, int nparts, int width, float* out, int accumulate, cudaStream_t st);
+// out[c] (+)= sum_p part[p * stride + c], c < ncols
+int reduce_rows_strided(const float* part, int nparts, int stride, int ncols, float* out, int accumulate, cudaStream_t st);
 int splitk_reduce(const float* ws, int splits, size_t n, float* out, int accumulate, cudaStream_t st);
 int splitk_reduce_t(const float* ws, int splits, int R, int Cc, float* out, int accumulate, cudaStream_t st);
 int apply_dropout(const void* src, int rows, int width, const Drop& drop, void* dst, int dt, cudaStream_t st);
 int fill_zero(float* p, size_t n, cudaStream_t st);
 int cast_f32_to_bf16(const float* in, size_t n, void* out, cudaStream_t st);
+
+// ---- esat_kernels.cu (region-level stages of the ESAT backbone, model/backbone.py:171-196) ---------------------------
+// emb[r] = mean_{k<16} relu(LN(y_pre[16r+k])) (+ pe[r]);  y_pre: T [rows, d], d % 32 == 0
+int ln_relu_mean16_fwd(const void* y_pre, const float* gamma, const float* beta, int rows, int d, float eps, const float* pe,
+                       float* emb, int dt, cudaStream_t st);
+int esat_ln_bwd_ctas(int R);   // partial-sum rows the two LayerNorm backward kernels write (workspace sizing)
+int ln_relu_mean16_bwd(const void* y_pre, const float* d_emb, const float* gamma, const float* beta, int rows, int d, float eps,
+                       void* d_y, float* dgamma, float* dbeta, float* dbias, float* ws /* >= ctas*3*d */, int dt, cudaStream_t st);
+// out = LN(a + b); b is overwritten with s = a + b
+int add_ln_fwd(const float* a, float* b_s, const float* gamma, const float* beta, int R, int d, float eps, float* out, cudaStream_t st);
+int add_ln_bwd(const float* s, const float* gamma, const float* d_out, int R, int d, float eps, float* d_s, float* dgamma,
+               float* dbeta, float* ws /* >= ctas*2*d */, cudaStream_t st);
+int add_rows(float* a, const float* b, size_t n, cudaStream_t st);   // a += b
+int sincos_pe(const int64_t* coord, const int32_t* ro, int bags, int d, const float* omega, float* pe, cudaStream_t st);
+// self-attention over the regions of each bag: qkv [R, 3d] -> ctx [R, d], lse [heads, R]; ro = region offsets [bags+1]
+int mha_fwd(const float* qkv, const int32_t* ro, const int32_t* ro_host, int bags, int Rtot, int d, int heads, const Drop& drop,
+            const uint8_t* mask, const int64_t* mask_off, float* ctx, float* lse, cudaStream_t st);
+int mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float* lse, const int32_t* ro, const int32_t* ro_host,
+            int bags, int Rtot, int d, int heads, const Drop& drop, const uint8_t* mask, const int64_t* mask_off, float* d_qkv,
+            float* Dq /* [heads, R] */, cudaStream_t st);
 
 // ---- tail_kernels.cu --------------------------------------------------------------------------
 int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, const float* noise1, int bags,

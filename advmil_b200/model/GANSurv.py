@@ -38,7 +38,12 @@ class Generator(nn.Module):
                                     out_scale=_OUT_SCALE.get(self.out_scale, 0), p_head=self.p_head)
 
     def gen_params(self):
+        if self.backbone.kind == "patch":
+            return [None] * 10 + self.head_params()
         return self.backbone.gen_params(self.MLPs)
+
+    def head_params(self):
+        return [self.MLPs[0][0].weight, self.MLPs[0][0].bias, self.MLPs[1][0].weight, self.MLPs[1][0].bias]
 
     def draw_noise(self, n_bags: int, device, zero_noise: bool):
         """Noise tensors in the order Generator.forward draws them (reference :33-38): one per layer with flag 1,
@@ -54,7 +59,9 @@ class Generator(nn.Module):
 
     # -- reference surface ------------------------------------------------------------------------
     def forward(self, x, x_ext, zero_noise=False):
-        """x [1,N,C]; x_ext ignored for ABMIL, cluster ids for DeepAttMISL -> [1,1]."""
+        """x [1,N,C]; x_ext ignored for ABMIL, cluster ids for DeepAttMISL, region coordinates (or None) for ESAT -> [1,1]."""
+        if self.backbone.kind == "patch":
+            return self.forward_packed(ops.PackedBags.from_single(x), zero_noise=zero_noise, coord=x_ext)
         if self.backbone.kind == "cluster":
             hc = self.backbone.cluster_rows(x, x_ext)
             # the attention stage sees num_clusters rows per bag: always the exact fp32 engine
@@ -64,11 +71,17 @@ class Generator(nn.Module):
 
     def forward_packed(self, bags: ops.PackedBags, noise: Optional[Sequence[Optional[torch.Tensor]]] = None,
                        zero_noise: bool = False, x_grad: Optional[torch.Tensor] = None,
-                       precision: Optional[int] = None) -> torch.Tensor:
+                       precision: Optional[int] = None, coord=None) -> torch.Tensor:
         """Packed bags -> [bags, 1]."""
         precision = ops.PRECISIONS[get_precision()] if precision is None else precision
         n0, n1 = noise if noise is not None else self.draw_noise(bags.bags, bags.x.device, zero_noise)
         train = self.training
+        if self.backbone.kind == "patch":
+            bb = self.backbone
+            masks = getattr(self, "_inject_masks", None)
+            pred = ops.EsatFn.apply(bb.esat_config(), self.config(), bags, bb.positional(bags, coord), n0, n1, train,
+                                    next_dropout_seed() if train else 0, masks, precision, *bb.esat_params(), *self.head_params())
+            return pred.unsqueeze(-1)
         pred = ops.GeneratorFn.apply(self.config(), bags, x_grad, n0, n1, train, next_dropout_seed() if train else 0,
                                      getattr(self, "_inject_masks", None), precision, *self.gen_params())
         return pred.unsqueeze(-1)

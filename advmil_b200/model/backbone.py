@@ -1,9 +1,10 @@
 """MIL encoders with the reference's constructor/forward surface and state_dict layout (model/backbone.py),
-executed by the fused CUDA path.  ABMIL and DeepAttMISL are on the AdvMIL hot path; PatchGCN and the ESAT transformer
-(`patch`) are out of scope for this build and raise NotImplementedError.
+executed by the fused CUDA path: ABMIL, DeepAttMISL (`cluster`) and the ESAT transformer DualTrans_HS (`patch`).
+PatchGCN (`graph`, needs torch_geometric) is out of scope and raises NotImplementedError.
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
 from typing import List, Optional
 
 import torch
@@ -11,22 +12,29 @@ import torch.nn as nn
 
 from .. import get_precision, ops
 from ..utils.func import next_dropout_seed
-from .backbone_utils import Attn_Net_Gated
+from .backbone_utils import Attn_Net_Gated, GAPool, make_embedding_layer, make_transformer_layer
 
 
 def load_backbone_param(mode, dims):
+    """Default parameters per mode (reference model/backbone.py:29-45)."""
+    if mode == "patch":
+        param_emb = SimpleNamespace(in_dim=dims[0], out_dim=dims[1], scale=4, dw_conv=False, ksize=1)
+        param_tra = SimpleNamespace(d_model=dims[1], nhead=8, dropout=0.25, num_layers=1)
+        return [dims[:3], "avgpool", param_emb, "Transformer", param_tra], {"dropout": 0.25}
     if mode == "cluster":
         return [dims[:3]], {"num_clusters": 8, "dropout": 0.25}
-    if mode in ("patch", "graph"):
-        raise NotImplementedError(f"backbone mode '{mode}' is outside the B200 hot path (abmil / cluster are built)")
+    if mode == "graph":
+        raise NotImplementedError("backbone mode 'graph' (PatchGCN) is outside the B200 hot path (abmil / cluster / patch are built)")
     return [dims[:3]], {"dropout": 0.25}
 
 
 def Model_Zoo(mode):
+    if mode == "patch":
+        return DualTrans_HS
     if mode == "cluster":
         return DeepAttMISL
-    if mode in ("patch", "graph"):
-        raise NotImplementedError(f"backbone mode '{mode}' is outside the B200 hot path (abmil / cluster are built)")
+    if mode == "graph":
+        raise NotImplementedError("backbone mode 'graph' (PatchGCN) is outside the B200 hot path (abmil / cluster / patch are built)")
     return ABMIL
 
 
@@ -127,6 +135,75 @@ class DeepAttMISL(_GatedMILBase):
                                   next_dropout_seed() if self.training else 0, getattr(self, "_inject_masks", None),
                                   ops.FP32, *self.gen_params())   # num_clusters rows: always the exact fp32 engine
         return H
+
+
+class DualTrans_HS(nn.Module):
+    """ESAT encoder (reference model/backbone.py:171-196): AVGPoolPatchEmbedding -> (+ sincos PE of the region
+    coordinates) -> one post-norm nn.TransformerEncoderLayer over the regions of the bag -> GAPool.  The sub-modules are
+    parameter containers with the reference's state_dict names; the arithmetic runs in advmil_esat_fwd/bwd."""
+
+    kind = "patch"
+
+    def __init__(self, dims: List, emb_backbone: str, args_emb_backbone, tra_backbone: str, args_tra_backbone,
+                 dropout: float = 0.25):
+        super().__init__()
+        assert len(dims) == 3  # dim_in, dim_hid, dim_out = [1024, 384, 384]
+        dim_in, dim_hid, dim_out = dims
+        assert dim_hid == dim_out
+        assert emb_backbone in ["avgpool", "gapool"]
+        assert tra_backbone in ["Transformer", "Identity"]
+        if tra_backbone != "Transformer" or args_tra_backbone.num_layers != 1:
+            raise NotImplementedError("the fused ESAT path covers one Transformer encoder layer (model/backbone.py:33)")
+        self.dims = (dim_in, dim_hid, dim_out)
+        self.patch_embedding_layer = make_embedding_layer(emb_backbone, args_emb_backbone)
+        self.dim_hid = dim_hid
+        self.patch_encoder_layer = make_transformer_layer(tra_backbone, args_tra_backbone)
+        self.pool = GAPool(dim_out, dim_out)
+        self.nhead, self.p = args_tra_backbone.nhead, args_tra_backbone.dropout
+        assert self.pool.p == self.p, "encoder-layer and GAPool dropout share one probability in the fused path"
+
+    def esat_config(self) -> ops.EsatConfig:
+        layer = self.patch_encoder_layer.layers[0]
+        return ops.EsatConfig(C=self.dims[0], d=self.dim_hid, ff=layer.linear1.out_features, nhead=self.nhead, p=self.p,
+                              ln_eps=layer.norm1.eps)
+
+    def config(self, hid=0, noise=(0, 0), out_scale=0, p_head=0.0) -> ops.GenConfig:
+        """The Generator's noise head on top of H (no rho layer)."""
+        d = self.dim_hid
+        return ops.GenConfig(C=d, h=d, o=d, hid=hid, noise0=noise[0], noise1=noise[1], out_scale=out_scale, p_backbone=0.0,
+                             p_head=p_head, has_rho=False)
+
+    def esat_params(self):
+        e, layer, pool = self.patch_embedding_layer, self.patch_encoder_layer.layers[0], self.pool
+        sa = layer.self_attn
+        return [e.conv.weight, e.conv.bias, e.norm.weight, e.norm.bias, sa.in_proj_weight, sa.in_proj_bias,
+                sa.out_proj.weight, sa.out_proj.bias, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight,
+                layer.linear2.bias, layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias,
+                pool.fc1[0].weight, pool.fc1[0].bias, pool.score[0].weight, pool.score[0].bias, pool.fc2.weight, pool.fc2.bias]
+
+    def positional(self, bags: ops.PackedBags, coord) -> Optional[torch.Tensor]:
+        """coord: None (no PE, model/backbone.py:192) or the regions' discretised coordinates [1,R,2] / [R,2]."""
+        if coord is None:
+            return None
+        if coord.dim() == 3:
+            assert coord.shape[0] == 1   # backbone_utils.py:91
+            coord = coord.squeeze(0)
+        if coord.dim() != 2 or coord.shape[-1] != 2:   # the handler's placeholder Tensor([0]) (dataset/PatchWSI.py:83) fails in the reference too
+            raise IndexError("Dimension out of range: coord must be [B, N, 2] region coordinates or None "
+                             "(model/backbone_utils.py:90-99)")
+        return ops.sincos_pe(coord, bags, self.dim_hid)
+
+    def forward_packed(self, bags: ops.PackedBags, coord=None, head=None, head_params=(None,) * 4, noise=(None, None),
+                       precision: Optional[int] = None) -> torch.Tensor:
+        precision = ops.PRECISIONS[get_precision()] if precision is None else precision
+        train = self.training
+        return ops.EsatFn.apply(self.esat_config(), head, bags, self.positional(bags, coord), noise[0], noise[1], train,
+                                next_dropout_seed() if train else 0, getattr(self, "_inject_masks", None), precision,
+                                *self.esat_params(), *head_params)
+
+    def forward(self, x, coord, *args):
+        """x: [B, N, d], coord: the coordinates after discretization if not None -> H [1, dim_out]."""
+        return self.forward_packed(ops.PackedBags.from_single(x), coord)
 
 
 class ClusterPoolFn(torch.autograd.Function):

@@ -89,3 +89,16 @@ def make_embedding_layer(backbone: str, args):
     if backbone == "gapool":
         raise NotImplementedError("gapool patch embedding is outside the AdvMIL hot path (disc_netx_backbone: avgpool)")
     raise NotImplementedError(f"{backbone} has not implemented.")
+
+
+def make_transformer_layer(backbone: str, args):
+    """[B, N, C] --Transformer--> [B, N, C] (reference model/backbone_utils.py:112-127).  The returned nn.TransformerEncoder
+    is a parameter container (same state_dict names and default initialisation as the reference's); DualTrans_HS runs its
+    arithmetic in the fused CUDA path."""
+    if backbone == "Transformer":
+        layer = nn.TransformerEncoderLayer(args.d_model, args.nhead, dim_feedforward=args.d_model, dropout=args.dropout,
+                                           activation="relu", batch_first=True)
+        return nn.TransformerEncoder(layer, num_layers=args.num_layers)
+    if backbone == "Identity":
+        return nn.Identity()
+    raise NotImplementedError(f"{backbone} has not implemented.")

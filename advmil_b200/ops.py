@@ -13,8 +13,8 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import (Bags, DiscGrads, DiscParams, EmbedActs, GenActs, GenGrads, GenParams, HeadActs, DISC_TENSORS,
-                   GEN_TENSORS, check)
+from ._lib import (Bags, DiscGrads, DiscParams, EmbedActs, EsatActs, EsatGrads, EsatParams, GenActs, GenGrads, GenParams, HeadActs,
+                   DISC_TENSORS, ESAT_TENSORS, GEN_TENSORS, check)
 
 FP32, TF32, TF32X3, BF16 = 0, 1, 2, 3
 PRECISIONS = {"fp32": FP32, "tf32": TF32, "tf32x3": TF32X3, "bf16": BF16}
@@ -262,6 +262,147 @@ class GeneratorFn(torch.autograd.Function):
 
 
 # -------------------------------------------------------------------------------------------------
+# ESAT backbone (DualTrans_HS, reference model/backbone.py:171-196) + noise head
+# -------------------------------------------------------------------------------------------------
+@dataclass
+class EsatConfig:
+    C: int
+    d: int
+    ff: int
+    nhead: int = 8
+    p: float = 0.25
+    ln_eps: float = 1e-5
+
+    def c(self, params: Sequence[Optional[torch.Tensor]]) -> EsatParams:
+        s = EsatParams()
+        for name, t in zip(ESAT_TENSORS, params):
+            setattr(s, name, _ptr(t))
+        s.C, s.d, s.ff, s.nhead, s.p, s.ln_eps = self.C, self.d, self.ff, self.nhead, self.p, self.ln_eps
+        return s
+
+
+def sincos_pe(coord: torch.Tensor, bags: PackedBags, d: int) -> torch.Tensor:
+    """compute_pe (reference model/backbone_utils.py:79-99) for packed bags: coord [R,2] integer region coordinates ->
+    PE [R,d].  omega is evaluated exactly as the reference evaluates it (d/4 values); the kernel does the rest."""
+    lib = _lib.load()
+    _need_cuda(coord, "coord")
+    assert coord.dim() == 2 and coord.shape[1] == 2 and coord.shape[0] == bags.rows // 16, "one (x, y) per 16-row region"
+    assert d % 4 == 0, "feature dimension must be multiple of 4 for sincos emb"
+    omega = torch.arange(d // 4) / (d // 4 - 1)
+    omega = (1.0 / (10000 ** omega)).to(torch.float32).to(coord.device)
+    c = coord.to(torch.int64).contiguous()
+    pe = torch.empty(c.shape[0], d, dtype=torch.float32, device=coord.device)
+    ws = _ws(4096, coord.device)
+    check(lib.advmil_sincos_pe(c.data_ptr(), bags.offsets.data_ptr(), bags.bags, d, omega.data_ptr(), pe.data_ptr(), ws.data_ptr(),
+                               ws.numel(), _stream()), "advmil_sincos_pe")
+    return pe
+
+
+def _esat_structs(cfg: EsatConfig, head: Optional[GenConfig], params, head_params, acts, ws):
+    p = cfg.c(params)
+    hp = None
+    if head is not None:
+        hp = head.c([None] * 10 + list(head_params))
+    a = EsatActs()
+    for n in _lib.ESAT_ACTS:
+        setattr(a, n, _ptr(acts.get(n)))
+    a.pe, a.noise0, a.noise1 = _ptr(acts.get("pe")), _ptr(acts.get("noise0")), _ptr(acts.get("noise1"))
+    m = acts["masks"]
+    a.mask_attn, a.mask_attn_off = _ptr(m.get("attn")), _ptr(m.get("attn_off"))
+    for k in ("sa", "ff1", "ff2", "ga", "gs", "mlp0"):
+        setattr(a, "mask_" + k, _ptr(m.get(k)))
+    a.seed, a.train, a.precision = acts["seed"], int(acts["train"]), acts["precision"]
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    return p, hp, a
+
+
+def esat_prepare_masks(masks, bags: PackedBags, nhead: int):
+    """Injected keep masks (tests): 'attn' may be a list of per-bag [nhead, R_b, R_b] tensors; it is flattened and its
+    per-bag element offsets are added as 'attn_off'."""
+    if not masks:
+        return {}
+    m = {k: v for k, v in masks.items() if k != "attn"}
+    if masks.get("attn") is not None:
+        per_bag = masks["attn"] if isinstance(masks["attn"], (list, tuple)) else [masks["attn"]]
+        assert len(per_bag) == bags.bags
+        offs, tot = [], 0
+        for t, n in zip(per_bag, bags.lengths):
+            assert tuple(t.shape) == (nhead, n // 16, n // 16), "attention mask of a bag is [nhead, R_b, R_b]"
+            offs.append(tot)
+            tot += t.numel()
+        m["attn"] = torch.cat([t.reshape(-1) for t in per_bag]).to(torch.uint8).contiguous()
+        m["attn_off"] = torch.tensor(offs, dtype=torch.int64, device=bags.x.device)
+    return {k: (v if k == "attn_off" else v.to(torch.uint8).contiguous()) for k, v in m.items()}
+
+
+def esat_forward(cfg: EsatConfig, head: Optional[GenConfig], params, head_params, bags: PackedBags, pe=None, noise0=None,
+                 noise1=None, train=False, seed=0, masks=None, precision: int = FP32) -> Dict[str, torch.Tensor]:
+    lib = _lib.load()
+    bags = bags.for_precision(precision)
+    dev = bags.x.device
+    rows, nb, R, d = bags.rows, bags.bags, bags.rows // 16, cfg.d
+    abw = lib.advmil_gate_packed_width(d)
+    f = dict(dtype=torch.float32, device=dev)
+    acts = {"y_pre": torch.empty(rows, d, dtype=act_dtype(precision), device=dev), "emb": torch.empty(R, d, **f),
+            "qkv": torch.empty(R, 3 * d, **f), "lse": torch.empty(cfg.nhead, R, **f), "ctx": torch.empty(R, d, **f),
+            "s1": torch.empty(R, d, **f), "x1": torch.empty(R, d, **f), "f": torch.empty(R, cfg.ff, **f),
+            "s2": torch.empty(R, d, **f), "x2": torch.empty(R, d, **f), "ab": torch.empty(R, abw, **f),
+            "rep": torch.empty(R, **f), "attn": torch.empty(R, **f), "H": torch.empty(nb, d, **f),
+            "pe": None if pe is None else _f32c(pe), "noise0": None if noise0 is None else _f32c(noise0),
+            "noise1": None if noise1 is None else _f32c(noise1), "masks": esat_prepare_masks(masks, bags, cfg.nhead),
+            "seed": int(seed), "train": bool(train), "precision": int(precision)}
+    if head is not None:
+        acts.update(H1=torch.empty(nb, head.hid, **f), pre=torch.empty(nb, **f), pred=torch.empty(nb, **f))
+    p0, hp0 = cfg.c(params), (None if head is None else head.c([None] * 10 + list(head_params)))
+    ws = _ws(lib.advmil_esat_workspace_bytes(C.byref(p0), None if hp0 is None else C.byref(hp0), rows, nb, 0), dev)
+    p, hp, a = _esat_structs(cfg, head, params, head_params, acts, ws)
+    b = bags.c()
+    check(lib.advmil_esat_fwd(C.byref(p), None if hp is None else C.byref(hp), C.byref(b), C.byref(a), _stream()), "advmil_esat_fwd")
+    return acts
+
+
+def esat_backward(cfg: EsatConfig, head: Optional[GenConfig], params, head_params, bags: PackedBags, acts, d_out: torch.Tensor):
+    lib = _lib.load()
+    bags = bags.for_precision(acts["precision"])
+    dev = bags.x.device
+    grads = [None if t is None else torch.empty_like(t, dtype=torch.float32) for t in params]
+    hgrads = [None if t is None else torch.empty_like(t, dtype=torch.float32) for t in head_params]
+    g = EsatGrads()
+    for n, t in zip(ESAT_TENSORS, grads):
+        setattr(g, n, _ptr(t))
+    hg = GenGrads()
+    for n, t in zip(GEN_TENSORS[10:], hgrads):
+        setattr(hg, n, _ptr(t))
+    p0, hp0 = cfg.c(params), (None if head is None else head.c([None] * 10 + list(head_params)))
+    ws = _ws(lib.advmil_esat_workspace_bytes(C.byref(p0), None if hp0 is None else C.byref(hp0), bags.rows, bags.bags, 1), dev)
+    p, hp, a = _esat_structs(cfg, head, params, head_params, acts, ws)
+    b = bags.c()
+    d_out = _f32c(d_out)
+    check(lib.advmil_esat_bwd(C.byref(p), None if hp is None else C.byref(hp), C.byref(b), C.byref(a), d_out.data_ptr(), C.byref(g),
+                              None if head is None else C.byref(hg), _stream()), "advmil_esat_bwd")
+    return grads, hgrads
+
+
+class EsatFn(torch.autograd.Function):
+    """pred[bags] (with a head) or H[bags,d] of the ESAT generator over packed bags; gradients for the 22 backbone tensors
+    and the 4 head tensors.  The bag features get no gradient (they are pre-extracted inputs)."""
+
+    @staticmethod
+    def forward(ctx, cfg, head, bags, pe, noise0, noise1, train, seed, masks, precision, *tensors):
+        params, head_params = tensors[:len(ESAT_TENSORS)], tensors[len(ESAT_TENSORS):]
+        acts = esat_forward(cfg, head, params, head_params, bags, pe, noise0, noise1, train, seed, masks, precision)
+        ctx.cfg, ctx.head, ctx.bags, ctx.acts, ctx.tensors = cfg, head, bags, acts, tensors
+        return (acts["pred"] if head is not None else acts["H"]).clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        n = len(ESAT_TENSORS)
+        det = [None if t is None else t.detach() for t in ctx.tensors]
+        grads, hgrads = esat_backward(ctx.cfg, ctx.head, det[:n], det[n:], ctx.bags, ctx.acts, d_out.contiguous())
+        return (None,) * 10 + tuple(grads) + tuple(hgrads)
+
+
+# -------------------------------------------------------------------------------------------------
 # discriminator
 # -------------------------------------------------------------------------------------------------
 @dataclass
@@ -488,7 +629,8 @@ def region_of_rows(rows: int, scale: int = 4, device="cuda") -> torch.Tensor:
     return out
 
 
-DROP_SITES = {"h": 1, "a": 2, "b": 3, "rho": 4, "mlp0": 5, "fc1": 11, "ga": 12, "gs": 13, "fc2": 14}
+DROP_SITES = {"h": 1, "a": 2, "b": 3, "rho": 4, "mlp0": 5, "fc1": 11, "ga": 12, "gs": 13, "fc2": 14,
+              "attn": 21, "sa": 22, "ff1": 23, "ff2": 24}     # attn: row = region * nhead + head, col = key region
 
 
 def dropout_mask(seed: int, site: str, p: float, rows: int, width: int, device="cuda") -> torch.Tensor:

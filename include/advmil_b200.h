@@ -36,7 +36,7 @@ typedef enum AdvmilStatus {
   ADVMIL_ERR_NO_DEVICE = 4  /* no sm_100 device */
 } AdvmilStatus;
 
-#define ADVMIL_ABI_VERSION 2
+#define ADVMIL_ABI_VERSION 3
 #if defined(__GNUC__)
 #define ADVMIL_API __attribute__((visibility("default")))
 #else
@@ -343,6 +343,75 @@ ADVMIL_API size_t advmil_adv_step_workspace_bytes(const AdvmilGenParams* gen, co
                                        int32_t bags, int32_t precision);
 ADVMIL_API int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream);
 ADVMIL_API int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream);
+
+/* ---- ESAT backbone: DualTrans_HS (model/backbone.py:171-196) as load_backbone('patch', dims) builds it (:31-35):
+ *      AVGPoolPatchEmbedding(C -> d, scale 4, ksize 1; model/backbone_utils.py:129-168) -> optional sincos positional
+ *      embedding (:79-99) -> one post-norm nn.TransformerEncoderLayer(d, nhead, dim_feedforward = ff, dropout p, relu)
+ *      (make_transformer_layer, model/backbone_utils.py:112-127) -> GAPool(d, d) (:31-56), followed by the Generator's
+ *      noise head (model/GANSurv.py:32-49) when `head` is given.  Parameter names are the reference state_dict's. ---- */
+typedef struct AdvmilEsatParams {
+  const float *Wc, *bc, *ln_g, *ln_b;     /* patch_embedding_layer.conv [d,C(,1,1)],[d]; .norm [d],[d] */
+  const float *Win, *bin;                 /* patch_encoder_layer.layers.0.self_attn.in_proj_weight [3d,d], in_proj_bias [3d] */
+  const float *Wout, *bout;               /* ...self_attn.out_proj [d,d],[d] */
+  const float *W1, *b1, *W2, *b2;         /* ...linear1 [ff,d],[ff]; linear2 [d,ff],[d] */
+  const float *n1_g, *n1_b, *n2_g, *n2_b; /* ...norm1, norm2 [d] */
+  const float *Pa_w, *Pa_b;               /* pool.fc1.0   [d,d],[d] (tanh branch)    */
+  const float *Ps_w, *Ps_b;               /* pool.score.0 [d,d],[d] (sigmoid branch) */
+  const float *Pc_w, *Pc_b;               /* pool.fc2     [1,d],[1] */
+  int32_t C, d, ff, nhead;
+  float p;                                /* dropout of the encoder layer (attention probabilities, both residual branches,
+                                             feed-forward) and of GAPool */
+  float ln_eps;
+} AdvmilEsatParams;
+
+typedef struct AdvmilEsatGrads {          /* same tensors, written (not accumulated) */
+  float *Wc, *bc, *ln_g, *ln_b, *Win, *bin, *Wout, *bout, *W1, *b1, *W2, *b2, *n1_g, *n1_b, *n2_g, *n2_b,
+        *Pa_w, *Pa_b, *Ps_w, *Ps_b, *Pc_w, *Pc_b;
+} AdvmilEsatGrads;
+
+typedef struct AdvmilEsatActs {           /* caller-allocated; R = rows / 16 region rows, packed like the bags */
+  void* y_pre;    /* T [rows,d] pre-LayerNorm projection */
+  float* emb;     /* [R,d] region embedding (+ pe) */
+  float* qkv;     /* [R,3d] */
+  float* lse;     /* [nhead,R] log-sum-exp of the attention logits */
+  float* ctx;     /* [R,d] attention output before out_proj */
+  float* s1;      /* [R,d] emb + dropout1(out_proj(ctx)) */
+  float* x1;      /* [R,d] norm1(s1) */
+  float* f;       /* [R,ff] dropout(relu(linear1(x1))) */
+  float* s2;      /* [R,d] x1 + dropout2(linear2(f)) */
+  float* x2;      /* [R,d] norm2(s2): the encoder output that GAPool pools */
+  float* ab;      /* [R,abw] GAPool gate activations (advmil_gate_packed_width(d)) */
+  float* rep;     /* [R] GAPool logits */
+  float* attn;    /* [R] GAPool softmax weights */
+  float* H;       /* [bags,d] backbone output */
+  float* H1;      /* [bags,hid] head (NULL without head) */
+  float* pre;     /* [bags] */
+  float* pred;    /* [bags] */
+  const float* pe;       /* optional [R,d] positional embedding (advmil_sincos_pe), added to emb */
+  const float* noise0;   /* [bags,d] or NULL */
+  const float* noise1;   /* [bags,hid] or NULL */
+  /* optional injected keep masks: attention probabilities per bag [nhead, R_b, R_b] at mask_attn_off[bag] (int64 element
+   * offsets, device); sa / ff2 / ga / gs [R,d]; ff1 [R,ff]; mlp0 [bags,hid] */
+  const uint8_t* mask_attn; const int64_t* mask_attn_off;
+  const uint8_t *mask_sa, *mask_ff1, *mask_ff2, *mask_ga, *mask_gs, *mask_mlp0;
+  uint64_t seed;
+  int32_t train, precision;
+  void* workspace; size_t workspace_bytes;
+} AdvmilEsatActs;
+
+ADVMIL_API size_t advmil_esat_workspace_bytes(const AdvmilEsatParams* p, const AdvmilGenParams* head, int32_t rows, int32_t bags,
+                                   int32_t backward);
+/* head == NULL: backbone only (DualTrans_HS.forward), result in acts->H.  head: AdvmilGenParams with Wrho == NULL,
+ * h == o == d and the MLPs tensors (W0, b0, Wl, bl, hid, noise0/1, out_scale, p_head); result in acts->pred. */
+ADVMIL_API int advmil_esat_fwd(const AdvmilEsatParams* p, const AdvmilGenParams* head, const AdvmilBags* bags, AdvmilEsatActs* acts,
+                    void* stream);
+/* d_out: dL/dpred [bags] with a head, dL/dH [bags,d] without.  head_grads: W0, b0, Wl, bl are written. */
+ADVMIL_API int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams* head, const AdvmilBags* bags, const AdvmilEsatActs* acts,
+                    const float* d_out, AdvmilEsatGrads* grads, AdvmilGenGrads* head_grads, void* stream);
+/* compute_pe (model/backbone_utils.py:90-99): coord [R,2] int64 region coordinates (packed like the regions), made
+ * relative to each bag's minimum; omega [d/4] = 1 / 10000^(k / (d/4 - 1)) as the reference computes it; pe [R,d]. */
+ADVMIL_API int advmil_sincos_pe(const int64_t* coord, const int32_t* offsets /* bag row offsets [bags+1], device */, int32_t bags,
+                     int32_t d, const float* omega, float* pe, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype"
-    assert lib.advmil_abi_version() == 2
+    assert lib.advmil_abi_version() == 3
     for i, st in enumerate(_lib.ABI_STRUCTS):
         assert lib.advmil_abi_sizeof(i) == ctypes.sizeof(st)
     assert lib.advmil_gate_packed_width(384) == 768 and lib.advmil_gate_packed_width(128) == 256
