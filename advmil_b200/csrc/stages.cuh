@@ -101,10 +101,10 @@ int add_rows(float* a, const float* b, size_t n, cudaStream_t st);   // a += b
 int sincos_pe(const int64_t* coord, const int32_t* ro, int bags, int d, const float* omega, float* pe, cudaStream_t st);
 // self-attention over the regions of each bag: qkv [R, 3d] -> ctx [R, d], lse [heads, R]; ro = region offsets [bags+1]
 int mha_fwd(const float* qkv, const int32_t* ro, const int32_t* ro_host, int bags, int Rtot, int d, int heads, const Drop& drop,
-            const uint8_t* mask, const int64_t* mask_off, float* ctx, float* lse, cudaStream_t st);
+            const uint8_t* mask, const int64_t* mask_off, float* ctx, float* lse, int precision, cudaStream_t st);
 int mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float* lse, const int32_t* ro, const int32_t* ro_host,
             int bags, int Rtot, int d, int heads, const Drop& drop, const uint8_t* mask, const int64_t* mask_off, float* d_qkv,
-            float* Dq /* [heads, R] */, cudaStream_t st);
+            float* Dq /* [heads, R] */, int precision, cudaStream_t st);
 
 // ---- tail_kernels.cu --------------------------------------------------------------------------
 int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, const float* noise1, int bags,

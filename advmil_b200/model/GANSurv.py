@@ -78,7 +78,7 @@ class Generator(nn.Module):
         train = self.training
         if self.backbone.kind == "patch":
             bb = self.backbone
-            masks = getattr(self, "_inject_masks", None)
+            masks = getattr(self, "_inject_masks", None) if train else None
             pred = ops.EsatFn.apply(bb.esat_config(), self.config(), bags, bb.positional(bags, coord), n0, n1, train,
                                     next_dropout_seed() if train else 0, masks, precision, *bb.esat_params(), *self.head_params())
             return pred.unsqueeze(-1)

@@ -198,8 +198,8 @@ class DualTrans_HS(nn.Module):
         precision = ops.PRECISIONS[get_precision()] if precision is None else precision
         train = self.training
         return ops.EsatFn.apply(self.esat_config(), head, bags, self.positional(bags, coord), noise[0], noise[1], train,
-                                next_dropout_seed() if train else 0, getattr(self, "_inject_masks", None), precision,
-                                *self.esat_params(), *head_params)
+                                next_dropout_seed() if train else 0, getattr(self, "_inject_masks", None) if train else None,
+                                precision, *self.esat_params(), *head_params)
 
     def forward(self, x, coord, *args):
         """x: [B, N, d], coord: the coordinates after discretization if not None -> H [1, dim_out]."""

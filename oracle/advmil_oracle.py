@@ -634,7 +634,8 @@ class CpuTrainer:
     the same ATen kernels the reference's modules dispatch to on CPU."""
 
     def __init__(self, sdG: SD, sdD: SD, lr: float = 8e-5, wd_g: float = 5e-4, coef_gan: float = 0.004,
-                 coef_l1: float = 1e-5, which: str = "bce"):
+                 coef_l1: float = 1e-5, which: str = "bce", backbone: str = "abmil"):
+        self.backbone = backbone
         self.sdG = {k: v.clone().requires_grad_(True) for k, v in sdG.items()}
         self.sdD = {k: v.clone().requires_grad_(True) for k, v in sdD.items()}
         no_decay = [v for k, v in self.sdG.items() if v.ndim == 1 or k.endswith(".bias")]
@@ -646,12 +647,14 @@ class CpuTrainer:
     def step(self, bags, ts, es, visible, noise_d, noise_g, d_masks_real=None, d_masks_fake=None, g_masks=None):
         nzd = [[None, n.reshape(1, -1)] for n in noise_d]
         nzg = [[None, n.reshape(1, -1)] for n in noise_g]
-        d = disc_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzd, d_masks_real, d_masks_fake, self.which)
+        d = disc_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzd, d_masks_real, d_masks_fake, self.which,
+                           backbone=self.backbone)
         self.optD.zero_grad()
         d["loss"].backward()
         d_grads = {k: v.grad.clone() for k, v in self.sdD.items()}
         self.optD.step()
-        g = gen_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzg, g_masks, self.coef_gan, self.coef_l1)
+        g = gen_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzg, g_masks, self.coef_gan, self.coef_l1,
+                          backbone=self.backbone)
         self.optG.zero_grad()
         for v in self.sdD.values():
             v.grad = None
