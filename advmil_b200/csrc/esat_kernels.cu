@@ -485,17 +485,20 @@ __device__ __forceinline__ void load_a_frags(const float* __restrict__ base, siz
     a[ks][3] = f2tf32(v1 ? p1[ks * 8 + t + 4] * mul : 0.f);
   }
 }
-// cooperative load of `n` rows x HD columns (row stride ld, zero beyond nvalid) into S[n][HD + 4] as tf32 bit patterns
+// asynchronous copy of N rows x HD columns (row stride ld floats, zero beyond nvalid) into S[N][HD + 4]: 16-byte cp.async
+// chunks, raw fp32 bits (the tensor core reads the top 19 bits of each word: tf32 by truncation).  The caller commits
+// and waits for the group.
 template <int HD, int N>
-__device__ __forceinline__ void load_tile_tf32(const float* __restrict__ base, size_t ld, int nvalid, float mul, uint32_t (*S)[HD + 4]) {
+__device__ __forceinline__ void tile_copy_async(const float* __restrict__ base, size_t ld, int nvalid, uint32_t (*S)[HD + 4]) {
   for (int i = threadIdx.x; i < N * (HD / 4); i += blockDim.x) {
     const int j = i / (HD / 4), c4 = i % (HD / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < nvalid) v = *reinterpret_cast<const float4*>(base + (size_t)j * ld + 4 * c4);
-    S[j][4 * c4] = f2tf32(v.x * mul); S[j][4 * c4 + 1] = f2tf32(v.y * mul);
-    S[j][4 * c4 + 2] = f2tf32(v.z * mul); S[j][4 * c4 + 3] = f2tf32(v.w * mul);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S[j][4 * c4]);
+    if (j < nvalid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(base + (size_t)j * ld + 4 * c4) : "memory");
+    else *reinterpret_cast<uint4*>(&S[j][4 * c4]) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // C[nt] (16 x 8 per tile, NT tiles) += A (16 x HD) . B^T where B rows are the column items: B(k = c, n = item)
 template <int HD, int NT>
 __device__ __forceinline__ void mma_rows_x_items(float (&c)[NT][4], const uint32_t (&a)[HD / 8][4], const uint32_t (*S)[HD + 4], int lane) {
@@ -526,13 +529,16 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 constexpr int TCF_KT = 64;   // keys per shared-memory tile, forward
+template <int HD> constexpr size_t mha_fwd_tc_smem() { return (size_t)2 * 2 * TCF_KT * (HD + 4) * sizeof(uint32_t); }
 template <int HD>
-__global__ void __launch_bounds__(32 * TCA_WARPS) mha_fwd_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ ro, int d,
+__global__ void __launch_bounds__(32 * TCA_WARPS, 4) mha_fwd_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ ro, int d,
                                                                    float scale, AttDrop ad, float* __restrict__ ctx,
                                                                    float* __restrict__ lse, int Rtot) {
   pdl_prologue();
-  __shared__ __align__(16) uint32_t Ks[TCF_KT][HD + 4];
-  __shared__ __align__(16) uint32_t Vs[TCF_KT][HD + 4];
+  extern __shared__ __align__(16) uint32_t tca_smem[];
+  typedef uint32_t (*Tile)[HD + 4];
+  auto Kt = [&](int i) { return reinterpret_cast<Tile>(tca_smem + (size_t)i * 2 * TCF_KT * (HD + 4)); };   // [K tile | V tile] per buffer
+  auto Vt = [&](int i) { return Kt(i) + TCF_KT; };
   constexpr int NT = TCF_KT / 8;
   const int b = blockIdx.y, head = blockIdx.z, r0 = ro[b], Rb = ro[b + 1] - r0;
   if ((int)blockIdx.x * TCA_ROWS >= Rb) return;
@@ -540,6 +546,9 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_fwd_tc_kernel(const float*
   const int q0 = blockIdx.x * TCA_ROWS + wid * 16;
   const size_t ld = 3 * (size_t)d;
   const float* Q = qkv + (size_t)r0 * ld + head * HD;
+  tile_copy_async<HD, TCF_KT>(Q + d, ld, min(TCF_KT, Rb), Kt(0));
+  tile_copy_async<HD, TCF_KT>(Q + 2 * d, ld, min(TCF_KT, Rb), Vt(0));
+  cp_async_commit();
   uint32_t qa[HD / 8][4];
   load_a_frags<HD>(Q, ld, q0, Rb, lane, scale, qa);
   float o[HD / 8][4];
@@ -547,16 +556,23 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_fwd_tc_kernel(const float*
   for (int no = 0; no < HD / 8; ++no) o[no][0] = o[no][1] = o[no][2] = o[no][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int qi0 = q0 + g, qi1 = q0 + g + 8;
-  for (int k0 = 0; k0 < Rb; k0 += TCF_KT) {
+  int buf = 0;
+  for (int k0 = 0; k0 < Rb; k0 += TCF_KT, buf ^= 1) {
     const int nk = min(TCF_KT, Rb - k0);
-    __syncthreads();
-    load_tile_tf32<HD, TCF_KT>(Q + (size_t)k0 * ld + d, ld, nk, 1.f, Ks);
-    load_tile_tf32<HD, TCF_KT>(Q + (size_t)k0 * ld + 2 * d, ld, nk, 1.f, Vs);
+    if (k0 + TCF_KT < Rb) {            // prefetch the next tile into the other buffer
+      const int nn = min(TCF_KT, Rb - k0 - TCF_KT);
+      tile_copy_async<HD, TCF_KT>(Q + (size_t)(k0 + TCF_KT) * ld + d, ld, nn, Kt(buf ^ 1));
+      tile_copy_async<HD, TCF_KT>(Q + (size_t)(k0 + TCF_KT) * ld + 2 * d, ld, nn, Vt(buf ^ 1));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    mma_rows_x_items<HD, NT>(s, qa, Ks, lane);
+    mma_rows_x_items<HD, NT>(s, qa, Kt(buf), lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -594,8 +610,9 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_fwd_tc_kernel(const float*
       }
       s[nt][0] = p0; s[nt][1] = p1; s[nt][2] = p2; s[nt][3] = p3;
     }
-    mma_probs_x_values<HD, NT>(o, s, Vs, lane);
+    mma_probs_x_values<HD, NT>(o, s, Vt(buf), lane);
     m0 = mn0; m1 = mn1;
+    __syncthreads();                   // this buffer is refilled by the prefetch of the iteration after next
   }
   l0 = quad_sum(l0); l1 = quad_sum(l1);
   const float i0 = ad.drop.inv_keep / l0, i1 = ad.drop.inv_keep / l1;
@@ -614,13 +631,13 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_fwd_tc_kernel(const float*
 //   rows: the warp's row items (r_lo = g, r_hi = g + 8), columns: tile items 2t, 2t+1 of each 8-wide block
 constexpr int TCB_T = 32;    // column items per shared-memory tile, backward
 template <int HD>
-__global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_q_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
+__global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_q_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
                                                                      const float* __restrict__ d_ctx, const float* __restrict__ lse,
                                                                      const int32_t* __restrict__ ro, int d, float scale, AttDrop ad,
                                                                      float* __restrict__ d_qkv, float* __restrict__ Dq, int Rtot) {
   pdl_prologue();
-  __shared__ __align__(16) uint32_t Ks[TCB_T][HD + 4];
-  __shared__ __align__(16) uint32_t Vs[TCB_T][HD + 4];
+  __shared__ __align__(16) uint32_t Ks[2][TCB_T][HD + 4];
+  __shared__ __align__(16) uint32_t Vs[2][TCB_T][HD + 4];
   constexpr int NT = TCB_T / 8;
   const int b = blockIdx.y, head = blockIdx.z, r0 = ro[b], Rb = ro[b + 1] - r0;
   if ((int)blockIdx.x * TCA_ROWS >= Rb) return;
@@ -630,6 +647,9 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_q_tc_kernel(const floa
   const float* Q = qkv + (size_t)r0 * ld + head * HD;
   const float* G = d_ctx + (size_t)r0 * d + head * HD;
   const float* O = ctx + (size_t)r0 * d + head * HD;
+  tile_copy_async<HD, TCB_T>(Q + d, ld, min(TCB_T, Rb), Ks[0]);
+  tile_copy_async<HD, TCB_T>(Q + 2 * d, ld, min(TCB_T, Rb), Vs[0]);
+  cp_async_commit();
   const int qi0 = q0 + g, qi1 = q0 + g + 8;
   uint32_t qa[HD / 8][4], ga[HD / 8][4];
   load_a_frags<HD>(Q, ld, q0, Rb, lane, scale, qa);
@@ -651,17 +671,24 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_q_tc_kernel(const floa
 #pragma unroll
   for (int no = 0; no < HD / 8; ++no) dq[no][0] = dq[no][1] = dq[no][2] = dq[no][3] = 0.f;
   const float ik = ad.drop.inv_keep;
-  for (int k0 = 0; k0 < Rb; k0 += TCB_T) {
+  int buf = 0;
+  for (int k0 = 0; k0 < Rb; k0 += TCB_T, buf ^= 1) {
     const int nk = min(TCB_T, Rb - k0);
-    __syncthreads();
-    load_tile_tf32<HD, TCB_T>(Q + (size_t)k0 * ld + d, ld, nk, 1.f, Ks);
-    load_tile_tf32<HD, TCB_T>(Q + (size_t)k0 * ld + 2 * d, ld, nk, 1.f, Vs);
+    if (k0 + TCB_T < Rb) {
+      const int nn = min(TCB_T, Rb - k0 - TCB_T);
+      tile_copy_async<HD, TCB_T>(Q + (size_t)(k0 + TCB_T) * ld + d, ld, nn, Ks[buf ^ 1]);
+      tile_copy_async<HD, TCB_T>(Q + (size_t)(k0 + TCB_T) * ld + 2 * d, ld, nn, Vs[buf ^ 1]);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[NT][4], dp[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
-    mma_rows_x_items<HD, NT>(s, qa, Ks, lane);
-    mma_rows_x_items<HD, NT>(dp, ga, Vs, lane);
+    mma_rows_x_items<HD, NT>(s, qa, Ks[buf], lane);
+    mma_rows_x_items<HD, NT>(dp, ga, Vs[buf], lane);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int kl = nt * 8 + 2 * t, kc = k0 + kl;
@@ -680,7 +707,8 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_q_tc_kernel(const floa
       s[nt][0] = p0 * ((k00 ? dp[nt][0] * ik : 0.f) - D0); s[nt][1] = p1 * ((k01 ? dp[nt][1] * ik : 0.f) - D0);
       s[nt][2] = p2 * ((k10 ? dp[nt][2] * ik : 0.f) - D1); s[nt][3] = p3 * ((k11 ? dp[nt][3] * ik : 0.f) - D1);
     }
-    mma_probs_x_values<HD, NT>(dq, s, Ks, lane);
+    mma_probs_x_values<HD, NT>(dq, s, Ks[buf], lane);
+    __syncthreads();
   }
 #pragma unroll
   for (int no = 0; no < HD / 8; ++no) {
@@ -691,14 +719,14 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_q_tc_kernel(const floa
 
 // dK, dV: the warp's rows are keys, the streamed columns are queries (transposed tiles S^T = K Q^T, dP^T = V dO^T)
 template <int HD>
-__global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_kv_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx,
+__global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_kv_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx,
                                                                       const float* __restrict__ lse, const float* __restrict__ Dq,
                                                                       const int32_t* __restrict__ ro, int d, float scale, AttDrop ad,
                                                                       float* __restrict__ d_qkv, int Rtot) {
   pdl_prologue();
-  __shared__ __align__(16) uint32_t Qs[TCB_T][HD + 4];
-  __shared__ __align__(16) uint32_t Gs[TCB_T][HD + 4];
-  __shared__ float Ls[TCB_T], Ds[TCB_T];
+  __shared__ __align__(16) uint32_t Qs[2][TCB_T][HD + 4];
+  __shared__ __align__(16) uint32_t Gs[2][TCB_T][HD + 4];
+  __shared__ float Ls[2][TCB_T], Ds[2][TCB_T];
   constexpr int NT = TCB_T / 8;
   const int b = blockIdx.y, head = blockIdx.z, r0 = ro[b], Rb = ro[b + 1] - r0;
   if ((int)blockIdx.x * TCA_ROWS >= Rb) return;
@@ -708,6 +736,9 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_kv_tc_kernel(const flo
   const float* Q = qkv + (size_t)r0 * ld + head * HD;
   const float* G = d_ctx + (size_t)r0 * d + head * HD;
   const int kj0 = kb0 + g, kj1 = kb0 + g + 8;
+  tile_copy_async<HD, TCB_T>(Q, ld, min(TCB_T, Rb), Qs[0]);
+  tile_copy_async<HD, TCB_T>(G, d, min(TCB_T, Rb), Gs[0]);
+  cp_async_commit();
   uint32_t ka[HD / 8][4], va[HD / 8][4];
   load_a_frags<HD>(Q + d, ld, kb0, Rb, lane, 1.f, ka);
   load_a_frags<HD>(Q + 2 * d, ld, kb0, Rb, lane, 1.f, va);
@@ -715,21 +746,28 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_kv_tc_kernel(const flo
 #pragma unroll
   for (int no = 0; no < HD / 8; ++no) { dk[no][0] = dk[no][1] = dk[no][2] = dk[no][3] = 0.f; dv[no][0] = dv[no][1] = dv[no][2] = dv[no][3] = 0.f; }
   const float ik = ad.drop.inv_keep;
-  for (int q0 = 0; q0 < Rb; q0 += TCB_T) {
+  int buf = 0;
+  for (int q0 = 0; q0 < Rb; q0 += TCB_T, buf ^= 1) {
     const int nq = min(TCB_T, Rb - q0);
-    __syncthreads();
-    load_tile_tf32<HD, TCB_T>(Q + (size_t)q0 * ld, ld, nq, scale, Qs);
-    load_tile_tf32<HD, TCB_T>(G + (size_t)q0 * d, d, nq, 1.f, Gs);
-    if (threadIdx.x < TCB_T) {
-      Ls[threadIdx.x] = (int)threadIdx.x < nq ? lse[(size_t)head * Rtot + r0 + q0 + threadIdx.x] : 0.f;
-      Ds[threadIdx.x] = (int)threadIdx.x < nq ? Dq[(size_t)head * Rtot + r0 + q0 + threadIdx.x] : 0.f;
+    if (threadIdx.x < TCB_T) {         // (this buffer's previous readers passed the barrier that ended the iteration before last)
+      Ls[buf][threadIdx.x] = (int)threadIdx.x < nq ? lse[(size_t)head * Rtot + r0 + q0 + threadIdx.x] : 0.f;
+      Ds[buf][threadIdx.x] = (int)threadIdx.x < nq ? Dq[(size_t)head * Rtot + r0 + q0 + threadIdx.x] : 0.f;
+    }
+    if (q0 + TCB_T < Rb) {
+      const int nn = min(TCB_T, Rb - q0 - TCB_T);
+      tile_copy_async<HD, TCB_T>(Q + (size_t)(q0 + TCB_T) * ld, ld, nn, Qs[buf ^ 1]);
+      tile_copy_async<HD, TCB_T>(G + (size_t)(q0 + TCB_T) * d, d, nn, Gs[buf ^ 1]);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     float s[NT][4], dp[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
-    mma_rows_x_items<HD, NT>(s, ka, Qs, lane);       // S^T[key][query]
-    mma_rows_x_items<HD, NT>(dp, va, Gs, lane);      // dP^T[key][query]
+    mma_rows_x_items<HD, NT>(s, ka, Qs[buf], lane);       // S^T[key][query] without the 1/sqrt(hd) factor
+    mma_rows_x_items<HD, NT>(dp, va, Gs[buf], lane);      // dP^T[key][query]
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int ql = nt * 8 + 2 * t, qc = q0 + ql;    // this lane's two queries: qc, qc + 1 (columns); keys kj0 / kj1 (rows)
@@ -739,24 +777,25 @@ __global__ void __launch_bounds__(32 * TCA_WARPS) mha_bwd_kv_tc_kernel(const flo
         k00 = ad.keep(b, head, qa_, ka_, Rb, r0 + qa_); k01 = ad.keep(b, head, qb_, ka_, Rb, r0 + qb_);
         k10 = ad.keep(b, head, qa_, kb_, Rb, r0 + qa_); k11 = ad.keep(b, head, qb_, kb_, Rb, r0 + qb_);
       }
-      const float La = Ls[ql], Lb = Ls[ql + 1], Da = Ds[ql], Db = Ds[ql + 1];
-      const float p0 = ql < nq ? __expf(s[nt][0] - La) : 0.f, p1 = ql + 1 < nq ? __expf(s[nt][1] - Lb) : 0.f;
-      const float p2 = ql < nq ? __expf(s[nt][2] - La) : 0.f, p3 = ql + 1 < nq ? __expf(s[nt][3] - Lb) : 0.f;
+      const float La = Ls[buf][ql], Lb = Ls[buf][ql + 1], Da = Ds[buf][ql], Db = Ds[buf][ql + 1];
+      const float p0 = ql < nq ? __expf(fmaf(s[nt][0], scale, -La)) : 0.f, p1 = ql + 1 < nq ? __expf(fmaf(s[nt][1], scale, -Lb)) : 0.f;
+      const float p2 = ql < nq ? __expf(fmaf(s[nt][2], scale, -La)) : 0.f, p3 = ql + 1 < nq ? __expf(fmaf(s[nt][3], scale, -Lb)) : 0.f;
       s[nt][0] = p0 * ((k00 ? dp[nt][0] * ik : 0.f) - Da); s[nt][1] = p1 * ((k01 ? dp[nt][1] * ik : 0.f) - Db);
       s[nt][2] = p2 * ((k10 ? dp[nt][2] * ik : 0.f) - Da); s[nt][3] = p3 * ((k11 ? dp[nt][3] * ik : 0.f) - Db);
       dp[nt][0] = k00 ? p0 * ik : 0.f; dp[nt][1] = k01 ? p1 * ik : 0.f; dp[nt][2] = k10 ? p2 * ik : 0.f; dp[nt][3] = k11 ? p3 * ik : 0.f;
     }
-    mma_probs_x_values<HD, NT>(dv, dp, Gs, lane);    // dV += Pd^T dO
-    mma_probs_x_values<HD, NT>(dk, s, Qs, lane);     // dK += dS^T (scale Q)
+    mma_probs_x_values<HD, NT>(dv, dp, Gs[buf], lane);    // dV += Pd^T dO
+    mma_probs_x_values<HD, NT>(dk, s, Qs[buf], lane);     // dK += dS^T Q (the 1/sqrt(hd) factor is applied at the store)
+    __syncthreads();
   }
 #pragma unroll
   for (int no = 0; no < HD / 8; ++no) {
     if (kj0 < Rb) {
-      *reinterpret_cast<float2*>(d_qkv + (size_t)(r0 + kj0) * ld + d + head * HD + no * 8 + 2 * t) = make_float2(dk[no][0], dk[no][1]);
+      *reinterpret_cast<float2*>(d_qkv + (size_t)(r0 + kj0) * ld + d + head * HD + no * 8 + 2 * t) = make_float2(dk[no][0] * scale, dk[no][1] * scale);
       *reinterpret_cast<float2*>(d_qkv + (size_t)(r0 + kj0) * ld + 2 * d + head * HD + no * 8 + 2 * t) = make_float2(dv[no][0], dv[no][1]);
     }
     if (kj1 < Rb) {
-      *reinterpret_cast<float2*>(d_qkv + (size_t)(r0 + kj1) * ld + d + head * HD + no * 8 + 2 * t) = make_float2(dk[no][2], dk[no][3]);
+      *reinterpret_cast<float2*>(d_qkv + (size_t)(r0 + kj1) * ld + d + head * HD + no * 8 + 2 * t) = make_float2(dk[no][2] * scale, dk[no][3] * scale);
       *reinterpret_cast<float2*>(d_qkv + (size_t)(r0 + kj1) * ld + 2 * d + head * HD + no * 8 + 2 * t) = make_float2(dv[no][2], dv[no][3]);
     }
   }
@@ -884,7 +923,11 @@ int mha_fwd(const float* qkv, const int32_t* ro, const int32_t* ro_host, int bag
   const AttDrop ad = make_att_drop(drop, mask, mask_off, heads);
   const float scale = 1.0f / sqrtf((float)hd);
   if (mha_use_tc(precision, hd)) {
-    ESAT_HD8_SWITCH(hd, (launch_k(mha_fwd_tc_kernel<HD>, dim3(cdiv(mx, TCA_ROWS), bags, heads), dim3(32 * TCA_WARPS), 0, st, qkv, ro, d, scale, ad, ctx, lse, Rtot)));
+    ESAT_HD8_SWITCH(hd, {
+      static bool attr_set = false;    // > 48 KB of dynamic shared memory needs the opt-in once per instantiation
+      if (!attr_set) { ADVMIL_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mha_fwd_tc_smem<HD>())); attr_set = true; }
+      launch_k(mha_fwd_tc_kernel<HD>, dim3(cdiv(mx, TCA_ROWS), bags, heads), dim3(32 * TCA_WARPS), mha_fwd_tc_smem<HD>(), st, qkv, ro, d, scale, ad, ctx, lse, Rtot);
+    });
   } else {
     ESAT_HD_SWITCH(hd, (launch_k(mha_fwd_kernel<HD>, dim3(cdiv(mx, ATT_BQ), bags, heads), dim3(ATT_BQ), 0, st, qkv, ro, d, scale, ad, ctx, lse, Rtot)));
   }
