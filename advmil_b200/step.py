@@ -196,6 +196,129 @@ class AdvStep:
         return {"dis_loss": v[0], "t_reg_loss": v[1], "gen_loss": v[2], "gen_total_loss": v[3] + l1}
 
 
+class ModuleAdvStep:
+    """One D update + one G update over packed bags for ANY generator backbone (ABMIL, DeepAttMISL, ESAT), composed from
+    the modules' packed forwards and their autograd Functions: the same step semantics as `AdvStep`
+    (model/model_handler.py:349-498; global-count loss normalisation, flat parameter buffers, one all-reduce and one fused
+    Adam launch per network, L1 and weight decay inside the Adam kernel) without the ABMIL-specific cross-phase sharing
+    of `advmil_adv_step_disc/gen`.  Used for `bcb_mode: patch`; `AdvStep` remains the path for the ABMIL benchmark."""
+
+    def __init__(self, netG, netD, lr_g=8e-5, lr_d=8e-5, weight_decay_g=5e-4, coef_gan=0.004, coef_l1=1e-5, loss_d="bce",
+                 recon_alpha=0.0, recon_gamma=0.0, precision="fp32", process_group=None):
+        self.netG, self.netD = netG, netD
+        self.gparams = [p for p in netG.parameters()]
+        self.dparams = [p for p in netD.parameters()]
+        self.G = FlatParams(netG, self.gparams, weight_decay_rule=True)
+        self.D = FlatParams(netD, self.dparams, weight_decay_rule=False)
+        for p, g in zip(self.gparams, self.G.grad_views):
+            p.grad = g                      # autograd accumulates in place into the flat gradient buffers
+        for p, g in zip(self.dparams, self.D.grad_views):
+            p.grad = g
+        self.lr_g, self.lr_d, self.wd_g = lr_g, lr_d, weight_decay_g
+        self.coef_gan, self.coef_l1, self.loss_d = coef_gan, coef_l1, loss_d
+        self.recon_alpha, self.recon_gamma = recon_alpha, recon_gamma
+        self.precision, self.precision_name = ops.PRECISIONS[precision], precision
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def step(self, *args, **kwargs) -> Dict:
+        """See `_step`; runs it under this engine's precision mode (the modules read the package-wide setting)."""
+        from . import get_precision, set_precision
+        saved = get_precision()
+        set_precision(self.precision_name)
+        try:
+            return self._step(*args, **kwargs)
+        finally:
+            set_precision(saved)
+
+    def _disc_loss(self, f_real, f_fake, real_mask, n_real, n_fake):
+        """real_fake_loss (loss/utils.py:182-203) over packed bags: every bag has a fake pair, bags under `real_mask` a real
+        pair; means are over the GLOBAL pair counts."""
+        m = real_mask.float()
+        if self.loss_d == "bce":
+            loss = -(1.0 - torch.log(torch.sigmoid(f_fake) + 1e-8)).sum() / n_fake
+            if n_real > 0:
+                loss = loss - (m * torch.log(torch.sigmoid(f_real) + 1e-8)).sum() / n_real
+        elif self.loss_d == "hinge":
+            loss = torch.relu(1.0 + f_fake).sum() / n_fake
+            if n_real > 0:
+                loss = loss + (m * torch.relu(1.0 - f_real)).sum() / n_real
+        elif self.loss_d == "wasserstein":
+            loss = f_fake.sum() / n_fake
+            if n_real > 0:
+                loss = loss - (m * f_real).sum() / n_real
+        else:
+            raise ValueError(self.loss_d)
+        return loss
+
+    def _step(self, bags: ops.PackedBags, t, e, visible, noise_d=None, noise_g=None, coord=None, global_counts=None,
+              masks_d_real=None, masks_d_fake=None, masks_g=None) -> Dict:
+        G, D = self.netG, self.netD
+        bags = bags.for_precision(self.precision)
+        dev, nb = bags.x.device, bags.bags
+        t, e = t.reshape(-1).float(), e.reshape(-1).float()
+        vis = visible.reshape(-1) != 0
+        real_mask = (e == 1) & vis
+        if global_counts is None:
+            cnt = torch.stack([real_mask.sum(), torch.tensor(nb, device=dev), vis.sum()]).float()
+            self._allreduce(cnt)
+            n_real, n_fake, n_vis = [float(v) for v in cnt.tolist()]
+        else:
+            n_real, n_fake, n_vis = [float(v) for v in global_counts]
+        nz_d = [None, noise_d] if noise_d is not None else None
+        nz_g = [None, noise_g] if noise_g is not None else None
+        kw = {"coord": coord} if G.backbone.kind == "patch" else {}
+        # ---------------- D step: D.train / G.eval (model_handler.py:355-356) ----------------
+        D.train()
+        G.eval()
+        self.D.grad.zero_()
+        with torch.no_grad():
+            pred_d = G.forward_packed(bags, noise=nz_d, precision=self.precision, **kw)
+        D._inject_masks = masks_d_fake
+        f_fake = D.forward_packed(bags, pred_d.detach()).reshape(-1)
+        f_real = None
+        if n_real > 0:
+            D._inject_masks = masks_d_real
+            f_real = D.forward_packed(bags, t.reshape(-1, 1)).reshape(-1)
+        dis_loss = self._disc_loss(f_real, f_fake, real_mask, n_real, n_fake)
+        dis_loss.backward()
+        self._allreduce(self.D.grad)
+        self.D.adam(self.lr_d)
+        # ---------------- G step: D.eval / G.train (model_handler.py:432-433) ----------------
+        D.eval()
+        G.train()
+        self.G.grad.zero_()
+        for p in self.dparams:
+            p.requires_grad_(False)         # D only hands dL/dt back to G
+        try:
+            G._inject_masks = masks_g
+            pred_g = G.forward_packed(bags, noise=nz_g, precision=self.precision, **kw)
+            f_g = D.forward_packed(bags, pred_g).reshape(-1)
+            gen_loss = -f_g.sum() / n_fake                                        # fake_generator_loss (loss/utils.py:205-208)
+            pg = pred_g.reshape(-1)
+            lo = e * torch.abs(pg - t)                                            # recon_loss, l1 (loss/utils.py:21-41)
+            lc = (1.0 - e) * torch.relu(self.recon_gamma - (pg - t))
+            t_reg = (vis.float() * ((1.0 - self.recon_alpha) * (lo + lc) + self.recon_alpha * lo)).sum() / max(n_vis, 1.0)
+            total = t_reg + self.coef_gan * gen_loss
+            total.backward()
+        finally:
+            for p in self.dparams:
+                p.requires_grad_(True)
+        self._allreduce(self.G.grad)
+        l1 = self.G.flat.abs().sum() if self.coef_l1 > 1e-8 else None             # value only; its gradient is in the Adam kernel
+        self.G.adam(self.lr_g, weight_decay=self.wd_g, l1_coef=self.coef_l1 if self.coef_l1 > 1e-8 else 0.0)
+        return {"dis_loss": dis_loss.detach(), "gen_loss": gen_loss.detach(), "t_reg_loss": t_reg.detach(),
+                "gen_total_loss": total.detach() + (self.coef_l1 * l1 if l1 is not None else 0.0),
+                "pred_d": pred_d.reshape(-1), "pred_g": pred_g.detach().reshape(-1), "f_fake_d": f_fake.detach(),
+                "f_real": None if f_real is None else f_real.detach(), "f_fake_g": f_g.detach()}
+
+
 @torch.no_grad()
 def sample_inference(netG, netD, bags: ops.PackedBags, times_test_sample: int = 30, zero_noise: bool = False,
                      precision: str = "fp32"):

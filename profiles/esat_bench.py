@@ -50,3 +50,38 @@ for mode in args.modes.split(","):
     print(json.dumps({"what": "ESAT generator fwd+bwd (train mode)", "mode": mode, "bags": args.bags, "rows_per_bag": args.rows,
                       "ms_per_call": ms, "bags_per_s": args.bags / ms * 1e3}))
 advmil_b200.set_precision("fp32")
+
+# full adversarial step (D update + G update, both Adam steps) with the ESAT generator and the RLIP discriminator
+from types import SimpleNamespace as NS  # noqa: E402
+
+from advmil_b200.model.GANSurv import PrjDiscriminator  # noqa: E402
+from advmil_b200.step import ModuleAdvStep  # noqa: E402
+
+for mode in args.modes.split(","):
+    torch.manual_seed(0)
+    G2 = Generator(384, 1, load_backbone("patch", [1024, 384, 384]), SimpleNamespace(noise=[0, 1], hops=1, noise_dist="uniform"), False,
+                   0.6, "sigmoid").cuda()
+    D2 = PrjDiscriminator(NS(in_dim=1024, out_dim=128, ksize=1, backbone="avgpool", dropout=0.25),
+                          NS(in_dim=1, hid_dims=[64, 128], norm=False, dropout=0.0), prj_path="x", inner_product="instance").cuda()
+    eng = ModuleAdvStep(G2, D2, precision=mode)
+    x = x32.to(torch.bfloat16) if mode == "bf16" else x32
+    bags = ops.PackedBags(x, [args.rows] * args.bags)
+    t = torch.rand(args.bags, device="cuda")
+    e = (torch.rand(args.bags, device="cuda") < 0.35).float()
+    e[0] = 1.0
+    vis = torch.ones(args.bags, dtype=torch.uint8, device="cuda")
+    nz = torch.rand(args.bags, 192, device="cuda")
+    counts = (float(e.sum()), float(args.bags), float(args.bags))
+    for _ in range(3):
+        eng.step(bags, t, e, vis, noise_d=nz, noise_g=nz, global_counts=counts)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = eng.step(bags, t, e, vis, noise_d=nz, noise_g=nz, global_counts=counts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"what": "ESAT G + RLIP D adversarial step (ModuleAdvStep: D update + G update + both Adam steps)", "mode": mode,
+                      "bags": args.bags, "rows_per_bag": args.rows, "ms_per_step": ms, "bags_per_s": args.bags / ms * 1e3,
+                      "dis_loss": float(out["dis_loss"]), "gen_total_loss": float(out["gen_total_loss"])}))

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import advmil_oracle as O
-from tests.util import assert_close, build_D, build_G, d_masks, g_masks, golden, grad_floor, sub
+from tests.util import assert_close, build_D, build_G, d_masks, esat_masks, g_masks, golden, grad_floor, sub
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -249,6 +249,53 @@ def test_semi_supervised_steps_vs_oracle_trainer(case):
     for k, p in D.named_parameters():
         if not k.endswith(ZERO_GRAD):     # hinge: the per-bag upstream gradients sum to zero, see `slack` above
             assert_close(p.detach().cpu(), tr.sdD[k].detach(), RTOL, "D param " + k, atol=8e-5 * 2 * (1.0 if case == "hinge" else 2e-2))
+    for k, p in G.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
+
+
+def test_module_step_with_esat_generator_vs_oracle_trainer():
+    """ModuleAdvStep (packed bags, flat buffers, fused Adam with L1/weight decay) with the ESAT generator and the RLIP
+    discriminator: two optimiser steps in the fp32 mode against the oracle's restatement of _update_disc/_update_gen over
+    the same bags (mixed labelled / unlabelled), injected masks at every dropout site."""
+    from advmil_b200 import ops
+    from advmil_b200.step import ModuleAdvStep
+    C, d = 1024, 384
+    Ns = [160, 320, 96, 640]
+    B = len(Ns)
+    sdG, sdD = O.synth_state_dict(O.G_ESAT_SHAPES(C, d), 131), O.synth_state_dict(O.D_SHAPES(), 132)
+    tr = O.CpuTrainer(sdG, sdD, backbone="patch")
+    G, D = build_G((C, d, d), mode="patch"), build_D()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    eng = ModuleAdvStep(G, D)
+    xs = [O.synth_bag(n, 140 + i, C) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(B, 133)
+    es[0] = 1.0
+    vis = [True, True, False, True]
+    bags = ops.PackedBags.from_list([x.cuda() for x in xs])
+    for step in range(2):
+        rng = np.random.default_rng(134 + step)
+        nd = torch.tensor(rng.uniform(size=(B, d // 2)), dtype=torch.float32)
+        ng = torch.tensor(rng.uniform(size=(B, d // 2)), dtype=torch.float32)
+        mr = [d_masks(n // 16, 128, 600 + 10 * i + step) for i, n in enumerate(Ns)]
+        mf = [d_masks(n // 16, 128, 700 + 10 * i + step) for i, n in enumerate(Ns)]
+        mg = [esat_masks(n // 16, d, 800 + 10 * i + step) for i, n in enumerate(Ns)]
+        ref = tr.step(xs, ts, es, vis, list(nd), list(ng), mr, mf, mg)
+        mgd = _cat_masks(mg, ["sa", "ff1", "ff2", "ga", "gs", "mlp0"])
+        mgd["attn"] = [m["attn"].to(torch.uint8).cuda() for m in mg]
+        out = eng.step(bags, ts.cuda(), es.cuda(), torch.tensor(vis, dtype=torch.uint8).cuda(), noise_d=nd.cuda(), noise_g=ng.cuda(),
+                       masks_d_real=_cat_masks(mr, ["fc1", "ga", "gs", "fc2"]), masks_d_fake=_cat_masks(mf, ["fc1", "ga", "gs", "fc2"]),
+                       masks_g=mgd)
+        assert_close(out["pred_d"].cpu(), ref["pred_d"].reshape(-1), RTOL, f"pred_d {step}")
+        assert_close(out["pred_g"].cpu(), ref["pred_g"].reshape(-1), RTOL, f"pred_g {step}")
+        assert_close(out["f_fake_d"].cpu(), ref["fake_d"].reshape(-1), RTOL, f"fake_d {step}", atol_scale=1e-1)
+        assert_close(out["f_fake_g"].cpu(), ref["fake_g"].reshape(-1), RTOL, f"fake_g {step}", atol_scale=1e-1)
+        assert abs(float(out["dis_loss"]) - ref["dis_loss"]) < 2e-5 and abs(float(out["gen_loss"]) - ref["gen_loss"]) < 2e-5
+        assert abs(float(out["t_reg_loss"]) - ref["t_reg"]) < 2e-5 and abs(float(out["gen_total_loss"]) - ref["total"]) < 2e-5
+    for k, p in D.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdD[k].detach(), RTOL, "D param " + k, atol=8e-5 * 2 * 2e-2)
     for k, p in G.named_parameters():
         if not k.endswith(ZERO_GRAD):
             assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
