@@ -197,7 +197,7 @@ class AdvStep:
 
 
 class ModuleAdvStep:
-    """One D update + one G update over packed bags for ANY generator backbone (ABMIL, DeepAttMISL, ESAT), composed from
+    """One D update + one G update over packed bags for any built generator backbone (ABMIL, DeepAttMISL, ESAT), composed from
     the modules' packed forwards and their autograd Functions: the same step semantics as `AdvStep`
     (model/model_handler.py:349-498; global-count loss normalisation, flat parameter buffers, one all-reduce and one fused
     Adam launch per network, L1 and weight decay inside the Adam kernel) without the ABMIL-specific cross-phase sharing
@@ -257,8 +257,20 @@ class ModuleAdvStep:
             raise ValueError(self.loss_d)
         return loss
 
+    def _generate(self, bags: ops.PackedBags, noise, ext, coord):
+        """G over packed bags: ext = cluster ids [rows] (DeepAttMISL), coord = region coordinates [R,2] or None (ESAT)."""
+        G = self.netG
+        kind = G.backbone.kind
+        if kind == "cluster":
+            bb = G.backbone
+            hc = bb.cluster_rows(bags.x, ext, bags.lengths)          # [bags * clusters, h], differentiable
+            # the attention stage sees num_clusters rows per bag: always the exact fp32 engine (like Generator.forward)
+            return G.forward_packed(ops.PackedBags(hc, [bb.num_clusters] * bags.bags), noise=noise, x_grad=hc, precision=ops.FP32)
+        kw = {"coord": coord} if kind == "patch" else {}
+        return G.forward_packed(bags, noise=noise, precision=self.precision, **kw)
+
     def _step(self, bags: ops.PackedBags, t, e, visible, noise_d=None, noise_g=None, coord=None, global_counts=None,
-              masks_d_real=None, masks_d_fake=None, masks_g=None) -> Dict:
+              masks_d_real=None, masks_d_fake=None, masks_g=None, ext=None) -> Dict:
         G, D = self.netG, self.netD
         bags = bags.for_precision(self.precision)
         dev, nb = bags.x.device, bags.bags
@@ -273,13 +285,12 @@ class ModuleAdvStep:
             n_real, n_fake, n_vis = [float(v) for v in global_counts]
         nz_d = [None, noise_d] if noise_d is not None else None
         nz_g = [None, noise_g] if noise_g is not None else None
-        kw = {"coord": coord} if G.backbone.kind == "patch" else {}
         # ---------------- D step: D.train / G.eval (model_handler.py:355-356) ----------------
         D.train()
         G.eval()
         self.D.grad.zero_()
         with torch.no_grad():
-            pred_d = G.forward_packed(bags, noise=nz_d, precision=self.precision, **kw)
+            pred_d = self._generate(bags, nz_d, ext, coord)
         D._inject_masks = masks_d_fake
         f_fake = D.forward_packed(bags, pred_d.detach()).reshape(-1)
         f_real = None
@@ -298,7 +309,7 @@ class ModuleAdvStep:
             p.requires_grad_(False)         # D only hands dL/dt back to G
         try:
             G._inject_masks = masks_g
-            pred_g = G.forward_packed(bags, noise=nz_g, precision=self.precision, **kw)
+            pred_g = self._generate(bags, nz_g, ext, coord)
             f_g = D.forward_packed(bags, pred_g).reshape(-1)
             gen_loss = -f_g.sum() / n_fake                                        # fake_generator_loss (loss/utils.py:205-208)
             pg = pred_g.reshape(-1)

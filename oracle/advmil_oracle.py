@@ -644,17 +644,17 @@ class CpuTrainer:
         self.optD = torch.optim.Adam(list(self.sdD.values()), lr=lr, betas=(0.9, 0.999), weight_decay=0.0)
         self.coef_gan, self.coef_l1, self.which = coef_gan, coef_l1, which
 
-    def step(self, bags, ts, es, visible, noise_d, noise_g, d_masks_real=None, d_masks_fake=None, g_masks=None):
+    def step(self, bags, ts, es, visible, noise_d, noise_g, d_masks_real=None, d_masks_fake=None, g_masks=None, exts=None):
         nzd = [[None, n.reshape(1, -1)] for n in noise_d]
         nzg = [[None, n.reshape(1, -1)] for n in noise_g]
         d = disc_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzd, d_masks_real, d_masks_fake, self.which,
-                           backbone=self.backbone)
+                           exts=exts, backbone=self.backbone)
         self.optD.zero_grad()
         d["loss"].backward()
         d_grads = {k: v.grad.clone() for k, v in self.sdD.items()}
         self.optD.step()
         g = gen_step_loss(self.sdG, self.sdD, bags, ts, es, visible, nzg, g_masks, self.coef_gan, self.coef_l1,
-                          backbone=self.backbone)
+                          exts=exts, backbone=self.backbone)
         self.optG.zero_grad()
         for v in self.sdD.values():
             v.grad = None

@@ -299,3 +299,50 @@ def test_module_step_with_esat_generator_vs_oracle_trainer():
     for k, p in G.named_parameters():
         if not k.endswith(ZERO_GRAD):
             assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
+
+
+def test_module_step_with_cluster_generator_vs_oracle_trainer():
+    """configs[3]: the full adversarial step with the DeepAttMISL generator (per-cluster mean of relu(phi(x)), gated
+    attention over the 8 clusters; one bag with an empty cluster) and the RLIP discriminator through ModuleAdvStep, fp32
+    mode, two steps against the oracle trainer."""
+    from advmil_b200 import ops
+    from advmil_b200.step import ModuleAdvStep
+    C, h = 1024, 384
+    Ns = [160, 320, 96]
+    B = len(Ns)
+    sdG, sdD = O.synth_state_dict(O.G_CLUSTER_SHAPES(C, h), 151), O.synth_state_dict(O.D_SHAPES(), 152)
+    tr = O.CpuTrainer(sdG, sdD, backbone="cluster")
+    G, D = build_G((C, h, h), mode="cluster"), build_D()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    eng = ModuleAdvStep(G, D)
+    xs = [O.synth_bag(n, 160 + i, C) for i, n in enumerate(Ns)]
+    rng = np.random.default_rng(153)
+    cids = [torch.tensor(rng.integers(0, 8, size=n), dtype=torch.float32) for n in Ns]
+    cids[1][cids[1] == 5] = 4.0            # cluster 5 of bag 1 is empty (model/backbone.py:114-115)
+    ts, es = O.synth_labels(B, 154)
+    es[0] = 1.0
+    vis = [True, True, True]
+    bags = ops.PackedBags.from_list([x.cuda() for x in xs])
+    for step in range(2):
+        nd = torch.tensor(rng.uniform(size=(B, h // 2)), dtype=torch.float32)
+        ng = torch.tensor(rng.uniform(size=(B, h // 2)), dtype=torch.float32)
+        mr = [d_masks(n // 16, 128, 900 + 10 * i + step) for i, n in enumerate(Ns)]
+        mf = [d_masks(n // 16, 128, 950 + 10 * i + step) for i, n in enumerate(Ns)]
+        mg = [{"h": O.synth_masks((8, h), 0.75, 1000 + 10 * i + step), "a": O.synth_masks((8, h), 0.75, 1001 + 10 * i + step),
+               "b": O.synth_masks((8, h), 0.75, 1002 + 10 * i + step), "mlp0": O.synth_masks((1, h // 2), 0.4, 1003 + 10 * i + step)}
+              for i in range(B)]
+        ref = tr.step(xs, ts, es, vis, list(nd), list(ng), mr, mf, mg, exts=cids)
+        out = eng.step(bags, ts.cuda(), es.cuda(), torch.tensor(vis, dtype=torch.uint8).cuda(), noise_d=nd.cuda(), noise_g=ng.cuda(),
+                       masks_d_real=_cat_masks(mr, ["fc1", "ga", "gs", "fc2"]), masks_d_fake=_cat_masks(mf, ["fc1", "ga", "gs", "fc2"]),
+                       masks_g=_cat_masks(mg, ["h", "a", "b", "mlp0"]), ext=torch.cat(cids).cuda())
+        assert_close(out["pred_d"].cpu(), ref["pred_d"].reshape(-1), RTOL, f"pred_d {step}")
+        assert_close(out["pred_g"].cpu(), ref["pred_g"].reshape(-1), RTOL, f"pred_g {step}")
+        assert_close(out["f_fake_g"].cpu(), ref["fake_g"].reshape(-1), RTOL, f"fake_g {step}", atol_scale=1e-1)
+        assert abs(float(out["dis_loss"]) - ref["dis_loss"]) < 2e-5 and abs(float(out["gen_total_loss"]) - ref["total"]) < 2e-5
+    for k, p in D.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdD[k].detach(), RTOL, "D param " + k, atol=8e-5 * 2 * 2e-2)
+    for k, p in G.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
