@@ -104,7 +104,7 @@ class EsatActs(C.Structure):
         ("pe", c_fp), ("noise0", c_fp), ("noise1", c_fp), ("mask_attn", c_u8p), ("mask_attn_off", C.c_void_p),
         ("mask_sa", c_u8p), ("mask_ff1", c_u8p), ("mask_ff2", c_u8p), ("mask_ga", c_u8p), ("mask_gs", c_u8p), ("mask_mlp0", c_u8p),
         ("seed", C.c_uint64), ("train", C.c_int32), ("precision", C.c_int32),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("emb_ready", C.c_int32)]
 
 
 ABI_STRUCTS = [Bags, GenParams, GenGrads, GenActs, DiscParams, DiscGrads, EmbedActs, HeadActs, StepArgs, EsatParams, EsatGrads,

@@ -100,9 +100,11 @@ extern "C" int advmil_esat_fwd(const AdvmilEsatParams* p, const AdvmilGenParams*
   std::vector<int32_t> ro_host;
   ADVMIL_TRY(region_offsets(bags, ro_host, ro, st));
   // patch embedding (model/backbone_utils.py:158-168) + positional embedding (model/backbone.py:192-194)
-  { ProfScope ps(PROF_EMBED, st);
+  if (!a->emb_ready) {
+    ProfScope ps(PROF_EMBED, st);
     ADVMIL_TRY(linear_fwd(bags->x, p->Wc, p->bc, rows, C, d, 0, dr.none, a->y_pre, a->precision, st));
-    ADVMIL_TRY(ln_relu_mean16_fwd(a->y_pre, p->ln_g, p->ln_b, rows, d, p->ln_eps, a->pe, a->emb, dt, st)); }
+    ADVMIL_TRY(ln_relu_mean16_fwd(a->y_pre, p->ln_g, p->ln_b, rows, d, p->ln_eps, a->pe, a->emb, dt, st));
+  }
   ProfScope ps(PROF_HEAD_FWD, st);
   // encoder layer, post-norm
   ADVMIL_TRY(linear_fwd(a->emb, p->Win, p->bin, R, d, 3 * d, 0, dr.none, a->qkv, rp, st));

@@ -71,16 +71,18 @@ class Generator(nn.Module):
 
     def forward_packed(self, bags: ops.PackedBags, noise: Optional[Sequence[Optional[torch.Tensor]]] = None,
                        zero_noise: bool = False, x_grad: Optional[torch.Tensor] = None,
-                       precision: Optional[int] = None, coord=None) -> torch.Tensor:
-        """Packed bags -> [bags, 1]."""
+                       precision: Optional[int] = None, coord=None, reuse_embedding=None) -> torch.Tensor:
+        """Packed bags -> [bags, 1].  reuse_embedding (ESAT): activations of an earlier forward over the same bags,
+        coordinates and embedding parameters (ops.EsatFn.last_acts) whose patch embedding is shared."""
         precision = ops.PRECISIONS[get_precision()] if precision is None else precision
         n0, n1 = noise if noise is not None else self.draw_noise(bags.bags, bags.x.device, zero_noise)
         train = self.training
         if self.backbone.kind == "patch":
             bb = self.backbone
             masks = getattr(self, "_inject_masks", None) if train else None
-            pred = ops.EsatFn.apply(bb.esat_config(), self.config(), bags, bb.positional(bags, coord), n0, n1, train,
-                                    next_dropout_seed() if train else 0, masks, precision, *bb.esat_params(), *self.head_params())
+            pe = None if reuse_embedding is not None else bb.positional(bags, coord)
+            pred = ops.EsatFn.apply(bb.esat_config(), self.config(), bags, pe, n0, n1, train, next_dropout_seed() if train else 0,
+                                    masks, precision, reuse_embedding, *bb.esat_params(), *self.head_params())
             return pred.unsqueeze(-1)
         pred = ops.GeneratorFn.apply(self.config(), bags, x_grad, n0, n1, train, next_dropout_seed() if train else 0,
                                      getattr(self, "_inject_masks", None), precision, *self.gen_params())

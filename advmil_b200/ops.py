@@ -313,6 +313,7 @@ def _esat_structs(cfg: EsatConfig, head: Optional[GenConfig], params, head_param
         setattr(a, "mask_" + k, _ptr(m.get(k)))
     a.seed, a.train, a.precision = acts["seed"], int(acts["train"]), acts["precision"]
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.emb_ready = int(bool(acts.get("emb_ready")))
     return p, hp, a
 
 
@@ -336,7 +337,9 @@ def esat_prepare_masks(masks, bags: PackedBags, nhead: int):
 
 
 def esat_forward(cfg: EsatConfig, head: Optional[GenConfig], params, head_params, bags: PackedBags, pe=None, noise0=None,
-                 noise1=None, train=False, seed=0, masks=None, precision: int = FP32) -> Dict[str, torch.Tensor]:
+                 noise1=None, train=False, seed=0, masks=None, precision: int = FP32, reuse=None) -> Dict[str, torch.Tensor]:
+    """reuse: the activation dict of an earlier forward over the SAME bags, positional embedding and conv / norm
+    parameters (e.g. the eval pass of the D step): its patch embedding (y_pre, emb) is shared instead of recomputed."""
     lib = _lib.load()
     bags = bags.for_precision(precision)
     dev = bags.x.device
@@ -353,6 +356,9 @@ def esat_forward(cfg: EsatConfig, head: Optional[GenConfig], params, head_params
             "seed": int(seed), "train": bool(train), "precision": int(precision)}
     if head is not None:
         acts.update(H1=torch.empty(nb, head.hid, **f), pre=torch.empty(nb, **f), pred=torch.empty(nb, **f))
+    if reuse is not None:
+        assert reuse["precision"] == int(precision) and reuse["y_pre"].shape == acts["y_pre"].shape
+        acts.update(y_pre=reuse["y_pre"], emb=reuse["emb"], emb_ready=True)
     p0, hp0 = cfg.c(params), (None if head is None else head.c([None] * 10 + list(head_params)))
     ws = _ws(lib.advmil_esat_workspace_bytes(C.byref(p0), None if hp0 is None else C.byref(hp0), rows, nb, 0), dev)
     p, hp, a = _esat_structs(cfg, head, params, head_params, acts, ws)
@@ -387,10 +393,13 @@ class EsatFn(torch.autograd.Function):
     """pred[bags] (with a head) or H[bags,d] of the ESAT generator over packed bags; gradients for the 22 backbone tensors
     and the 4 head tensors.  The bag features get no gradient (they are pre-extracted inputs)."""
 
+    last_acts = None    # activations of the most recent forward (ModuleAdvStep shares the D step's embedding with the G step)
+
     @staticmethod
-    def forward(ctx, cfg, head, bags, pe, noise0, noise1, train, seed, masks, precision, *tensors):
+    def forward(ctx, cfg, head, bags, pe, noise0, noise1, train, seed, masks, precision, reuse, *tensors):
         params, head_params = tensors[:len(ESAT_TENSORS)], tensors[len(ESAT_TENSORS):]
-        acts = esat_forward(cfg, head, params, head_params, bags, pe, noise0, noise1, train, seed, masks, precision)
+        acts = esat_forward(cfg, head, params, head_params, bags, pe, noise0, noise1, train, seed, masks, precision, reuse=reuse)
+        EsatFn.last_acts = acts
         ctx.cfg, ctx.head, ctx.bags, ctx.acts, ctx.tensors = cfg, head, bags, acts, tensors
         return (acts["pred"] if head is not None else acts["H"]).clone()
 
@@ -399,7 +408,7 @@ class EsatFn(torch.autograd.Function):
         n = len(ESAT_TENSORS)
         det = [None if t is None else t.detach() for t in ctx.tensors]
         grads, hgrads = esat_backward(ctx.cfg, ctx.head, det[:n], det[n:], ctx.bags, ctx.acts, d_out.contiguous())
-        return (None,) * 10 + tuple(grads) + tuple(hgrads)
+        return (None,) * 11 + tuple(grads) + tuple(hgrads)
 
 
 # -------------------------------------------------------------------------------------------------

@@ -257,8 +257,10 @@ class ModuleAdvStep:
             raise ValueError(self.loss_d)
         return loss
 
-    def _generate(self, bags: ops.PackedBags, noise, ext, coord):
-        """G over packed bags: ext = cluster ids [rows] (DeepAttMISL), coord = region coordinates [R,2] or None (ESAT)."""
+    def _generate(self, bags: ops.PackedBags, noise, ext, coord, reuse=None):
+        """G over packed bags: ext = cluster ids [rows] (DeepAttMISL), coord = region coordinates [R,2] or None (ESAT).
+        reuse (ESAT): activations of the D step's eval pass -- G's parameters do not change between the two passes and the
+        patch embedding has no dropout, so the G step's train pass shares its x.Wc^T projection and LayerNorm stream."""
         G = self.netG
         kind = G.backbone.kind
         if kind == "cluster":
@@ -266,7 +268,7 @@ class ModuleAdvStep:
             hc = bb.cluster_rows(bags.x, ext, bags.lengths)          # [bags * clusters, h], differentiable
             # the attention stage sees num_clusters rows per bag: always the exact fp32 engine (like Generator.forward)
             return G.forward_packed(ops.PackedBags(hc, [bb.num_clusters] * bags.bags), noise=noise, x_grad=hc, precision=ops.FP32)
-        kw = {"coord": coord} if kind == "patch" else {}
+        kw = {"coord": coord, "reuse_embedding": reuse} if kind == "patch" else {}
         return G.forward_packed(bags, noise=noise, precision=self.precision, **kw)
 
     def _step(self, bags: ops.PackedBags, t, e, visible, noise_d=None, noise_g=None, coord=None, global_counts=None,
@@ -291,6 +293,7 @@ class ModuleAdvStep:
         self.D.grad.zero_()
         with torch.no_grad():
             pred_d = self._generate(bags, nz_d, ext, coord)
+        shared = ops.EsatFn.last_acts if G.backbone.kind == "patch" else None
         D._inject_masks = masks_d_fake
         f_fake = D.forward_packed(bags, pred_d.detach()).reshape(-1)
         f_real = None
@@ -309,7 +312,7 @@ class ModuleAdvStep:
             p.requires_grad_(False)         # D only hands dL/dt back to G
         try:
             G._inject_masks = masks_g
-            pred_g = self._generate(bags, nz_g, ext, coord)
+            pred_g = self._generate(bags, nz_g, ext, coord, reuse=shared)
             f_g = D.forward_packed(bags, pred_g).reshape(-1)
             gen_loss = -f_g.sum() / n_fake                                        # fake_generator_loss (loss/utils.py:205-208)
             pg = pred_g.reshape(-1)

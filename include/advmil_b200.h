@@ -397,6 +397,9 @@ typedef struct AdvmilEsatActs {           /* caller-allocated; R = rows / 16 reg
   uint64_t seed;
   int32_t train, precision;
   void* workspace; size_t workspace_bytes;
+  int32_t emb_ready;  /* != 0: y_pre and emb already hold the patch embedding of these bags under the current conv / norm
+                         parameters (written by an earlier call, e.g. the eval pass of the D step): the projection and its
+                         LayerNorm stream are skipped (the embedding has no dropout, so eval and train passes share it) */
 } AdvmilEsatActs;
 
 ADVMIL_API size_t advmil_esat_workspace_bytes(const AdvmilEsatParams* p, const AdvmilGenParams* head, int32_t rows, int32_t bags,
