@@ -211,7 +211,8 @@ class ModuleAdvStep:
         self.G = FlatParams(netG, self.gparams, weight_decay_rule=True)
         self.D = FlatParams(netD, self.dparams, weight_decay_rule=False)
         for p, g in zip(self.gparams, self.G.grad_views):
-            p.grad = g                      # autograd accumulates in place into the flat gradient buffers
+            p.grad = g                      # autograd accumulates in place into the flat gradient buffers (do not call
+                                            # zero_grad(set_to_none=True) on these modules: step() zeroes the buffers itself)
         for p, g in zip(self.dparams, self.D.grad_views):
             p.grad = g
         self.lr_g, self.lr_d, self.wd_g = lr_g, lr_d, weight_decay_g
@@ -324,6 +325,7 @@ class ModuleAdvStep:
         finally:
             for p in self.dparams:
                 p.requires_grad_(True)
+        ops.EsatFn.last_acts = None         # do not keep the step's activations alive
         self._allreduce(self.G.grad)
         l1 = self.G.flat.abs().sum() if self.coef_l1 > 1e-8 else None             # value only; its gradient is in the Adam kernel
         self.G.adam(self.lr_g, weight_decay=self.wd_g, l1_coef=self.coef_l1 if self.coef_l1 > 1e-8 else 0.0)
