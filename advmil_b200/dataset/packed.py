@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from ..ops import PackedBags
+from .codec import P12, decode_p12_device
 
 
 @dataclass
@@ -32,6 +33,7 @@ class PinnedStep:
     visible: torch.Tensor      # [bags] uint8 (label_visible_mask, model_handler.py:591-596)
     cluster_id: Optional[torch.Tensor] = None   # [rows] int32 (cluster mode)
     offsets: Optional[torch.Tensor] = None      # [bags+1] int32 prefix sums of lengths, pinned
+    p12: Optional["P12"] = None                 # lossless 12-bit transport form of x (bf16 only): what the feeder copies
 
     def __post_init__(self):
         if self.offsets is None:
@@ -42,7 +44,18 @@ class PinnedStep:
 
     @property
     def nbytes(self) -> int:
-        return self.x.numel() * self.x.element_size() + (self.t.numel() + self.e.numel()) * 4 + self.visible.numel()
+        """Bytes the feeder copies to the device for this step."""
+        feat = self.p12.nbytes if self.p12 is not None else self.x.numel() * self.x.element_size()
+        return feat + (self.t.numel() + self.e.numel()) * 4 + self.visible.numel()
+
+    def pack12(self) -> "PinnedStep":
+        """Adds the 12-bit transport form of the bf16 features (dataset/codec.py); the feeder then copies 12 instead of
+        16 bits per element and decodes on the device.  Exact: the device sees the same bf16 words."""
+        from .codec import encode_bf16_p12
+        assert self.x.dtype == torch.bfloat16, "the 12-bit transport format packs bf16 features"
+        if self.p12 is None:
+            self.p12 = encode_bf16_p12(self.x).pin()
+        return self
 
 
 def _pin(t: torch.Tensor) -> torch.Tensor:
@@ -138,7 +151,10 @@ class DeviceFeeder:
         self.device = torch.device(device)
         self.depth = max(2, depth)
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.decode_stream = torch.cuda.Stream(device=self.device)    # p12 decode runs beside the next step's copies
+        self._copied = [torch.cuda.Event() for _ in range(self.depth)]
         self._xbuf: List[Optional[torch.Tensor]] = [None] * self.depth
+        self._pbuf: List[Optional[tuple]] = [None] * self.depth      # device staging of the 12-bit planes (lo, hi)
         self._ready = [torch.cuda.Event() for _ in range(self.depth)]
         self._free = [torch.cuda.Event() for _ in range(self.depth)]
 
@@ -157,9 +173,29 @@ class DeviceFeeder:
             cid = None if st.cluster_id is None else st.cluster_id.to(self.device, non_blocking=True)
             self.copy_stream.wait_event(self._free[slot])          # consumer finished with this slot
             xd = buf[:rows]
-            xd.copy_(st.x, non_blocking=True)
+            if st.p12 is None:
+                xd.copy_(st.x, non_blocking=True)
+            else:       # 12 bits per element over the link; decoded on a second stream so the next copies are not held up
+                n = rows * C
+                pb = self._pbuf[slot]
+                if pb is None or pb[0].numel() < n:
+                    pb = (torch.empty(n, dtype=torch.uint8, device=self.device), torch.empty(n // 2, dtype=torch.uint8, device=self.device))
+                    self._pbuf[slot] = pb
+                lo, hi = pb[0][:n], pb[1][:n // 2]
+                ei = st.p12.esc_idx.to(self.device, non_blocking=True)
+                ee = st.p12.esc_exp.to(self.device, non_blocking=True)
+                lo.copy_(st.p12.lo, non_blocking=True)
+                hi.copy_(st.p12.hi, non_blocking=True)
+                self._copied[slot].record(self.copy_stream)
+                with torch.cuda.stream(self.decode_stream):
+                    self.decode_stream.wait_event(self._copied[slot])
+                    decode_p12_device(lo, hi, st.p12.table, ei, ee, xd)
+                    for ten in (ei, ee):
+                        ten.record_stream(self.decode_stream)
+                    self._ready[slot].record(self.decode_stream)
             bags = PackedBags(xd, st.lengths, offsets=offs)
-            self._ready[slot].record(self.copy_stream)
+            if st.p12 is None:
+                self._ready[slot].record(self.copy_stream)
         n_real = float(((st.e == 1) & (st.visible != 0)).sum())
         counts = (n_real, float(len(st.lengths)), float(st.visible.sum()))
         return DeviceStep(bags, t, e, vis, st.idx, cid, st.nbytes, counts, slot)

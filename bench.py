@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--bags", type=int, default=BAGS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p12", choices=["p12", "raw"],
+                    help="end-to-end leg, bf16 mode: copy the features in the packed loader's lossless 12-bit transport format "
+                         "(decoded on the device) or as raw bf16")
     ap.add_argument("--ragged", action="store_true",
                     help="configs[2] instead of configs[1]: bag lengths log-uniform in [1024, 100000] (multiples of 16)")
     args = ap.parse_args()
@@ -303,6 +306,10 @@ def main():
     losses = engine.loss_dict(out)
 
     # ================= (B) end-to-end through the public API: pinned host -> device every step =================
+    p12 = args.precision == "bf16" and args.transport == "p12"
+    if p12:
+        for st in steps[:2]:
+            st.pack12()           # done once, at packing time (the list cycles the same two steps)
     feeder = DeviceFeeder(steps, device=dev, depth=2)
     it = iter(feeder)
     h2d = steps[0].nbytes
@@ -387,6 +394,8 @@ def main():
                        "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "h2d_gbs_per_gpu": h2d * args.steps / (float(ems.item()) / 1e3) / 1e9,
+                    "transport": ("p12: lossless 12-bit form of the bf16 features (8 bits sign+mantissa, 4-bit exponent code, sparse "
+                                  "escapes), decoded on the device inside the timed region" if p12 else "raw"),
                     "note": "pinned host -> device copy of every step's features overlapped with the previous step's compute "
                             "(DeviceFeeder); bound by the PCIe link when h2d_gbs_per_gpu is ~55 GB/s"},
             "gpu_launches": launches, "host_issue_ms_per_step": host_ms, "profiled_pass_ms_per_step": prof_ms / prof_steps,

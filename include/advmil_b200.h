@@ -416,6 +416,13 @@ ADVMIL_API int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams*
 ADVMIL_API int advmil_sincos_pe(const int64_t* coord, const int32_t* offsets /* bag row offsets [bags+1], device */, int32_t bags,
                      int32_t d, const float* omega, float* pe, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- lossless 12-bit transport format of bf16 features (the packed loader that replaces dataset/PatchWSI.py:65-94 +
+ *      model_handler.py:315-316's `.cuda()`): lo[n] = sign<<7 | mantissa, hi[n/2] = two 4-bit exponent codes, table16 (HOST
+ *      pointer, code -> exponent byte, code 15 = escape), escapes (element index, exponent byte).  Decodes n elements
+ *      (n % 8 == 0) into out_bf16 exactly; see advmil_b200/dataset/codec.py for the encoder. */
+ADVMIL_API int advmil_bf16p12_decode(const uint8_t* lo, const uint8_t* hi, const uint8_t* table16_host, const int32_t* esc_idx,
+                          const uint8_t* esc_exp, int64_t n, int32_t n_esc, void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -346,3 +346,25 @@ def test_module_step_with_cluster_generator_vs_oracle_trainer():
     for k, p in G.named_parameters():
         if not k.endswith(ZERO_GRAD):
             assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
+
+
+def test_p12_transport_decodes_bit_exactly_on_the_device_and_through_the_feeder():
+    """csrc/codec.cu against the host decoder: every bf16 bit pattern class, escapes, and the DeviceFeeder path (the
+    device buffer of a p12 step equals the stored bf16 features word for word)."""
+    from advmil_b200.dataset.codec import decode_p12_device, encode_bf16_p12
+    from advmil_b200.dataset.packed import DeviceFeeder, pack_step
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2048, 1024, generator=g).to(torch.bfloat16)
+    x[0, :8] = torch.tensor([0.0, -0.0, float("inf"), float("-inf"), float("nan"), 1e-40, -3e38, 1.0]).to(torch.bfloat16)
+    x[7] = (torch.randn(1024, generator=g) * torch.logspace(-30, 30, 1024)).to(torch.bfloat16)
+    p = encode_bf16_p12(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device="cuda")
+    decode_p12_device(p.lo.cuda(), p.hi.cuda(), p.table, p.esc_idx.cuda(), p.esc_exp.cuda(), out)
+    assert torch.equal(out.cpu().view(torch.int16), x.view(torch.int16))
+    lens = [640, 16, 1040, 352]
+    bags = [torch.randn(n, 1024, generator=g) for n in lens]
+    steps = [pack_step(bags, [(0.5, 1.0)] * 4, dtype=torch.bfloat16).pack12() for _ in range(3)]
+    assert steps[0].nbytes < 0.76 * steps[0].x.numel() * 2
+    for s in DeviceFeeder(steps, device="cuda"):
+        assert torch.equal(s.bags.x.cpu().view(torch.int16), steps[0].x.view(torch.int16))
+        assert s.bags.offsets.cpu().tolist() == [0, 640, 656, 1696, 2048]

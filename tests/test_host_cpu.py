@@ -222,3 +222,22 @@ def test_packed_file_round_trip_fp32_and_bf16(tmp_path):
     assert pf.lengths == [64, 32] and pf.names == ["p0", "p1"]
     assert torch.equal(pf.bag(0), torch.cat([torch.load(f) for f in slides["p0"]]))
     assert torch.equal(pf.bag(1), torch.load(slides["p1"][0])[:32])
+
+
+def test_p12_transport_format_round_trip_is_bit_exact():
+    """dataset/codec.py: the 12-bit transport form of bf16 features decodes to the same 16-bit words for every kind of
+    value (zeros of both signs, denormals, infinities, NaN) and for matrices with more than 15 distinct exponents
+    (escapes); Gaussian features cost 12.0x bits per element."""
+    from advmil_b200.dataset.codec import decode_p12_host, encode_bf16_p12
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(512, 1024, generator=g).to(torch.bfloat16)
+    x[0, :8] = torch.tensor([0.0, -0.0, float("inf"), float("-inf"), float("nan"), 1e-40, -3e38, 1.0]).to(torch.bfloat16)
+    x[5] = (torch.randn(1024, generator=g) * torch.logspace(-30, 30, 1024)).to(torch.bfloat16)
+    p = encode_bf16_p12(x)
+    assert p.esc_idx.numel() > 0 and p.lo.numel() == x.numel() and p.hi.numel() == x.numel() // 2
+    assert torch.equal(decode_p12_host(p).view(torch.int16), x.view(torch.int16))
+    y = torch.randn(256, 1024, generator=g).to(torch.bfloat16)
+    q = encode_bf16_p12(y)
+    assert q.nbytes / (y.numel() * 2) < 0.7505 and torch.equal(decode_p12_host(q).view(torch.int16), y.view(torch.int16))
+    z = torch.relu(torch.randn(64, 1024, generator=g)).to(torch.bfloat16)          # post-ReLU features: zeros take a table entry
+    assert torch.equal(decode_p12_host(encode_bf16_p12(z)).view(torch.int16), z.view(torch.int16))
