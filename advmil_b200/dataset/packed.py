@@ -159,7 +159,7 @@ class DeviceFeeder:
         self._free = [torch.cuda.Event() for _ in range(self.depth)]
 
     def _issue(self, slot: int, st: PinnedStep) -> DeviceStep:
-        rows, C = st.x.shape
+        rows, C = (st.p12.shape if st.p12 is not None else st.x.shape)     # a p12-file step carries no host bf16 matrix
         buf = self._xbuf[slot]
         if buf is None or buf.shape[0] < rows or buf.shape[1] != C or buf.dtype != st.x.dtype:
             buf = torch.empty(rows, C, dtype=st.x.dtype, device=self.device)

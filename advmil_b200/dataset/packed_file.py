@@ -9,12 +9,16 @@ with one asynchronous H2D copy.
 
 Layout (little endian):
     0    8   magic  b"ADVMILPK"
-    8    4   version (1)          12  4  dtype (0 = float32, 1 = bfloat16)
+    8    4   version (1)          12  4  dtype (0 = float32, 1 = bfloat16, 2 = bfloat16 in the 12-bit transport form)
     16   4   C                    20  4  n_bags
     24   8   rows                 32  8  offsets_pos   40  8  labels_pos   48  8  names_pos   56  8  feats_pos
     offsets_pos : int64[n_bags + 1]       labels_pos : float32[n_bags, 2] = (t, e)
     names_pos   : utf-8, one patient id per line (may be empty)
     feats_pos   : 4096-byte aligned, rows * C elements
+    dtype 2 (dataset/codec.py; written by `write_packed(..., dtype=torch.bfloat16, transport="p12")`): at feats_pos the `lo`
+    plane uint8[rows * C], then (4096-aligned) the `hi` plane uint8[rows * C / 2], then (4096-aligned) the code table
+    uint8[16], n_esc int64, the sorted global escape indices int64[n_esc] and their exponent bytes uint8[n_esc].  One table
+    for the whole file, so the planes of any selection of bags concatenate into a step without re-encoding.
 """
 from __future__ import annotations
 
@@ -25,6 +29,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from .codec import P12
 from .packed import PinnedStep, _pin
 
 MAGIC = b"ADVMILPK"
@@ -38,9 +43,18 @@ PAGE = 4096
 
 def write_packed(path: str, bags: Iterable[torch.Tensor], labels: Sequence[Sequence[float]],
                  dtype: torch.dtype = torch.float32, names: Optional[Sequence[str]] = None,
-                 require_multiple_of: int = 16) -> Dict[str, int]:
-    """Streams `bags` ([N_i, C] tensors, e.g. the torch.cat of a patient's slides, PatchWSI.py:79) into `path`."""
+                 require_multiple_of: int = 16, transport: str = "raw") -> Dict[str, int]:
+    """Streams `bags` ([N_i, C] tensors, e.g. the torch.cat of a patient's slides, PatchWSI.py:79) into `path`.
+    transport="p12" (bf16 only) stores the lossless 12-bit form that the feeder copies to the device as is."""
     assert dtype in _DT, "features are stored as float32 or bfloat16"
+    assert transport in ("raw", "p12")
+    if transport == "p12":
+        assert dtype == torch.bfloat16, "the 12-bit transport form packs bf16 features"
+        info = write_packed(path + ".raw", bags, labels, dtype, names, require_multiple_of)
+        try:
+            return _convert_to_p12(path + ".raw", path, info)
+        finally:
+            os.remove(path + ".raw")
     labels = np.asarray(labels, dtype=np.float32).reshape(-1, 2)
     n_bags = labels.shape[0]
     names_blob = ("\n".join(names)).encode() if names is not None else b""
@@ -84,6 +98,50 @@ def write_packed(path: str, bags: Iterable[torch.Tensor], labels: Sequence[Seque
     return {"bags": n_bags, "rows": offsets[-1], "C": C, "bytes": os.path.getsize(path)}
 
 
+def _convert_to_p12(raw_path: str, path: str, info: Dict[str, int], chunk_rows: int = 1 << 15) -> Dict[str, int]:
+    """Second pass of write_packed(transport="p12"): one exponent histogram over the whole file -> one code table."""
+    src = PackedFile(raw_path)
+    C, rows = src.C, src.rows
+    assert (rows * C) % 8 == 0
+    hist = np.zeros(256, dtype=np.int64)
+    for a in range(0, rows, chunk_rows):
+        v = np.asarray(src._mm[a:a + chunk_rows]).reshape(-1)
+        hist += np.bincount(((v >> 7) & 0xFF).astype(np.uint8), minlength=256)
+    top = np.argsort(-hist, kind="stable")[:15].astype(np.uint8)
+    lut = np.full(256, 15, dtype=np.uint8)
+    lut[top] = np.arange(15, dtype=np.uint8)
+    with open(raw_path, "rb") as f:
+        head = f.read(src._feats_pos)
+    lo_pos = src._feats_pos
+    hi_pos = (lo_pos + rows * C + PAGE - 1) // PAGE * PAGE
+    tail_pos = (hi_pos + rows * C // 2 + PAGE - 1) // PAGE * PAGE
+    esc_idx, esc_exp = [], []
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        f.write(head)
+        for a in range(0, rows, chunk_rows):
+            v = np.asarray(src._mm[a:a + chunk_rows]).reshape(-1)
+            exp = ((v >> 7) & 0xFF).astype(np.uint8)
+            codes = lut[exp]
+            e = np.nonzero(codes == 15)[0]
+            esc_idx.append(e.astype(np.int64) + a * C)
+            esc_exp.append(exp[e])
+            f.seek(lo_pos + a * C)
+            f.write((((v >> 8) & 0x80) | (v & 0x7F)).astype(np.uint8).tobytes())
+            f.seek(hi_pos + a * C // 2)
+            f.write((codes[0::2] | (codes[1::2] << 4)).astype(np.uint8).tobytes())
+        ei, ee = np.concatenate(esc_idx), np.concatenate(esc_exp)
+        f.seek(tail_pos)
+        f.write(bytes(top.tolist()) + bytes(16 - len(top)))
+        f.write(struct.pack("<q", ei.size))
+        f.write(ei.tobytes())
+        f.write(ee.tobytes())
+        f.seek(12)
+        f.write(struct.pack("<I", 2))
+    os.replace(tmp, path)
+    return {**info, "bytes": os.path.getsize(path), "escapes": int(ei.size)}
+
+
 def pack_reference_layout(patient_slides: Dict[str, List[str]], labels: Dict[str, Tuple[float, float]], out_path: str,
                           dtype: torch.dtype = torch.float32, trim_to_multiple_of: int = 16) -> Dict[str, int]:
     """Converts the reference's per-slide `.pt` feature files (utils/io.py:78-101 `read_patch_data`, one [n, C] tensor per
@@ -121,11 +179,26 @@ class PackedFile:
             f.seek(npos)
             blob = f.read(fpos - npos).rstrip(b"\x00")
             self.names = blob.decode().split("\n") if blob else None
-        if int(self.offsets[-1]) != rows or os.path.getsize(path) < fpos + rows * C * (4 if dt == 0 else 2):
+        need = rows * C * 4 if dt == 0 else rows * C * 2 if dt == 1 else rows * C * 3 // 2
+        if int(self.offsets[-1]) != rows or os.path.getsize(path) < fpos + need:
             raise ValueError(f"{path}: truncated or inconsistent packed file")
         self.C, self.n_bags, self.rows, self.code = int(C), int(n_bags), int(rows), int(dt)
-        self.dtype = _TORCH[dt]
-        self._mm = np.memmap(path, dtype=_NP[dt], mode="r", offset=fpos, shape=(self.rows, self.C))
+        self._feats_pos = int(fpos)
+        self.dtype = torch.bfloat16 if dt == 2 else _TORCH[dt]
+        if dt == 2:     # 12-bit transport form: two byte planes + table + sorted global escapes
+            hi_pos = (fpos + rows * C + PAGE - 1) // PAGE * PAGE
+            tail_pos = (hi_pos + rows * C // 2 + PAGE - 1) // PAGE * PAGE
+            self._lo = np.memmap(path, dtype=np.uint8, mode="r", offset=fpos, shape=(self.rows, self.C))
+            self._hi = np.memmap(path, dtype=np.uint8, mode="r", offset=hi_pos, shape=(self.rows, self.C // 2))
+            with open(path, "rb") as f:
+                f.seek(tail_pos)
+                self._table = f.read(16)
+                n_esc = struct.unpack("<q", f.read(8))[0]
+                self._esc_idx = np.frombuffer(f.read(8 * n_esc), dtype=np.int64).copy()
+                self._esc_exp = np.frombuffer(f.read(n_esc), dtype=np.uint8).copy()
+            self._mm = None
+        else:
+            self._mm = np.memmap(path, dtype=_NP[dt], mode="r", offset=fpos, shape=(self.rows, self.C))
 
     def __len__(self) -> int:
         return self.n_bags
@@ -137,24 +210,54 @@ class PackedFile:
     def bag(self, i: int) -> torch.Tensor:
         """[N_i, C] copy of bag i in the stored dtype (what WSIPatch.__getitem__ returns as `feats`, PatchWSI.py:79)."""
         a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        if self.code == 2:
+            from .codec import decode_p12_host
+            return decode_p12_host(self._p12([i], pin=False))
         v = torch.from_numpy(np.array(self._mm[a:b]))
         return v.view(torch.bfloat16) if self.code == 1 else v
+
+    def _p12(self, indices: Sequence[int], pin: bool) -> P12:
+        """The 12-bit planes of the bags `indices`, concatenated in step order (escape indices re-based to the step)."""
+        lens = [int(self.offsets[i + 1] - self.offsets[i]) for i in indices]
+        rows = sum(lens)
+        lo, hi = torch.empty(rows * self.C, dtype=torch.uint8), torch.empty(rows * self.C // 2, dtype=torch.uint8)
+        if pin:
+            lo, hi = _pin(lo), _pin(hi)
+        lo_np, hi_np = lo.numpy().reshape(rows, self.C), hi.numpy().reshape(rows, self.C // 2)
+        ei, ee, off = [], [], 0
+        for i, n in zip(indices, lens):
+            a = int(self.offsets[i])
+            np.copyto(lo_np[off:off + n], self._lo[a:a + n])
+            np.copyto(hi_np[off:off + n], self._hi[a:a + n])
+            l, r = np.searchsorted(self._esc_idx, [a * self.C, (a + n) * self.C])
+            ei.append(self._esc_idx[l:r] - a * self.C + off * self.C)
+            ee.append(self._esc_exp[l:r])
+            off += n
+        ei = torch.from_numpy(np.concatenate(ei).astype(np.int32))
+        ee = torch.from_numpy(np.concatenate(ee).copy())
+        mk = _pin if pin else (lambda v: v)
+        return P12(lo, hi, self._table, mk(ei), mk(ee), (rows, self.C))
 
     def step(self, indices: Sequence[int], visible: Optional[Sequence[bool]] = None, pin: bool = True) -> PinnedStep:
         """The bags `indices` of one optimiser step as a pinned, packed buffer (page cache -> pinned memory, one copy)."""
         lens = [int(self.offsets[i + 1] - self.offsets[i]) for i in indices]
-        x = torch.empty(sum(lens), self.C, dtype=self.dtype)
-        if pin:
-            x = _pin(x)
-        dst = x.view(torch.int16).numpy() if self.code == 1 else x.numpy()
-        off = 0
-        for i, n in zip(indices, lens):
-            a = int(self.offsets[i])
-            np.copyto(dst[off:off + n], self._mm[a:a + n].view(np.int16) if self.code == 1 else self._mm[a:a + n])
-            off += n
+        p12 = None
+        if self.code == 2:      # the planes go to the device as stored; the bf16 matrix only exists there
+            p12 = self._p12(indices, pin)
+            x = torch.empty(0, self.C, dtype=torch.bfloat16)
+        else:
+            x = torch.empty(sum(lens), self.C, dtype=self.dtype)
+            if pin:
+                x = _pin(x)
+            dst = x.view(torch.int16).numpy() if self.code == 1 else x.numpy()
+            off = 0
+            for i, n in zip(indices, lens):
+                a = int(self.offsets[i])
+                np.copyto(dst[off:off + n], self._mm[a:a + n].view(np.int16) if self.code == 1 else self._mm[a:a + n])
+                off += n
         lab = torch.from_numpy(self.labels[list(indices)].copy())
         mk = _pin if pin else (lambda v: v)
         vis = [True] * len(lens) if visible is None else list(visible)
         return PinnedStep(x=x, lengths=lens, t=mk(lab[:, 0].contiguous()), e=mk(lab[:, 1].contiguous()),
                           idx=torch.tensor(list(indices), dtype=torch.int32),
-                          visible=mk(torch.tensor([1 if v else 0 for v in vis], dtype=torch.uint8)))
+                          visible=mk(torch.tensor([1 if v else 0 for v in vis], dtype=torch.uint8)), p12=p12)

@@ -368,3 +368,21 @@ def test_p12_transport_decodes_bit_exactly_on_the_device_and_through_the_feeder(
     for s in DeviceFeeder(steps, device="cuda"):
         assert torch.equal(s.bags.x.cpu().view(torch.int16), steps[0].x.view(torch.int16))
         assert s.bags.offsets.cpu().tolist() == [0, 640, 656, 1696, 2048]
+
+
+def test_p12_packed_file_through_the_feeder(tmp_path):
+    """A split stored in the 12-bit transport form (dataset/packed_file.py, transport="p12"): the feeder copies the planes
+    as stored and the device sees exactly the bf16 features of the raw bf16 file, step after step."""
+    from advmil_b200.dataset.packed import DeviceFeeder, group_steps
+    from advmil_b200.dataset.packed_file import PackedFile, write_packed
+    g = torch.Generator().manual_seed(13)
+    lens = [64, 320, 16, 160, 96, 48, 640, 32]
+    bags = [torch.randn(n, 1024, generator=g) for n in lens]
+    labels = [(0.1 + 0.1 * i, float(i % 2 == 0)) for i in range(len(lens))]
+    write_packed(str(tmp_path / "p12.advmil"), iter(bags), labels, dtype=torch.bfloat16, transport="p12")
+    pf = PackedFile(str(tmp_path / "p12.advmil"))
+    groups = group_steps(len(pf), 4)
+    for s, idx in zip(DeviceFeeder((pf.step(i) for i in groups), device="cuda"), groups):
+        want = torch.cat([bags[i] for i in idx]).to(torch.bfloat16)
+        assert torch.equal(s.bags.x.cpu().view(torch.int16), want.view(torch.int16))
+        assert s.t.cpu().tolist() == pytest.approx([labels[i][0] for i in idx])

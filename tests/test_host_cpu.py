@@ -241,3 +241,29 @@ def test_p12_transport_format_round_trip_is_bit_exact():
     assert q.nbytes / (y.numel() * 2) < 0.7505 and torch.equal(decode_p12_host(q).view(torch.int16), y.view(torch.int16))
     z = torch.relu(torch.randn(64, 1024, generator=g)).to(torch.bfloat16)          # post-ReLU features: zeros take a table entry
     assert torch.equal(decode_p12_host(encode_bf16_p12(z)).view(torch.int16), z.view(torch.int16))
+
+
+def test_packed_file_p12_storage_round_trip(tmp_path):
+    """write_packed(transport="p12"): one code table for the file, planes of any bag selection concatenate into a step;
+    bag() and step() reproduce the bf16 words of the raw bf16 file exactly, at 3/4 of its feature bytes."""
+    from advmil_b200.dataset.codec import decode_p12_host
+    from advmil_b200.dataset.packed_file import PackedFile, write_packed
+    g = torch.Generator().manual_seed(11)
+    lens = [64, 320, 16, 160, 96]
+    bags = [torch.randn(n, 1024, generator=g) for n in lens]
+    bags[2][3] = torch.randn(1024, generator=g) * torch.logspace(-30, 30, 1024)        # escapes inside the smallest bag
+    labels = [(0.1 * i, float(i % 2)) for i in range(len(lens))]
+    raw, p12 = str(tmp_path / "raw.advmil"), str(tmp_path / "p12.advmil")
+    write_packed(raw, iter(bags), labels, dtype=torch.bfloat16)
+    info = write_packed(p12, iter(bags), labels, dtype=torch.bfloat16, transport="p12")
+    assert info["escapes"] > 0
+    fr, fp = PackedFile(raw), PackedFile(p12)
+    assert fp.lengths == lens and fp.dtype == torch.bfloat16 and np.array_equal(fp.labels, fr.labels)
+    for i in range(len(lens)):
+        assert torch.equal(fp.bag(i).view(torch.int16), fr.bag(i).view(torch.int16))
+    sel = [3, 2, 0]
+    sp, sr = fp.step(sel, pin=False), fr.step(sel, pin=False)
+    assert sp.p12 is not None and sp.lengths == sr.lengths and sp.nbytes < 0.78 * sr.nbytes
+    assert torch.equal(decode_p12_host(sp.p12).view(torch.int16), sr.x.view(torch.int16))
+    feats = lambda path: os.path.getsize(path) - PackedFile(path)._feats_pos                  # noqa: E731
+    assert feats(p12) < 0.77 * feats(raw)
