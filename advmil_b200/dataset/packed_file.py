@@ -143,7 +143,7 @@ def _convert_to_p12(raw_path: str, path: str, info: Dict[str, int], chunk_rows: 
 
 
 def pack_reference_layout(patient_slides: Dict[str, List[str]], labels: Dict[str, Tuple[float, float]], out_path: str,
-                          dtype: torch.dtype = torch.float32, trim_to_multiple_of: int = 16) -> Dict[str, int]:
+                          dtype: torch.dtype = torch.float32, trim_to_multiple_of: int = 16, transport: str = "raw") -> Dict[str, int]:
     """Converts the reference's per-slide `.pt` feature files (utils/io.py:78-101 `read_patch_data`, one [n, C] tensor per
     slide) into one packed file: per patient the slides are concatenated in the given order (PatchWSI.py:74-79).
     trim_to_multiple_of drops the trailing rows that do not fill a 16-row region (level-1 features produced by
@@ -159,7 +159,7 @@ def pack_reference_layout(patient_slides: Dict[str, List[str]], labels: Dict[str
             yield x
 
     return write_packed(out_path, gen(), [labels[p] for p in pids], dtype=dtype, names=pids,
-                        require_multiple_of=trim_to_multiple_of)
+                        require_multiple_of=trim_to_multiple_of, transport=transport)
 
 
 class PackedFile:
