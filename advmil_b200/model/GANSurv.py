@@ -135,6 +135,18 @@ class PrjDiscriminator(nn.Module):
                                         *self.disc_params())
         return out.unsqueeze(-1)
 
+    def embed_packed(self, bags: ops.PackedBags) -> torch.Tensor:
+        """Region embedding [rows/16, d] of packed bags (net_pair_one.embedding) as its own autograd node: the embedding has
+        no dropout, so the real and the fake pairs of a D step share it (`head_packed`)."""
+        return ops.DiscEmbedFn.apply(self.config(), bags, ops.PRECISIONS[get_precision()], *self.disc_params())
+
+    def head_packed(self, bags: ops.PackedBags, emb: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """D(x, t) from a precomputed region embedding -> [bags, 1]."""
+        train = self.training
+        out = ops.DiscHeadFn.apply(self.config(), bags, emb, t.reshape(-1), train, next_dropout_seed() if train else 0,
+                                   getattr(self, "_inject_masks", None), ops.PRECISIONS[get_precision()], *self.disc_params())
+        return out.unsqueeze(-1)
+
 
 class Discriminator(PrjDiscriminator):
     """Concat discriminator (reference model/GANSurv.py:52-68): out = fc(cat[EmbedX(x), time_embed(t)]).  Same fused RLIP

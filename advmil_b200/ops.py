@@ -545,6 +545,51 @@ class DiscriminatorFn(torch.autograd.Function):
         return (None, None, None if d_t is None else d_t.reshape(ctx.t_shape), None, None, None, None) + out_grads
 
 
+class DiscEmbedFn(torch.autograd.Function):
+    """emb[R, d] = AVGPoolPatchEmbedding(packed bags) (K5+K6) as its own autograd node: several head passes over the same
+    bags (the real and the fake pairs of a D step) share one embedding, and autograd sums their d_emb before the single
+    LayerNorm/region-mean backward and weight-gradient GEMM."""
+
+    @staticmethod
+    def forward(ctx, cfg, bags, precision, *params):
+        need = any(p is not None and p.requires_grad for p in params[:4])
+        acts = disc_embed_forward(cfg, params, bags, precision, save=need)
+        ctx.cfg, ctx.bags, ctx.acts, ctx.params = cfg, bags, acts, params
+        return acts["emb"]
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        params = [None if p is None else p.detach() for p in ctx.params]
+        grads = [None if (t is None or i >= 4) else torch.empty_like(t, dtype=torch.float32) for i, t in enumerate(params)]
+        disc_embed_backward(ctx.cfg, params, ctx.bags, ctx.acts, d_emb.contiguous(), grads, accumulate=False)
+        return (None, None, None) + tuple(grads)
+
+
+class DiscHeadFn(torch.autograd.Function):
+    """out[bags] = RLIP head(emb, t): region MLP, GAPool, bag MLP, time embedding, inner product / projection; gradients
+    for emb, t and the head tensors (the embedding's own four tensors get none here)."""
+
+    @staticmethod
+    def forward(ctx, cfg, bags, emb, t, train, seed, masks, precision, *params):
+        head = disc_head_forward(cfg, params, bags, emb.detach(), t.detach(), train, seed, masks, precision)
+        ctx.cfg, ctx.bags, ctx.head, ctx.params, ctx.t_shape = cfg, bags, head, params, t.shape
+        ctx.need_param_grads = any(p is not None and p.requires_grad for p in params)
+        return head["out"].clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        cfg, bags, params = ctx.cfg, ctx.bags, [None if p is None else p.detach() for p in ctx.params]
+        dev = bags.x.device
+        d_t = torch.empty(bags.bags, dtype=torch.float32, device=dev) if ctx.needs_input_grad[3] else None
+        d_emb = torch.empty(bags.rows // 16, cfg.d, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
+        grads = None
+        if ctx.need_param_grads:
+            grads = [None if (t is None or i < 4) else torch.empty_like(t, dtype=torch.float32) for i, t in enumerate(params)]
+        disc_head_backward(cfg, params, bags, ctx.head, d_out.contiguous(), d_emb, d_t, grads, accumulate=False)
+        out_grads = tuple(grads) if grads is not None else (None,) * len(params)
+        return (None, None, d_emb, None if d_t is None else d_t.reshape(ctx.t_shape), None, None, None, None) + out_grads
+
+
 # -------------------------------------------------------------------------------------------------
 # small stage-level wrappers (used by the DeepAttMISL path, the loader tools and the kernel tests)
 # -------------------------------------------------------------------------------------------------

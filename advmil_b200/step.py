@@ -295,12 +295,13 @@ class ModuleAdvStep:
         with torch.no_grad():
             pred_d = self._generate(bags, nz_d, ext, coord)
         shared = ops.EsatFn.last_acts if G.backbone.kind == "patch" else None
+        emb = D.embed_packed(bags)          # shared by the fake and the real pairs (no dropout in the embedding)
         D._inject_masks = masks_d_fake
-        f_fake = D.forward_packed(bags, pred_d.detach()).reshape(-1)
+        f_fake = D.head_packed(bags, emb, pred_d.detach()).reshape(-1)
         f_real = None
         if n_real > 0:
             D._inject_masks = masks_d_real
-            f_real = D.forward_packed(bags, t.reshape(-1, 1)).reshape(-1)
+            f_real = D.head_packed(bags, emb, t.reshape(-1, 1)).reshape(-1)
         dis_loss = self._disc_loss(f_real, f_fake, real_mask, n_real, n_fake)
         dis_loss.backward()
         self._allreduce(self.D.grad)
@@ -340,7 +341,18 @@ def sample_inference(netG, netD, bags: ops.PackedBags, times_test_sample: int = 
                      precision: str = "fp32"):
     """MyHandler.test_model for a batch of bags (reference model/model_handler.py:598-643) from ONE backbone pass:
     y_hat [bags,1] with its own noise draw, f_fake = D(x, y_hat) [bags,1], dist_y_hat [bags,S,1] from S more draws,
-    avg_y_hat = lower median over the S draws (torch.median semantics)."""
+    avg_y_hat = lower median over the S draws (torch.median semantics).  Runs under `precision` (the discriminator module
+    reads the package-wide mode, which is restored afterwards)."""
+    from . import get_precision, set_precision
+    saved = get_precision()
+    set_precision(precision)
+    try:
+        return _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision)
+    finally:
+        set_precision(saved)
+
+
+def _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision):
     cfg, params = netG.config(), netG.gen_params()
     bags = bags.for_precision(ops.PRECISIONS[precision])
     nb, dev = bags.bags, bags.x.device

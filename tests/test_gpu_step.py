@@ -386,3 +386,41 @@ def test_p12_packed_file_through_the_feeder(tmp_path):
         want = torch.cat([bags[i] for i in idx]).to(torch.bfloat16)
         assert torch.equal(s.bags.x.cpu().view(torch.int16), want.view(torch.int16))
         assert s.t.cpu().tolist() == pytest.approx([labels[i][0] for i in idx])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cindex_and_sampled_distributions_over_447_patients(precision):
+    """configs[0]'s evaluation: MyHandler.test_model over 447 patients (NLST size), 1 + 30 generator samples per bag, lower
+    median, Harrell's C (model/model_handler.py:598-643, eval/cindex.py).  The CUDA path replays the oracle's CPU noise
+    stream; fp32 mode: every sampled time within 1e-5 and the same C-index; bf16 mode: sampled times within 2e-2 and the
+    C-index within 0.005 (north_star)."""
+    from advmil_b200 import ops
+    from advmil_b200.eval.cindex import concordance_index
+    from advmil_b200.step import sample_inference
+    P, S = 447, 30
+    rng = np.random.default_rng(21)
+    Ns = [16 * int(rng.integers(2, 12)) for _ in range(P)]
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(), 23), O.synth_state_dict(O.D_SHAPES(), 24)
+    G, D = build_G().eval(), build_D().eval()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    xs = [O.synth_bag(n, 3000 + i) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(P, 25)
+    es[0] = 1.0
+    torch.manual_seed(99)
+    res = sample_inference(G, D, ops.PackedBags.from_list([x.cuda() for x in xs]), times_test_sample=S, precision=precision)
+    torch.manual_seed(99)
+    first = torch.rand(P, 192)
+    draws = [torch.rand(P, 192) for _ in range(S)]
+    want_dist = torch.stack([O.sample_times(sdG, x, [d_[b:b + 1] for d_ in draws]) for b, x in enumerate(xs)])    # [P, S]
+    want_avg = O.lower_median(want_dist, dim=1)
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    assert_close(res["dist_y_hat"][:, :, 0].cpu(), want_dist, tol, "sampled times")
+    y_true = np.stack([ts.numpy(), es.numpy()], axis=1)
+    ci_ref = O.concordance_index(ts.numpy(), es.numpy(), want_avg.numpy())
+    ci = concordance_index(y_true, res["avg_y_hat"].cpu().numpy().reshape(-1, 1))
+    if precision == "fp32":
+        assert abs(ci - ci_ref) <= 1e-4, (ci, ci_ref)      # a median may pick the neighbouring sample where two are 1e-7 apart
+    else:
+        assert abs(ci - ci_ref) <= 0.005, (ci, ci_ref)
+    assert 0.0 <= ci <= 1.0 and first.shape == (P, 192)
