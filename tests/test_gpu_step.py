@@ -424,3 +424,46 @@ def test_cindex_and_sampled_distributions_over_447_patients(precision):
     else:
         assert abs(ci - ci_ref) <= 0.005, (ci, ci_ref)
     assert 0.0 <= ci <= 1.0 and first.shape == (P, 192)
+
+
+def test_fused_step_many_small_bags_vs_oracle_trainer():
+    """64 bags of 16..320 rows in one fused step (bags smaller than one GEMM tile, several bags per row chunk, four times
+    the benchmark's 16 bags, labelled and unlabelled mixed): fp32 mode, one D+G step with injected masks."""
+    from advmil_b200 import ops
+    from advmil_b200.step import AdvStep
+    rng = np.random.default_rng(171)
+    Ns = [16 * int(rng.integers(1, 21)) for _ in range(64)]
+    B = len(Ns)
+    sdG, sdD = O.synth_state_dict(O.G_SHAPES(), 172), O.synth_state_dict(O.D_SHAPES(), 173)
+    tr = O.CpuTrainer(sdG, sdD)
+    G, D = build_G(), build_D()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    eng = AdvStep(G, D)
+    xs = [O.synth_bag(n, 5000 + i) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(B, 174)
+    es[0] = 1.0
+    vis = [bool(v) for v in rng.uniform(size=B) < 0.6]
+    vis[0] = True
+    nd = torch.tensor(rng.uniform(size=(B, 192)), dtype=torch.float32)
+    ng = torch.tensor(rng.uniform(size=(B, 192)), dtype=torch.float32)
+    mr = [d_masks(n // 16, 128, 7000 + 10 * i) for i, n in enumerate(Ns)]
+    mf = [d_masks(n // 16, 128, 8000 + 10 * i) for i, n in enumerate(Ns)]
+    mg = [g_masks(n, 384, 384, 9000 + 10 * i) for i, n in enumerate(Ns)]
+    ref = tr.step(xs, ts, es, vis, list(nd), list(ng), mr, mf, mg)
+    out = eng.step(ops.PackedBags.from_list([x.cuda() for x in xs]), ts.cuda(), es.cuda(), torch.tensor(vis, dtype=torch.uint8).cuda(),
+                   noise_d=nd.cuda(), noise_g=ng.cuda(), masks_d_real=_cat_masks(mr, ["fc1", "ga", "gs", "fc2"]),
+                   masks_d_fake=_cat_masks(mf, ["fc1", "ga", "gs", "fc2"]), masks_g=_cat_masks(mg, ["h", "a", "b", "rho", "mlp0"]))
+    L = eng.loss_dict(out)
+    assert_close(out["pred_d"].cpu(), ref["pred_d"].reshape(-1), RTOL, "pred_d")
+    assert_close(out["pred_g"].cpu(), ref["pred_g"].reshape(-1), RTOL, "pred_g")
+    assert_close(out["f_fake_d"].cpu(), ref["fake_d"].reshape(-1), RTOL, "fake_d", atol_scale=1e-1)
+    assert_close(out["f_fake_g"].cpu(), ref["fake_g"].reshape(-1), RTOL, "fake_g", atol_scale=1e-1)
+    assert abs(L["dis_loss"] - ref["dis_loss"]) < 2e-5 and abs(L["gen_loss"] - ref["gen_loss"]) < 2e-5
+    assert abs(L["t_reg_loss"] - ref["t_reg"]) < 2e-5 and abs(L["gen_total_loss"] - ref["total"]) < 2e-5
+    for k, p in D.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdD[k].detach(), RTOL, "D param " + k, atol=8e-5 * 2e-2)
+    for k, p in G.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2e-2)
