@@ -160,7 +160,8 @@ SYMBOLS = {
 }
 
 PROF_TAGS = ["proj_fwd", "gate_fwd", "pool_fwd", "embed_fwd", "pool_gate_bwd", "bwd_data", "bwd_w_gate", "bwd_w_proj",
-             "ln_bwd", "bwd_w_embed", "colsum", "dropout", "head_fwd", "head_bwd", "gen_tail", "loss_opt", "proj_embed_fwd"]
+             "ln_bwd", "bwd_w_embed", "colsum", "dropout", "head_fwd", "head_bwd", "gen_tail", "loss_opt", "proj_embed_fwd",
+             "attn_fwd", "attn_bwd"]
 
 _lib = None
 

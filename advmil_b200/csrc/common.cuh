@@ -102,7 +102,9 @@ enum ProfTag : int {
   PROF_GEN_TAIL = 14,   // generator per-bag head fwd/bwd, small outer products, gate weight packing
   PROF_LOSS_OPT = 15,   // losses, Adam, L1 value
   PROF_PROJ_EMBED = 16, // K1 + K5/K6 fused over stacked weights (bf16 fused step)
-  PROF_NTAGS = 17
+  PROF_ATTN_FWD = 17,   // ESAT self-attention forward
+  PROF_ATTN_BWD = 18,   // ESAT self-attention backward (dQ pass + dK/dV pass)
+  PROF_NTAGS = 19
 };
 struct ProfScope {
   int tag; cudaStream_t st; void* rec;

@@ -108,7 +108,8 @@ extern "C" int advmil_esat_fwd(const AdvmilEsatParams* p, const AdvmilGenParams*
   ProfScope ps(PROF_HEAD_FWD, st);
   // encoder layer, post-norm
   ADVMIL_TRY(linear_fwd(a->emb, p->Win, p->bin, R, d, 3 * d, 0, dr.none, a->qkv, rp, st));
-  ADVMIL_TRY(mha_fwd(a->qkv, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off, a->ctx, a->lse, rp, st));
+  { ProfScope pa(PROF_ATTN_FWD, st);
+    ADVMIL_TRY(mha_fwd(a->qkv, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off, a->ctx, a->lse, rp, st)); }
   ADVMIL_TRY(linear_fwd(a->ctx, p->Wout, p->bout, R, d, d, 0, dr.sa, a->s1, rp, st));
   ADVMIL_TRY(add_ln_fwd(a->emb, a->s1, p->n1_g, p->n1_b, R, d, p->ln_eps, a->x1, st));
   ADVMIL_TRY(linear_fwd(a->x1, p->W1, p->b1, R, d, ff, 1, dr.ff1, a->f, rp, st));
@@ -209,8 +210,9 @@ extern "C" int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams*
   ADVMIL_TRY(colsum(gsa, ELEM_F32, R, d, d, g->bout, 0, csws, st));
   { BwdDataExtras ex;
     ADVMIL_TRY(bwd_data(gsa, p->Wout, R, d, d, d_ctx, ex, rp, st)); }
-  ADVMIL_TRY(mha_bwd(a->qkv, a->ctx, d_ctx, a->lse, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off,
-                     d_qkv, Dq, rp, st));
+  { ProfScope pa(PROF_ATTN_BWD, st);
+    ADVMIL_TRY(mha_bwd(a->qkv, a->ctx, d_ctx, a->lse, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off,
+                       d_qkv, Dq, rp, st)); }
   ADVMIL_TRY(bwd_weight(d_qkv, a->emb, R, 3 * d, d, g->Win, 0, bwws, rp, st));
   ADVMIL_TRY(colsum(d_qkv, ELEM_F32, R, 3 * d, 3 * d, g->bin, 0, csws, st));
   { BwdDataExtras ex;

@@ -146,13 +146,13 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference's PyTorch path; the reference is pure Python and cannot travel)
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(n_rows, bags_per_sample, steps, warmup, threads=None):
+def cpu_reference_step_time(n_rows, bags_per_sample, steps, warmup, threads=None, backbone="abmil"):
     from oracle import advmil_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    sdG = O.synth_state_dict(O.G_SHAPES(), 42)
+    sdG = O.synth_state_dict(O.G_ESAT_SHAPES() if backbone == "patch" else O.G_SHAPES(), 42)
     sdD = O.synth_state_dict(O.D_SHAPES(), 43)
-    tr = O.CpuTrainer(sdG, sdD)
+    tr = O.CpuTrainer(sdG, sdD, backbone=backbone)
     gen = torch.Generator().manual_seed(42)
     bags = [torch.randn(n_rows, C_IN, generator=gen) for _ in range(bags_per_sample)]
     ts, es = O.synth_labels(bags_per_sample, 42)
@@ -162,7 +162,7 @@ def cpu_reference_step_time(n_rows, bags_per_sample, steps, warmup, threads=None
     for it in range(warmup + steps):
         nzd = [torch.rand(1, 192) for _ in bags]
         nzg = [torch.rand(1, 192) for _ in bags]
-        gm = [O.random_g_masks(n_rows, 384, 384, gen) for _ in bags]
+        gm = None if backbone == "patch" else [O.random_g_masks(n_rows, 384, 384, gen) for _ in bags]   # ESAT: dropout-free sample
         dmr = [O.random_d_masks(n_rows // 16, 128, gen) for _ in bags]
         dmf = [O.random_d_masks(n_rows // 16, 128, gen) for _ in bags]
         t0 = time.perf_counter()
@@ -192,6 +192,150 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_esat(args, rank, world, local_rank):
+    """`--backbone patch`: the same metric for the ESAT generator (DualTrans_HS, bcb_mode patch; the reference's default
+    backbone) with the RLIP discriminator, through step.ModuleAdvStep.  Same shape, timing rules and JSON keys as the ABMIL
+    line; the roofline object is the self-attention forward kernel against the tf32 tensor peak (half the measured bf16
+    figure: MEASURED_PEAKS.json holds no tf32 number)."""
+    import contextlib
+    from types import SimpleNamespace as NS
+
+    import advmil_b200
+    from advmil_b200 import _lib, ops
+    from advmil_b200.dataset.packed import DeviceFeeder, synthetic_steps
+    from advmil_b200.model.backbone import load_backbone
+    from advmil_b200.model.GANSurv import Generator, PrjDiscriminator
+    from advmil_b200.step import ModuleAdvStep
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    torch.manual_seed(42)
+    with contextlib.redirect_stdout(sys.stderr):
+        G = Generator(384, 1, load_backbone("patch", [C_IN, 384, 384]), NS(noise=[0, 1], hops=1, noise_dist="uniform"), False, 0.6,
+                      "sigmoid").to(dev)
+        D = PrjDiscriminator(NS(in_dim=C_IN, out_dim=128, ksize=1, backbone="avgpool", dropout=0.25),
+                             NS(in_dim=1, hid_dims=[64, 128], norm=False, dropout=0.0), prj_path="x", inner_product="instance").to(dev)
+    eng = ModuleAdvStep(G, D, precision=args.precision)
+    feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    steps = synthetic_steps(args.warmup + args.steps, args.bags, args.rows, C_IN, seed=42 + rank, distinct=2, dtype=feat_dtype)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    resident = [(ops.PackedBags(st.x.to(dev), st.lengths), st.t.to(dev), st.e.to(dev), st.visible.to(dev)) for st in steps[:2]]
+    nz = torch.rand(args.bags, 192, device=dev)
+    counts = [(float(((s.e == 1) & (s.visible != 0)).sum()) * world, float(args.bags * world), float(s.visible.sum()) * world) for s in steps[:2]]
+
+    def one_step(i):
+        b, t, e, v = resident[i % 2]
+        return eng.step(b, t, e, v, noise_d=nz, noise_g=nz, global_counts=counts[i % 2])
+
+    sampler = NvmlSampler(local_rank)
+    if not sampler.ok:
+        sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    lib.advmil_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    th0 = time.perf_counter()
+    for i in range(args.steps):
+        out = one_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop(th0, time.perf_counter()) if rank == 0 else None
+    launches = int(lib.advmil_launch_count(0))
+    tms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+    ms_dev = float(tms.item())
+    value = args.bags * world * args.steps / (ms_dev / 1e3)
+    # per-kernel-class events in a separate pass
+    ntags = len(_lib.PROF_TAGS)
+    pms, pcnt = (C.c_double * ntags)(), (C.c_int64 * ntags)()
+    prof_steps = min(args.steps, 10)
+    lib.advmil_profile_enable(1)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for i in range(prof_steps):
+        one_step(i)
+    pe1.record()
+    torch.cuda.synchronize()
+    lib.advmil_profile_enable(0)
+    lib.advmil_profile_read(pms, pcnt, ntags)
+    prof_ms = pe0.elapsed_time(pe1)
+    R = args.rows // 16
+    pair_flop = 2.0 * 48 * 8 * args.bags * R * R                    # one [R, R] x 48 contraction over 8 heads and all bags
+    flop = {"attn_fwd": 2 * pair_flop, "attn_bwd": 5 * pair_flop}   # algorithmic: S, PV / S, dP, dV, dK, dQ
+    kern = {}
+    for i, tag in enumerate(_lib.PROF_TAGS):
+        if pcnt[i]:
+            avg = pms[i] / pcnt[i]
+            kern[tag] = {"ms_per_launch": avg, "launches_per_step": pcnt[i] / prof_steps, "share_of_step": pms[i] / prof_ms}
+            if tag in flop:
+                kern[tag]["tflops"] = flop[tag] / (avg * 1e-3) / 1e12
+    peaks = load_peaks()
+    roof = None
+    if "attn_fwd" in kern and args.precision != "fp32":
+        roof = {"kernel": "attn_fwd", "bound": "tensor", "achieved": kern["attn_fwd"]["tflops"], "peak": peaks["tflops"] / 2, "unit": "TFLOP/s",
+                "frac": kern["attn_fwd"]["tflops"] / (peaks["tflops"] / 2), "traffic": None,
+                "peak_source": peaks["src"] + " bf16 sustained / 2 (tf32 operands; warp-level mma.sync kernels)"}
+    # end to end: pinned host -> device every step (12-bit transport in the bf16 mode)
+    p12 = args.precision == "bf16" and args.transport == "p12"
+    if p12:
+        for st in steps[:2]:
+            st.pack12()
+    it = iter(DeviceFeeder(steps, device=dev, depth=2))
+    h2d = steps[0].nbytes
+    for i in range(args.warmup):
+        s = next(it)
+        float(eng.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)["dis_loss"])
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        s = next(it)
+        o = eng.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)
+        host = [float(o[k]) for k in ("dis_loss", "gen_loss", "t_reg_loss", "gen_total_loss")]     # device -> host read of the result
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        mean_s, best_s, threads = cpu_reference_step_time(args.rows, 1, 3, 1, backbone="patch")
+        cpu = {"value": 1.0 / mean_s, "unit": "bags/s", "cores": threads, "kind": "port",
+               "sample": f"3 steps x 1 bag of {args.rows}x1024 after 1 warm-up (D step + G step + Adam), oracle port of the ESAT path, torch CPU fp32"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+                "config": {"workload": f"AdvMIL-ESAT (bcb_mode patch: DualTrans_HS generator, RLIP discriminator) G+D step, {args.bags} "
+                                       f"synthetic bags of {args.rows}x1024 per step per GPU; D step + G step + both Adam updates",
+                           "rows_per_step_per_gpu": args.bags * args.rows, "precision_mode": args.precision,
+                           "l2": "inputs (two alternating steps of 512 MiB or more) larger than the 126 MB L2; no flush",
+                           "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
+                "e2e": {"value": args.bags * world * args.steps / (float(ems.item()) / 1e3), "unit": "bags/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 16, "transport": "p12" if p12 else "raw"},
+                "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+                "losses_last_step": dict(zip(("dis_loss", "gen_loss", "t_reg_loss", "gen_total_loss"), host))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -206,6 +350,8 @@ def main():
     ap.add_argument("--transport", default="p12", choices=["p12", "raw"],
                     help="end-to-end leg, bf16 mode: copy the features in the packed loader's lossless 12-bit transport format "
                          "(decoded on the device) or as raw bf16")
+    ap.add_argument("--backbone", default="abmil", choices=["abmil", "patch"],
+                    help="generator backbone: abmil (the benchmark's workload, C-fused AdvStep) or patch (ESAT, ModuleAdvStep)")
     ap.add_argument("--ragged", action="store_true",
                     help="configs[2] instead of configs[1]: bag lengths log-uniform in [1024, 100000] (multiples of 16)")
     args = ap.parse_args()
@@ -216,6 +362,9 @@ def main():
         run_reference(args, rank, world)
         return
     assert args.warmup >= 3, "timing rule: at least 3 warm-up steps"
+    if args.backbone == "patch":
+        run_esat(args, rank, world, local_rank)
+        return
 
     import advmil_b200
     from advmil_b200 import _lib, ops
