@@ -91,3 +91,59 @@ def test_two_rank_step_equals_single_rank():
     assert float(np.abs(g1 - g2).max()) <= 1e-5 * float(np.abs(g1).max())
     assert float(np.abs(d1 - d2).max()) <= 1e-5 * float(np.abs(d1).max())
     assert float(np.abs(l1[:4] - l2[:4]).max()) < 1e-5
+
+
+def _run_esat(rank, world, port, q):
+    """ModuleAdvStep with the ESAT generator, eval-style arithmetic (dropout probabilities zeroed) on sharded bags."""
+    from advmil_b200 import ops
+    from advmil_b200.dataset.packed import shard_bags_balanced
+    from advmil_b200.step import ModuleAdvStep
+    from oracle import advmil_oracle as O
+    from tests.util import build_D, build_G
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                             device_id=dev)
+    G, D = build_G((1024, 384, 384), mode="patch", device=dev), build_D(device=dev)
+    G.load_state_dict(O.synth_state_dict(O.G_ESAT_SHAPES(), 3))
+    D.load_state_dict(O.synth_state_dict(O.D_SHAPES(), 4))
+    G.backbone.p = G.backbone.pool.p = 0.0
+    G.p_head = 0.0
+    D.net_pair_one.p = 0.0
+    eng = ModuleAdvStep(G, D)
+    xs, t, e, vis, nd, ng = _inputs()
+    mine = shard_bags_balanced(NS, world)[rank]
+    bags = ops.PackedBags.from_list([xs[i].to(dev) for i in mine])
+    out = eng.step(bags, t[mine].to(dev), e[mine].to(dev), vis[mine].to(dev), noise_d=nd[mine].to(dev), noise_g=ng[mine].to(dev))
+    torch.cuda.synchronize()
+    losses = torch.stack([out["dis_loss"], out["gen_loss"], out["t_reg_loss"]])
+    if world > 1:
+        torch.distributed.all_reduce(losses)              # every rank holds its bags' share of the globally normalised losses
+    if rank == 0:
+        q.put((eng.G.grad.cpu().numpy(), eng.D.grad.cpu().numpy(), losses.cpu().numpy()))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_module_step_with_esat_equals_single_rank():
+    """The same check for ModuleAdvStep (ESAT generator): global-count loss normalisation + flat-buffer all-reduce give the
+    single-process gradients of both networks."""
+    ctx = mp.get_context("spawn")
+    res = {}
+    for world in (1, 2):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_run_esat, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res[world] = q.get()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+    g1, d1, l1 = res[1]
+    g2, d2, l2 = res[2]
+    assert float(np.abs(g1 - g2).max()) <= 1e-5 * float(np.abs(g1).max())
+    assert float(np.abs(d1 - d2).max()) <= 1e-5 * float(np.abs(d1).max())
+    assert float(np.abs(l1 - l2).max()) < 1e-5
