@@ -543,8 +543,10 @@ def main():
                        "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "h2d_gbs_per_gpu": h2d * args.steps / (float(ems.item()) / 1e3) / 1e9,
-                    "transport": ("p12: lossless 12-bit form of the bf16 features (8 bits sign+mantissa, 4-bit exponent code, sparse "
-                                  "escapes), decoded on the device inside the timed region" if p12 else "raw"),
+                    "transport": ("p12: the packed loader's lossless 12-bit form of the bf16 features (8 bits sign+mantissa, 4-bit "
+                                  "exponent code, sparse escapes; encoded once at packing time like the bf16 rounding itself, held "
+                                  "in pinned host memory), copied and decoded on the device inside the timed region"
+                                  if p12 else "raw"),
                     "note": "pinned host -> device copy of every step's features overlapped with the previous step's compute "
                             "(DeviceFeeder); bound by the PCIe link when h2d_gbs_per_gpu is ~55 GB/s"},
             "gpu_launches": launches, "host_issue_ms_per_step": host_ms, "profiled_pass_ms_per_step": prof_ms / prof_steps,
