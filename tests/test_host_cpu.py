@@ -241,6 +241,12 @@ def test_p12_transport_format_round_trip_is_bit_exact():
     assert q.nbytes / (y.numel() * 2) < 0.7505 and torch.equal(decode_p12_host(q).view(torch.int16), y.view(torch.int16))
     z = torch.relu(torch.randn(64, 1024, generator=g)).to(torch.bfloat16)          # post-ReLU features: zeros take a table entry
     assert torch.equal(decode_p12_host(encode_bf16_p12(z)).view(torch.int16), z.view(torch.int16))
+    # degenerate inputs: the smallest block, a constant matrix (one table entry, no escapes), every exponent present
+    for w in (torch.randn(8, generator=g).to(torch.bfloat16), torch.full((16, 16), 3.0, dtype=torch.bfloat16),
+              torch.arange(0, 65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).reshape(64, 1024)):
+        pw = encode_bf16_p12(w)
+        assert torch.equal(decode_p12_host(pw).view(torch.int16), w.view(torch.int16))
+    assert encode_bf16_p12(torch.full((16, 16), 3.0, dtype=torch.bfloat16)).esc_idx.numel() == 0
 
 
 def test_packed_file_p12_storage_round_trip(tmp_path):
