@@ -361,6 +361,11 @@ def test_p12_transport_decodes_bit_exactly_on_the_device_and_through_the_feeder(
     out = torch.empty(x.shape, dtype=torch.bfloat16, device="cuda")
     decode_p12_device(p.lo.cuda(), p.hi.cuda(), p.table, p.esc_idx.cuda(), p.esc_exp.cuda(), out)
     assert torch.equal(out.cpu().view(torch.int16), x.view(torch.int16))
+    allbits = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).reshape(64, 1024)   # every bf16 word
+    pa = encode_bf16_p12(allbits)
+    oa = torch.empty(allbits.shape, dtype=torch.bfloat16, device="cuda")
+    decode_p12_device(pa.lo.cuda(), pa.hi.cuda(), pa.table, pa.esc_idx.cuda(), pa.esc_exp.cuda(), oa)
+    assert torch.equal(oa.cpu().view(torch.int16), allbits.view(torch.int16))
     lens = [640, 16, 1040, 352]
     bags = [torch.randn(n, 1024, generator=g) for n in lens]
     steps = [pack_step(bags, [(0.5, 1.0)] * 4, dtype=torch.bfloat16).pack12() for _ in range(3)]
