@@ -519,6 +519,13 @@ __device__ __forceinline__ void mma_probs_x_values(float (&o)[HD / 8][4], const 
     for (int no = 0; no < HD / 8; ++no) mma_tf32(o[no], a, S[nt * 8 + 2 * t][no * 8 + g], S[nt * 8 + 2 * t + 1][no * 8 + g]);
   }
 }
+// 2^x on the SFU; the attention kernels keep their logits in log2 units (q is pre-scaled by log2(e) / sqrt(hd))
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 4) mha_fwd_tc_kernel(const flo
   tile_copy_async<HD, TCF_KT>(Q + 2 * d, ld, min(TCF_KT, Rb), Vt(0));
   cp_async_commit();
   uint32_t qa[HD / 8][4];
-  load_a_frags<HD>(Q, ld, q0, Rb, lane, scale, qa);
+  load_a_frags<HD>(Q, ld, q0, Rb, lane, scale * kLog2e, qa);      // logits in log2 units
   float o[HD / 8][4];
 #pragma unroll
   for (int no = 0; no < HD / 8; ++no) o[no][0] = o[no][1] = o[no][2] = o[no][3] = 0.f;
@@ -574,23 +581,28 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 4) mha_fwd_tc_kernel(const flo
     for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
     mma_rows_x_items<HD, NT>(s, qa, Kt(buf), lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (nk < TCF_KT) {                 // only the last tile of a bag has keys to mask
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int kc = nt * 8 + 2 * t;
+        if (kc >= nk) s[nt][0] = s[nt][2] = -INFINITY;
+        if (kc + 1 >= nk) s[nt][1] = s[nt][3] = -INFINITY;
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      const int kc = nt * 8 + 2 * t;
-      if (kc >= nk) s[nt][0] = s[nt][2] = -INFINITY;
-      if (kc + 1 >= nk) s[nt][1] = s[nt][3] = -INFINITY;
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
-    const float c0 = __expf(m0 - mn0), c1 = __expf(m1 - mn1);
+    const float c0 = ex2f(m0 - mn0), c1 = ex2f(m1 - mn1);
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int no = 0; no < HD / 8; ++no) { o[no][0] *= c0; o[no][1] *= c0; o[no][2] *= c1; o[no][3] *= c1; }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int kc = k0 + nt * 8 + 2 * t;
-      float p0 = __expf(s[nt][0] - mn0), p1 = __expf(s[nt][1] - mn0), p2 = __expf(s[nt][2] - mn1), p3 = __expf(s[nt][3] - mn1);
+      float p0 = ex2f(s[nt][0] - mn0), p1 = ex2f(s[nt][1] - mn0), p2 = ex2f(s[nt][2] - mn1), p3 = ex2f(s[nt][3] - mn1);
       l0 += p0 + p1; l1 += p2 + p3;
       if (ad.drop.active) {
         if (ad.mask) {
@@ -622,8 +634,8 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 4) mha_fwd_tc_kernel(const flo
     if (qi1 < Rb) *reinterpret_cast<float2*>(ctx + (size_t)(r0 + qi1) * d + head * HD + no * 8 + 2 * t) = make_float2(o[no][2] * i1, o[no][3] * i1);
   }
   if (t == 0) {
-    if (qi0 < Rb) lse[(size_t)head * Rtot + r0 + qi0] = m0 + __logf(l0);
-    if (qi1 < Rb) lse[(size_t)head * Rtot + r0 + qi1] = m1 + __logf(l1);
+    if (qi0 < Rb) lse[(size_t)head * Rtot + r0 + qi0] = m0 * kLn2 + __logf(l0);      // back to natural units
+    if (qi1 < Rb) lse[(size_t)head * Rtot + r0 + qi1] = m1 * kLn2 + __logf(l1);
   }
 }
 
@@ -652,7 +664,7 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_q_tc_kernel(const f
   cp_async_commit();
   const int qi0 = q0 + g, qi1 = q0 + g + 8;
   uint32_t qa[HD / 8][4], ga[HD / 8][4];
-  load_a_frags<HD>(Q, ld, q0, Rb, lane, scale, qa);
+  load_a_frags<HD>(Q, ld, q0, Rb, lane, scale * kLog2e, qa);      // logits in log2 units
   load_a_frags<HD>(G, d, q0, Rb, lane, 1.f, ga);
   // D_i = dO_i . O_i in full fp32 (each lane owns columns t, t+4 of every k-step; the quad completes the row)
   float D0 = 0.f, D1 = 0.f;
@@ -662,7 +674,7 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_q_tc_kernel(const f
     if (qi1 < Rb) D1 += G[(size_t)qi1 * d + ks * 8 + t] * O[(size_t)qi1 * d + ks * 8 + t] + G[(size_t)qi1 * d + ks * 8 + t + 4] * O[(size_t)qi1 * d + ks * 8 + t + 4];
   }
   D0 = quad_sum(D0); D1 = quad_sum(D1);
-  const float L0 = qi0 < Rb ? lse[(size_t)head * Rtot + r0 + qi0] : 0.f, L1 = qi1 < Rb ? lse[(size_t)head * Rtot + r0 + qi1] : 0.f;
+  const float L0 = qi0 < Rb ? lse[(size_t)head * Rtot + r0 + qi0] * kLog2e : 0.f, L1 = qi1 < Rb ? lse[(size_t)head * Rtot + r0 + qi1] * kLog2e : 0.f;
   if (t == 0) {
     if (qi0 < Rb) Dq[(size_t)head * Rtot + r0 + qi0] = D0;
     if (qi1 < Rb) Dq[(size_t)head * Rtot + r0 + qi1] = D1;
@@ -702,8 +714,8 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_q_tc_kernel(const f
           ad.drop.keep2((uint32_t)(r0 + qi1) * (uint32_t)ad.heads + (uint32_t)head, (uint32_t)kc, k10, k11);
         }
       }
-      const float p0 = kl < nk ? __expf(s[nt][0] - L0) : 0.f, p1 = kl + 1 < nk ? __expf(s[nt][1] - L0) : 0.f;
-      const float p2 = kl < nk ? __expf(s[nt][2] - L1) : 0.f, p3 = kl + 1 < nk ? __expf(s[nt][3] - L1) : 0.f;
+      const float p0 = kl < nk ? ex2f(s[nt][0] - L0) : 0.f, p1 = kl + 1 < nk ? ex2f(s[nt][1] - L0) : 0.f;
+      const float p2 = kl < nk ? ex2f(s[nt][2] - L1) : 0.f, p3 = kl + 1 < nk ? ex2f(s[nt][3] - L1) : 0.f;
       s[nt][0] = p0 * ((k00 ? dp[nt][0] * ik : 0.f) - D0); s[nt][1] = p1 * ((k01 ? dp[nt][1] * ik : 0.f) - D0);
       s[nt][2] = p2 * ((k10 ? dp[nt][2] * ik : 0.f) - D1); s[nt][3] = p3 * ((k11 ? dp[nt][3] * ik : 0.f) - D1);
     }
@@ -745,12 +757,12 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_kv_tc_kernel(const 
   float dk[HD / 8][4], dv[HD / 8][4];
 #pragma unroll
   for (int no = 0; no < HD / 8; ++no) { dk[no][0] = dk[no][1] = dk[no][2] = dk[no][3] = 0.f; dv[no][0] = dv[no][1] = dv[no][2] = dv[no][3] = 0.f; }
-  const float ik = ad.drop.inv_keep;
+  const float ik = ad.drop.inv_keep, sl2 = scale * kLog2e;
   int buf = 0;
   for (int q0 = 0; q0 < Rb; q0 += TCB_T, buf ^= 1) {
     const int nq = min(TCB_T, Rb - q0);
     if (threadIdx.x < TCB_T) {         // (this buffer's previous readers passed the barrier that ended the iteration before last)
-      Ls[buf][threadIdx.x] = (int)threadIdx.x < nq ? lse[(size_t)head * Rtot + r0 + q0 + threadIdx.x] : 0.f;
+      Ls[buf][threadIdx.x] = (int)threadIdx.x < nq ? lse[(size_t)head * Rtot + r0 + q0 + threadIdx.x] * kLog2e : 0.f;   // log2 units
       Ds[buf][threadIdx.x] = (int)threadIdx.x < nq ? Dq[(size_t)head * Rtot + r0 + q0 + threadIdx.x] : 0.f;
     }
     if (q0 + TCB_T < Rb) {
@@ -778,8 +790,8 @@ __global__ void __launch_bounds__(32 * TCA_WARPS, 3) mha_bwd_kv_tc_kernel(const 
         k10 = ad.keep(b, head, qa_, kb_, Rb, r0 + qa_); k11 = ad.keep(b, head, qb_, kb_, Rb, r0 + qb_);
       }
       const float La = Ls[buf][ql], Lb = Ls[buf][ql + 1], Da = Ds[buf][ql], Db = Ds[buf][ql + 1];
-      const float p0 = ql < nq ? __expf(fmaf(s[nt][0], scale, -La)) : 0.f, p1 = ql + 1 < nq ? __expf(fmaf(s[nt][1], scale, -Lb)) : 0.f;
-      const float p2 = ql < nq ? __expf(fmaf(s[nt][2], scale, -La)) : 0.f, p3 = ql + 1 < nq ? __expf(fmaf(s[nt][3], scale, -Lb)) : 0.f;
+      const float p0 = ql < nq ? ex2f(fmaf(s[nt][0], sl2, -La)) : 0.f, p1 = ql + 1 < nq ? ex2f(fmaf(s[nt][1], sl2, -Lb)) : 0.f;
+      const float p2 = ql < nq ? ex2f(fmaf(s[nt][2], sl2, -La)) : 0.f, p3 = ql + 1 < nq ? ex2f(fmaf(s[nt][3], sl2, -Lb)) : 0.f;
       s[nt][0] = p0 * ((k00 ? dp[nt][0] * ik : 0.f) - Da); s[nt][1] = p1 * ((k01 ? dp[nt][1] * ik : 0.f) - Db);
       s[nt][2] = p2 * ((k10 ? dp[nt][2] * ik : 0.f) - Da); s[nt][3] = p3 * ((k11 ? dp[nt][3] * ik : 0.f) - Db);
       dp[nt][0] = k00 ? p0 * ik : 0.f; dp[nt][1] = k01 ? p1 * ik : 0.f; dp[nt][2] = k10 ? p2 * ik : 0.f; dp[nt][3] = k11 ? p3 * ik : 0.f;
