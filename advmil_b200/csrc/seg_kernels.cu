@@ -313,10 +313,30 @@ constexpr int POOL_CH = 256;  // rows per pooling chunk (1024 CTAs at the benchm
 // z_c = sum exp(s - m_c) v; the final kernel rescales by exp(m_c - M).  When `sparts` is given the logits are first
 // assembled from the gate kernel's per-tile partial scores (s = sum_t sparts[t][row] + bc) and written to s.
 // grid (maxchunks, bags); threads = RG row groups x WV 16-byte vectors per row
-template <typename T>
+// 16-byte vector of T kept packed in four registers until it is consumed (the bf16 stream holds 4 rows = 16 registers in
+// flight instead of 32 unpacked floats: the register count decides how many CTAs stream per SM)
+__device__ __forceinline__ uint4 ld_raw16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+template <typename T, bool MEAN>
+__device__ __forceinline__ void acc_raw(const uint4& q, float w, float (&acc)[VecN<T>::N], float (&accm)[VecN<T>::N]) {
+  if constexpr (sizeof(T) == 4) {
+    const float x[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc[e] = fmaf(w, x[e], acc[e]); if (MEAN) accm[e] += x[e]; }
+  } else {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = __uint_as_float(u[k] << 16), hi = __uint_as_float(u[k] & 0xFFFF0000u);
+      acc[2 * k] = fmaf(w, lo, acc[2 * k]); acc[2 * k + 1] = fmaf(w, hi, acc[2 * k + 1]);
+      if (MEAN) { accm[2 * k] += lo; accm[2 * k + 1] += hi; }
+    }
+  }
+}
+
+template <typename T, bool MEAN>
 __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
     float* __restrict__ s, const float* __restrict__ sparts, int ntiles, int rows, const float* __restrict__ bc,
-    const T* __restrict__ v, const int32_t* __restrict__ offsets, int width, int want_mean,
+    const T* __restrict__ v, const int32_t* __restrict__ offsets, int width,
     float* __restrict__ cstats /*[chunk][2] = m_c, l_c*/, float* __restrict__ part /*[offsets[b]/POOL_CH + b + chunk][width]*/,
     float* __restrict__ part_mean) {
   pdl_prologue();
@@ -362,23 +382,25 @@ __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
     const T* vp = v + (size_t)beg * width + cv * VEC;
     int r = rg;
     for (; r + 3 * RG < nrows; r += 4 * RG) {
-      float x0[VEC], x1[VEC], x2[VEC], x3[VEC];
-      ldv(vp + (size_t)r * width, x0); ldv(vp + (size_t)(r + RG) * width, x1);
-      ldv(vp + (size_t)(r + 2 * RG) * width, x2); ldv(vp + (size_t)(r + 3 * RG) * width, x3);
+      const uint4 q0 = ld_raw16(vp + (size_t)r * width), q1 = ld_raw16(vp + (size_t)(r + RG) * width);
+      const uint4 q2 = ld_raw16(vp + (size_t)(r + 2 * RG) * width), q3 = ld_raw16(vp + (size_t)(r + 3 * RG) * width);
       const float w0 = w_s[r], w1 = w_s[r + RG], w2 = w_s[r + 2 * RG], w3 = w_s[r + 3 * RG];
+      if constexpr (sizeof(T) == 4) {      // fp32: the vectors are the floats themselves; four independent products per element
+        const float x0[4] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w)};
+        const float x1[4] = {__uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
+        const float x2[4] = {__uint_as_float(q2.x), __uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w)};
+        const float x3[4] = {__uint_as_float(q3.x), __uint_as_float(q3.y), __uint_as_float(q3.z), __uint_as_float(q3.w)};
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        acc[e] += w0 * x0[e] + w1 * x1[e] + w2 * x2[e] + w3 * x3[e];
-        if (want_mean) accm[e] += (x0[e] + x1[e]) + (x2[e] + x3[e]);
+        for (int e = 0; e < 4; ++e) {
+          acc[e] += w0 * x0[e] + w1 * x1[e] + w2 * x2[e] + w3 * x3[e];
+          if (MEAN) accm[e] += (x0[e] + x1[e]) + (x2[e] + x3[e]);
+        }
+      } else {
+        acc_raw<T, MEAN>(q0, w0, acc, accm); acc_raw<T, MEAN>(q1, w1, acc, accm);
+        acc_raw<T, MEAN>(q2, w2, acc, accm); acc_raw<T, MEAN>(q3, w3, acc, accm);
       }
     }
-    for (; r < nrows; r += RG) {
-      float x0[VEC];
-      ldv(vp + (size_t)r * width, x0);
-      const float w0 = w_s[r];
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) { acc[e] += w0 * x0[e]; if (want_mean) accm[e] += x0[e]; }
-    }
+    for (; r < nrows; r += RG) acc_raw<T, MEAN>(ld_raw16(vp + (size_t)r * width), w_s[r], acc, accm);
   }
   float* red = sm + POOL_CH;
   float* redm = red + (size_t)RG * width;
@@ -386,15 +408,15 @@ __global__ void __launch_bounds__(512) seg_pool_partial_kernel(
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       red[(size_t)rg * width + cv * VEC + e] = acc[e];
-      if (want_mean) redm[(size_t)rg * width + cv * VEC + e] = accm[e];
+      if (MEAN) redm[(size_t)rg * width + cv * VEC + e] = accm[e];
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float t = 0.f, tm = 0.f;
-    for (int g = 0; g < RG; ++g) { t += red[(size_t)g * width + c]; if (want_mean) tm += redm[(size_t)g * width + c]; }
+    for (int g = 0; g < RG; ++g) { t += red[(size_t)g * width + c]; if (MEAN) tm += redm[(size_t)g * width + c]; }
     part[ci * width + c] = t;
-    if (want_mean) part_mean[ci * width + c] = tm;
+    if (MEAN) part_mean[ci * width + c] = tm;
   }
 }
 
@@ -475,8 +497,8 @@ static int seg_softmax_pool_fwd_t(float* s, const float* sparts, int ntiles, con
   else if ((4 * WV) % 32 == 0 && 4 * WV <= 512) threads = 4 * WV;
   int RG = min(threads / WV, POOL_CH);
   size_t smem = (POOL_CH + (size_t)RG * width * (mean ? 2 : 1)) * sizeof(float);
-  launch_k(seg_pool_partial_kernel<T>, dim3(dim3(maxchunks, bags)), dim3(threads), smem, st, s, sparts, ntiles, rows, bc, v, offsets, width,
-                                                                        mean ? 1 : 0, cstats, part, part_mean);
+  if (mean) launch_k(seg_pool_partial_kernel<T, true>, dim3(maxchunks, bags), dim3(threads), smem, st, s, sparts, ntiles, rows, bc, v, offsets, width, cstats, part, part_mean);
+  else launch_k(seg_pool_partial_kernel<T, false>, dim3(maxchunks, bags), dim3(threads), smem, st, s, sparts, ntiles, rows, bc, v, offsets, width, cstats, part, part_mean);
   ADVMIL_CHECK_LAUNCH();
   launch_k(seg_pool_final_kernel, dim3(dim3(max(maxchunks, cdiv(width, 32)), bags)), dim3(256), 0, st, s, cstats, part, mean ? part_mean : nullptr,
                                                                                      offsets, width, w, z, mean);
