@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(256) pool_ds_kernel(const T* __restrict__ v, c
 // 16-byte loads of the tanh / sigmoid vectors, 16-byte stores of dA / dB.  Also accumulates dwc and the column sums of
 // dAB (the packed gate-bias gradient), so no separate pass over dAB is needed.
 template <typename T>
-__global__ void __launch_bounds__(256) pool_gate_bwd_kernel(
+__global__ void __launch_bounds__(256, 4) pool_gate_bwd_kernel(
     const float* __restrict__ ds_g, const T* __restrict__ ab, const float* __restrict__ wc, int rows, int D, int abw, int RGN,
     Drop da, Drop db, T* __restrict__ dAB, float* __restrict__ part /*[chunks][D+1]*/, float* __restrict__ part_b /*[chunks][abw] or null*/) {
   pdl_prologue();
