@@ -1,6 +1,7 @@
 """Import recipe for the live reference (TEST INFRASTRUCTURE, build container only).
 
-/root/reference is read-only and exists only in the build container.  Its modules import a few
+/root/reference is read-only and exists only in the build container; on the GPU box the copy staged by
+oracle/build_ref.py under oracle/_ref (git-ignored) is used instead.  Its modules import a few
 packages that are absent here (matplotlib, h5py, torch_geometric, torch_sparse) at import time only;
 empty module stubs are registered so `model.GANSurv`, `model.backbone`, `loss.utils`, `optim`,
 `eval.cindex` and `utils.func` import and run on CPU.  Nothing here is used by the
@@ -10,7 +11,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ADVMIL_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (git-ignored, ships via gpurun)
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("ADVMIL_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/model"):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = _resolve_root()
 
 
 def available() -> bool:
