@@ -142,6 +142,7 @@ SYMBOLS = {
     "advmil_cast_f32_to_bf16": (C.c_int, [_vp, _i64, _vp, _vp]),
     "advmil_dropout_mask": (C.c_int, [_u64, _i32, _f, _i32, _i32, _vp, _vp]),
     "advmil_cindex_counts": (C.c_int, [_vp, _vp, _vp, _i32, _f, _vp, _vp]),
+    "advmil_cindex_counts_f64": (C.c_int, [_vp, _vp, _vp, _i32, C.c_double, _vp, _vp]),
     "advmil_adv_step_workspace_bytes": (_sz, [_P(GenParams), _P(DiscParams), _i32, _i32, _i32]),
     "advmil_adv_step_disc": (C.c_int, [_P(StepArgs), _vp]),
     "advmil_adv_step_gen": (C.c_int, [_P(StepArgs), _vp]),

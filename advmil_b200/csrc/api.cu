@@ -151,6 +151,7 @@ extern "C" int advmil_generator_fwd(const AdvmilGenParams* p, const AdvmilBags* 
   Drop dh = Drop::make(a->mask_h, a->seed, SITE_H, p->p_backbone, a->train, p->h);
   Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train, p->h);
   Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train, p->h);
+  Drop::pair_gate(da, db);
   Drop drho = Drop::make(a->mask_rho, a->seed, SITE_RHO, p->p_backbone, a->train, p->o);
   Drop dmlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, p->p_head, a->train, p->hid);
   const int dt = elem_of_precision(a->precision);
@@ -201,6 +202,7 @@ extern "C" int advmil_generator_bwd(const AdvmilGenParams* p, const AdvmilBags* 
   const float ik_hd = (a->train && p->p_head > 0.f) ? 1.f / (1.f - p->p_head) : 1.f;
   Drop da = Drop::make(a->mask_a, a->seed, SITE_A, p->p_backbone, a->train, p->h);
   Drop db = Drop::make(a->mask_b, a->seed, SITE_B, p->p_backbone, a->train, p->h);
+  Drop::pair_gate(da, db);
   // head
   { ProfScope ps(PROF_GEN_TAIL, st);
     ADVMIL_TRY(gen_head_bwd(*p, d_pred, a->H, a->H1, a->pred, nb, ik_bb, ik_hd, dz, dHpre, dH1pre, dpre, st));
@@ -337,10 +339,11 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   Drop dfc1 = Drop::make(a->mask_fc1, a->seed, SITE_FC1, p->p, a->train, p->d / 2);
   Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train, p->d);
   Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train, p->d);
+  Drop::pair_gate(dga, dgs);
   Drop dfc2 = Drop::make(a->mask_fc2, a->seed, SITE_FC2, p->p, a->train, p->d / 2);
   Drop none = Drop::make(nullptr, 0, 0, 0.f, 0, 0);
-  // region-level tensors are fp32; outside the exact-fp32 mode their contractions run on tcgen05 kind::tf32
-  const int rp = a->precision == ADVMIL_FP32 ? ADVMIL_FP32 : ADVMIL_TF32;
+  // region-level tensors are fp32; outside the exact-fp32 mode their contractions run on the tcgen05 tf32 pipe
+  const int rp = region_precision(a->precision, a->train != 0);
   ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, rp, st));
   ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, rp, st));
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
@@ -361,7 +364,7 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   const int nb = bags->bags, d = p->d, dh = p->d / 2, R = bags->rows / 16, t1 = p->t1, t2 = p->t2;
   const int abw = gate_width(d);
   const float ik = (a->train && p->p > 0.f) ? 1.f / (1.f - p->p) : 1.f;
-  const int rp = a->precision == ADVMIL_FP32 ? ADVMIL_FP32 : ADVMIL_TF32;
+  const int rp = region_precision(a->precision, g != nullptr);
   Workspace ws(a->workspace, a->workspace_bytes);
   RegionOffsets ro;
   ADVMIL_TRY(make_region_offsets(bags, ws, st, ro));
@@ -402,6 +405,7 @@ extern "C" int advmil_disc_head_bwd(const AdvmilDiscParams* p, const AdvmilBags*
   WS_TAKE(cp_f1, float, (size_t)4 * row_chunks(R) * d);
   Drop dga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train, p->d);
   Drop dgs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train, p->d);
+  Drop::pair_gate(dga, dgs);
   ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
   ADVMIL_TRY(pool_gate_bwd(a->fi, a->attn, a->bagv, d_bagv, a->ab, p->Pc_w, ro.dev, R, nb, d, d, dga, dgs, dAB,
                            g ? g->Pc_w : dwc_scratch, g ? g->Pc_b : dwc_scratch + d, g ? dbp : nullptr, g ? accumulate : 0, pgws,
@@ -487,6 +491,7 @@ extern "C" int advmil_gated_score_fwd(const void* v, const float* Wa, const floa
   WS_TAKE(part, float, (size_t)(abw / 128) * rows);
   Drop da = Drop::make(mask_a, seed, SITE_USER + site, p_drop, train, D);
   Drop db = Drop::make(mask_b, seed, SITE_USER + site + 1, p_drop, train, D);
+  Drop::pair_gate(da, db);
   ADVMIL_TRY(gate_pack_weights(Wa, ba, Wb, bb, L, D, Wp, bp, st));
   return gated_score_fwd(v, Wp, bp, wc, bc, rows, L, D, da, db, ab, s, part, precision, st);
 }

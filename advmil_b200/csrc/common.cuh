@@ -161,6 +161,7 @@ struct Drop {          // one dropout site
   int width;           // logical row width of the dropped tensor (index of an injected mask = row * width + col)
   uint32_t key;        // per-(seed, site) 32-bit key of the counter-based generator
   uint32_t thresh16;   // an element is dropped when its 16 random bits < thresh16 (= round(p * 2^16))
+  uint32_t thresh8j;   // gate sites (Drop::pair_gate): a (tanh_j, sigmoid_j) pair is dropped when its 8 random bits < thresh8j
   __host__ static Drop make(const uint8_t* mask, uint64_t seed, int site, float p, int train, int width) {
     Drop d;
     d.mask = mask; d.seed = seed; d.site = site; d.p = p; d.width = width;
@@ -169,7 +170,19 @@ struct Drop {          // one dropout site
     d.key = (uint32_t)(mix64(seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1)) >> 32);
     double t = (double)p * 65536.0 + 0.5;
     d.thresh16 = t >= 65536.0 ? 65536u : (uint32_t)t;
+    d.thresh8j = 0;
     return d;
+  }
+  // The two dropouts of a gated-attention pair (tanh_j and sigmoid_j, reference model/backbone_utils.py:15-22) only ever act
+  // through their product: a_j b_j contributes, forward and backward, iff BOTH units are kept.  The in-kernel generator
+  // therefore draws the JOINT keep bit, Bernoulli((1-p_a)(1-p_b)) -- the same distribution as two independent draws --
+  // from 8 random bits per pair (one 32-bit draw serves 4 pairs; the joint drop probability is quantised to 2^-8:
+  // p = 0.25 -> 112/256 exactly).  Materialised masks (advmil_dropout_mask) carry the joint bit on the tanh site and
+  // all-ones on the sigmoid site.  Injected masks are used as given.
+  __host__ static void pair_gate(Drop& a, Drop& b) {
+    const double pj = 1.0 - (1.0 - (a.active ? (double)a.p : 0.0)) * (1.0 - (b.active ? (double)b.p : 0.0));
+    const double t = pj * 256.0 + 0.5;
+    a.thresh8j = b.thresh8j = t >= 256.0 ? 256u : (uint32_t)t;
   }
   // 32 random bits of the counter (row, col): 2-D multiply-xor counter + murmur3 finaliser, ~9 integer instructions.
   // One draw serves TWO elements (16 bits each; the keep probability is quantised to 2^-16, a relative bias < 2e-5):
@@ -198,8 +211,15 @@ struct Drop {          // one dropout site
   }
 };
 
-// keep bits of the (tanh_j, sigmoid_j) pair of a gated-attention row from ONE draw keyed by the tanh site
+// keep bits of the (tanh_j, sigmoid_j) pair of a gated-attention row: the joint bit of Drop::pair_gate (byte j % 4 of the
+// draw of pair group j / 4, keyed by the tanh site) when neither site has an injected mask
 __device__ __forceinline__ void gate_keep(const Drop& da, const Drop& db, uint32_t row, uint32_t j, bool& ka, bool& kb) {
+  if (!da.mask && !db.mask) {
+    const uint32_t h = da.bits(row, j & ~3u);
+    ka = ((h >> (8u * (j & 3u))) & 0xFFu) >= da.thresh8j;
+    kb = true;
+    return;
+  }
   uint32_t h = 0;
   if (!da.mask || !db.mask) h = da.bits(row, j);
   ka = da.mask ? da.mask[(size_t)row * da.width + j] != 0 : (h & 0xFFFFu) >= da.thresh16;

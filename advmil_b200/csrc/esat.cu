@@ -43,6 +43,7 @@ static EsatDrops esat_drops(const AdvmilEsatParams* p, const AdvmilGenParams* he
   d.ff2 = Drop::make(a->mask_ff2, a->seed, SITE_FF2, p->p, a->train, p->d);
   d.ga = Drop::make(a->mask_ga, a->seed, SITE_GA, p->p, a->train, p->d);
   d.gs = Drop::make(a->mask_gs, a->seed, SITE_GS, p->p, a->train, p->d);
+  Drop::pair_gate(d.ga, d.gs);
   d.mlp0 = Drop::make(a->mask_mlp0, a->seed, SITE_MLP0, head ? head->p_head : 0.f, a->train, head ? head->hid : 0);
   d.none = Drop::make(nullptr, 0, 0, 0.f, 0, 0);
   return d;
@@ -89,7 +90,7 @@ extern "C" int advmil_esat_fwd(const AdvmilEsatParams* p, const AdvmilGenParams*
   const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = p->d, ff = p->ff, C = p->C;
   const int abw = gate_width(d);
   const int dt = elem_of_precision(a->precision);
-  const int rp = a->precision == ADVMIL_FP32 ? ADVMIL_FP32 : ADVMIL_TF32;      // region-level contractions
+  const int rp = region_precision(a->precision, false);      // region-level contractions
   const EsatDrops dr = esat_drops(p, head, a);
   Workspace ws(a->workspace, a->workspace_bytes);
   ESAT_TAKE(ro, int32_t, nb + 1);
@@ -109,7 +110,7 @@ extern "C" int advmil_esat_fwd(const AdvmilEsatParams* p, const AdvmilGenParams*
   // encoder layer, post-norm
   ADVMIL_TRY(linear_fwd(a->emb, p->Win, p->bin, R, d, 3 * d, 0, dr.none, a->qkv, rp, st));
   { ProfScope pa(PROF_ATTN_FWD, st);
-    ADVMIL_TRY(mha_fwd(a->qkv, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off, a->ctx, a->lse, rp, st)); }
+    ADVMIL_TRY(mha_fwd(a->qkv, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off, a->ctx, a->lse, attention_precision(a->precision), st)); }
   ADVMIL_TRY(linear_fwd(a->ctx, p->Wout, p->bout, R, d, d, 0, dr.sa, a->s1, rp, st));
   ADVMIL_TRY(add_ln_fwd(a->emb, a->s1, p->n1_g, p->n1_b, R, d, p->ln_eps, a->x1, st));
   ADVMIL_TRY(linear_fwd(a->x1, p->W1, p->b1, R, d, ff, 1, dr.ff1, a->f, rp, st));
@@ -134,7 +135,7 @@ extern "C" int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams*
   const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = p->d, ff = p->ff, C = p->C;
   const int abw = gate_width(d);
   const int dt = elem_of_precision(a->precision);
-  const int rp = a->precision == ADVMIL_FP32 ? ADVMIL_FP32 : ADVMIL_TF32;
+  const int rp = region_precision(a->precision, false);
   const EsatDrops dr = esat_drops(p, head, a);
   const float ik = dr.sa.inv_keep;
   Workspace ws(a->workspace, a->workspace_bytes);
@@ -212,7 +213,7 @@ extern "C" int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams*
     ADVMIL_TRY(bwd_data(gsa, p->Wout, R, d, d, d_ctx, ex, rp, st)); }
   { ProfScope pa(PROF_ATTN_BWD, st);
     ADVMIL_TRY(mha_bwd(a->qkv, a->ctx, d_ctx, a->lse, ro, ro_host.data(), nb, R, d, p->nhead, dr.att, a->mask_attn, a->mask_attn_off,
-                       d_qkv, Dq, rp, st)); }
+                       d_qkv, Dq, attention_precision(a->precision), st)); }
   ADVMIL_TRY(bwd_weight(d_qkv, a->emb, R, 3 * d, d, g->Win, 0, bwws, rp, st));
   ADVMIL_TRY(colsum(d_qkv, ELEM_F32, R, 3 * d, 3 * d, g->bin, 0, csws, st));
   { BwdDataExtras ex;

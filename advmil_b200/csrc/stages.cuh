@@ -4,6 +4,23 @@
 
 namespace advmil {
 
+// Precision of the RLIP head's region-level (rows / 16) and bag-level contractions.  fp32 stays fp32 (FFMA) and the tf32
+// mode runs them on plain tf32 (the mode's definition).  The split-tf32 mode runs them on split tf32; so does the bf16
+// mode WHEN THE DISCRIMINATOR TRAINS (`exact`): its parameter gradients are sums in which real and fake pair terms cancel,
+// which amplifies plain tf32's truncation error to 3-12 % of some tensors (profiles/r02_bf16_parity.md: with split tf32 the
+// CUDA path agrees with the bf16-storage oracle to 1.4e-3 on every tensor).  These contractions are a fraction of a percent
+// of the step's FLOPs and latency-bound; the eval-mode passes (G step, inference) keep plain tf32.
+static inline int region_precision(int precision, bool exact) {
+  if (precision == ADVMIL_FP32 || precision == ADVMIL_TF32) return precision;
+  if (precision == ADVMIL_TF32X3) return ADVMIL_TF32X3;
+  return exact ? ADVMIL_TF32X3 : ADVMIL_TF32;      // bf16 mode
+}
+// ESAT self-attention: FFMA kernels in the exact modes (fp32, split tf32), warp-level tf32 tensor-core kernels otherwise
+static inline int attention_precision(int precision) {
+  return (precision == ADVMIL_FP32 || precision == ADVMIL_TF32X3) ? ADVMIL_FP32 : ADVMIL_TF32;
+}
+
+
 // ---- gemm_stages.cu ---------------------------------------------------------------------------
 // Activation tensors ([rows, *]: x, y, v, ab, y_pre, dY, dX, X, relu_src) are `const void*` / `void*`: bf16 when
 // precision == ADVMIL_BF16 (or dt == ELEM_BF16), fp32 otherwise.  Weights, biases, statistics and outputs at bag / region

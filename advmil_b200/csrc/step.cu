@@ -7,6 +7,7 @@
 //    kernel of the D phase writes both the eval activations and the G step's dropped copy (its seed is known up front);
 //  * the G step asks D only for dL/dt and never touches D-parameter gradients.
 #include <stdlib.h>
+#include <mutex>
 #include <vector>
 #include "stages.cuh"
 
@@ -63,20 +64,31 @@ struct SideState {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, done[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   const void* pending_ws[SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // workspace whose train forward was forked
-  int enabled = -1;
   int find(const void* ws) const { for (int i = 0; i < SLOTS; ++i) if (pending_ws[i] == ws) return i; return -1; }
 };
-static SideState g_side;
-static int side_init() {
-  if (g_side.enabled < 0) {
+// One side stream and event set PER DEVICE (created on the device that is current at the call, which is the device of the
+// caller's stream and workspace), guarded by a mutex: several engines, devices or host threads in one process never
+// share a stream of the wrong device or race on the slot table.
+static constexpr int MAX_DEVICES = 64;
+static SideState g_side[MAX_DEVICES];
+static std::mutex g_side_mu;
+static int g_side_enabled = -1;
+static int side_get(SideState** out) {
+  *out = nullptr;
+  if (g_side_enabled < 0) {
     const char* e = getenv("ADVMIL_STEP_OVERLAP");
-    g_side.enabled = (e && atoi(e) == 0) ? 0 : 1;
+    g_side_enabled = (e && atoi(e) == 0) ? 0 : 1;
   }
-  if (g_side.enabled && !g_side.stream) {
-    ADVMIL_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking));
-    ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
-    for (int i = 0; i < SideState::SLOTS; ++i) ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&g_side.done[i], cudaEventDisableTiming));
+  int dev = 0;
+  ADVMIL_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return ADVMIL_OK;     // no overlap on an out-of-range ordinal: the gen call runs the forward
+  SideState& s = g_side[dev];
+  if (g_side_enabled && !s.stream) {
+    ADVMIL_CHECK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    for (int i = 0; i < SideState::SLOTS; ++i) ADVMIL_CHECK_CUDA(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
   }
+  *out = &s;
   return ADVMIL_OK;
 }
 
@@ -154,8 +166,15 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   ADVMIL_TRY(take_persist(ws, gp, rows, nb, es, P));
   char* h_eval = P.h_eval;
   int32_t* offs2 = P.offs2;
-  ADVMIL_TRY(side_init());
-  { const int old = g_side.find(a->workspace); if (old >= 0) g_side.pending_ws[old] = nullptr; }   // a gen call never came
+  std::lock_guard<std::mutex> side_lock(g_side_mu);
+  SideState* side = nullptr;
+  ADVMIL_TRY(side_get(&side));
+  if (side && side->stream) {
+    // a gen call never came for this workspace (exception between the phases): the forked forward may still be reading
+    // and writing the persistent region -- the new step must not overwrite it before that forward has drained
+    const int old = side->find(a->workspace);
+    if (old >= 0) { ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(st, side->done[old], 0)); side->pending_ws[old] = nullptr; }
+  }
   // ---- generator, eval mode, detached (model_handler.py:383-387) ----
   GenBufs gb;
   if (!take_gen(ws, gp, rows, nb, gb)) { set_error("adv_step_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
@@ -187,15 +206,15 @@ extern "C" int advmil_adv_step_disc(const AdvmilStepArgs* a, void* stream) {
   ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
   if (!fused) ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &ea, stream));
   // ---- fork: the G step's train-mode generator forward runs on the side stream from here on ----
-  const int slot = g_side.find(nullptr);      // no free slot: the gen call runs the forward itself
-  if (g_side.enabled && slot >= 0 && a->gen_grads && a->pred_g && a->noise_g) {
-    ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.fork, st));
-    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(g_side.stream, g_side.fork, 0));
+  const int slot = (side && side->stream) ? side->find(nullptr) : -1;      // no free slot: the gen call runs the forward itself
+  if (g_side_enabled && slot >= 0 && a->gen_grads && a->pred_g && a->noise_g) {
+    ADVMIL_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     AdvmilGenActs gt;
     fill_train_acts(a, P, gt);
-    ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &gt, (void*)g_side.stream));
-    ADVMIL_CHECK_CUDA(cudaEventRecord(g_side.done[slot], g_side.stream));
-    g_side.pending_ws[slot] = a->workspace;
+    ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &gt, (void*)side->stream));
+    ADVMIL_CHECK_CUDA(cudaEventRecord(side->done[slot], side->stream));
+    side->pending_ws[slot] = a->workspace;
   }
   // ---- batched head over the virtual bags [fake pairs | real pairs] ----
   AdvmilHeadActs ha{};
@@ -247,11 +266,16 @@ extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
   // ---- generator, train mode, on the cached eval projection: join the side stream, or run it here ----
   AdvmilGenActs ga;
   fill_train_acts(a, P, ga);
-  const int slot = g_side.stream ? g_side.find(a->workspace) : -1;
+  std::unique_lock<std::mutex> side_lock(g_side_mu);
+  SideState* side = nullptr;
+  ADVMIL_TRY(side_get(&side));
+  const int slot = (side && side->stream) ? side->find(a->workspace) : -1;
   if (slot >= 0) {
-    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(st, g_side.done[slot], 0));
-    g_side.pending_ws[slot] = nullptr;
+    ADVMIL_CHECK_CUDA(cudaStreamWaitEvent(st, side->done[slot], 0));
+    side->pending_ws[slot] = nullptr;
+    side_lock.unlock();
   } else {
+    side_lock.unlock();
     ADVMIL_TRY(advmil_generator_fwd(&gp, bags, &ga, stream));
   }
   // ---- D(x, pred_g) with the updated discriminator, eval mode ----

@@ -855,6 +855,7 @@ extern "C" int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t
   const int role = gate_a ? 1 : gate_b ? 2 : 0;
   Drop d = Drop::make(nullptr, seed, gate_b ? site - 1 : site, p, 1, width);   // the pair is keyed by the tanh site
   Drop d2 = Drop::make(nullptr, seed, gate_b ? site : site + 1, p, 1, width);
+  if (role != 0) Drop::pair_gate(d, d2);      // joint keep bit on the tanh site, all-ones on the sigmoid site
   const size_t n = (size_t)rows * width;
   if (n == 0) return ADVMIL_OK;
   launch_k(dropout_mask_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, d, d2, role, rows, width, out);
@@ -865,21 +866,23 @@ extern "C" int advmil_dropout_mask(uint64_t seed, int32_t site, float p, int32_t
 // =============================================================================================
 // Harrell's C (eval/cindex.py:82-143): one thread per event sample i, all j; integer counts via block reduce + atomics
 // =============================================================================================
-__global__ void __launch_bounds__(256) cindex_kernel(const float* __restrict__ t, const float* __restrict__ e,
-                                                     const float* __restrict__ pred, int n, float tol,
+template <typename T>
+__global__ void __launch_bounds__(256) cindex_kernel(const T* __restrict__ t, const T* __restrict__ e,
+                                                     const T* __restrict__ pred, int n, T tol,
                                                      unsigned long long* __restrict__ counts) {
   pdl_prologue();
   __shared__ unsigned long long sm[3][8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long con = 0, tie = 0, cmp = 0;
-  if (i < n && e[i] != 0.f) {
-    const float ti = t[i], ri = -pred[i];
+  if (i < n && e[i] != (T)0) {
+    const T ti = t[i], ri = -pred[i];
     for (int j = 0; j < n; ++j) {
-      const float tj = t[j];
-      const bool comparable = (tj > ti) || (tj == ti && e[j] == 0.f);   // j == i: equal time and an event -> false
+      const T tj = t[j];
+      const bool comparable = (tj > ti) || (tj == ti && e[j] == (T)0);   // j == i: equal time and an event -> false
       if (!comparable) continue;
-      const float rj = -pred[j];
-      const bool is_tie = fabsf(rj - ri) <= tol;
+      const T rj = -pred[j];
+      const T diff = rj - ri;
+      const bool is_tie = (diff < (T)0 ? -diff : diff) <= tol;
       cmp += 1;
       tie += is_tie ? 1 : 0;
       con += (!is_tie && rj < ri) ? 1 : 0;
@@ -902,7 +905,16 @@ extern "C" int advmil_cindex_counts(const float* t, const float* e, const float*
   ADVMIL_REQUIRE(t && e && pred && counts && n >= 2, "cindex_counts: need at least two samples (eval/cindex.py:72-73)");
   cudaStream_t st = (cudaStream_t)stream;
   ADVMIL_CHECK_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), st));
-  launch_k(cindex_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, t, e, pred, n, tied_tol, (unsigned long long*)counts);
+  launch_k(cindex_kernel<float>, dim3(cdiv(n, 256)), dim3(256), 0, st, t, e, pred, n, tied_tol, (unsigned long long*)counts);
+  ADVMIL_CHECK_LAUNCH();
+  return ADVMIL_OK;
+}
+extern "C" int advmil_cindex_counts_f64(const double* t, const double* e, const double* pred, int32_t n, double tied_tol,
+                                        int64_t* counts, void* stream) {
+  ADVMIL_REQUIRE(t && e && pred && counts && n >= 2, "cindex_counts_f64: need at least two samples (eval/cindex.py:72-73)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ADVMIL_CHECK_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int64_t), st));
+  launch_k(cindex_kernel<double>, dim3(cdiv(n, 256)), dim3(256), 0, st, t, e, pred, n, tied_tol, (unsigned long long*)counts);
   ADVMIL_CHECK_LAUNCH();
   return ADVMIL_OK;
 }

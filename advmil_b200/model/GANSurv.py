@@ -45,14 +45,15 @@ class Generator(nn.Module):
     def head_params(self):
         return [self.MLPs[0][0].weight, self.MLPs[0][0].bias, self.MLPs[1][0].weight, self.MLPs[1][0].bias]
 
-    def draw_noise(self, n_bags: int, device, zero_noise: bool):
+    def draw_noise(self, n_bags: int, device, zero_noise: bool, generator=None):
         """Noise tensors in the order Generator.forward draws them (reference :33-38): one per layer with flag 1,
-        from the CPU generator (utils/func.py:154-164).  zero_noise -> None (the kernels read zeros)."""
+        from the CPU generator (utils/func.py:154-164; `generator`: a private CPU generator instead of the default
+        one, used per rank under data parallelism).  zero_noise -> None (the kernels read zeros)."""
         widths = [self.dim_in, self.MLPs[0][0].out_features]
         out = []
         for i in range(2):
             if self.noise[i] == 1 and not zero_noise:
-                out.append(generate_noise(n_bags, widths[i], to_device=device, distribution=self.noise_dist))
+                out.append(generate_noise(n_bags, widths[i], to_device=device, distribution=self.noise_dist, generator=generator))
             else:
                 out.append(None)
         return out
@@ -71,9 +72,10 @@ class Generator(nn.Module):
 
     def forward_packed(self, bags: ops.PackedBags, noise: Optional[Sequence[Optional[torch.Tensor]]] = None,
                        zero_noise: bool = False, x_grad: Optional[torch.Tensor] = None,
-                       precision: Optional[int] = None, coord=None, reuse_embedding=None) -> torch.Tensor:
+                       precision: Optional[int] = None, coord=None, reuse_embedding=None, acts_sink=None) -> torch.Tensor:
         """Packed bags -> [bags, 1].  reuse_embedding (ESAT): activations of an earlier forward over the same bags,
-        coordinates and embedding parameters (ops.EsatFn.last_acts) whose patch embedding is shared."""
+        coordinates and embedding parameters whose patch embedding is shared; acts_sink (ESAT): a list that receives this
+        forward's activation dict (what a later call passes as reuse_embedding)."""
         precision = ops.PRECISIONS[get_precision()] if precision is None else precision
         n0, n1 = noise if noise is not None else self.draw_noise(bags.bags, bags.x.device, zero_noise)
         train = self.training
@@ -82,7 +84,7 @@ class Generator(nn.Module):
             masks = getattr(self, "_inject_masks", None) if train else None
             pe = None if reuse_embedding is not None else bb.positional(bags, coord)
             pred = ops.EsatFn.apply(bb.esat_config(), self.config(), bags, pe, n0, n1, train, next_dropout_seed() if train else 0,
-                                    masks, precision, reuse_embedding, *bb.esat_params(), *self.head_params())
+                                    masks, precision, reuse_embedding, acts_sink, *bb.esat_params(), *self.head_params())
             return pred.unsqueeze(-1)
         pred = ops.GeneratorFn.apply(self.config(), bags, x_grad, n0, n1, train, next_dropout_seed() if train else 0,
                                      getattr(self, "_inject_masks", None), precision, *self.gen_params())

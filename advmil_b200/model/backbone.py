@@ -199,7 +199,7 @@ class DualTrans_HS(nn.Module):
         train = self.training
         return ops.EsatFn.apply(self.esat_config(), head, bags, self.positional(bags, coord), noise[0], noise[1], train,
                                 next_dropout_seed() if train else 0, getattr(self, "_inject_masks", None) if train else None,
-                                precision, None, *self.esat_params(), *head_params)
+                                precision, None, None, *self.esat_params(), *head_params)
 
     def forward(self, x, coord, *args):
         """x: [B, N, d], coord: the coordinates after discretization if not None -> H [1, dim_out]."""

@@ -393,13 +393,14 @@ class EsatFn(torch.autograd.Function):
     """pred[bags] (with a head) or H[bags,d] of the ESAT generator over packed bags; gradients for the 22 backbone tensors
     and the 4 head tensors.  The bag features get no gradient (they are pre-extracted inputs)."""
 
-    last_acts = None    # activations of the most recent forward (ModuleAdvStep shares the D step's embedding with the G step)
-
     @staticmethod
-    def forward(ctx, cfg, head, bags, pe, noise0, noise1, train, seed, masks, precision, reuse, *tensors):
+    def forward(ctx, cfg, head, bags, pe, noise0, noise1, train, seed, masks, precision, reuse, sink, *tensors):
+        """sink: optional list that receives this forward's activation dict (the caller that wants to share the patch
+        embedding with a later pass over the same bags -- step.ModuleAdvStep -- owns it; nothing is kept globally)."""
         params, head_params = tensors[:len(ESAT_TENSORS)], tensors[len(ESAT_TENSORS):]
         acts = esat_forward(cfg, head, params, head_params, bags, pe, noise0, noise1, train, seed, masks, precision, reuse=reuse)
-        EsatFn.last_acts = acts
+        if sink is not None:
+            sink.append(acts)
         ctx.cfg, ctx.head, ctx.bags, ctx.acts, ctx.tensors = cfg, head, bags, acts, tensors
         return (acts["pred"] if head is not None else acts["H"]).clone()
 
@@ -408,7 +409,7 @@ class EsatFn(torch.autograd.Function):
         n = len(ESAT_TENSORS)
         det = [None if t is None else t.detach() for t in ctx.tensors]
         grads, hgrads = esat_backward(ctx.cfg, ctx.head, det[:n], det[n:], ctx.bags, ctx.acts, d_out.contiguous())
-        return (None,) * 11 + tuple(grads) + tuple(hgrads)
+        return (None,) * 12 + tuple(grads) + tuple(hgrads)
 
 
 # -------------------------------------------------------------------------------------------------

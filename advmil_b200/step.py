@@ -55,6 +55,15 @@ class FlatParams:
         self.v = torch.zeros_like(self.flat)
         self.step_count = 0
 
+    def broadcast(self, group=None, src: int = 0):
+        """Data parallel: every replica starts from rank `src`'s parameters and optimiser state (a checkpoint loaded on one
+        rank only, or a different seed per rank, would otherwise make the replicas diverge silently)."""
+        for t in (self.flat, self.m, self.v):
+            torch.distributed.broadcast(t, src, group=group)
+        cnt = torch.tensor([self.step_count], dtype=torch.int64, device=self.flat.device)
+        torch.distributed.broadcast(cnt, src, group=group)
+        self.step_count = int(cnt.item())
+
     def grads_for(self, tensors: Sequence[Optional[torch.Tensor]]):
         idx = {id(t): i for i, t in enumerate(self.order)}
         return [None if t is None else self.grad_views[idx[id(t)]] for t in tensors]
@@ -68,11 +77,54 @@ class FlatParams:
                                    torch.cuda.current_stream().cuda_stream), "advmil_adam_step")
 
 
-class AdvStep:
+class _DataParallelMixin:
+    """One process per GPU; the only exchange is the all-reduce of the flat gradient buckets.  Replicas are synchronised at
+    construction (broadcast of parameters and Adam state from rank 0); every rank mixes its rank into the dropout seeds and
+    draws its generator noise from its own CPU generator, so shards do not repeat each other's masks and noise (a single
+    process keeps the default generator: the reference's stream, utils/func.py:154-164)."""
+
+    def _init_dp(self, process_group):
+        self.pg = process_group
+        self.world, self.rank = 1, 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        self._noise_gen = None
+        if self.world > 1:
+            self.G.broadcast(process_group)
+            self.D.broadcast(process_group)
+            self._noise_gen = torch.Generator().manual_seed((torch.initial_seed() + 7919 * (self.rank + 1)) % (2 ** 63))
+
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def _seed(self) -> int:
+        return next_dropout_seed() ^ (self.rank * 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+
+    def _draw(self, nb, dev):
+        """Noise for the second head layer, drawn like Generator.forward does (model/GANSurv.py:33-38)."""
+        return self.netG.draw_noise(nb, dev, False, generator=self._noise_gen)[1]
+
+    def global_losses(self, losses: torch.Tensor) -> torch.Tensor:
+        """The step's loss scalars are rank-local partial sums over GLOBAL pair counts: their sum over the ranks is the value
+        the reference prints (one small all-reduce; call it only when the values are logged)."""
+        if self.world > 1:
+            losses = losses.clone()
+            self._allreduce(losses)
+        return losses
+
+
+class AdvStep(_DataParallelMixin):
     def __init__(self, netG, netD, lr_g=8e-5, lr_d=8e-5, weight_decay_g=5e-4, coef_gan=0.004, coef_l1=1e-5,
                  loss_d="bce", recon_norm="l1", recon_alpha=0.0, recon_gamma=0.0, precision="fp32",
                  process_group=None):
-        assert netG.backbone.kind == "abmil", "the fused step covers the ABMIL generator"
+        if netG.backbone.kind != "abmil":
+            raise NotImplementedError("AdvStep is the C-fused step of the ABMIL generator; use ModuleAdvStep for bcb_mode "
+                                      f"'{netG.backbone.kind}'")
+        if list(netG.noise) != [0, 1]:
+            raise NotImplementedError(f"AdvStep covers gen_noi_noise '0-1' (config/cfg_nlst.yaml:30), got {list(netG.noise)}: noise "
+                                      "on the first head layer runs through the module path (Generator.forward / ModuleAdvStep)")
         self.netG, self.netD = netG, netD
         self.gcfg, self.dcfg = netG.config(), netD.config()
         self.gparams, self.dparams = netG.gen_params(), netD.disc_params()
@@ -84,16 +136,10 @@ class AdvStep:
         self.loss_d = {"bce": 0, "hinge": 1, "wasserstein": 2}[loss_d]
         self.recon = ({"l1": 0, "l2": 1}[recon_norm], recon_alpha, recon_gamma)
         self.precision = ops.PRECISIONS[precision]
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+        self._inflight = None
+        self._init_dp(process_group)
 
     # ---------------------------------------------------------------------------------------------
-    def _allreduce(self, t: torch.Tensor):
-        if self.world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-
     def _structs(self):
         """C views of the parameter / gradient tensors (their storage is the flat buffers and never moves)."""
         if getattr(self, "_c", None) is None:
@@ -146,9 +192,9 @@ class AdvStep:
         else:
             n_real, n_fake, n_vis = [float(v) for v in global_counts]
         if noise_d is None:
-            noise_d = G.draw_noise(nb, dev, False)[1]
+            noise_d = self._draw(nb, dev)
         if noise_g is None:
-            noise_g = G.draw_noise(nb, dev, False)[1]
+            noise_g = self._draw(nb, dev)
         noise_d, noise_g = noise_d.contiguous().float(), noise_g.contiguous().float()
         gp, dp, gg, dg = self._structs()
         ws = self._workspace(lib, gp, dp, bags.rows, nb, dev)
@@ -166,7 +212,7 @@ class AdvStep:
             setattr(a, "g_mask_" + k, ops._ptr(mg.get(k)))
         for k in ("fc1", "ga", "gs", "fc2"):
             setattr(a, "d_mask_" + k, ops._ptr(md.get(k)))
-        a.seed_d, a.seed_g = next_dropout_seed(), next_dropout_seed()
+        a.seed_d, a.seed_g = self._seed(), self._seed()
         a.n_real, a.n_fake, a.n_visible, a.loss_d = n_real, n_fake, n_vis, self.loss_d
         a.recon_norm, a.recon_alpha, a.recon_gamma = self.recon
         a.coef_gan, a.precision = self.coef_gan, self.precision
@@ -187,16 +233,21 @@ class AdvStep:
         out["f_fake_d"] = out["f_d"][:nb]
         out["f_real"] = out["f_d"][nb:] if n_real > 0 else None
         out["_keep"] = (t, e, visible, noise_d, noise_g, md, mg, bags)     # inputs stay alive until the stream is done with them
+        # pred_g / noise_g / the masks are also touched by the library's side stream (the forked train forward): the engine
+        # keeps the step's tensors until the NEXT step has been issued, by which time the main stream has joined the side
+        # stream -- a caller that drops `out` early cannot hand their memory back to the allocator under the side stream
+        self._inflight = out
         return out
 
     def loss_dict(self, out) -> Dict[str, float]:
-        """Host copy of the step's scalars (one sync): the values the handler prints (model_handler.py:413,486-494)."""
-        v = out["losses"].tolist()
+        """Host copy of the step's scalars (one sync): the values the handler prints (model_handler.py:413,486-494); under
+        data parallelism the sum over the ranks (the per-rank values are partial sums over global counts)."""
+        v = self.global_losses(out["losses"]).tolist()
         l1 = self.coef_l1 * v[4] if self.coef_l1 > 1e-8 else 0.0
         return {"dis_loss": v[0], "t_reg_loss": v[1], "gen_loss": v[2], "gen_total_loss": v[3] + l1}
 
 
-class ModuleAdvStep:
+class ModuleAdvStep(_DataParallelMixin):
     """One D update + one G update over packed bags for any built generator backbone (ABMIL, DeepAttMISL, ESAT), composed from
     the modules' packed forwards and their autograd Functions: the same step semantics as `AdvStep`
     (model/model_handler.py:349-498; global-count loss normalisation, flat parameter buffers, one all-reduce and one fused
@@ -204,7 +255,9 @@ class ModuleAdvStep:
     of `advmil_adv_step_disc/gen`.  Used for `bcb_mode: patch`; `AdvStep` remains the path for the ABMIL benchmark."""
 
     def __init__(self, netG, netD, lr_g=8e-5, lr_d=8e-5, weight_decay_g=5e-4, coef_gan=0.004, coef_l1=1e-5, loss_d="bce",
-                 recon_alpha=0.0, recon_gamma=0.0, precision="fp32", process_group=None):
+                 recon_norm="l1", recon_alpha=0.0, recon_gamma=0.0, precision="fp32", process_group=None):
+        assert recon_norm in ("l1", "l2"), recon_norm          # loss/utils.py:21-41
+        self.recon_norm = recon_norm
         self.netG, self.netD = netG, netD
         self.gparams = [p for p in netG.parameters()]
         self.dparams = [p for p in netD.parameters()]
@@ -219,14 +272,7 @@ class ModuleAdvStep:
         self.coef_gan, self.coef_l1, self.loss_d = coef_gan, coef_l1, loss_d
         self.recon_alpha, self.recon_gamma = recon_alpha, recon_gamma
         self.precision, self.precision_name = ops.PRECISIONS[precision], precision
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
-
-    def _allreduce(self, t):
-        if self.world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self._init_dp(process_group)
 
     def step(self, *args, **kwargs) -> Dict:
         """See `_step`; runs it under this engine's precision mode (the modules read the package-wide setting)."""
@@ -258,7 +304,7 @@ class ModuleAdvStep:
             raise ValueError(self.loss_d)
         return loss
 
-    def _generate(self, bags: ops.PackedBags, noise, ext, coord, reuse=None):
+    def _generate(self, bags: ops.PackedBags, noise, ext, coord, reuse=None, sink=None):
         """G over packed bags: ext = cluster ids [rows] (DeepAttMISL), coord = region coordinates [R,2] or None (ESAT).
         reuse (ESAT): activations of the D step's eval pass -- G's parameters do not change between the two passes and the
         patch embedding has no dropout, so the G step's train pass shares its x.Wc^T projection and LayerNorm stream."""
@@ -269,7 +315,7 @@ class ModuleAdvStep:
             hc = bb.cluster_rows(bags.x, ext, bags.lengths)          # [bags * clusters, h], differentiable
             # the attention stage sees num_clusters rows per bag: always the exact fp32 engine (like Generator.forward)
             return G.forward_packed(ops.PackedBags(hc, [bb.num_clusters] * bags.bags), noise=noise, x_grad=hc, precision=ops.FP32)
-        kw = {"coord": coord, "reuse_embedding": reuse} if kind == "patch" else {}
+        kw = {"coord": coord, "reuse_embedding": reuse, "acts_sink": sink} if kind == "patch" else {}
         return G.forward_packed(bags, noise=noise, precision=self.precision, **kw)
 
     def _step(self, bags: ops.PackedBags, t, e, visible, noise_d=None, noise_g=None, coord=None, global_counts=None,
@@ -286,15 +332,16 @@ class ModuleAdvStep:
             n_real, n_fake, n_vis = [float(v) for v in cnt.tolist()]
         else:
             n_real, n_fake, n_vis = [float(v) for v in global_counts]
-        nz_d = [None, noise_d] if noise_d is not None else None
-        nz_g = [None, noise_g] if noise_g is not None else None
+        nz_d = [None, noise_d if noise_d is not None else self._draw(nb, dev)]
+        nz_g = [None, noise_g if noise_g is not None else self._draw(nb, dev)]
         # ---------------- D step: D.train / G.eval (model_handler.py:355-356) ----------------
         D.train()
         G.eval()
         self.D.grad.zero_()
         with torch.no_grad():
-            pred_d = self._generate(bags, nz_d, ext, coord)
-        shared = ops.EsatFn.last_acts if G.backbone.kind == "patch" else None
+            sink = [] if G.backbone.kind == "patch" else None      # this step's own hand-off of the patch embedding
+            pred_d = self._generate(bags, nz_d, ext, coord, sink=sink)
+        shared = sink[0] if sink else None
         emb = D.embed_packed(bags)          # shared by the fake and the real pairs (no dropout in the embedding)
         D._inject_masks = masks_d_fake
         f_fake = D.head_packed(bags, emb, pred_d.detach()).reshape(-1)
@@ -318,15 +365,17 @@ class ModuleAdvStep:
             f_g = D.forward_packed(bags, pred_g).reshape(-1)
             gen_loss = -f_g.sum() / n_fake                                        # fake_generator_loss (loss/utils.py:205-208)
             pg = pred_g.reshape(-1)
-            lo = e * torch.abs(pg - t)                                            # recon_loss, l1 (loss/utils.py:21-41)
+            lo = e * torch.abs(pg - t)                                            # recon_loss (loss/utils.py:21-41)
             lc = (1.0 - e) * torch.relu(self.recon_gamma - (pg - t))
+            if self.recon_norm == "l2":
+                lo, lc = lo * lo, lc * lc
             t_reg = (vis.float() * ((1.0 - self.recon_alpha) * (lo + lc) + self.recon_alpha * lo)).sum() / max(n_vis, 1.0)
             total = t_reg + self.coef_gan * gen_loss
             total.backward()
         finally:
             for p in self.dparams:
                 p.requires_grad_(True)
-        ops.EsatFn.last_acts = None         # do not keep the step's activations alive
+        shared = sink = None                # do not keep the step's activations alive
         self._allreduce(self.G.grad)
         l1 = self.G.flat.abs().sum() if self.coef_l1 > 1e-8 else None             # value only; its gradient is in the Adam kernel
         self.G.adam(self.lr_g, weight_decay=self.wd_g, l1_coef=self.coef_l1 if self.coef_l1 > 1e-8 else 0.0)
@@ -338,27 +387,49 @@ class ModuleAdvStep:
 
 @torch.no_grad()
 def sample_inference(netG, netD, bags: ops.PackedBags, times_test_sample: int = 30, zero_noise: bool = False,
-                     precision: str = "fp32"):
-    """MyHandler.test_model for a batch of bags (reference model/model_handler.py:598-643) from ONE backbone pass:
-    y_hat [bags,1] with its own noise draw, f_fake = D(x, y_hat) [bags,1], dist_y_hat [bags,S,1] from S more draws,
-    avg_y_hat = lower median over the S draws (torch.median semantics).  Runs under `precision` (the discriminator module
-    reads the package-wide mode, which is restored afterwards)."""
+                     precision: str = "fp32", coord=None, ext=None):
+    """MyHandler.test_model for a batch of bags (reference model/model_handler.py:598-643) from ONE backbone pass, for any
+    built generator backbone: y_hat [bags,1] with its own noise draw, f_fake = D(x, y_hat) [bags,1], dist_y_hat [bags,S,1]
+    from S more draws, avg_y_hat = lower median over the S draws (torch.median semantics).  coord: region coordinates of the
+    ESAT generator (None = no positional embedding, what the handler passes, :613); ext: cluster ids per row (DeepAttMISL).
+    Runs under `precision` (the modules read the package-wide mode, which is restored afterwards)."""
     from . import get_precision, set_precision
     saved = get_precision()
     set_precision(precision)
     try:
-        return _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision)
+        return _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision, coord, ext)
     finally:
         set_precision(saved)
 
 
-def _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision):
+def _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision, coord, ext):
     cfg, params = netG.config(), netG.gen_params()
-    bags = bags.for_precision(ops.PRECISIONS[precision])
+    prec = ops.PRECISIONS[precision]
+    bags = bags.for_precision(prec)
     nb, dev = bags.bags, bags.x.device
-    n0, n1 = netG.draw_noise(nb, dev, zero_noise)
-    acts = ops.generator_forward(cfg, params, bags, n0, n1, train=False, precision=ops.PRECISIONS[precision], save=False)
-    y_hat = acts["pred"].reshape(nb, 1)
+    kind = netG.backbone.kind
+    was_training = netG.training
+    netG.eval()
+    try:
+        n0, n1 = netG.draw_noise(nb, dev, zero_noise)
+        if kind == "abmil":
+            acts = ops.generator_forward(cfg, params, bags, n0, n1, train=False, precision=prec, save=False)
+            y_hat, H = acts["pred"].reshape(nb, 1), acts["H"]
+        elif kind == "patch":          # ESAT: the bag embedding H is handed out by the forward's activation sink
+            sink = []
+            y_hat = netG.forward_packed(bags, noise=[n0, n1], precision=prec, coord=coord, acts_sink=sink).reshape(nb, 1)
+            H = sink[0]["H"]
+        elif kind == "cluster":        # DeepAttMISL: per-(bag, cluster) means, then the 8-row attention stage in fp32
+            assert ext is not None, "the cluster generator needs the cluster id of every row (ext)"
+            bb = netG.backbone
+            hc = bb.cluster_rows(bags.x, ext, bags.lengths)
+            acts = ops.generator_forward(cfg, params, ops.PackedBags(hc, [bb.num_clusters] * nb), n0, n1, train=False,
+                                         precision=ops.FP32, save=False)
+            y_hat, H = acts["pred"].reshape(nb, 1), acts["H"]
+        else:
+            raise NotImplementedError(f"sample_inference: generator backbone '{kind}'")
+    finally:
+        netG.train(was_training)
     f_fake = netD.forward_packed(bags, y_hat)
     res = {"y_hat": y_hat, "f_fake": f_fake}
     if times_test_sample > 1:
@@ -370,7 +441,7 @@ def _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision
             draws1.append(b)
         N0 = None if draws0[0] is None else torch.stack(draws0)
         N1 = None if draws1[0] is None else torch.stack(draws1)
-        ys = ops.generator_sample(cfg, params, acts["H"], N1, S, noise0=N0)      # [S, bags]
+        ys = ops.generator_sample(cfg, params, H, N1, S, noise0=N0)      # [S, bags]
         res["dist_y_hat"] = ys.transpose(0, 1).unsqueeze(-1).contiguous()        # [bags, S, 1]
         res["avg_y_hat"] = torch.median(ys, dim=0)[0].reshape(nb, 1)
     return res

@@ -8,11 +8,11 @@ import torch
 _seed_counter = itertools.count(1)
 
 
-def generate_noise(*dims, to_device="cpu", distribution="uniform"):
+def generate_noise(*dims, to_device="cpu", distribution="uniform", generator=None):
     """Same RNG stream as the reference's generate_noise (utils/func.py:154-164): Uniform(0,1)/Normal(0,1).sample
     on the CPU default generator is torch.rand / torch.randn of shape dims, then copied to the device."""
     assert distribution in ["uniform", "gaussian"]
-    data = torch.rand(*dims) if distribution == "uniform" else torch.randn(*dims)
+    data = torch.rand(*dims, generator=generator) if distribution == "uniform" else torch.randn(*dims, generator=generator)
     return data.to(to_device, non_blocking=True)
 
 

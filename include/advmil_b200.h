@@ -303,6 +303,9 @@ ADVMIL_API int advmil_abs_sum(const float* p, int64_t n, float* out, void* strea
  *      (t_j == t_i and !e_j)); concordant when pred_j > pred_i (risk = -pred), tied when |pred_i - pred_j| <= tied_tol. */
 ADVMIL_API int advmil_cindex_counts(const float* t, const float* e, const float* pred, int32_t n, float tied_tol,
                          int64_t* counts, void* stream);
+/* same in float64 (the reference counts in the caller's dtype: float64 inputs are compared as float64) */
+ADVMIL_API int advmil_cindex_counts_f64(const double* t, const double* e, const double* pred, int32_t n, double tied_tol,
+                                        int64_t* counts, void* stream);
 
 /* ---- fused adversarial step (replaces the bodies of MyHandler._update_disc / _update_gen, model/model_handler.py:349-498,
  *      for one optimiser step of `bags`; the Adam updates and the data-parallel gradient all-reduce stay with the caller,
