@@ -222,7 +222,7 @@ __device__ __forceinline__ void store_rows_bf16(uint8_t* stgb, const float (&v)[
 template <bool FAST, int MODE>
 __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], const float* __restrict__ cba,
                                             const float* __restrict__ cbb, const float* __restrict__ cwc, const Drop& da,
-                                            const Drop& db, uint32_t row, uint32_t j0, float partial) {
+                                            const Drop& db, uint32_t row, uint32_t j0, float partial, bool row_valid = true) {
   const uint32_t rowterm = row * 0x9E3779B1u, tj = da.thresh8j, key = da.key;
 #pragma unroll
   for (int i0 = 0; i0 < 32; i0 += 4) {
@@ -246,8 +246,8 @@ __device__ __forceinline__ float gate_chunk(float (&va)[32], float (&vb)[32], co
         if (MODE == 1) {
           keep = ((x >> (8 * k)) & 0xFFu) >= tj;
         } else {
-          bool ka, kb;
-          gate_keep(da, db, row, j0 + i, ka, kb);
+          bool ka = false, kb = false;
+          if (row_valid) gate_keep(da, db, row, j0 + i, ka, kb);      // rows past M of the last tile have no mask entries
           keep = ka && kb;
         }
         vb[i] = keep ? b : -b;
@@ -928,7 +928,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (q == PCW - 1) { release_acc(&tempty[acc]); }
           if (!train) partial = gate_chunk<FAST, 0>(va, vb, cf, cf + 32, cf + 64, ea.drop_a, ea.drop_b, m_row, j0, partial);
           else if (!masked) partial = gate_chunk<FAST, 1>(va, vb, cf, cf + 32, cf + 64, ea.drop_a, ea.drop_b, m_row, j0, partial);
-          else partial = gate_chunk<FAST, 2>(va, vb, cf, cf + 32, cf + 64, ea.drop_a, ea.drop_b, m_row, j0, partial);
+          else partial = gate_chunk<FAST, 2>(va, vb, cf, cf + 32, cf + 64, ea.drop_a, ea.drop_b, m_row, j0, partial, m_row < M);
           if constexpr (sizeof(T) == 2) {
             if (ea.ab) {
               store_rows_bf16(reinterpret_cast<uint8_t*>(stg), va, reinterpret_cast<bf16*>(ea.ab), ea.ldo, m_base, M, n0 + ca, lane);
@@ -1255,27 +1255,38 @@ static int pick_block_n(int N) {
 static int kblk_of(int dt) { return dt == ELEM_BF16 ? TcElem<bf16>::KBLK : TcElem<float>::KBLK; }
 
 // library-owned, grow-only scratch for operand copies of the (small) weights: bf16 conversions, W^T and the split-tf32
-// parts.  At most a few MB per device; the "no allocation" rule of the ABI is about activations.  One slot per use so that
-// two operands of one call never alias; reuse across calls is ordered by the stream.  Slots are kept PER DEVICE (the
-// device current at the call, i.e. the device of the caller's stream) and the table is guarded by a mutex.
+// parts.  At most a few MB per device; the "no allocation" rule of the ABI is about activations.  One buffer per
+// (device, STREAM, use): two operands of one call never alias, reuse along one stream is ordered by that stream, and the
+// fused step's side stream (the G step's train forward, which overlaps the D phase's head chain on the caller's stream)
+// never shares a buffer with the main stream -- a shared slot would let one stream overwrite, or a growing reallocation
+// free, weights that a kernel of the other stream is still reading.  Growing a buffer synchronises its own stream first.
 enum WSlot : int { WS_LINEAR = 0, WS_GATE = 1, WS_EMBED = 2, WS_BWD_T = 3, WS_NSLOTS = 4 };
 static int weight_scratch(int slot, size_t bytes, cudaStream_t st, void** out) {
-  constexpr int MAX_DEV = 64;
-  static void* buf[MAX_DEV][WS_NSLOTS] = {};
-  static size_t cap[MAX_DEV][WS_NSLOTS] = {};
+  struct Entry { int dev; cudaStream_t st; int slot; void* buf; size_t cap; };
+  constexpr int MAX_ENTRIES = 256;
+  static Entry tab[MAX_ENTRIES];
+  static int n = 0;
   static std::mutex mu;
   int dev = 0;
   ADVMIL_CHECK_CUDA(cudaGetDevice(&dev));
-  ADVMIL_REQUIRE(dev >= 0 && dev < MAX_DEV, "weight_scratch: device ordinal %d out of range", dev);
   std::lock_guard<std::mutex> lock(mu);
-  if (bytes > cap[dev][slot]) {
-    ADVMIL_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (buf[dev][slot]) cudaFree(buf[dev][slot]);
-    buf[dev][slot] = nullptr; cap[dev][slot] = 0;
-    ADVMIL_CHECK_CUDA(cudaMalloc(&buf[dev][slot], bytes));
-    cap[dev][slot] = bytes;
+  Entry* e = nullptr;
+  for (int i = 0; i < n; ++i)
+    if (tab[i].dev == dev && tab[i].st == st && tab[i].slot == slot) { e = &tab[i]; break; }
+  if (!e) {
+    ADVMIL_REQUIRE(n < MAX_ENTRIES, "weight_scratch: more than %d (device, stream, use) combinations", MAX_ENTRIES);
+    e = &tab[n++];
+    *e = Entry{dev, st, slot, nullptr, 0};
   }
-  *out = buf[dev][slot];
+  if (bytes > e->cap) {
+    ADVMIL_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (e->buf) cudaFree(e->buf);
+    e->buf = nullptr; e->cap = 0;
+    const size_t want = bytes + bytes / 2;                 // headroom: fewer reallocations when shapes vary
+    ADVMIL_CHECK_CUDA(cudaMalloc(&e->buf, want));
+    e->cap = want;
+  }
+  *out = e->buf;
   return ADVMIL_OK;
 }
 

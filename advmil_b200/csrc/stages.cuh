@@ -6,10 +6,11 @@ namespace advmil {
 
 // Precision of the RLIP head's region-level (rows / 16) and bag-level contractions.  fp32 stays fp32 (FFMA) and the tf32
 // mode runs them on plain tf32 (the mode's definition).  The split-tf32 mode runs them on split tf32; so does the bf16
-// mode WHEN THE DISCRIMINATOR TRAINS (`exact`): its parameter gradients are sums in which real and fake pair terms cancel,
-// which amplifies plain tf32's truncation error to 3-12 % of some tensors (profiles/r02_bf16_parity.md: with split tf32 the
-// CUDA path agrees with the bf16-storage oracle to 1.4e-3 on every tensor).  These contractions are a fraction of a percent
-// of the step's FLOPs and latency-bound; the eval-mode passes (G step, inference) keep plain tf32.
+// mode in the FORWARD pass of a training discriminator (`exact`): the discriminator's parameter gradients are sums in which
+// real and fake pair terms cancel, which amplifies the error of the forward outputs f (through dL/df) -- with plain tf32
+// (operands truncated to 10 mantissa bits) some tensors were 3-12 % off the bf16-storage oracle, with split tf32 every
+// tensor agrees with it to 1.4e-3 (profiles/r02_bf16_parity.md).  These contractions are a fraction of a percent of the
+// step's FLOPs and latency-bound; the backward contractions and the eval-mode passes (G step, inference) keep plain tf32.
 static inline int region_precision(int precision, bool exact) {
   if (precision == ADVMIL_FP32 || precision == ADVMIL_TF32) return precision;
   if (precision == ADVMIL_TF32X3) return ADVMIL_TF32X3;

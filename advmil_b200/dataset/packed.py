@@ -58,6 +58,43 @@ class PinnedStep:
         return self
 
 
+def bind_host_to_gpu(device_index: int, ranks_on_node: int = 1, local_rank: int = 0) -> dict:
+    """Pins the calling process to the CPU cores of the NUMA node its GPU hangs off (NVML's ideal CPU affinity) BEFORE any
+    pinned staging buffer is allocated: with the kernel's first-touch policy the pinned arena then lives in the memory
+    that is local to the GPU's PCIe root, instead of wherever the launcher happened to start the rank.  Without this,
+    eight ranks of one node read their features out of one socket's memory (round 1: 22 GB/s per GPU at N = 8 against 55
+    GB/s alone).  When several ranks share a node's core set the set is split evenly between them.  Returns what it did;
+    never raises (a box without NVML / sched_setaffinity keeps the inherited affinity)."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip() != ""]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return info
+        # ranks whose GPUs share this core set split it (same NVML mask => same set): contiguous slices by local rank
+        share = max(1, min(ranks_on_node, len(allowed)))
+        per = max(1, len(allowed) // share)
+        k = local_rank % share
+        mine = allowed[k * per:(k + 1) * per] if share > 1 else allowed
+        os.sched_setaffinity(0, mine or allowed)
+        info.update(bound=True, cpus=len(mine or allowed), first_cpu=(mine or allowed)[0], numa_cpus=len(allowed))
+    except Exception as ex:       # noqa: BLE001
+        info["error"] = str(ex)[:120]
+    return info
+
+
 def _pin(t: torch.Tensor) -> torch.Tensor:
     try:
         return t.pin_memory()

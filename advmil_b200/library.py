@@ -1,0 +1,257 @@
+"""torch.library registration of the hot-path operators (namespace `advmil_b200`).
+
+The reference's "FFI" for this path is the nn.Module surface; north_star asks for the kernels to sit behind thin
+torch.library / C-ABI custom ops.  The C ABI is `libadvmil_b200.so` (ctypes, `_lib.py`); this module registers the two
+operators the drop-in modules call -- the packed generator and the packed discriminator, forward and backward -- as
+`torch.library.custom_op`s with
+
+  * a CUDA implementation that calls the C ABI (through the same `ops.generator_forward` / `ops.disc_*` glue),
+  * a fake (meta) implementation that only computes output shapes, so FakeTensor tracing / `torch.compile` /
+    `torch.export` of code that calls the modules sees ordinary operators with known shapes,
+  * `register_autograd`: the backward is itself a registered operator (`*_bwd`), gradients flow to the parameters, the
+    noise-conditioned prediction t (discriminator) and, in the fp32/tf32 modes, the bag rows (generator, optional).
+
+Schema conventions: packed bags are (x [rows, C], offsets int32 [bags+1] on the device, lengths int[]); configuration
+is an int[] + float[] pair (see `_gen_cfg` / `_disc_cfg`); parameters travel as `Tensor?[]` in the C ABI's tensor order
+(`_lib.GEN_TENSORS` / `_lib.DISC_TENSORS`); injected dropout masks (parity tests) as `Tensor?[]`.
+
+`ops.GeneratorFn` / `ops.DiscriminatorFn` (autograd.Function) remain for the ESAT and DeepAttMISL paths and as the
+implementation the operators are checked against (tests/test_gpu_library.py)."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+
+_GEN_MASKS = ("h", "a", "b", "rho", "mlp0")
+_DISC_MASKS = ("fc1", "ga", "gs", "fc2")
+_GEN_SAVED = ("h", "ab", "s", "w", "z", "H", "H1", "pre", "pred")
+_HEAD_SAVED = ("f1", "fi", "ab", "rep", "attn", "bagv", "fbar", "g1", "hx", "u1", "ht", "out")
+
+
+def _gen_cfg(icfg: Sequence[int], fcfg: Sequence[float]) -> ops.GenConfig:
+    C, h, o, hid, n0, n1, scale, has_rho = [int(v) for v in icfg]
+    return ops.GenConfig(C=C, h=h, o=o, hid=hid, noise0=n0, noise1=n1, out_scale=scale, p_backbone=float(fcfg[0]),
+                         p_head=float(fcfg[1]), has_rho=bool(has_rho))
+
+
+def gen_cfg_lists(cfg: ops.GenConfig):
+    return ([cfg.C, cfg.h, cfg.o, cfg.hid, cfg.noise0, cfg.noise1, cfg.out_scale, int(cfg.has_rho)], [cfg.p_backbone, cfg.p_head])
+
+
+def _disc_cfg(icfg: Sequence[int], fcfg: Sequence[float]) -> ops.DiscConfig:
+    C, d, t1, t2, inner, prj = [int(v) for v in icfg]
+    return ops.DiscConfig(C=C, d=d, t1=t1, t2=t2, inner_instance=inner, prj_path=prj, p=float(fcfg[0]), ln_eps=float(fcfg[1]))
+
+
+def disc_cfg_lists(cfg: ops.DiscConfig):
+    return ([cfg.C, cfg.d, cfg.t1, cfg.t2, cfg.inner_instance, cfg.prj_path], [cfg.p, cfg.ln_eps])
+
+
+def _masks(names, masks: Sequence[Optional[Tensor]]):
+    return {k: m for k, m in zip(names, masks) if m is not None and m.numel()}
+
+
+def _opt(ts: Sequence[Optional[Tensor]]):
+    """Placeholders (0 elements) back to None."""
+    return [None if (t is None or t.numel() == 0) else t for t in ts]
+
+
+def _dense(ts: Sequence[Optional[Tensor]], like: Tensor):
+    """Absent tensors -> 0-element placeholders.  torch.library's autograd glue treats a list argument that holds a None
+    as an opaque leaf (no gradients flow into ANY of its tensors, and the backward must return a bare None for it); a list
+    of tensors only is flattened and differentiated element-wise.  So the parameter and mask lists always travel dense."""
+    return [like.new_empty(0, dtype=torch.float32) if t is None else t for t in ts]
+
+
+def _act(precision: int):
+    return ops.act_dtype(precision)
+
+
+# =====================================================================================================
+# generator
+# =====================================================================================================
+@torch.library.custom_op("advmil_b200::generator_fwd", mutates_args=(), device_types="cuda")
+def generator_fwd(x: Tensor, offsets: Tensor, lengths: List[int], icfg: List[int], fcfg: List[float], noise0: Optional[Tensor],
+                  noise1: Optional[Tensor], train: bool, seed: int, precision: int, save: bool, masks: List[Tensor],
+                  params: List[Tensor]) -> List[Tensor]:
+    """-> [out [bags] (pred, or H [bags, o] without a head), h, ab, s, w, z, H, H1, pre, pred] (ab empty unless `save`)."""
+    cfg = _gen_cfg(icfg, fcfg)
+    params = _opt(params)
+    bags = ops.PackedBags(x, lengths, offsets=offsets)
+    acts = ops.generator_forward(cfg, params, bags, noise0, noise1, train, seed, _masks(_GEN_MASKS, masks), precision, save=save)
+    head = params[_lib.GEN_TENSORS.index("W0")] is not None
+    out = (acts["pred"] if head else acts["H"]).clone()
+    saved = [acts[k] if acts[k] is not None else x.new_empty(0) for k in _GEN_SAVED]
+    return [out] + saved
+
+
+@generator_fwd.register_fake
+def _(x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, save, masks, params):
+    cfg = _gen_cfg(icfg, fcfg)
+    params = _opt(params)
+    rows, nb = x.shape[0], len(lengths)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    act = dict(dtype=_act(precision), device=x.device)
+    abw = 128 * ((cfg.h + 63) // 64)
+    head = params[_lib.GEN_TENSORS.index("W0")] is not None
+    out = torch.empty(nb, **f32) if head else torch.empty(nb, cfg.o, **f32)
+    return [out, torch.empty(rows, cfg.h, **act), torch.empty((rows, abw) if save else (0,), **act), torch.empty(rows, **f32),
+            torch.empty(rows, **f32), torch.empty(nb, cfg.h, **f32), torch.empty(nb, cfg.o, **f32),
+            torch.empty(nb, max(cfg.hid, 1), **f32), torch.empty(nb, **f32), torch.empty(nb, **f32)]
+
+
+@torch.library.custom_op("advmil_b200::generator_bwd", mutates_args=(), device_types="cuda")
+def generator_bwd(x: Tensor, offsets: Tensor, lengths: List[int], icfg: List[int], fcfg: List[float], noise0: Optional[Tensor],
+                  noise1: Optional[Tensor], train: bool, seed: int, precision: int, masks: List[Tensor],
+                  params: List[Tensor], saved: List[Tensor], d_out: Tensor, need_dx: bool) -> List[Tensor]:
+    """-> gradients of the 14 generator tensors (empty for absent ones) + dx (empty unless need_dx)."""
+    cfg = _gen_cfg(icfg, fcfg)
+    params = _opt(params)
+    bags = ops.PackedBags(x, lengths, offsets=offsets)
+    acts = {k: (v if v.numel() else None) for k, v in zip(_GEN_SAVED, saved)}
+    acts.update(noise0=None if noise0 is None else ops._f32c(noise0), noise1=None if noise1 is None else ops._f32c(noise1),
+                h_eval=None, masks=_masks(_GEN_MASKS, masks), seed=int(seed), train=bool(train), precision=int(precision))
+    grads, dx = ops.generator_backward(cfg, [None if p is None else p.detach() for p in params], bags, acts, d_out.contiguous(),
+                                       need_dx=need_dx)
+    return [g if g is not None else x.new_empty(0, dtype=torch.float32) for g in grads] + [dx if dx is not None else x.new_empty(0)]
+
+
+@generator_bwd.register_fake
+def _(x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks, params, saved, d_out, need_dx):
+    return [torch.empty_like(p, dtype=torch.float32) for p in params] + \
+           [torch.empty_like(x) if need_dx else x.new_empty(0)]
+
+
+def _gen_setup(ctx, inputs, output):
+    (x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, save, masks, params) = inputs
+    ctx.args = (offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks)
+    ctx.x, ctx.params, ctx.saved = x, params, list(output[1:])
+    ctx.mask_grads = [None] * len(masks)
+    ctx.need_dx = bool(x.requires_grad)
+
+
+def _gen_backward(ctx, grads):
+    offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks = ctx.args
+    d_out = grads[0]
+    res = generator_bwd(ctx.x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks, ctx.params, ctx.saved,
+                        d_out.contiguous(), ctx.need_dx)
+    n = len(ctx.params)
+    pg = [res[i].reshape(p.shape) if p.numel() else None for i, p in enumerate(ctx.params)]
+    dx = res[n] if ctx.need_dx else None
+    return dx, None, None, None, None, None, None, None, None, None, None, ctx.mask_grads, pg
+
+
+generator_fwd.register_autograd(_gen_backward, setup_context=_gen_setup)
+
+
+def generator(cfg: ops.GenConfig, bags: ops.PackedBags, noise0, noise1, train: bool, seed: int, masks, precision: int,
+              params: Sequence[Optional[Tensor]], x_grad: Optional[Tensor] = None) -> Tensor:
+    """pred [bags] (or H [bags, o] in backbone-only mode) through the registered operator."""
+    icfg, fcfg = gen_cfg_lists(cfg)
+    need = any(p is not None and p.requires_grad for p in params) or (x_grad is not None and x_grad.requires_grad)
+    m = masks or {}
+    x = x_grad if (x_grad is not None and x_grad.requires_grad) else bags.x
+    return torch.ops.advmil_b200.generator_fwd(x, bags.offsets, list(bags.lengths), icfg, fcfg, noise0, noise1, bool(train), int(seed),
+                                               int(precision), bool(need), _dense([m.get(k) for k in _GEN_MASKS], x),
+                                               _dense(params, x))[0]
+
+
+# =====================================================================================================
+# discriminator (region embedding + RLIP head)
+# =====================================================================================================
+@torch.library.custom_op("advmil_b200::discriminator_fwd", mutates_args=(), device_types="cuda")
+def discriminator_fwd(x: Tensor, offsets: Tensor, lengths: List[int], icfg: List[int], fcfg: List[float], t: Tensor, train: bool,
+                      seed: int, precision: int, save: bool, masks: List[Tensor],
+                      params: List[Tensor]) -> List[Tensor]:
+    """-> [out [bags], emb [R, d], y_pre [rows, d] (empty unless `save`), f1, fi, ab, rep, attn, bagv, fbar, g1, hx, u1, ht, out]."""
+    cfg = _disc_cfg(icfg, fcfg)
+    params = _opt(params)
+    bags = ops.PackedBags(x, lengths, offsets=offsets)
+    emb = ops.disc_embed_forward(cfg, params, bags, precision, save=save)
+    head = ops.disc_head_forward(cfg, params, bags, emb["emb"], t.detach(), train, seed, _masks(_DISC_MASKS, masks), precision)
+    y_pre = emb["y_pre"] if emb["y_pre"] is not None else x.new_empty(0)
+    return [head["out"].clone(), emb["emb"], y_pre] + [head[k] for k in _HEAD_SAVED]
+
+
+@discriminator_fwd.register_fake
+def _(x, offsets, lengths, icfg, fcfg, t, train, seed, precision, save, masks, params):
+    cfg = _disc_cfg(icfg, fcfg)
+    rows, nb, R, d, dh = x.shape[0], len(lengths), x.shape[0] // 16, cfg.d, cfg.d // 2
+    f = dict(dtype=torch.float32, device=x.device)
+    abw = 128 * ((d + 63) // 64)
+    e = torch.empty
+    return [e(nb, **f), e(R, d, **f), e((rows, d) if save else (0,), dtype=_act(precision), device=x.device), e(R, dh, **f), e(R, d, **f),
+            e(R, abw, **f), e(R, **f), e(R, **f), e(nb, d, **f), e(nb, d, **f), e(nb, dh, **f), e(nb, d, **f), e(nb, cfg.t1, **f),
+            e(nb, cfg.t2, **f), e(nb, **f)]
+
+
+@torch.library.custom_op("advmil_b200::discriminator_bwd", mutates_args=(), device_types="cuda")
+def discriminator_bwd(x: Tensor, offsets: Tensor, lengths: List[int], icfg: List[int], fcfg: List[float], t: Tensor, train: bool,
+                      seed: int, precision: int, masks: List[Tensor], params: List[Tensor], saved: List[Tensor],
+                      d_out: Tensor, need_param_grads: bool, need_dt: bool) -> List[Tensor]:
+    """-> gradients of the 24 discriminator tensors (empty when not requested / absent) + d_t [bags] (empty unless need_dt)."""
+    cfg = _disc_cfg(icfg, fcfg)
+    params = _opt(params)
+    bags = ops.PackedBags(x, lengths, offsets=offsets)
+    det = [None if p is None else p.detach() for p in params]
+    emb, y_pre = saved[0], saved[1]
+    head = dict(zip(_HEAD_SAVED, saved[2:]))
+    head.update(emb=emb, t=ops._f32c(t.reshape(-1)), masks=_masks(_DISC_MASKS, masks), seed=int(seed), train=bool(train),
+                precision=int(precision))
+    dev = x.device
+    d_t = torch.empty(bags.bags, dtype=torch.float32, device=dev) if need_dt else None
+    grads, d_emb = None, None
+    if need_param_grads:
+        grads = [None if p is None else torch.empty_like(p, dtype=torch.float32) for p in det]
+        d_emb = torch.empty_like(emb)
+    ops.disc_head_backward(cfg, det, bags, head, d_out.contiguous(), d_emb, d_t, grads, accumulate=False)
+    if need_param_grads:
+        ops.disc_embed_backward(cfg, det, bags, {"emb": emb, "y_pre": y_pre if y_pre.numel() else None, "precision": int(precision)},
+                                d_emb, grads, accumulate=False)
+    def empty():                                          # one storage per output: operator outputs must not alias each other
+        return x.new_empty(0, dtype=torch.float32)
+    out = [empty() if (grads is None or g is None) else g for g in (grads if grads is not None else [None] * len(params))]
+    return out + [d_t if d_t is not None else empty()]
+
+
+@discriminator_bwd.register_fake
+def _(x, offsets, lengths, icfg, fcfg, t, train, seed, precision, masks, params, saved, d_out, need_param_grads, need_dt):
+    out = [torch.empty_like(p, dtype=torch.float32) if need_param_grads else x.new_empty(0, dtype=torch.float32) for p in params]
+    return out + [torch.empty(len(lengths), dtype=torch.float32, device=x.device) if need_dt else x.new_empty(0, dtype=torch.float32)]
+
+
+def _disc_setup(ctx, inputs, output):
+    (x, offsets, lengths, icfg, fcfg, t, train, seed, precision, save, masks, params) = inputs
+    ctx.args = (offsets, lengths, icfg, fcfg, train, seed, precision, masks)
+    ctx.x, ctx.t, ctx.params, ctx.saved = x, t, params, list(output[1:])
+    ctx.mask_grads = [None] * len(masks)
+    ctx.need_param_grads = bool(save)
+    ctx.need_dt = bool(t.requires_grad)
+
+
+def _disc_backward(ctx, grads):
+    offsets, lengths, icfg, fcfg, train, seed, precision, masks = ctx.args
+    res = discriminator_bwd(ctx.x, offsets, lengths, icfg, fcfg, ctx.t, train, seed, precision, masks, ctx.params, ctx.saved,
+                            grads[0].contiguous(), ctx.need_param_grads, ctx.need_dt)
+    n = len(ctx.params)
+    pg = [res[i].reshape(p.shape) if (p.numel() and ctx.need_param_grads) else None for i, p in enumerate(ctx.params)]
+    d_t = res[n].reshape(ctx.t.shape) if ctx.need_dt else None
+    return None, None, None, None, None, d_t, None, None, None, None, ctx.mask_grads, pg
+
+
+discriminator_fwd.register_autograd(_disc_backward, setup_context=_disc_setup)
+
+
+def discriminator(cfg: ops.DiscConfig, bags: ops.PackedBags, t: Tensor, train: bool, seed: int, masks, precision: int,
+                  params: Sequence[Optional[Tensor]]) -> Tensor:
+    """out [bags] = D(packed bags, t [bags]) through the registered operator."""
+    icfg, fcfg = disc_cfg_lists(cfg)
+    need = any(p is not None and p.requires_grad for p in params)
+    m = masks or {}
+    return torch.ops.advmil_b200.discriminator_fwd(bags.x, bags.offsets, list(bags.lengths), icfg, fcfg, t.reshape(-1), bool(train),
+                                                   int(seed), int(precision), bool(need),
+                                                   _dense([m.get(k) for k in _DISC_MASKS], bags.x), _dense(params, bags.x))[0]

@@ -626,6 +626,11 @@ def run_main(args, rank, world, local_rank):
     ctx = Ctx(args, rank, world, local_rank)
     dev = ctx.dev
     lib = _lib.load()
+    # NUMA: pin this rank to its GPU's cores before the pinned staging memory is allocated (first touch)
+    from advmil_b200.dataset.packed import bind_host_to_gpu
+    numa = bind_host_to_gpu(local_rank, ranks_on_node=world, local_rank=local_rank) if world > 1 else {"bound": False}
+    if numa.get("bound"):
+        torch.set_num_threads(max(1, min(numa["cpus"], 8)))
     advmil_b200.set_precision(args.precision)
     torch.manual_seed(42)
     G, D = build_networks(dev)
@@ -818,7 +823,7 @@ def run_main(args, rank, world, local_rank):
                                      "gradients within 4x the reference's own fp32-vs-fp64 error; bf16 mode: 2e-2 norm-wise "
                                      "(per-tensor measured errors in DESIGN.md §2)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "h2d_gbs_per_gpu": h2d * args.steps / (ems / 1e3) / 1e9,
+                    "h2d_gbs_per_gpu": h2d * args.steps / (ems / 1e3) / 1e9, "host_numa_binding": numa,
                     "transport": ("p12: the packed loader's lossless 12-bit form of the bf16 features (8 bits sign+mantissa, 4-bit "
                                   "exponent code, sparse escapes; encoded once at packing time like the bf16 rounding itself, held "
                                   "in pinned host memory), copied and decoded on the device inside the timed region"

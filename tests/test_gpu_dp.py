@@ -70,21 +70,39 @@ def _free_port():
     s.close()
     return p
 
+def _launch(target, world, timeout=240):
+    """Runs `target(rank, world, port, q)` on `world` spawned ranks and returns what rank 0 put on the queue.  Never blocks
+    for ever: a rank that dies (or the deadline) fails the test and the surviving ranks are terminated."""
+    import queue as _queue
+    import time
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out, t0 = None, time.time()
+    try:
+        while out is None:
+            try:
+                out = q.get(timeout=2.0)
+            except _queue.Empty:
+                dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+                assert not dead, f"a rank exited with {dead} before rank 0 reported"
+                assert time.time() - t0 < timeout, "ranks did not report in time"
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+    return out
+
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_rank_step_equals_single_rank():
-    ctx = mp.get_context("spawn")
-    res = {}
-    for world in (1, 2):
-        q = ctx.SimpleQueue()
-        port = _free_port()
-        procs = [ctx.Process(target=_run, args=(r, world, port, q)) for r in range(world)]
-        for p in procs:
-            p.start()
-        res[world] = q.get()
-        for p in procs:
-            p.join(120)
-            assert p.exitcode == 0
+    res = {world: _launch(_run, world) for world in (1, 2)}
     g1, d1, l1 = res[1]
     g2, d2, l2 = res[2]
     # all-reduced gradients of both networks and the global losses; only the fp32 reduction order differs
@@ -130,18 +148,7 @@ def _run_esat(rank, world, port, q):
 def test_two_rank_module_step_with_esat_equals_single_rank():
     """The same check for ModuleAdvStep (ESAT generator): global-count loss normalisation + flat-buffer all-reduce give the
     single-process gradients of both networks."""
-    ctx = mp.get_context("spawn")
-    res = {}
-    for world in (1, 2):
-        q = ctx.SimpleQueue()
-        port = _free_port()
-        procs = [ctx.Process(target=_run_esat, args=(r, world, port, q)) for r in range(world)]
-        for p in procs:
-            p.start()
-        res[world] = q.get()
-        for p in procs:
-            p.join(120)
-            assert p.exitcode == 0
+    res = {world: _launch(_run_esat, world) for world in (1, 2)}
     g1, d1, l1 = res[1]
     g2, d2, l2 = res[2]
     assert float(np.abs(g1 - g2).max()) <= 1e-5 * float(np.abs(g1).max())

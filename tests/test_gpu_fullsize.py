@@ -27,7 +27,7 @@ def _engine(precision, sdG, sdD, **kw):
     return AdvStep(G, D, precision=precision, **kw), G, D
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "bf16"])
 def test_full_size_step_vs_oracle(precision):
     """One D step + G step + both Adam updates on 16 x 16384 x 1024 with injected dropout masks against the oracle's
     restatement of _update_disc/_update_gen (model/model_handler.py:349-498).  fp32 mode: rtol 1e-5 (SURVEY.md tier
@@ -52,17 +52,18 @@ def test_full_size_step_vs_oracle(precision):
                    masks_d_real=_cat(mr, ["fc1", "ga", "gs", "fc2"]), masks_d_fake=_cat(mf, ["fc1", "ga", "gs", "fc2"]),
                    masks_g=_cat(mg, ["h", "a", "b", "rho", "mlp0"]))
     L = eng.loss_dict(out)
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    exact = precision in ("fp32", "tf32x3")          # tf32x3: the exact-parity mode on the tensor cores (split tf32)
+    tol = 1e-5 if exact else 2e-2
     assert_close(out["pred_d"].cpu(), ref["pred_d"].reshape(-1), tol, "pred_d")
     assert_close(out["pred_g"].cpu(), ref["pred_g"].reshape(-1), tol, "pred_g")
     assert_close(out["f_fake_d"].cpu(), ref["fake_d"].reshape(-1), tol, "fake_d", atol_scale=1e-1)
     assert_close(out["f_fake_g"].cpu(), ref["fake_g"].reshape(-1), tol, "fake_g", atol_scale=1e-1)
-    ltol = 2e-5 if precision == "fp32" else 2e-2
+    ltol = 2e-5 if exact else 2e-2
     assert abs(L["dis_loss"] - ref["dis_loss"]) < ltol and abs(L["gen_loss"] - ref["gen_loss"]) < ltol
     assert abs(L["t_reg_loss"] - ref["t_reg"]) < ltol and abs(L["gen_total_loss"] - ref["total"]) < ltol
-    if precision != "fp32":
-        return
-    # Gradients (fp32 mode).  Every weight gradient here is a sum over 262,144 rows in which real and fake pair terms of
+    if not exact:
+        return                     # bf16: gradients and post-Adam parameters in tests/test_gpu_bf16_step.py
+    # Gradients (fp32 / split-tf32 modes).  Every weight gradient here is a sum over 262,144 rows in which real and fake pair terms of
     # opposite sign cancel: two correct fp32 evaluations differ by the rounding of the cancelled partial sums, not by 1e-5
     # of the result.  The yardstick is therefore the oracle re-run in float64: the CUDA path must be as close to it as
     # the reference's own fp32 arithmetic is (factor 4), or within rtol 1e-5.
@@ -74,7 +75,10 @@ def test_full_size_step_vs_oracle(precision):
         got, r32, r64 = got.detach().double().cpu().reshape(-1), r32.double().reshape(-1), r64.reshape(-1)
         scale = float(r64.abs().max())
         ours, theirs = float((got - r64).abs().max()), float((r32 - r64).abs().max())
-        assert ours <= max(4.0 * theirs, 1e-5 * scale), f"{name}: |cuda - f64| {ours:.3e} vs |ref fp32 - f64| {theirs:.3e} (scale {scale:.3e})"
+        # split tf32: products are fp32-grade but the tensor core's accumulation truncates (stage tests: 4e-6 of the largest
+        # entry against 1-2e-6 for an fp32 FFMA chain), hence the wider factor
+        factor = 4.0 if precision == "fp32" else 10.0
+        assert ours <= max(factor * theirs, 1e-5 * scale), f"{name}: |cuda - f64| {ours:.3e} vs |ref fp32 - f64| {theirs:.3e} (scale {scale:.3e})"
 
     pos = {id(t): i for i, t in enumerate(eng.dparams) if t is not None}
     for k, p in D.named_parameters():

@@ -113,6 +113,42 @@ def test_sample_inference_matches_oracle_and_lower_median():
         assert abs(float(res["avg_y_hat"][b]) - float(med)) < 1e-6
 
 
+@pytest.mark.parametrize("kind", ["patch", "cluster"])
+def test_sample_inference_for_the_other_backbones(kind):
+    """MyHandler.test_model (model_handler.py:598-643) works for any backbone: sample_inference for the ESAT (`patch`) and
+    DeepAttMISL (`cluster`) generators from ONE backbone pass equals the reference's 1 + S per-bag generator forwards
+    replayed on the same CPU noise stream through the oracle; lower median; D(x, y_hat)."""
+    from advmil_b200 import ops
+    from advmil_b200.step import sample_inference
+    dims, S = (1024, 384, 384), 7
+    shapes = O.G_ESAT_SHAPES() if kind == "patch" else O.G_CLUSTER_SHAPES(dims[0], dims[1])
+    sdG, sdD = O.synth_state_dict(shapes, 31), O.synth_state_dict(O.D_SHAPES(), 32)
+    G, D = build_G(dims, mode=kind).eval(), build_D().eval()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    Ns = [320, 640, 160]
+    xs = [O.synth_bag(n, 170 + i) for i, n in enumerate(Ns)]
+    rng = np.random.default_rng(33)
+    cids = [torch.tensor(rng.integers(0, 8, size=n), dtype=torch.float32) for n in Ns]
+    ext = torch.cat(cids).cuda() if kind == "cluster" else None
+    torch.manual_seed(77)
+    res = sample_inference(G, D, ops.PackedBags.from_list([x.cuda() for x in xs]), times_test_sample=S, ext=ext)
+    torch.manual_seed(77)
+    first = torch.rand(len(Ns), 192)
+    draws = [torch.rand(len(Ns), 192) for _ in range(S)]
+    for b, x in enumerate(xs):
+        kw = {"backbone": kind}
+        if kind == "cluster":
+            kw["cluster_id"] = cids[b]
+        y = O.generator_forward(sdG, x, [None, first[b:b + 1]], (0, 1), None, **kw)["pred"]
+        assert_close(res["y_hat"][b].cpu(), y.reshape(-1), RTOL, f"y_hat {b}")
+        f = O.prjdisc_forward(sdD, x, y)["out"]
+        assert_close(res["f_fake"][b].cpu(), f.reshape(-1), RTOL, f"f_fake {b}", atol_scale=1e-1)
+        dist = torch.stack([O.generator_forward(sdG, x, [None, d_[b:b + 1]], (0, 1), None, **kw)["pred"].reshape(()) for d_ in draws])
+        assert_close(res["dist_y_hat"][b, :, 0].cpu(), dist, RTOL, f"dist {b}")
+        assert abs(float(res["avg_y_hat"][b]) - float(O.lower_median(dist))) < 1e-6
+
+
 def test_device_cindex_matches_reference_golden_and_oracle_counts():
     """eval/cindex.py on the device: the value of the reference's concordance_index on 447 patients with tied times and
     tied predictions (tests/golden/misc.npz, written by the live reference) is reproduced exactly (integer pair counts,

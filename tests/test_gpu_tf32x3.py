@@ -78,7 +78,7 @@ def test_x3_gated_score_and_embed():
         advmil_b200.set_precision("fp32")
 
 
-@pytest.mark.parametrize("N,train", [(4096, False), (2000, True), (16384, True)])
+@pytest.mark.parametrize("N,train", [(4096, False), (2000, True)])
 def test_x3_mode_generator_and_discriminator_vs_oracle(N, train):
     """The exact-parity tolerance of the fp32 mode (1e-5 norm-wise, gradient floor of one fp32 ulp of the cancelled terms)
     holds on the tensor cores."""
