@@ -126,23 +126,52 @@ def _(x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, m
            [torch.empty_like(x) if need_dx else x.new_empty(0)]
 
 
+def _stash(ctx, output, tensors, lists):
+    """Everything the backward needs goes through save_for_backward (outputs stored as plain attributes of the node would form
+    a reference cycle output -> grad_fn -> ctx -> output that only the cyclic collector frees: activations of every bag
+    of a step would pile up in HBM); the activation outputs are marked non-differentiable (no grad_fn, no zero-filled
+    gradients materialised for them)."""
+    flat, layout = [], []
+    for t in tensors:
+        layout.append(None if t is None else len(flat))
+        if t is not None:
+            flat.append(t)
+    spans = []
+    for ts in lists:
+        spans.append((len(flat), len(ts)))
+        flat.extend(ts)
+    ctx.save_for_backward(*flat)
+    ctx.layout, ctx.spans = layout, spans
+    ctx.mark_non_differentiable(*output[1:])
+    ctx.set_materialize_grads(False)
+
+
+def _unstash(ctx):
+    flat = ctx.saved_tensors
+    return [None if i is None else flat[i] for i in ctx.layout], [list(flat[a:a + n]) for a, n in ctx.spans]
+
+
 def _gen_setup(ctx, inputs, output):
     (x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, save, masks, params) = inputs
-    ctx.args = (offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks)
-    ctx.x, ctx.params, ctx.saved = x, params, list(output[1:])
-    ctx.mask_grads = [None] * len(masks)
+    ctx.args = (lengths, icfg, fcfg, train, seed, precision)
+    _stash(ctx, output, [x, offsets, noise0, noise1], [masks, params, list(output[1:])])
+    ctx.n_masks = len(masks)
     ctx.need_dx = bool(x.requires_grad)
 
 
 def _gen_backward(ctx, grads):
-    offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks = ctx.args
+    lengths, icfg, fcfg, train, seed, precision = ctx.args
+    (x, offsets, noise0, noise1), (masks, params, saved) = _unstash(ctx)
     d_out = grads[0]
-    res = generator_bwd(ctx.x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks, ctx.params, ctx.saved,
+    none = (None,) * 11 + ([None] * ctx.n_masks,)
+    if d_out is None:
+        return none + ([None] * len(params),)
+    res = generator_bwd(x, offsets, lengths, icfg, fcfg, noise0, noise1, train, seed, precision, masks, params, saved,
                         d_out.contiguous(), ctx.need_dx)
-    n = len(ctx.params)
-    pg = [res[i].reshape(p.shape) if p.numel() else None for i, p in enumerate(ctx.params)]
+    n = len(params)
+    pg = [res[i].reshape(p.shape) if p.numel() else None for i, p in enumerate(params)]
     dx = res[n] if ctx.need_dx else None
-    return dx, None, None, None, None, None, None, None, None, None, None, ctx.mask_grads, pg
+    return (dx,) + none[1:] + (pg,)
 
 
 generator_fwd.register_autograd(_gen_backward, setup_context=_gen_setup)
@@ -226,21 +255,26 @@ def _(x, offsets, lengths, icfg, fcfg, t, train, seed, precision, masks, params,
 
 def _disc_setup(ctx, inputs, output):
     (x, offsets, lengths, icfg, fcfg, t, train, seed, precision, save, masks, params) = inputs
-    ctx.args = (offsets, lengths, icfg, fcfg, train, seed, precision, masks)
-    ctx.x, ctx.t, ctx.params, ctx.saved = x, t, params, list(output[1:])
-    ctx.mask_grads = [None] * len(masks)
+    ctx.args = (lengths, icfg, fcfg, train, seed, precision)
+    _stash(ctx, output, [x, offsets, t], [masks, params, list(output[1:])])
+    ctx.n_masks = len(masks)
     ctx.need_param_grads = bool(save)
     ctx.need_dt = bool(t.requires_grad)
 
 
 def _disc_backward(ctx, grads):
-    offsets, lengths, icfg, fcfg, train, seed, precision, masks = ctx.args
-    res = discriminator_bwd(ctx.x, offsets, lengths, icfg, fcfg, ctx.t, train, seed, precision, masks, ctx.params, ctx.saved,
-                            grads[0].contiguous(), ctx.need_param_grads, ctx.need_dt)
-    n = len(ctx.params)
-    pg = [res[i].reshape(p.shape) if (p.numel() and ctx.need_param_grads) else None for i, p in enumerate(ctx.params)]
-    d_t = res[n].reshape(ctx.t.shape) if ctx.need_dt else None
-    return None, None, None, None, None, d_t, None, None, None, None, ctx.mask_grads, pg
+    lengths, icfg, fcfg, train, seed, precision = ctx.args
+    (x, offsets, t), (masks, params, saved) = _unstash(ctx)
+    d_out = grads[0]
+    none = (None,) * 10 + ([None] * ctx.n_masks,)
+    if d_out is None:
+        return none + ([None] * len(params),)
+    res = discriminator_bwd(x, offsets, lengths, icfg, fcfg, t, train, seed, precision, masks, params, saved,
+                            d_out.contiguous(), ctx.need_param_grads, ctx.need_dt)
+    n = len(params)
+    pg = [res[i].reshape(p.shape) if (p.numel() and ctx.need_param_grads) else None for i, p in enumerate(params)]
+    d_t = res[n].reshape(t.shape) if ctx.need_dt else None
+    return none[:5] + (d_t,) + none[6:] + (pg,)
 
 
 discriminator_fwd.register_autograd(_disc_backward, setup_context=_disc_setup)

@@ -63,3 +63,32 @@ def test_opcheck_and_fake_tracing():
         fb.x = fx
         out = library.generator(G.config(), fb, None, mode.from_tensor(noise), False, 0, None, ops.FP32, G.gen_params())
         assert tuple(out.shape) == (1,)
+
+
+def test_activations_are_released_by_reference_counting():
+    """The saved activations must not sit in a reference cycle (output -> grad_fn -> ctx -> output): dropping the result of
+    a forward frees its activations at once, without the cyclic collector (the drop-in handler runs 16 bags x 5 module
+    calls per optimiser step; a cycle made every allocation a cudaMalloc and the step 8x slower)."""
+    import gc
+    G, D = _nets()
+    G.train(); D.train()
+    bags = ops.PackedBags.from_single(O.synth_bag(4096, 9).cuda())
+    noise = torch.rand(1, 192, device="cuda")
+
+    def fwd():
+        pred = library.generator(G.config(), bags, None, noise, True, 3, None, ops.FP32, G.gen_params())
+        return library.discriminator(D.config(), bags, pred, True, 4, None, ops.FP32, D.disc_params())
+
+    f = fwd()
+    del f
+    gc.collect()
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    gc.disable()
+    try:
+        f = fwd()
+        assert torch.cuda.memory_allocated() > base + 4096 * 512 * 4          # the activations are alive with the graph
+        del f
+        assert torch.cuda.memory_allocated() <= base + (1 << 20)
+    finally:
+        gc.enable()
