@@ -344,10 +344,14 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   Drop none = Drop::make(nullptr, 0, 0, 0.f, 0, 0);
   // region-level tensors are fp32; outside the exact-fp32 mode their contractions run on the tcgen05 tf32 pipe
   const int rp = region_precision(a->precision, a->train != 0);
-  ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, rp, st));
-  ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, rp, st));
-  ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
-  ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, nullptr, part, rp, st));
+  if (rlip_chain_supported(d)) {      // one exact-fp32 kernel for the region-level chain (rlip_chain.cu), every precision mode
+    ADVMIL_TRY(rlip_chain_fwd(a->emb, *p, R, dfc1, dga, dgs, a->f1, a->fi, a->ab, part, st));
+  } else {
+    ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, rp, st));
+    ADVMIL_TRY(linear_fwd(a->f1, p->F1b_w, p->F1b_b, R, dh, d, 0, none, a->fi, rp, st));
+    ADVMIL_TRY(gate_pack_weights(p->Pg_w, p->Pg_b, p->Ps_w, p->Ps_b, d, d, Wp, bp, st));
+    ADVMIL_TRY(gated_score_fwd(a->fi, Wp, bp, p->Pc_w, p->Pc_b, R, d, d, dga, dgs, a->ab, nullptr, part, rp, st));
+  }
   ADVMIL_TRY(seg_softmax_pool_fwd(a->rep, part, abw / 128, p->Pc_b, a->fi, ELEM_F32, ro.dev, ro.host.data(), R, nb, d, a->attn,
                                   a->bagv, a->fbar, poolws, st));
   ADVMIL_TRY(rlip_tail_fwd(*p, a->bagv, a->fbar, a->t, nb, dfc2, a->g1, a->hx, a->u1, a->ht, a->out, st));

@@ -4,6 +4,7 @@
 // rows/16 "region" rows; the N-row contraction of the embedding runs on the GEMM engines (gemm_stages.cu).
 #include <limits.h>
 #include "stages.cuh"
+#include "esat_attn.cuh"
 
 namespace advmil {
 
@@ -229,18 +230,6 @@ __global__ void __launch_bounds__(256) sincos_pe_kernel(const int64_t* __restric
 // =============================================================================================
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BK = 32;
-
-struct AttDrop {             // dropout on the attention probabilities of (bag, head, query, key)
-  Drop drop;                 // counter generator (drop.mask unused)
-  const uint8_t* mask;       // injected keep masks: per bag [heads, Rb, Rb] at mask_off[bag], or nullptr
-  const int64_t* mask_off;
-  int heads;
-  __device__ __forceinline__ bool keep(int bag, int head, int q, int k, int Rb, int grow) const {
-    if (!drop.active) return true;
-    if (mask) return mask[mask_off[bag] + ((int64_t)head * Rb + q) * Rb + k] != 0;
-    return drop.keep((uint32_t)grow * (uint32_t)heads + (uint32_t)head, (uint32_t)k);
-  }
-};
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_BQ) mha_fwd_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ ro, int d,
@@ -934,6 +923,8 @@ int mha_fwd(const float* qkv, const int32_t* ro, const int32_t* ro_host, int bag
   for (int b = 0; b < bags; ++b) mx = max(mx, ro_host[b + 1] - ro_host[b]);
   const AttDrop ad = make_att_drop(drop, mask, mask_off, heads);
   const float scale = 1.0f / sqrtf((float)hd);
+  if (mha_use_tc(precision, hd) && mha_tcgen05_supported(hd, d))     // tcgen05 / TMEM / TMA kernel (esat_attn_tc.cu)
+    return mha_fwd_tcgen05(qkv, ro, bags, Rtot, d, heads, mx, scale, ad, ctx, lse, st);
   if (mha_use_tc(precision, hd)) {
     ESAT_HD8_SWITCH(hd, {
       static bool attr_set = false;    // > 48 KB of dynamic shared memory needs the opt-in once per instantiation

@@ -60,6 +60,13 @@ size_t bwd_weight_ws_floats(int rows, int N1, int N2);
 int bwd_weight(const void* dY, const void* X, int rows, int N1, int N2, float* dW, int accumulate, float* ws,
                int precision, cudaStream_t st);
 
+// ---- rlip_chain.cu ----------------------------------------------------------------------------
+// fc1 MLP + GAPool gate of the RLIP head over R regions in one FFMA kernel (d == 128): writes f1 [R, d/2], fi [R, d],
+// ab [R, 2d] packed (optional) and the per-64-pair partial logits part [d/64][R] (finished by seg_softmax_pool_fwd)
+bool rlip_chain_supported(int d);
+int rlip_chain_fwd(const float* emb, const AdvmilDiscParams& p, int R, const Drop& dfc1, const Drop& dga, const Drop& dgs,
+                   float* f1, float* fi, float* ab, float* part, cudaStream_t st);
+
 // ---- seg_kernels.cu ---------------------------------------------------------------------------
 int gate_pack_weights(const float* Wa, const float* ba, const float* Wb, const float* bb, int L, int D, float* Wp,
                       float* bp, cudaStream_t st);

@@ -290,6 +290,7 @@ extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
   STEP_TAKE(d_t, float, nb);
   const size_t dws_bytes = advmil_disc_workspace_bytes(&dp, rows, nb, 1);
   STEP_TAKE(dws, char, dws_bytes);
+  ha.ab = nullptr;      // the G step asks D only for dL/dt: the gate activations are never read back
   ha.emb = emb; ha.t = a->pred_g; ha.out = a->f_fake_g; ha.seed = 0; ha.train = 0; ha.precision = a->precision;
   ha.workspace = dws; ha.workspace_bytes = dws_bytes;
   ADVMIL_TRY(advmil_disc_head_fwd(&dp, bags, &ha, stream));
