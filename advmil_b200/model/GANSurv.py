@@ -86,10 +86,13 @@ class Generator(nn.Module):
             pred = ops.EsatFn.apply(bb.esat_config(), self.config(), bags, pe, n0, n1, train, next_dropout_seed() if train else 0,
                                     masks, precision, reuse_embedding, acts_sink, *bb.esat_params(), *self.head_params())
             return pred.unsqueeze(-1)
-        # registered operator advmil_b200::generator_fwd (torch.library: CUDA impl over the C ABI, fake impl, autograd)
         from .. import library
-        pred = library.generator(self.config(), bags, n0, n1, train, next_dropout_seed() if train else 0,
-                                 getattr(self, "_inject_masks", None), precision, self.gen_params(), x_grad=x_grad)
+        seed, masks = next_dropout_seed() if train else 0, getattr(self, "_inject_masks", None)
+        if library.should_dispatch(bags.x):
+            # registered operator advmil_b200::generator_fwd (torch.library: CUDA impl over the C ABI, fake impl, autograd)
+            pred = library.generator(self.config(), bags, n0, n1, train, seed, masks, precision, self.gen_params(), x_grad=x_grad)
+        else:
+            pred = ops.GeneratorFn.apply(self.config(), bags, x_grad, n0, n1, train, seed, masks, precision, *self.gen_params())
         return pred.unsqueeze(-1)
 
 
@@ -134,10 +137,14 @@ class PrjDiscriminator(nn.Module):
 
     def forward_packed(self, bags: ops.PackedBags, t: torch.Tensor) -> torch.Tensor:
         train = self.training
-        # registered operator advmil_b200::discriminator_fwd (torch.library: CUDA impl over the C ABI, fake impl, autograd)
         from .. import library
-        out = library.discriminator(self.config(), bags, t.reshape(-1), train, next_dropout_seed() if train else 0,
-                                    getattr(self, "_inject_masks", None), ops.PRECISIONS[get_precision()], self.disc_params())
+        seed, masks = next_dropout_seed() if train else 0, getattr(self, "_inject_masks", None)
+        if library.should_dispatch(bags.x):
+            # registered operator advmil_b200::discriminator_fwd (torch.library: CUDA impl over the C ABI, fake impl, autograd)
+            out = library.discriminator(self.config(), bags, t.reshape(-1), train, seed, masks, ops.PRECISIONS[get_precision()], self.disc_params())
+        else:
+            out = ops.DiscriminatorFn.apply(self.config(), bags, t.reshape(-1), train, seed, masks, ops.PRECISIONS[get_precision()],
+                                            *self.disc_params())
         return out.unsqueeze(-1)
 
     def embed_packed(self, bags: ops.PackedBags) -> torch.Tensor:

@@ -35,7 +35,7 @@ def _stream() -> int:
 
 
 def _need_cuda(t: torch.Tensor, what: str):
-    if not t.is_cuda:
+    if not (t.is_cuda or t.device.type == "meta"):      # meta: shape-only tracing through the registered operators (library.py)
         raise _lib.AdvmilError(f"{what} must be a CUDA tensor: advmil_b200 has no CPU path")
 
 

@@ -77,3 +77,17 @@ def test_discriminator_t_gradient_and_frozen_parameters():
     f.sum().backward()
     assert t.grad is not None and t.grad.shape == t.shape
     assert all(p.grad is None for p in dp if p is not None)
+
+
+def test_module_surface_traces_on_meta_through_the_registered_ops():
+    """The drop-in modules themselves (reference signatures: G(x [1,N,C], x_ext), D(x, t)) dispatch to the registered operators
+    when they are traced: on the meta device a forward + backward runs shape-only, without any kernel."""
+    G, D = build_G(device="meta"), build_D(device="meta")
+    G.train(); D.train()
+    x = torch.empty(1, 640, 1024, device="meta")
+    pred = G(x, None)
+    assert tuple(pred.shape) == (1, 1)
+    f = D(x, pred)
+    assert tuple(f.shape) == (1, 1)
+    (f.sum() + pred.sum()).backward()
+    assert all(p.grad is not None and p.grad.shape == p.shape for p in list(G.parameters()) + list(D.parameters()))
