@@ -8,6 +8,7 @@ per step; decoding costs ~0.2 ms per 16-bag step on the copy stream (csrc/codec.
 from __future__ import annotations
 
 from dataclasses import dataclass
+from typing import Optional
 
 import numpy as np
 import torch
@@ -77,4 +78,110 @@ def decode_p12_device(lo: torch.Tensor, hi: torch.Tensor, table: bytes, esc_idx:
     _lib.check(lib.advmil_bf16p12_decode(lo.data_ptr(), hi.data_ptr(), table, esc_idx.data_ptr() if n_esc else None,
                                          esc_exp.data_ptr() if n_esc else None, lo.numel(), n_esc, out.data_ptr(),
                                          torch.cuda.current_stream().cuda_stream), "advmil_bf16p12_decode")
+    return out
+
+
+# =====================================================================================================
+# "vl": the same transport format with the exponent plane entropy-coded (csrc/codec.cu)
+# =====================================================================================================
+@dataclass
+class VL:
+    lo: torch.Tensor        # [n] uint8
+    stream: torch.Tensor    # [words] int32 (uint32 bit patterns), incl. 2 guard words
+    sbase: torch.Tensor     # [n / 4096] int32
+    loff: torch.Tensor      # [n / 128] int16 (uint16 bit patterns)
+    tab_exp: np.ndarray     # [16] uint8, host
+    tab_len: np.ndarray     # [16] uint8, host
+    tab_code: np.ndarray    # [16] uint16, host
+    esc_idx: torch.Tensor   # [m] int32
+    esc_exp: torch.Tensor   # [m] uint8
+    shape: tuple
+    blob: Optional[torch.Tensor] = None      # set by pin(): one pinned buffer holding every plane
+    blob_offsets: Optional[list] = None
+
+    @property
+    def nbytes(self) -> int:
+        return self.lo.numel() + 4 * self.stream.numel() + 4 * self.sbase.numel() + 2 * self.loff.numel() + 64 + 5 * self.esc_idx.numel()
+
+    @property
+    def bits_per_element(self) -> float:
+        return 8.0 * self.nbytes / max(self.lo.numel(), 1)
+
+    def pin(self) -> "VL":
+        """One pinned blob [lo | stream | sbase | loff | esc_idx | esc_exp] (256-byte aligned parts): the feeder moves a step's
+        features with a single copy; the member tensors become views into the blob."""
+        parts = [self.lo, self.stream, self.sbase, self.loff, self.esc_idx, self.esc_exp]
+        offs, total = [], 0
+        for t in parts:
+            offs.append(total)
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+        try:
+            blob = torch.empty(max(total, 256), dtype=torch.uint8).pin_memory()
+        except RuntimeError:
+            blob = torch.empty(max(total, 256), dtype=torch.uint8)
+        views = []
+        for t, o in zip(parts, offs):
+            nb = t.numel() * t.element_size()
+            v = blob[o:o + nb].view(t.dtype)
+            v.copy_(t.reshape(-1))
+            views.append(v)
+        out = VL(views[0], views[1], views[2], views[3], self.tab_exp, self.tab_len, self.tab_code, views[4], views[5], self.shape)
+        out.blob, out.blob_offsets = blob, offs
+        return out
+
+
+def _np_ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def encode_bf16_vl(x: torch.Tensor) -> VL:
+    """x: bfloat16 CPU tensor with numel % 4096 == 0 (and < 2^31 elements) -> VL (pageable; call .pin() for the feeder).
+    The encoder is the library's host function advmil_bf16vl_encode (one sequential pass, ~1 ns per element)."""
+    import ctypes as C
+    from .. import _lib
+    lib = _lib.load()
+    assert x.dtype == torch.bfloat16 and not x.is_cuda and x.numel() % 4096 == 0 and x.numel() < 2 ** 31
+    v = x.contiguous().view(torch.int16).numpy().view(np.uint16).reshape(-1)
+    n = v.size
+    cap = n // 4 + n // 128 + 2
+    lo = np.empty(n, dtype=np.uint8)
+    stream = np.empty(cap, dtype=np.uint32)
+    sbase = np.empty(max(n // 4096, 1), dtype=np.uint32)
+    loff = np.empty(max(n // 128, 1), dtype=np.uint16)
+    te, tl, tc = np.zeros(16, np.uint8), np.zeros(16, np.uint8), np.zeros(16, np.uint16)
+    esc_cap = n
+    ei, ee = np.empty(esc_cap, dtype=np.int32), np.empty(esc_cap, dtype=np.uint8)
+    words, nesc = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.advmil_bf16vl_encode(_np_ptr(v), n, _np_ptr(lo), _np_ptr(stream), cap, _np_ptr(sbase), _np_ptr(loff), _np_ptr(te),
+                                        _np_ptr(tl), _np_ptr(tc), _np_ptr(ei), _np_ptr(ee), esc_cap, C.byref(words), C.byref(nesc)),
+               "advmil_bf16vl_encode")
+    w, m = int(words.value), int(nesc.value)
+    return VL(torch.from_numpy(lo), torch.from_numpy(stream[:w].copy().view(np.int32)), torch.from_numpy(sbase[:n // 4096].view(np.int32)),
+              torch.from_numpy(loff[:n // 128].view(np.int16)), te, tl, tc, torch.from_numpy(ei[:m].copy()), torch.from_numpy(ee[:m].copy()),
+              tuple(x.shape))
+
+
+def decode_vl_host(p: VL) -> torch.Tensor:
+    """Host decoder (the library's sequential reference, advmil_bf16vl_decode_host) -- what the device kernel is tested against."""
+    from .. import _lib
+    lib = _lib.load()
+    n = p.lo.numel()
+    out = np.empty(n, dtype=np.uint16)
+    m = int(p.esc_idx.numel())
+    _lib.check(lib.advmil_bf16vl_decode_host(p.lo.data_ptr(), p.stream.data_ptr(), p.sbase.data_ptr(), p.loff.data_ptr(), _np_ptr(p.tab_exp),
+                                             _np_ptr(p.tab_len), _np_ptr(p.tab_code), p.esc_idx.data_ptr() if m else None,
+                                             p.esc_exp.data_ptr() if m else None, n, m, _np_ptr(out)), "advmil_bf16vl_decode_host")
+    return torch.from_numpy(out.view(np.int16)).view(torch.bfloat16).reshape(p.shape)
+
+
+def decode_vl_device(lo, stream, sbase, loff, p: VL, esc_idx, esc_exp, out: torch.Tensor) -> torch.Tensor:
+    """Planes on the device (tables from `p`, host); decodes on the current stream into `out` (bfloat16, lo.numel() elements)."""
+    from .. import _lib
+    lib = _lib.load()
+    assert lo.is_cuda and out.is_cuda and out.dtype == torch.bfloat16 and out.numel() == lo.numel() and out.is_contiguous()
+    m = int(esc_idx.numel())
+    _lib.check(lib.advmil_bf16vl_decode(lo.data_ptr(), stream.data_ptr(), sbase.data_ptr(), loff.data_ptr(), _np_ptr(p.tab_exp),
+                                        _np_ptr(p.tab_len), _np_ptr(p.tab_code), esc_idx.data_ptr() if m else None,
+                                        esc_exp.data_ptr() if m else None, lo.numel(), m, out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream), "advmil_bf16vl_decode")
     return out

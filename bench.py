@@ -579,10 +579,10 @@ def run_esat(args, rank, world, local_rank):
         roof = {"kernel": "attn_fwd", "bound": "tensor", "achieved": kern["attn_fwd"]["tflops"], "peak": peaks["tflops"] / 2, "unit": "TFLOP/s",
                 "frac": kern["attn_fwd"]["tflops"] / (peaks["tflops"] / 2), "traffic": None,
                 "peak_source": f"{peaks['src']} bf16 {peaks['kind']} / 2 (tf32 operands; warp-level mma.sync kernels)"}
-    p12 = args.precision == "bf16" and args.transport == "p12"
+    p12 = args.precision == "bf16" and args.transport in ("p12", "vl")
     if p12:
         for st in steps[:2]:
-            st.pack12()
+            st.packvl() if args.transport == "vl" else st.pack12()
     it = iter(DeviceFeeder(steps, device=dev, depth=2))
     h2d = steps[0].nbytes
     for i in range(args.warmup):
@@ -610,7 +610,7 @@ def run_esat(args, rank, world, local_rank):
                            "l2": "inputs (two alternating steps of 512 MiB or more) larger than the 126 MB L2; no flush",
                            "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
                 "e2e": {"value": args.bags * world * args.steps / (ems / 1e3), "unit": "bags/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 16, "transport": "p12" if p12 else "raw"},
+                        "d2h_bytes_per_step": 16, "transport": args.transport if p12 else "raw"},
                 "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": None, "clocks": clocks,
                 "losses_last_step": dict(zip(("dis_loss", "gen_loss", "t_reg_loss", "gen_total_loss"), host))}
         print(json.dumps(line), flush=True)
@@ -689,10 +689,10 @@ def run_main(args, rank, world, local_rank):
     losses = engine.loss_dict(out)
 
     # ================= (B) end-to-end through the public API: pinned host -> device every step =================
-    p12 = args.precision == "bf16" and args.transport == "p12"
+    p12 = args.precision == "bf16" and args.transport in ("p12", "vl")
     if p12:
-        for st in steps[:2]:
-            st.pack12()           # done once, at packing time (the list cycles the same two steps)
+        for st in steps[:2]:      # done once, at packing time (the list cycles the same two steps)
+            st.packvl() if args.transport == "vl" else st.pack12()
     feeder = DeviceFeeder(steps, device=dev, depth=2)
     it = iter(feeder)
     h2d = steps[0].nbytes
@@ -824,7 +824,12 @@ def run_main(args, rank, world, local_rank):
                                      "(per-tensor measured errors in DESIGN.md §2)"},
             "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "h2d_gbs_per_gpu": h2d * args.steps / (ems / 1e3) / 1e9, "host_numa_binding": numa,
-                    "transport": ("p12: the packed loader's lossless 12-bit form of the bf16 features (8 bits sign+mantissa, 4-bit "
+                    "transport": (("vl: the packed loader's lossless entropy-coded form of the bf16 features (8 bits sign+mantissa, "
+                                   "canonical-Huffman exponent codes in 32 sub-streams per 4096 elements, sparse escapes; %.2f bits "
+                                   "per element; encoded once at packing time like the bf16 rounding itself, held in pinned host "
+                                   "memory), copied and decoded on the device inside the timed region" % (8.0 * steps[0].vl.nbytes / steps[0].vl.lo.numel()))
+                                  if (p12 and args.transport == "vl") else
+                                  "p12: the packed loader's lossless 12-bit form of the bf16 features (8 bits sign+mantissa, 4-bit "
                                   "exponent code, sparse escapes; encoded once at packing time like the bf16 rounding itself, held "
                                   "in pinned host memory), copied and decoded on the device inside the timed region"
                                   if p12 else "raw"),
@@ -850,9 +855,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline and the two handler legs")
     ap.add_argument("--no-extra-legs", action="store_true", help="only the main line (value / e2e / roofline)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0)
-    ap.add_argument("--transport", default="p12", choices=["p12", "raw"],
-                    help="end-to-end leg, bf16 mode: copy the features in the packed loader's lossless 12-bit transport format "
-                         "(decoded on the device) or as raw bf16")
+    ap.add_argument("--transport", default=os.environ.get("ADVMIL_TRANSPORT", "vl"), choices=["vl", "p12", "raw"],
+                    help="end-to-end leg, bf16 mode: copy the features in the packed loader's lossless entropy-coded transport "
+                         "format (vl, ~10.9 bits per element), its fixed 12-bit form (p12) -- both decoded on the device -- or as raw bf16")
     ap.add_argument("--backbone", default="abmil", choices=["abmil", "patch"],
                     help="generator backbone: abmil (the benchmark's workload, C-fused AdvStep) or patch (ESAT, ModuleAdvStep)")
     ap.add_argument("--ragged", action="store_true",

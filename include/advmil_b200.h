@@ -426,6 +426,24 @@ ADVMIL_API int advmil_sincos_pe(const int64_t* coord, const int32_t* offsets /* 
 ADVMIL_API int advmil_bf16p12_decode(const uint8_t* lo, const uint8_t* hi, const uint8_t* table16_host, const int32_t* esc_idx,
                           const uint8_t* esc_exp, int64_t n, int32_t n_esc, void* out_bf16, void* stream);
 
+/* ---- "vl": the same transport format with the exponent plane entropy-coded (canonical Huffman, <= 8 bits, LSB-first; ~10.9
+ *      instead of 12 bits per element on Gaussian-like features).  Elements are dealt to 32 sub-streams per super-block of 4096
+ *      (lane t owns elements r*128 + 4t + {0..3}) so that the decoder's loads and stores stay coalesced: lo[n] as in p12,
+ *      stream[] uint32 words (+2 guard words), sbase[n/4096] word offset of a super-block, loff[n/128] word offset of a
+ *      sub-stream inside its super-block, tables (HOST pointers: symbol -> exponent byte / code length / LSB-first code), escapes
+ *      as in p12.  n % 4096 == 0, n < 2^31.
+ *      advmil_bf16vl_encode and advmil_bf16vl_decode_host are HOST functions (packing time / tests; no GPU needed):
+ *      x = n bf16 words; stream_cap_words >= n/4 + n/128 + 2 always suffices; returns the words and escapes written. */
+ADVMIL_API int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words, uint32_t* sbase,
+                         uint16_t* loff, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16, int32_t* esc_idx,
+                         uint8_t* esc_exp, int64_t esc_cap, int64_t* stream_words, int64_t* n_esc);
+ADVMIL_API int advmil_bf16vl_decode_host(const uint8_t* lo, const uint32_t* stream, const uint32_t* sbase, const uint16_t* loff,
+                              const uint8_t* tab_exp16, const uint8_t* tab_len16, const uint16_t* tab_code16,
+                              const int32_t* esc_idx, const uint8_t* esc_exp, int64_t n, int64_t n_esc, uint16_t* out);
+ADVMIL_API int advmil_bf16vl_decode(const uint8_t* lo, const uint32_t* stream, const uint32_t* sbase, const uint16_t* loff,
+                         const uint8_t* tab_exp16_host, const uint8_t* tab_len16_host, const uint16_t* tab_code16_host,
+                         const int32_t* esc_idx, const uint8_t* esc_exp, int64_t n, int32_t n_esc, void* out_bf16, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

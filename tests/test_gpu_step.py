@@ -508,3 +508,26 @@ def test_fused_step_many_small_bags_vs_oracle_trainer():
     for k, p in G.named_parameters():
         if not k.endswith(ZERO_GRAD):
             assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2e-2)
+
+
+def test_vl_transport_decodes_bit_exactly_on_the_device_and_through_the_feeder():
+    """The entropy-coded transport form: the device decoder equals the stored bf16 words for Gaussian features, for every bit
+    pattern and for zeros-heavy features, and a packvl() step arrives through the DeviceFeeder word for word."""
+    from advmil_b200.dataset.codec import decode_vl_device, encode_bf16_vl
+    from advmil_b200.dataset.packed import DeviceFeeder, pack_step
+    torch.manual_seed(5)
+    cases = [torch.randn(256 * 4096).to(torch.bfloat16),
+             torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).repeat(2),
+             torch.relu(torch.randn(32 * 4096)).mul(0.5).to(torch.bfloat16), torch.zeros(4096, dtype=torch.bfloat16)]
+    for x in cases:
+        p = encode_bf16_vl(x)
+        out = torch.empty(x.numel(), dtype=torch.bfloat16, device="cuda")
+        decode_vl_device(p.lo.cuda(), p.stream.cuda(), p.sbase.cuda(), p.loff.cuda(), p, p.esc_idx.cuda(), p.esc_exp.cuda(), out)
+        assert torch.equal(out.cpu().view(torch.int16), x.view(torch.int16))
+    xs = [torch.randn(n, 1024) for n in (320, 1600, 128)]
+    labels = [(0.3, 1.0), (0.5, 0.0), (0.9, 1.0)]
+    steps = [pack_step(xs, labels, dtype=torch.bfloat16).packvl() for _ in range(3)]
+    assert steps[0].nbytes < 0.70 * steps[0].x.numel() * 2
+    for st, dv in zip(steps, DeviceFeeder(steps, device="cuda", depth=2)):
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(dv.bags.x.cpu().view(torch.int16), st.x.view(torch.int16))

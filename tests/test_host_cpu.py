@@ -273,3 +273,25 @@ def test_packed_file_p12_storage_round_trip(tmp_path):
     assert torch.equal(decode_p12_host(sp.p12).view(torch.int16), sr.x.view(torch.int16))
     feats = lambda path: os.path.getsize(path) - PackedFile(path)._feats_pos                  # noqa: E731
     assert feats(p12) < 0.77 * feats(raw)
+
+
+def test_vl_transport_format_round_trip_is_bit_exact():
+    """The entropy-coded transport form (host encoder + the library's sequential reference decoder, no GPU): exact for
+    Gaussian features, for every bf16 bit pattern (escapes), for a constant matrix (one 1-bit code) and a minimal block;
+    ~10.9 bits per element on Gaussian features."""
+    from advmil_b200.dataset.codec import decode_vl_host, encode_bf16_vl
+    torch.manual_seed(3)
+    x = torch.randn(64 * 4096).to(torch.bfloat16)
+    p = encode_bf16_vl(x)
+    assert torch.equal(decode_vl_host(p).view(torch.int16), x.view(torch.int16))
+    assert 10.5 < p.bits_per_element < 11.1 and int(p.tab_len.max()) <= 8
+    kraft = sum(2.0 ** -int(l) for l in p.tab_len if l)
+    assert abs(kraft - 1.0) < 1e-12
+    allbits = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).repeat(2)
+    pa = encode_bf16_vl(allbits)
+    assert pa.esc_idx.numel() > 0 and torch.equal(decode_vl_host(pa).view(torch.int16), allbits.view(torch.int16))
+    c = torch.full((4096,), -0.375).to(torch.bfloat16)
+    pc = encode_bf16_vl(c)
+    assert torch.equal(decode_vl_host(pc).view(torch.int16), c.view(torch.int16)) and pc.bits_per_element < 9.5
+    nn_ = torch.relu(torch.randn(8 * 4096)).mul(0.5).to(torch.bfloat16)          # non-negative features with exact zeros
+    assert torch.equal(decode_vl_host(encode_bf16_vl(nn_)).view(torch.int16), nn_.view(torch.int16))
