@@ -33,6 +33,62 @@ __device__ __forceinline__ void row_stats(const float (&v)[NPL], float eps, floa
   rstd = rsqrtf(warp_sum(q) * (1.0f / (32 * NPL)) + eps);
 }
 
+// ---- vector-friendly column ownership for the N-row streams (y_pre, d_y): lane l owns CONTIGUOUS chunks so that a row moves
+// in 16-byte (bf16: 8 columns) / 8-byte pieces instead of 2-byte scalars.  LayerNorm does not care which lane owns which
+// column; only gamma / beta / the outputs are indexed through col().  NPL = 12 in bf16: columns [0, 256) in chunks of 8,
+// [256, 384) in chunks of 4.  Widths without a vector layout keep the strided ownership (lane, lane + 32, ...).
+template <typename T, int NPL> struct RowMap {
+  static constexpr int C0 = (sizeof(T) == 2) ? (NPL >= 8 ? 8 : (NPL == 4 ? 4 : 0)) : (NPL % 4 == 0 ? 4 : 0);     // first chunk size
+  static constexpr bool VEC = C0 != 0 && (sizeof(T) == 2 ? (NPL == 4 || NPL == 8 || NPL == 12) : true);
+  // column of this lane's k-th element
+  __device__ __forceinline__ static int col(int lane, int k) {
+    if (!VEC) return lane + 32 * k;
+    if (sizeof(T) == 2) return k < 8 ? (NPL >= 8 ? 8 * lane + k : 4 * lane + k) : 256 + 4 * lane + (k - 8);
+    return 128 * (k >> 2) + 4 * lane + (k & 3);
+  }
+  __device__ __forceinline__ static void load(const T* __restrict__ p, int lane, float (&v)[NPL]) {
+    if constexpr (!VEC) {
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) v[k] = to_f32(p[lane + 32 * k]);
+    } else if constexpr (sizeof(T) == 2) {
+      if constexpr (NPL >= 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p + 8 * lane);
+        v[0] = bf_lo(u.x); v[1] = bf_hi(u.x); v[2] = bf_lo(u.y); v[3] = bf_hi(u.y); v[4] = bf_lo(u.z); v[5] = bf_hi(u.z); v[6] = bf_lo(u.w); v[7] = bf_hi(u.w);
+        if constexpr (NPL == 12) {
+          const uint2 w = *reinterpret_cast<const uint2*>(p + 256 + 4 * lane);
+          v[8] = bf_lo(w.x); v[9] = bf_hi(w.x); v[10] = bf_lo(w.y); v[11] = bf_hi(w.y);
+        }
+      } else {
+        const uint2 w = *reinterpret_cast<const uint2*>(p + 4 * lane);
+        v[0] = bf_lo(w.x); v[1] = bf_hi(w.x); v[2] = bf_lo(w.y); v[3] = bf_hi(w.y);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NPL / 4; ++c) {
+        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + 128 * c + 4 * lane);
+        v[4 * c] = f.x; v[4 * c + 1] = f.y; v[4 * c + 2] = f.z; v[4 * c + 3] = f.w;
+      }
+    }
+  }
+  __device__ __forceinline__ static void store(T* __restrict__ p, int lane, const float (&v)[NPL]) {
+    if constexpr (!VEC) {
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) p[lane + 32 * k] = from_f32<T>(v[k]);
+    } else if constexpr (sizeof(T) == 2) {
+      if constexpr (NPL >= 8) {
+        *reinterpret_cast<uint4*>(p + 8 * lane) = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
+        if constexpr (NPL == 12) *reinterpret_cast<uint2*>(p + 256 + 4 * lane) = make_uint2(pack_bf2(v[8], v[9]), pack_bf2(v[10], v[11]));
+      } else {
+        *reinterpret_cast<uint2*>(p + 4 * lane) = make_uint2(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NPL / 4; ++c)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + 128 * c + 4 * lane) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
+  }
+};
+
 // =============================================================================================
 // emb[r] = mean_{k<16} relu(LayerNorm(y_pre[16 r + k]))  (AVGPoolPatchEmbedding, model/backbone_utils.py:160-167)
 // one warp per region; optional positional embedding added to the result (model/backbone.py:192-194)
@@ -45,19 +101,21 @@ __global__ void __launch_bounds__(256) ln_relu_mean16_fwd_kernel(const T* __rest
   constexpr int d = 32 * NPL;
   const int lane = threadIdx.x & 31, r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
+  using Map = RowMap<T, NPL>;
   float g[NPL], b[NPL], acc[NPL];
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) { g[k] = gamma[lane + 32 * k]; b[k] = beta[lane + 32 * k]; acc[k] = 0.f; }
+  for (int k = 0; k < NPL; ++k) { g[k] = gamma[Map::col(lane, k)]; b[k] = beta[Map::col(lane, k)]; acc[k] = 0.f; }
+#pragma unroll 2
   for (int i = 0; i < 16; ++i) {
     float v[NPL], mean, rstd;
-    row_load<T, NPL>(y_pre + ((size_t)r * 16 + i) * d, lane, v);
+    Map::load(y_pre + ((size_t)r * 16 + i) * d, lane, v);
     row_stats<NPL>(v, eps, mean, rstd);
 #pragma unroll
     for (int k = 0; k < NPL; ++k) acc[k] += fmaxf(fmaf((v[k] - mean) * rstd, g[k], b[k]), 0.f);
   }
 #pragma unroll
   for (int k = 0; k < NPL; ++k) {
-    const size_t o = (size_t)r * d + lane + 32 * k;
+    const size_t o = (size_t)r * d + Map::col(lane, k);
     emb[o] = acc[k] * (1.0f / 16.0f) + (pe ? pe[o] : 0.f);
   }
 }
@@ -72,17 +130,19 @@ __global__ void __launch_bounds__(256) ln_relu_mean16_bwd_kernel(const T* __rest
   constexpr int d = 32 * NPL;
   __shared__ float red[8][3 * d];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  using Map = RowMap<T, NPL>;
   float g[NPL], b[NPL], dg[NPL], db[NPL], dc[NPL];
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) { g[k] = gamma[lane + 32 * k]; b[k] = beta[lane + 32 * k]; dg[k] = db[k] = dc[k] = 0.f; }
+  for (int k = 0; k < NPL; ++k) { g[k] = gamma[Map::col(lane, k)]; b[k] = beta[Map::col(lane, k)]; dg[k] = db[k] = dc[k] = 0.f; }
   for (int r = blockIdx.x * nw + wid; r < R; r += gridDim.x * nw) {
     float de[NPL];
 #pragma unroll
-    for (int k = 0; k < NPL; ++k) de[k] = d_emb[(size_t)r * d + lane + 32 * k] * (1.0f / 16.0f);
+    for (int k = 0; k < NPL; ++k) de[k] = d_emb[(size_t)r * d + Map::col(lane, k)] * (1.0f / 16.0f);
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) {
       const size_t row = (size_t)r * 16 + i;
       float v[NPL], mean, rstd;
-      row_load<T, NPL>(y_pre + row * d, lane, v);
+      Map::load(y_pre + row * d, lane, v);
       row_stats<NPL>(v, eps, mean, rstd);
       float gy[NPL], s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -98,17 +158,19 @@ __global__ void __launch_bounds__(256) ln_relu_mean16_bwd_kernel(const T* __rest
       }
       s1 = warp_sum(s1) * (1.0f / d);
       s2 = warp_sum(s2) * (1.0f / d);
+      float dy[NPL];
 #pragma unroll
       for (int k = 0; k < NPL; ++k) {
-        const float dy = rstd * (gy[k] - s1 - v[k] * s2);
-        dc[k] += dy;
-        d_y[row * d + lane + 32 * k] = from_f32<T>(dy);
+        dy[k] = rstd * (gy[k] - s1 - v[k] * s2);
+        dc[k] += dy[k];
       }
+      Map::store(d_y + row * d, lane, dy);
     }
   }
 #pragma unroll
   for (int k = 0; k < NPL; ++k) {
-    red[wid][lane + 32 * k] = dg[k]; red[wid][d + lane + 32 * k] = db[k]; red[wid][2 * d + lane + 32 * k] = dc[k];
+    const int c = Map::col(lane, k);
+    red[wid][c] = dg[k]; red[wid][d + c] = db[k]; red[wid][2 * d + c] = dc[k];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) {
