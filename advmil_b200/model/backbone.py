@@ -118,15 +118,25 @@ class DeepAttMISL(_GatedMILBase):
         return ops.GenConfig(C=h, h=h, o=h, hid=hid, noise0=noise[0], noise1=noise[1], out_scale=out_scale,
                              p_backbone=self.p, p_head=p_head, has_rho=False)
 
-    def cluster_rows(self, x_path: torch.Tensor, cluster_id: torch.Tensor, lengths=None) -> torch.Tensor:
-        """[rows,C] (+ ids) -> per-(bag, cluster) mean of relu(phis(x)) [bags*num_clusters, h], differentiable."""
+    def cluster_rows(self, x_path: torch.Tensor, cluster_id: torch.Tensor, lengths=None, offsets=None) -> torch.Tensor:
+        """[rows,C] (+ ids) -> per-(bag, cluster) mean of relu(phis(x)) [bags*num_clusters, h], differentiable.
+        offsets: the packed bags' int32 device offsets when the caller already has them (building them here costs a
+        synchronous pageable H2D copy, i.e. a host-device sync per call)."""
         x = x_path[0] if x_path.dim() == 3 else x_path
         cid = cluster_id.reshape(-1)  # accepts the handler's [1,N] as well as [N] (reference quirk A.4#7)
         assert cid.shape[0] == x.shape[0], "one cluster id per instance (dataset/PatchWSI.py:93)"
         lengths = [x.shape[0]] if lengths is None else lengths
         W = self.phis[0].weight
-        return ClusterPoolFn.apply(x, cid.to(torch.int32), lengths, self.num_clusters,
-                                   ops.PRECISIONS[get_precision()], W.reshape(W.shape[0], -1), self.phis[0].bias)
+        return ClusterPoolFn.apply(x, cid if cid.dtype == torch.int32 else cid.to(torch.int32), lengths, self.num_clusters,
+                                   ops.PRECISIONS[get_precision()], W.reshape(W.shape[0], -1), self.phis[0].bias, offsets)
+
+    def cluster_bags(self, hc: torch.Tensor, n_bags: int) -> "ops.PackedBags":
+        """Packed view of the per-(bag, cluster) rows: num_clusters rows per bag; the device offsets are cached per shape."""
+        key = (n_bags, str(hc.device))
+        cache = self.__dict__.setdefault("_cluster_offsets", {})
+        if key not in cache:
+            cache[key] = torch.arange(0, (n_bags + 1) * self.num_clusters, self.num_clusters, dtype=torch.int32, device=hc.device)
+        return ops.PackedBags(hc, [self.num_clusters] * n_bags, offsets=cache[key])
 
     def forward(self, x_path, cluster_id, *args):
         hc = self.cluster_rows(x_path, cluster_id)
@@ -210,11 +220,11 @@ class ClusterPoolFn(torch.autograd.Function):
     """K9: hx = relu(x Wphi^T + b) on every row (projection GEMM), then segment-mean by cluster id."""
 
     @staticmethod
-    def forward(ctx, x, cid, lengths, ncl, precision, W, b):
+    def forward(ctx, x, cid, lengths, ncl, precision, W, b, offsets=None):
         import ctypes as C
         from .. import _lib
         lib = _lib.load()
-        bags = ops.PackedBags(x.detach(), lengths).for_precision(precision)
+        bags = ops.PackedBags(x.detach(), lengths, offsets=offsets).for_precision(precision)
         hx = ops.linear_forward(bags.x, W.detach(), b.detach(), act=1, precision=precision)
         elem = ops.ELEM_BF16 if hx.dtype == torch.bfloat16 else ops.ELEM_F32
         h = W.shape[0]
@@ -243,4 +253,4 @@ class ClusterPoolFn(torch.autograd.Function):
                                                      counts.data_ptr(), bags.rows, bags.bags, h, ncl, 1, d_hx.data_ptr(),
                                                      torch.cuda.current_stream().cuda_stream), "advmil_segment_mean_by_id_bwd")
         _, dW, db = ops.linear_backward(d_hx, bags.x, W.detach(), need_dx=False, precision=precision)
-        return None, None, None, None, None, dW.reshape(W.shape), db
+        return None, None, None, None, None, dW.reshape(W.shape), db, None

@@ -72,6 +72,34 @@ def _cached_cast(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+_OFFS_RING: dict = {}      # device -> [pinned int32 ring, next slot]
+_OFFS_SLOT, _OFFS_SLOTS = 1024, 64
+
+
+def _device_offsets(offs, device) -> torch.Tensor:
+    """int32 offsets [bags + 1] on the device WITHOUT a host-device synchronisation: `torch.tensor(list, device=cuda)` is a
+    pageable copy that blocks the host until the device has drained, once per module call in the reference's per-bag loop.
+    One bag (the handler's batch_size 1): generated on the device (arange).  Several bags: staged through a ring of pinned
+    slots and copied asynchronously (a slot is reused after 64 later calls; longer offset lists fall back to the blocking copy)."""
+    if device.type != "cuda":
+        return torch.tensor(offs, dtype=torch.int32, device=device)
+    if len(offs) == 2 and offs[1] > 0:
+        return torch.arange(0, offs[1] + 1, offs[1], dtype=torch.int32, device=device)
+    if len(offs) > _OFFS_SLOT:
+        return torch.tensor(offs, dtype=torch.int32, device=device)
+    ring = _OFFS_RING.get(device)
+    if ring is None:
+        try:
+            ring = [torch.empty(_OFFS_SLOTS, _OFFS_SLOT, dtype=torch.int32).pin_memory(), 0]
+        except RuntimeError:
+            return torch.tensor(offs, dtype=torch.int32, device=device)
+        _OFFS_RING[device] = ring
+    slot = ring[0][ring[1] % _OFFS_SLOTS, :len(offs)]
+    ring[1] += 1
+    slot.copy_(torch.tensor(offs, dtype=torch.int32))
+    return slot.to(device, non_blocking=True)
+
+
 class PackedBags:
     """Packed variable-length bags: x [rows, C] fp32 (or bf16 for the bf16 mode) + int32 offsets [bags+1] (AdvmilBags)."""
 
@@ -89,7 +117,7 @@ class PackedBags:
             offs.append(offs[-1] + n)
         self.offsets_list = offs
         self.offsets_host = (C.c_int32 * len(offs))(*offs)
-        self.offsets = torch.tensor(offs, dtype=torch.int32, device=x.device) if offsets is None else offsets
+        self.offsets = _device_offsets(offs, x.device) if offsets is None else offsets
         self.rows, self.C = self.x.shape
         self.bags = len(self.lengths)
 

@@ -272,7 +272,15 @@ class ModuleAdvStep(_DataParallelMixin):
         self.coef_gan, self.coef_l1, self.loss_d = coef_gan, coef_l1, loss_d
         self.recon_alpha, self.recon_gamma = recon_alpha, recon_gamma
         self.precision, self.precision_name = ops.PRECISIONS[precision], precision
+        self._gmods, self._dmods = list(netG.modules()), list(netD.modules())
         self._init_dp(process_group)
+
+    @staticmethod
+    def _set_training(mods, flag: bool):
+        """nn.Module.train(flag) without the recursion and the __setattr__ hooks: ~150 sub-modules are toggled four times per
+        step, which cost 1.5 ms of host time per step through the module API."""
+        for m in mods:
+            m.__dict__["training"] = flag
 
     def step(self, *args, **kwargs) -> Dict:
         """See `_step`; runs it under this engine's precision mode (the modules read the package-wide setting)."""
@@ -312,9 +320,9 @@ class ModuleAdvStep(_DataParallelMixin):
         kind = G.backbone.kind
         if kind == "cluster":
             bb = G.backbone
-            hc = bb.cluster_rows(bags.x, ext, bags.lengths)          # [bags * clusters, h], differentiable
+            hc = bb.cluster_rows(bags.x, ext, bags.lengths, offsets=bags.offsets)          # [bags * clusters, h], differentiable
             # the attention stage sees num_clusters rows per bag: always the exact fp32 engine (like Generator.forward)
-            return G.forward_packed(ops.PackedBags(hc, [bb.num_clusters] * bags.bags), noise=noise, x_grad=hc, precision=ops.FP32)
+            return G.forward_packed(bb.cluster_bags(hc, bags.bags), noise=noise, x_grad=hc, precision=ops.FP32)
         kw = {"coord": coord, "reuse_embedding": reuse, "acts_sink": sink} if kind == "patch" else {}
         return G.forward_packed(bags, noise=noise, precision=self.precision, **kw)
 
@@ -335,8 +343,8 @@ class ModuleAdvStep(_DataParallelMixin):
         nz_d = [None, noise_d if noise_d is not None else self._draw(nb, dev)]
         nz_g = [None, noise_g if noise_g is not None else self._draw(nb, dev)]
         # ---------------- D step: D.train / G.eval (model_handler.py:355-356) ----------------
-        D.train()
-        G.eval()
+        self._set_training(self._dmods, True)
+        self._set_training(self._gmods, False)
         self.D.grad.zero_()
         with torch.no_grad():
             sink = [] if G.backbone.kind == "patch" else None      # this step's own hand-off of the patch embedding
@@ -354,8 +362,8 @@ class ModuleAdvStep(_DataParallelMixin):
         self._allreduce(self.D.grad)
         self.D.adam(self.lr_d)
         # ---------------- G step: D.eval / G.train (model_handler.py:432-433) ----------------
-        D.eval()
-        G.train()
+        self._set_training(self._dmods, False)
+        self._set_training(self._gmods, True)
         self.G.grad.zero_()
         for p in self.dparams:
             p.requires_grad_(False)         # D only hands dL/dt back to G
@@ -422,7 +430,7 @@ def _sample_inference(netG, netD, bags, times_test_sample, zero_noise, precision
         elif kind == "cluster":        # DeepAttMISL: per-(bag, cluster) means, then the 8-row attention stage in fp32
             assert ext is not None, "the cluster generator needs the cluster id of every row (ext)"
             bb = netG.backbone
-            hc = bb.cluster_rows(bags.x, ext, bags.lengths)
+            hc = bb.cluster_rows(bags.x, ext, bags.lengths, offsets=bags.offsets)
             acts = ops.generator_forward(cfg, params, ops.PackedBags(hc, [bb.num_clusters] * nb), n0, n1, train=False,
                                          precision=ops.FP32, save=False)
             y_hat, H = acts["pred"].reshape(nb, 1), acts["H"]
