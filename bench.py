@@ -578,7 +578,7 @@ def run_esat(args, rank, world, local_rank):
     if "attn_fwd" in kern and args.precision != "fp32":
         roof = {"kernel": "attn_fwd", "bound": "tensor", "achieved": kern["attn_fwd"]["tflops"], "peak": peaks["tflops"] / 2, "unit": "TFLOP/s",
                 "frac": kern["attn_fwd"]["tflops"] / (peaks["tflops"] / 2), "traffic": None,
-                "peak_source": f"{peaks['src']} bf16 {peaks['kind']} / 2 (tf32 operands; warp-level mma.sync kernels)"}
+                "peak_source": f"{peaks['src']} bf16 {peaks['kind']} / 2 (tf32 operands; tcgen05 forward kernel, eval and train launches averaged)"}
     p12 = args.precision == "bf16" and args.transport in ("p12", "vl")
     if p12:
         for st in steps[:2]:
