@@ -237,3 +237,27 @@ extern "C" int advmil_sincos_pe(const int64_t* coord, const int32_t* offsets, in
   ADVMIL_CHECK_LAUNCH();
   return sincos_pe(coord, ro, bags, d, omega, pe, st);
 }
+
+// ---- stage-level entry points of the self-attention (kernel unit tests: every head width / ragged region counts) ----------
+extern "C" int advmil_mha_fwd(const float* qkv, const int32_t* region_offsets, const int32_t* region_offsets_host, int32_t bags,
+                              int32_t d, int32_t heads, float p_drop, uint64_t seed, int32_t train, const uint8_t* mask,
+                              const int64_t* mask_off, int32_t precision, float* ctx, float* lse, void* stream) {
+  ADVMIL_REQUIRE(qkv && region_offsets && region_offsets_host && ctx && lse && bags > 0 && heads > 0 && d % heads == 0,
+                 "mha_fwd: bad arguments");
+  const int R = region_offsets_host[bags];
+  const Drop dr = Drop::make(nullptr, seed, SITE_ATT, p_drop, train, 0);
+  return mha_fwd(qkv, region_offsets, region_offsets_host, bags, R, d, heads, dr, mask, mask_off, ctx, lse, attention_precision(precision),
+                 (cudaStream_t)stream);
+}
+
+extern "C" int advmil_mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float* lse, const int32_t* region_offsets,
+                              const int32_t* region_offsets_host, int32_t bags, int32_t d, int32_t heads, float p_drop, uint64_t seed,
+                              int32_t train, const uint8_t* mask, const int64_t* mask_off, int32_t precision, float* d_qkv,
+                              float* scratch /* [heads * R] */, void* stream) {
+  ADVMIL_REQUIRE(qkv && ctx && d_ctx && lse && region_offsets && region_offsets_host && d_qkv && scratch && bags > 0 && heads > 0 &&
+                 d % heads == 0, "mha_bwd: bad arguments");
+  const int R = region_offsets_host[bags];
+  const Drop dr = Drop::make(nullptr, seed, SITE_ATT, p_drop, train, 0);
+  return mha_bwd(qkv, ctx, d_ctx, lse, region_offsets, region_offsets_host, bags, R, d, heads, dr, mask, mask_off, d_qkv, scratch,
+                 attention_precision(precision), (cudaStream_t)stream);
+}

@@ -419,6 +419,19 @@ ADVMIL_API int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams*
 ADVMIL_API int advmil_sincos_pe(const int64_t* coord, const int32_t* offsets /* bag row offsets [bags+1], device */, int32_t bags,
                      int32_t d, const float* omega, float* pe, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- ESAT self-attention, stage level (nn.MultiheadAttention inside the encoder layer, model/backbone_utils.py:112-127):
+ *      qkv [R, 3d] fp32 (the packed in-projection), region offsets [bags+1] on the device and on the host, -> ctx [R, d],
+ *      lse [heads, R].  Dropout on the probabilities by the counter generator (seed, train, p_drop) or injected per-bag masks
+ *      [heads, Rb, Rb] at mask_off[bag].  precision FP32 / TF32X3 = FFMA kernels, TF32 / BF16 = tensor-core kernels (forward on
+ *      tcgen05 for head widths 16/32/48/64).  Used by the kernel unit tests; the model goes through advmil_esat_fwd/bwd. */
+ADVMIL_API int advmil_mha_fwd(const float* qkv, const int32_t* region_offsets, const int32_t* region_offsets_host, int32_t bags,
+                   int32_t d, int32_t heads, float p_drop, uint64_t seed, int32_t train, const uint8_t* mask,
+                   const int64_t* mask_off, int32_t precision, float* ctx, float* lse, void* stream);
+ADVMIL_API int advmil_mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float* lse, const int32_t* region_offsets,
+                   const int32_t* region_offsets_host, int32_t bags, int32_t d, int32_t heads, float p_drop, uint64_t seed,
+                   int32_t train, const uint8_t* mask, const int64_t* mask_off, int32_t precision, float* d_qkv,
+                   float* scratch /* [heads * R] */, void* stream);
+
 /* ---- lossless 12-bit transport format of bf16 features (the packed loader that replaces dataset/PatchWSI.py:65-94 +
  *      model_handler.py:315-316's `.cuda()`): lo[n] = sign<<7 | mantissa, hi[n/2] = two 4-bit exponent codes, table16 (HOST
  *      pointer, code -> exponent byte, code 15 = escape), escapes (element index, exponent byte).  Decodes n elements
