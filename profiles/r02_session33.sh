@@ -1,0 +1,9 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_esat.py tests/test_gpu_attention.py tests/test_gpu_step.py tests/test_gpu_dropin_loop.py -q -m gpu 2>&1 | grep -v "^  \|Warning\|^$" | tail -8 | cut -c1-300
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k 'regex:mha_|att_bits' -c 16 --csv --log-file gpurun_out/esat_attn_list.csv python profiles/esat_bench.py --modes bf16 --steps 3 > /dev/null 2>&1
+grep "mha\|att_bits" gpurun_out/esat_attn_list.csv | awk -F'","' '{print substr($5,1,44), $NF}'
+timeout 300 python profiles/esat_bench.py --modes bf16 --steps 10 2>&1 | grep "^{" | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print({k:d[k] for k in d if k in ('what','ms_per_call','ms_per_step','bags_per_s')})"
