@@ -248,3 +248,26 @@ def test_region_index_map_closed_form_at_maximum_size():
     n = np.arange(rows)
     assert np.array_equal(reg[:, 0], n // 16) and np.array_equal(reg[:, 1], (n % 16) // 4) and np.array_equal(reg[:, 2], n % 4)
     assert int(reg[:, 0].astype(np.int64).sum()) == int((n // 16).sum())
+
+
+@pytest.mark.parametrize("form", ["vl", "p12"])
+def test_transport_forms_are_bit_exact_at_the_full_step_size(form):
+    """BASELINE.json's step size (16 x 16384 x 1024 bf16 = 268 M elements) through the packed loader's transport forms:
+    encode on the host, copy + decode on the device (DeviceFeeder), compare every word with the stored bf16 features -- for
+    Gaussian features with injected zeros, denormals, infinities and NaN payloads (escapes)."""
+    from advmil_b200.dataset.packed import DeviceFeeder, PinnedStep
+    torch.manual_seed(11)
+    rows, C = 16 * 16384, 1024
+    x = torch.randn(rows, C).to(torch.bfloat16)
+    v = x.view(torch.int16).reshape(-1)
+    idx = torch.randint(0, v.numel(), (4096,))
+    v[idx] = torch.randint(-32768, 32767, (4096,), dtype=torch.int32).to(torch.int16)        # arbitrary bit patterns: escapes
+    v[:64] = 0
+    st = PinnedStep(x=x, lengths=[16384] * 16, t=torch.rand(16), e=torch.ones(16), idx=torch.arange(16, dtype=torch.int32),
+                    visible=torch.ones(16, dtype=torch.uint8))
+    st = st.packvl() if form == "vl" else st.pack12()
+    bits = 8.0 * st.nbytes / x.numel()
+    assert (bits < 11.1) if form == "vl" else (bits < 12.1)
+    for dv in DeviceFeeder([st], device="cuda", depth=2):
+        torch.cuda.synchronize()
+        assert torch.equal(dv.bags.x.view(torch.int16).cpu(), x.view(torch.int16))
