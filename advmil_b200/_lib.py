@@ -161,6 +161,8 @@ SYMBOLS = {
     "advmil_mha_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _u64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "advmil_bf16p12_decode": (C.c_int, [_vp, _vp, C.c_char_p, _vp, _vp, _i64, _i32, _vp, _vp]),
     "advmil_bf16vl_encode": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _P(_i64), _P(_i64)]),
+    "advmil_bf16vl_tables": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "advmil_bf16vl_encode_with_tables": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _P(_i64), _P(_i64)]),
     "advmil_bf16vl_decode_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "advmil_bf16vl_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
 }

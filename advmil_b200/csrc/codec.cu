@@ -184,13 +184,8 @@ void vl_codes(const uint8_t (&len)[16], uint16_t (&code)[16]) {
 }
 }  // namespace
 
-extern "C" int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words, uint32_t* sbase,
-                                    uint16_t* loff, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16, int32_t* esc_idx,
-                                    uint8_t* esc_exp, int64_t esc_cap, int64_t* stream_words, int64_t* n_esc) {
-  ADVMIL_REQUIRE(x && lo && stream && sbase && loff && tab_exp16 && tab_len16 && tab_code16 && stream_words && n_esc && n >= 0 &&
-                 n % VL_SUPER == 0 && n < ((int64_t)1 << 31), "bf16vl_encode: bad arguments (n must be a multiple of 4096, < 2^31)");
-  uint64_t hist[256] = {};
-  for (int64_t i = 0; i < n; ++i) ++hist[(x[i] >> 7) & 0xFF];
+// tables of a file / step from its exponent histogram: the 15 most frequent exponent bytes + escape, code lengths, codes
+static void vl_tables_from_hist(const uint64_t* hist, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16) {
   int order[256];
   for (int i = 0; i < 256; ++i) order[i] = i;
   for (int i = 0; i < 15; ++i) {            // the 15 most frequent exponent bytes (ties: smaller byte first)
@@ -198,16 +193,30 @@ extern "C" int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, u
     for (int j = i + 1; j < 256; ++j) if (hist[order[j]] > hist[order[best]] || (hist[order[j]] == hist[order[best]] && order[j] < order[best])) best = j;
     const int t = order[i]; order[i] = order[best]; order[best] = t;
   }
-  uint8_t sym_of[256];
   uint64_t cnt[16] = {};
-  for (int i = 0; i < 256; ++i) sym_of[i] = 15;
-  for (int s = 0; s < 15; ++s) { sym_of[order[s]] = (uint8_t)s; tab_exp16[s] = (uint8_t)order[s]; cnt[s] = hist[order[s]]; }
+  for (int s = 0; s < 15; ++s) { tab_exp16[s] = (uint8_t)order[s]; cnt[s] = hist[order[s]]; }
   tab_exp16[15] = 0;
   for (int i = 15; i < 256; ++i) cnt[15] += hist[order[i]];
   uint8_t len[16]; uint16_t code[16];
   vl_lengths(cnt, len);
   vl_codes(len, code);
   for (int s = 0; s < 16; ++s) { tab_len16[s] = len[s]; tab_code16[s] = code[s]; }
+}
+
+extern "C" int advmil_bf16vl_tables(const uint64_t* hist256, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16) {
+  ADVMIL_REQUIRE(hist256 && tab_exp16 && tab_len16 && tab_code16, "bf16vl_tables: null argument");
+  vl_tables_from_hist(hist256, tab_exp16, tab_len16, tab_code16);
+  return ADVMIL_OK;
+}
+
+static int vl_encode_body(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words, uint32_t* sbase,
+                          uint16_t* loff, const uint8_t* tab_exp16, const uint8_t* tab_len16, const uint16_t* tab_code16,
+                          int32_t* esc_idx, uint8_t* esc_exp, int64_t esc_cap, int64_t* stream_words, int64_t* n_esc) {
+  uint8_t sym_of[256], len[16];
+  uint16_t code[16];
+  for (int i = 0; i < 256; ++i) sym_of[i] = 15;
+  for (int s = 0; s < 16; ++s) { len[s] = tab_len16[s]; code[s] = tab_code16[s]; }
+  for (int s = 14; s >= 0; --s) if (len[s]) sym_of[tab_exp16[s]] = (uint8_t)s;      // unused table slots (length 0) map nothing
   int64_t w = 0, ne = 0;
   const int64_t nsuper = n / VL_SUPER;
   for (int64_t sb = 0; sb < nsuper; ++sb) {
@@ -224,6 +233,7 @@ extern "C" int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, u
           const uint8_t ex = (uint8_t)((v >> 7) & 0xFF), s = sym_of[ex];
           lo[i] = (uint8_t)(((v >> 8) & 0x80) | (v & 0x7F));
           if (s == 15) {
+            ADVMIL_REQUIRE(len[15] != 0, "bf16vl_encode: an exponent outside the given tables, which have no escape code");
             ADVMIL_REQUIRE(esc_idx && esc_exp && ne < esc_cap, "bf16vl_encode: escape list too small");
             esc_idx[ne] = (int32_t)i; esc_exp[ne] = ex; ++ne;
           }
@@ -244,6 +254,35 @@ extern "C" int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, u
   *stream_words = w + 2;
   *n_esc = ne;
   return ADVMIL_OK;
+}
+
+static int vl_check_args(const void* x, int64_t n, const void* lo, const void* stream, const void* sbase, const void* loff, const void* te,
+                         const void* tl, const void* tc, const void* sw, const void* ne) {
+  ADVMIL_REQUIRE(x && lo && stream && sbase && loff && te && tl && tc && sw && ne && n >= 0 && n % VL_SUPER == 0 && n < ((int64_t)1 << 31),
+                 "bf16vl_encode: bad arguments (n must be a multiple of 4096, < 2^31)");
+  return ADVMIL_OK;
+}
+
+extern "C" int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words, uint32_t* sbase,
+                                    uint16_t* loff, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16, int32_t* esc_idx,
+                                    uint8_t* esc_exp, int64_t esc_cap, int64_t* stream_words, int64_t* n_esc) {
+  ADVMIL_TRY(vl_check_args(x, n, lo, stream, sbase, loff, tab_exp16, tab_len16, tab_code16, stream_words, n_esc));
+  uint64_t hist[256] = {};
+  for (int64_t i = 0; i < n; ++i) ++hist[(x[i] >> 7) & 0xFF];
+  vl_tables_from_hist(hist, tab_exp16, tab_len16, tab_code16);
+  return vl_encode_body(x, n, lo, stream, stream_cap_words, sbase, loff, tab_exp16, tab_len16, tab_code16, esc_idx, esc_exp, esc_cap,
+                        stream_words, n_esc);
+}
+
+// same with GIVEN tables (advmil_bf16vl_tables over a whole file): every bag of a packed file shares one table, so the planes
+// and streams of any selection of bags concatenate into a step without re-encoding
+extern "C" int advmil_bf16vl_encode_with_tables(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words,
+                                                uint32_t* sbase, uint16_t* loff, const uint8_t* tab_exp16, const uint8_t* tab_len16,
+                                                const uint16_t* tab_code16, int32_t* esc_idx, uint8_t* esc_exp, int64_t esc_cap,
+                                                int64_t* stream_words, int64_t* n_esc) {
+  ADVMIL_TRY(vl_check_args(x, n, lo, stream, sbase, loff, tab_exp16, tab_len16, tab_code16, stream_words, n_esc));
+  return vl_encode_body(x, n, lo, stream, stream_cap_words, sbase, loff, tab_exp16, tab_len16, tab_code16, esc_idx, esc_exp, esc_cap,
+                        stream_words, n_esc);
 }
 
 extern "C" int advmil_bf16vl_decode_host(const uint8_t* lo, const uint32_t* stream, const uint32_t* sbase, const uint16_t* loff,

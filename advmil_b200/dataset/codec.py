@@ -134,9 +134,21 @@ def _np_ptr(a: np.ndarray) -> int:
     return a.ctypes.data
 
 
-def encode_bf16_vl(x: torch.Tensor) -> VL:
+def vl_tables(hist256: np.ndarray):
+    """(tab_exp, tab_len, tab_code) from an exponent histogram (256 counts), e.g. of a whole packed file."""
+    from .. import _lib
+    lib = _lib.load()
+    h = np.ascontiguousarray(hist256, dtype=np.uint64)
+    assert h.size == 256
+    te, tl, tc = np.zeros(16, np.uint8), np.zeros(16, np.uint8), np.zeros(16, np.uint16)
+    _lib.check(lib.advmil_bf16vl_tables(_np_ptr(h), _np_ptr(te), _np_ptr(tl), _np_ptr(tc)), "advmil_bf16vl_tables")
+    return te, tl, tc
+
+
+def encode_bf16_vl(x: torch.Tensor, tables=None) -> VL:
     """x: bfloat16 CPU tensor with numel % 4096 == 0 (and < 2^31 elements) -> VL (pageable; call .pin() for the feeder).
-    The encoder is the library's host function advmil_bf16vl_encode (one sequential pass, ~1 ns per element)."""
+    The encoder is the library's host function advmil_bf16vl_encode (one sequential pass, ~1 ns per element).
+    tables: (tab_exp, tab_len, tab_code) from `vl_tables` to encode with a shared (per-file) table instead of x's own."""
     import ctypes as C
     from .. import _lib
     lib = _lib.load()
@@ -148,13 +160,17 @@ def encode_bf16_vl(x: torch.Tensor) -> VL:
     stream = np.empty(cap, dtype=np.uint32)
     sbase = np.empty(max(n // 4096, 1), dtype=np.uint32)
     loff = np.empty(max(n // 128, 1), dtype=np.uint16)
-    te, tl, tc = np.zeros(16, np.uint8), np.zeros(16, np.uint8), np.zeros(16, np.uint16)
+    if tables is None:
+        te, tl, tc = np.zeros(16, np.uint8), np.zeros(16, np.uint8), np.zeros(16, np.uint16)
+        fn = lib.advmil_bf16vl_encode
+    else:
+        te, tl, tc = (np.ascontiguousarray(t) for t in tables)
+        fn = lib.advmil_bf16vl_encode_with_tables
     esc_cap = n
     ei, ee = np.empty(esc_cap, dtype=np.int32), np.empty(esc_cap, dtype=np.uint8)
     words, nesc = C.c_int64(0), C.c_int64(0)
-    _lib.check(lib.advmil_bf16vl_encode(_np_ptr(v), n, _np_ptr(lo), _np_ptr(stream), cap, _np_ptr(sbase), _np_ptr(loff), _np_ptr(te),
-                                        _np_ptr(tl), _np_ptr(tc), _np_ptr(ei), _np_ptr(ee), esc_cap, C.byref(words), C.byref(nesc)),
-               "advmil_bf16vl_encode")
+    _lib.check(fn(_np_ptr(v), n, _np_ptr(lo), _np_ptr(stream), cap, _np_ptr(sbase), _np_ptr(loff), _np_ptr(te), _np_ptr(tl), _np_ptr(tc),
+                  _np_ptr(ei), _np_ptr(ee), esc_cap, C.byref(words), C.byref(nesc)), "advmil_bf16vl_encode")
     w, m = int(words.value), int(nesc.value)
     return VL(torch.from_numpy(lo), torch.from_numpy(stream[:w].copy().view(np.int32)), torch.from_numpy(sbase[:n // 4096].view(np.int32)),
               torch.from_numpy(loff[:n // 128].view(np.int16)), te, tl, tc, torch.from_numpy(ei[:m].copy()), torch.from_numpy(ee[:m].copy()),

@@ -19,6 +19,13 @@ Layout (little endian):
     plane uint8[rows * C], then (4096-aligned) the `hi` plane uint8[rows * C / 2], then (4096-aligned) the code table
     uint8[16], n_esc int64, the sorted global escape indices int64[n_esc] and their exponent bytes uint8[n_esc].  One table
     for the whole file, so the planes of any selection of bags concatenate into a step without re-encoding.
+    dtype 3 (`transport="vl"`, the entropy-coded form of dataset/codec.py, ~10.9 bits per element): at feats_pos the `lo` plane
+    uint8[rows * C]; then (4096-aligned each) one page holding int64 tail_pos, the Huffman stream uint32[words] (bag after bag, every bag encoded on its own
+    with the FILE's tables and closed by two guard words), sbase uint32[rows * C / 4096] (word offset of a super-block inside
+    ITS BAG's stream), loff uint16[rows * C / 128]; then the tail: int64 words, int64 bag_words[n_bags + 1] (word offset of
+    every bag's stream), tab_exp uint8[16], tab_len uint8[16], tab_code uint16[16], n_esc int64, escape indices int64[n_esc]
+    (global element index), exponent bytes uint8[n_esc].  rows * C of every bag must be a multiple of 4096 (C = 1024 and 16-row
+    regions: always).
 """
 from __future__ import annotations
 
@@ -29,7 +36,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .codec import P12
+from .codec import P12, VL
 from .packed import PinnedStep, _pin
 
 MAGIC = b"ADVMILPK"
@@ -47,12 +54,12 @@ def write_packed(path: str, bags: Iterable[torch.Tensor], labels: Sequence[Seque
     """Streams `bags` ([N_i, C] tensors, e.g. the torch.cat of a patient's slides, PatchWSI.py:79) into `path`.
     transport="p12" (bf16 only) stores the lossless 12-bit form that the feeder copies to the device as is."""
     assert dtype in _DT, "features are stored as float32 or bfloat16"
-    assert transport in ("raw", "p12")
-    if transport == "p12":
-        assert dtype == torch.bfloat16, "the 12-bit transport form packs bf16 features"
+    assert transport in ("raw", "p12", "vl")
+    if transport in ("p12", "vl"):
+        assert dtype == torch.bfloat16, "the transport forms pack bf16 features"
         info = write_packed(path + ".raw", bags, labels, dtype, names, require_multiple_of)
         try:
-            return _convert_to_p12(path + ".raw", path, info)
+            return (_convert_to_p12 if transport == "p12" else _convert_to_vl)(path + ".raw", path, info)
         finally:
             os.remove(path + ".raw")
     labels = np.asarray(labels, dtype=np.float32).reshape(-1, 2)
@@ -142,6 +149,71 @@ def _convert_to_p12(raw_path: str, path: str, info: Dict[str, int], chunk_rows: 
     return {**info, "bytes": os.path.getsize(path), "escapes": int(ei.size)}
 
 
+def _align(v: int) -> int:
+    return (v + PAGE - 1) // PAGE * PAGE
+
+
+def _convert_to_vl(raw_path: str, path: str, info: Dict[str, int], chunk_rows: int = 1 << 15) -> Dict[str, int]:
+    """Second pass of write_packed(transport="vl"): one exponent histogram over the whole file -> one Huffman table; every
+    bag is then encoded on its own with that table (its sub-stream offsets are relative to the bag)."""
+    from .codec import encode_bf16_vl, vl_tables
+    src = PackedFile(raw_path)
+    C, rows = src.C, src.rows
+    hist = np.zeros(256, dtype=np.int64)
+    for a in range(0, rows, chunk_rows):
+        v = np.asarray(src._mm[a:a + chunk_rows]).reshape(-1)
+        hist += np.bincount(((v >> 7) & 0xFF).astype(np.uint8), minlength=256)
+    tabs = vl_tables(hist)
+    with open(raw_path, "rb") as f:
+        head = f.read(src._feats_pos)
+    n = rows * C
+    lo_pos = src._feats_pos
+    dir_pos = _align(lo_pos + n)            # one page: int64 tail_pos
+    stream_pos = dir_pos + PAGE
+    tmp = path + ".tmp"
+    sbase_all, loff_all, bag_words, esc_idx, esc_exp = [], [], [0], [], []
+    with open(tmp, "wb") as f:
+        f.write(head)
+        f.seek(stream_pos)
+        for i in range(src.n_bags):
+            a, b = int(src.offsets[i]), int(src.offsets[i + 1])
+            assert ((b - a) * C) % 4096 == 0, f"bag {i}: rows * C must be a multiple of 4096 for the vl form"
+            x = torch.from_numpy(np.array(src._mm[a:b])).view(torch.bfloat16)
+            p = encode_bf16_vl(x, tables=tabs)
+            f.write(p.stream.numpy().tobytes())
+            bag_words.append(bag_words[-1] + p.stream.numel())
+            sbase_all.append(p.sbase.numpy().view(np.uint32))
+            loff_all.append(p.loff.numpy().view(np.uint16))
+            esc_idx.append(p.esc_idx.numpy().astype(np.int64) + a * C)
+            esc_exp.append(p.esc_exp.numpy())
+            pos = f.tell()
+            f.seek(lo_pos + a * C)
+            f.write(p.lo.numpy().tobytes())
+            f.seek(pos)
+        words = bag_words[-1]
+        sbase_pos = _align(stream_pos + 4 * words)
+        loff_pos = _align(sbase_pos + 4 * (n // 4096))
+        tail_pos = _align(loff_pos + 2 * (n // 128))
+        f.seek(sbase_pos)
+        f.write(np.concatenate(sbase_all).astype(np.uint32).tobytes())
+        f.seek(loff_pos)
+        f.write(np.concatenate(loff_all).astype(np.uint16).tobytes())
+        ei, ee = np.concatenate(esc_idx), np.concatenate(esc_exp)
+        f.seek(tail_pos)
+        f.write(struct.pack("<q", words))
+        f.write(np.asarray(bag_words, dtype=np.int64).tobytes())
+        f.write(tabs[0].tobytes() + tabs[1].tobytes() + tabs[2].astype(np.uint16).tobytes())
+        f.write(struct.pack("<q", ei.size))
+        f.write(ei.tobytes())
+        f.write(ee.astype(np.uint8).tobytes())
+        f.seek(dir_pos)
+        f.write(struct.pack("<q", tail_pos))
+        f.seek(12)
+        f.write(struct.pack("<I", 3))
+    os.replace(tmp, path)
+    return {**info, "bytes": os.path.getsize(path), "escapes": int(ei.size), "bits_per_element": 8.0 * (os.path.getsize(path) - lo_pos) / n}
+
+
 def pack_reference_layout(patient_slides: Dict[str, List[str]], labels: Dict[str, Tuple[float, float]], out_path: str,
                           dtype: torch.dtype = torch.float32, trim_to_multiple_of: int = 16, transport: str = "raw") -> Dict[str, int]:
     """Converts the reference's per-slide `.pt` feature files (utils/io.py:78-101 `read_patch_data`, one [n, C] tensor per
@@ -179,13 +251,35 @@ class PackedFile:
             f.seek(npos)
             blob = f.read(fpos - npos).rstrip(b"\x00")
             self.names = blob.decode().split("\n") if blob else None
-        need = rows * C * 4 if dt == 0 else rows * C * 2 if dt == 1 else rows * C * 3 // 2
+        need = rows * C * 4 if dt == 0 else rows * C * 2 if dt == 1 else rows * C * 3 // 2 if dt == 2 else rows * C
         if int(self.offsets[-1]) != rows or os.path.getsize(path) < fpos + need:
             raise ValueError(f"{path}: truncated or inconsistent packed file")
         self.C, self.n_bags, self.rows, self.code = int(C), int(n_bags), int(rows), int(dt)
         self._feats_pos = int(fpos)
-        self.dtype = torch.bfloat16 if dt == 2 else _TORCH[dt]
-        if dt == 2:     # 12-bit transport form: two byte planes + table + sorted global escapes
+        self.dtype = torch.bfloat16 if dt in (2, 3) else _TORCH[dt]
+        if dt == 3:     # entropy-coded transport form: lo plane + per-bag Huffman streams + file-wide tables
+            n = self.rows * self.C
+            dir_pos = _align(fpos + n)
+            stream_pos = dir_pos + PAGE
+            with open(path, "rb") as f:
+                f.seek(dir_pos)
+                tail_pos = struct.unpack("<q", f.read(8))[0]
+                f.seek(tail_pos)
+                words = struct.unpack("<q", f.read(8))[0]
+                self._bag_words = np.frombuffer(f.read(8 * (n_bags + 1)), dtype=np.int64).copy()
+                self._tabs = (np.frombuffer(f.read(16), dtype=np.uint8).copy(), np.frombuffer(f.read(16), dtype=np.uint8).copy(),
+                              np.frombuffer(f.read(32), dtype=np.uint16).copy())
+                n_esc = struct.unpack("<q", f.read(8))[0]
+                self._esc_idx = np.frombuffer(f.read(8 * n_esc), dtype=np.int64).copy()
+                self._esc_exp = np.frombuffer(f.read(n_esc), dtype=np.uint8).copy()
+            sbase_pos = _align(stream_pos + 4 * words)
+            loff_pos = _align(sbase_pos + 4 * (n // 4096))
+            self._lo = np.memmap(path, dtype=np.uint8, mode="r", offset=fpos, shape=(self.rows, self.C))
+            self._stream = np.memmap(path, dtype=np.int32, mode="r", offset=stream_pos, shape=(int(words),))
+            self._sbase = np.memmap(path, dtype=np.int32, mode="r", offset=sbase_pos, shape=(n // 4096,))
+            self._loff = np.memmap(path, dtype=np.int16, mode="r", offset=loff_pos, shape=(n // 128,))
+            self._mm = None
+        elif dt == 2:     # 12-bit transport form: two byte planes + table + sorted global escapes
             hi_pos = (fpos + rows * C + PAGE - 1) // PAGE * PAGE
             tail_pos = (hi_pos + rows * C // 2 + PAGE - 1) // PAGE * PAGE
             self._lo = np.memmap(path, dtype=np.uint8, mode="r", offset=fpos, shape=(self.rows, self.C))
@@ -213,6 +307,9 @@ class PackedFile:
         if self.code == 2:
             from .codec import decode_p12_host
             return decode_p12_host(self._p12([i], pin=False))
+        if self.code == 3:
+            from .codec import decode_vl_host
+            return decode_vl_host(self._vl([i]))
         v = torch.from_numpy(np.array(self._mm[a:b]))
         return v.view(torch.bfloat16) if self.code == 1 else v
 
@@ -238,12 +335,41 @@ class PackedFile:
         mk = _pin if pin else (lambda v: v)
         return P12(lo, hi, self._table, mk(ei), mk(ee), (rows, self.C))
 
+    def _vl(self, indices: Sequence[int]) -> VL:
+        """The entropy-coded form of the bags `indices`, concatenated in step order: lo planes and streams as stored, the
+        super-block offsets re-based to the step's stream, escape indices re-based to the step (pageable; VL.pin() makes the
+        feeder's single pinned blob)."""
+        lens = [int(self.offsets[i + 1] - self.offsets[i]) for i in indices]
+        rows, C = sum(lens), self.C
+        lo = np.empty(rows * C, dtype=np.uint8)
+        streams, sbases, loffs, ei, ee, off, woff = [], [], [], [], [], 0, 0
+        for i, n in zip(indices, lens):
+            a = int(self.offsets[i])
+            lo[off * C:(off + n) * C] = self._lo[a:a + n].reshape(-1)
+            w0, w1 = int(self._bag_words[i]), int(self._bag_words[i + 1])
+            streams.append(np.asarray(self._stream[w0:w1]))
+            sbases.append(np.asarray(self._sbase[a * C // 4096:(a + n) * C // 4096]).astype(np.int64) + woff)
+            loffs.append(np.asarray(self._loff[a * C // 128:(a + n) * C // 128]))
+            l, r = np.searchsorted(self._esc_idx, [a * C, (a + n) * C])
+            ei.append(self._esc_idx[l:r] - a * C + off * C)
+            ee.append(self._esc_exp[l:r])
+            off += n
+            woff += w1 - w0
+        return VL(torch.from_numpy(lo), torch.from_numpy(np.concatenate(streams).astype(np.int32)),
+                  torch.from_numpy(np.concatenate(sbases).astype(np.uint32).view(np.int32)), torch.from_numpy(np.concatenate(loffs).astype(np.int16)),
+                  self._tabs[0], self._tabs[1], self._tabs[2], torch.from_numpy(np.concatenate(ei).astype(np.int32)),
+                  torch.from_numpy(np.concatenate(ee).copy()), (rows, C))
+
     def step(self, indices: Sequence[int], visible: Optional[Sequence[bool]] = None, pin: bool = True) -> PinnedStep:
         """The bags `indices` of one optimiser step as a pinned, packed buffer (page cache -> pinned memory, one copy)."""
         lens = [int(self.offsets[i + 1] - self.offsets[i]) for i in indices]
-        p12 = None
+        p12 = vl = None
         if self.code == 2:      # the planes go to the device as stored; the bf16 matrix only exists there
             p12 = self._p12(indices, pin)
+            x = torch.empty(0, self.C, dtype=torch.bfloat16)
+        elif self.code == 3:
+            vl = self._vl(indices)
+            vl = vl.pin() if pin else vl
             x = torch.empty(0, self.C, dtype=torch.bfloat16)
         else:
             x = torch.empty(sum(lens), self.C, dtype=self.dtype)
@@ -260,4 +386,4 @@ class PackedFile:
         vis = [True] * len(lens) if visible is None else list(visible)
         return PinnedStep(x=x, lengths=lens, t=mk(lab[:, 0].contiguous()), e=mk(lab[:, 1].contiguous()),
                           idx=torch.tensor(list(indices), dtype=torch.int32),
-                          visible=mk(torch.tensor([1 if v else 0 for v in vis], dtype=torch.uint8)), p12=p12)
+                          visible=mk(torch.tensor([1 if v else 0 for v in vis], dtype=torch.uint8)), p12=p12, vl=vl)

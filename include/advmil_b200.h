@@ -450,6 +450,14 @@ ADVMIL_API int advmil_bf16p12_decode(const uint8_t* lo, const uint8_t* hi, const
 ADVMIL_API int advmil_bf16vl_encode(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words, uint32_t* sbase,
                          uint16_t* loff, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16, int32_t* esc_idx,
                          uint8_t* esc_exp, int64_t esc_cap, int64_t* stream_words, int64_t* n_esc);
+/* tables from an exponent histogram (hist256[e] = number of elements with exponent byte e), e.g. of a whole packed file, and
+ * the encoder with GIVEN tables: every bag of a file then shares one table and the streams of any selection of bags
+ * concatenate into a step without re-encoding (advmil_b200/dataset/packed_file.py, transport "vl") */
+ADVMIL_API int advmil_bf16vl_tables(const uint64_t* hist256, uint8_t* tab_exp16, uint8_t* tab_len16, uint16_t* tab_code16);
+ADVMIL_API int advmil_bf16vl_encode_with_tables(const uint16_t* x, int64_t n, uint8_t* lo, uint32_t* stream, int64_t stream_cap_words,
+                                     uint32_t* sbase, uint16_t* loff, const uint8_t* tab_exp16, const uint8_t* tab_len16,
+                                     const uint16_t* tab_code16, int32_t* esc_idx, uint8_t* esc_exp, int64_t esc_cap,
+                                     int64_t* stream_words, int64_t* n_esc);
 ADVMIL_API int advmil_bf16vl_decode_host(const uint8_t* lo, const uint32_t* stream, const uint32_t* sbase, const uint16_t* loff,
                               const uint8_t* tab_exp16, const uint8_t* tab_len16, const uint16_t* tab_code16,
                               const int32_t* esc_idx, const uint8_t* esc_exp, int64_t n, int64_t n_esc, uint16_t* out);

@@ -411,16 +411,17 @@ def test_p12_transport_decodes_bit_exactly_on_the_device_and_through_the_feeder(
         assert s.bags.offsets.cpu().tolist() == [0, 640, 656, 1696, 2048]
 
 
-def test_p12_packed_file_through_the_feeder(tmp_path):
-    """A split stored in the 12-bit transport form (dataset/packed_file.py, transport="p12"): the feeder copies the planes
-    as stored and the device sees exactly the bf16 features of the raw bf16 file, step after step."""
+@pytest.mark.parametrize("transport", ["p12", "vl"])
+def test_p12_packed_file_through_the_feeder(tmp_path, transport):
+    """A split stored in a transport form (dataset/packed_file.py, transport="p12" / "vl"): the feeder copies the planes
+    (and Huffman streams) as stored and the device sees exactly the bf16 features of the raw bf16 file, step after step."""
     from advmil_b200.dataset.packed import DeviceFeeder, group_steps
     from advmil_b200.dataset.packed_file import PackedFile, write_packed
     g = torch.Generator().manual_seed(13)
     lens = [64, 320, 16, 160, 96, 48, 640, 32]
     bags = [torch.randn(n, 1024, generator=g) for n in lens]
     labels = [(0.1 + 0.1 * i, float(i % 2 == 0)) for i in range(len(lens))]
-    write_packed(str(tmp_path / "p12.advmil"), iter(bags), labels, dtype=torch.bfloat16, transport="p12")
+    write_packed(str(tmp_path / "p12.advmil"), iter(bags), labels, dtype=torch.bfloat16, transport=transport)
     pf = PackedFile(str(tmp_path / "p12.advmil"))
     groups = group_steps(len(pf), 4)
     for s, idx in zip(DeviceFeeder((pf.step(i) for i in groups), device="cuda"), groups):

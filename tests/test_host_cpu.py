@@ -295,3 +295,30 @@ def test_vl_transport_format_round_trip_is_bit_exact():
     assert torch.equal(decode_vl_host(pc).view(torch.int16), c.view(torch.int16)) and pc.bits_per_element < 9.5
     nn_ = torch.relu(torch.randn(8 * 4096)).mul(0.5).to(torch.bfloat16)          # non-negative features with exact zeros
     assert torch.equal(decode_vl_host(encode_bf16_vl(nn_)).view(torch.int16), nn_.view(torch.int16))
+
+
+def test_vl_packed_file_round_trip_and_step_assembly(tmp_path):
+    """transport="vl" on disk: one Huffman table per file, every bag encoded on its own; single bags and arbitrary step
+    selections decode (host reference decoder) to the bf16 words of the raw file, special values included; the file is
+    smaller than the p12 file."""
+    import os
+    from advmil_b200.dataset.codec import decode_vl_host
+    from advmil_b200.dataset.packed_file import PackedFile, write_packed
+    g = torch.Generator().manual_seed(17)
+    lens = [320, 1600, 48, 16, 2048]
+    bags = [torch.randn(n, 1024, generator=g) for n in lens]
+    bags[2][0, :7] = 0.0
+    bags[3].view(-1)[5] = float("inf")
+    bags[3].view(-1)[9] = 1e-40
+    labels = [(0.1 * i, float(i % 2)) for i in range(len(lens))]
+    vl = write_packed(str(tmp_path / "a.vl"), iter(bags), labels, dtype=torch.bfloat16, transport="vl", names=[f"p{i}" for i in range(5)])
+    p12 = write_packed(str(tmp_path / "a.p12"), iter(bags), labels, dtype=torch.bfloat16, transport="p12")
+    assert vl["bytes"] < 0.93 * p12["bytes"] and vl["bits_per_element"] < 11.1
+    pf = PackedFile(str(tmp_path / "a.vl"))
+    assert pf.names == [f"p{i}" for i in range(5)] and pf.lengths == lens
+    for i, b in enumerate(bags):
+        assert torch.equal(pf.bag(i).view(torch.int16), b.to(torch.bfloat16).view(torch.int16))
+    st = pf.step([3, 1, 4], pin=False)
+    want = torch.cat([bags[i] for i in (3, 1, 4)]).to(torch.bfloat16)
+    assert torch.equal(decode_vl_host(st.vl).view(torch.int16), want.view(torch.int16))
+    assert st.lengths == [16, 1600, 2048] and st.nbytes < 0.70 * want.numel() * 2
