@@ -21,4 +21,8 @@ bool mha_tcgen05_supported(int hd, int d);
 int mha_fwd_tcgen05(const float* qkv, const int32_t* ro, int bags, int Rtot, int d, int heads, int mx, float scale, const AttDrop& ad,
                     float* ctx, float* lse, cudaStream_t st);
 
+// tcgen05 backward (esat_attn_bwd_tc.cu): dQ pass + dK/dV pass, same head widths; Dq [heads, Rtot] scratch (D = dO . O)
+int mha_bwd_tcgen05(const float* qkv, const float* ctx, const float* d_ctx, const float* lse, const int32_t* ro, int bags, int Rtot, int d,
+                    int heads, int mx, float scale, const AttDrop& ad, float* d_qkv, float* Dq, cudaStream_t st);
+
 }  // namespace advmil

@@ -3,6 +3,7 @@
 // and multi-head self-attention over the regions of each bag (forward and backward).  Everything here works on
 // rows/16 "region" rows; the N-row contraction of the embedding runs on the GEMM engines (gemm_stages.cu).
 #include <limits.h>
+#include <stdlib.h>
 #include "stages.cuh"
 #include "esat_attn.cuh"
 
@@ -1000,6 +1001,12 @@ int mha_fwd(const float* qkv, const int32_t* ro, const int32_t* ro_host, int bag
   return ADVMIL_OK;
 }
 
+static bool mha_bwd_tcgen05_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("ADVMIL_ATTN_BWD_TCGEN05"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  return enabled != 0;
+}
+
 // Dq: [heads, Rtot] scratch
 int mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float* lse, const int32_t* ro, const int32_t* ro_host,
             int bags, int Rtot, int d, int heads, const Drop& drop, const uint8_t* mask, const int64_t* mask_off, float* d_qkv,
@@ -1011,6 +1018,8 @@ int mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float*
   for (int b = 0; b < bags; ++b) mx = max(mx, ro_host[b + 1] - ro_host[b]);
   const AttDrop ad = make_att_drop(drop, mask, mask_off, heads);
   const float scale = 1.0f / sqrtf((float)hd);
+  if (mha_use_tc(precision, hd) && mha_tcgen05_supported(hd, d) && mha_bwd_tcgen05_enabled())     // esat_attn_bwd_tc.cu
+    return mha_bwd_tcgen05(qkv, ctx, d_ctx, lse, ro, bags, Rtot, d, heads, mx, scale, ad, d_qkv, Dq, st);
   if (mha_use_tc(precision, hd)) {
     const dim3 grid(cdiv(mx, TCA_ROWS), bags, heads);
     ESAT_HD8_SWITCH(hd, (launch_k(mha_bwd_q_tc_kernel<HD>, grid, dim3(32 * TCA_WARPS), 0, st, qkv, ctx, d_ctx, lse, ro, d, scale, ad, d_qkv, Dq, Rtot)));
