@@ -107,8 +107,21 @@ class EsatActs(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("emb_ready", C.c_int32)]
 
 
+class EsatStepArgs(C.Structure):
+    _fields_ = [("esat", C.POINTER(EsatParams)), ("head", C.POINTER(GenParams)), ("disc", C.POINTER(DiscParams)),
+                ("esat_grads", C.POINTER(EsatGrads)), ("head_grads", C.POINTER(GenGrads)), ("disc_grads", C.POINTER(DiscGrads)),
+                ("bags", C.POINTER(Bags)),
+                ("t", c_fp), ("e", c_fp), ("visible", c_u8p), ("noise_d", c_fp), ("noise_g", c_fp), ("pe", c_fp),
+                ("seed_d", C.c_uint64), ("seed_g", C.c_uint64),
+                ("n_real", C.c_float), ("n_fake", C.c_float), ("n_visible", C.c_float), ("loss_d", C.c_int32),
+                ("coef_gan", C.c_float), ("recon_alpha", C.c_float), ("recon_gamma", C.c_float), ("recon_norm", C.c_int32),
+                ("precision", C.c_int32),
+                ("losses", c_fp), ("pred_d", c_fp), ("f_fake_d", c_fp), ("real_mask", c_u8p), ("pred_g", c_fp), ("f_fake_g", c_fp),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 ABI_STRUCTS = [Bags, GenParams, GenGrads, GenActs, DiscParams, DiscGrads, EmbedActs, HeadActs, StepArgs, EsatParams, EsatGrads,
-               EsatActs]
+               EsatActs, EsatStepArgs]
 
 # every symbol include/advmil_b200.h declares: name -> (restype, argtypes)
 _i32, _i64, _f, _vp, _sz, _u64 = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t, C.c_uint64
@@ -157,6 +170,9 @@ SYMBOLS = {
     "advmil_esat_fwd": (C.c_int, [_P(EsatParams), _P(GenParams), _P(Bags), _P(EsatActs), _vp]),
     "advmil_esat_bwd": (C.c_int, [_P(EsatParams), _P(GenParams), _P(Bags), _P(EsatActs), _vp, _P(EsatGrads), _P(GenGrads), _vp]),
     "advmil_sincos_pe": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "advmil_adv_step_esat_workspace_bytes": (_sz, [_P(EsatParams), _P(GenParams), _P(DiscParams), _i32, _i32, _i32]),
+    "advmil_adv_step_esat_disc": (C.c_int, [_P(EsatStepArgs), _vp]),
+    "advmil_adv_step_esat_gen": (C.c_int, [_P(EsatStepArgs), _vp]),
     "advmil_mha_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f, _u64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "advmil_mha_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f, _u64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "advmil_bf16p12_decode": (C.c_int, [_vp, _vp, C.c_char_p, _vp, _vp, _i64, _i32, _vp, _vp]),

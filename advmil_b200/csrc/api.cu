@@ -90,6 +90,7 @@ extern "C" size_t advmil_abi_sizeof(int which) {
     case 9: return sizeof(AdvmilEsatParams);
     case 10: return sizeof(AdvmilEsatGrads);
     case 11: return sizeof(AdvmilEsatActs);
+    case 12: return sizeof(AdvmilEsatStepArgs);
     default: return 0;
   }
 }

@@ -302,3 +302,164 @@ extern "C" int advmil_adv_step_gen(const AdvmilStepArgs* a, void* stream) {
   ADVMIL_CHECK_LAUNCH();
   return advmil_generator_bwd(&gp, bags, &ga, d_pred, a->gen_grads, stream);
 }
+
+
+// =====================================================================================================================
+// The same two-phase step for the ESAT generator (bcb_mode `patch`: DualTrans_HS + noise head, advmil_esat_fwd / _bwd) with
+// the RLIP discriminator: the launch sequence of ModuleAdvStep (step.py) issued from C.  The eval pass of the D phase and the
+// train pass of the G phase share ONE activation set in the persistent region: the patch embedding (y_pre, emb) has no
+// dropout and G's parameters do not change between the phases, so the train pass runs with emb_ready = 1; real and fake D
+// pairs share the region embedding and run through one batched head pass, exactly like the ABMIL step above.
+// In-kernel dropout only (seed_d / seed_g); injected masks go through the module path.
+// =====================================================================================================================
+namespace advmil {
+struct EsatBufs {
+  char* y_pre; float *emb, *qkv, *lse, *ctx, *s1, *x1, *f, *s2, *x2, *ab, *rep, *attn, *H, *H1, *pre;
+  char* ews; size_t ews_bytes;
+  int32_t* offs2;
+};
+static size_t esat_acts_bytes(const AdvmilEsatParams& p, const AdvmilGenParams& h, size_t rows, size_t nb, size_t es) {
+  const size_t R = rows / 16, d = p.d, abw = gate_width(p.d);
+  return align_up(rows * d * es, 256) + (R * (d * 9 + p.ff + abw + 2) + (size_t)p.nhead * R + nb * (d + h.hid + 1)) * sizeof(float) + 20 * 256;
+}
+static int take_esat(Workspace& ws, const AdvmilEsatParams& p, const AdvmilGenParams& h, int rows, int nb, size_t es, EsatBufs& b) {
+  const size_t R = rows / 16, d = p.d, abw = gate_width(p.d);
+  b.y_pre = ws.take<char>((size_t)rows * d * es);
+  b.emb = ws.take<float>(R * d); b.qkv = ws.take<float>(R * 3 * d); b.lse = ws.take<float>((size_t)p.nhead * R); b.ctx = ws.take<float>(R * d);
+  b.s1 = ws.take<float>(R * d); b.x1 = ws.take<float>(R * d); b.f = ws.take<float>(R * p.ff); b.s2 = ws.take<float>(R * d);
+  b.x2 = ws.take<float>(R * d); b.ab = ws.take<float>(R * abw); b.rep = ws.take<float>(R); b.attn = ws.take<float>(R);
+  b.H = ws.take<float>((size_t)nb * d); b.H1 = ws.take<float>((size_t)nb * (h.hid > 0 ? h.hid : 1)); b.pre = ws.take<float>(nb);
+  const size_t e0 = advmil_esat_workspace_bytes(&p, &h, rows, nb, 0), e1 = advmil_esat_workspace_bytes(&p, &h, rows, nb, 1);
+  b.ews_bytes = e0 > e1 ? e0 : e1;
+  b.ews = ws.take<char>(b.ews_bytes);
+  b.offs2 = ws.take<int32_t>(2 * nb + 2);
+  if (!b.y_pre || !b.emb || !b.qkv || !b.lse || !b.ctx || !b.s1 || !b.x1 || !b.f || !b.s2 || !b.x2 || !b.ab || !b.rep || !b.attn || !b.H ||
+      !b.H1 || !b.pre || !b.ews || !b.offs2) {
+    set_error("adv_step_esat: workspace too small (have %zu bytes)", ws.cap);
+    return ADVMIL_ERR_WORKSPACE;
+  }
+  return ADVMIL_OK;
+}
+static void fill_esat_acts(const AdvmilEsatStepArgs* a, const EsatBufs& b, int train, AdvmilEsatActs& ea) {
+  ea = AdvmilEsatActs{};
+  ea.y_pre = b.y_pre; ea.emb = b.emb; ea.qkv = b.qkv; ea.lse = b.lse; ea.ctx = b.ctx; ea.s1 = b.s1; ea.x1 = b.x1; ea.f = b.f; ea.s2 = b.s2;
+  ea.x2 = b.x2; ea.ab = b.ab; ea.rep = b.rep; ea.attn = b.attn; ea.H = b.H; ea.H1 = b.H1; ea.pre = b.pre;
+  ea.pred = train ? a->pred_g : a->pred_d;
+  ea.pe = a->pe; ea.noise0 = nullptr; ea.noise1 = train ? a->noise_g : a->noise_d;
+  ea.seed = train ? a->seed_g : 0; ea.train = train; ea.precision = a->precision;
+  ea.workspace = b.ews; ea.workspace_bytes = b.ews_bytes;
+  ea.emb_ready = train;        // the eval pass of the D phase wrote y_pre / emb of these bags under the same parameters
+}
+static int esat_step_check(const AdvmilEsatStepArgs* a) {
+  ADVMIL_REQUIRE(a && a->esat && a->head && a->disc && a->bags && a->t && a->e && a->visible && a->losses && a->workspace,
+                 "adv_step_esat: null argument");
+  ADVMIL_REQUIRE(a->head->W0 && a->head->noise0 == 0, "adv_step_esat: needs the noise head with gen_noi_noise '0-1'");
+  return ADVMIL_OK;
+}
+}  // namespace advmil
+
+extern "C" size_t advmil_adv_step_esat_workspace_bytes(const AdvmilEsatParams* g, const AdvmilGenParams* head, const AdvmilDiscParams* d,
+                                                       int32_t rows, int32_t bags, int32_t precision) {
+  const size_t es = elem_bytes(elem_of_precision(precision));
+  const size_t R = rows / 16, nb = bags;
+  const size_t e0 = advmil_esat_workspace_bytes(g, head, rows, bags, 0), e1 = advmil_esat_workspace_bytes(g, head, rows, bags, 1);
+  size_t persistent = esat_acts_bytes(*g, *head, rows, nb, es) + (e0 > e1 ? e0 : e1) + 256 + align_up((2 * nb + 2) * sizeof(int32_t), 256);
+  size_t disc = align_up(2 * R * d->d * sizeof(float), 256) + align_up((size_t)rows * d->d * es, 256) + head_bytes(*d, 2 * R, 2 * nb) +
+                align_up(2 * R * d->d * sizeof(float), 256) + 8 * 256 + 6 * nb * sizeof(float) +
+                advmil_disc_workspace_bytes(d, 2 * rows, 2 * bags, 1) + 256;
+  size_t gen = align_up(R * d->d * sizeof(float), 256) + head_bytes(*d, R, nb) + 8 * 256 + 4 * nb * sizeof(float) +
+               advmil_disc_workspace_bytes(d, rows, bags, 1) + 256;
+  return persistent + (disc > gen ? disc : gen) + 4096;
+}
+
+extern "C" int advmil_adv_step_esat_disc(const AdvmilEsatStepArgs* a, void* stream) {
+  ADVMIL_TRY(esat_step_check(a));
+  ADVMIL_REQUIRE(a->disc_grads && a->pred_d && a->f_fake_d && a->real_mask, "adv_step_esat_disc: missing output buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdvmilDiscParams& dp = *a->disc;
+  const AdvmilBags* bags = a->bags;
+  const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = dp.d;
+  const size_t es = elem_bytes(elem_of_precision(a->precision));
+  const bool batched = a->n_real > 0.f;
+  const int nbv = batched ? 2 * nb : nb;
+  Workspace ws(a->workspace, a->workspace_bytes);
+  EsatBufs B;
+  ADVMIL_TRY(take_esat(ws, *a->esat, *a->head, rows, nb, es, B));
+  // ---- generator, eval mode, detached (model_handler.py:383-387) ----
+  AdvmilEsatActs ea;
+  fill_esat_acts(a, B, 0, ea);
+  ADVMIL_TRY(advmil_esat_fwd(a->esat, a->head, bags, &ea, stream));
+  // ---- shared region embedding, duplicated for the batched head ----
+  STEP_TAKE(emb2, float, (size_t)2 * R * d);
+  STEP_TAKE(y_pre, char, (size_t)rows * d * es);
+  AdvmilEmbedActs da{};
+  da.emb = emb2; da.y_pre = y_pre; da.precision = a->precision;
+  ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &da, stream));
+  AdvmilHeadActs ha{};
+  if (!take_head(ws, dp, 2 * (size_t)R, 2 * (size_t)nb, ha)) { set_error("adv_step_esat_disc: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  STEP_TAKE(d_emb2, float, (size_t)2 * R * d);
+  STEP_TAKE(t2, float, 2 * nb);
+  STEP_TAKE(d_out2, float, 2 * nb);
+  const size_t dws_bytes = advmil_disc_workspace_bytes(&dp, 2 * rows, 2 * nb, 1);
+  STEP_TAKE(dws, char, dws_bytes);
+  std::vector<int32_t> offs2_host(2 * nb + 1);
+  for (int i = 0; i <= nb; ++i) { offs2_host[i] = bags->offsets_host[i]; offs2_host[nb + i] = bags->offsets_host[i] + rows; }
+  launch_k(dup_offsets_kernel, dim3(cdiv(nb + 1, 128)), dim3(128), 0, st, bags->offsets, nb, rows, B.offs2);
+  ADVMIL_CHECK_LAUNCH();
+  launch_k(real_mask_kernel, dim3(cdiv(nb, 128)), dim3(128), 0, st, a->e, a->visible, nb, a->real_mask);
+  ADVMIL_CHECK_LAUNCH();
+  ADVMIL_CHECK_CUDA(cudaMemcpyAsync(t2, a->pred_d, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (batched) {
+    ADVMIL_CHECK_CUDA(cudaMemcpyAsync(t2 + nb, a->t, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ADVMIL_CHECK_CUDA(cudaMemcpyAsync(emb2 + (size_t)R * d, emb2, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  AdvmilBags vb = *bags;
+  vb.offsets = B.offs2; vb.offsets_host = offs2_host.data(); vb.rows = batched ? 2 * rows : rows; vb.bags = nbv;
+  ha.emb = emb2; ha.t = t2; ha.out = a->f_fake_d;
+  ha.seed = a->seed_d; ha.train = 1; ha.precision = a->precision; ha.workspace = dws; ha.workspace_bytes = dws_bytes;
+  ADVMIL_TRY(advmil_disc_head_fwd(&dp, &vb, &ha, stream));
+  ADVMIL_TRY(advmil_disc_loss(a->f_fake_d + nb, a->f_fake_d, a->real_mask, nb, a->loss_d, a->n_real, a->n_fake, a->losses,
+                              d_out2 + nb, d_out2, stream));
+  ADVMIL_TRY(advmil_disc_head_bwd(&dp, &vb, &ha, d_out2, d_emb2, nullptr, a->disc_grads, 0, stream));
+  da.workspace = dws; da.workspace_bytes = dws_bytes;
+  return disc_embed_bwd_impl(&dp, bags, &da, d_emb2, batched ? d_emb2 + (size_t)R * d : nullptr, a->disc_grads, 0, st);
+}
+
+extern "C" int advmil_adv_step_esat_gen(const AdvmilEsatStepArgs* a, void* stream) {
+  ADVMIL_TRY(esat_step_check(a));
+  ADVMIL_REQUIRE(a->esat_grads && a->head_grads && a->pred_g && a->f_fake_g, "adv_step_esat_gen: missing output buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdvmilDiscParams& dp = *a->disc;
+  const AdvmilBags* bags = a->bags;
+  const int rows = bags->rows, nb = bags->bags, R = rows / 16, d = dp.d;
+  const size_t es = elem_bytes(elem_of_precision(a->precision));
+  Workspace ws(a->workspace, a->workspace_bytes);
+  EsatBufs B;                                      // y_pre / emb were written by advmil_adv_step_esat_disc on this workspace
+  ADVMIL_TRY(take_esat(ws, *a->esat, *a->head, rows, nb, es, B));
+  // ---- generator, train mode, on the cached patch embedding ----
+  AdvmilEsatActs ea;
+  fill_esat_acts(a, B, 1, ea);
+  ADVMIL_TRY(advmil_esat_fwd(a->esat, a->head, bags, &ea, stream));
+  // ---- D(x, pred_g) with the updated discriminator, eval mode ----
+  STEP_TAKE(emb, float, (size_t)R * d);
+  AdvmilEmbedActs da{};
+  da.emb = emb; da.y_pre = nullptr; da.precision = a->precision;
+  ADVMIL_TRY(advmil_disc_embed_fwd(&dp, bags, &da, stream));
+  AdvmilHeadActs ha{};
+  if (!take_head(ws, dp, R, nb, ha)) { set_error("adv_step_esat_gen: workspace too small"); return ADVMIL_ERR_WORKSPACE; }
+  STEP_TAKE(d_pred, float, nb);
+  STEP_TAKE(d_fake, float, nb);
+  STEP_TAKE(d_t, float, nb);
+  const size_t dws_bytes = advmil_disc_workspace_bytes(&dp, rows, nb, 1);
+  STEP_TAKE(dws, char, dws_bytes);
+  ha.ab = nullptr;
+  ha.emb = emb; ha.t = a->pred_g; ha.out = a->f_fake_g; ha.seed = 0; ha.train = 0; ha.precision = a->precision;
+  ha.workspace = dws; ha.workspace_bytes = dws_bytes;
+  ADVMIL_TRY(advmil_disc_head_fwd(&dp, bags, &ha, stream));
+  ADVMIL_TRY(advmil_gen_loss(a->pred_g, a->t, a->e, a->visible, a->f_fake_g, nb, a->n_visible, a->n_fake, a->coef_gan,
+                             a->recon_alpha, a->recon_gamma, a->recon_norm, a->losses + 1, d_pred, d_fake, stream));
+  ADVMIL_TRY(advmil_disc_head_bwd(&dp, bags, &ha, d_fake, nullptr, d_t, nullptr, 0, stream));
+  launch_k(add_inplace_kernel, dim3(cdiv(nb, 128)), dim3(128), 0, st, d_pred, d_t, nb);
+  ADVMIL_CHECK_LAUNCH();
+  return advmil_esat_bwd(a->esat, a->head, bags, &ea, d_pred, a->esat_grads, a->head_grads, stream);
+}

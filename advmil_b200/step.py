@@ -247,6 +247,107 @@ class AdvStep(_DataParallelMixin):
         return {"dis_loss": v[0], "t_reg_loss": v[1], "gen_loss": v[2], "gen_total_loss": v[3] + l1}
 
 
+class EsatAdvStep(AdvStep):
+    """The C-fused adversarial step for the ESAT generator (`bcb_mode: patch`, DualTrans_HS + noise head) with the RLIP
+    discriminator: `advmil_adv_step_esat_disc / _gen` issue the launch sequence of `ModuleAdvStep` from two host calls (no
+    Python between the kernels, one grow-only workspace, the D phase's eval pass hands its patch embedding to the G phase's
+    train pass).  Same step semantics, outputs and `loss_dict` as `AdvStep` (model/model_handler.py:349-498).  In-kernel dropout
+    only: injected masks (parity tests) go through `ModuleAdvStep`.  coord: region coordinates for the sincos positional
+    embedding, or None (what the handler passes, model_handler.py:613)."""
+
+    def __init__(self, netG, netD, lr_g=8e-5, lr_d=8e-5, weight_decay_g=5e-4, coef_gan=0.004, coef_l1=1e-5,
+                 loss_d="bce", recon_norm="l1", recon_alpha=0.0, recon_gamma=0.0, precision="fp32", process_group=None):
+        if netG.backbone.kind != "patch":
+            raise NotImplementedError(f"EsatAdvStep is the C-fused step of the ESAT generator, got bcb_mode '{netG.backbone.kind}'")
+        if list(netG.noise) != [0, 1]:
+            raise NotImplementedError(f"EsatAdvStep covers gen_noi_noise '0-1', got {list(netG.noise)}")
+        self.netG, self.netD = netG, netD
+        bb = netG.backbone
+        self.ecfg, self.hcfg, self.dcfg = bb.esat_config(), netG.config(), netD.config()
+        self.eparams, self.hparams, self.dparams = bb.esat_params(), netG.head_params(), netD.disc_params()
+        self.G = FlatParams(netG, list(netG.parameters()), weight_decay_rule=True)
+        self.D = FlatParams(netD, self.dparams, weight_decay_rule=False)
+        self.egrads, self.hgrads, self.dgrads = self.G.grads_for(self.eparams), self.G.grads_for(self.hparams), self.D.grads_for(self.dparams)
+        assert self.G.total == sum((t.numel() + 3) // 4 * 4 for t in self.eparams + self.hparams), "generator parameters outside the ESAT step"
+        self.lr_g, self.lr_d, self.wd_g = lr_g, lr_d, weight_decay_g
+        self.coef_gan, self.coef_l1 = coef_gan, coef_l1
+        self.loss_d = {"bce": 0, "hinge": 1, "wasserstein": 2}[loss_d]
+        self.recon = ({"l1": 0, "l2": 1}[recon_norm], recon_alpha, recon_gamma)
+        self.precision = ops.PRECISIONS[precision]
+        self._inflight = None
+        self._init_dp(process_group)
+
+    def _structs(self):
+        if getattr(self, "_c", None) is None:
+            ep, hp, dp = self.ecfg.c(self.eparams), self.hcfg.c([None] * 10 + list(self.hparams)), self.dcfg.c(self.dparams)
+            eg, hg, dg = _lib.EsatGrads(), _lib.GenGrads(), _lib.DiscGrads()
+            for name, tns in zip(_lib.ESAT_TENSORS, self.egrads):
+                setattr(eg, name, tns.data_ptr())
+            for name, tns in zip(_lib.GEN_TENSORS, [None] * 10 + list(self.hgrads)):
+                setattr(hg, name, None if tns is None else tns.data_ptr())
+            hg.dx = None
+            for name, tns in zip(_lib.DISC_TENSORS, self.dgrads):
+                setattr(dg, name, None if tns is None else tns.data_ptr())
+            self._c = (ep, hp, dp, eg, hg, dg)
+        return self._c
+
+    def step(self, bags: ops.PackedBags, t: torch.Tensor, e: torch.Tensor, visible: torch.Tensor,
+             noise_d: Optional[torch.Tensor] = None, noise_g: Optional[torch.Tensor] = None, coord=None, global_counts=None) -> Dict:
+        lib = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        bags = bags.for_precision(self.precision)
+        dev, nb = bags.x.device, bags.bags
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = t.reshape(-1).contiguous().float()
+        e = e.reshape(-1).contiguous().float()
+        visible = visible.reshape(-1).to(torch.uint8).contiguous()
+        if global_counts is None:
+            real_mask = ((e == 1) & (visible != 0))
+            cnt = torch.stack([real_mask.sum(), torch.tensor(nb, device=dev), visible.sum()]).float()
+            self._allreduce(cnt)
+            n_real, n_fake, n_vis = [float(v) for v in cnt.tolist()]
+        else:
+            n_real, n_fake, n_vis = [float(v) for v in global_counts]
+        noise_d = (noise_d if noise_d is not None else self._draw(nb, dev)).contiguous().float()
+        noise_g = (noise_g if noise_g is not None else self._draw(nb, dev)).contiguous().float()
+        pe = self.netG.backbone.positional(bags, coord)
+        ep, hp, dp, eg, hg, dg = self._structs()
+        need = lib.advmil_adv_step_esat_workspace_bytes(C.byref(ep), C.byref(hp), C.byref(dp), bags.rows, nb, self.precision)
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            self._ws = ws = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=dev)      # grow-only
+        out = {"losses": torch.zeros(8, **f32), "pred_d": torch.empty(nb, **f32), "pred_g": torch.empty(nb, **f32),
+               "f_d": torch.empty(2 * nb, **f32), "f_fake_g": torch.empty(nb, **f32),
+               "real_mask": torch.empty(nb, dtype=torch.uint8, device=dev)}
+        b = bags.c()
+        a = _lib.EsatStepArgs()
+        a.esat, a.head, a.disc = C.pointer(ep), C.pointer(hp), C.pointer(dp)
+        a.esat_grads, a.head_grads, a.disc_grads, a.bags = C.pointer(eg), C.pointer(hg), C.pointer(dg), C.pointer(b)
+        a.t, a.e, a.visible = t.data_ptr(), e.data_ptr(), visible.data_ptr()
+        a.noise_d, a.noise_g, a.pe = noise_d.data_ptr(), noise_g.data_ptr(), ops._ptr(pe)
+        a.seed_d, a.seed_g = self._seed(), self._seed()
+        a.n_real, a.n_fake, a.n_visible, a.loss_d = n_real, n_fake, n_vis, self.loss_d
+        a.recon_norm, a.recon_alpha, a.recon_gamma = self.recon
+        a.coef_gan, a.precision = self.coef_gan, self.precision
+        a.losses, a.pred_d, a.f_fake_d, a.real_mask = (out["losses"].data_ptr(), out["pred_d"].data_ptr(),
+                                                       out["f_d"].data_ptr(), out["real_mask"].data_ptr())
+        a.pred_g, a.f_fake_g = out["pred_g"].data_ptr(), out["f_fake_g"].data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.advmil_adv_step_esat_disc(C.byref(a), st), "advmil_adv_step_esat_disc")
+        self._allreduce(self.D.grad)
+        self.D.adam(self.lr_d)
+        check(lib.advmil_adv_step_esat_gen(C.byref(a), st), "advmil_adv_step_esat_gen")
+        if self.coef_l1 > 1e-8:
+            check(lib.advmil_abs_sum(self.G.flat.data_ptr(), self.G.total, out["losses"][4:].data_ptr(), st), "advmil_abs_sum")
+        self._allreduce(self.G.grad)
+        self.G.adam(self.lr_g, weight_decay=self.wd_g, l1_coef=self.coef_l1 if self.coef_l1 > 1e-8 else 0.0)
+        out["f_fake_d"] = out["f_d"][:nb]
+        out["f_real"] = out["f_d"][nb:] if n_real > 0 else None
+        out["_keep"] = (t, e, visible, noise_d, noise_g, pe, bags)
+        self._inflight = out
+        return out
+
+
 class ModuleAdvStep(_DataParallelMixin):
     """One D update + one G update over packed bags for any built generator backbone (ABMIL, DeepAttMISL, ESAT), composed from
     the modules' packed forwards and their autograd Functions: the same step semantics as `AdvStep`

@@ -514,14 +514,16 @@ def run_esat(args, rank, world, local_rank):
     figure: MEASURED_PEAKS.json holds no tf32 number)."""
     from advmil_b200 import _lib, ops
     from advmil_b200.dataset.packed import DeviceFeeder, synthetic_steps
-    from advmil_b200.step import ModuleAdvStep
+    from advmil_b200.step import EsatAdvStep, ModuleAdvStep
 
     ctx = Ctx(args, rank, world, local_rank)
     dev = ctx.dev
     lib = _lib.load()
     torch.manual_seed(42)
     G, D = build_networks(dev, "patch")
-    eng = ModuleAdvStep(G, D, precision=args.precision)
+    # the C-fused ESAT step (advmil_adv_step_esat_disc / _gen); ADVMIL_ESAT_ENGINE=module times the Python-composed ModuleAdvStep
+    use_c = os.environ.get("ADVMIL_ESAT_ENGINE", "c") != "module"
+    eng = (EsatAdvStep if use_c else ModuleAdvStep)(G, D, precision=args.precision)
     feat_dtype = torch.bfloat16 if args.precision == "bf16" else torch.float32
     steps = synthetic_steps(args.warmup + args.steps, args.bags, args.rows, C_IN, seed=42 + rank, distinct=2, dtype=feat_dtype)
     resident = resident_steps(ctx, steps[:2])
@@ -587,7 +589,8 @@ def run_esat(args, rank, world, local_rank):
     h2d = steps[0].nbytes
     for i in range(args.warmup):
         s = next(it)
-        float(eng.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)["dis_loss"])
+        o = eng.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)
+        float(o["losses"][0] if use_c else o["dis_loss"])
     ctx.barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -595,7 +598,11 @@ def run_esat(args, rank, world, local_rank):
     for i in range(args.steps):
         s = next(it)
         o = eng.step(s.bags, s.t, s.e, s.visible, global_counts=s.counts if world == 1 else None)
-        host = [float(o[k]) for k in ("dis_loss", "gen_loss", "t_reg_loss", "gen_total_loss")]     # device -> host read of the result
+        if use_c:
+            ld = eng.loss_dict(o)                                                                   # device -> host read of the result
+            host = [ld[k] for k in ("dis_loss", "gen_loss", "t_reg_loss", "gen_total_loss")]
+        else:
+            host = [float(o[k]) for k in ("dis_loss", "gen_loss", "t_reg_loss", "gen_total_loss")]     # device -> host read of the result
     e1.record()
     ctx.barrier()
     wall = time.perf_counter() - t0
@@ -607,6 +614,7 @@ def run_esat(args, rank, world, local_rank):
                 "config": {"workload": f"AdvMIL-ESAT (bcb_mode patch: DualTrans_HS generator, RLIP discriminator) G+D step, {args.bags} "
                                        f"synthetic bags of {args.rows}x1024 per step per GPU; D step + G step + both Adam updates",
                            "rows_per_step_per_gpu": args.bags * args.rows, "precision_mode": args.precision,
+                           "engine": "EsatAdvStep (C-fused: advmil_adv_step_esat_disc/gen)" if use_c else "ModuleAdvStep (Python-composed)",
                            "l2": "inputs (two alternating steps of 512 MiB or more) larger than the 126 MB L2; no flush",
                            "parallelism": f"dp{world} (bags sharded, NCCL all-reduce of flat G/D grads)"},
                 "e2e": {"value": args.bags * world * args.steps / (ems / 1e3), "unit": "bags/s", "h2d_bytes_per_step": h2d,
@@ -859,7 +867,7 @@ def main():
                     help="end-to-end leg, bf16 mode: copy the features in the packed loader's lossless entropy-coded transport "
                          "format (vl, ~10.9 bits per element), its fixed 12-bit form (p12) -- both decoded on the device -- or as raw bf16")
     ap.add_argument("--backbone", default="abmil", choices=["abmil", "patch"],
-                    help="generator backbone: abmil (the benchmark's workload, C-fused AdvStep) or patch (ESAT, ModuleAdvStep)")
+                    help="generator backbone: abmil (the benchmark's workload, C-fused AdvStep) or patch (ESAT, C-fused EsatAdvStep)")
     ap.add_argument("--ragged", action="store_true",
                     help="main line on configs[2] instead of configs[1]: bag lengths log-uniform in [1024, 100000]")
     args = ap.parse_args()

@@ -174,7 +174,7 @@ typedef struct AdvmilHeadActs {       /* K7+K8: region MLP, GAPool, bag MLP, tim
 ADVMIL_API int advmil_abi_version(void);
 ADVMIL_API const char* advmil_last_error(void);
 /* sizeof() of the ABI structs, for binding self-checks: which = 0 Bags, 1 GenParams, 2 GenGrads, 3 GenActs,
- * 4 DiscParams, 5 DiscGrads, 6 EmbedActs, 7 HeadActs, 8 StepArgs */
+ * 4 DiscParams, 5 DiscGrads, 6 EmbedActs, 7 HeadActs, 8 StepArgs, 9 EsatParams, 10 EsatGrads, 11 EsatActs, 12 EsatStepArgs */
 ADVMIL_API size_t advmil_abi_sizeof(int which);
 /* counts kernel launches issued by this library since the last reset (bench "gpu_launches") */
 ADVMIL_API int64_t advmil_launch_count(int reset);
@@ -418,6 +418,30 @@ ADVMIL_API int advmil_esat_bwd(const AdvmilEsatParams* p, const AdvmilGenParams*
  * relative to each bag's minimum; omega [d/4] = 1 / 10000^(k / (d/4 - 1)) as the reference computes it; pe [R,d]. */
 ADVMIL_API int advmil_sincos_pe(const int64_t* coord, const int32_t* offsets /* bag row offsets [bags+1], device */, int32_t bags,
                      int32_t d, const float* omega, float* pe, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the fused adversarial step for the ESAT generator (the launch sequence of step.ModuleAdvStep issued from C; same
+ *      semantics, outputs and loss layout as advmil_adv_step_disc / _gen; in-kernel dropout only).  pe: optional [R, d]
+ *      positional embedding (advmil_sincos_pe).  The two calls share one workspace: the D phase's eval pass leaves the patch
+ *      embedding of the bags in it for the G phase's train pass. */
+typedef struct AdvmilEsatStepArgs {
+  const AdvmilEsatParams* esat; const AdvmilGenParams* head; const AdvmilDiscParams* disc;
+  AdvmilEsatGrads* esat_grads; AdvmilGenGrads* head_grads; AdvmilDiscGrads* disc_grads;
+  const AdvmilBags* bags;
+  const float* t; const float* e; const uint8_t* visible;
+  const float* noise_d; const float* noise_g;
+  const float* pe;
+  uint64_t seed_d, seed_g;
+  float n_real, n_fake, n_visible;
+  int32_t loss_d;
+  float coef_gan, recon_alpha, recon_gamma; int32_t recon_norm;
+  int32_t precision;
+  float* losses; float* pred_d; float* f_fake_d; uint8_t* real_mask; float* pred_g; float* f_fake_g;
+  void* workspace; size_t workspace_bytes;
+} AdvmilEsatStepArgs;
+ADVMIL_API size_t advmil_adv_step_esat_workspace_bytes(const AdvmilEsatParams* esat, const AdvmilGenParams* head, const AdvmilDiscParams* disc,
+                                            int32_t rows, int32_t bags, int32_t precision);
+ADVMIL_API int advmil_adv_step_esat_disc(const AdvmilEsatStepArgs* a, void* stream);
+ADVMIL_API int advmil_adv_step_esat_gen(const AdvmilEsatStepArgs* a, void* stream);
 
 /* ---- ESAT self-attention, stage level (nn.MultiheadAttention inside the encoder layer, model/backbone_utils.py:112-127):
  *      qkv [R, 3d] fp32 (the packed in-projection), region offsets [bags+1] on the device and on the host, -> ctx [R, d],

@@ -55,15 +55,15 @@ advmil_b200.set_precision("fp32")
 from types import SimpleNamespace as NS  # noqa: E402
 
 from advmil_b200.model.GANSurv import PrjDiscriminator  # noqa: E402
-from advmil_b200.step import ModuleAdvStep  # noqa: E402
+from advmil_b200.step import EsatAdvStep, ModuleAdvStep  # noqa: E402
 
-for mode in args.modes.split(","):
+for mode, Engine in [(m, E) for m in args.modes.split(",") for E in (ModuleAdvStep, EsatAdvStep)]:
     torch.manual_seed(0)
     G2 = Generator(384, 1, load_backbone("patch", [1024, 384, 384]), SimpleNamespace(noise=[0, 1], hops=1, noise_dist="uniform"), False,
                    0.6, "sigmoid").cuda()
     D2 = PrjDiscriminator(NS(in_dim=1024, out_dim=128, ksize=1, backbone="avgpool", dropout=0.25),
                           NS(in_dim=1, hid_dims=[64, 128], norm=False, dropout=0.0), prj_path="x", inner_product="instance").cuda()
-    eng = ModuleAdvStep(G2, D2, precision=mode)
+    eng = Engine(G2, D2, precision=mode)
     x = x32.to(torch.bfloat16) if mode == "bf16" else x32
     bags = ops.PackedBags(x, [args.rows] * args.bags)
     t = torch.rand(args.bags, device="cuda")
@@ -82,6 +82,7 @@ for mode in args.modes.split(","):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"what": "ESAT G + RLIP D adversarial step (ModuleAdvStep: D update + G update + both Adam steps)", "mode": mode,
+    ld = eng.loss_dict(out) if Engine is EsatAdvStep else {k: float(out[k]) for k in ("dis_loss", "gen_total_loss")}
+    print(json.dumps({"what": f"ESAT G + RLIP D adversarial step ({Engine.__name__}: D update + G update + both Adam steps)", "mode": mode,
                       "bags": args.bags, "rows_per_bag": args.rows, "ms_per_step": ms, "bags_per_s": args.bags / ms * 1e3,
-                      "dis_loss": float(out["dis_loss"]), "gen_total_loss": float(out["gen_total_loss"])}))
+                      "dis_loss": ld["dis_loss"], "gen_total_loss": ld["gen_total_loss"]}))

@@ -532,3 +532,83 @@ def test_vl_transport_decodes_bit_exactly_on_the_device_and_through_the_feeder()
     for st, dv in zip(steps, DeviceFeeder(steps, device="cuda", depth=2)):
         torch.cuda.current_stream().synchronize()
         assert torch.equal(dv.bags.x.cpu().view(torch.int16), st.x.view(torch.int16))
+
+
+def _esat_nets_without_dropout(C, d, seed_g, seed_d):
+    sdG, sdD = O.synth_state_dict(O.G_ESAT_SHAPES(C, d), seed_g), O.synth_state_dict(O.D_SHAPES(), seed_d)
+    G, D = build_G((C, d, d), mode="patch"), build_D()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    G.backbone.p = G.backbone.pool.p = 0.0          # the C step draws its own dropout bits: compare the deterministic arithmetic
+    G.p_head = 0.0
+    D.net_pair_one.p = 0.0
+    return sdG, sdD, G, D
+
+
+def test_c_fused_esat_step_vs_oracle_trainer_and_module_step():
+    """EsatAdvStep (advmil_adv_step_esat_disc / _gen: the ESAT generator's adversarial step issued from C) in the fp32 mode:
+    two optimiser steps against the oracle's restatement of _update_disc/_update_gen (dropout probabilities zeroed) and
+    against ModuleAdvStep on the same inputs; mixed labelled / unlabelled bags."""
+    from advmil_b200 import ops
+    from advmil_b200.step import EsatAdvStep, ModuleAdvStep
+    C, d = 1024, 384
+    Ns = [160, 320, 96, 640]
+    B = len(Ns)
+    sdG, sdD, G, D = _esat_nets_without_dropout(C, d, 171, 172)
+    _, _, G2, D2 = _esat_nets_without_dropout(C, d, 171, 172)
+    tr = O.CpuTrainer(sdG, sdD, backbone="patch")
+    eng, mod = EsatAdvStep(G, D), ModuleAdvStep(G2, D2)
+    xs = [O.synth_bag(n, 180 + i, C) for i, n in enumerate(Ns)]
+    ts, es = O.synth_labels(B, 173)
+    es[0] = 1.0
+    vis = [True, True, False, True]
+    bags = ops.PackedBags.from_list([x.cuda() for x in xs])
+    for step in range(2):
+        rng = np.random.default_rng(174 + step)
+        nd = torch.tensor(rng.uniform(size=(B, d // 2)), dtype=torch.float32)
+        ng = torch.tensor(rng.uniform(size=(B, d // 2)), dtype=torch.float32)
+        ref = tr.step(xs, ts, es, vis, list(nd), list(ng))
+        args = (bags, ts.cuda(), es.cuda(), torch.tensor(vis, dtype=torch.uint8).cuda())
+        out = eng.step(*args, noise_d=nd.cuda(), noise_g=ng.cuda())
+        om = mod.step(*args, noise_d=nd.cuda(), noise_g=ng.cuda())
+        L = eng.loss_dict(out)
+        assert_close(out["pred_d"].cpu(), ref["pred_d"].reshape(-1), RTOL, f"pred_d {step}")
+        assert_close(out["pred_g"].cpu(), ref["pred_g"].reshape(-1), RTOL, f"pred_g {step}")
+        assert_close(out["f_fake_d"].cpu(), ref["fake_d"].reshape(-1), RTOL, f"fake_d {step}", atol_scale=1e-1)
+        assert_close(out["f_fake_g"].cpu(), ref["fake_g"].reshape(-1), RTOL, f"fake_g {step}", atol_scale=1e-1)
+        assert abs(L["dis_loss"] - ref["dis_loss"]) < 2e-5 and abs(L["gen_loss"] - ref["gen_loss"]) < 2e-5
+        assert abs(L["t_reg_loss"] - ref["t_reg"]) < 2e-5 and abs(L["gen_total_loss"] - ref["total"]) < 2e-5
+        assert_close(out["pred_g"].cpu(), om["pred_g"].cpu(), RTOL, f"pred_g vs module step {step}")
+    for k, p in D.named_parameters():
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdD[k].detach(), RTOL, "D param " + k, atol=8e-5 * 2 * 2e-2)
+    for (k, p), p2 in zip(G.named_parameters(), G2.parameters()):
+        if not k.endswith(ZERO_GRAD):
+            assert_close(p.detach().cpu(), tr.sdG[k].detach(), RTOL, "G param " + k, atol=8e-5 * 2 * 2e-2)
+            assert_close(p.detach().cpu(), p2.detach().cpu(), RTOL, "G param vs module step " + k, atol=8e-5 * 2 * 2e-2)
+
+
+def test_c_fused_esat_step_bf16_with_dropout_runs_and_learns():
+    """bf16 mode with the in-kernel dropout of every site: finite losses, parameters move, and the reconstruction loss
+    falls over a few steps on a fixed batch (the full path: tcgen05 attention forward / backward, chain kernels, Adam)."""
+    from advmil_b200 import ops
+    from advmil_b200.step import EsatAdvStep
+    C, d = 1024, 384
+    Ns = [320, 640, 160, 2048]
+    sdG, sdD = O.synth_state_dict(O.G_ESAT_SHAPES(C, d), 191), O.synth_state_dict(O.D_SHAPES(), 192)
+    G, D = build_G((C, d, d), mode="patch"), build_D()
+    G.load_state_dict(sdG)
+    D.load_state_dict(sdD)
+    eng = EsatAdvStep(G, D, precision="bf16", lr_g=2e-3)
+    bags = ops.PackedBags.from_list([O.synth_bag(n, 200 + i, C).cuda() for i, n in enumerate(Ns)])
+    t = torch.tensor([0.2, 0.5, 0.7, 0.9], device="cuda")
+    e = torch.ones(4, device="cuda")
+    vis = torch.ones(4, dtype=torch.uint8, device="cuda")
+    p0 = eng.G.flat.clone()
+    hist = []
+    for _ in range(12):
+        L = eng.loss_dict(eng.step(bags, t, e, vis))
+        assert all(np.isfinite(v) for v in L.values())
+        hist.append(L["t_reg_loss"])
+    assert float((eng.G.flat - p0).abs().max()) > 0
+    assert min(hist[-3:]) < hist[0]
