@@ -22,20 +22,24 @@ __global__ void region_offsets_kernel(const int32_t* __restrict__ offs, int n, i
 // ---- side stream of the backward pass ------------------------------------------------------------------------------------
 // Each region-level layer's backward is three independent pieces of work once dY exists: dX = dY W (the chain the next layer
 // waits for), dW = dY^T X and db = colsum(dY).  They are all 10-30 us kernels on 16 k region rows that leave most of the chip
-// idle, so the weight / bias gradients CAN run on a second stream beside the data-gradient chain: ADVMIL_ESAT_OVERLAP=1.
-// Off by default: measured on a B200 the generator's forward + backward gains 4 % (2.22 -> 2.13 ms), but the Python-composed
-// ModuleAdvStep is within a few percent of being host-bound and the six extra event record / wait pairs per backward cost it
-// more host time than the overlap saves (4.42 -> 4.60 ms per step).
+// idle, so the weight / bias gradients can run on a second stream beside the data-gradient chain.  The C-fused step
+// (advmil_adv_step_esat_gen) requests it: 3.40 -> 3.32 ms per step.  The module path does not: the generator's forward +
+// backward alone gains 4 % (2.22 -> 2.13 ms), but the Python-composed ModuleAdvStep is within a few percent of being
+// host-bound and the six extra event record / wait pairs per backward cost it more host time than the overlap saves
+// (4.42 -> 4.60 ms per step).  ADVMIL_ESAT_OVERLAP=1 / 0 forces it on / off everywhere.
 struct EsatSide {
   cudaStream_t st = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 static EsatSide g_esat_side[64];
 static std::mutex g_esat_mu;
+static thread_local int g_esat_overlap_request = 0;      // set by the C-fused step around its backward call
+void esat_request_overlap(int on) { g_esat_overlap_request = on; }
 static int esat_side_get(EsatSide** out) {
   *out = nullptr;
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("ADVMIL_ESAT_OVERLAP"); enabled = (e && atoi(e) == 1) ? 1 : 0; }
+  static int env = -2;                                    // ADVMIL_ESAT_OVERLAP: 1 = always, 0 = never, unset = only where requested
+  if (env == -2) { const char* e = getenv("ADVMIL_ESAT_OVERLAP"); env = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
+  const int enabled = env >= 0 ? env : g_esat_overlap_request;
   if (!enabled) return ADVMIL_OK;
   int dev = 0;
   ADVMIL_CHECK_CUDA(cudaGetDevice(&dev));

@@ -131,6 +131,9 @@ int mha_bwd(const float* qkv, const float* ctx, const float* d_ctx, const float*
             int bags, int Rtot, int d, int heads, const Drop& drop, const uint8_t* mask, const int64_t* mask_off, float* d_qkv,
             float* Dq /* [heads, R] */, int precision, cudaStream_t st);
 
+// ---- esat.cu ------------------------------------------------------------------------------------
+void esat_request_overlap(int on);   // this thread's next advmil_esat_bwd calls may use the backward side stream (C-fused step)
+
 // ---- tail_kernels.cu --------------------------------------------------------------------------
 int gen_head_fwd(const AdvmilGenParams& p, const float* z, const float* noise0, const float* noise1, int bags,
                  int samples, const Drop& drho, const Drop& dmlp0, float* H, float* H1, float* pre, float* pred,

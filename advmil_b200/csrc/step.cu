@@ -461,5 +461,8 @@ extern "C" int advmil_adv_step_esat_gen(const AdvmilEsatStepArgs* a, void* strea
   ADVMIL_TRY(advmil_disc_head_bwd(&dp, bags, &ha, d_fake, nullptr, d_t, nullptr, 0, stream));
   launch_k(add_inplace_kernel, dim3(cdiv(nb, 128)), dim3(128), 0, st, d_pred, d_t, nb);
   ADVMIL_CHECK_LAUNCH();
-  return advmil_esat_bwd(a->esat, a->head, bags, &ea, d_pred, a->esat_grads, a->head_grads, stream);
+  esat_request_overlap(1);     // weight / bias gradients of the region-level layers on the backward side stream
+  const int rc = advmil_esat_bwd(a->esat, a->head, bags, &ea, d_pred, a->esat_grads, a->head_grads, stream);
+  esat_request_overlap(0);
+  return rc;
 }

@@ -599,16 +599,18 @@ def test_c_fused_esat_step_bf16_with_dropout_runs_and_learns():
     G, D = build_G((C, d, d), mode="patch"), build_D()
     G.load_state_dict(sdG)
     D.load_state_dict(sdD)
-    eng = EsatAdvStep(G, D, precision="bf16", lr_g=2e-3)
+    torch.manual_seed(1234)              # the dropout seeds and the generator noise come from torch's default CPU generator
+    eng = EsatAdvStep(G, D, precision="bf16", lr_g=1e-3)
     bags = ops.PackedBags.from_list([O.synth_bag(n, 200 + i, C).cuda() for i, n in enumerate(Ns)])
     t = torch.tensor([0.2, 0.5, 0.7, 0.9], device="cuda")
     e = torch.ones(4, device="cuda")
     vis = torch.ones(4, dtype=torch.uint8, device="cuda")
+    nz = torch.rand(4, d // 2, device="cuda")
     p0 = eng.G.flat.clone()
     hist = []
-    for _ in range(12):
-        L = eng.loss_dict(eng.step(bags, t, e, vis))
+    for _ in range(30):
+        L = eng.loss_dict(eng.step(bags, t, e, vis, noise_d=nz, noise_g=nz))
         assert all(np.isfinite(v) for v in L.values())
         hist.append(L["t_reg_loss"])
     assert float((eng.G.flat - p0).abs().max()) > 0
-    assert min(hist[-3:]) < hist[0]
+    assert float(np.mean(hist[-5:])) < float(np.mean(hist[:3])), hist
