@@ -345,7 +345,7 @@ extern "C" int advmil_disc_head_fwd(const AdvmilDiscParams* p, const AdvmilBags*
   Drop none = Drop::make(nullptr, 0, 0, 0.f, 0, 0);
   // region-level tensors are fp32; outside the exact-fp32 mode their contractions run on the tcgen05 tf32 pipe
   const int rp = region_precision(a->precision, a->train != 0);
-  if (rlip_chain_supported(d)) {      // one exact-fp32 kernel for the region-level chain (rlip_chain.cu), every precision mode
+  if (rlip_chain_supported(d)) {      // one fp32-grade kernel for the region-level chain (rlip_chain.cu: split-tf32 mma.sync), every precision mode
     ADVMIL_TRY(rlip_chain_fwd(a->emb, *p, R, dfc1, dga, dgs, a->f1, a->fi, a->ab, part, st));
   } else {
     ADVMIL_TRY(linear_fwd(a->emb, p->F1a_w, p->F1a_b, R, d, dh, 1, dfc1, a->f1, rp, st));
