@@ -1,6 +1,7 @@
 // Segmented (per-bag) kernels and row-streaming backward kernels.  HBM-bound: coalesced float4 streams,
 // warp-shuffle reductions, deterministic two-level reductions (no atomics).
 #include <stdarg.h>
+#include <stdlib.h>
 #include "stages.cuh"
 
 namespace advmil {
@@ -772,8 +773,8 @@ __global__ void __launch_bounds__(256) ln_pool_bwd_kernel(
 // d == 128: 16 lanes per row (8 columns per lane as 16-byte vectors interleaved across the 16 lanes, so every load
 // instruction covers 256 contiguous bytes per row), 2 rows per warp and 4 such pairs in flight: 8 rows = half a region
 // per warp iteration; 24 partial-sum registers per lane keep the occupancy at 4+ CTAs per SM
-template <typename T>
-__global__ void __launch_bounds__(128) ln_pool_bwd128_kernel(
+template <typename T, int OCC>
+__global__ void __launch_bounds__(128, OCC) ln_pool_bwd128_kernel(
     const T* __restrict__ y_pre, const float* __restrict__ d_emb, const float* __restrict__ d_emb2,
     const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float eps, T* __restrict__ d_y,
     float* __restrict__ part) {
@@ -895,10 +896,10 @@ int ln_pool_bwd(const void* y_pre, const float* d_emb, const float* d_emb2, cons
   ADVMIL_REQUIRE(dt == ELEM_F32 || d == 128, "ln_pool_bwd: the bf16 mode supports d == 128 only (d=%d)", d);
   int chunks = row_chunks(rows);
   size_t smem = (size_t)8 * 3 * d * sizeof(float);
-  if (d == 128 && dt == ELEM_BF16)
-    launch_k(ln_pool_bwd128_kernel<bf16>, dim3(chunks), dim3(128), 0, st, (const bf16*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (bf16*)d_y, ws);
+  if (d == 128 && dt == ELEM_BF16)      // 96 registers (32 bytes of spills), 5 CTAs per SM: 58 -> 56 us
+    launch_k(ln_pool_bwd128_kernel<bf16, 5>, dim3(chunks), dim3(128), 0, st, (const bf16*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (bf16*)d_y, ws);
   else if (d == 128)
-    launch_k(ln_pool_bwd128_kernel<float>, dim3(chunks), dim3(128), 0, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (float*)d_y, ws);
+    launch_k(ln_pool_bwd128_kernel<float, 4>, dim3(chunks), dim3(128), 0, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, eps, (float*)d_y, ws);
   else if (d <= 128) launch_k(ln_pool_bwd_kernel<4>, dim3(chunks), dim3(256), smem, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   else launch_k(ln_pool_bwd_kernel<8>, dim3(chunks), dim3(256), smem, st, (const float*)y_pre, d_emb, d_emb2, gamma, beta, rows, d, eps, (float*)d_y, ws);
   ADVMIL_CHECK_LAUNCH();

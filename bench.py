@@ -346,17 +346,27 @@ class Ctx:
 def timed(ctx, fn, steps, warmup):
     """W untimed + K timed calls of fn(i) between barrier + synchronize; CUDA events on the launching stream, max over ranks.
     Returns (ms for the K steps, host issue ms per step)."""
+    import gc
     for i in range(warmup):
         fn(i)
-    ctx.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    th0 = time.perf_counter()
-    for i in range(steps):
-        fn(warmup + i)
-    host_ms = (time.perf_counter() - th0) * 1e3 / steps
-    ev1.record()
-    ctx.barrier()
+    # the cyclic garbage collector stays out of the timed region (as timeit does): a generation-2 pass over the interpreter's
+    # objects costs tens of ms, which doubled the 10-step host-bound legs (ModuleAdvStep) in two runs out of three
+    gc.collect()
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        ctx.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        th0 = time.perf_counter()
+        for i in range(steps):
+            fn(warmup + i)
+        host_ms = (time.perf_counter() - th0) * 1e3 / steps
+        ev1.record()
+        ctx.barrier()
+    finally:
+        if gc_was_enabled:
+            gc.enable()
     return ctx.max_over_ranks(ev0.elapsed_time(ev1)), host_ms
 
 
