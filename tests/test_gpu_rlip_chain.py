@@ -90,7 +90,8 @@ def test_chain_variants_agree_with_the_oracle_and_with_each_other():
         for k in names:
             if k.startswith("out"):
                 _close(res[v][k], ref[k], 1e-5, f"variant {v} vs FFMA: {k}", atol=1e-5 * 1e-2)
-    # the three tilings run the same arithmetic in the same order
-    for k in names:
-        if k.startswith("out"):
-            assert np.array_equal(res[1][k], res[2][k]) and np.array_equal(res[1][k], res[3][k]), k
+    # the three tilings run the same arithmetic on different CTA shapes
+    for v in (2, 3):
+        for k in names:
+            if k.startswith("out"):
+                _close(res[v][k], res[1][k], 1e-5, f"variant {v} vs variant 1: {k}", atol=1e-5 * 1e-2)
