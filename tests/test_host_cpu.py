@@ -322,3 +322,39 @@ def test_vl_packed_file_round_trip_and_step_assembly(tmp_path):
     want = torch.cat([bags[i] for i in (3, 1, 4)]).to(torch.bfloat16)
     assert torch.equal(decode_vl_host(st.vl).view(torch.int16), want.view(torch.int16))
     assert st.lengths == [16, 1600, 2048] and st.nbytes < 0.70 * want.numel() * 2
+
+
+def test_split_tf32_arithmetic_is_fp32_grade():
+    """Numerics of the split-tf32 ("3xTF32") contractions (csrc/rlip_chain.cu split3 / mma_chunk, csrc/gemm_tc.cu X3), restated
+    in numpy: hi = rna_tf32(x) (integer add + mask, as the kernels do it), lo = x - hi exactly, the tensor core sees lo
+    truncated to tf32, a product is hi.hi + lo.hi + hi.lo with the small terms summed apart from the main chain.  The
+    dropped lo.lo term and the truncation of lo bound the relative error of a product by ~2^-20; a K = 128 dot product
+    (the region-level chain of the RLIP head, reference model/model_utils.py:202-210) stays within 1e-6 of sum |a||b|."""
+    rng = np.random.default_rng(0)
+
+    def split(x):
+        bits = x.view(np.uint32)
+        hi = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = (x - hi).astype(np.float32)                                  # exact: |lo| <= 2^-11 |x|
+        assert np.array_equal(lo.astype(np.float64), x.astype(np.float64) - hi.astype(np.float64))
+        lo_t = (lo.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)   # what the tensor core reads
+        return hi, lo_t
+
+    a = (rng.standard_normal((4096, 128)) * np.exp(rng.uniform(-3, 3, (4096, 128)))).astype(np.float32)
+    b = (rng.standard_normal((4096, 128)) * np.exp(rng.uniform(-3, 3, (4096, 128)))).astype(np.float32)
+    ah, al = split(a)
+    bh, bl = split(b)
+    assert float(np.abs(a - ah).max() / np.abs(a).max()) < 2.0 ** -10    # plain tf32 would stop here: ~5e-4 per operand
+    exact = a.astype(np.float64) * b.astype(np.float64)
+    main = ah.astype(np.float64) * bh.astype(np.float64)
+    small = al.astype(np.float64) * bh.astype(np.float64) + ah.astype(np.float64) * bl.astype(np.float64)
+    rel = np.abs(main + small - exact) / np.abs(exact)
+    assert float(rel.max()) < 2.0 ** -19.5, float(rel.max())
+    # dot products with fp32 accumulation of the two chains (round-to-nearest here; the tensor core truncates, which is why the
+    # kernels keep the small terms out of the main accumulator and add the two once at the end)
+    dot = (main.astype(np.float32).sum(1, dtype=np.float32) + small.astype(np.float32).sum(1, dtype=np.float32)).astype(np.float64)
+    ref = exact.sum(1)
+    bound = (np.abs(a).astype(np.float64) * np.abs(b).astype(np.float64)).sum(1)
+    assert float((np.abs(dot - ref) / bound).max()) < 1e-6
+    # plain tf32 (hi.hi only) misses the 1e-5 parity bar of the fp32 mode by two orders of magnitude
+    assert float((np.abs(main.sum(1) - ref) / bound).max()) > 1e-5
